@@ -1,0 +1,235 @@
+"""TEST INFRASTRUCTURE ONLY -- freezes outputs of the UNMODIFIED reference into tests/golden/*.npz.
+
+Run in the build container (needs /root/reference):   python -m oracle.gen_golden
+The fixtures are committed; tests read only the .npz files, never /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader as rl  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def _sd(model, prefix="sd:"):
+    return {prefix + k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def _train_step_record(ref, model, x, il, tg, tl, texts):
+    """forward -> criterion exactly as base_asr_models.py:78-81, then backward."""
+    model.zero_grad()
+    out, ol = model.forward(x, il)
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    loss.backward()
+    rec = {"out": out, "out_len": ol, "loss": loss}
+    for n, p in model.named_parameters():
+        rec["grad:" + n] = p.grad.clone()
+    rec["decoded"] = np.array(model.ctc_decoder.decode(out, ol))
+    return rec
+
+
+def gen_decoder(ref):
+    D = ref.decoder.GreedyDecoder
+    cases = {}
+    # unit_tests/decoder_test.py:40-42
+    lab = ["_", "A", "B", " "]
+    p = torch.FloatTensor([[0.8, 0.2, 0, 0], [0.6, 0.4, 0, 0]]).unsqueeze(0)
+    cases["unit"] = (lab, p, None)
+    # decoder.py:305-311 (__main__ vectors)
+    lab2 = ["_", "a", "b", " "]
+    cases["main_a"] = (lab2, torch.Tensor([[[0.4, 0.6, 0, 0]]]), None)
+    cases["main_space"] = (lab2, torch.Tensor([[[0.4, 0.1, 0, 0.5]]]), None)
+    cases["main_aba"] = (lab2, torch.Tensor([[[0.0, 0.6, 0.3, 0.1], [0.0, 0.6, 0.3, 0.1], [0.0, 0.3, 0.6, 0.1],
+                                             [0.0, 0.6, 0.3, 0.1]], [[0.4, 0.1, 0, 0.5]] * 4]), [4, 1])
+    # ties, NaN, a _ a, sizes truncation, random
+    cases["ties"] = (lab2, torch.Tensor([[[0.5, 0.5, 0, 0], [0.1, 0.4, 0.4, 0.1], [0, 0, 0.5, 0.5]]]), None)
+    cases["a_blank_a"] = (lab2, torch.Tensor([[[0, 1, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0], [0, 1, 0, 0]]]), None)
+    nan = float("nan")
+    cases["nan"] = (lab2, torch.Tensor([[[0.9, nan, 0.1, 0], [0.2, 0.1, nan, nan], [nan, 0.9, 0, 0], [0, 0, 0, 1]]]), None)
+    g = torch.Generator().manual_seed(3)
+    eng = list(ref.label_sets.labels_map["english_lowercase"])
+    pr = torch.softmax(3 * torch.randn(5, 97, 29, generator=g), -1)
+    pr[:, :, 0] += 0.15
+    cases["random"] = (eng, pr, [97, 50, 1, 0, 96])
+    lpq = torch.round(torch.log_softmax(torch.randn(3, 64, 29, generator=g), -1) * 2) / 2   # many exact ties
+    cases["quantised"] = (eng, lpq, None)
+    out = {}
+    for name, (lab, p, sizes) in cases.items():
+        strings, offsets = D(lab).decode(p, sizes=sizes, return_offsets=True)
+        out[name + ":labels"] = np.array(lab)
+        out[name + ":probs"] = p.numpy()
+        out[name + ":sizes"] = np.array(sizes if sizes is not None else [-1])
+        out[name + ":strings"] = np.array(strings)
+        for i, o in enumerate(offsets):
+            out[name + ":offsets:%d" % i] = o[0].numpy()
+        _, am = torch.max(p, 2)
+        out[name + ":argmax"] = am.numpy()
+    np.savez_compressed(os.path.join(OUT, "decoder.npz"), **out)
+
+
+def gen_conv_block(ref):
+    torch.manual_seed(0)
+    out = {}
+    for tag, args in {"l0": (64, 256, (11,), 2, 0.0, 1), "dil": (32, 48, (5,), 1, -1.0, 2),
+                      "odd": (33, 16, (4,), 2, -1.0, 1)}.items():
+        blk = ref.wav2letter.Conv1dBlock(*args[:4], drop_out_prob=args[4], dilation=args[5])
+        with torch.no_grad():
+            blk.batch_norm.weight.uniform_(0.5, 1.5)
+            blk.batch_norm.bias.uniform_(-0.5, 0.5)
+        x = torch.randn(2, args[0], 61)
+        out.update(_np({tag + ":" + k: v for k, v in _sd(blk, "").items()}))
+        out[tag + ":x"] = x.numpy()
+        blk.train()
+        out[tag + ":y_train"] = blk(x).detach().numpy()
+        out[tag + ":running_mean_after"] = blk.batch_norm.running_mean.numpy().copy()
+        out[tag + ":running_var_after"] = blk.batch_norm.running_var.numpy().copy()
+        blk.eval()
+        out[tag + ":y_eval"] = blk(x).detach().numpy()
+        out[tag + ":pad"] = np.array(blk.paddingAdded.padding if hasattr(blk.paddingAdded, "padding") else (0, 0))
+    np.savez_compressed(os.path.join(OUT, "conv_block.npz"), **out)
+
+
+def gen_w2l(ref):
+    torch.manual_seed(1)
+    cfg = rl.reference_model_cfg("wav2letter", mid_layers=3, dropout=-1)
+    small = [dict(output_size=64, kernel_size=11, stride=2, dilation=1, dropout=-1),
+             dict(output_size=128, kernel_size=13, stride=1, dilation=1, dropout=-1),
+             dict(output_size=64, kernel_size=5, stride=1, dilation=2, dropout=-1)]
+    cfg["layers"] = rl.to_attr(small)
+    model = ref.wav2letter.Wav2Letter(cfg)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 64, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 20), dtype=torch.int32)
+    tl = torch.tensor([20, 12, 7], dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "layers": np.array([[l["output_size"], l["kernel_size"], l["stride"],
+                                                                     l["dilation"]] for l in small])}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update(_sd(model, "sd1:"))                       # running stats after one training forward
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["eval:decoded"] = np.array(model.ctc_decoder.decode(o, ol))
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "w2l_small.npz"), **_np(out))
+
+
+def gen_jasper(ref):
+    torch.manual_seed(2)
+    blocks = [dict(layer_size=64, kernel_size=10, stride=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=64, kernel_size=11, stride=1, residual=True, separable=False, repeat=3),
+              dict(layer_size=128, kernel_size=12, stride=1, residual=True, separable=True, repeat=2),
+              dict(layer_size=128, kernel_size=7, stride=1, dilation=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=64, kernel_size=1, stride=1, residual=False, separable=False, repeat=1)]
+    cfg = rl.reference_model_cfg("jasper", mid_layers=5, dropout=0, jasper_blocks=blocks)
+    model = ref.jasper.Jasper(cfg)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 64, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 20), dtype=torch.int32)
+    tl = torch.tensor([20, 12, 7], dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+        x[n, :, il[n]:] = 0
+    import json
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "blocks_json": np.array(json.dumps(blocks))}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update(_sd(model, "sd1:"))
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "jasper_small.npz"), **_np(out))
+
+
+def gen_ctc(ref):
+    g = torch.Generator().manual_seed(5)
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)    # base_asr_models.py:23
+    out = {}
+    cases = {
+        "ragged": (4, 50, 29, [50, 41, 30, 17], [12, 9, 0, 8]),
+        "infeasible": (3, 6, 5, [6, 2, 4], [3, 2, 4]),       # n=1: T=2,S=2 w/ repeat forced below; n=2: S=T=4 w/ repeats
+        "long": (2, 300, 29, [300, 257], [120, 64]),
+        "single": (1, 1, 4, [1], [1]),
+    }
+    for name, (N, T, C, il, tl) in cases.items():
+        lp = torch.log_softmax(torch.randn(N, T, C, generator=g), -1)
+        S = max(max(tl), 1)
+        tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+        if name == "infeasible":
+            tg[1, :2] = torch.tensor([2, 2])
+            tg[2, :4] = torch.tensor([1, 1, 3, 3])
+        for n in range(N):
+            tg[n, tl[n]:] = 0
+        lp.requires_grad_(True)
+        ilt, tlt = torch.tensor(il, dtype=torch.int32), torch.tensor(tl, dtype=torch.int32)
+        loss = crit(lp.transpose(0, 1), tg, ilt, tlt)
+        loss.backward()
+        nll = torch.nn.functional.ctc_loss(lp.detach().transpose(0, 1), tg, ilt, tlt, blank=0, reduction="none",
+                                           zero_infinity=True)
+        out.update({name + ":lp": lp.detach(), name + ":tg": tg, name + ":il": ilt, name + ":tl": tlt,
+                    name + ":loss": loss.detach(), name + ":grad": lp.grad, name + ":nll": nll})
+    np.savez_compressed(os.path.join(OUT, "ctc.npz"), **_np(out))
+
+
+def gen_novograd(ref):
+    torch.manual_seed(7)
+    import warnings
+    out = {}
+    p = [torch.nn.Parameter(torch.randn(16, 8, 3)), torch.nn.Parameter(torch.randn(16))]
+    out["p0:0"], out["p0:1"] = p[0].detach().clone(), p[1].detach().clone()
+    opt = ref.novograd.Novograd(p, lr=0.01, betas=(0.95, 0.5), weight_decay=1e-3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(3):
+            for i, q in enumerate(p):
+                q.grad = torch.randn_like(q)
+                out["g%d:%d" % (step, i)] = q.grad.clone()
+            opt.step()
+            for i, q in enumerate(p):
+                out["p%d:%d" % (step + 1, i)] = q.detach().clone()
+    np.savez_compressed(os.path.join(OUT, "novograd.npz"), **_np(out))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = rl.load_reference()
+    torch.set_num_threads(1)
+    gen_decoder(ref)
+    gen_conv_block(ref)
+    gen_w2l(ref)
+    gen_jasper(ref)
+    gen_ctc(ref)
+    gen_novograd(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

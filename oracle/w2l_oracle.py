@@ -1,0 +1,407 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the reference hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import this module, and only as the checker / the CPU yard-stick -- never as the thing
+shipped.  The product path (``wav2letter_pytorch_b200``) must not import anything from ``oracle/``.
+
+What is restated (reference file:line given at each function):
+  * Conv1dBlock / Wav2Letter forward      -- wav2letter.py:12-92
+  * MaskedConv1d / JasperBlock / Jasper   -- jasper.py:53-132, 154-419, 422-475
+  * CTC loss (mean, blank 0, zero_inf)    -- base_asr_models.py:23,81 (+ torch.nn.CTCLoss semantics)
+  * GreedyDecoder argmax + collapse       -- decoder.py:89-145
+  * Novograd.step                         -- novograd.py:52-114
+
+The arithmetic of conv / batch-norm / log_softmax in the reference is the installed torch's CPU
+library (the reference calls nn.Conv1d etc. and pins no version), so the oracle calls the same
+``torch.nn.functional`` primitives on CPU tensors, in fp32 or fp64.  CTC and greedy decoding are
+additionally restated from scratch (numpy / python loops) so that they can be checked independently
+of torch.  Parity pinning: ``tests/test_oracle_golden.py`` checks every function here against
+``tests/golden/*.npz``, which ``oracle/gen_golden.py`` produced by running the *unmodified*
+reference modules in the build container (where /root/reference is mounted).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# labels (data/label_sets.py:2-14): blank '_' at 0, then ', a..z, then ' ' at 28
+# --------------------------------------------------------------------------------------------
+ENGLISH_LOWERCASE = ["_", "'"] + [chr(ord("a") + i) for i in range(26)] + [" "]
+
+# --------------------------------------------------------------------------------------------
+# Wav2Letter layer table (configuration/model/wav2letter.yaml:5-104):
+# (output_size, kernel_size, stride, dilation, dropout)
+# --------------------------------------------------------------------------------------------
+W2L_LAYERS = (
+    [(256, 11, 2, 1, 0.2)] + [(256, 11, 1, 1, 0.2)] * 3 + [(384, 13, 1, 1, 0.2)] * 3
+    + [(512, 17, 1, 1, 0.2)] * 3 + [(640, 21, 1, 1, 0.3)] * 3 + [(768, 25, 1, 1, 0.3)] * 3
+    + [(896, 29, 1, 2, 0.4)] * 3 + [(1024, 1, 1, 1, 0.4)]
+)
+
+
+def w2l_layer_specs(mid_layers, input_size=64, n_labels=29, dropout=None):
+    """wav2letter.py:59-71 -- blocks from cfg.layers[:mid_layers] plus the k=1 head (no BN/activation)."""
+    specs, cin = [], input_size
+    for (co, k, s, d, p) in W2L_LAYERS[:mid_layers]:
+        specs.append(dict(cin=cin, cout=co, k=k, stride=s, dilation=d,
+                          dropout=p if dropout is None else dropout, bn=True, act=True))
+        cin = co
+    specs.append(dict(cin=cin, cout=n_labels, k=1, stride=1, dilation=1, dropout=-1.0, bn=False, act=False))
+    return specs
+
+
+def reflect_pad_amounts(cin, k, stride, dilation):
+    """wav2letter.py:24-34.  NB: the rule is computed from the *channel count*, not the time length."""
+    out_rows = (cin + stride - 1) // stride
+    pad = max(0, (out_rows - 1) * stride + (k - 1) * dilation + 1 - cin)
+    return pad // 2, (pad + 1) // 2
+
+
+def conv1d_block_forward(x, sd, prefix, spec, training, dropout_mask=None, update_running=True):
+    """wav2letter.py:40-47: ReflectionPad1d -> Conv1d(bias) -> BatchNorm1d(eps 1e-3, momentum 0.9)
+    -> Dropout -> clamp(0, 20).  ``x`` is [B, Cin, T] (NCW).  ``sd`` maps reference state_dict names to
+    tensors; running stats are updated in place when training (as nn.BatchNorm1d does)."""
+    pl, pr = reflect_pad_amounts(spec["cin"], spec["k"], spec["stride"], spec["dilation"])
+    if pl + pr > 0:
+        x = F.pad(x, (pl, pr), mode="reflect")
+    z = F.conv1d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"], stride=spec["stride"],
+                 dilation=spec["dilation"])
+    if spec["bn"]:
+        rm, rv = sd[prefix + "batch_norm.running_mean"], sd[prefix + "batch_norm.running_var"]
+        if training and not update_running:
+            rm, rv = rm.clone(), rv.clone()
+        z = F.batch_norm(z, rm, rv, sd[prefix + "batch_norm.weight"], sd[prefix + "batch_norm.bias"],
+                         training=training, momentum=0.9, eps=1e-3)
+    if training and spec["dropout"] != -1 and spec["dropout"] > 0:
+        if dropout_mask is not None:           # mask shared with the implementation under test
+            z = z * dropout_mask / (1.0 - spec["dropout"])
+        else:
+            z = F.dropout(z, spec["dropout"], training=True)
+    if spec["act"]:
+        z = torch.clamp(z, min=0, max=20)
+    return z
+
+
+def w2l_forward(x, input_lengths, sd, specs, training, update_running=True, return_logits=False):
+    """wav2letter.py:84-92.  Returns (log_probs [B,T',C], output_lengths)."""
+    for i, spec in enumerate(specs):
+        x = conv1d_block_forward(x, sd, "conv1ds.conv1d_%d." % i, spec, training, update_running=update_running)
+    logits = x.transpose(1, 2)
+    lp = F.log_softmax(logits, dim=-1)
+    scaling = int(np.prod([s["stride"] for s in specs]))
+    out_len = None if input_lengths is None else input_lengths // scaling   # base_asr_models.py:33-39
+    if return_logits:
+        return lp, out_len, logits
+    return lp, out_len
+
+
+def w2l_init_state_dict(specs, seed=0, dtype=torch.float32):
+    """Random init with nn.Conv1d's default scheme (kaiming-uniform a=sqrt(5) => U(-1/sqrt(fan_in), ..))."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for i, s in enumerate(specs):
+        p = "conv1ds.conv1d_%d." % i
+        bound = 1.0 / math.sqrt(s["cin"] * s["k"])
+        sd[p + "conv1.weight"] = ((torch.rand(s["cout"], s["cin"], s["k"], generator=g) * 2 - 1) * bound).to(dtype)
+        sd[p + "conv1.bias"] = ((torch.rand(s["cout"], generator=g) * 2 - 1) * bound).to(dtype)
+        if s["bn"]:
+            sd[p + "batch_norm.weight"] = torch.ones(s["cout"], dtype=dtype)
+            sd[p + "batch_norm.bias"] = torch.zeros(s["cout"], dtype=dtype)
+            sd[p + "batch_norm.running_mean"] = torch.zeros(s["cout"], dtype=dtype)
+            sd[p + "batch_norm.running_var"] = torch.ones(s["cout"], dtype=dtype)
+            sd[p + "batch_norm.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+# Jasper (dense / separable, batch norm, 'add' residual, groups=1 -- what Jasper._build_encoder
+# can reach, jasper.py:436-453)
+# --------------------------------------------------------------------------------------------
+def jasper_kernel_size(k, factor=1.0):
+    """jasper.py:53-58 -- even kernel sizes are bumped to the next odd value."""
+    k = max(int(k * factor), 1)
+    return k + 1 if k % 2 == 0 else k
+
+
+def jasper_same_padding(k, stride, dilation):
+    """jasper.py:61-66."""
+    if stride > 1 and dilation > 1:
+        raise ValueError("Only stride OR dilation may be greater than 1")
+    if dilation > 1:
+        return (dilation * k) // 2 - 1
+    return k // 2
+
+
+def jasper_block_specs(blocks, input_size=64):
+    """``blocks``: list of dicts with the reference's yaml keys (layer_size, kernel_size, stride,
+    dilation, residual, repeat, separable, dropout, conv_mask) -- defaults as jasper.py:440-449."""
+    specs, cin = [], input_size
+    for b in blocks:
+        k = jasper_kernel_size(b["kernel_size"])
+        s, d = b.get("stride", 1), b.get("dilation", 1)
+        specs.append(dict(cin=cin, cout=b["layer_size"], k=k, stride=s, dilation=d,
+                          pad=jasper_same_padding(k, s, d), residual=bool(b["residual"]),
+                          repeat=b.get("repeat", 1), separable=b.get("separable", True),
+                          conv_mask=b.get("conv_mask", True), dropout=b.get("dropout", 0)))
+        cin = b["layer_size"]
+    return specs
+
+
+def masked_conv1d(x, lens, w, stride, pad, dilation, groups, use_mask, bias=None):
+    """jasper.py:114-132 -- zero t >= len, conv, lens' = (lens + 2p - d(k-1) - 1)/s + 1 (true division)."""
+    if use_mask:
+        lens = lens.to(dtype=torch.long)
+        T = x.size(2)
+        mask = torch.arange(T).expand(len(lens), T) >= lens.unsqueeze(1)
+        x = x.masked_fill(mask.unsqueeze(1), 0)
+        lens = (lens + 2 * pad - dilation * (w.shape[2] - 1) - 1) / stride + 1
+    return F.conv1d(x, w, bias, stride=stride, padding=pad, dilation=dilation, groups=groups), lens
+
+
+def _jasper_conv_bn(x, lens, sd, prefix, idx, spec, cin, k, stride, pad, dilation, training, separable):
+    """one _get_conv_bn_layer group (jasper.py:300-368): [depthwise+]conv, BatchNorm1d(eps 1e-3, mom 0.1)."""
+    if separable:
+        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], stride, pad, dilation,
+                                cin, spec["conv_mask"])
+        idx += 1
+        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], 1, 0, 1, 1, spec["conv_mask"])
+        idx += 1
+    else:
+        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], stride, pad, dilation, 1,
+                                spec["conv_mask"])
+        idx += 1
+    p = "%s%d." % (prefix, idx)
+    x = F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                     training=training, momentum=0.1, eps=1e-3)
+    return x, lens, idx + 1
+
+
+def jasper_block_forward(x, lens, sd, bi, spec, training):
+    """JasperBlock.forward, jasper.py:379-419 (non-dense residual, 'add')."""
+    xs, lens_orig = x, lens
+    prefix = "jasper_encoder.%d.mconv." % bi
+    idx, cin, out = 0, spec["cin"], x
+    for r in range(spec["repeat"]):
+        out, lens, idx = _jasper_conv_bn(out, lens, sd, prefix, idx, spec, cin, spec["k"], spec["stride"],
+                                         spec["pad"], spec["dilation"], training, spec["separable"])
+        cin = spec["cout"]
+        if r != spec["repeat"] - 1:
+            out = F.relu(out)
+            if training and spec["dropout"] > 0:
+                out = F.dropout(out, spec["dropout"], True)
+            idx += 2                                     # activation + dropout occupy ModuleList slots
+    if spec["residual"]:
+        rp = "jasper_encoder.%d.res.0." % bi
+        res, _ = masked_conv1d(xs, lens_orig, sd[rp + "0.conv.weight"], 1, 0, 1, 1, spec["conv_mask"])
+        res = F.batch_norm(res, sd[rp + "1.running_mean"], sd[rp + "1.running_var"], sd[rp + "1.weight"],
+                           sd[rp + "1.bias"], training=training, momentum=0.1, eps=1e-3)
+        out = out + res
+    out = F.relu(out)
+    if training and spec["dropout"] > 0:
+        out = F.dropout(out, spec["dropout"], True)
+    return out, lens
+
+
+def jasper_forward(x, input_lengths, sd, specs, training):
+    """Jasper.forward, jasper.py:462-475: encoder, unmasked 1x1 head with bias, transpose,
+    log_softmax when training / softmax in eval (reference quirk, replicated)."""
+    lens = input_lengths
+    for bi, spec in enumerate(specs):
+        x, lens = jasper_block_forward(x, lens, sd, bi, spec, training)
+    out_len = lens.to(dtype=int)
+    z = F.conv1d(x, sd["final_layer.0.weight"], sd["final_layer.0.bias"]).transpose(2, 1)
+    z = F.log_softmax(z, dim=-1) if training else F.softmax(z, dim=-1)
+    assert not (z != z).any()
+    return z, out_len
+
+
+# --------------------------------------------------------------------------------------------
+# CTC
+# --------------------------------------------------------------------------------------------
+def ctc_loss_torch(log_probs_ntc, targets, input_lengths, target_lengths, dtype=torch.float32):
+    """The reference's exact call (base_asr_models.py:23,81): nn.CTCLoss(blank=0, reduction='mean',
+    zero_infinity=True) on ``out.transpose(0,1)`` ([T,N,C] view of the contiguous [N,T,C] tensor).
+    Returns (loss, d loss / d log_probs as [N,T,C])."""
+    lp = log_probs_ntc.detach().to("cpu", dtype).clone().requires_grad_(True)
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)
+    loss = crit(lp.transpose(0, 1), targets.cpu(), input_lengths.cpu(), target_lengths.cpu())
+    (g,) = torch.autograd.grad(loss, lp)
+    return loss.detach(), g
+
+
+def _lse(a, b):
+    if a == -math.inf:
+        return b
+    if b == -math.inf:
+        return a
+    m = max(a, b)
+    return m + math.log(math.exp(a - m) + math.exp(b - m))
+
+
+def ctc_nll_and_grad_numpy(lp, target, T, blank=0):
+    """From-scratch log-space alpha/beta recursion over the blank-extended label lattice for ONE
+    utterance (float64).  ``lp`` [Tmax, C] log-probs, ``target`` 1-D ints (no blanks), ``T`` valid frames.
+    Returns (nll, dnll/dlp [Tmax, C]) with the ATen convention grad = exp(lp) - occupancy/exp(lp)
+    for t < T and 0 beyond (torch CTCLoss applied to a log_softmax output)."""
+    lp = np.asarray(lp, dtype=np.float64)
+    S = len(target)
+    L = 2 * S + 1
+    ext = [blank] * L
+    for i, c in enumerate(target):
+        ext[2 * i + 1] = int(c)
+    NEG = -math.inf
+    grad = np.zeros_like(lp)
+    if T == 0:
+        return (0.0 if S == 0 else math.inf), grad
+    alpha = np.full((T, L), NEG)
+    alpha[0, 0] = lp[0, blank]
+    if L > 1:
+        alpha[0, 1] = lp[0, ext[1]]
+    for t in range(1, T):
+        for s in range(L):
+            a = alpha[t - 1, s]
+            if s >= 1:
+                a = _lse(a, alpha[t - 1, s - 1])
+            if s >= 2 and ext[s] != blank and ext[s] != ext[s - 2]:
+                a = _lse(a, alpha[t - 1, s - 2])
+            alpha[t, s] = a + lp[t, ext[s]] if a != NEG else NEG
+    ll = alpha[T - 1, L - 1]
+    if L > 1:
+        ll = _lse(ll, alpha[T - 1, L - 2])
+    nll = -ll
+    if not math.isfinite(nll):
+        return math.inf, grad
+    beta = np.full((T, L), NEG)
+    beta[T - 1, L - 1] = lp[T - 1, blank]
+    if L > 1:
+        beta[T - 1, L - 2] = lp[T - 1, ext[L - 2]]
+    for t in range(T - 2, -1, -1):
+        for s in range(L):
+            b = beta[t + 1, s]
+            if s + 1 < L:
+                b = _lse(b, beta[t + 1, s + 1])
+            if s + 2 < L and ext[s + 2] != blank and ext[s + 2] != ext[s]:
+                b = _lse(b, beta[t + 1, s + 2])
+            beta[t, s] = b + lp[t, ext[s]] if b != NEG else NEG
+    for t in range(T):
+        occ = np.zeros(lp.shape[1])
+        for s in range(L):
+            ab = alpha[t, s] + beta[t, s]
+            if ab != NEG:
+                occ[ext[s]] += math.exp(ab + nll - lp[t, ext[s]])
+        grad[t] = np.exp(lp[t]) - occ
+    return nll, grad
+
+
+def ctc_loss_numpy(log_probs_ntc, targets, input_lengths, target_lengths, blank=0, zero_infinity=True):
+    """mean reduction of torch.nn.CTCLoss: mean_n(nll_n / max(S_n, 1)); inf -> 0 (+ zero grad)."""
+    lp = np.asarray(log_probs_ntc, dtype=np.float64)
+    N = lp.shape[0]
+    grad = np.zeros_like(lp)
+    total = 0.0
+    nlls = []
+    for n in range(N):
+        S = int(target_lengths[n])
+        nll, g = ctc_nll_and_grad_numpy(lp[n], np.asarray(targets[n][:S]), int(input_lengths[n]), blank)
+        if not math.isfinite(nll):
+            if zero_infinity:
+                nll, g = 0.0, np.zeros_like(g)
+        nlls.append(nll)
+        total += nll / max(S, 1)
+        grad[n] = g / (max(S, 1) * N)
+    return total / N, grad, np.asarray(nlls)
+
+
+# --------------------------------------------------------------------------------------------
+# Greedy decoding (decoder.py:89-145)
+# --------------------------------------------------------------------------------------------
+def greedy_argmax(probs):
+    """decoder.py:136 ``torch.max(probs, 2)``: first index wins ties, NaN counts as the maximum."""
+    p = np.asarray(probs)
+    N, T, C = p.shape
+    out = np.zeros((N, T), dtype=np.int64)
+    for n in range(N):
+        for t in range(T):
+            best, bi = p[n, t, 0], 0
+            for c in range(1, C):
+                v = p[n, t, c]
+                if best != best:           # NaN already holds the maximum
+                    break
+                if v != v or v > best:
+                    best, bi = v, c
+            out[n, t] = bi
+    return out
+
+
+def greedy_collapse(argmax_nt, sizes=None, blank=0):
+    """decoder.py:104-119 with remove_repetitions=True: drop blanks, drop a symbol equal to the *previous
+    frame's raw argmax*.  Returns (tokens list per utterance, frame offsets list per utterance)."""
+    toks, offs = [], []
+    for n in range(len(argmax_nt)):
+        seq = argmax_nt[n]
+        size = int(sizes[n]) if sizes is not None else len(seq)
+        tk, of = [], []
+        for i in range(size):
+            c = int(seq[i])
+            if c != blank and not (i != 0 and c == int(seq[i - 1])):
+                tk.append(c)
+                of.append(i)
+        toks.append(tk)
+        offs.append(of)
+    return toks, offs
+
+
+def greedy_decode(probs, sizes=None, labels=ENGLISH_LOWERCASE, blank=0):
+    """GreedyDecoder.decode (decoder.py:121-145): strings + offsets."""
+    am = greedy_argmax(np.asarray(probs))
+    toks, offs = greedy_collapse(am, sizes, blank)
+    return ["".join(labels[c] for c in tk) for tk in toks], offs
+
+
+# --------------------------------------------------------------------------------------------
+# Novograd (novograd.py:52-114), betas=(0.95, 0) default, no amsgrad
+# --------------------------------------------------------------------------------------------
+def novograd_step(params, grads, state, lr=1e-3, betas=(0.95, 0.0), eps=1e-8, weight_decay=0.0,
+                  grad_averaging=False):
+    """In-place on ``params`` (list of tensors); ``state`` is a list of dicts carried across steps."""
+    b1, b2 = betas
+    for p, g, st in zip(params, grads, state):
+        if not st:
+            st["exp_avg"] = torch.zeros_like(p)
+            st["exp_avg_sq"] = torch.zeros((), dtype=p.dtype)
+        norm = torch.sum(g * g)
+        if st["exp_avg_sq"] == 0:
+            st["exp_avg_sq"] = norm.clone()
+        else:
+            st["exp_avg_sq"] = st["exp_avg_sq"] * b2 + (1 - b2) * norm
+        g = g / (st["exp_avg_sq"].sqrt() + eps)
+        if weight_decay != 0:
+            g = g + weight_decay * p
+        if grad_averaging:
+            g = g * (1 - b1)
+        st["exp_avg"].mul_(b1).add_(g)
+        p.add_(st["exp_avg"], alpha=-lr)
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic batch: the collated-batch layout of data_loader.py:149-158
+# --------------------------------------------------------------------------------------------
+def synthetic_batch(B, seconds, seed=0, n_labels=29, ragged=False, feat=64):
+    g = torch.Generator().manual_seed(seed)
+    T = 1 + 100 * seconds
+    S = 15 * seconds
+    x = torch.randn(B, feat, T, generator=g)
+    targets = torch.randint(1, n_labels, (B, S), generator=g, dtype=torch.int32)
+    if ragged:
+        il = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, dtype=torch.int32)
+        il[0] = T
+        tl = torch.randint(S // 2, S + 1, (B,), generator=g, dtype=torch.int32)
+        for n in range(B):
+            x[n, :, il[n]:] = 0
+            targets[n, tl[n]:] = 0
+    else:
+        il = torch.full((B,), T, dtype=torch.int32)
+        tl = torch.full((B,), S, dtype=torch.int32)
+    return x, il, targets, tl
