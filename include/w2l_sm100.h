@@ -1,0 +1,196 @@
+/* libw2l_sm100 -- C ABI of the B200 (sm_100a) hot path for wav2letter_pytorch.
+ *
+ * The reference (assafmu/wav2letter_pytorch) has no FFI of its own: its hot path is a chain of torch
+ * library calls made from Python.  Each entry point below replaces one of those call sites; the
+ * reference file:line it stands in for is cited at the declaration.  The Python host package
+ * (wav2letter_pytorch_b200/) binds these with ctypes and mirrors the reference's module API.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *     (including workspaces); the library never allocates, frees or synchronises; work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*)
+ *   - return value: 0 = W2L_OK, otherwise an error code; w2l_last_error() gives thread-local text
+ *   - activations are TIME-MAJOR: [B, T, C] with C contiguous ("rows" = frames); bf16 unless stated
+ *   - conv weights are packed [k, Cout_pad, Cin] bf16 (tap-major; each tap is a K-major GEMM operand)
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns W2L_ERR_CUDA
+ */
+#ifndef W2L_SM100_H_
+#define W2L_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2L_OK 0
+#define W2L_ERR_INVALID_ARGUMENT 1
+#define W2L_ERR_CUDA 2
+#define W2L_ERR_UNSUPPORTED 3
+
+#define W2L_ACT_NONE 0
+#define W2L_ACT_RELU 1      /* jasper.py:448  activation=torch.nn.ReLU()            */
+#define W2L_ACT_CLAMP20 2   /* wav2letter.py:46 torch.clamp(output, min=0, max=20) */
+
+#define W2L_PAD_ZERO 0      /* jasper.py:96-105 nn.Conv1d(padding=p)                */
+#define W2L_PAD_REFLECT 1   /* wav2letter.py:28-34 nn.ReflectionPad1d               */
+
+#define W2L_DTYPE_BF16 0
+#define W2L_DTYPE_F32 1
+
+int w2l_version(void);
+const char* w2l_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t w2l_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Greedy CTC decoding.  Replaces GreedyDecoder.decode -> torch.max(probs, 2) + the per-frame Python
+ * loop of process_string (decoder.py:104-119, 121-145).
+ *   scores  [N, T, C] fp32, arbitrary N/T strides (elements), class stride 1
+ *   sizes   [N] int32 or NULL (=> T for every utterance); values are clamped to [0, T]
+ *   argmax  [N, T] int32 out : first maximal index, NaN counts as maximal (torch.max semantics)
+ *   tokens  [N, T] int32 out : kept symbols, compacted to the front of each row
+ *   offsets [N, T] int32 out : frame index of each kept symbol
+ *   counts  [N]    int32 out : number of kept symbols
+ * keep(t) = t < size && a[t] != blank && (t == 0 || a[t] != a[t-1])  (previous frame's RAW argmax).
+ * workspace: w2l_greedy_decode_workspace_bytes(N, T) bytes.
+ */
+size_t w2l_greedy_decode_workspace_bytes(int64_t N, int64_t T);
+int w2l_greedy_decode(const float* scores, int64_t N, int64_t T, int64_t C, int64_t stride_n, int64_t stride_t,
+                      const int32_t* sizes, int32_t blank, int32_t* argmax, int32_t* tokens, int32_t* offsets,
+                      int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC loss + gradient.  Replaces self.criterion = nn.CTCLoss(blank=0, reduction='mean',
+ * zero_infinity=True) and its backward (base_asr_models.py:23, 81, 90).
+ *   x        [N, T, C] fp32 with N/T strides in elements (the reference passes out.transpose(0,1), a
+ *            [T,N,C] view of this very layout).  from_logits=0: x holds log-probabilities and `grad`
+ *            is d nll/d log_probs in the ATen convention (exp(lp) - occupancy).  from_logits=1: x
+ *            holds raw logits, log_softmax is computed on the fly and `grad` is d nll/d logits
+ *            (log_softmax backward fused).
+ *   targets  [N, target_stride] int32, zero padded (data_loader.py:151-158)
+ *   nll      [N] fp32 out: per-utterance negative log likelihood (inf -> 0 when zero_infinity)
+ *   grad     [N, T, C] fp32 contiguous out, multiplied by grad_scale_n:
+ *              reduction_mean=1 -> 1 / (N * max(S_n, 1))   (torch 'mean');  0 -> 1
+ *            rows t >= input_length_n and infeasible utterances get exact zeros.  NULL skips it.
+ *   loss     [1] fp32 out (optional): mean_n(nll_n / max(S_n,1)) if reduction_mean else sum_n nll_n
+ * workspace: w2l_ctc_loss_workspace_bytes(N, T, S_max).
+ */
+size_t w2l_ctc_loss_workspace_bytes(int64_t N, int64_t T, int64_t S_max);
+int w2l_ctc_loss(const float* x, int32_t from_logits, int64_t N, int64_t T, int64_t C, int64_t stride_n,
+                 int64_t stride_t, const int32_t* targets, int64_t target_stride, const int32_t* input_lengths,
+                 const int32_t* target_lengths, int32_t blank, int32_t zero_infinity, int32_t reduction_mean,
+                 float* nll, float* grad, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conv1d as a tcgen05/TMEM implicit GEMM fed by TMA.  Replaces nn.Conv1d forward / backward-data /
+ * backward-weight at wav2letter.py:35-36,42 and jasper.py:96-105,127,433,468 (stride 1; the stride-2
+ * first layer goes through w2l_im2col_ncw first and then runs here with k=1).
+ *
+ * w2l_conv1d_fwd:  y[b, t, co] = bias[co] + sum_j sum_ci x[b, t + x_row_offset + j*dilation, ci] * w[j, co, ci]
+ *   x  [B, x_rows, Cin] bf16 (already padded when x_row_offset = 0; rows outside [0, x_rows) read as 0,
+ *      which is exactly Jasper's zero padding with x_row_offset = -p)
+ *   w  [k, Cout_pad, Cin] bf16, Cout_pad % 16 == 0, Cin % 8 == 0
+ *   y  [B, y_rows, ldy] (bf16 or fp32): rows t in [0, T_out) are written at y row (t + y_row_offset),
+ *      columns [0, Cout)
+ *   epilogue: v = acc + bias;  if scale: v = v*scale[co] + shift[co];  act(v)
+ * w2l_conv1d_dgrad: dx[b, u, ci] = sum_j sum_co dy[b, u + dy_row_offset - j*dilation, co] * w[j, co, ci]
+ *   (same packed weights, read as an MN-major operand; no transposed copy is kept)
+ * w2l_conv1d_wgrad: dw[j, co, ci] (+)= sum_b sum_t dy[b, t, co] * x[b, t + x_row_offset + j*dilation, ci]
+ *   dw [k, Cout, Cin] fp32; accumulate=0 requires dw to be zero-filled by the caller iff the kernel
+ *   reports split-K > 1 through w2l_conv1d_wgrad_splits().
+ */
+typedef struct {
+  int32_t B;            /* utterances                                  */
+  int32_t T_out;        /* output rows per utterance                   */
+  int32_t Cin, Cout;    /* logical channel counts                      */
+  int32_t Cout_pad;     /* rows per tap in the packed weight tensor    */
+  int32_t k, dilation;
+  int32_t x_rows;       /* rows per utterance in the input buffer      */
+  int32_t x_row_offset; /* input row read by tap 0 of output row 0     */
+  int32_t y_rows;       /* rows per utterance in the output buffer     */
+  int32_t y_row_offset;
+  int32_t ldy;          /* output row pitch in elements                */
+  int32_t y_dtype;      /* W2L_DTYPE_*                                 */
+  int32_t act;          /* W2L_ACT_*                                   */
+} w2l_conv_desc;
+
+int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, void* y,
+                   const w2l_conv_desc* d, void* stream);
+int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream);
+int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d);
+int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Memory-bound companions of the conv kernels (all time-major).
+ */
+/* [B, F, T] fp32 NCW (the collated batch, data_loader.py:149-158) -> [B, rows, k*F] bf16 with
+ * out[b, r, j*F + f] = xpad[b, f, r*stride + j*dilation], xpad = x padded by (pad_left, ...) in `pad_mode`.
+ * k=1, stride=1 gives the plain padded time-major copy.  wav2letter.py:41 + the layer-0 unfold. */
+int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                   int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream);
+/* time-major bf16/fp32 [B, T, C] (row pitch ld) -> NCW fp32 [B, C, T] */
+int w2l_tm_to_ncw(const void* x, int32_t x_dtype, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows,
+                  int32_t x_row_offset, int32_t ld, void* stream);
+/* NCW fp32 [B, C, T] -> time-major bf16 [B, T, C] (dense) */
+int w2l_ncw_to_tm(const float* x, void* out, int32_t B, int32_t C, int32_t T, void* stream);
+
+/* per-channel sum / sum of squares over all B*T rows of z [B*T, C] bf16 -> stats[0:C], stats[C:2C]
+ * (fp32, must be zeroed by the caller).  nn.BatchNorm1d training statistics, wav2letter.py:43, jasper.py:363 */
+int w2l_bn_stats(const void* z, int64_t rows, int32_t C, float* stats, void* stream);
+/* stats -> scale/shift (+ saved mean / invstd) and the running-stat update
+ * r = (1-momentum)*r + momentum*batch (unbiased variance), as torch.nn.BatchNorm1d does. */
+int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* gamma, const float* beta,
+                    const float* conv_bias /* nullable: added to the mean for running_mean only when z excludes it */,
+                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                    float* mean, float* invstd, void* stream);
+/* y = act(dropout(z*scale + shift [+ res*res_scale + res_shift])), written into a (possibly halo'd)
+ * buffer: y[b, pad_left + t, c]; reflect halos of pad_left / pad_right rows are filled from the
+ * interior (nn.ReflectionPad1d of the NEXT layer, wav2letter.py:28-34,41); rows t >= lens[b] are zeroed
+ * when lens != NULL (the masked_fill of the consumer MaskedConv1d, jasper.py:116-119).
+ * dropout: keep-mask from Philox(seed, element index), p = drop_p (0 disables). */
+int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
+                   const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
+                   int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream);
+/* Backward of the above + BatchNorm backward, two passes over (dy_padded, z):
+ *   g = fold_reflect(dyp)[b,t,c] * act'(.) * dropmask;  pass 1 reduces sum(g), sum(g*xhat) into
+ *   red[0:C], red[C:2C] (zeroed by caller); pass 2 writes dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)).
+ *   dgamma = red[C:2C], dbeta = red[0:C]. */
+int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
+                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
+                          float* red, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act,
+                          float drop_p, uint64_t seed, const int32_t* lens, void* stream);
+int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
+                         const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
+                         const float* gamma, const float* red, void* dz, void* g_out /* nullable: masked g, bf16 */,
+                         int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
+                         uint64_t seed, const int32_t* lens, void* stream);
+
+/* logits [rows, ld] fp32 -> log_softmax / softmax over the first C columns -> out [rows, C] fp32
+ * (wav2letter.py:87, jasper.py:470-473).  mode 0 = log_softmax, 1 = softmax. */
+int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, void* stream);
+/* d logits = g - exp(lp) * sum_c g  (log_softmax backward), scaled by *gscale (device scalar, nullable),
+ * written as bf16 into [rows, ld_out] with zero padding in columns >= C. */
+int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out,
+                        int64_t rows, int32_t C, int32_t fused_identity, void* stream);
+/* column sums of a bf16 [rows, ld] matrix -> out[C] fp32 (zeroed by the caller): bias gradient */
+int w2l_colsum(const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream);
+/* fp32 -> bf16 cast (packed weight shadow refresh) */
+int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor NovoGrad step.  Replaces the per-parameter Python loop of Novograd.step
+ * (novograd.py:52-114): layer-wise second moment of ||g||^2, normalised gradient, decoupled weight
+ * decay term, first moment, parameter update -- and refreshes the bf16 weight shadow in the same pass.
+ * Arrays of device pointers / sizes live in device memory (n_tensors entries).
+ */
+int w2l_novograd_step(float* const* params, float* const* grads, float* const* exp_avg, float* exp_avg_sq /*[n]*/,
+                      void* const* shadow_bf16 /* nullable entries */, const int64_t* numel, int32_t n_tensors,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t grad_averaging,
+                      float* norms_ws /*[n] scratch*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2L_SM100_H_ */

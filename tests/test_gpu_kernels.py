@@ -1,0 +1,325 @@
+"""Parity of each CUDA kernel (called through the C ABI) against the CPU oracle / plain torch fp32, on a B200."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+from oracle import w2l_oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+@pytest.fixture(scope="module")
+def F():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from wav2letter_pytorch_b200 import functional
+    return functional
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------- decode
+def _check_decode(F, probs, sizes, blank=0):
+    p = torch.as_tensor(probs, dtype=torch.float32)
+    sz = None if sizes is None else torch.as_tensor(sizes, dtype=torch.int32)
+    am, tok, off, cnt = F.greedy_decode(p.cuda(), None if sz is None else sz.cuda(), blank)
+    am_ref = O.greedy_argmax(p.numpy())
+    tok_ref, off_ref = O.greedy_collapse(am_ref, None if sizes is None else list(sizes), blank)
+    assert np.array_equal(am.cpu().numpy(), am_ref)
+    cnt = cnt.cpu().numpy()
+    for n in range(p.shape[0]):
+        assert cnt[n] == len(tok_ref[n])
+        assert tok[n, :cnt[n]].cpu().tolist() == tok_ref[n]
+        assert off[n, :cnt[n]].cpu().tolist() == off_ref[n]
+        assert (tok[n, cnt[n]:] == -1).all()
+
+
+def test_decode_golden(F, golden):
+    g = golden("decoder")
+    for name in sorted({k.split(":")[0] for k in g.files}):
+        sizes = g[name + ":sizes"]
+        _check_decode(F, g[name + ":probs"], None if sizes[0] == -1 else sizes)
+
+
+@pytest.mark.parametrize("N,T,C", [(1, 1, 4), (3, 255, 29), (2, 256, 29), (5, 257, 29), (4, 750, 29), (2, 1031, 32), (3, 300, 5)])
+def test_decode_random(F, N, T, C):
+    g = torch.Generator().manual_seed(N * 1000 + T)
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g) * 2, -1)
+    lp[:, :, 0] += 1.0
+    lp = torch.round(lp * 4) / 4                       # plenty of exact ties and repeats
+    sizes = torch.randint(0, T + 1, (N,), generator=g).tolist()
+    sizes[0] = T
+    _check_decode(F, lp, sizes)
+    _check_decode(F, lp, None)
+    # non-contiguous view [N,T,C] of a [T,N,C] tensor (stride_t != C path)
+    v = lp.transpose(0, 1).contiguous().cuda().transpose(0, 1)
+    am, tok, off, cnt = F.greedy_decode(v, None)
+    assert np.array_equal(am.cpu().numpy(), O.greedy_argmax(lp.numpy()))
+
+
+def test_decode_full_size_properties(F):
+    """BASELINE config 5 upper end (N=512, T=3000): size-independent properties."""
+    g = torch.Generator().manual_seed(0)
+    N, T, C = 512, 3000, 29
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g), -1).cuda()
+    am, tok, off, cnt = F.greedy_decode(lp, None)
+    assert torch.equal(am.long(), lp.argmax(-1))
+    keep = (am != 0)
+    keep[:, 1:] &= am[:, 1:] != am[:, :-1]
+    assert torch.equal(cnt.long(), keep.sum(1))
+    n = 17
+    assert torch.equal(tok[n, :cnt[n]], am[n][keep[n]])
+    assert torch.equal(off[n, :cnt[n]].long(), torch.nonzero(keep[n]).flatten())
+    # idempotence: decoding a one-hot rendering of the collapsed path gives the same tokens
+    o1 = off[n, :cnt[n]].long()
+    assert (o1[1:] > o1[:-1]).all()
+
+
+# ------------------------------------------------------------------------------------------- CTC
+def _check_ctc(F, lp, tg, il, tl, from_logits=False, loss_tol=1e-4, grad_tol=2e-3):
+    lp = torch.as_tensor(lp, dtype=torch.float32)
+    tg, il, tl = (torch.as_tensor(v, dtype=torch.int32) for v in (tg, il, tl))
+    ref_in = torch.log_softmax(lp.double(), -1) if from_logits else lp.double()
+    loss_ref, grad_ref = O.ctc_loss_torch(ref_in, tg, il, tl, dtype=torch.float64)
+    if from_logits:   # chain through log_softmax in fp64
+        x = lp.double().clone().requires_grad_(True)
+        l = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(torch.log_softmax(x, -1).transpose(0, 1), tg, il, tl)
+        (grad_ref,) = torch.autograd.grad(l, x)
+    loss, nll, grad = F.ctc_loss_raw(lp.cuda(), tg.cuda(), il.cuda(), tl.cuda(), from_logits=from_logits)
+    assert abs(loss.item() - loss_ref.item()) <= loss_tol * max(1.0, abs(loss_ref.item()))      # CTC loss within 1e-4 relative
+    gmax = grad_ref.abs().max().item() + 1e-12
+    err = (grad.cpu().double() - grad_ref).abs().max().item()
+    assert err <= grad_tol * gmax, (err, gmax)
+    for n in range(lp.shape[0]):
+        assert (grad[n, int(il[n]):] == 0).all()
+    return nll
+
+
+@pytest.mark.parametrize("name", ["ragged", "infeasible", "long", "single"])
+def test_ctc_golden(F, golden, name):
+    g = golden("ctc")
+    nll = _check_ctc(F, g[name + ":lp"], g[name + ":tg"], g[name + ":il"], g[name + ":tl"])
+    np.testing.assert_allclose(nll.cpu().numpy(), g[name + ":nll"], rtol=1e-4, atol=1e-5)
+    # vs the reference's own numbers (fp32 torch through nn.CTCLoss)
+    lp = torch.from_numpy(g[name + ":lp"]).cuda()
+    _, _, grad = F.ctc_loss_raw(lp, torch.from_numpy(g[name + ":tg"]).cuda(), torch.from_numpy(g[name + ":il"]).cuda(),
+                                torch.from_numpy(g[name + ":tl"]).cuda())
+    gref = g[name + ":grad"]
+    assert np.abs(grad.cpu().numpy() - gref).max() <= 2e-3 * np.abs(gref).max() + 1e-7
+
+
+@pytest.mark.parametrize("N,T,S,C", [(8, 500, 150, 29), (64, 750, 225, 29), (4, 200, 50, 29), (3, 1000, 300, 29), (2, 1300, 600, 29),
+                                     (5, 64, 10, 5), (2, 40, 1, 29)])
+@pytest.mark.parametrize("from_logits", [False, True])
+def test_ctc_random(F, N, T, S, C, from_logits):
+    g = torch.Generator().manual_seed(T + S)
+    x = torch.randn(N, T, C, generator=g) * 1.5
+    lp = x if from_logits else torch.log_softmax(x, -1)
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    tg[:, 1::3] = tg[:, 0::3][:, : tg[:, 1::3].shape[1]]         # force repeated labels
+    il = torch.randint(max(1, T // 2), T + 1, (N,), generator=g, dtype=torch.int32)
+    tl = torch.randint(0, S + 1, (N,), generator=g, dtype=torch.int32)
+    il[0], tl[0] = T, S
+    for n in range(N):
+        tg[n, tl[n]:] = 0
+    _check_ctc(F, lp, tg, il, tl, from_logits=from_logits)
+
+
+def test_ctc_transposed_view(F):
+    """the reference passes out.transpose(0,1): a [T,N,C] view of the contiguous [N,T,C] tensor."""
+    g = torch.Generator().manual_seed(9)
+    N, T, C, S = 6, 120, 29, 30
+    lp = torch.log_softmax(torch.randn(T, N, C, generator=g), -1)          # genuinely [T,N,C]-contiguous
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    il = torch.full((N,), T, dtype=torch.int32)
+    tl = torch.full((N,), S, dtype=torch.int32)
+    loss, nll, grad = F.ctc_loss_raw(lp.cuda().transpose(0, 1), tg.cuda(), il.cuda(), tl.cuda())
+    loss_ref, grad_ref = O.ctc_loss_torch(lp.transpose(0, 1).contiguous(), tg, il, tl, dtype=torch.float64)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    assert (grad.cpu().double() - grad_ref).abs().max() <= 2e-3 * grad_ref.abs().max()
+
+
+def test_ctc_full_size_properties(F):
+    """N=512, T=3000, S=600: per-frame gradient rows sum to ~0 (softmax minus occupancies), loss finite & positive,
+    and equals the loss of a 16-utterance slice computed by the oracle."""
+    g = torch.Generator().manual_seed(1)
+    N, T, S, C = 512, 3000, 600, 29
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g), -1)
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    il = torch.full((N,), T, dtype=torch.int32)
+    tl = torch.full((N,), S, dtype=torch.int32)
+    loss, nll, grad = F.ctc_loss_raw(lp.cuda(), tg.cuda(), il.cuda(), tl.cuda())
+    assert torch.isfinite(nll).all() and (nll > 0).all()
+    assert grad.sum(-1).abs().max().item() < 1e-6
+    ref = TF.ctc_loss(lp[:4].double().transpose(0, 1), tg[:4], il[:4], tl[:4], reduction="none")
+    np.testing.assert_allclose(nll[:4].cpu().numpy(), ref.numpy(), rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------- conv (tcgen05)
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _pack_w(w, cout_pad):
+    """[Co, Ci, k] fp32 -> packed [k, Co_pad, Ci] bf16 (zero rows in the pad)."""
+    co, ci, k = w.shape
+    p = torch.zeros(k, cout_pad, ci, dtype=torch.bfloat16)
+    p[:, :co] = w.permute(2, 0, 1).to(torch.bfloat16)
+    return p
+
+
+CONV_CASES = [
+    # B, T, Cin, Cout, k, d, pad(left,right: rows of zero padding)
+    (2, 300, 64, 256, 1, 1, (0, 0)),
+    (3, 200, 128, 224, 5, 1, (2, 2)),
+    (2, 131, 64, 160, 11, 1, (5, 5)),
+    (2, 260, 192, 29, 1, 1, (0, 0)),
+    (2, 150, 64, 96, 7, 2, (6, 6)),
+    (1, 128, 704, 256, 1, 1, (0, 0)),
+    (2, 97, 256, 384, 3, 1, (1, 1)),
+]
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,k,d,pad", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(F, B, T, Cin, Cout, k, d, pad):
+    g = torch.Generator().manual_seed(B * T + Cin + k)
+    pl, pr = pad
+    x = _bf(torch.randn(B, T, Cin, generator=g))                 # time-major, UNpadded: zero padding via TMA OOB fill
+    w = _bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    bias = torch.randn(Cout, generator=g)
+    T_out = T + pl + pr - d * (k - 1)
+    cout_pad = max(64, (Cout + 15) // 16 * 16)
+    ldy = (Cout + 7) // 8 * 8
+    # ---- reference: plain torch fp32 on the same bf16-rounded operands
+    xr = x.transpose(1, 2).clone().requires_grad_(True)          # NCW
+    wr = w.clone().requires_grad_(True)
+    y_ref = TF.conv1d(TF.pad(xr, (pl, pr)), wr, bias, dilation=d)
+    dy = _bf(torch.randn(B, Cout, T_out, generator=g))
+    y_ref.backward(dy)
+    # ---- forward
+    xc, wc = x.to(torch.bfloat16).cuda(), _pack_w(w, cout_pad).cuda()
+    desc = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, ldy, F.DT_F32, F.ACT_NONE)
+    y = torch.zeros(B, T_out, ldy, dtype=torch.float32, device="cuda")
+    F.conv1d_fwd(xc, wc, desc, y, bias=bias.cuda())
+    got = y[:, :, :Cout].cpu()
+    want = y_ref.detach().transpose(1, 2)
+    assert rel_l2(got, want) < 2e-5, rel_l2(got, want)           # fp32 accumulate of identical bf16 operands
+    # bf16 output + fused scale/shift + clamp epilogue
+    desc2 = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out + 3, 2, ldy, F.DT_BF16, F.ACT_CLAMP20)
+    y2 = torch.full((B, T_out + 3, ldy), 7.0, dtype=torch.bfloat16, device="cuda")
+    sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    F.conv1d_fwd(xc, wc, desc2, y2, bias=bias.cuda(), scale=sc.cuda(), shift=sh.cuda())
+    want2 = torch.clamp(want * sc + sh, 0, 20)
+    assert rel_l2(y2[:, 2:2 + T_out, :Cout].float().cpu(), want2) < 6e-3
+    assert (y2[:, :2] == 7.0).all() and (y2[:, 2 + T_out:] == 7.0).all()      # rows outside [off, off+T_out) untouched
+    # ---- dgrad
+    dyc = torch.zeros(B, T_out, cout_pad, dtype=torch.bfloat16, device="cuda")
+    dyc[:, :, :Cout] = dy.transpose(1, 2).to(torch.bfloat16).cuda()
+    desc3 = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, cout_pad)
+    dx = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
+    F.conv1d_dgrad(dyc, wc, desc3, dx)
+    assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
+    # ---- wgrad
+    dw = torch.full((k, Cout, Cin), 3.0, dtype=torch.float32, device="cuda")
+    F.conv1d_wgrad(dyc, xc, desc3, dw)
+    assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
+
+
+def test_conv_full_size_layer(F):
+    """one config-2-sized layer (B=64, T'=750, 896->896, k=29, d=2): linearity + spot-check vs torch fp32 on a slice."""
+    g = torch.Generator().manual_seed(3)
+    B, T, C, k, d = 64, 750, 896, 29, 2
+    pad = (k - 1) * d // 2
+    x = torch.randn(B, T, C, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(C, C, k, generator=g) / (C * k) ** 0.5).to(torch.bfloat16)
+    wc = w.permute(2, 0, 1).contiguous().cuda()
+    desc = F.make_desc(B, T, C, C, C, k, d, T, -pad, T, 0, C, F.DT_F32, F.ACT_NONE)
+    y = torch.empty(B, T, C, dtype=torch.float32, device="cuda")
+    F.conv1d_fwd(x, wc, desc, y)
+    ref = TF.conv1d(x[5:6].float().cpu().transpose(1, 2), w.float(), padding=pad, dilation=d).transpose(1, 2)
+    assert rel_l2(y[5:6].cpu(), ref) < 2e-5
+    y2 = torch.empty_like(y)
+    F.conv1d_fwd((x.float() * 2).to(torch.bfloat16), wc, desc, y2)           # exact in bf16: linearity
+    assert rel_l2(y2, 2 * y) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- elementwise
+def test_im2col_and_transposes(F):
+    g = torch.Generator().manual_seed(4)
+    B, Fdim, T = 3, 64, 201
+    x = torch.randn(B, Fdim, T, generator=g)
+    pl, pr = O.reflect_pad_amounts(64, 11, 2, 1)
+    rows = (T + pl + pr - 11) // 2 + 1
+    got = F.im2col_ncw(x.cuda(), rows, 11, 2, 1, pl, F.PAD_REFLECT).float().cpu()
+    xp = TF.pad(x, (pl, pr), mode="reflect")
+    want = xp.unfold(2, 11, 2).permute(0, 2, 3, 1).reshape(B, rows, 11 * Fdim)      # [B, rows, j*F + f]
+    assert torch.equal(got, _bf(want))
+    # padded time-major copy with zero pad + length mask
+    lens = torch.tensor([201, 100, 7], dtype=torch.int32)
+    got = F.im2col_ncw(x.cuda(), T + 4, 1, 1, 1, 2, F.PAD_ZERO, lens.cuda()).float().cpu()
+    want = TF.pad(x * (torch.arange(T)[None, None] < lens[:, None, None]), (2, 2)).transpose(1, 2)
+    assert torch.equal(got, _bf(want))
+    back = F.tm_to_ncw(got.to(torch.bfloat16).cuda(), T, Fdim, x_row_offset=2).cpu()
+    assert torch.equal(back, _bf(want[:, 2:2 + T]).transpose(1, 2))
+
+
+@pytest.mark.parametrize("act,drop", [(2, 0.0), (1, 0.0), (2, 0.25)])
+def test_bn_act_forward_backward(F, act, drop):
+    g = torch.Generator().manual_seed(5)
+    B, T, C, pl, pr = 3, 90, 264, 4, 5
+    z = _bf(torch.randn(B, T, C, generator=g) * 2 + 0.5)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    zc = z.to(torch.bfloat16).cuda()
+    stats = F.bn_stats(zc, C)
+    np.testing.assert_allclose(stats[:C].cpu().numpy(), z.sum((0, 1)).numpy(), rtol=1e-4, atol=1e-2)
+    rmc, rvc = rm.cuda(), rv.cuda()
+    fin = F.bn_finalize(stats, B * T, C, gamma.cuda(), beta.cuda(), None, 1e-3, 0.9, rmc, rvc)
+    scale, shift, mean, invstd = fin[0], fin[1], fin[2], fin[3]
+    # torch reference (channel-first)
+    zr = z.transpose(1, 2).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    bn = TF.batch_norm(zr, rm, rv, gr, br, training=True, momentum=0.9, eps=1e-3)
+    np.testing.assert_allclose(rmc.cpu().numpy(), rm.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rvc.cpu().numpy(), rv.numpy(), rtol=1e-4, atol=1e-5)
+    seed = 1234
+    if drop > 0:   # export the kernel's own keep-mask: z=0, scale=0, shift=1, no act
+        ones = F.bn_act_pad(torch.zeros_like(zc), torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"), B, T, C, 0, 0, 0, drop, seed)
+        mult = ones.float().cpu().transpose(1, 2)
+        keep = (mult > 0).float().mean().item()
+        assert abs(keep - (1 - drop)) < 0.02
+        np.testing.assert_allclose(mult[mult > 0].numpy(), 1 / (1 - drop), rtol=1e-2)
+        bn = bn * mult
+    y_ref = torch.clamp(bn, 0, 20) if act == 2 else torch.relu(bn)
+    yp_ref = TF.pad(y_ref, (pl, pr), mode="reflect")
+    yp = F.bn_act_pad(zc, scale, shift, B, T, C, pl, pr, act, drop, seed)
+    assert rel_l2(yp.float().cpu(), yp_ref.detach().transpose(1, 2)) < 4e-3
+    dyp = _bf(torch.randn(B, C, T + pl + pr, generator=g))
+    yp_ref.backward(dyp)
+    dz, red, _ = F.bn_act_bwd(dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda(), zc, scale, shift, mean, invstd, gamma.cuda(),
+                              B, T, C, pl, pr, act, drop, seed)
+    assert rel_l2(dz.float().cpu(), zr.grad.transpose(1, 2)) < 1e-2
+    assert rel_l2(red[:C].cpu(), br.grad) < 5e-3 and rel_l2(red[C:].cpu(), gr.grad) < 5e-3
+
+
+def test_log_softmax_and_colsum(F):
+    g = torch.Generator().manual_seed(6)
+    logits = torch.randn(4, 75, 32, generator=g) * 3
+    lp = F.log_softmax(logits.cuda(), 29)
+    assert rel_l2(lp.cpu(), torch.log_softmax(logits[..., :29], -1)) < 1e-6
+    sm = F.log_softmax(logits.cuda(), 29, mode=1)
+    assert rel_l2(sm.cpu(), torch.softmax(logits[..., :29], -1)) < 1e-6
+    gr = torch.randn(4, 75, 29, generator=g)
+    x = logits[..., :29].clone().requires_grad_(True)
+    torch.log_softmax(x, -1).backward(gr)
+    dl = F.log_softmax_bwd(gr.cuda(), lp, 64)
+    assert rel_l2(dl[..., :29].float().cpu(), x.grad) < 5e-3 and (dl[..., 29:] == 0).all()
+    m = _bf(torch.randn(1000, 64, generator=g))
+    cs = F.colsum(m.to(torch.bfloat16).cuda(), 29)
+    np.testing.assert_allclose(cs.cpu().numpy(), m[:, :29].sum(0).numpy(), rtol=1e-4, atol=1e-3)
+    w = torch.randn(1001, generator=g)
+    assert torch.equal(F.cast_bf16(w.cuda()).cpu(), w.to(torch.bfloat16))

@@ -1,0 +1,131 @@
+"""ctypes binding of libw2l_sm100.so (C ABI declared in include/w2l_sm100.h) + the in-tree nvcc build.
+
+There is deliberately NO CPU fallback here: if the shared library is missing or a call fails the caller
+gets a RuntimeError carrying ``w2l_last_error()``.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libw2l_sm100.so")
+SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu"]
+_lock = threading.Lock()
+_lib = None
+
+
+def _needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "w2l_sm100.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into an in-tree shared library (nvcc cross-compiles without a GPU)."""
+    if not force and not _needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    builddir = os.path.join(_HERE, "build")
+    os.makedirs(builddir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(builddir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        srcp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
+                os.path.getmtime(srcp), os.path.getmtime(os.path.join(CSRC, "common.cuh")),
+                os.path.getmtime(os.path.join(os.path.dirname(_HERE), "include", "w2l_sm100.h"))):
+            continue
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+               "-c", srcp, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode()))
+        if verbose and out:
+            print(out.decode())
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout.decode()))
+    return LIB_PATH
+
+
+c_i32, c_i64, c_f32, c_u64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64
+c_ptr, c_size = ctypes.c_void_p, ctypes.c_size_t
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of w2l_conv_desc."""
+    _fields_ = [(n, c_i32) for n in ("B", "T_out", "Cin", "Cout", "Cout_pad", "k", "dilation", "x_rows", "x_row_offset",
+                                     "y_rows", "y_row_offset", "ldy", "y_dtype", "act")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/w2l_sm100.h appears here
+SIGNATURES = {
+    "w2l_version": (c_i32, []),
+    "w2l_last_error": (ctypes.c_char_p, []),
+    "w2l_launch_count": (c_i64, []),
+    "w2l_greedy_decode_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "w2l_greedy_decode": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_size, c_ptr]),
+    "w2l_ctc_loss_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "w2l_ctc_loss": (c_i32, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_i32, c_i32,
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "w2l_conv1d_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_conv1d_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_conv1d_wgrad_splits": (c_i32, [ctypes.POINTER(ConvDesc)]),
+    "w2l_conv1d_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_im2col_ncw": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "w2l_tm_to_ncw": (c_i32, [c_ptr, c_i32, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_ncw_to_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_bn_stats": (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
+    "w2l_bn_finalize": (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                c_ptr]),
+    "w2l_bn_act_pad": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32,
+                               c_u64, c_ptr, c_ptr]),
+    "w2l_bn_act_bwd_reduce": (c_i32, [c_ptr] * 10 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr]),
+    "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 13 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr]),
+    "w2l_log_softmax": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr]),
+    "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
+    "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "w2l_cast_bf16": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
+    "w2l_novograd_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_ptr,
+                                  c_ptr]),
+}
+
+
+def load():
+    """Returns the loaded library (building it first if the .so is missing)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                build()
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class W2LError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().w2l_last_error().decode(errors="replace")
+        raise W2LError("libw2l_sm100 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(load().w2l_launch_count())

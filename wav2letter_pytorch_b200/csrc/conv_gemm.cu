@@ -1,0 +1,523 @@
+// Conv1d forward / backward-data / backward-weight as tcgen05 implicit GEMMs (sm_100a).
+// Replaces nn.Conv1d fwd+bwd at wav2letter.py:35-36,42 and jasper.py:96-105,127,433,468.
+//
+// One persistent, warp-specialised kernel template (192 threads, 1 CTA per SM):
+//   warp 0      TMA producer   : cp.async.bulk.tensor (3-D tiled maps, 128B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32) into one of
+//                                two 256-column TMEM accumulators; tcgen05.commit releases smem stages / signals
+//                                the epilogue
+//   warps 2..5  epilogue       : tcgen05.ld the finished accumulator (overlapping the next tile's mainloop),
+//                                fused bias / BatchNorm-fold / ReLU-clamp, bf16 or fp32 stores (or fp32 atomics
+//                                for split-K weight gradients)
+// The convolution is never unfolded in memory: a K-step is (tap j, 64-channel chunk); tap j just shifts the row
+// coordinate of the activation tile by j*dilation, and rows outside the tensor are zero-filled by TMA (which
+// is Jasper's zero padding; Wav2Letter's reflection halo is materialised by the producer of the activation).
+//   FWD   : D[t, co]  = sum_{j,ci} X[b, t+off+j*d, ci] * W[j, co, ci]      A = X  (K-major)   B = W[j] (K-major)
+//   DGRAD : D[u, ci]  = sum_{j,co} dY[b, u-off-j*d, co] * W[j, co, ci]     A = dY (K-major)   B = W[j] (MN-major)
+//   WGRAD : D[co, ci] = sum_{b,t}  dY[b, t, co] * X[b, t+off+j*d, ci]      A = dY (MN-major)  B = X    (MN-major)
+#include <cstring>
+
+#include "common.cuh"
+
+namespace w2l {
+
+enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+constexpr int kStages = 4;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                     // bf16 elements per K-step = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kBBytesMax = 256 * kBlockK * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kAccCols = 256;
+constexpr int kGemmThreads = 192;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmParams {
+  CUtensorMap tmA, tmB;
+  int32_t B;            // utterances
+  int32_t m_tiles;      // tiles along M per utterance (fwd/dgrad) or along Cout (wgrad)
+  int32_t n_tiles;
+  int32_t BN;
+  int32_t k, dil;
+  int32_t kc_steps;     // 64-wide chunks of the contraction channels (fwd/dgrad) or of T_out (wgrad)
+  int32_t a_row_off;    // fwd/dgrad: row coordinate of tap 0 for output row 0
+  int32_t a_tap_step;   // +dil (fwd) / -dil (dgrad)
+  int32_t b_row_off;    // wgrad: x row for (t=0, tap 0)
+  int32_t M_valid;      // rows to store per utterance (fwd/dgrad) / Cout (wgrad)
+  int32_t N_valid;      // columns to store
+  int32_t num_tiles;
+  // epilogue
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int32_t act;
+  int32_t y_dtype;
+  void* y;
+  int64_t y_batch_stride;   // elements
+  int32_t y_row_off;
+  int32_t ldy;
+  // wgrad
+  int32_t splits, b_per_split;
+  int64_t dw_tap_stride;    // Cout*Cin
+};
+
+struct TileCoord {
+  int m0, n0, b0, b1, j;
+};
+
+template <int MODE>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord c;
+  if (MODE == MODE_WGRAD) {
+    int s = tile % p.splits;
+    tile /= p.splits;
+    int mt = tile % p.m_tiles;
+    tile /= p.m_tiles;
+    int nt = tile % p.n_tiles;
+    c.j = tile / p.n_tiles;
+    c.m0 = mt * kBlockM;
+    c.n0 = nt * p.BN;
+    c.b0 = s * p.b_per_split;
+    c.b1 = min(p.B, c.b0 + p.b_per_split);
+  } else {
+    int mt = tile % p.m_tiles;
+    tile /= p.m_tiles;
+    int b = tile % p.B;
+    int nt = tile / p.B;
+    c.m0 = mt * kBlockM;
+    c.n0 = nt * p.BN;
+    c.b0 = b;
+    c.b1 = b + 1;
+    c.j = 0;
+  }
+  return c;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                  // [kStages]
+  uint64_t* empty_bar = bars + kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool kAMN = (MODE == MODE_WGRAD);
+  constexpr bool kBMN = (MODE != MODE_FWD);
+  const int b_chunks = (p.BN + 63) >> 6;
+  const uint32_t stage_tx = kABytes + (kBMN ? (uint32_t)b_chunks * 8192u : (uint32_t)p.BN * 128u);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * kAccCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ksteps_per_b = (MODE == MODE_WGRAD) ? p.kc_steps : p.k * p.kc_steps;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<MODE>(p, tile);
+        for (int b = tc.b0; b < tc.b1; ++b) {
+          for (int ks = 0; ks < ksteps_per_b; ++ks) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], stage_tx);
+            uint8_t* sa = smem + stage * kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            if (MODE == MODE_WGRAD) {
+              const int t0 = ks * kBlockK;
+              tma_load_3d(sa, &p.tmA, &full_bar[stage], tc.m0, t0, b);
+              tma_load_3d(sa + 8192, &p.tmA, &full_bar[stage], tc.m0 + 64, t0, b);
+              const int xr = t0 + p.b_row_off + tc.j * p.dil;
+              for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], tc.n0 + c * 64, xr, b);
+            } else {
+              const int j = ks / p.kc_steps, kc = ks - j * p.kc_steps;
+              tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * kBlockK, tc.m0 + p.a_row_off + j * p.a_tap_step, b);
+              if (MODE == MODE_FWD) {
+                tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, tc.n0, j);
+              } else {
+                for (int c = 0; c < b_chunks; ++c)
+                  tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], tc.n0 + c * 64, kc * kBlockK, j);
+              }
+            }
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, kAMN, kBMN);
+      constexpr uint32_t a_kstep = kAMN ? 2048u : 32u;   // bytes per UMMA_K (16 elements of K)
+      constexpr uint32_t b_kstep = kBMN ? 2048u : 32u;
+      constexpr uint32_t a_lbo = kAMN ? 8192u : 16u;
+      constexpr uint32_t b_lbo = kBMN ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile<MODE>(p, tile);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        uint32_t accumulate = 0;
+        for (int b = tc.b0; b < tc.b1; ++b) {
+          for (int ks = 0; ks < ksteps_per_b; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              const uint64_t adesc = make_smem_desc(a_addr + kk * a_kstep, a_lbo, 1024u);
+              const uint64_t bdesc = make_smem_desc(b_addr + kk * b_kstep, b_lbo, 1024u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5)
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile<MODE>(p, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
+      const int m = tc.m0 + row;
+      const bool row_ok = m < p.M_valid;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        const int nbase = tc.n0 + c0;
+        if (MODE == MODE_WGRAD) {
+          if (row_ok) {
+            float* dst = reinterpret_cast<float*>(p.y) + (int64_t)tc.j * p.dw_tap_stride + (int64_t)m * p.ldy + nbase;
+            if (p.splits > 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < p.BN && nbase + i < p.N_valid) atomicAdd(dst + i, __uint_as_float(r[i]));
+            } else if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __uint_as_float(r[i]);
+            }
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]);
+            const int n = nbase + i;
+            if (MODE == MODE_FWD && n < p.N_valid) {
+              if (p.bias) x += __ldg(p.bias + n);
+              if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+              if (p.act == W2L_ACT_RELU) x = fmaxf(x, 0.f);
+              else if (p.act == W2L_ACT_CLAMP20) x = fminf(fmaxf(x, 0.f), 20.f);
+            }
+            v[i] = x;
+          }
+          if (row_ok) {
+            const int64_t off = (int64_t)tc.b0 * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
+            const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
+            if (p.y_dtype == W2L_DTYPE_BF16) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + off;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                  uint4 q;
+                  q.x = pack_bf16x2(v[i], v[i + 1]);
+                  q.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                  q.z = pack_bf16x2(v[i + 4], v[i + 5]);
+                  q.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                  *reinterpret_cast<uint4*>(dst + i) = q;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __float2bfloat16_rn(v[i]);
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(p.y) + off;
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = v[i];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kAccCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int pick_bn(int n_pad16) {
+  // largest multiple of 16 (<= 256) dividing the padded N extent
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (n_pad16 % bn == 0) return bn;
+  return 16;
+}
+
+template <int MODE>
+static int launch_gemm(const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    configured = true;
+  }
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (grid < 1) return W2L_OK;
+  conv_gemm_kernel<MODE><<<grid, kGemmThreads, kGemmSmem, st>>>(p);
+  return after_launch(MODE == MODE_FWD ? "conv_gemm_kernel<fwd>" : MODE == MODE_DGRAD ? "conv_gemm_kernel<dgrad>" : "conv_gemm_kernel<wgrad>");
+}
+
+static int check_desc(const w2l_conv_desc* d, const char* who) {
+  W2L_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  W2L_REQUIRE(d->B >= 1 && d->T_out >= 1 && d->k >= 1 && d->dilation >= 1, "%s: bad B/T_out/k/dilation", who);
+  W2L_REQUIRE(d->Cin >= 64 && d->Cin % 8 == 0, "%s: Cin=%d must be >= 64 and a multiple of 8", who, d->Cin);
+  W2L_REQUIRE(d->Cout >= 1 && d->Cout_pad >= d->Cout && d->Cout_pad % 16 == 0, "%s: Cout=%d Cout_pad=%d (pad must be a multiple of 16)",
+              who, d->Cout, d->Cout_pad);
+  W2L_REQUIRE(d->x_rows >= 1 && d->y_rows >= d->T_out + d->y_row_offset && d->y_row_offset >= 0, "%s: bad row geometry", who);
+  W2L_REQUIRE(d->ldy % 8 == 0, "%s: ldy=%d must be a multiple of 8", who, d->ldy);
+  return W2L_OK;
+}
+
+static int wgrad_splits(const w2l_conv_desc* d, int* bn_out) {
+  const int n_pad = (d->Cin + 15) / 16 * 16;
+  const int bn = pick_bn(n_pad);
+  if (bn_out) *bn_out = bn;
+  const int64_t tiles0 = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * (n_pad / bn);
+  const int sms = num_sms();
+  int best = 1;
+  double best_eff = 0.0;
+  const int max_s = d->B < 32 ? d->B : 32;
+  for (int s = 1; s <= max_s; ++s) {
+    const int64_t tiles = tiles0 * s;
+    const int64_t waves = (tiles + sms - 1) / sms;
+    // each split re-walks ceil(B/s) utterances; efficiency = useful work / (waves * machine)
+    const int per = (d->B + s - 1) / s;
+    const double eff = (double)tiles0 * d->B / ((double)waves * sms * per);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  const int per = (d->B + best - 1) / best;   // utterances per split; drop empty trailing splits
+  return (d->B + per - 1) / per;
+}
+
+}  // namespace w2l
+
+extern "C" {
+
+int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, void* y,
+                   const w2l_conv_desc* d, void* stream) {
+  using namespace w2l;
+  int rc = check_desc(d, "conv1d_fwd");
+  if (rc) return rc;
+  W2L_REQUIRE(x && w && y, "conv1d_fwd: null pointer");
+  W2L_REQUIRE((scale == nullptr) == (shift == nullptr), "conv1d_fwd: scale and shift must be given together");
+  W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_fwd: ldy < Cout");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
+    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, x, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.BN = pick_bn(d->Cout_pad);
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {kBlockK, (uint32_t)p.BN, 1};
+    rc = make_tensor_map(&p.tmB, w, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.B = d->B;
+  p.m_tiles = (d->T_out + kBlockM - 1) / kBlockM;
+  p.n_tiles = d->Cout_pad / p.BN;
+  p.k = d->k;
+  p.dil = d->dilation;
+  p.kc_steps = (d->Cin + kBlockK - 1) / kBlockK;
+  p.a_row_off = d->x_row_offset;
+  p.a_tap_step = d->dilation;
+  p.M_valid = d->T_out;
+  p.N_valid = d->Cout;
+  p.num_tiles = p.m_tiles * p.n_tiles * p.B;
+  p.bias = bias;
+  p.scale = scale;
+  p.shift = shift;
+  p.act = d->act;
+  p.y_dtype = d->y_dtype;
+  p.y = y;
+  p.y_batch_stride = (int64_t)d->y_rows * d->ldy;
+  p.y_row_off = d->y_row_offset;
+  p.ldy = d->ldy;
+  p.splits = 1;
+  return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
+}
+
+int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream) {
+  using namespace w2l;
+  int rc = check_desc(d, "conv1d_dgrad");
+  if (rc) return rc;
+  W2L_REQUIRE(dy && w && dx, "conv1d_dgrad: null pointer");
+  W2L_REQUIRE(d->Cout_pad >= 64, "conv1d_dgrad: Cout_pad=%d must be >= 64 (pad dy/weights)", d->Cout_pad);
+  W2L_REQUIRE(d->ldy >= d->Cout_pad, "conv1d_dgrad: dy row pitch %d < Cout_pad %d", d->ldy, d->Cout_pad);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    // dy viewed as [B, T_out, Cout_pad] inside a [B, y_rows, ldy] buffer
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+    uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)d->T_out, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
+    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  const int n_pad = (d->Cin + 15) / 16 * 16;
+  p.BN = pick_bn(n_pad);
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
+    uint32_t box[3] = {64, 64, 1};
+    rc = make_tensor_map(&p.tmB, w, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.B = d->B;
+  p.m_tiles = (d->x_rows + kBlockM - 1) / kBlockM;
+  p.n_tiles = n_pad / p.BN;
+  p.k = d->k;
+  p.dil = d->dilation;
+  p.kc_steps = (d->Cout_pad + kBlockK - 1) / kBlockK;
+  p.a_row_off = -d->x_row_offset;
+  p.a_tap_step = -d->dilation;
+  p.M_valid = d->x_rows;
+  p.N_valid = d->Cin;
+  p.num_tiles = p.m_tiles * p.n_tiles * p.B;
+  p.act = W2L_ACT_NONE;
+  p.y_dtype = W2L_DTYPE_BF16;
+  p.y = dx;
+  p.y_batch_stride = (int64_t)d->x_rows * d->Cin;
+  p.y_row_off = 0;
+  p.ldy = d->Cin;
+  p.splits = 1;
+  return launch_gemm<MODE_DGRAD>(p, (cudaStream_t)stream);
+}
+
+int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
+  if (!d || d->B < 1) return 1;
+  return w2l::wgrad_splits(d, nullptr);
+}
+
+int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream) {
+  using namespace w2l;
+  int rc = check_desc(d, "conv1d_wgrad");
+  if (rc) return rc;
+  W2L_REQUIRE(dy && x && dw, "conv1d_wgrad: null pointer");
+  W2L_REQUIRE(d->ldy >= 64 && d->ldy % 8 == 0, "conv1d_wgrad: dy row pitch %d must be >= 64 and a multiple of 8", d->ldy);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+    uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->T_out, (uint64_t)d->B};   // columns >= Cout read as zero
+    uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
+    uint32_t box[3] = {64, kBlockK, 1};
+    rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
+    uint32_t box[3] = {64, kBlockK, 1};
+    rc = make_tensor_map(&p.tmB, x, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  int bn = 0;
+  p.splits = wgrad_splits(d, &bn);
+  p.BN = bn;
+  const int n_pad = (d->Cin + 15) / 16 * 16;
+  p.B = d->B;
+  p.b_per_split = (d->B + p.splits - 1) / p.splits;
+  p.m_tiles = (d->Cout + kBlockM - 1) / kBlockM;
+  p.n_tiles = n_pad / p.BN;
+  p.k = d->k;
+  p.dil = d->dilation;
+  p.kc_steps = (d->T_out + kBlockK - 1) / kBlockK;
+  p.b_row_off = d->x_row_offset;
+  p.M_valid = d->Cout;
+  p.N_valid = d->Cin;
+  p.num_tiles = p.k * p.m_tiles * p.n_tiles * p.splits;
+  p.y = dw;
+  p.ldy = d->Cin;
+  p.dw_tap_stride = (int64_t)d->Cout * d->Cin;
+  return launch_gemm<MODE_WGRAD>(p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

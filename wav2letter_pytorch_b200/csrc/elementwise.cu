@@ -1,0 +1,623 @@
+// Memory-bound companions of the conv kernels: layout changes, BatchNorm statistics / apply / backward with
+// fused activation, dropout, reflection halo and length mask, log_softmax fwd/bwd, bias gradient, casts.
+// All activations are time-major [B, T, C] bf16; every kernel moves 16 bytes (8 channels) per thread access.
+#include "common.cuh"
+
+namespace w2l {
+
+// ---------------------------------------------------------------- Philox4x32-10 (dropout masks)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// keep-multipliers (0 or 1/(1-p)) for the 8 consecutive elements starting at element index e (e % 8 == 0)
+__device__ __forceinline__ void dropout_mult8(uint64_t seed, uint64_t e, float p, float (&m)[8]) {
+  if (p <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = 1.f;
+    return;
+  }
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint64_t c0 = e >> 2;
+  const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+  const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(c0 + 1), (uint32_t)((c0 + 1) >> 32), 0u, 0u), key);
+  const uint32_t u[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const float inv = 1.f / (1.f - p);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = ((float)(u[i] >> 8) * (1.f / 16777216.f) >= p) ? inv : 0.f;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  return q;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ---------------------------------------------------------------- NCW fp32 -> (unfolded, padded) time-major bf16
+// block: 32 output rows of one utterance; the needed input span is staged (transposed) in shared memory.
+__global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int F, int T, int rows, int k,
+                                  int stride, int dil, int pad_left, int pad_mode, const int32_t* __restrict__ lens, int span,
+                                  int pitch) {
+  extern __shared__ float tile[];   // [F][pitch]
+  const int b = blockIdx.y, r0 = blockIdx.x * 32;
+  const int nrows = min(32, rows - r0);
+  const int tstart = r0 * stride - pad_left;
+  const int len = lens ? min(T, max(0, lens[b])) : T;
+  const float* xb = x + (int64_t)b * F * T;
+  for (int i = threadIdx.x; i < F * span; i += blockDim.x) {
+    const int f = i / span, dt = i - f * span;
+    int t = tstart + dt;
+    float v = 0.f;
+    if (pad_mode == W2L_PAD_REFLECT) {
+      if (t < 0) t = -t;
+      if (t >= T) t = 2 * (T - 1) - t;
+      if (t >= 0 && t < T) v = xb[(int64_t)f * T + t];
+    } else if (t >= 0 && t < T) {
+      v = xb[(int64_t)f * T + t];
+    }
+    if (t >= len) v = 0.f;
+    tile[f * pitch + dt] = v;
+  }
+  __syncthreads();
+  const int KF = k * F;
+  __nv_bfloat16* ob = out + ((int64_t)b * rows + r0) * KF;
+  for (int i = threadIdx.x; i < nrows * KF; i += blockDim.x) {
+    const int r = i / KF, c = i - r * KF;
+    const int j = c / F, f = c - j * F;
+    ob[i] = __float2bfloat16_rn(tile[f * pitch + r * stride + j * dil]);
+  }
+}
+
+// time-major (bf16 | f32) -> NCW fp32, 32x32 shared-memory transpose
+template <typename TIn>
+__global__ void tm_to_ncw_kernel(const TIn* __restrict__ x, float* __restrict__ out, int T, int C, int64_t x_batch_stride,
+                                 int x_row_offset, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const TIn* xb = x + (int64_t)b * x_batch_stride + (int64_t)x_row_offset * ld;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? (float)xb[(int64_t)t * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) out[((int64_t)b * C + c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm statistics
+// block (32, 8): 32 threads x 8 channels = 256 channels, 8 row lanes; grid (ceil(C/256), row_blocks)
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t rows, int C, float* __restrict__ stats,
+                                int rows_per_block) {
+  __shared__ float s_sum[8][256 + 8], s_sq[8][256 + 8];
+  const int c = blockIdx.x * 256 + threadIdx.x * 8;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum[i] = sq[i] = 0.f;
+  if (c < C) {
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(z + r * C + c));
+      float v[8];
+      unpack8(q, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += v[i];
+        sq[i] = fmaf(v[i], v[i], sq[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_sum[threadIdx.y][threadIdx.x * 8 + i] = sum[i];
+    s_sq[threadIdx.y][threadIdx.x * 8 + i] = sq[i];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;   // 256 threads -> one channel each
+  const int cc = blockIdx.x * 256 + tid;
+  if (cc < C) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      a += s_sum[y][tid];
+      q += s_sq[y][tid];
+    }
+    atomicAdd(stats + cc, a);
+    atomicAdd(stats + C + cc, q);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t rows, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = (double)rows;
+  const double mean = (double)stats[c] / n;
+  double var = (double)stats[C + c] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = bt - (float)mean * g * invstd;
+  if (mean_out) mean_out[c] = (float)mean;
+  if (invstd_out) invstd_out[c] = invstd;
+  if (running_mean) {
+    const float m_full = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m_full;
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------- BN apply + dropout + act + halo + mask
+struct BnActArgs {
+  const __nv_bfloat16* z;
+  const __nv_bfloat16* res;
+  const float* scale;
+  const float* shift;
+  const float* res_scale;
+  const float* res_shift;
+  int B, T, C, pl, pr, act;
+  float drop_p;
+  uint64_t seed;
+  const int32_t* lens;
+};
+
+// value before the activation, after dropout ("pre"), for 8 channels of element (b, t, c..c+7)
+__device__ __forceinline__ void bn_pre8(const BnActArgs& a, int b, int t, int c, float (&pre)[8], float (&mult)[8], float (&zv)[8]) {
+  const int64_t e = ((int64_t)b * a.T + t) * a.C + c;
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a.z + e)), zv);
+  float sc[8], sh[8];
+  load8f(a.scale + c, sc);
+  load8f(a.shift + c, sh);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], sc[i], sh[i]);
+  if (a.res) {
+    float rv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(a.res + e)), rv);
+    load8f(a.res_scale + c, sc);
+    load8f(a.res_shift + c, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], sc[i], sh[i]);
+  }
+  dropout_mult8(a.seed, (uint64_t)e, a.drop_p, mult);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
+}
+
+__global__ void bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y) {
+  const int c8 = a.C >> 3;
+  const int64_t total = (int64_t)a.B * a.T * c8;
+  const int Tp = a.pl + a.T + a.pr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    const int64_t bt = i / c8;
+    const int t = (int)(bt % a.T), b = (int)(bt / a.T);
+    float pre[8], mult[8], zv[8];
+    bn_pre8(a, b, t, c, pre, mult, zv);
+    const bool masked = a.lens && t >= a.lens[b];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = pre[k];
+      if (a.act == W2L_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (a.act == W2L_ACT_CLAMP20) v = fminf(fmaxf(v, 0.f), 20.f);
+      pre[k] = masked ? 0.f : v;
+    }
+    const uint4 q = pack8(pre);
+    __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
+    *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
+    if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
+    const int d = a.T - 1 - t;
+    if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
+  }
+}
+
+// upstream gradient of output element (b,t,c..c+7): fold of the reflect halo of the padded gradient
+__device__ __forceinline__ void fold_grad8(const __nv_bfloat16* __restrict__ dyp, int b, int t, int c, int T, int C, int pl, int pr,
+                                           float (&g)[8]) {
+  const int Tp = pl + T + pr;
+  const __nv_bfloat16* base = dyp + (int64_t)b * Tp * C + c;
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl + t) * C)), g);
+  if (t >= 1 && t <= pl) {
+    float h[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl - t) * C)), h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += h[i];
+  }
+  const int d = T - 1 - t;
+  if (d >= 1 && d <= pr) {
+    float h[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl + T - 1 + d) * C)), h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] += h[i];
+  }
+}
+
+// g (masked upstream gradient wrt the BN output) and xhat for 8 channels
+__device__ __forceinline__ void bwd_g8(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int b, int t, int c, float (&g)[8], float (&xhat)[8]) {
+  float pre[8], mult[8], zv[8];
+  bn_pre8(a, b, t, c, pre, mult, zv);
+  fold_grad8(dyp, b, t, c, a.T, a.C, a.pl, a.pr, g);
+  const bool masked = a.lens && t >= a.lens[b];
+  float mu[8], is[8];
+  load8f(mean + c, mu);
+  load8f(invstd + c, is);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bool pass = true;
+    if (a.act == W2L_ACT_RELU) pass = pre[i] > 0.f;
+    else if (a.act == W2L_ACT_CLAMP20) pass = pre[i] >= 0.f && pre[i] <= 20.f;
+    g[i] = (pass && !masked) ? g[i] * mult[i] : 0.f;
+    xhat[i] = (zv[i] - mu[i]) * is[i];
+  }
+}
+
+// block (32, 8) like bn_stats; red[0:C] += sum g, red[C:2C] += sum g*xhat
+__global__ void bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
+                                         const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
+  __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
+  const int c = blockIdx.x * 256 + threadIdx.x * 8;
+  const int64_t rows = (int64_t)a.B * a.T;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float sg[8], sx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
+  if (c < a.C) {
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const int b = (int)(r / a.T), t = (int)(r - (int64_t)b * a.T);
+      float g[8], xh[8];
+      bwd_g8(a, dyp, mean, invstd, b, t, c, g, xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sg[i] += g[i];
+        sx[i] = fmaf(g[i], xh[i], sx[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_a[threadIdx.y][threadIdx.x * 8 + i] = sg[i];
+    s_b[threadIdx.y][threadIdx.x * 8 + i] = sx[i];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int cc = blockIdx.x * 256 + tid;
+  if (cc < a.C) {
+    float u = 0.f, v = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      u += s_a[y][tid];
+      v += s_b[y][tid];
+    }
+    atomicAdd(red + cc, u);
+    atomicAdd(red + a.C + cc, v);
+  }
+}
+
+__global__ void bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ red, __nv_bfloat16* __restrict__ dz,
+                                        __nv_bfloat16* __restrict__ g_out) {
+  const int c8 = a.C >> 3;
+  const int64_t total = (int64_t)a.B * a.T * c8;
+  const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    const int64_t bt = i / c8;
+    const int t = (int)(bt % a.T), b = (int)(bt / a.T);
+    float g[8], xh[8];
+    bwd_g8(a, dyp, mean, invstd, b, t, c, g, xh);
+    float sg[8], sx[8], ga[8], is[8], o[8];
+    load8f(red + c, sg);
+    load8f(red + a.C + c, sx);
+    load8f(invstd + c, is);
+    if (gamma) load8f(gamma + c, ga);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gm = gamma ? ga[k] : 1.f;
+      o[k] = gm * is[k] * (g[k] - sg[k] * inv_m - xh[k] * sx[k] * inv_m);
+    }
+    const int64_t e = bt * a.C + c;
+    *reinterpret_cast<uint4*>(dz + e) = pack8(o);
+    if (g_out) *reinterpret_cast<uint4*>(g_out + e) = pack8(g);
+  }
+}
+
+// ---------------------------------------------------------------- log_softmax fwd / bwd (one warp per row)
+__global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int64_t rows, int C, int mode) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* src = logits + row * ld;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, src[c]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(src[c] - m);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float lse = m + logf(s);
+  for (int c = lane; c < C; c += 32) out[row * C + c] = mode == 0 ? src[c] - lse : expf(src[c] - lse);
+}
+
+__global__ void log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp, const float* __restrict__ gscale,
+                                       __nv_bfloat16* __restrict__ dlogits, int ld_out, int64_t rows, int C, int fused_identity) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float sc = gscale ? *gscale : 1.f;
+  float s = 0.f;
+  if (!fused_identity) {
+    for (int c = lane; c < C; c += 32) s += g[row * C + c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  for (int c = lane; c < ld_out; c += 32) {
+    float v = 0.f;
+    if (c < C) {
+      v = g[row * C + c];
+      if (!fused_identity) v -= expf(lp[row * C + c]) * s;
+      v *= sc;
+    }
+    dlogits[row * ld_out + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// column sums of a bf16 matrix (bias gradient); block (32, 8), 32 channels per block-column
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out,
+                              int rows_per_block) {
+  __shared__ float s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) acc += __bfloat162float(x[r * ld + c]);
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += s[y][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t n8 = n >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8f(src + i * 8, v);
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = n8 * 8; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+static inline int grid_for(int64_t items, int threads) {
+  int64_t blocks = (items + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static BnActArgs make_args(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
+                           const float* res_shift, int B, int T, int C, int pl, int pr, int act, float drop_p, uint64_t seed,
+                           const int32_t* lens) {
+  BnActArgs a;
+  a.z = (const __nv_bfloat16*)z;
+  a.res = (const __nv_bfloat16*)res;
+  a.scale = scale;
+  a.shift = shift;
+  a.res_scale = res_scale;
+  a.res_shift = res_shift;
+  a.B = B;
+  a.T = T;
+  a.C = C;
+  a.pl = pl;
+  a.pr = pr;
+  a.act = act;
+  a.drop_p = drop_p;
+  a.seed = seed;
+  a.lens = lens;
+  return a;
+}
+
+static int check_bn_args(const char* who, const void* z, const float* scale, const float* shift, const void* res,
+                         const float* res_scale, const float* res_shift, int B, int T, int C, int pl, int pr, float drop_p) {
+  W2L_REQUIRE(z && scale && shift, "%s: null pointer", who);
+  W2L_REQUIRE(!res || (res_scale && res_shift), "%s: residual needs res_scale/res_shift", who);
+  W2L_REQUIRE(B >= 1 && T >= 1 && C >= 8 && C % 8 == 0, "%s: bad shape B=%d T=%d C=%d (C must be a multiple of 8)", who, B, T, C);
+  W2L_REQUIRE(pl >= 0 && pr >= 0 && pl < T && pr < T, "%s: reflect halo (%d,%d) must be smaller than T=%d", who, pl, pr, T);
+  W2L_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p=%f out of [0,1)", who, drop_p);
+  return W2L_OK;
+}
+
+static int rows_per_block_for(int64_t rows, int col_blocks) {
+  int64_t target_blocks = (int64_t)num_sms() * 4 / (col_blocks > 0 ? col_blocks : 1);
+  if (target_blocks < 1) target_blocks = 1;
+  int64_t rpb = (rows + target_blocks - 1) / target_blocks;
+  if (rpb < 64) rpb = 64;
+  return (int)rpb;
+}
+
+}  // namespace w2l
+
+extern "C" {
+
+int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                   int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(x && out, "im2col_ncw: null pointer");
+  W2L_REQUIRE(B >= 1 && F >= 1 && T >= 1 && rows >= 1 && k >= 1 && stride >= 1 && dilation >= 1 && pad_left >= 0, "im2col_ncw: bad geometry");
+  W2L_REQUIRE(pad_mode != W2L_PAD_REFLECT || pad_left < T, "im2col_ncw: reflect pad %d must be < T=%d", pad_left, T);
+  W2L_REQUIRE(B <= 65535, "im2col_ncw: B too large");
+  const int span = 31 * stride + (k - 1) * dilation + 1;
+  const int pitch = span | 1;
+  const size_t smem = (size_t)F * pitch * sizeof(float);
+  W2L_REQUIRE(smem <= 200 * 1024, "im2col_ncw: F=%d k=%d needs %zu bytes of shared memory", F, k, smem);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    W2L_CUDA(cudaFuncSetAttribute(im2col_ncw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((rows + 31) / 32, B);
+  im2col_ncw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, F, T, rows, k, stride, dilation, pad_left,
+                                                               pad_mode, lens, span, pitch);
+  return after_launch("im2col_ncw_kernel");
+}
+
+int w2l_ncw_to_tm(const float* x, void* out, int32_t B, int32_t C, int32_t T, void* stream) {
+  return w2l_im2col_ncw(x, out, B, C, T, T, 1, 1, 1, 0, W2L_PAD_ZERO, nullptr, stream);
+}
+
+int w2l_tm_to_ncw(const void* x, int32_t x_dtype, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows, int32_t x_row_offset,
+                  int32_t ld, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(x && out && B >= 1 && T >= 1 && C >= 1 && ld >= C && x_rows >= T + x_row_offset, "tm_to_ncw: bad arguments");
+  W2L_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tm_to_ncw: shape too large");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  const int64_t bs = (int64_t)x_rows * ld;
+  if (x_dtype == W2L_DTYPE_BF16)
+    tm_to_ncw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, T, C, bs, x_row_offset, ld);
+  else
+    tm_to_ncw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, out, T, C, bs, x_row_offset, ld);
+  return after_launch("tm_to_ncw_kernel");
+}
+
+int w2l_bn_stats(const void* z, int64_t rows, int32_t C, float* stats, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(z && stats && rows >= 1 && C >= 8 && C % 8 == 0, "bn_stats: bad arguments (C must be a multiple of 8)");
+  const int col_blocks = (C + 255) / 256;
+  const int rpb = rows_per_block_for(rows, col_blocks);
+  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
+  bn_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, rows, C, stats, rpb);
+  return after_launch("bn_stats_kernel");
+}
+
+int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* gamma, const float* beta, const float* conv_bias,
+                    float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                    float* invstd, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(stats && scale && shift && rows >= 1 && C >= 1, "bn_finalize: bad arguments");
+  W2L_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must be given together");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, rows, C, gamma, beta, conv_bias, eps, momentum,
+                                                                        running_mean, running_var, scale, shift, mean, invstd);
+  return after_launch("bn_finalize_kernel");
+}
+
+int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
+                   const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right,
+                   int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream) {
+  using namespace w2l;
+  int rc = check_bn_args("bn_act_pad", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  if (rc) return rc;
+  W2L_REQUIRE(y != nullptr, "bn_act_pad: null output");
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  const int64_t total = (int64_t)B * T * (C / 8);
+  bn_act_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y);
+  return after_launch("bn_act_pad_kernel");
+}
+
+int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
+                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd, float* red,
+                          int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
+                          uint64_t seed, const int32_t* lens, void* stream) {
+  using namespace w2l;
+  int rc = check_bn_args("bn_act_bwd_reduce", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  if (rc) return rc;
+  W2L_REQUIRE(dyp && mean && invstd && red, "bn_act_bwd_reduce: null pointer");
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  const int64_t rows = (int64_t)B * T;
+  const int col_blocks = (C + 255) / 256;
+  const int rpb = rows_per_block_for(rows, col_blocks);
+  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
+  bn_act_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
+  return after_launch("bn_act_bwd_reduce_kernel");
+}
+
+int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
+                         const float* res_scale, const float* res_shift, const float* mean, const float* invstd, const float* gamma,
+                         const float* red, void* dz, void* g_out, int32_t B, int32_t T, int32_t C, int32_t pad_left,
+                         int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream) {
+  using namespace w2l;
+  int rc = check_bn_args("bn_act_bwd_apply", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  if (rc) return rc;
+  W2L_REQUIRE(dyp && mean && invstd && red && dz, "bn_act_bwd_apply: null pointer");
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  const int64_t total = (int64_t)B * T * (C / 8);
+  bn_act_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma,
+                                                                                 red, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
+  return after_launch("bn_act_bwd_apply_kernel");
+}
+
+int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(logits && out && rows >= 1 && C >= 1 && ld >= C, "log_softmax: bad arguments");
+  log_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, out, rows, C, mode);
+  return after_launch("log_softmax_kernel");
+}
+
+int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out, int64_t rows,
+                        int32_t C, int32_t fused_identity, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(g && dlogits && rows >= 1 && C >= 1 && ld_out >= C, "log_softmax_bwd: bad arguments");
+  W2L_REQUIRE(fused_identity || lp, "log_softmax_bwd: log-probs required");
+  log_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, lp, gscale, (__nv_bfloat16*)dlogits, ld_out,
+                                                                                      rows, C, fused_identity);
+  return after_launch("log_softmax_bwd_kernel");
+}
+
+int w2l_colsum(const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(x && out && rows >= 1 && C >= 1 && ld >= C, "colsum: bad arguments");
+  const int col_blocks = (C + 31) / 32;
+  const int rpb = rows_per_block_for(rows, col_blocks);
+  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
+  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out, rpb);
+  return after_launch("colsum_kernel");
+}
+
+int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(src && dst && n >= 0, "cast_bf16: bad arguments");
+  if (n == 0) return W2L_OK;
+  W2L_REQUIRE(((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0, "cast_bf16: pointers must be 32/16-byte aligned");
+  cast_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  return after_launch("cast_bf16_kernel");
+}
+
+}  // extern "C"

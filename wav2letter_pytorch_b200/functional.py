@@ -1,0 +1,234 @@
+"""Thin tensor-level wrappers over the C ABI (include/w2l_sm100.h).
+
+PyTorch is used here for device memory, streams and autograd plumbing only; every computation is done by the
+hand-written sm_100a kernels in libw2l_sm100.so.  CPU tensors are rejected -- there is no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc
+
+ACT_NONE, ACT_RELU, ACT_CLAMP20 = 0, 1, 2
+PAD_ZERO, PAD_REFLECT = 0, 1
+DT_BF16, DT_F32 = 0, 1
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("wav2letter_pytorch_b200: CUDA tensors required (got a %s tensor); there is no CPU path"
+                               % t.device.type)
+
+
+# --------------------------------------------------------------------------------------------- decode
+def greedy_decode(scores, sizes=None, blank=0):
+    """scores [N,T,C] fp32 cuda -> (argmax [N,T], tokens [N,T], offsets [N,T], counts [N]) int32 cuda.
+    decoder.py:121-145 (argmax + collapse)."""
+    _need_cuda(scores, sizes)
+    lib = _lib.load()
+    if scores.dtype != torch.float32:
+        scores = scores.float()
+    if scores.stride(2) != 1:
+        scores = scores.contiguous()
+    N, T, C = scores.shape
+    dev = scores.device
+    argmax = torch.empty((N, T), dtype=torch.int32, device=dev)
+    tokens = torch.empty((N, T), dtype=torch.int32, device=dev)
+    offsets = torch.empty((N, T), dtype=torch.int32, device=dev)
+    counts = torch.empty((N,), dtype=torch.int32, device=dev)
+    if sizes is not None:
+        sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
+    wsb = lib.w2l_greedy_decode_workspace_bytes(N, T)
+    ws = torch.empty((max(wsb, 4),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.w2l_greedy_decode(_ptr(scores), N, T, C, scores.stride(0), scores.stride(1), _ptr(sizes), blank, _ptr(argmax),
+                                         _ptr(tokens), _ptr(offsets), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
+                   "greedy_decode")
+    return argmax, tokens, offsets, counts
+
+
+# --------------------------------------------------------------------------------------------- CTC
+def ctc_loss_raw(x, targets, input_lengths, target_lengths, blank=0, zero_infinity=True, reduction_mean=True,
+                 from_logits=False, need_grad=True):
+    """x [N,T,C] fp32 cuda (any N/T strides).  Returns (loss[1], nll[N], grad[N,T,C] | None).
+    grad already carries the 1/(N*max(S,1)) factor of reduction='mean'."""
+    _need_cuda(x, targets)
+    lib = _lib.load()
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    N, T, C = x.shape
+    dev = x.device
+    targets = targets.to(device=dev, dtype=torch.int32)
+    if targets.dim() != 2:
+        raise ValueError("targets must be the 2-D zero padded [N, S_max] tensor the collator emits")
+    targets = targets.contiguous()
+    il = input_lengths.to(device=dev, dtype=torch.int32).contiguous()
+    tl = target_lengths.to(device=dev, dtype=torch.int32).contiguous()
+    S = targets.shape[1]
+    wsb = lib.w2l_ctc_loss_workspace_bytes(N, T, S)
+    if wsb == 0:
+        raise RuntimeError("ctc_loss: target length %d not supported" % S)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    nll = torch.empty((N,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    grad = torch.empty((N, T, C), dtype=torch.float32, device=dev) if need_grad else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.w2l_ctc_loss(_ptr(x), int(from_logits), N, T, C, x.stride(0), x.stride(1), _ptr(targets), S, _ptr(il), _ptr(tl),
+                                    blank, int(zero_infinity), int(reduction_mean), _ptr(nll), _ptr(grad), _ptr(loss), _ptr(ws),
+                                    ws.numel(), _stream()), "ctc_loss")
+    return loss, nll, grad
+
+
+# --------------------------------------------------------------------------------------------- conv
+def make_desc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype=DT_BF16,
+              act=ACT_NONE):
+    return ConvDesc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype, act)
+
+
+def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None):
+    _need_cuda(x, w, y)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_conv1d_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(y), ctypes.byref(desc),
+                                              _stream()), "conv1d_fwd")
+    return y
+
+
+def conv1d_dgrad(dy, w, desc, dx):
+    _need_cuda(dy, w, dx)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().w2l_conv1d_dgrad(_ptr(dy), _ptr(w), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad")
+    return dx
+
+
+def conv1d_wgrad(dy, x, desc, dw):
+    """dw [k, Cout, Cin] fp32; zero-filled here when the kernel will run split-K (atomic accumulation)."""
+    _need_cuda(dy, x, dw)
+    lib = _lib.load()
+    with torch.cuda.device(dy.device):
+        if lib.w2l_conv1d_wgrad_splits(ctypes.byref(desc)) > 1:
+            dw.zero_()
+        _lib.check(lib.w2l_conv1d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(desc), _stream()), "conv1d_wgrad")
+    return dw
+
+
+# --------------------------------------------------------------------------------------------- elementwise
+def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
+    """x [B,F,T] fp32 -> [B, rows, k*F] bf16 (unfold + pad + transpose + cast)."""
+    _need_cuda(x, lens)
+    x = x.contiguous().float()
+    B, F, T = x.shape
+    out = torch.empty((B, rows, k * F), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_im2col_ncw(_ptr(x), _ptr(out), B, F, T, rows, k, stride, dilation, pad_left, pad_mode, _ptr(lens),
+                                              _stream()), "im2col_ncw")
+    return out
+
+
+def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
+    """time-major [B, x_rows, ld] (bf16|f32) -> NCW fp32 [B, C, T]."""
+    _need_cuda(x)
+    B, rows, ld = x.shape
+    out = torch.empty((B, C, T), dtype=torch.float32, device=x.device)
+    dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_F32
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_tm_to_ncw(_ptr(x), dt, _ptr(out), B, T, C, rows, x_row_offset, ld, _stream()), "tm_to_ncw")
+    return out
+
+
+def bn_stats(z, C):
+    rows = z.numel() // C
+    stats = torch.zeros((2 * C,), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().w2l_bn_stats(_ptr(z), rows, C, _ptr(stats), _stream()), "bn_stats")
+    return stats
+
+
+def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var):
+    dev = stats.device
+    out = torch.empty((4, C), dtype=torch.float32, device=dev)     # scale, shift, mean, invstd
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().w2l_bn_finalize(_ptr(stats), rows, C, _ptr(gamma), _ptr(beta), _ptr(conv_bias), eps, momentum,
+                                               _ptr(running_mean), _ptr(running_var), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                               _ptr(out[3]), _stream()), "bn_finalize")
+    return out
+
+
+def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None,
+               res_shift=None, out=None):
+    if out is None:
+        out = torch.empty((B, pad_left + T + pad_right, C), dtype=torch.bfloat16, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().w2l_bn_act_pad(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
+                                              B, T, C, pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()),
+                   "bn_act_pad")
+    return out
+
+
+def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
+               res=None, res_scale=None, res_shift=None, want_g=False):
+    """Returns (dz bf16 [B,T,C], red fp32 [2C] = (dbeta, dgamma), g bf16 | None)."""
+    dev = z.device
+    red = torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+    dz = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev)
+    g = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev) if want_g else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
+                                             _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
+                                             int(seed), _ptr(lens), _stream()), "bn_act_bwd_reduce")
+        _lib.check(lib.w2l_bn_act_bwd_apply(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
+                                            _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), _ptr(g), B, T, C, pad_left,
+                                            pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()), "bn_act_bwd_apply")
+    return dz, red, g
+
+
+def log_softmax(logits, C, mode=0):
+    """logits [..., ld] fp32 -> [..., C] fp32 (mode 0 log_softmax, 1 softmax) over the first C columns."""
+    ld = logits.shape[-1]
+    rows = logits.numel() // ld
+    out = torch.empty(logits.shape[:-1] + (C,), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.check(_lib.load().w2l_log_softmax(_ptr(logits), ld, _ptr(out), rows, C, mode, _stream()), "log_softmax")
+    return out
+
+
+def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
+    """g, lp [..., C] fp32 -> d logits bf16 [..., ld_out] (zero padded)."""
+    C = g.shape[-1]
+    rows = g.numel() // C
+    g = g.contiguous()
+    out = torch.empty(g.shape[:-1] + (ld_out,), dtype=torch.bfloat16, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.load().w2l_log_softmax_bwd(_ptr(g), _ptr(lp), _ptr(gscale), _ptr(out), ld_out, rows, C, int(fused_identity),
+                                                   _stream()), "log_softmax_bwd")
+    return out
+
+
+def colsum(x, C):
+    ld = x.shape[-1]
+    rows = x.numel() // ld
+    out = torch.zeros((C,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_colsum(_ptr(x), rows, C, ld, _ptr(out), _stream()), "colsum")
+    return out
+
+
+def cast_bf16(src, dst=None):
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().w2l_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_bf16")
+    return dst
