@@ -153,6 +153,9 @@ int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* ga
 int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
                    int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream);
+/* In-place reflect halo for a buffer whose interior rows [pad_left, pad_left+T) were written by the fused
+ * conv epilogue (inference: BatchNorm folded into scale/shift, wav2letter.py:41-46). */
+int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream);
 /* Backward of the above + BatchNorm backward, two passes over (dy_padded, z):
  *   g = fold_reflect(dyp)[b,t,c] * act'(.) * dropmask;  pass 1 reduces sum(g), sum(g*xhat) into
  *   red[0:C], red[C:2C] (zeroed by caller); pass 2 writes dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)).

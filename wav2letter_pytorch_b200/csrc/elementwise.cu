@@ -621,3 +621,32 @@ int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- reflect halo fill (inference path)
+// y [B, pl+T+pr, C] bf16 whose interior rows [pl, pl+T) are already written: fills the mirrored halo rows in place.
+namespace w2l {
+__global__ void reflect_halo_kernel(__nv_bfloat16* __restrict__ y, int B, int T, int C, int pl, int pr) {
+  const int c8 = C >> 3, halo = pl + pr, Tp = pl + T + pr;
+  const int64_t total = (int64_t)B * halo * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    const int64_t bh = i / c8;
+    const int h = (int)(bh % halo), b = (int)(bh / halo);
+    // halo row index and its mirror source (both in padded coordinates)
+    const int dst = h < pl ? h : pl + T + (h - pl);
+    const int src = h < pl ? 2 * pl - h : pl + T - 2 - (h - pl);
+    __nv_bfloat16* yb = y + (int64_t)b * Tp * C + c;
+    *reinterpret_cast<uint4*>(yb + (int64_t)dst * C) = *reinterpret_cast<const uint4*>(yb + (int64_t)src * C);
+  }
+}
+}  // namespace w2l
+
+extern "C" int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(y && B >= 1 && T >= 1 && C >= 8 && C % 8 == 0, "reflect_halo: bad arguments");
+  W2L_REQUIRE(pad_left >= 0 && pad_right >= 0 && pad_left < T && pad_right < T, "reflect_halo: halo must be smaller than T");
+  if (pad_left + pad_right == 0) return W2L_OK;
+  const int64_t total = (int64_t)B * (pad_left + pad_right) * (C / 8);
+  reflect_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)y, B, T, C, pad_left, pad_right);
+  return after_launch("reflect_halo_kernel");
+}

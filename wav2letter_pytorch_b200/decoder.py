@@ -1,0 +1,87 @@
+"""Decoders with the reference's interface (decoder.py:11-145): ``Decoder(labels, blank_index)``, ``decode(probs,
+sizes=None[, return_offsets])``, ``wer`` / ``cer`` / ``wer_ratio`` / ``cer_ratio``.
+
+``GreedyDecoder`` runs argmax + collapse as one coalesced CUDA pass (csrc/decode.cu) instead of the reference's
+per-frame Python loop with two ``.item()`` device syncs per frame; a single device->host copy of the compacted
+tokens then builds the strings."""
+import torch
+
+from . import functional as F
+from . import label_sets
+
+
+def _edit_distance(a, b):
+    """Levenshtein distance between two sequences (the reference uses the python-Levenshtein C extension)."""
+    if len(a) < len(b):
+        a, b = b, a
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i] + [0] * len(b)
+        for j, cb in enumerate(b, 1):
+            cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb))
+        prev = cur
+    return prev[-1]
+
+
+class Decoder(object):
+    def __init__(self, labels, blank_index=0):
+        # decoder.py:22-29; NB the reference builds int_to_char from the *argument* even when it is a label-set
+        # name -- callers always pass the list (config.yaml:16), and so must users of this class.
+        self.labels = label_sets.labels_map[labels] if type(labels) is str else labels
+        self.int_to_char = dict(enumerate(self.labels))
+        self.blank_index = blank_index
+        self.space_index = self.labels.index(" ") if " " in self.labels else len(self.labels)
+
+    def wer(self, s1, s2):
+        return _edit_distance(s1.split(), s2.split())
+
+    def cer(self, s1, s2):
+        return _edit_distance(s1.replace(" ", ""), s2.replace(" ", ""))
+
+    def cer_ratio(self, expected, predicted):
+        return self.cer(expected, predicted), len(expected.replace(" ", ""))
+
+    def wer_ratio(self, expected, predicted):
+        return self.wer(expected, predicted), len(expected.split())
+
+    def decode(self, probs, sizes=None):
+        raise NotImplementedError
+
+
+class GreedyDecoder(Decoder):
+    def decode_tokens(self, probs, sizes=None):
+        """Device-side part: returns (tokens [N,T], offsets [N,T], counts [N]) int32 CUDA tensors."""
+        if not torch.is_tensor(probs):
+            probs = torch.as_tensor(probs, dtype=torch.float32)
+        if probs.dim() == 2:
+            probs = probs.unsqueeze(0)
+        if not probs.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("GreedyDecoder: a CUDA device is required (no CPU fallback)")
+            probs = probs.cuda()
+        if sizes is not None and not torch.is_tensor(sizes):
+            sizes = torch.as_tensor([int(s) for s in sizes], dtype=torch.int32)
+        if sizes is not None:
+            sizes = sizes.to(probs.device)
+        _, tokens, offsets, counts = F.greedy_decode(probs.detach(), sizes, self.blank_index)
+        return tokens, offsets, counts
+
+    def decode(self, probs, sizes=None, return_offsets=False):
+        """probs [N,T,C] (or [T,C]) -> list[str] (and list[[IntTensor]] of frame offsets), decoder.py:121-145."""
+        tokens, offsets, counts = self.decode_tokens(probs, sizes)
+        N, T = tokens.shape
+        counts_h = counts.cpu()
+        width = int(counts_h.max().item()) if N > 0 else 0
+        packed = torch.stack([tokens[:, :width], offsets[:, :width]]).cpu() if width > 0 else None    # one D2H copy
+        strings, offs = [], []
+        for n in range(N):
+            c = int(counts_h[n])
+            ids = packed[0, n, :c].tolist() if c else []
+            if ids and self.space_index >= len(self.labels):
+                raise IndexError("list index out of range")          # decoder.py:113 with no ' ' in labels
+            strings.append("".join(self.int_to_char[i] for i in ids))
+            if return_offsets:
+                offs.append([packed[1, n, :c].to(torch.int32) if c else torch.IntTensor([])])
+        if return_offsets:
+            return strings, offs
+        return strings

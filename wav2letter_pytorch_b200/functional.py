@@ -176,6 +176,13 @@ def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, s
     return out
 
 
+def reflect_halo(y, T, pad_left, pad_right):
+    B, rows, C = y.shape
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.load().w2l_reflect_halo(_ptr(y), B, T, C, pad_left, pad_right, _stream()), "reflect_halo")
+    return y
+
+
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
                res=None, res_scale=None, res_shift=None, want_g=False):
     """Returns (dz bf16 [B,T,C], red fp32 [2C] = (dbeta, dgamma), g bf16 | None)."""

@@ -1,0 +1,261 @@
+"""Building blocks shared by Wav2Letter and Jasper: parameter containers whose state_dict keys and shapes match the
+reference's nn.Conv1d / nn.BatchNorm1d, and autograd Functions that run conv -> BatchNorm -> dropout -> activation
+(-> reflection halo / length mask of the consumer) on the hand-written sm_100a kernels.
+
+Layout contract between blocks: activations are time-major bf16 ``[B, rows, C]``; a producer writes the rows its
+consumer's padding rule needs (Wav2Letter: mirrored halo rows; Jasper: none, zero padding comes from TMA OOB fill).
+Conv weights keep the reference's parameter shape ``[Cout, Cin, k]`` but live in memory in the layout the GEMM
+kernels read (``[k, Cout, Cin]``, or ``[Cout, k, Cin]`` for the unfolded strided first layer): the Parameter is a
+permuted view, so packing a bf16 shadow is a plain cast and weight gradients need no re-layout."""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functional as F
+
+_seed_counter = [0]
+
+
+def next_dropout_seed():
+    _seed_counter[0] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+class ConvParams(nn.Module):
+    """Stands where the reference has an ``nn.Conv1d`` (wav2letter.py:35-36, jasper.py:96-105): same attribute
+    names (weight, bias, kernel_size, stride, dilation, padding, in/out_channels) and state_dict entries."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True, unfold=False,
+                 init="conv_default"):
+        super().__init__()
+        k = kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.dilation, self.padding = (k,), (stride,), (dilation,), (padding,)
+        self.groups = 1
+        self.unfold = bool(unfold)            # strided layer: input is unfolded (im2col) and the conv runs with k=1
+        # reference-shaped init (same RNG consumption order as nn.Conv1d.reset_parameters), then re-layout
+        w = torch.empty(out_channels, in_channels, k)
+        if init == "xavier_uniform":          # jasper.py:29-35
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            b0 = self._default_bias(w) if bias else None
+            nn.init.xavier_uniform_(w, gain=1.0)
+        else:
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            b0 = self._default_bias(w) if bias else None
+        perm = (0, 2, 1) if self.unfold else (2, 0, 1)
+        store = w.permute(*perm).contiguous()
+        self.weight = nn.Parameter(store.permute(*self._inverse(perm)))
+        self.bias = nn.Parameter(b0) if bias else None
+        self._shadow = None
+        self._shadow_version = None
+
+    @staticmethod
+    def _default_bias(w):
+        fan_in = w.shape[1] * w.shape[2]
+        bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+        return torch.empty(w.shape[0]).uniform_(-bound, bound)
+
+    @staticmethod
+    def _inverse(perm):
+        inv = [0] * len(perm)
+        for i, p in enumerate(perm):
+            inv[p] = i
+        return tuple(inv)
+
+    # ---- kernel-side geometry
+    @property
+    def k_eff(self):
+        return 1 if self.unfold else self.kernel_size[0]
+
+    @property
+    def cin_eff(self):
+        return self.in_channels * self.kernel_size[0] if self.unfold else self.in_channels
+
+    @property
+    def cout_pad(self):
+        """rows per tap of the packed weights: multiple of 16 (UMMA N granularity), at least 64 (dgrad K chunk)"""
+        return max(64, (self.out_channels + 15) // 16 * 16)
+
+    def storage(self):
+        """fp32 weights in kernel layout [k_eff, Cout, cin_eff] (a view of the Parameter's memory)."""
+        perm = (0, 2, 1) if self.unfold else (2, 0, 1)
+        v = self.weight.detach().permute(*perm)
+        if not v.is_contiguous():             # e.g. a Parameter re-created by external code: restore the layout
+            v = v.contiguous()
+            self.weight.data = v.permute(*self._inverse(perm))
+        return v.reshape(self.k_eff, self.out_channels, self.cin_eff)
+
+    def grad_view(self, dw_store):
+        """[k_eff, Cout, cin_eff] fp32 -> tensor shaped/strided like the Parameter."""
+        k = self.kernel_size[0]
+        if self.unfold:
+            return dw_store.view(self.out_channels, k, self.in_channels).permute(0, 2, 1)
+        return dw_store.view(k, self.out_channels, self.in_channels).permute(1, 2, 0)
+
+    def packed(self):
+        """bf16 shadow [k_eff, cout_pad, cin_eff] read by the GEMM kernels; refreshed when the Parameter changed."""
+        w = self.weight
+        ver = (w._version, w.data_ptr())
+        if self._shadow is None or self._shadow.device != w.device:
+            self._shadow = torch.zeros((self.k_eff, self.cout_pad, self.cin_eff), dtype=torch.bfloat16, device=w.device)
+            self._shadow_version = None
+        if self._shadow_version != ver:
+            st = self.storage()
+            if self.cout_pad == self.out_channels:
+                F.cast_bf16(st, self._shadow)
+            else:                              # padded rows stay zero; k_eff == 1 for the only such layer (the head)
+                for j in range(self.k_eff):
+                    F.cast_bf16(st[j], self._shadow[j, :self.out_channels])
+            self._shadow_version = ver
+        return self._shadow
+
+    def mark_shadow_fresh(self):
+        """Called by the fused optimizer, which rewrites the shadow itself."""
+        self._shadow_version = (self.weight._version, self.weight.data_ptr())
+
+    def extra_repr(self):
+        return "%d, %d, kernel_size=%s, stride=%s, dilation=%s" % (self.in_channels, self.out_channels, self.kernel_size,
+                                                                  self.stride, self.dilation)
+
+
+class BatchNormParams(nn.Module):
+    """Stands where the reference has ``nn.BatchNorm1d`` (wav2letter.py:37, jasper.py:363)."""
+
+    def __init__(self, num_features, eps=1e-3, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.affine, self.track_running_stats = True, True
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def eval_scale_shift(self, conv_bias=None):
+        scale = self.weight.detach() * torch.rsqrt(self.running_var + self.eps)
+        shift = self.bias.detach() - self.running_mean * scale
+        if conv_bias is not None:
+            shift = shift + conv_bias.detach() * scale
+        return scale.contiguous(), shift.contiguous()
+
+    def extra_repr(self):
+        return "%d, eps=%g, momentum=%g" % (self.num_features, self.eps, self.momentum)
+
+
+def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0, ldy=None, y_dtype=F.DT_BF16, act=F.ACT_NONE):
+    return F.make_desc(B, T_out, conv.cin_eff, conv.out_channels, conv.cout_pad, conv.k_eff, conv.dilation[0], x_rows, x_row_offset,
+                       T_out if y_rows is None else y_rows, y_row_offset, conv.out_channels if ldy is None else ldy, y_dtype, act)
+
+
+class ConvBNActFn(torch.autograd.Function):
+    """conv (+bias) -> BatchNorm(train statistics) -> dropout -> activation, written into the consumer's padded
+    buffer.  Inputs: time-major bf16 ``xin`` ([B, x_rows, cin_eff]), the conv/BN parameters, and a geometry dict:
+      x_row_offset, out_pad=(pl, pr) reflect halo wanted by the consumer, act, drop_p, lens (int32 [B] | None),
+      res=(z_res, res_fin) residual branch already convolved (Jasper), momentum/eps come from ``bn``.
+    Returns yp [B, pl+T_out+pr, Cout] bf16."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, bias, gamma, beta, conv, bn, geo):
+        B, x_rows, _ = xin.shape
+        k, d = conv.k_eff, conv.dilation[0]
+        T_out = geo["T_out"]
+        Co = conv.out_channels
+        pl, pr = geo.get("out_pad", (0, 0))
+        z = torch.empty((B, T_out, Co), dtype=torch.bfloat16, device=xin.device)
+        desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
+        F.conv1d_fwd(xin, conv.packed(), desc, z)          # conv bias is folded into the BN statistics below
+        stats = F.bn_stats(z, Co)
+        fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+        seed = next_dropout_seed() if geo.get("drop_p", 0.0) > 0 else 0
+        res = geo.get("res")
+        yp = F.bn_act_pad(z, fin[0], fin[1], B, T_out, Co, pl, pr, geo["act"], geo.get("drop_p", 0.0), seed, geo.get("lens"),
+                          res=None if res is None else res[0], res_scale=None if res is None else res[1][0],
+                          res_shift=None if res is None else res[1][1])
+        ctx.conv, ctx.bn, ctx.geo, ctx.seed, ctx.desc = conv, bn, geo, seed, desc
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xin, z, fin, gamma)
+        return yp
+
+    @staticmethod
+    def backward(ctx, dyp):
+        xin, z, fin, gamma = ctx.saved_tensors
+        conv, geo = ctx.conv, ctx.geo
+        B, T_out, Co = z.shape
+        pl, pr = geo.get("out_pad", (0, 0))
+        res = geo.get("res")
+        dyp = dyp.contiguous()
+        dz, red, g = F.bn_act_bwd(dyp, z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
+                                  geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=None if res is None else res[0],
+                                  res_scale=None if res is None else res[1][0], res_shift=None if res is None else res[1][1],
+                                  want_g=res is not None)
+        if res is not None:
+            geo["res_grad_sink"](g)                        # hand the masked upstream gradient to the residual branch
+        dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
+        F.conv1d_wgrad(dz, xin, ctx.desc, dw)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(xin)
+            F.conv1d_dgrad(dz, conv.packed(), ctx.desc, dx)
+        dbias = torch.zeros(Co, dtype=torch.float32, device=z.device) if ctx.has_bias else None   # exactly 0 under train BN
+        return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], None, None, None
+
+
+class ConvHeadFn(torch.autograd.Function):
+    """k=1 conv with bias to the label logits (fp32), then log_softmax / softmax (wav2letter.py:66,86-87;
+    jasper.py:433,468-473).  Returns [B, T, n_labels] fp32 contiguous."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, bias, conv, mode):
+        B, T, _ = xin.shape
+        Co = conv.out_channels
+        ld = (Co + 7) // 8 * 8
+        logits = torch.empty((B, T, ld), dtype=torch.float32, device=xin.device)
+        desc = conv_desc(conv, B, T, T, 0, ldy=ld, y_dtype=F.DT_F32)
+        F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
+        out = F.log_softmax(logits, Co, mode)
+        ctx.conv, ctx.mode = conv, mode
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xin, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xin, out = ctx.saved_tensors
+        conv = ctx.conv
+        if ctx.mode != 0:
+            raise NotImplementedError("backward through the eval-mode softmax head is not supported")
+        B, T, _ = xin.shape
+        Co, cp = conv.out_channels, conv.cout_pad
+        dl = F.log_softmax_bwd(dout.contiguous(), out, cp)            # bf16 [B,T,cout_pad], zero padded
+        desc = conv_desc(conv, B, T, T, 0, ldy=cp)
+        dw = torch.empty((1, Co, conv.cin_eff), dtype=torch.float32, device=xin.device)
+        F.conv1d_wgrad(dl, xin, desc, dw)
+        dbias = F.colsum(dl, Co) if ctx.has_bias else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(xin)
+            F.conv1d_dgrad(dl, conv.packed(), desc, dx)
+        return dx, conv.grad_view(dw), dbias, None, None
+
+
+def conv_bn_act_eval(xin, conv, bn, geo):
+    """Inference path: BatchNorm folded into the conv epilogue (scale/shift/activation fused), then the halo/mask
+    pass only if the consumer needs padded or masked rows."""
+    B, x_rows, _ = xin.shape
+    T_out, Co = geo["T_out"], conv.out_channels
+    pl, pr = geo.get("out_pad", (0, 0))
+    res = geo.get("res")
+    lens = geo.get("lens")
+    scale, shift = bn.eval_scale_shift(conv.bias)
+    if res is None and lens is None:
+        y = torch.empty((B, pl + T_out + pr, Co), dtype=torch.bfloat16, device=xin.device)
+        desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=pl + T_out + pr, y_row_offset=pl, act=geo["act"])
+        F.conv1d_fwd(xin, conv.packed(), desc, y, scale=scale, shift=shift)
+        return F.reflect_halo(y, T_out, pl, pr)
+    z = torch.empty((B, T_out, Co), dtype=torch.bfloat16, device=xin.device)
+    desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
+    F.conv1d_fwd(xin, conv.packed(), desc, z)
+    return F.bn_act_pad(z, scale, shift, B, T_out, Co, pl, pr, geo["act"], 0.0, 0, lens, res=None if res is None else res[0],
+                        res_scale=None if res is None else res[1][0], res_shift=None if res is None else res[1][1])

@@ -1,0 +1,126 @@
+"""NovoGrad with the reference's constructor and update rule (novograd.py:12-114), executed as ONE fused
+multi-tensor CUDA step (csrc/novograd.cu) instead of ~8 elementwise kernels plus a host sync per parameter:
+
+    v_t   = ||g||^2                       if v == 0 else  b2*v + (1-b2)*||g||^2      (per tensor)
+    g'    = g / (sqrt(v_t) + eps) + wd*p  [* (1-b1) when grad_averaging]
+    m_t   = b1*m + g'
+    p    -= lr * m_t
+
+The same pass refreshes the bf16 weight shadow the conv kernels read (see ``attach_model``)."""
+import torch
+from torch.optim import Optimizer
+
+from . import _lib
+from . import functional as F
+
+
+class Novograd(Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.95, 0), eps=1e-8, weight_decay=0, grad_averaging=False, amsgrad=False):
+        if not 0.0 <= lr:
+            raise ValueError("Invalid learning rate: {}".format(lr))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {}".format(eps))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
+        if amsgrad:
+            raise NotImplementedError("amsgrad is not implemented by the fused NovoGrad step")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay,
+                                      grad_averaging=grad_averaging, amsgrad=amsgrad))
+        self._conv_of = {}         # id(weight param) -> ConvParams module (bf16 shadow owner)
+        self._plans = {}
+
+    def attach_model(self, model):
+        """Lets the step refresh each conv layer's packed bf16 weights in the same pass."""
+        from .layers import ConvParams
+        for m in model.modules():
+            if isinstance(m, ConvParams):
+                self._conv_of[id(m.weight)] = m
+        self._plans.clear()
+        return self
+
+    def _plan(self, gi, params):
+        key = (gi, tuple(id(p) for p in params))
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        dev = params[0].device
+        n = len(params)
+        v = torch.zeros(n, dtype=torch.float32, device=dev)
+        shadows, convs = [], []
+        for i, p in enumerate(params):
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            elif "exp_avg_sq" in st:
+                v[i] = st["exp_avg_sq"]
+            st["exp_avg_sq"] = v[i]                      # 0-dim view, as in the reference's state layout
+            conv = self._conv_of.get(id(p))
+            if conv is not None and conv.cout_pad == conv.out_channels:
+                shadows.append(conv.packed().data_ptr())
+                convs.append(conv)
+            else:
+                shadows.append(0)
+                if conv is not None:
+                    convs.append(None)
+        # pointer table rows: params, grads (rewritten every step), exp_avg, bf16 shadows, numel.  The pinned host
+        # copies rotate so that a CPU running ahead of the GPU never overwrites a table still waiting to be uploaded.
+        hosts = []
+        for _ in range(4):
+            host = torch.empty((5, n), dtype=torch.int64).pin_memory()
+            host[0] = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64)
+            host[2] = torch.tensor([self.state[p]["exp_avg"].data_ptr() for p in params], dtype=torch.int64)
+            host[3] = torch.tensor(shadows, dtype=torch.int64)
+            host[4] = torch.tensor([p.numel() for p in params], dtype=torch.int64)
+            hosts.append([host, None])
+        plan = dict(hosts=hosts, turn=0, dev=torch.empty((5, n), dtype=torch.int64, device=dev), v=v,
+                    ws=torch.empty(n, dtype=torch.float32, device=dev), convs=[c for c in convs if c is not None])
+        self._plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            params = [p for p in group["params"] if p.grad is not None]
+            if not params:
+                continue
+            grads = []
+            for p in params:
+                if not p.is_cuda:
+                    raise RuntimeError("Novograd (fused): CUDA parameters required")
+                g = p.grad
+                if g.is_sparse:
+                    raise RuntimeError("Sparse gradients are not supported.")
+                if g.dtype != torch.float32 or g.stride() != p.stride():
+                    g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
+                grads.append(g)
+            plan = self._plan(gi, params)
+            dev = plan["dev"]
+            slot = plan["hosts"][plan["turn"] % len(plan["hosts"])]
+            plan["turn"] += 1
+            if slot[1] is not None:
+                slot[1].synchronize()
+            slot[0][1] = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64)
+            dev.copy_(slot[0], non_blocking=True)
+            slot[1] = torch.cuda.Event()
+            slot[1].record()
+            b1, b2 = group["betas"]
+            P = F._ptr
+            with torch.cuda.device(dev.device):
+                _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]), P(dev[3]), P(dev[4]), len(params),
+                                                 float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                 float(group["weight_decay"]), int(bool(group["grad_averaging"])), P(plan["ws"]),
+                                                 F._stream()), "novograd_step")
+            for p in params:
+                self.state[p]["step"] += 1
+                torch.autograd.graph.increment_version(p)
+            for conv in plan["convs"]:
+                conv.mark_shadow_fresh()
+        return loss
