@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Wav2Letter train step on B200 (the metric BASELINE.json names).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
+
+A "step" is one full training step of Wav2Letter through the reference-shaped API: ``training_step`` (forward over
+the conv stack, CTC loss, greedy decode + WER/CER as base_asr_models.py:78-85 does every step), ``backward`` and
+``Novograd.step`` -- on a synthetic collated batch (B=64 utterances of 15 s per GPU, 64 mel bins, 225 labels each).
+
+Prints ONE JSON line (rank 0): value = audio-seconds/second with inputs resident in HBM, timed with CUDA events
+(max over ranks); e2e = same with pinned-host inputs copied in and the loss read back each step; roofline = the
+conv implicit-GEMM kernels' achieved TFLOP/s (algorithmic FLOPs / CUDA-event time of those launches inside the timed
+region) against the measured bf16 peak; cpu_baseline = the oracle port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UTT_SEC = 15
+BATCH = 64
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def conv_flops_per_utt(specs, t_in):
+    """2*T_out*Cout*Cin*k per conv per pass; fwd + wgrad for every layer, dgrad for all but the first."""
+    fwd, total, t = 0.0, 0.0, t_in
+    for i, s in enumerate(specs):
+        from oracle.w2l_oracle import reflect_pad_amounts
+        pl, pr = reflect_pad_amounts(s["cin"], s["k"], s["stride"], s["dilation"])
+        t = (t + pl + pr - s["dilation"] * (s["k"] - 1) - 1) // s["stride"] + 1
+        f = 2.0 * t * s["cout"] * s["cin"] * s["k"]
+        fwd += f
+        total += f * (2 if i == 0 else 3)
+    return fwd, total
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def synthetic_batch(B, seconds, seed):
+    from oracle.w2l_oracle import ENGLISH_LOWERCASE
+    g = torch.Generator().manual_seed(seed)
+    T, S = 1 + 100 * seconds, 15 * seconds
+    x = torch.randn(B, 64, T, generator=g)
+    tg = torch.randint(1, 29, (B, S), generator=g, dtype=torch.int32)
+    il = torch.full((B,), T, dtype=torch.int32)
+    tl = torch.full((B,), S, dtype=torch.int32)
+    texts = ["".join(ENGLISH_LOWERCASE[c] for c in row.tolist()) for row in tg]
+    return x, il, tg, tl, texts
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_train_step_factory(mid_layers, B, seconds, seed=0):
+    """The reference's CPU path restated (oracle/w2l_oracle.py): fwd + CTC + greedy decode + backward + NovoGrad."""
+    from oracle import w2l_oracle as O
+    specs = O.w2l_layer_specs(mid_layers)
+    sd = O.w2l_init_state_dict(specs, seed=seed)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    for k in names:
+        sd[k].requires_grad_(True)
+    x, il, tg, tl, texts = synthetic_batch(B, seconds, seed)
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)
+    state = [{} for _ in names]
+
+    def step():
+        lp, ol = O.w2l_forward(x, il, sd, specs, training=True)
+        loss = crit(lp.transpose(0, 1), tg, ol, tl)
+        am = lp.detach().argmax(-1).numpy()                       # torch.max(probs, 2), decoder.py:136
+        O.greedy_collapse(am, ol.numpy())                         # the per-frame Python loop, decoder.py:104-119
+        grads = torch.autograd.grad(loss, [sd[k] for k in names])
+        with torch.no_grad():
+            O.novograd_step([sd[k] for k in names], list(grads), state, lr=1e-3, weight_decay=1e-3)
+        return float(loss)
+
+    return step
+
+
+def run_cpu_arm(args, as_reference):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_batch
+    step = cpu_train_step_factory(args.mid_layers, B, UTT_SEC)
+    for _ in range(args.warmup if as_reference else 0):
+        step()
+    n = args.steps if as_reference else 1
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    value = B * UTT_SEC / dt
+    sample = "oracle port (torch CPU fp32 + Python greedy loop): Wav2Letter mid_layers=%d train step, B=%d x %d s" % (args.mid_layers, B, UTT_SEC)
+    return dict(value=value, unit="audio-s/s", cores=cores, kind="port", sample=sample, ms_per_step=dt * 1e3)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class KernelTimer:
+    """CUDA-event timing of individual library calls on the launching stream (recorded inside the timed region)."""
+
+    def __init__(self):
+        self.spans = []
+
+    def wrap(self, F, names):
+        self._orig = {n: getattr(F, n) for n in names}
+        for n in names:
+            def make(fn, tag):
+                def timed(*a, **k):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = fn(*a, **k)
+                    e1.record()
+                    self.spans.append((tag, e0, e1))
+                    return r
+                return timed
+            setattr(F, n, make(self._orig[n], n))
+        self._F = F
+
+    def unwrap(self):
+        for n, fn in self._orig.items():
+            setattr(self._F, n, fn)
+
+    def totals_ms(self):
+        out = {}
+        for tag, e0, e1 in self.spans:
+            out[tag] = out.get(tag, 0.0) + e0.elapsed_time(e1)
+        return out
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200 import _lib, config
+    from wav2letter_pytorch_b200 import functional as F
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def build(mid_layers):
+        cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers, "optimizer=novograd"]).model
+        torch.manual_seed(0)
+        model = Wav2Letter(cfg).to(dev).train()
+        (opt,), _ = model.configure_optimizers()
+        reducer = None
+        if world > 1:
+            from wav2letter_pytorch_b200.distributed import GradientReducer
+            reducer = GradientReducer(model)
+        return model, opt, reducer
+
+    x, il, tg, tl, texts = synthetic_batch(BATCH, UTT_SEC, seed=rank)
+    host = [t.pin_memory() for t in (x, il, tg, tl)]
+    resident = tuple(t.to(dev) for t in host)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+
+    def one_step(model, opt, reducer, batch, it):
+        opt.zero_grad(set_to_none=True)
+        loss = model.training_step(batch + (None, texts), it)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(model, opt, reducer, steps, warmup, from_host):
+        def batch():
+            return tuple(t.to(dev, non_blocking=True) for t in host) if from_host else resident
+        for it in range(warmup):
+            l = one_step(model, opt, reducer, batch(), it)
+            if from_host:
+                l.item()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(steps):
+            l = one_step(model, opt, reducer, batch(), it)
+            if from_host:
+                l.item()                                  # device->host read of the step's loss
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    model, opt, reducer = build(args.mid_layers)
+    specs = O.w2l_layer_specs(args.mid_layers)
+    fwd_flops, train_flops = conv_flops_per_utt(specs, 1 + 100 * UTT_SEC)
+
+    # ---- device-resident throughput (the headline `value`), conv kernels timed live with CUDA events
+    timer = KernelTimer()
+    sampler = ClockSampler(local)
+    timed(model, opt, reducer, 0, args.warmup, False)
+    timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_wgrad"])
+    launches0 = _lib.launch_count()
+    if rank == 0:
+        sampler.start()
+    ms = timed(model, opt, reducer, args.steps, 0, False)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    timer.unwrap()
+    conv_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
+    # ---- end to end: pinned host inputs in, loss out, every step
+    ms_e2e = timed(model, opt, reducer, args.steps, 1, True)
+
+    # ---- the literal default config (mid_layers=1), reported beside the full stack
+    extra = None
+    if args.mid_layers != 1 and not args.skip_default:
+        del model, opt, reducer
+        torch.cuda.empty_cache()
+        m1, o1, r1 = build(1)
+        ms1 = timed(m1, o1, r1, max(args.steps, 10), max(args.warmup, 3), False)
+        extra = {"workload": "Wav2Letter mid_layers=1 (literal yaml default) train step, B=%d/GPU x %d s" % (BATCH, UTT_SEC),
+                 "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s"}
+        del m1, o1, r1
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    conv_total_ms = sum(conv_ms.values())
+    achieved = train_flops * BATCH / (conv_total_ms / 1e3) / 1e12 if conv_total_ms > 0 else 0.0
+    value = world * BATCH * UTT_SEC / (ms / 1e3)
+    line = {
+        "metric": "audio-sec/sec per train step", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Wav2Letter mid_layers=%d (full layers: list of the default yaml) train step: fwd+CTC+greedy decode+bwd+NovoGrad, "
+                               "B=%d/GPU x %d s utterances, 64 mel bins, 225 labels" % (args.mid_layers, BATCH, UTT_SEC),
+                   "global_batch": world * BATCH, "parallelism": "dp%d" % world,
+                   "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<fwd|dgrad|wgrad> (tcgen05 implicit GEMM)", "achieved": achieved,
+                     "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained", "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                     "flops_per_step": train_flops * BATCH, "kernel_ms_per_step": conv_total_ms, "by_pass_ms": conv_ms,
+                     "share_of_step": conv_total_ms / ms},
+    }
+    if extra:
+        line["default_config"] = extra
+    if world == 1 and not args.skip_cpu:
+        line["cpu_baseline"] = run_cpu_arm(args, as_reference=False)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mid-layers", dest="mid_layers", type=int, default=20)
+    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4, help="utterances in the bounded CPU sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-default", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = run_cpu_arm(args, as_reference=True)
+        line = {"impl": "reference", "metric": "audio-sec/sec per train step", "value": r["value"], "unit": "audio-s/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "Wav2Letter mid_layers=%d train step on the host CPU (bounded sample B=%d x %d s)"
+                                       % (args.mid_layers, args.cpu_batch, UTT_SEC)},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,10 @@ const char* w2l_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t w2l_launch_count(void);
 
+/* Host-side Levenshtein distance between two int32 symbol sequences (HOST pointers).  Replaces the
+ * python-Levenshtein calls behind Decoder.wer / Decoder.cer (decoder.py:31-60).  Returns -1 on bad input. */
+int64_t w2l_edit_distance_host(const int32_t* a_host, int64_t n, const int32_t* b_host, int64_t m);
+
 /* ---------------------------------------------------------------------------------------------
  * Greedy CTC decoding.  Replaces GreedyDecoder.decode -> torch.max(probs, 2) + the per-frame Python
  * loop of process_string (decoder.py:104-119, 121-145).

@@ -405,3 +405,69 @@ def synthetic_batch(B, seconds, seed=0, n_labels=29, ragged=False, feat=64):
         il = torch.full((B,), T, dtype=torch.int32)
         tl = torch.full((B,), S, dtype=torch.int32)
     return x, il, targets, tl
+
+
+# --------------------------------------------------------------------------------------------
+# The same Wav2Letter forward with the implementation's STATED storage precision emulated on the CPU:
+# bf16 operands / fp32 accumulation, activations and activation-gradients stored as bf16 (DESIGN.md "precision").
+# Used as the fairness yard-stick next to the fp32 oracle: a CUDA result must match this tightly, and may differ
+# from the fp32 reference only by about as much as this emulation itself does.
+# --------------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    """value and gradient both pass through a bf16 store"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundGradBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _bf16_weight(w):
+    return w + (w.to(torch.bfloat16).to(w.dtype) - w).detach()       # bf16 shadow forward, fp32 master gradient
+
+
+def w2l_forward_bf16emu(x, input_lengths, sd, specs, training=True):
+    h = x.to(torch.bfloat16).float()
+    for i, spec in enumerate(specs):
+        p = "conv1ds.conv1d_%d." % i
+        pl, pr = reflect_pad_amounts(spec["cin"], spec["k"], spec["stride"], spec["dilation"])
+        if i == 0 and pl + pr > 0:
+            h = F.pad(h, (pl, pr), mode="reflect")
+        w = _bf16_weight(sd[p + "conv1.weight"])
+        if not spec["bn"]:
+            z = F.conv1d(h, w, sd[p + "conv1.bias"], stride=spec["stride"], dilation=spec["dilation"])
+            z = _RoundGradBF16.apply(z)
+            h = z
+            continue
+        z = _RoundBF16.apply(F.conv1d(h, w, None, stride=spec["stride"], dilation=spec["dilation"]))
+        if training:
+            mean = z.mean((0, 2), keepdim=True)
+            var = z.var((0, 2), unbiased=False, keepdim=True)
+        else:
+            mean = (sd[p + "batch_norm.running_mean"] - sd[p + "conv1.bias"]).view(1, -1, 1)
+            var = sd[p + "batch_norm.running_var"].view(1, -1, 1)
+        y = (z - mean) * torch.rsqrt(var + 1e-3) * sd[p + "batch_norm.weight"].view(1, -1, 1) + sd[p + "batch_norm.bias"].view(1, -1, 1)
+        if spec["act"]:
+            y = torch.clamp(y, 0, 20)
+        if i + 1 < len(specs):
+            nxt = specs[i + 1]
+            npl, npr = reflect_pad_amounts(nxt["cin"], nxt["k"], nxt["stride"], nxt["dilation"])
+            if npl + npr > 0:
+                y = F.pad(y, (npl, npr), mode="reflect")
+        h = _RoundBF16.apply(y)
+    lp = F.log_softmax(h.transpose(1, 2), dim=-1)
+    scaling = int(np.prod([s["stride"] for s in specs]))
+    return lp, (None if input_lengths is None else input_lengths // scaling)

@@ -98,3 +98,34 @@ int w2l_version(void) { return 100; }
 const char* w2l_last_error(void) { return w2l::g_err; }
 int64_t w2l_launch_count(void) { return w2l::g_launches.load(); }
 }
+
+// ---------------------------------------------------------------- host-side Levenshtein (WER/CER bookkeeping)
+// The reference scores every training step's transcripts with the python-Levenshtein C extension
+// (decoder.py:31-66, base_asr_models.py:58-69); this is the same dynamic programme over int32 symbol ids.
+extern "C" int64_t w2l_edit_distance_host(const int32_t* a, int64_t n, const int32_t* b, int64_t m) {
+  if (n < 0 || m < 0 || (n && !a) || (m && !b)) return -1;
+  if (n < m) {
+    const int32_t* t = a; a = b; b = t;
+    int64_t q = n; n = m; m = q;
+  }
+  if (m == 0) return n;
+  int64_t stack_row[1024];
+  int64_t* row = m + 1 <= 1024 ? stack_row : new int64_t[m + 1];
+  for (int64_t j = 0; j <= m; ++j) row[j] = j;
+  for (int64_t i = 1; i <= n; ++i) {
+    int64_t diag = row[0];
+    row[0] = i;
+    const int32_t ai = a[i - 1];
+    for (int64_t j = 1; j <= m; ++j) {
+      const int64_t up = row[j];
+      int64_t best = diag + (ai != b[j - 1]);
+      if (up + 1 < best) best = up + 1;
+      if (row[j - 1] + 1 < best) best = row[j - 1] + 1;
+      row[j] = best;
+      diag = up;
+    }
+  }
+  const int64_t r = row[m];
+  if (row != stack_row) delete[] row;
+  return r;
+}

@@ -11,16 +11,20 @@ from . import label_sets
 
 
 def _edit_distance(a, b):
-    """Levenshtein distance between two sequences (the reference uses the python-Levenshtein C extension)."""
-    if len(a) < len(b):
-        a, b = b, a
-    prev = list(range(len(b) + 1))
-    for i, ca in enumerate(a, 1):
-        cur = [i] + [0] * len(b)
-        for j, cb in enumerate(b, 1):
-            cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb))
-        prev = cur
-    return prev[-1]
+    """Levenshtein distance between two sequences of hashable symbols (characters or words), computed by the
+    library's host routine (the reference uses the python-Levenshtein C extension, decoder.py:31-60)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    ids = {}
+    ia = np.fromiter((ids.setdefault(s, len(ids)) for s in a), dtype=np.int32, count=len(a))
+    ib = np.fromiter((ids.setdefault(s, len(ids)) for s in b), dtype=np.int32, count=len(b))
+    d = _lib.load().w2l_edit_distance_host(ia.ctypes.data_as(ctypes.c_void_p), len(ia), ib.ctypes.data_as(ctypes.c_void_p), len(ib))
+    if d < 0:
+        raise RuntimeError("w2l_edit_distance_host failed")
+    return int(d)
 
 
 class Decoder(object):
