@@ -235,6 +235,8 @@ def run_gpu_arm(args):
             if from_host:
                 l.item()
         barrier()
+        if steps == 0:
+            return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for it in range(steps):

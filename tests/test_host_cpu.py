@@ -1,0 +1,214 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares, argument validation works
+without a GPU, the host-side mirror of the reference interface behaves like the reference (config composition, label
+tables, padding rule, parameter layout, state_dict contract, error behaviour), and the data-parallel reducer is
+exercised with world_size=2 over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from wav2letter_pytorch_b200 import _lib
+    _lib.build()
+    return _lib.load()
+
+
+def test_abi_exports_every_declared_symbol(lib):
+    from wav2letter_pytorch_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "w2l_sm100.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(w2l_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "missing export: %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.w2l_version() >= 100
+    assert lib.w2l_launch_count() == 0                      # nothing computes on the CPU box
+
+
+def test_abi_argument_validation_without_gpu(lib):
+    from wav2letter_pytorch_b200 import _lib
+    from wav2letter_pytorch_b200._lib import ConvDesc
+    d = ConvDesc(2, 100, 60, 64, 64, 3, 1, 100, 0, 100, 0, 64, 0, 0)       # Cin = 60 < 64
+    buf = ctypes.c_void_p(0x1000)
+    rc = lib.w2l_conv1d_fwd(buf, buf, None, None, None, buf, ctypes.byref(d), None)
+    assert rc == 1 and b"Cin" in lib.w2l_last_error()
+    assert lib.w2l_conv1d_fwd(buf, buf, None, None, None, buf, None, None) == 1
+    assert lib.w2l_greedy_decode(None, 2, 10, 29, 290, 29, None, 0, None, None, None, None, None, 0, None) == 1
+    assert lib.w2l_ctc_loss(buf, 0, 2, 10, 500, 5000, 500, buf, 4, buf, buf, 0, 1, 1, None, None, None, buf, 1 << 20, None) == 1
+    assert lib.w2l_ctc_loss_workspace_bytes(64, 750, 225) > 64 * 750 * 451 * 4
+    assert lib.w2l_ctc_loss_workspace_bytes(1, 10, 100000) == 0          # lattice too long -> unsupported
+    assert lib.w2l_greedy_decode_workspace_bytes(64, 750) == 64 * 3 * 4
+    with pytest.raises(_lib.W2LError):
+        _lib.check(1, "probe")
+    # host Levenshtein
+    a = np.array([1, 2, 3, 4], dtype=np.int32)
+    b = np.array([1, 3, 4, 5, 6], dtype=np.int32)
+    P = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    assert lib.w2l_edit_distance_host(P(a), 4, P(b), 5) == 3
+    assert lib.w2l_edit_distance_host(P(a), 0, P(b), 5) == 5
+
+
+def test_no_cpu_fallback():
+    from wav2letter_pytorch_b200 import config, functional as F
+    from wav2letter_pytorch_b200.ctc_loss import CTCLoss
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    with pytest.raises(RuntimeError):
+        F.greedy_decode(torch.rand(1, 4, 5))
+    with pytest.raises(RuntimeError):
+        CTCLoss(zero_infinity=True)(torch.randn(5, 1, 4).log_softmax(-1), torch.ones(1, 2, dtype=torch.int32), torch.tensor([5]), torch.tensor([2]))
+    model = Wav2Letter(config.compose().model)
+    with pytest.raises(RuntimeError):
+        model(torch.randn(1, 64, 50), torch.tensor([50]))
+    src = "".join(open(os.path.join(ROOT, "wav2letter_pytorch_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "wav2letter_pytorch_b200"))
+                  if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle/", "")          # the product never imports the checker
+
+
+def test_config_compose_and_labels():
+    from wav2letter_pytorch_b200 import config, label_sets
+    cfg = config.compose()
+    assert cfg.model.name == "wav2letter" and cfg.model.mid_layers == 1 and len(cfg.model.layers) == 20
+    assert cfg.model.input_size == 64 and cfg.data.mel_spec == 64 and cfg.data.audio_conf == cfg.model.audio_conf
+    assert cfg.model.labels == label_sets.english_lowercase_labels and len(cfg.model.labels) == 29
+    assert cfg.model.labels[0] == "_" and cfg.model.labels[28] == " " and cfg.model.labels[1] == "'"
+    assert cfg.model.decoder["_target_"] == "decoder.GreedyDecoder" and cfg.model.decoder.labels == cfg.model.labels
+    assert cfg.model.optimizer["_target_"] == "torch.optim.SGD" and cfg.model.optimizer.nesterov is True
+    j = config.compose(overrides=["model=jasper", "model.mid_layers=15", "trainer.gpus=8"])
+    assert j.model.name == "jasper" and len(j.model.jasper_blocks) == 15 and j.trainer.gpus == 8
+    assert [b.kernel_size for b in j.model.jasper_blocks][:5] == [32, 32, 32, 32, 38]
+    j10 = config.compose(overrides=["model=jasper10x5", "optimizer=novograd"])
+    assert sum(b.get("repeat", 1) for b in j10.model.jasper_blocks) == 53 and j10.model.optimizer["_target_"] == "novograd.Novograd"
+    assert len(label_sets.hebrew_labels) == 29 and len(label_sets.english_labels) == 29
+    dec = config.instantiate(cfg.model.decoder)
+    assert type(dec).__name__ == "GreedyDecoder" and dec.space_index == 28 and dec.blank_index == 0
+
+
+def test_padding_rule_and_model_contract():
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.wav2letter import Conv1dBlock, Wav2Letter, reflect_padding
+    # SURVEY 8a-1 table
+    assert reflect_padding(64, 11, 2, 1) == (4, 5) and reflect_padding(256, 11, 1, 1) == (5, 5)
+    assert reflect_padding(768, 29, 1, 2) == (28, 28) and reflect_padding(896, 1, 1, 1) == (0, 0)
+    for cin in (33, 64, 161):
+        for k in (1, 4, 11):
+            for s in (1, 2, 3):
+                for d in (1, 2):
+                    assert reflect_padding(cin, k, s, d) == O.reflect_pad_amounts(cin, k, s, d)
+    model = Wav2Letter(config.compose(overrides=["model.mid_layers=20"]).model)
+    assert sum(p.numel() for p in model.parameters()) == 153074845              # SURVEY section 0.1 [probe]
+    assert model.scaling_factor == 2
+    il = torch.tensor([1001, 800], dtype=torch.int32)
+    out_len = model.compute_output_lengths(il)
+    assert out_len.tolist() == [500, 400] and out_len.dtype == torch.int32
+    keys = list(model.state_dict().keys())
+    assert keys[0] == "conv1ds.conv1d_0.conv1.weight" and "conv1ds.conv1d_20.conv1.bias" in keys
+    assert "conv1ds.conv1d_19.batch_norm.num_batches_tracked" in keys and "conv1ds.conv1d_20.batch_norm.weight" not in keys
+    blk = model.conv1ds.conv1d_16
+    assert blk.conv1.weight.shape == (896, 768, 29) and blk.pad_lr == (28, 28) and blk.batch_norm.momentum == 0.9
+    assert model.conv1ds.conv1d_15.next_pad == (28, 28) and model.conv1ds.conv1d_19.next_pad == (0, 0)
+    assert Wav2Letter(config.compose().model).conv1ds.conv1d_1.conv1.out_channels == 29         # literal default: 1 block + head
+    with pytest.raises(ValueError):
+        Conv1dBlock(64, 100, (3,), 1)
+
+
+def test_conv_params_layout_roundtrip():
+    from wav2letter_pytorch_b200.layers import ConvParams
+    torch.manual_seed(0)
+    ref = torch.nn.Conv1d(8, 16, 5)
+    torch.manual_seed(0)
+    for unfold in (False, True):
+        torch.manual_seed(0)
+        c = ConvParams(8, 16, 5, stride=2 if unfold else 1, unfold=unfold)
+        assert torch.equal(c.weight.detach(), ref.weight.detach()) and torch.equal(c.bias.detach(), ref.bias.detach())   # same init stream
+        st = c.storage()
+        assert st.is_contiguous() and st.data_ptr() == c.weight.data_ptr()
+        if unfold:
+            assert st.shape == (1, 16, 40) and torch.equal(st[0].view(16, 5, 8).permute(0, 2, 1), c.weight.detach())
+        else:
+            assert st.shape == (5, 16, 8) and torch.equal(st.permute(1, 2, 0), c.weight.detach())
+        dw = torch.randn_like(st)
+        gv = c.grad_view(dw)
+        assert gv.shape == c.weight.shape and gv.stride() == c.weight.stride()
+        w2 = torch.randn(16, 8, 5)
+        c.load_state_dict({"weight": w2, "bias": torch.zeros(16)})
+        assert torch.equal(c.weight.detach(), w2) and c.storage().data_ptr() == c.weight.data_ptr()
+        import copy
+        c2 = copy.deepcopy(c)
+        assert c2.weight.stride() == c.weight.stride() and c2.storage().is_contiguous()
+    assert ConvParams(64, 29, 1).cout_pad == 64 and ConvParams(64, 896, 3).cout_pad == 896
+
+
+def test_decoder_host_logic():
+    from wav2letter_pytorch_b200.decoder import Decoder, GreedyDecoder, _edit_distance
+    d = Decoder(["_", "a", "b", " "])
+    assert d.int_to_char == {0: "_", 1: "a", 2: "b", 3: " "} and d.space_index == 3
+    assert Decoder(["_", "a"]).space_index == 2                      # no space -> out-of-range index, as the reference
+    assert d.cer("ab ba", "abba") == 0 and d.wer("ab ba", "ab b a") == 2
+    assert d.cer_ratio("a b", "b") == (1, 2) and d.wer_ratio("a b c", "a c") == (1, 3)
+    assert _edit_distance("kitten", "sitting") == 3 and _edit_distance("", "") == 0
+    with pytest.raises(NotImplementedError):
+        d.decode(None)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            GreedyDecoder(["_", "a", "b", " "]).decode(torch.rand(1, 3, 4))
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from wav2letter_pytorch_b200.distributed import GradientReducer, broadcast_buffers, shard_batch, dense_view
+from wav2letter_pytorch_b200.layers import ConvParams, BatchNormParams
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = ConvParams(4, 6, 3)
+        self.bn = BatchNormParams(6)
+net = Net()
+red = GradientReducer(net)
+# a stand-in loss that touches every parameter through its reference-shaped view
+def loss_of(scale):
+    return scale * ((net.conv.weight ** 2).sum() + net.conv.bias.sum() + (net.bn.weight * net.bn.bias).sum() + net.bn.weight.sum())
+loss_of(float(rank + 1)).backward()
+red.finish()
+expect = (1.0 + 2.0) / 2
+assert torch.allclose(net.conv.weight.grad, 2 * expect * net.conv.weight.detach(), atol=1e-6), rank
+assert net.conv.weight.grad.stride() == net.conv.weight.stride()
+assert torch.allclose(net.conv.bias.grad, torch.full((6,), expect))
+assert dense_view(net.conv.weight.grad).is_contiguous()
+net.bn.running_mean.fill_(float(rank + 5))
+broadcast_buffers(net)
+assert float(net.bn.running_mean[0]) == 5.0
+b = shard_batch((torch.arange(8).view(8, 1), torch.arange(8), None), rank, world)
+assert b[1].tolist() == list(range(rank * 4, rank * 4 + 4)) and b[2] is None
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gradient_reducer_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and "rank %d ok" % r in o, o

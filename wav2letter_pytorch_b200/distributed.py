@@ -1,0 +1,74 @@
+"""Data-parallel plumbing: one process per GPU, gradients averaged with NCCL over NVLink, overlapped with backward.
+
+The reference has no distributed code of its own; it delegates to Lightning's DDP (README.md:40, config.yaml:21),
+i.e. bucketed gradient all-reduce (mean) overlapped with backward, per-replica BatchNorm statistics (no SyncBN) and
+rank-0 buffer broadcast.  ``GradientReducer`` gives the same semantics for the modules of this package:
+
+  * every parameter gets a post-accumulate-grad hook; the moment a layer's wgrad kernel has produced the gradient the
+    all-reduce for that tensor is enqueued on NCCL's stream (it waits for the wgrad through a stream event), so the
+    reduction of layer i overlaps the dgrad/wgrad kernels of layers i-1, i-2, ... that are still running;
+  * ``finish()`` makes the compute stream wait for all pending reductions (no host synchronisation) -- call it before
+    ``optimizer.step()``;
+  * conv weights are permuted views over kernel-layout storage; the reducer all-reduces the dense storage view, so no
+    gradient is copied or re-laid-out for the wire.
+"""
+import torch
+import torch.distributed as dist
+
+
+def dense_view(t):
+    """A contiguous view of a dense, non-overlapping tensor (dims sorted by stride) sharing its memory."""
+    if t.is_contiguous():
+        return t
+    order = sorted(range(t.dim()), key=lambda d: t.stride(d), reverse=True)
+    v = t.permute(*order)
+    if not v.is_contiguous():
+        raise RuntimeError("gradient is not a dense tensor; cannot all-reduce in place")
+    return v
+
+
+class GradientReducer:
+    def __init__(self, model, process_group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("GradientReducer needs an initialised torch.distributed process group")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.use_avg = dist.get_backend(process_group) == "nccl"
+        self.pending = []
+        self.hooks = []
+        for p in model.parameters():
+            if p.requires_grad:
+                self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p):
+        g = dense_view(p.grad)
+        if self.use_avg:
+            work = dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:                       # gloo (CPU tests): sum now, scale in finish()
+            work = dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.pending.append((work, g))
+
+    def finish(self):
+        for work, g in self.pending:
+            work.wait()
+            if not self.use_avg:
+                g.div_(self.world)
+        self.pending.clear()
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks.clear()
+
+
+def broadcast_buffers(model, src=0, process_group=None):
+    """DDP's rank-0 buffer broadcast (BatchNorm running statistics are per-replica during training)."""
+    for b in model.buffers():
+        dist.broadcast(b, src=src, group=process_group)
+
+
+def shard_batch(batch, rank, world):
+    """Utterances [rank*B/W, (rank+1)*B/W) of a collated batch (inputs, input_lengths, targets, target_lengths, paths, texts)."""
+    n = batch[0].shape[0]
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    return tuple(b[lo:hi] if b is not None else None for b in batch)
