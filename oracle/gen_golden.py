@@ -168,6 +168,47 @@ def gen_jasper(ref):
     np.savez_compressed(os.path.join(OUT, "jasper_small.npz"), **_np(out))
 
 
+def gen_jasper_dense(ref):
+    """dense (non-separable) Jasper with masks, a stride-2 prologue, repeats, residuals and a dilated block --
+    the structure of Jasper 10x5 (BASELINE config 3) at toy widths."""
+    torch.manual_seed(4)
+    import json
+    blocks = [dict(layer_size=64, kernel_size=10, stride=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=64, kernel_size=5, stride=1, residual=True, separable=False, repeat=3),
+              dict(layer_size=128, kernel_size=6, stride=1, residual=True, separable=False, repeat=2),
+              dict(layer_size=128, kernel_size=3, stride=1, dilation=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=64, kernel_size=1, stride=1, residual=False, separable=False, repeat=1)]
+    cfg = rl.reference_model_cfg("jasper", mid_layers=5, dropout=0, jasper_blocks=blocks)
+    model = ref.jasper.Jasper(cfg)
+    out = {"blocks_json": np.array(json.dumps(blocks))}
+    # a few tensors of the freshly constructed model, to check seeded-init parity (torch.manual_seed(4))
+    out.update({k: v for k, v in _sd(model, "sd_init:").items()
+                if any(t in k for t in ("encoder.0.mconv.0", "encoder.2.res.0.0", "encoder.1.mconv.8", "final_layer"))})
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 64, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 20), dtype=torch.int32)
+    tl = torch.tensor([20, 12, 7], dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+        x[n, :, il[n]:] = 0
+    out.update({"x": x, "il": il, "tg": tg, "tl": tl})
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update({k: v for k, v in _sd(model, "sd1:").items() if "running" in k or "num_batches" in k})
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    np.savez_compressed(os.path.join(OUT, "jasper_dense.npz"), **_np(out))
+
+
 def gen_ctc(ref):
     g = torch.Generator().manual_seed(5)
     crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)    # base_asr_models.py:23
@@ -225,6 +266,7 @@ def main():
     gen_conv_block(ref)
     gen_w2l(ref)
     gen_jasper(ref)
+    gen_jasper_dense(ref)
     gen_ctc(ref)
     gen_novograd(ref)
     for f in sorted(os.listdir(OUT)):

@@ -214,3 +214,42 @@ def test_training_step_end_to_end(pkg):
     assert set(model.logged) == {"train_loss", "learning_rate", "train_cer", "train_wer", "train_len_ratio"}
     conv = model.conv1ds.conv1d_1.conv1
     assert torch.equal(conv.packed().float(), conv.storage().to(torch.bfloat16).float())
+
+
+def test_jasper_dense_golden(pkg, golden):
+    """Jasper with masks, stride-2 prologue, repeats, residual 1x1+BN branches, dilation, unmasked head, softmax in eval."""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    g = golden("jasper_dense")
+    blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=5"]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    torch.manual_seed(4)
+    model = Jasper(cfg)
+    for k in g.files:                                                   # seeded construction == the reference's
+        if k.startswith("sd_init:"):
+            assert np.array_equal(model.state_dict()[k[8:]].numpy(), g[k]), k
+    assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0:"))
+    _load_sd(model, g, "sd0:")
+    model.cuda().train()
+    x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
+    tg, tl = torch.from_numpy(g["tg"]).cuda(), torch.from_numpy(g["tl"]).cuda()
+    out, ol = model(x, il)
+    assert np.array_equal(ol.cpu().numpy(), g["train:out_len"]) and ol.dtype == torch.int64
+    assert rel_l2(out.detach(), g["train:out"]) < 2e-2
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    assert abs(loss.item() - float(g["train:loss"])) < 2e-2 * abs(float(g["train:loss"]))
+    loss.backward()
+    for name, p in model.named_parameters():
+        ref = torch.from_numpy(g["train:grad:" + name])
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        gcpu = p.grad.cpu()
+        cos = float((gcpu.double().flatten() @ ref.double().flatten()) / (gcpu.double().norm() * ref.double().norm() + 1e-30))
+        assert cos > 0.985 and rel_l2(gcpu, ref) < 0.2, (name, cos, rel_l2(gcpu, ref))     # bf16 storage, see the W2L test
+    for k in g.files:
+        if k.startswith("sd1:") and "running" in k:
+            np.testing.assert_allclose(model.state_dict()[k[4:]].cpu().numpy(), g[k], rtol=2e-2, atol=2e-3, err_msg=k)
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    assert rel_l2(o, g["eval:out"]) < 2e-2 and abs(float(o.sum(-1).mean()) - 1.0) < 1e-5    # probabilities in eval

@@ -38,7 +38,8 @@ class ConvCTCASR(_Base):
     def create_example_input_array(self):
         """(features [4, input_size, 200], lengths [4]) -- what Lightning uses for its model summary."""
         n, lo, hi = 4, 100, 200
-        return torch.rand(n, self._cfg.input_size, hi), torch.randint(lo, hi, (n,))
+        lengths = torch.randint(lo, hi, (n,))            # drawn first, like the reference, so seeded inits line up
+        return torch.rand(n, self._cfg.input_size, hi), lengths
 
     # ---- length bookkeeping: subclasses define scaling_factor (product of the strides)
     @property

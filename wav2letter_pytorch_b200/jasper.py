@@ -1,0 +1,234 @@
+"""Jasper with the reference's constructor / forward / state_dict surface (jasper.py:22-475) on the sm_100a kernels.
+
+What ``Jasper._build_encoder`` can reach (jasper.py:436-453) is supported: batch normalisation, ReLU, 'add' residual
+through a 1x1 conv + BN, groups=1, length masking, ``repeat`` sub-blocks, dense convolutions.  Time-major execution:
+
+  * masked_fill(t >= len, 0) before every MaskedConv1d (jasper.py:116-119) is folded into the PRODUCER's fused
+    BN/ReLU pass (rows past the utterance are written as zeros), and into the unfold pass for the raw features;
+  * 'same' zero padding (jasper.py:61-66) costs nothing: the conv kernel starts its taps at row -p and TMA zero-fills
+    rows outside the tensor;
+  * conv -> BN -> (+ BN(conv1x1(block input))) -> ReLU -> dropout is one GEMM plus one fused elementwise pass
+    (two GEMMs with a residual), instead of the reference's 8-10 separate library kernels per sub-block.
+
+Not implemented (raise NotImplementedError at construction): separable/depthwise sub-blocks (the shipped
+model/jasper.yaml), group/instance/layer norm, groups > 1, heads, residual_mode='max', dense residuals."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from .base_asr_models import ConvCTCASR
+from .layers import BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, ResidualBranchFn, conv_bn_act_eval, conv_desc
+
+jasper_activations = {"hardtanh": nn.Hardtanh, "relu": nn.ReLU, "selu": nn.SELU}
+
+
+def compute_new_kernel_size(kernel_size, kernel_width):
+    """jasper.py:53-58: scale, then bump even sizes to the next odd one."""
+    k = max(int(kernel_size * kernel_width), 1)
+    return k + 1 if k % 2 == 0 else k
+
+
+def get_same_padding(kernel_size, stride, dilation):
+    """jasper.py:61-66."""
+    if stride > 1 and dilation > 1:
+        raise ValueError("Only stride OR dilation may be greater than 1")
+    if dilation > 1:
+        return (dilation * kernel_size) // 2 - 1
+    return kernel_size // 2
+
+
+def init_weights(m, mode="xavier_uniform"):
+    """jasper.py:29-50 applied to this package's parameter containers (same RNG consumption: the values are drawn
+    into a reference-shaped contiguous tensor and copied into the kernel-layout storage)."""
+    if isinstance(m, MaskedConv1d):
+        init_weights(m.conv, mode)
+    if isinstance(m, ConvParams):
+        w = torch.empty(m.out_channels, m.in_channels, m.kernel_size[0])
+        if mode == "xavier_uniform":
+            nn.init.xavier_uniform_(w, gain=1.0)
+        elif mode == "xavier_normal":
+            nn.init.xavier_normal_(w, gain=1.0)
+        elif mode == "kaiming_uniform":
+            nn.init.kaiming_uniform_(w, nonlinearity="relu")
+        elif mode == "kaiming_normal":
+            nn.init.kaiming_normal_(w, nonlinearity="relu")
+        else:
+            raise ValueError("Unknown Initialization mode: {0}".format(mode))
+        with torch.no_grad():
+            m.weight.copy_(w)
+    elif isinstance(m, BatchNormParams):
+        with torch.no_grad():
+            m.running_mean.zero_()
+            m.running_var.fill_(1)
+            m.num_batches_tracked.zero_()
+            m.weight.fill_(1.0)
+            m.bias.zero_()
+
+
+class MaskedConv1d(nn.Module):
+    """Parameter holder with the reference's layout (``.conv.weight``); the masking itself is fused upstream."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, heads=-1, bias=False,
+                 use_mask=True):
+        super().__init__()
+        if not (heads == -1 or groups == in_channels):
+            raise ValueError("Only use heads for depthwise convolutions")
+        if groups != 1 or heads != -1:
+            raise NotImplementedError("grouped / depthwise MaskedConv1d is not implemented on the tensor-core path")
+        self.real_out_channels = out_channels
+        self.conv = ConvParams(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation, bias=bias,
+                               unfold=stride > 1)
+        self.use_mask = use_mask
+        self.heads = heads
+
+    def get_seq_len(self, lens):
+        c = self.conv
+        return (lens + 2 * c.padding[0] - c.dilation[0] * (c.kernel_size[0] - 1) - 1) / c.stride[0] + 1       # true division
+
+
+class JasperBlock(nn.Module):
+    def __init__(self, inplanes, planes, repeat=3, kernel_size=11, kernel_size_factor=1, stride=1, dilation=1, padding="same",
+                 dropout=0, activation=None, residual=True, groups=1, separable=False, heads=-1, normalization="batch",
+                 norm_groups=1, residual_mode="add", residual_panes=[], conv_mask=False):
+        super().__init__()
+        if padding != "same":
+            raise ValueError("currently only 'same' padding is supported")
+        if normalization != "batch":
+            raise NotImplementedError("only batch normalisation is reachable from Jasper._build_encoder and implemented")
+        if separable or groups != 1 or heads != -1:
+            raise NotImplementedError("separable / grouped Jasper sub-blocks need the depthwise kernel (not implemented yet)")
+        if residual_mode != "add" or len(residual_panes) != 0:
+            raise NotImplementedError("only the plain 'add' residual is implemented")
+        if planes % 16 or planes < 64 or (inplanes % 8) or inplanes < 64:
+            raise ValueError("JasperBlock: widths (%d -> %d) must be >= 64, multiples of 8 / 16 for the tensor-core path" % (inplanes, planes))
+        kernel_size = compute_new_kernel_size(kernel_size, float(kernel_size_factor))
+        pad = get_same_padding(kernel_size, stride, dilation)
+        self.conv_mask, self.separable, self.residual_mode = conv_mask, separable, residual_mode
+        self.dropout_p = float(dropout)
+        if activation is None:
+            activation = nn.Hardtanh(min_val=0.0, max_val=20.0)
+        if isinstance(activation, nn.ReLU):
+            self.act = F.ACT_RELU
+        elif isinstance(activation, nn.Hardtanh) and activation.min_val == 0.0 and activation.max_val == 20.0:
+            self.act = F.ACT_CLAMP20
+        else:
+            raise NotImplementedError("activation %r is not implemented in the fused epilogues" % (activation,))
+        # ModuleList positions mirror the reference so that checkpoints load: [conv, bn, act, drop] * (repeat-1) + [conv, bn]
+        mods, cin = [], inplanes
+        for r in range(repeat):
+            mods.append(MaskedConv1d(cin, planes, kernel_size, stride=stride, dilation=dilation, padding=pad, use_mask=conv_mask))
+            mods.append(BatchNormParams(planes, eps=1e-3, momentum=0.1))
+            if r != repeat - 1:
+                mods.extend([type(activation)() if not isinstance(activation, nn.Hardtanh) else nn.Hardtanh(0.0, 20.0), nn.Dropout(p=dropout)])
+            cin = planes
+        self.mconv = nn.ModuleList(mods)
+        self.dense_residual = False
+        if residual:
+            self.res = nn.ModuleList([nn.ModuleList([MaskedConv1d(inplanes, planes, 1, use_mask=conv_mask),
+                                                     BatchNormParams(planes, eps=1e-3, momentum=0.1)])])
+        else:
+            self.res = None
+        self.mout = nn.Sequential(nn.ReLU() if self.act == F.ACT_RELU else nn.Hardtanh(0.0, 20.0), nn.Dropout(p=dropout))
+        self.repeat, self.stride, self.pad = repeat, stride, pad
+
+    def sub_blocks(self):
+        return [(self.mconv[i], self.mconv[i + 1]) for i in range(0, len(self.mconv), 4)]
+
+    def forward_tm(self, h, t, lens, from_ncw, mask_output):
+        """h: NCW fp32 (first block, ``from_ncw``) or time-major bf16 [B, t, C] whose rows >= len are already zero.
+        Returns (time-major bf16 output, t_out, lens_out)."""
+        subs = self.sub_blocks()
+        lens_in = lens
+        if from_ncw:
+            m0 = subs[0][0].conv
+            k, s, d, p = m0.kernel_size[0], m0.stride[0], m0.dilation[0], m0.padding[0]
+            mask = lens.to(torch.int32) if (self.conv_mask and lens is not None) else None
+            if m0.unfold:
+                t_first = (t + 2 * p - d * (k - 1) - 1) // s + 1
+                h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask)        # masked, zero padded, unfolded
+            else:
+                h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask)
+        elif subs[0][0].conv.unfold:
+            raise NotImplementedError("stride > 1 is only supported on the first Jasper block")
+        block_in, res_pair = h, None
+        training = self.training
+        if self.res is not None:
+            rconv, rbn = self.res[0][0].conv, self.res[0][1]
+            if training:
+                res_pair = ResidualBranchFn.apply(block_in, rconv.weight, rbn.weight, rbn.bias, rconv, rbn)
+            else:
+                zr = torch.empty((h.shape[0], t, rconv.out_channels), dtype=torch.bfloat16, device=h.device)
+                F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
+                res_pair = (zr, rbn.eval_scale_shift(None))
+        for r, (mc, bn) in enumerate(subs):
+            conv = mc.conv
+            last = r == len(subs) - 1
+            if conv.unfold:
+                t_out, x_off = h.shape[1], 0
+            else:
+                k, d, p = conv.kernel_size[0], conv.dilation[0], conv.padding[0]
+                t_out, x_off = t + 2 * p - d * (k - 1), -p
+            if self.conv_mask and lens is not None:
+                lens = mc.get_seq_len(lens.to(dtype=torch.long))                 # float after true division, as the reference
+            out_mask = None
+            if self.conv_mask and lens is not None and (not last or mask_output):
+                out_mask = lens.to(dtype=torch.long).to(torch.int32)            # the consumer truncates with .to(long)
+            geo = {"T_out": t_out, "x_row_offset": x_off, "out_pad": (0, 0), "act": self.act,
+                   "drop_p": self.dropout_p if training else 0.0, "lens": out_mask}
+            use_res = res_pair if last else None
+            if training:
+                h = ConvBNActFn.apply(h, conv.weight, None, bn.weight, bn.bias, use_res[0] if use_res else None,
+                                      use_res[1] if use_res else None, conv, bn, geo)
+            else:
+                h = conv_bn_act_eval(h, conv, bn, geo, res=use_res)
+            t = t_out
+        return h, t, lens
+
+
+class Jasper(ConvCTCASR):
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.mid_layers = cfg.mid_layers
+        if not cfg.input_size:
+            nfft = self.audio_conf["sample_rate"] * self.audio_conf["window_size"]
+            self.input_size = int(1 + nfft / 2)
+        else:
+            self.input_size = cfg.input_size
+        self._build_encoder(cfg)
+        last = self.jasper_encoder[-1].mconv[-1].num_features
+        self.final_layer = nn.Sequential(ConvParams(last, len(self.labels), 1, bias=True))
+        self.final_layer.apply(init_weights)
+
+    def _build_encoder(self, cfg):
+        width, blocks = self.input_size, []
+        for l in cfg.jasper_blocks[: cfg.mid_layers]:
+            blocks.append(JasperBlock(inplanes=width, planes=l.layer_size, kernel_size=l.kernel_size, stride=l.get("stride", 1),
+                                      dilation=l.get("dilation", 1), residual=l.residual, repeat=l.get("repeat", 1),
+                                      conv_mask=l.get("conv_mask", True), separable=l.get("separable", True),
+                                      activation=torch.nn.ReLU(), dropout=l.get("dropout", 0)))
+            width = l.layer_size
+        self.jasper_encoder = nn.Sequential(*blocks)
+        self.jasper_encoder.apply(init_weights)
+
+    @property
+    def scaling_factor(self):
+        if not hasattr(self, "_scaling_factor"):
+            self._scaling_factor = int(np.prod([b.mconv[0].conv.stride[0] for b in self.jasper_encoder]))
+        return self._scaling_factor
+
+    def forward(self, xs, input_lengths):
+        """[B, F, T] fp32 CUDA, lengths [B] -> ([B, T', n_labels] log-probs in training / probabilities in eval --
+        the reference's behaviour, jasper.py:470-473 -- , output lengths int64 [B])."""
+        if not xs.is_cuda:
+            raise RuntimeError("Jasper: CUDA input required (this build has no CPU path)")
+        lens = input_lengths.to(xs.device) if input_lengths is not None else None
+        h, t = xs, xs.shape[2]
+        blocks = list(self.jasper_encoder)
+        for i, blk in enumerate(blocks):
+            # the head (final_layer) is NOT masked in the reference (jasper.py:468): the last block keeps its padded rows
+            h, t, lens = blk.forward_tm(h, t, lens, from_ncw=(i == 0), mask_output=(i != len(blocks) - 1))
+        out_lens = lens.to(dtype=int) if lens is not None else None
+        head = self.final_layer[0]
+        scores = ConvHeadFn.apply(h, head.weight, head.bias, head, 0 if self.training else 1)
+        return scores, out_lens

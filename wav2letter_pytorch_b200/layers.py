@@ -149,16 +149,18 @@ def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0,
 
 
 class ConvBNActFn(torch.autograd.Function):
-    """conv (+bias) -> BatchNorm(train statistics) -> dropout -> activation, written into the consumer's padded
-    buffer.  Inputs: time-major bf16 ``xin`` ([B, x_rows, cin_eff]), the conv/BN parameters, and a geometry dict:
-      x_row_offset, out_pad=(pl, pr) reflect halo wanted by the consumer, act, drop_p, lens (int32 [B] | None),
-      res=(z_res, res_fin) residual branch already convolved (Jasper), momentum/eps come from ``bn``.
-    Returns yp [B, pl+T_out+pr, Cout] bf16."""
+    """conv (+bias) -> BatchNorm(train statistics) [+ residual branch] -> dropout -> activation, written into the
+    consumer's padded buffer.  Inputs: time-major bf16 ``xin`` ([B, x_rows, cin_eff]), the conv/BN parameters, the
+    optional residual pair (z_res, fin_res) produced by ``ResidualBranchFn``, and a geometry dict:
+      T_out, x_row_offset, out_pad=(pl, pr) reflect halo wanted by the consumer, act, drop_p, lens (int32 [B] | None).
+    Returns yp [B, pl+T_out+pr, Cout] bf16.
+
+    Gradient convention for the residual pair: the value returned for ``z_res`` is the (masked) gradient with
+    respect to the residual branch's BatchNorm OUTPUT, which is what ``ResidualBranchFn.backward`` expects."""
 
     @staticmethod
-    def forward(ctx, xin, weight, bias, gamma, beta, conv, bn, geo):
+    def forward(ctx, xin, weight, bias, gamma, beta, z_res, fin_res, conv, bn, geo):
         B, x_rows, _ = xin.shape
-        k, d = conv.k_eff, conv.dilation[0]
         T_out = geo["T_out"]
         Co = conv.out_channels
         pl, pr = geo.get("out_pad", (0, 0))
@@ -169,29 +171,24 @@ class ConvBNActFn(torch.autograd.Function):
         fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
         seed = next_dropout_seed() if geo.get("drop_p", 0.0) > 0 else 0
-        res = geo.get("res")
+        has_res = z_res is not None
         yp = F.bn_act_pad(z, fin[0], fin[1], B, T_out, Co, pl, pr, geo["act"], geo.get("drop_p", 0.0), seed, geo.get("lens"),
-                          res=None if res is None else res[0], res_scale=None if res is None else res[1][0],
-                          res_shift=None if res is None else res[1][1])
-        ctx.conv, ctx.bn, ctx.geo, ctx.seed, ctx.desc = conv, bn, geo, seed, desc
+                          res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None)
+        ctx.conv, ctx.geo, ctx.seed, ctx.desc, ctx.has_res = conv, geo, seed, desc, has_res
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(xin, z, fin, gamma)
+        ctx.save_for_backward(xin, z, fin, gamma, z_res, fin_res)
         return yp
 
     @staticmethod
     def backward(ctx, dyp):
-        xin, z, fin, gamma = ctx.saved_tensors
-        conv, geo = ctx.conv, ctx.geo
+        xin, z, fin, gamma, z_res, fin_res = ctx.saved_tensors
+        conv, geo, has_res = ctx.conv, ctx.geo, ctx.has_res
         B, T_out, Co = z.shape
         pl, pr = geo.get("out_pad", (0, 0))
-        res = geo.get("res")
-        dyp = dyp.contiguous()
-        dz, red, g = F.bn_act_bwd(dyp, z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
-                                  geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=None if res is None else res[0],
-                                  res_scale=None if res is None else res[1][0], res_shift=None if res is None else res[1][1],
-                                  want_g=res is not None)
-        if res is not None:
-            geo["res_grad_sink"](g)                        # hand the masked upstream gradient to the residual branch
+        dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
+                                  geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
+                                  res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
+                                  want_g=has_res)
         dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
         F.conv1d_wgrad(dz, xin, ctx.desc, dw)
         dx = None
@@ -199,7 +196,42 @@ class ConvBNActFn(torch.autograd.Function):
             dx = torch.empty_like(xin)
             F.conv1d_dgrad(dz, conv.packed(), ctx.desc, dx)
         dbias = torch.zeros(Co, dtype=torch.float32, device=z.device) if ctx.has_bias else None   # exactly 0 under train BN
-        return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], None, None, None
+        return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
+
+
+class ResidualBranchFn(torch.autograd.Function):
+    """Jasper residual branch (jasper.py:400-412): 1x1 conv of the block input, BatchNorm statistics.  Returns
+    (z_res bf16 [B,T,C], fin_res fp32 [4,C] = scale, shift, mean, invstd); the BatchNorm is APPLIED inside the main
+    branch's fused bn_act_pad pass.  backward() receives, for z_res, the gradient w.r.t. the branch's BN output."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, gamma, beta, conv, bn):
+        B, T, _ = xin.shape
+        Co = conv.out_channels
+        z = torch.empty((B, T, Co), dtype=torch.bfloat16, device=xin.device)
+        desc = conv_desc(conv, B, T, T, 0)
+        F.conv1d_fwd(xin, conv.packed(), desc, z)
+        stats = F.bn_stats(z, Co)
+        fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
+        bn.num_batches_tracked += 1
+        ctx.conv, ctx.desc = conv, desc
+        ctx.save_for_backward(xin, z, fin, gamma)
+        ctx.mark_non_differentiable(fin)
+        return z, fin
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        xin, z, fin, gamma = ctx.saved_tensors
+        conv = ctx.conv
+        B, T, Co = z.shape
+        dz, red, _ = F.bn_act_bwd(g.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, Co, 0, 0, F.ACT_NONE)
+        dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
+        F.conv1d_wgrad(dz, xin, ctx.desc, dw)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(xin)
+            F.conv1d_dgrad(dz, conv.packed(), ctx.desc, dx)
+        return dx, conv.grad_view(dw), red[Co:], red[:Co], None, None
 
 
 class ConvHeadFn(torch.autograd.Function):
@@ -240,13 +272,13 @@ class ConvHeadFn(torch.autograd.Function):
         return dx, conv.grad_view(dw), dbias, None, None
 
 
-def conv_bn_act_eval(xin, conv, bn, geo):
-    """Inference path: BatchNorm folded into the conv epilogue (scale/shift/activation fused), then the halo/mask
-    pass only if the consumer needs padded or masked rows."""
+def conv_bn_act_eval(xin, conv, bn, geo, res=None):
+    """Inference path: BatchNorm folded into the conv epilogue (scale/shift/activation fused), then the reflect-halo
+    fill; with a residual branch or a length mask the BN/act/mask pass runs as in training (running statistics).
+    ``res`` = (z_res, (scale_res, shift_res))."""
     B, x_rows, _ = xin.shape
     T_out, Co = geo["T_out"], conv.out_channels
     pl, pr = geo.get("out_pad", (0, 0))
-    res = geo.get("res")
     lens = geo.get("lens")
     scale, shift = bn.eval_scale_shift(conv.bias)
     if res is None and lens is None:

@@ -73,7 +73,7 @@ class Conv1dBlock(nn.Module):
                "act": F.ACT_CLAMP20 if self.activation_use else F.ACT_NONE}
         if self.training:
             bn = self.batch_norm
-            y = ConvBNActFn.apply(xin, conv.weight, conv.bias, bn.weight, bn.bias, conv, bn, geo)
+            y = ConvBNActFn.apply(xin, conv.weight, conv.bias, bn.weight, bn.bias, None, None, conv, bn, geo)
         else:
             y = conv_bn_act_eval(xin, conv, self.batch_norm, geo)
         return y, t_out
