@@ -47,6 +47,10 @@ int64_t w2l_launch_count(void);
 /* Host-side Levenshtein distance between two int32 symbol sequences (HOST pointers).  Replaces the
  * python-Levenshtein calls behind Decoder.wer / Decoder.cer (decoder.py:31-60).  Returns -1 on bad input. */
 int64_t w2l_edit_distance_host(const int32_t* a_host, int64_t n, const int32_t* b_host, int64_t m);
+/* Batched form (one call per training step): pair p compares a[a_off[p]:a_off[p+1]] with b[b_off[p]:b_off[p+1]];
+ * bit-parallel (Myers/Hyyro) and spread over `threads` host threads (0 = hardware concurrency, capped at 16). */
+int w2l_edit_distance_batch_host(const int32_t* a_host, const int64_t* a_off_host, const int32_t* b_host,
+                                 const int64_t* b_off_host, int64_t n_pairs, int64_t* out_host, int32_t threads);
 
 /* ---------------------------------------------------------------------------------------------
  * Greedy CTC decoding.  Replaces GreedyDecoder.decode -> torch.max(probs, 2) + the per-frame Python

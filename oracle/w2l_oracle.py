@@ -160,58 +160,76 @@ def masked_conv1d(x, lens, w, stride, pad, dilation, groups, use_mask, bias=None
     return F.conv1d(x, w, bias, stride=stride, padding=pad, dilation=dilation, groups=groups), lens
 
 
-def _jasper_conv_bn(x, lens, sd, prefix, idx, spec, cin, k, stride, pad, dilation, training, separable):
-    """one _get_conv_bn_layer group (jasper.py:300-368): [depthwise+]conv, BatchNorm1d(eps 1e-3, mom 0.1)."""
+def _ident(t):
+    return t
+
+
+def _jasper_conv_bn(x, lens, sd, prefix, idx, spec, cin, k, stride, pad, dilation, training, separable, emu=False):
+    """one _get_conv_bn_layer group (jasper.py:300-368): [depthwise+]conv, BatchNorm1d(eps 1e-3, mom 0.1).
+    ``emu``: bf16 weights / bf16-stored conv outputs (the CUDA path's storage precision), fp32 accumulation."""
+    Wq, Rz = (_bf16_weight, _RoundBF16.apply) if emu else (_ident, _ident)
     if separable:
-        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], stride, pad, dilation,
+        x, lens = masked_conv1d(x, lens, Wq(sd["%s%d.conv.weight" % (prefix, idx)]), stride, pad, dilation,
                                 cin, spec["conv_mask"])
         idx += 1
-        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], 1, 0, 1, 1, spec["conv_mask"])
+        x, lens = masked_conv1d(x, lens, Wq(sd["%s%d.conv.weight" % (prefix, idx)]), 1, 0, 1, 1, spec["conv_mask"])
         idx += 1
     else:
-        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], stride, pad, dilation, 1,
+        x, lens = masked_conv1d(x, lens, Wq(sd["%s%d.conv.weight" % (prefix, idx)]), stride, pad, dilation, 1,
                                 spec["conv_mask"])
         idx += 1
+    x = Rz(x)
     p = "%s%d." % (prefix, idx)
     x = F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                      training=training, momentum=0.1, eps=1e-3)
     return x, lens, idx + 1
 
 
-def jasper_block_forward(x, lens, sd, bi, spec, training):
+def jasper_block_forward(x, lens, sd, bi, spec, training, emu=False):
     """JasperBlock.forward, jasper.py:379-419 (non-dense residual, 'add')."""
+    Wq, Rz, Ry = (_bf16_weight, _RoundBF16.apply, _RoundBF16.apply) if emu else (_ident, _ident, _ident)
     xs, lens_orig = x, lens
     prefix = "jasper_encoder.%d.mconv." % bi
     idx, cin, out = 0, spec["cin"], x
     for r in range(spec["repeat"]):
         out, lens, idx = _jasper_conv_bn(out, lens, sd, prefix, idx, spec, cin, spec["k"], spec["stride"],
-                                         spec["pad"], spec["dilation"], training, spec["separable"])
+                                         spec["pad"], spec["dilation"], training, spec["separable"], emu)
         cin = spec["cout"]
         if r != spec["repeat"] - 1:
             out = F.relu(out)
             if training and spec["dropout"] > 0:
                 out = F.dropout(out, spec["dropout"], True)
+            out = Ry(out)
             idx += 2                                     # activation + dropout occupy ModuleList slots
     if spec["residual"]:
         rp = "jasper_encoder.%d.res.0." % bi
-        res, _ = masked_conv1d(xs, lens_orig, sd[rp + "0.conv.weight"], 1, 0, 1, 1, spec["conv_mask"])
+        res, _ = masked_conv1d(xs, lens_orig, Wq(sd[rp + "0.conv.weight"]), 1, 0, 1, 1, spec["conv_mask"])
+        res = Rz(res)
         res = F.batch_norm(res, sd[rp + "1.running_mean"], sd[rp + "1.running_var"], sd[rp + "1.weight"],
                            sd[rp + "1.bias"], training=training, momentum=0.1, eps=1e-3)
+        if emu:
+            res = _RoundGradBF16.apply(res)              # the masked upstream gradient is handed over as bf16
         out = out + res
     out = F.relu(out)
     if training and spec["dropout"] > 0:
         out = F.dropout(out, spec["dropout"], True)
-    return out, lens
+    return Ry(out), lens
 
 
-def jasper_forward(x, input_lengths, sd, specs, training):
+def jasper_forward(x, input_lengths, sd, specs, training, emu=False):
     """Jasper.forward, jasper.py:462-475: encoder, unmasked 1x1 head with bias, transpose,
     log_softmax when training / softmax in eval (reference quirk, replicated)."""
     lens = input_lengths
+    if emu:
+        x = x.to(torch.bfloat16).float()
     for bi, spec in enumerate(specs):
-        x, lens = jasper_block_forward(x, lens, sd, bi, spec, training)
+        x, lens = jasper_block_forward(x, lens, sd, bi, spec, training, emu)
     out_len = lens.to(dtype=int)
-    z = F.conv1d(x, sd["final_layer.0.weight"], sd["final_layer.0.bias"]).transpose(2, 1)
+    w = _bf16_weight(sd["final_layer.0.weight"]) if emu else sd["final_layer.0.weight"]
+    z = F.conv1d(x, w, sd["final_layer.0.bias"])
+    if emu:
+        z = _RoundGradBF16.apply(z)
+    z = z.transpose(2, 1)
     z = F.log_softmax(z, dim=-1) if training else F.softmax(z, dim=-1)
     assert not (z != z).any()
     return z, out_len

@@ -73,6 +73,7 @@ SIGNATURES = {
     "w2l_last_error": (ctypes.c_char_p, []),
     "w2l_launch_count": (c_i64, []),
     "w2l_edit_distance_host": (c_i64, [c_ptr, c_i64, c_ptr, c_i64]),
+    "w2l_edit_distance_batch_host": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32]),
     "w2l_greedy_decode_workspace_bytes": (c_size, [c_i64, c_i64]),
     "w2l_greedy_decode": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                   c_size, c_ptr]),

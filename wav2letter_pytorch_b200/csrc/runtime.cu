@@ -129,3 +129,75 @@ extern "C" int64_t w2l_edit_distance_host(const int32_t* a, int64_t n, const int
   if (row != stack_row) delete[] row;
   return r;
 }
+
+// ---------------------------------------------------------------- batched, bit-parallel Levenshtein
+// Myers' bit-vector algorithm in Hyyro's block formulation: O(ceil(m/64) * n) word operations per pair instead of
+// O(m*n) cells; pairs are spread over host threads.  One call scores a whole batch of transcripts.
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace w2l {
+static int64_t myers_distance(const int32_t* a, int64_t m, const int32_t* b, int64_t n) {
+  if (m == 0) return n;
+  if (n == 0) return m;
+  const int64_t words = (m + 63) / 64;
+  std::unordered_map<int32_t, int32_t> ids;
+  ids.reserve((size_t)m * 2);
+  for (int64_t i = 0; i < m; ++i) ids.emplace(a[i], (int32_t)ids.size());
+  std::vector<uint64_t> peq(ids.size() * (size_t)words, 0);
+  for (int64_t i = 0; i < m; ++i) peq[(size_t)ids[a[i]] * words + i / 64] |= 1ull << (i % 64);
+  std::vector<uint64_t> vp((size_t)words, ~0ull), vn((size_t)words, 0ull);
+  const std::vector<uint64_t> zero((size_t)words, 0ull);
+  const uint64_t last = 1ull << ((m - 1) % 64);
+  int64_t dist = m;
+  for (int64_t j = 0; j < n; ++j) {
+    auto it = ids.find(b[j]);
+    const uint64_t* pm = it == ids.end() ? zero.data() : &peq[(size_t)it->second * words];
+    uint64_t hp_carry = 1, hn_carry = 0;
+    for (int64_t w = 0; w < words; ++w) {
+      const uint64_t x = pm[w] | hn_carry;
+      const uint64_t d0 = (((x & vp[w]) + vp[w]) ^ vp[w]) | x | vn[w];
+      uint64_t hp = vn[w] | ~(d0 | vp[w]);
+      uint64_t hn = d0 & vp[w];
+      if (w == words - 1) {
+        dist += (hp & last) != 0;
+        dist -= (hn & last) != 0;
+      }
+      const uint64_t hp_out = hp >> 63, hn_out = hn >> 63;
+      hp = (hp << 1) | hp_carry;
+      hn = (hn << 1) | hn_carry;
+      hp_carry = hp_out;
+      hn_carry = hn_out;
+      vp[w] = hn | ~(d0 | hp);
+      vn[w] = hp & d0;
+    }
+  }
+  return dist;
+}
+}  // namespace w2l
+
+extern "C" int w2l_edit_distance_batch_host(const int32_t* a, const int64_t* a_off, const int32_t* b, const int64_t* b_off,
+                                            int64_t n_pairs, int64_t* out, int32_t threads) {
+  if (n_pairs < 0 || !a_off || !b_off || !out) return W2L_ERR_INVALID_ARGUMENT;
+  if (n_pairs == 0) return W2L_OK;
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t p = lo; p < hi; ++p)
+      out[p] = w2l::myers_distance(a + a_off[p], a_off[p + 1] - a_off[p], b + b_off[p], b_off[p + 1] - b_off[p]);
+  };
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt > n_pairs) nt = (int)n_pairs;
+  if (nt <= 1) {
+    work(0, n_pairs);
+    return W2L_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (n_pairs + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int64_t lo = t * per, hi = lo + per < n_pairs ? lo + per : n_pairs;
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return W2L_OK;
+}

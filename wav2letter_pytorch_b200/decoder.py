@@ -4,27 +4,49 @@ sizes=None[, return_offsets])``, ``wer`` / ``cer`` / ``wer_ratio`` / ``cer_ratio
 ``GreedyDecoder`` runs argmax + collapse as one coalesced CUDA pass (csrc/decode.cu) instead of the reference's
 per-frame Python loop with two ``.item()`` device syncs per frame; a single device->host copy of the compacted
 tokens then builds the strings."""
+import ctypes
+
+import numpy as np
 import torch
 
+from . import _lib
 from . import functional as F
 from . import label_sets
 
 
+def _as_ids(seq, vocab):
+    """characters -> code points (zero Python loop); words -> dense ids through ``vocab``."""
+    if isinstance(seq, str):
+        return np.frombuffer(seq.encode("utf-32-le"), dtype=np.int32)
+    return np.fromiter((vocab.setdefault(s, len(vocab)) for s in seq), dtype=np.int32, count=len(seq))
+
+
+def edit_distances(pairs):
+    """Levenshtein distance of every (a, b) in ``pairs`` (strings, or sequences of hashable symbols such as word
+    lists) in ONE call of the library's batched bit-parallel host routine (the reference calls the python-Levenshtein
+    C extension once per pair: decoder.py:31-60, base_asr_models.py:58-69)."""
+    n = len(pairs)
+    if n == 0:
+        return []
+    vocab = {}
+    a = [_as_ids(p[0], vocab) for p in pairs]
+    b = [_as_ids(p[1], vocab) for p in pairs]
+    a_off = np.zeros(n + 1, dtype=np.int64)
+    b_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in a], out=a_off[1:])
+    np.cumsum([len(x) for x in b], out=b_off[1:])
+    a_cat = np.ascontiguousarray(np.concatenate(a)) if a_off[-1] else np.zeros(1, dtype=np.int32)
+    b_cat = np.ascontiguousarray(np.concatenate(b)) if b_off[-1] else np.zeros(1, dtype=np.int32)
+    out = np.zeros(n, dtype=np.int64)
+    P = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    rc = _lib.load().w2l_edit_distance_batch_host(P(a_cat), P(a_off), P(b_cat), P(b_off), n, P(out), 0)
+    if rc != 0:
+        raise RuntimeError("w2l_edit_distance_batch_host failed")
+    return out.tolist()
+
+
 def _edit_distance(a, b):
-    """Levenshtein distance between two sequences of hashable symbols (characters or words), computed by the
-    library's host routine (the reference uses the python-Levenshtein C extension, decoder.py:31-60)."""
-    import ctypes
-
-    import numpy as np
-
-    from . import _lib
-    ids = {}
-    ia = np.fromiter((ids.setdefault(s, len(ids)) for s in a), dtype=np.int32, count=len(a))
-    ib = np.fromiter((ids.setdefault(s, len(ids)) for s in b), dtype=np.int32, count=len(b))
-    d = _lib.load().w2l_edit_distance_host(ia.ctypes.data_as(ctypes.c_void_p), len(ia), ib.ctypes.data_as(ctypes.c_void_p), len(ib))
-    if d < 0:
-        raise RuntimeError("w2l_edit_distance_host failed")
-    return int(d)
+    return edit_distances([(a, b)])[0]
 
 
 class Decoder(object):
@@ -47,6 +69,13 @@ class Decoder(object):
 
     def wer_ratio(self, expected, predicted):
         return self.wer(expected, predicted), len(expected.split())
+
+    def error_ratio_sums(self, expected, predicted):
+        """(sum cer, sum cer denominators, sum wer, sum wer denominators) over a batch -- the quantities
+        base_asr_models.py:58-67 accumulates pair by pair -- with two batched library calls."""
+        cer = edit_distances([(e.replace(" ", ""), p.replace(" ", "")) for e, p in zip(expected, predicted)])
+        wer = edit_distances([(e.split(), p.split()) for e, p in zip(expected, predicted)])
+        return (sum(cer), sum(len(e.replace(" ", "")) for e in expected), sum(wer), sum(len(e.split()) for e in expected))
 
     def decode(self, probs, sizes=None):
         raise NotImplementedError
