@@ -270,7 +270,7 @@ def run_gpu_arm(args):
     timer.unwrap()
     conv_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     # ---- end to end: pinned host inputs in, loss out, every step
-    ms_e2e = timed(model, opt, reducer, args.steps, 1, True)
+    ms_e2e = ms if args.profile else timed(model, opt, reducer, args.steps, 1, True)
 
     # ---- the literal default config (mid_layers=1), reported beside the full stack
     extra = None
@@ -328,8 +328,12 @@ def main():
     ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4, help="utterances in the bounded CPU sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-default", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: no warm-up floor, no e2e/default/CPU passes")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.profile:
+        args.skip_cpu = args.skip_default = True
+    else:
+        args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return

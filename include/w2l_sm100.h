@@ -127,6 +127,12 @@ typedef struct {
 int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, void* y,
                    const w2l_conv_desc* d, void* stream);
 int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream);
+/* Backward-data with a second, transposed bf16 shadow wt [k, Cin_pad16, Cout_pad] (wt[k-1-j][ci][co] = w[j][co][ci],
+ * written by w2l_pack_wt): both GEMM operands are then K-major, which the tensor pipe consumes ~30% faster than the
+ * MN-major read of w2l_conv1d_dgrad (profiles/).  Passing B=1 with T_out = x_rows = y_rows = B*(T+pad) over a dy buffer
+ * whose per-utterance tail rows are zero runs the whole batch as ONE flat row space (no per-utterance tile padding). */
+int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream);
+int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d);
 int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream);
 
@@ -174,7 +180,8 @@ int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const
                           float drop_p, uint64_t seed, const int32_t* lens, void* stream);
 int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
-                         const float* gamma, const float* red, void* dz, void* g_out /* nullable: masked g, bf16 */,
+                         const float* gamma, const float* red, void* dz /* [B, dz_rows, C]; rows >= T zero-filled */,
+                         int32_t dz_rows, void* g_out /* nullable: masked g, bf16 [B,T,C] */,
                          int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
                          uint64_t seed, const int32_t* lens, void* stream);
 

@@ -223,9 +223,42 @@ def test_conv_fwd_dgrad_wgrad(F, B, T, Cin, Cout, k, d, pad):
     dx = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
     F.conv1d_dgrad(dyc, wc, desc3, dx)
     assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
+    # ---- dgrad through the transposed (K-major) weight shadow
+    cin_pad = (Cin + 15) // 16 * 16
+    wt = torch.full((k, cin_pad, cout_pad), 9.0, dtype=torch.bfloat16, device="cuda")
+    F.pack_wt(w.permute(2, 0, 1).contiguous().cuda(), wt, Cout, Cin)
+    assert torch.equal(wt[:, :Cin, :Cout].float().cpu(), w.permute(2, 1, 0).flip(0)) and (wt[:, :, Cout:] == 0).all()
+    dx2 = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
+    F.conv1d_dgrad_wt(dyc, wt, desc3, dx2)
+    assert rel_l2(dx2.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
     # ---- wgrad
     dw = torch.full((k, Cout, Cin), 3.0, dtype=torch.float32, device="cuda")
     F.conv1d_wgrad(dyc, xc, desc3, dw)
+    assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
+
+
+@pytest.mark.parametrize("B,T,C,Co,k,d", [(3, 200, 64, 128, 5, 1), (5, 131, 128, 64, 7, 2), (2, 750, 256, 256, 11, 1)])
+def test_conv_dgrad_flat_prepadded(F, B, T, C, Co, k, d):
+    """Wav2Letter layout: the input carries its own halo (x_rows = T + (k-1)d), dz is stored with the input's row pitch and zero
+    tails, and backward-data runs over ONE flat [B*x_rows] row space; wgrad reads the same pitched dz."""
+    g = torch.Generator().manual_seed(B + T + k)
+    halo = (k - 1) * d
+    Tp = T + halo
+    xp = _bf(torch.randn(B, Tp, C, generator=g))
+    w = _bf(torch.randn(Co, C, k, generator=g) / (C * k) ** 0.5)
+    dy = _bf(torch.randn(B, T, Co, generator=g))
+    xr = xp.transpose(1, 2).clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    TF.conv1d(xr, wr, dilation=d).backward(dy.transpose(1, 2))
+    dz = torch.zeros(B, Tp, Co, dtype=torch.bfloat16, device="cuda")
+    dz[:, :T] = dy.to(torch.bfloat16).cuda()
+    wt = torch.empty(k, C, Co, dtype=torch.bfloat16, device="cuda")
+    F.pack_wt(w.permute(2, 0, 1).contiguous().cuda(), wt, Co, C)
+    dx = torch.empty(B, Tp, C, dtype=torch.bfloat16, device="cuda")
+    F.conv1d_dgrad_wt(dz, wt, F.make_desc(1, B * Tp, C, Co, Co, k, d, B * Tp, 0, B * Tp, 0, Co), dx)
+    assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
+    dw = torch.empty(k, Co, C, dtype=torch.float32, device="cuda")
+    F.conv1d_wgrad(dz, xp.to(torch.bfloat16).cuda(), F.make_desc(B, T, C, Co, Co, k, d, Tp, 0, Tp, 0, Co), dw)
     assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
 
 
@@ -304,6 +337,9 @@ def test_bn_act_forward_backward(F, act, drop):
                               B, T, C, pl, pr, act, drop, seed)
     assert rel_l2(dz.float().cpu(), zr.grad.transpose(1, 2)) < 1e-2
     assert rel_l2(red[:C].cpu(), br.grad) < 5e-3 and rel_l2(red[C:].cpu(), gr.grad) < 5e-3
+    dzp, _, _ = F.bn_act_bwd(dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda(), zc, scale, shift, mean, invstd, gamma.cuda(),
+                             B, T, C, pl, pr, act, drop, seed, dz_rows=T + 7)
+    assert torch.equal(dzp[:, :T], dz) and (dzp[:, T:] == 0).all()
 
 
 def test_log_softmax_and_colsum(F):

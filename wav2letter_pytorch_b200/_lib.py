@@ -82,6 +82,8 @@ SIGNATURES = {
                              c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "w2l_conv1d_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_conv1d_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_conv1d_dgrad_wt": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_pack_wt": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_conv1d_wgrad_splits": (c_i32, [ctypes.POINTER(ConvDesc)]),
     "w2l_conv1d_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_im2col_ncw": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
@@ -94,7 +96,7 @@ SIGNATURES = {
                                c_u64, c_ptr, c_ptr]),
     "w2l_reflect_halo": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_bn_act_bwd_reduce": (c_i32, [c_ptr] * 10 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr]),
-    "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 13 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr]),
+    "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 12 + [c_i32, c_ptr] + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr]),
     "w2l_log_softmax": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),

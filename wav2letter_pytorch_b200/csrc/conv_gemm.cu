@@ -471,6 +471,55 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
   return launch_gemm<MODE_DGRAD>(p, (cudaStream_t)stream);
 }
 
+int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream) {
+  // Backward-data as a FORWARD implicit GEMM over dy with tap-reversed, transposed weights wt[k-1-j][ci][co] = w[j][co][ci]:
+  //   dx[u, ci] = sum_{j'} sum_co dy[u - off - (k-1)d + j'd, co] * wt[j'][ci][co]      (both operands K-major)
+  using namespace w2l;
+  int rc = check_desc(d, "conv1d_dgrad_wt");
+  if (rc) return rc;
+  W2L_REQUIRE(dy && wt && dx, "conv1d_dgrad_wt: null pointer");
+  W2L_REQUIRE(d->Cout_pad >= 64 && d->Cout_pad % 8 == 0, "conv1d_dgrad_wt: Cout_pad=%d must be >= 64", d->Cout_pad);
+  W2L_REQUIRE(d->ldy >= d->Cout_pad, "conv1d_dgrad_wt: dy row pitch %d < Cout_pad %d", d->ldy, d->Cout_pad);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+    uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)d->T_out, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
+    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  const int n_pad = (d->Cin + 15) / 16 * 16;
+  p.BN = pick_bn(n_pad);
+  {
+    uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)n_pad, (uint64_t)d->k};
+    uint64_t str[2] = {(uint64_t)d->Cout_pad * 2, (uint64_t)n_pad * d->Cout_pad * 2};
+    uint32_t box[3] = {kBlockK, (uint32_t)p.BN, 1};
+    rc = make_tensor_map(&p.tmB, wt, 2, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.B = d->B;
+  p.m_tiles = (d->x_rows + kBlockM - 1) / kBlockM;
+  p.n_tiles = n_pad / p.BN;
+  p.k = d->k;
+  p.dil = d->dilation;
+  p.kc_steps = (d->Cout_pad + kBlockK - 1) / kBlockK;
+  p.a_row_off = -d->x_row_offset - (d->k - 1) * d->dilation;
+  p.a_tap_step = d->dilation;
+  p.M_valid = d->x_rows;
+  p.N_valid = d->Cin;
+  p.num_tiles = p.m_tiles * p.n_tiles * p.B;
+  p.act = W2L_ACT_NONE;
+  p.y_dtype = W2L_DTYPE_BF16;
+  p.y = dx;
+  p.y_batch_stride = (int64_t)d->x_rows * d->Cin;
+  p.y_row_off = 0;
+  p.ldy = d->Cin;
+  p.splits = 1;
+  return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
+}
+
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
   if (!d || d->B < 1) return 1;
   return w2l::wgrad_splits(d, nullptr);

@@ -179,6 +179,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t rows
 }
 
 // ---------------------------------------------------------------- BN apply + dropout + act + halo + mask
+// Thread mapping of the three kernels below: block (32, 8); threadIdx.x -> one 8-channel vector (16 B) of a row, so a warp
+// moves 512 contiguous bytes; blockIdx.x tiles the channel vectors, blockIdx.y a contiguous range of (b, t) rows walked
+// by the 8 row lanes.  A thread keeps its channel for the whole kernel, so the per-channel constants live in registers.
 struct BnActArgs {
   const __nv_bfloat16* z;
   const __nv_bfloat16* res;
@@ -192,45 +195,54 @@ struct BnActArgs {
   const int32_t* lens;
 };
 
-// value before the activation, after dropout ("pre"), for 8 channels of element (b, t, c..c+7)
-__device__ __forceinline__ void bn_pre8(const BnActArgs& a, int b, int t, int c, float (&pre)[8], float (&mult)[8], float (&zv)[8]) {
-  const int64_t e = ((int64_t)b * a.T + t) * a.C + c;
+struct ChanConsts {
+  float sc[8], sh[8], rsc[8], rsh[8];
+};
+
+__device__ __forceinline__ void load_consts(const BnActArgs& a, int c, ChanConsts& k) {
+  load8f(a.scale + c, k.sc);
+  load8f(a.shift + c, k.sh);
+  if (a.res) {
+    load8f(a.res_scale + c, k.rsc);
+    load8f(a.res_shift + c, k.rsh);
+  }
+}
+
+// value entering the activation ("pre": BN output [+ residual], dropout applied) for 8 channels of row (b, t)
+__device__ __forceinline__ void bn_pre8(const BnActArgs& a, const ChanConsts& k, int64_t e, float (&pre)[8], float (&mult)[8],
+                                        float (&zv)[8]) {
   unpack8(__ldg(reinterpret_cast<const uint4*>(a.z + e)), zv);
-  float sc[8], sh[8];
-  load8f(a.scale + c, sc);
-  load8f(a.shift + c, sh);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], sc[i], sh[i]);
+  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], k.sc[i], k.sh[i]);
   if (a.res) {
     float rv[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(a.res + e)), rv);
-    load8f(a.res_scale + c, sc);
-    load8f(a.res_shift + c, sh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], sc[i], sh[i]);
+    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], k.rsc[i], k.rsh[i]);
   }
   dropout_mult8(a.seed, (uint64_t)e, a.drop_p, mult);
 #pragma unroll
   for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
 }
 
-__global__ void bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y) {
-  const int c8 = a.C >> 3;
-  const int64_t total = (int64_t)a.B * a.T * c8;
-  const int Tp = a.pl + a.T + a.pr;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c8) * 8;
-    const int64_t bt = i / c8;
-    const int t = (int)(bt % a.T), b = (int)(bt / a.T);
+__global__ void __launch_bounds__(256) bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y, int rows_per_block) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  if (c >= a.C) return;
+  ChanConsts k;
+  load_consts(a, c, k);
+  const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+    const int b = r / a.T, t = r - b * a.T;
     float pre[8], mult[8], zv[8];
-    bn_pre8(a, b, t, c, pre, mult, zv);
+    bn_pre8(a, k, (int64_t)r * a.C + c, pre, mult, zv);
     const bool masked = a.lens && t >= a.lens[b];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float v = pre[k];
+    for (int i = 0; i < 8; ++i) {
+      float v = pre[i];
       if (a.act == W2L_ACT_RELU) v = fmaxf(v, 0.f);
       else if (a.act == W2L_ACT_CLAMP20) v = fminf(fmaxf(v, 0.f), 20.f);
-      pre[k] = masked ? 0.f : v;
+      pre[i] = masked ? 0.f : v;
     }
     const uint4 q = pack8(pre);
     __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
@@ -241,7 +253,7 @@ __global__ void bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y) {
   }
 }
 
-// upstream gradient of output element (b,t,c..c+7): fold of the reflect halo of the padded gradient
+// upstream gradient of output row (b,t): fold of the reflect halo of the padded gradient
 __device__ __forceinline__ void fold_grad8(const __nv_bfloat16* __restrict__ dyp, int b, int t, int c, int T, int C, int pl, int pr,
                                            float (&g)[8]) {
   const int Tp = pl + T + pr;
@@ -262,16 +274,14 @@ __device__ __forceinline__ void fold_grad8(const __nv_bfloat16* __restrict__ dyp
   }
 }
 
-// g (masked upstream gradient wrt the BN output) and xhat for 8 channels
-__device__ __forceinline__ void bwd_g8(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, int b, int t, int c, float (&g)[8], float (&xhat)[8]) {
+// g (masked upstream gradient wrt the BN output) and xhat for 8 channels of row r
+__device__ __forceinline__ void bwd_g8(const BnActArgs& a, const ChanConsts& k, const float (&mu)[8], const float (&is)[8],
+                                       const __nv_bfloat16* __restrict__ dyp, int r, int c, float (&g)[8], float (&xhat)[8]) {
+  const int b = r / a.T, t = r - b * a.T;
   float pre[8], mult[8], zv[8];
-  bn_pre8(a, b, t, c, pre, mult, zv);
+  bn_pre8(a, k, (int64_t)r * a.C + c, pre, mult, zv);
   fold_grad8(dyp, b, t, c, a.T, a.C, a.pl, a.pr, g);
   const bool masked = a.lens && t >= a.lens[b];
-  float mu[8], is[8];
-  load8f(mean + c, mu);
-  load8f(invstd + c, is);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     bool pass = true;
@@ -282,22 +292,26 @@ __device__ __forceinline__ void bwd_g8(const BnActArgs& a, const __nv_bfloat16* 
   }
 }
 
-// block (32, 8) like bn_stats; red[0:C] += sum g, red[C:2C] += sum g*xhat
-__global__ void bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
-                                         const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
+// red[0:C] += sum g, red[C:2C] += sum g*xhat
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
   __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
-  const int c = blockIdx.x * 256 + threadIdx.x * 8;
-  const int64_t rows = (int64_t)a.B * a.T;
-  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   float sg[8], sx[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
   if (c < a.C) {
-    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
-      const int b = (int)(r / a.T), t = (int)(r - (int64_t)b * a.T);
+    ChanConsts k;
+    float mu[8], is[8];
+    load_consts(a, c, k);
+    load8f(mean + c, mu);
+    load8f(invstd + c, is);
+    const int rows = a.B * a.T;
+    const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
       float g[8], xh[8];
-      bwd_g8(a, dyp, mean, invstd, b, t, c, g, xh);
+      bwd_g8(a, k, mu, is, dyp, r, c, g, xh);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         sg[i] += g[i];
@@ -325,32 +339,50 @@ __global__ void bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __res
   }
 }
 
-__global__ void bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
-                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                        const float* __restrict__ red, __nv_bfloat16* __restrict__ dz,
-                                        __nv_bfloat16* __restrict__ g_out) {
-  const int c8 = a.C >> 3;
-  const int64_t total = (int64_t)a.B * a.T * c8;
+// dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the
+// zero padding between utterances)
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ red,
+                        __nv_bfloat16* __restrict__ dz, int dz_rows, __nv_bfloat16* __restrict__ g_out, int rows_per_block) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  if (c >= a.C) return;
+  ChanConsts k;
+  float mu[8], is[8], sg[8], sx[8], coef[8];
+  load_consts(a, c, k);
+  load8f(mean + c, mu);
+  load8f(invstd + c, is);
+  load8f(red + c, sg);
+  load8f(red + a.C + c, sx);
   const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c8) * 8;
-    const int64_t bt = i / c8;
-    const int t = (int)(bt % a.T), b = (int)(bt / a.T);
-    float g[8], xh[8];
-    bwd_g8(a, dyp, mean, invstd, b, t, c, g, xh);
-    float sg[8], sx[8], ga[8], is[8], o[8];
-    load8f(red + c, sg);
-    load8f(red + a.C + c, sx);
-    load8f(invstd + c, is);
-    if (gamma) load8f(gamma + c, ga);
+  if (gamma) load8f(gamma + c, coef);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float gm = gamma ? ga[k] : 1.f;
-      o[k] = gm * is[k] * (g[k] - sg[k] * inv_m - xh[k] * sx[k] * inv_m);
+  for (int i = 0; i < 8; ++i) {
+    coef[i] = (gamma ? coef[i] : 1.f) * is[i];
+    sg[i] *= inv_m;
+    sx[i] *= inv_m;
+  }
+  const int rows = a.B * a.T;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+    float g[8], xh[8], o[8];
+    bwd_g8(a, k, mu, is, dyp, r, c, g, xh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = coef[i] * (g[i] - sg[i] - xh[i] * sx[i]);
+    const int b = r / a.T, t = r - b * a.T;
+    *reinterpret_cast<uint4*>(dz + ((int64_t)b * dz_rows + t) * a.C + c) = pack8(o);
+    if (g_out) *reinterpret_cast<uint4*>(g_out + (int64_t)r * a.C + c) = pack8(g);
+  }
+  // zero tails
+  const int tail = dz_rows - a.T;
+  if (tail > 0) {
+    const int trows = a.B * tail;
+    const int per = (trows + gridDim.y - 1) / gridDim.y;
+    const int q_begin = blockIdx.y * per, q_end = min(trows, q_begin + per);
+    for (int q = q_begin + threadIdx.y; q < q_end; q += 8) {
+      const int b = q / tail, t = a.T + (q - b * tail);
+      *reinterpret_cast<uint4*>(dz + ((int64_t)b * dz_rows + t) * a.C + c) = make_uint4(0u, 0u, 0u, 0u);
     }
-    const int64_t e = bt * a.C + c;
-    *reinterpret_cast<uint4*>(dz + e) = pack8(o);
-    if (g_out) *reinterpret_cast<uint4*>(g_out + e) = pack8(g);
   }
 }
 
@@ -462,15 +494,16 @@ static int check_bn_args(const char* who, const void* z, const float* scale, con
   W2L_REQUIRE(!res || (res_scale && res_shift), "%s: residual needs res_scale/res_shift", who);
   W2L_REQUIRE(B >= 1 && T >= 1 && C >= 8 && C % 8 == 0, "%s: bad shape B=%d T=%d C=%d (C must be a multiple of 8)", who, B, T, C);
   W2L_REQUIRE(pl >= 0 && pr >= 0 && pl < T && pr < T, "%s: reflect halo (%d,%d) must be smaller than T=%d", who, pl, pr, T);
+  W2L_REQUIRE((int64_t)B * (T + pl + pr) < (1ll << 31) / 8, "%s: B*T too large", who);
   W2L_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p=%f out of [0,1)", who, drop_p);
   return W2L_OK;
 }
 
 static int rows_per_block_for(int64_t rows, int col_blocks) {
-  int64_t target_blocks = (int64_t)num_sms() * 4 / (col_blocks > 0 ? col_blocks : 1);
+  int64_t target_blocks = (int64_t)num_sms() * 8 / (col_blocks > 0 ? col_blocks : 1);
   if (target_blocks < 1) target_blocks = 1;
   int64_t rpb = (rows + target_blocks - 1) / target_blocks;
-  if (rpb < 64) rpb = 64;
+  if (rpb < 32) rpb = 32;
   return (int)rpb;
 }
 
@@ -547,8 +580,11 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
   if (rc) return rc;
   W2L_REQUIRE(y != nullptr, "bn_act_pad: null output");
   BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
-  const int64_t total = (int64_t)B * T * (C / 8);
-  bn_act_pad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y);
+  const int64_t rows = (int64_t)B * T;
+  const int col_blocks = (C + 255) / 256;
+  const int rpb = rows_per_block_for(rows, col_blocks);
+  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
+  bn_act_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
   return after_launch("bn_act_pad_kernel");
 }
 
@@ -571,16 +607,21 @@ int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const
 
 int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd, const float* gamma,
-                         const float* red, void* dz, void* g_out, int32_t B, int32_t T, int32_t C, int32_t pad_left,
-                         int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream) {
+                         const float* red, void* dz, int32_t dz_rows, void* g_out, int32_t B, int32_t T, int32_t C,
+                         int32_t pad_left, int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens,
+                         void* stream) {
   using namespace w2l;
   int rc = check_bn_args("bn_act_bwd_apply", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
   if (rc) return rc;
   W2L_REQUIRE(dyp && mean && invstd && red && dz, "bn_act_bwd_apply: null pointer");
+  W2L_REQUIRE(dz_rows >= T, "bn_act_bwd_apply: dz_rows %d < T %d", dz_rows, T);
   BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
-  const int64_t total = (int64_t)B * T * (C / 8);
-  bn_act_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma,
-                                                                                 red, (__nv_bfloat16*)dz, (__nv_bfloat16*)g_out);
+  const int64_t rows = (int64_t)B * T;
+  const int col_blocks = (C + 255) / 256;
+  const int rpb = rows_per_block_for(rows, col_blocks);
+  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
+  bn_act_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
+                                                                   (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
   return after_launch("bn_act_bwd_apply_kernel");
 }
 
@@ -649,4 +690,33 @@ extern "C" int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_
   const int64_t total = (int64_t)B * (pad_left + pad_right) * (C / 8);
   reflect_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)y, B, T, C, pad_left, pad_right);
   return after_launch("reflect_halo_kernel");
+}
+
+// ---------------------------------------------------------------- transposed weight shadow for backward-data
+// w [k, Co, Ci] fp32 (kernel-layout master weights) -> wt [k, Ci_pad, Co_pad] bf16 with wt[k-1-j][ci][co] = w[j][co][ci]
+namespace w2l {
+__global__ void pack_wt_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int k, int Co, int Ci, int Co_pad, int Ci_pad) {
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const float* src = w + (int64_t)j * Co * Ci;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    tile[i][threadIdx.x] = (co < Co && ci < Ci) ? src[(int64_t)co * Ci + ci] : 0.f;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = wt + (int64_t)(k - 1 - j) * Ci_pad * Co_pad;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    if (ci < Ci_pad && co < Co_pad) dst[(int64_t)ci * Co_pad + co] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+}  // namespace w2l
+
+extern "C" int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(w && wt && k >= 1 && Cout >= 1 && Cin >= 1 && Cout_pad >= Cout && Cin_pad >= Cin, "pack_wt: bad arguments");
+  W2L_REQUIRE(k <= 65535 && (Cout_pad + 31) / 32 <= 65535, "pack_wt: shape too large");
+  dim3 grid((Cin_pad + 31) / 32, (Cout_pad + 31) / 32, k), block(32, 8);
+  pack_wt_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wt, k, Cout, Cin, Cout_pad, Cin_pad);
+  return after_launch("pack_wt_kernel");
 }

@@ -112,6 +112,22 @@ def conv1d_dgrad(dy, w, desc, dx):
     return dx
 
 
+def conv1d_dgrad_wt(dy, wt, desc, dx):
+    """backward-data with the transposed (K-major) weight shadow; see w2l_conv1d_dgrad_wt"""
+    _need_cuda(dy, wt, dx)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().w2l_conv1d_dgrad_wt(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad_wt")
+    return dx
+
+
+def pack_wt(w_store, wt, cout, cin):
+    """fp32 [k, Cout, Cin] -> bf16 wt [k, Cin_pad, Cout_pad], tap-reversed + transposed"""
+    k = w_store.shape[0]
+    with torch.cuda.device(w_store.device):
+        _lib.check(_lib.load().w2l_pack_wt(_ptr(w_store), _ptr(wt), k, cout, cin, wt.shape[2], wt.shape[1], _stream()), "pack_wt")
+    return wt
+
+
 def conv1d_wgrad(dy, x, desc, dw):
     """dw [k, Cout, Cin] fp32; zero-filled here when the kernel will run split-K (atomic accumulation)."""
     _need_cuda(dy, x, dw)
@@ -184,11 +200,12 @@ def reflect_halo(y, T, pad_left, pad_right):
 
 
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False):
-    """Returns (dz bf16 [B,T,C], red fp32 [2C] = (dbeta, dgamma), g bf16 | None)."""
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None):
+    """Returns (dz bf16 [B, dz_rows, C] (rows >= T zero), red fp32 [2C] = (dbeta, dgamma), g bf16 [B,T,C] | None)."""
     dev = z.device
+    dz_rows = T if dz_rows is None else dz_rows
     red = torch.zeros((2 * C,), dtype=torch.float32, device=dev)
-    dz = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev)
+    dz = torch.empty((B, dz_rows, C), dtype=torch.bfloat16, device=dev)
     g = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev) if want_g else None
     lib = _lib.load()
     with torch.cuda.device(dev):
@@ -196,8 +213,9 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
                                              _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
                                              int(seed), _ptr(lens), _stream()), "bn_act_bwd_reduce")
         _lib.check(lib.w2l_bn_act_bwd_apply(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
-                                            _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), _ptr(g), B, T, C, pad_left,
-                                            pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()), "bn_act_bwd_apply")
+                                            _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), dz_rows, _ptr(g), B, T, C,
+                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()),
+                   "bn_act_bwd_apply")
     return dz, red, g
 
 

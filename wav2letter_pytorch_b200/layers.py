@@ -110,6 +110,19 @@ class ConvParams(nn.Module):
             self._shadow_version = ver
         return self._shadow
 
+    def packed_t(self):
+        """bf16 shadow for backward-data: [k_eff, cin_pad16, cout_pad], taps reversed and transposed (K-major operand)."""
+        w = self.weight
+        ver = (w._version, w.data_ptr())
+        if getattr(self, "_shadow_t", None) is None or self._shadow_t.device != w.device:
+            cin_pad = (self.cin_eff + 15) // 16 * 16
+            self._shadow_t = torch.zeros((self.k_eff, cin_pad, self.cout_pad), dtype=torch.bfloat16, device=w.device)
+            self._shadow_t_version = None
+        if self._shadow_t_version != ver:
+            F.pack_wt(self.storage(), self._shadow_t, self.out_channels, self.cin_eff)
+            self._shadow_t_version = ver
+        return self._shadow_t
+
     def mark_shadow_fresh(self):
         """Called by the fused optimizer, which rewrites the shadow itself."""
         self._shadow_version = (self.weight._version, self.weight.data_ptr())
@@ -185,16 +198,25 @@ class ConvBNActFn(torch.autograd.Function):
         conv, geo, has_res = ctx.conv, ctx.geo, ctx.has_res
         B, T_out, Co = z.shape
         pl, pr = geo.get("out_pad", (0, 0))
+        x_rows = xin.shape[1]
+        halo = (conv.k_eff - 1) * conv.dilation[0]
+        # Inputs that carry their own halo (x_rows == T_out + (k-1)d, Wav2Letter): dz is stored with the INPUT's row pitch and
+        # zero tails, so that backward-data runs over one flat [B*x_rows] row space (no per-utterance tile padding).
+        flat = ctx.needs_input_grad[0] and geo["x_row_offset"] == 0 and x_rows == T_out + halo
+        dz_rows = x_rows if flat else T_out
         dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
-                                  want_g=has_res)
+                                  want_g=has_res, dz_rows=dz_rows)
         dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
-        F.conv1d_wgrad(dz, xin, ctx.desc, dw)
+        F.conv1d_wgrad(dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad(dz, conv.packed(), ctx.desc, dx)
+            if flat:
+                F.conv1d_dgrad_wt(dz, conv.packed_t(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx)
+            else:
+                F.conv1d_dgrad_wt(dz, conv.packed_t(), ctx.desc, dx)
         dbias = torch.zeros(Co, dtype=torch.float32, device=z.device) if ctx.has_bias else None   # exactly 0 under train BN
         return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
 
@@ -230,7 +252,7 @@ class ResidualBranchFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad(dz, conv.packed(), ctx.desc, dx)
+            F.conv1d_dgrad_wt(dz, conv.packed_t(), ctx.desc, dx)
         return dx, conv.grad_view(dw), red[Co:], red[:Co], None, None
 
 
@@ -268,7 +290,7 @@ class ConvHeadFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad(dl, conv.packed(), desc, dx)
+            F.conv1d_dgrad_wt(dl, conv.packed_t(), desc, dx)
         return dx, conv.grad_view(dw), dbias, None, None
 
 
