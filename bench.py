@@ -260,7 +260,7 @@ def run_gpu_arm(args):
     timer = KernelTimer()
     sampler = ClockSampler(local)
     timed(model, opt, reducer, 0, args.warmup, False)
-    timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_wgrad"])
+    timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad"])
     launches0 = _lib.launch_count()
     if rank == 0:
         sampler.start()

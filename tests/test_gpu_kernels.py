@@ -339,7 +339,7 @@ def test_bn_act_forward_backward(F, act, drop):
     assert rel_l2(red[:C].cpu(), br.grad) < 5e-3 and rel_l2(red[C:].cpu(), gr.grad) < 5e-3
     dzp, _, _ = F.bn_act_bwd(dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda(), zc, scale, shift, mean, invstd, gamma.cuda(),
                              B, T, C, pl, pr, act, drop, seed, dz_rows=T + 7)
-    assert torch.equal(dzp[:, :T], dz) and (dzp[:, T:] == 0).all()
+    assert rel_l2(dzp[:, :T].float(), dz.float()) < 1e-3 and (dzp[:, T:] == 0).all()      # reductions use fp32 atomics: last-bit noise
 
 
 def test_log_softmax_and_colsum(F):

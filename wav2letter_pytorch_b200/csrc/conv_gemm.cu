@@ -58,41 +58,71 @@ struct GemmParams {
   int32_t y_row_off;
   int32_t ldy;
   // wgrad
-  int32_t splits, b_per_split;
+  int32_t splits;           // > 1: some tiles are shared between CTAs (dw pre-zeroed by the caller)
   int64_t dw_tap_stride;    // Cout*Cin
 };
 
-struct TileCoord {
-  int m0, n0, b0, b1, j;
+// A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
+// walks (tap, channel chunk).  WGRAD: stream-K -- the global iteration space tiles x (utterance, time chunk) is cut into
+// gridDim.x equal contiguous ranges, so every CTA does the same number of MMAs whatever the tile count; a tile that
+// straddles two CTAs is accumulated with fp32 atomics (partial), a tile owned by one CTA is stored directly.
+struct Unit {
+  int m0, n0, b, j;      // b: utterance (fwd/dgrad); j: tap (wgrad)
+  int it_begin, it_end;  // K iterations of the tile covered by this unit
+  bool partial;
 };
 
 template <int MODE>
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
-  TileCoord c;
-  if (MODE == MODE_WGRAD) {
-    int s = tile % p.splits;
-    tile /= p.splits;
-    int mt = tile % p.m_tiles;
-    tile /= p.m_tiles;
-    int nt = tile % p.n_tiles;
-    c.j = tile / p.n_tiles;
-    c.m0 = mt * kBlockM;
-    c.n0 = nt * p.BN;
-    c.b0 = s * p.b_per_split;
-    c.b1 = min(p.B, c.b0 + p.b_per_split);
-  } else {
-    int mt = tile % p.m_tiles;
-    tile /= p.m_tiles;
-    int b = tile % p.B;
-    int nt = tile / p.B;
-    c.m0 = mt * kBlockM;
-    c.n0 = nt * p.BN;
-    c.b0 = b;
-    c.b1 = b + 1;
-    c.j = 0;
+struct UnitIter {
+  const GemmParams& p;
+  int tile;              // fwd/dgrad cursor
+  int64_t g, g_end;      // wgrad cursor in the global iteration space
+  int iters;             // K iterations per tile
+  __device__ UnitIter(const GemmParams& p_) : p(p_) {
+    if (MODE == MODE_WGRAD) {
+      iters = p.B * p.kc_steps;
+      const int64_t total = (int64_t)p.num_tiles * iters;
+      g = total * blockIdx.x / gridDim.x;
+      g_end = total * (blockIdx.x + 1) / gridDim.x;
+    } else {
+      iters = p.k * p.kc_steps;
+      tile = blockIdx.x;
+    }
   }
-  return c;
-}
+  __device__ bool next(Unit& u) {
+    if (MODE == MODE_WGRAD) {
+      if (g >= g_end) return false;
+      int t = (int)(g / iters);
+      u.it_begin = (int)(g - (int64_t)t * iters);
+      const int64_t left = g_end - g;
+      u.it_end = (int)((int64_t)(iters - u.it_begin) <= left ? iters : u.it_begin + left);
+      u.partial = (u.it_begin != 0) || (u.it_end != iters);
+      g += u.it_end - u.it_begin;
+      const int mt = t % p.m_tiles;
+      t /= p.m_tiles;
+      const int nt = t % p.n_tiles;
+      u.j = t / p.n_tiles;
+      u.m0 = mt * kBlockM;
+      u.n0 = nt * p.BN;
+      u.b = 0;
+      return true;
+    } else {
+      if (tile >= p.num_tiles) return false;
+      int t = tile;
+      tile += gridDim.x;
+      const int mt = t % p.m_tiles;
+      t /= p.m_tiles;
+      u.b = t % p.B;
+      u.n0 = (t / p.B) * p.BN;
+      u.m0 = mt * kBlockM;
+      u.j = 0;
+      u.it_begin = 0;
+      u.it_end = iters;
+      u.partial = false;
+      return true;
+    }
+  }
+};
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -134,41 +164,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int ksteps_per_b = (MODE == MODE_WGRAD) ? p.kc_steps : p.k * p.kc_steps;
-
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<MODE>(p, tile);
-        for (int b = tc.b0; b < tc.b1; ++b) {
-          for (int ks = 0; ks < ksteps_per_b; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], stage_tx);
-            uint8_t* sa = smem + stage * kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            if (MODE == MODE_WGRAD) {
-              const int t0 = ks * kBlockK;
-              tma_load_3d(sa, &p.tmA, &full_bar[stage], tc.m0, t0, b);
-              tma_load_3d(sa + 8192, &p.tmA, &full_bar[stage], tc.m0 + 64, t0, b);
-              const int xr = t0 + p.b_row_off + tc.j * p.dil;
-              for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], tc.n0 + c * 64, xr, b);
+      UnitIter<MODE> units(p);
+      Unit u;
+      while (units.next(u)) {
+        for (int it = u.it_begin; it < u.it_end; ++it) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          uint8_t* sa = smem + stage * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          if (MODE == MODE_WGRAD) {
+            const int b = it / p.kc_steps, t0 = (it - b * p.kc_steps) * kBlockK;
+            tma_load_3d(sa, &p.tmA, &full_bar[stage], u.m0, t0, b);
+            tma_load_3d(sa + 8192, &p.tmA, &full_bar[stage], u.m0 + 64, t0, b);
+            const int xr = t0 + p.b_row_off + u.j * p.dil;
+            for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], u.n0 + c * 64, xr, b);
+          } else {
+            const int j = it / p.kc_steps, kc = it - j * p.kc_steps;
+            tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * kBlockK, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
+            if (MODE == MODE_FWD) {
+              tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0, j);
             } else {
-              const int j = ks / p.kc_steps, kc = ks - j * p.kc_steps;
-              tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * kBlockK, tc.m0 + p.a_row_off + j * p.a_tap_step, b);
-              if (MODE == MODE_FWD) {
-                tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, tc.n0, j);
-              } else {
-                for (int c = 0; c < b_chunks; ++c)
-                  tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], tc.n0 + c * 64, kc * kBlockK, j);
-              }
+              for (int c = 0; c < b_chunks; ++c)
+                tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], u.n0 + c * 64, kc * kBlockK, j);
             }
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -185,30 +212,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<MODE>(p, tile);
+      UnitIter<MODE> units(p);
+      Unit u;
+      while (units.next(u)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
         uint32_t accumulate = 0;
-        for (int b = tc.b0; b < tc.b1; ++b) {
-          for (int ks = 0; ks < ksteps_per_b; ++ks) {
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-            const uint32_t b_addr = a_addr + kABytes;
+        for (int it = u.it_begin; it < u.it_end; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
-            for (int kk = 0; kk < kBlockK / 16; ++kk) {
-              const uint64_t adesc = make_smem_desc(a_addr + kk * a_kstep, a_lbo, 1024u);
-              const uint64_t bdesc = make_smem_desc(b_addr + kk * b_kstep, b_lbo, 1024u);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t adesc = make_smem_desc(a_addr + kk * a_kstep, a_lbo, 1024u);
+            const uint64_t bdesc = make_smem_desc(b_addr + kk * b_kstep, b_lbo, 1024u);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
         umma_commit(&tfull_bar[acc]);
@@ -222,8 +248,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int row = lane_base + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile<MODE>(p, tile);
+    UnitIter<MODE> units(p);
+    Unit tc;
+    while (units.next(tc)) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
@@ -237,10 +264,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
         if (MODE == MODE_WGRAD) {
           if (row_ok) {
             float* dst = reinterpret_cast<float*>(p.y) + (int64_t)tc.j * p.dw_tap_stride + (int64_t)m * p.ldy + nbase;
-            if (p.splits > 1) {
+            if (tc.partial) {
+              if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.BN && nbase + i < p.N_valid) atomicAdd(dst + i, __uint_as_float(r[i]));
+                for (int i = 0; i < 32; i += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
+                               "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c0 + i < p.BN && nbase + i < p.N_valid) atomicAdd(dst + i, __uint_as_float(r[i]));
+              }
             } else if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
@@ -267,7 +302,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             v[i] = x;
           }
           if (row_ok) {
-            const int64_t off = (int64_t)tc.b0 * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
+            const int64_t off = (int64_t)tc.b * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
             const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
             if (p.y_dtype == W2L_DTYPE_BF16) {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + off;
@@ -323,13 +358,13 @@ static int pick_bn(int n_pad16) {
 }
 
 template <int MODE>
-static int launch_gemm(const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const GemmParams& p, cudaStream_t st, int grid_override = 0) {
   static bool configured = false;
   if (!configured) {
     W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     configured = true;
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  int grid = grid_override > 0 ? grid_override : (p.num_tiles < num_sms() ? p.num_tiles : num_sms());
   if (grid < 1) return W2L_OK;
   conv_gemm_kernel<MODE><<<grid, kGemmThreads, kGemmSmem, st>>>(p);
   return after_launch(MODE == MODE_FWD ? "conv_gemm_kernel<fwd>" : MODE == MODE_DGRAD ? "conv_gemm_kernel<dgrad>" : "conv_gemm_kernel<wgrad>");
@@ -346,28 +381,20 @@ static int check_desc(const w2l_conv_desc* d, const char* who) {
   return W2L_OK;
 }
 
-static int wgrad_splits(const w2l_conv_desc* d, int* bn_out) {
+// Stream-K launch plan for wgrad: grid size and whether any tile is shared between CTAs (=> dw must be zero-filled).
+static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* zero_out) {
   const int n_pad = (d->Cin + 15) / 16 * 16;
   const int bn = pick_bn(n_pad);
+  const int64_t tiles = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * (n_pad / bn);
+  const int64_t iters = (int64_t)d->B * ((d->T_out + kBlockK - 1) / kBlockK);
+  const int64_t total = tiles * iters;
+  int64_t grid = num_sms();
+  const int64_t min_iters = 32;                       // keep the per-CTA mainloop long enough to amortise the epilogue
+  if (total / grid < min_iters) grid = total / min_iters > 0 ? total / min_iters : 1;
+  if (grid > tiles && tiles * iters / grid < min_iters) grid = tiles;
   if (bn_out) *bn_out = bn;
-  const int64_t tiles0 = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * (n_pad / bn);
-  const int sms = num_sms();
-  int best = 1;
-  double best_eff = 0.0;
-  const int max_s = d->B < 32 ? d->B : 32;
-  for (int s = 1; s <= max_s; ++s) {
-    const int64_t tiles = tiles0 * s;
-    const int64_t waves = (tiles + sms - 1) / sms;
-    // each split re-walks ceil(B/s) utterances; efficiency = useful work / (waves * machine)
-    const int per = (d->B + s - 1) / s;
-    const double eff = (double)tiles0 * d->B / ((double)waves * sms * per);
-    if (eff > best_eff + 0.02) {
-      best_eff = eff;
-      best = s;
-    }
-  }
-  const int per = (d->B + best - 1) / best;   // utterances per split; drop empty trailing splits
-  return (d->B + per - 1) / per;
+  if (grid_out) *grid_out = (int)grid;
+  if (zero_out) *zero_out = (total % grid != 0) || ((total / grid) % iters != 0);
 }
 
 }  // namespace w2l
@@ -521,8 +548,10 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
 }
 
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
-  if (!d || d->B < 1) return 1;
-  return w2l::wgrad_splits(d, nullptr);
+  if (!d || d->B < 1 || d->T_out < 1 || d->k < 1) return 1;
+  int zero = 0;
+  w2l::wgrad_plan(d, nullptr, nullptr, &zero);
+  return zero ? 2 : 1;
 }
 
 int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream) {
@@ -548,12 +577,12 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
     rc = make_tensor_map(&p.tmB, x, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
-  int bn = 0;
-  p.splits = wgrad_splits(d, &bn);
+  int bn = 0, grid = 0, zero = 0;
+  wgrad_plan(d, &bn, &grid, &zero);
   p.BN = bn;
+  p.splits = zero ? 2 : 1;
   const int n_pad = (d->Cin + 15) / 16 * 16;
   p.B = d->B;
-  p.b_per_split = (d->B + p.splits - 1) / p.splits;
   p.m_tiles = (d->Cout + kBlockM - 1) / kBlockM;
   p.n_tiles = n_pad / p.BN;
   p.k = d->k;
@@ -562,11 +591,11 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
   p.b_row_off = d->x_row_offset;
   p.M_valid = d->Cout;
   p.N_valid = d->Cin;
-  p.num_tiles = p.k * p.m_tiles * p.n_tiles * p.splits;
+  p.num_tiles = p.k * p.m_tiles * p.n_tiles;
   p.y = dw;
   p.ldy = d->Cin;
   p.dw_tap_stride = (int64_t)d->Cout * d->Cin;
-  return launch_gemm<MODE_WGRAD>(p, (cudaStream_t)stream);
+  return launch_gemm<MODE_WGRAD>(p, (cudaStream_t)stream, grid);
 }
 
 }  // extern "C"
