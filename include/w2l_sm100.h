@@ -70,6 +70,21 @@ int w2l_greedy_decode(const float* scores, int64_t N, int64_t T, int64_t C, int6
                       int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device-side CER / WER / length-ratio of a decoded batch (replaces the per-utterance host loop of
+ * ConvCTCASR.add_string_metrics, base_asr_models.py:53-69, and its device sync).
+ *   tokens/counts      output of w2l_greedy_decode (collapsed label ids per utterance)
+ *   ref_ids            [N, ref_stride] int32: the reference texts encoded as label ids (characters outside the label
+ *                      set: n_labels + code point), ref_lens [N]; ref_stride <= 1023
+ *   space_index        id of ' ': removed for CER (decoder.py:58 replace(' ', '')), word separator for WER (split())
+ *   *_den              the host-known denominators: sum len(ref without spaces), sum #words, sum len(text)
+ *   ratios [3] fp32 out: cer, wer, len_ratio.  Words are compared through 64-bit FNV-1a hashes of their ids.
+ */
+size_t w2l_string_metrics_workspace_bytes(int64_t N, int64_t T, int64_t ref_stride);
+int w2l_string_metrics(const int32_t* tokens, const int32_t* counts, int64_t N, int64_t T, int32_t space_index,
+                       const int32_t* ref_ids, const int32_t* ref_lens, int64_t ref_stride, float cer_den, float wer_den,
+                       float len_den, float* ratios, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * CTC loss + gradient.  Replaces self.criterion = nn.CTCLoss(blank=0, reduction='mean',
  * zero_infinity=True) and its backward (base_asr_models.py:23, 81, 90).
  *   x        [N, T, C] fp32 with N/T strides in elements (the reference passes out.transpose(0,1), a

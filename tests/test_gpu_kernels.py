@@ -359,3 +359,32 @@ def test_log_softmax_and_colsum(F):
     np.testing.assert_allclose(cs.cpu().numpy(), m[:, :29].sum(0).numpy(), rtol=1e-4, atol=1e-3)
     w = torch.randn(1001, generator=g)
     assert torch.equal(F.cast_bf16(w.cuda()).cpu(), w.to(torch.bfloat16))
+
+
+def test_string_metrics_device(F):
+    """device-side CER/WER/len-ratio vs the reference's host arithmetic (base_asr_models.py:58-69)."""
+    import random
+    from wav2letter_pytorch_b200.decoder import GreedyDecoder
+    labels = O.ENGLISH_LOWERCASE
+    dec = GreedyDecoder(labels)
+    rnd = random.Random(5)
+    N, T, C = 9, 120, 29
+    g = torch.Generator().manual_seed(2)
+    probs = torch.softmax(torch.randn(N, T, C, generator=g) * 3, -1)
+    probs[:, :, 28] *= 6                                        # plenty of spaces -> many words
+    probs[3] = 0
+    probs[3, :, 0] = 1                                          # an all-blank (empty) hypothesis
+    sizes = torch.tensor([T, T, 60, T, 1, T, 100, T, 7], dtype=torch.int32)
+    texts = ["".join(rnd.choice(labels[1:]) for _ in range(rnd.randint(1, 90))) for _ in range(N)]
+    texts[1] = "  " + texts[1] + "  a "                        # leading / trailing / double spaces
+    texts[5] = "word"
+    hyps = dec.decode(probs.cuda(), sizes.cuda())
+    ratios = dec.error_ratios_device(probs.cuda(), sizes.cuda(), texts)
+    assert ratios is not None and ratios.is_cuda
+    cer = sum(dec.cer(t, h) for t, h in zip(texts, hyps)) / sum(len(t.replace(" ", "")) for t in texts)
+    wer = sum(dec.wer(t, h) for t, h in zip(texts, hyps)) / sum(len(t.split()) for t in texts)
+    lr = sum(map(len, hyps)) / sum(map(len, texts))
+    np.testing.assert_allclose(ratios.cpu().numpy(), [cer, wer, lr], rtol=1e-6)
+    assert dec.error_ratios_device(probs.cuda(), sizes.cuda(), ["tab\there"] * N) is None     # exotic whitespace -> host path
+    with pytest.raises(ZeroDivisionError):
+        dec.error_ratios_device(probs.cuda(), sizes.cuda(), [" "] * N)

@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libw2l_sm100.so")
-SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu"]
+SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu", "metrics.cu"]
 _lock = threading.Lock()
 _lib = None
 
@@ -77,6 +77,9 @@ SIGNATURES = {
     "w2l_greedy_decode_workspace_bytes": (c_size, [c_i64, c_i64]),
     "w2l_greedy_decode": (c_i32, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                   c_size, c_ptr]),
+    "w2l_string_metrics_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "w2l_string_metrics": (c_i32, [c_ptr, c_ptr, c_i64, c_i64, c_i32, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_size,
+                                   c_ptr]),
     "w2l_ctc_loss_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "w2l_ctc_loss": (c_i32, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_i32, c_i32,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),

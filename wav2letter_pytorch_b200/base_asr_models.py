@@ -56,10 +56,17 @@ class ConvCTCASR(_Base):
 
     # ---- metrics: greedy transcripts (CUDA argmax+collapse) scored on the host against the reference texts
     def add_string_metrics(self, out, output_lengths, texts, prefix):
-        hyps = self.ctc_decoder.decode(out, output_lengths)
-        if random.random() < self.print_decoded_prob:
-            print("reference: %s\ndecoded  : %s" % (texts[0], hyps[0]))
         dec = self.ctc_decoder
+        show = random.random() < self.print_decoded_prob
+        if not show and out.is_cuda and hasattr(dec, "error_ratios_device"):
+            # decode + CER/WER entirely on the device: the logged values are 0-dim CUDA tensors (log_dict accepts them)
+            # and the step never waits for the GPU, unlike the reference's per-frame .item() loop + host Levenshtein
+            ratios = dec.error_ratios_device(out, output_lengths, texts)
+            if ratios is not None:
+                return {prefix + "_cer": ratios[0], prefix + "_wer": ratios[1], prefix + "_len_ratio": ratios[2]}
+        hyps = dec.decode(out, output_lengths)
+        if show:
+            print("reference: %s\ndecoded  : %s" % (texts[0], hyps[0]))
         if hasattr(dec, "error_ratio_sums"):          # one batched, threaded host call instead of 2*B scalar ones
             cer_num, cer_den, wer_num, wer_den = dec.error_ratio_sums(texts, hyps)
         else:

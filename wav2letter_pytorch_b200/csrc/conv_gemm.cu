@@ -15,6 +15,7 @@
 //   FWD   : D[t, co]  = sum_{j,ci} X[b, t+off+j*d, ci] * W[j, co, ci]      A = X  (K-major)   B = W[j] (K-major)
 //   DGRAD : D[u, ci]  = sum_{j,co} dY[b, u-off-j*d, co] * W[j, co, ci]     A = dY (K-major)   B = W[j] (MN-major)
 //   WGRAD : D[co, ci] = sum_{b,t}  dY[b, t, co] * X[b, t+off+j*d, ci]      A = dY (MN-major)  B = X    (MN-major)
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -31,7 +32,8 @@ constexpr int kBBytesMax = 256 * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kAccCols = 256;
 constexpr int kGemmThreads = 192;
-constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kAffBytes = 2 * 256 * 8;          // per-accumulator (scale, shift) of the tile's columns for the epilogue
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kAffBytes;
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
@@ -59,6 +61,9 @@ struct GemmParams {
   int32_t ldy;
   // wgrad
   int32_t splits;           // > 1: some tiles are shared between CTAs (dw pre-zeroed by the caller)
+  int32_t wg_rounds;        // wgrad: whole-tile rounds per CTA before the stream-K remainder
+  int32_t mn4d;             // wgrad: operands are loaded through 4-D maps (64 x rows x chunks x B), one TMA op each
+  int32_t dbg;              // development knobs (env W2L_DBG): 1 = fwd B tile as 64-row TMA boxes, 2 = skip epilogue stores
   int64_t dw_tap_stride;    // Cout*Cin
 };
 
@@ -75,52 +80,61 @@ struct Unit {
 template <int MODE>
 struct UnitIter {
   const GemmParams& p;
-  int tile;              // fwd/dgrad cursor
-  int64_t g, g_end;      // wgrad cursor in the global iteration space
+  int tile;              // whole-tile cursor (fwd/dgrad; wgrad's data-parallel rounds)
+  int tile_end;
+  int64_t g, g_end;      // wgrad stream-K cursor in the remainder iteration space
   int iters;             // K iterations per tile
   __device__ UnitIter(const GemmParams& p_) : p(p_) {
+    tile = blockIdx.x;
     if (MODE == MODE_WGRAD) {
       iters = p.B * p.kc_steps;
-      const int64_t total = (int64_t)p.num_tiles * iters;
-      g = total * blockIdx.x / gridDim.x;
-      g_end = total * (blockIdx.x + 1) / gridDim.x;
+      tile_end = p.wg_rounds * gridDim.x;
+      const int64_t rem = (int64_t)(p.num_tiles - tile_end) * iters;
+      g = rem * blockIdx.x / gridDim.x;
+      g_end = rem * (blockIdx.x + 1) / gridDim.x;
     } else {
       iters = p.k * p.kc_steps;
-      tile = blockIdx.x;
+      tile_end = p.num_tiles;
     }
   }
+  __device__ void decode_wgrad(int t, Unit& u) const {      // tap fastest: neighbouring CTAs share dy and (shifted) x rows
+    u.j = t % p.k;
+    t /= p.k;
+    u.n0 = (t % p.n_tiles) * p.BN;
+    u.m0 = (t / p.n_tiles) * kBlockM;
+    u.b = 0;
+  }
   __device__ bool next(Unit& u) {
+    if (tile < tile_end) {
+      int t = tile;
+      tile += gridDim.x;
+      u.it_begin = 0;
+      u.it_end = iters;
+      u.partial = false;
+      if (MODE == MODE_WGRAD) {
+        decode_wgrad(t, u);
+      } else {
+        const int mt = t % p.m_tiles;
+        t /= p.m_tiles;
+        u.b = t % p.B;
+        u.n0 = (t / p.B) * p.BN;
+        u.m0 = mt * kBlockM;
+        u.j = 0;
+      }
+      return true;
+    }
     if (MODE == MODE_WGRAD) {
       if (g >= g_end) return false;
-      int t = (int)(g / iters);
+      const int t = (int)(g / iters);
       u.it_begin = (int)(g - (int64_t)t * iters);
       const int64_t left = g_end - g;
       u.it_end = (int)((int64_t)(iters - u.it_begin) <= left ? iters : u.it_begin + left);
       u.partial = (u.it_begin != 0) || (u.it_end != iters);
       g += u.it_end - u.it_begin;
-      const int mt = t % p.m_tiles;
-      t /= p.m_tiles;
-      const int nt = t % p.n_tiles;
-      u.j = t / p.n_tiles;
-      u.m0 = mt * kBlockM;
-      u.n0 = nt * p.BN;
-      u.b = 0;
-      return true;
-    } else {
-      if (tile >= p.num_tiles) return false;
-      int t = tile;
-      tile += gridDim.x;
-      const int mt = t % p.m_tiles;
-      t /= p.m_tiles;
-      u.b = t % p.B;
-      u.n0 = (t / p.B) * p.BN;
-      u.m0 = mt * kBlockM;
-      u.j = 0;
-      u.it_begin = 0;
-      u.it_end = iters;
-      u.partial = false;
+      decode_wgrad(tile_end + t, u);
       return true;
     }
+    return false;
   }
 };
 
@@ -135,12 +149,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* s_aff = reinterpret_cast<float2*>(smem + kStages * kStageBytes + 256);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool kAMN = (MODE == MODE_WGRAD);
   constexpr bool kBMN = (MODE != MODE_FWD);
   const int b_chunks = (p.BN + 63) >> 6;
-  const uint32_t stage_tx = kABytes + (kBMN ? (uint32_t)b_chunks * 8192u : (uint32_t)p.BN * 128u);
+  const uint32_t stage_tx = kABytes + ((kBMN || (p.dbg & 1)) ? (uint32_t)b_chunks * 8192u : (uint32_t)p.BN * 128u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -179,15 +194,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           uint8_t* sb = sa + kABytes;
           if (MODE == MODE_WGRAD) {
             const int b = it / p.kc_steps, t0 = (it - b * p.kc_steps) * kBlockK;
-            tma_load_3d(sa, &p.tmA, &full_bar[stage], u.m0, t0, b);
-            tma_load_3d(sa + 8192, &p.tmA, &full_bar[stage], u.m0 + 64, t0, b);
             const int xr = t0 + p.b_row_off + u.j * p.dil;
-            for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], u.n0 + c * 64, xr, b);
+            if (p.mn4d) {       // one TMA op per operand: box (64 ch, 64 rows, chunks, 1) lands as [chunk][row][64]
+              tma_load_4d(sa, &p.tmA, &full_bar[stage], 0, t0, u.m0 >> 6, b);
+              tma_load_4d(sb, &p.tmB, &full_bar[stage], 0, xr, u.n0 >> 6, b);
+            } else {
+              tma_load_3d(sa, &p.tmA, &full_bar[stage], u.m0, t0, b);
+              tma_load_3d(sa + 8192, &p.tmA, &full_bar[stage], u.m0 + 64, t0, b);
+              for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], u.n0 + c * 64, xr, b);
+            }
           } else {
             const int j = it / p.kc_steps, kc = it - j * p.kc_steps;
             tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * kBlockK, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
             if (MODE == MODE_FWD) {
-              tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0, j);
+              if (p.dbg & 1) {
+                for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0 + c * 64, j);
+              } else {
+                tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0, j);
+              }
             } else {
               for (int c = 0; c < b_chunks; ++c)
                 tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], u.n0 + c * 64, kc * kBlockK, j);
@@ -248,9 +272,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     const int row = lane_base + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // fused epilogue: v = clamp(acc * scale + shift', lo, hi) with shift' = bias * scale + shift (kernel-uniform switches)
+    const bool has_aff = (MODE == MODE_FWD) && (p.bias != nullptr || p.scale != nullptr);
+    const bool has_act = (MODE == MODE_FWD) && p.act != W2L_ACT_NONE;
+    const float act_hi = p.act == W2L_ACT_CLAMP20 ? 20.f : INFINITY;
+    const int ep_tid = threadIdx.x - 64;                       // 0..127 within the epilogue warps
     UnitIter<MODE> units(p);
     Unit tc;
     while (units.next(tc)) {
+      if (has_aff) {                                           // stage this tile's per-channel constants (broadcast reads below)
+        for (int c = ep_tid; c < p.BN; c += 128) {
+          const int n = min(tc.n0 + c, p.N_valid - 1);
+          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
+          const float sh = (p.bias ? __ldg(p.bias + n) * sc : 0.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
+          s_aff[acc * 256 + c] = make_float2(sc, sh);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
@@ -289,19 +327,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           }
         } else {
           float v[32];
+          if (has_aff) {
+            const float2* aff = s_aff + acc * 256 + c0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[i]);
-            const int n = nbase + i;
-            if (MODE == MODE_FWD && n < p.N_valid) {
-              if (p.bias) x += __ldg(p.bias + n);
-              if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
-              if (p.act == W2L_ACT_RELU) x = fmaxf(x, 0.f);
-              else if (p.act == W2L_ACT_CLAMP20) x = fminf(fmaxf(x, 0.f), 20.f);
+            for (int i = 0; i < 32; ++i) {
+              const float2 a = aff[i];
+              v[i] = fmaf(__uint_as_float(r[i]), a.x, a.y);
             }
-            v[i] = x;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           }
-          if (row_ok) {
+          if (has_act) {   // NaN passes through, as torch.clamp / relu do
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (v[i] != v[i]) ? v[i] : fminf(fmaxf(v[i], 0.f), act_hi);
+          }
+          if (row_ok && !(p.dbg & 2)) {
             const int64_t off = (int64_t)tc.b * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
             const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
             if (p.y_dtype == W2L_DTYPE_BF16) {
@@ -381,20 +422,22 @@ static int check_desc(const w2l_conv_desc* d, const char* who) {
   return W2L_OK;
 }
 
-// Stream-K launch plan for wgrad: grid size and whether any tile is shared between CTAs (=> dw must be zero-filled).
-static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* zero_out) {
+// Launch plan for wgrad: `rounds` whole tiles per CTA (data parallel, all CTAs sweep (b, t) in step -> L2 reuse), then the
+// remaining tiles*iters iterations are cut into equal contiguous ranges (stream-K).  zero != 0 => dw must be pre-zeroed.
+static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* rounds_out, int* zero_out) {
   const int n_pad = (d->Cin + 15) / 16 * 16;
   const int bn = pick_bn(n_pad);
   const int64_t tiles = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * (n_pad / bn);
   const int64_t iters = (int64_t)d->B * ((d->T_out + kBlockK - 1) / kBlockK);
-  const int64_t total = tiles * iters;
   int64_t grid = num_sms();
   const int64_t min_iters = 32;                       // keep the per-CTA mainloop long enough to amortise the epilogue
-  if (total / grid < min_iters) grid = total / min_iters > 0 ? total / min_iters : 1;
-  if (grid > tiles && tiles * iters / grid < min_iters) grid = tiles;
+  if (tiles * iters / grid < min_iters) grid = tiles * iters / min_iters > 0 ? tiles * iters / min_iters : 1;
+  const int64_t rounds = tiles / grid;
+  const int64_t rem_tiles = tiles - rounds * grid;
   if (bn_out) *bn_out = bn;
   if (grid_out) *grid_out = (int)grid;
-  if (zero_out) *zero_out = (total % grid != 0) || ((total / grid) % iters != 0);
+  if (rounds_out) *rounds_out = (int)rounds;
+  if (zero_out) *zero_out = rem_tiles > 0;
 }
 
 }  // namespace w2l
@@ -420,9 +463,13 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   }
   p.BN = pick_bn(d->Cout_pad);
   {
+    const char* e = getenv("W2L_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
-    uint32_t box[3] = {kBlockK, (uint32_t)p.BN, 1};
+    uint32_t box[3] = {kBlockK, (p.dbg & 1) ? 64u : (uint32_t)p.BN, 1};
     rc = make_tensor_map(&p.tmB, w, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
@@ -550,7 +597,7 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
   if (!d || d->B < 1 || d->T_out < 1 || d->k < 1) return 1;
   int zero = 0;
-  w2l::wgrad_plan(d, nullptr, nullptr, &zero);
+  w2l::wgrad_plan(d, nullptr, nullptr, nullptr, &zero);
   return zero ? 2 : 1;
 }
 
@@ -562,25 +609,45 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
   W2L_REQUIRE(d->ldy >= 64 && d->ldy % 8 == 0, "conv1d_wgrad: dy row pitch %d must be >= 64 and a multiple of 8", d->ldy);
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  {
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
-    uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->T_out, (uint64_t)d->B};   // columns >= Cout read as zero
-    uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
-    uint32_t box[3] = {64, kBlockK, 1};
-    rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
-    if (rc) return rc;
+  const __nv_bfloat16* dy_base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+  // 4-D maps need whole 64-channel chunks (a chunk that ran past the row end would alias the next row)
+  p.mn4d = (d->ldy % 64 == 0) && (d->Cin % 64 == 0) && (d->Cout == d->ldy || d->Cout_pad == d->ldy);
+  int bn = 0, grid = 0, rounds = 0, zero = 0;
+  wgrad_plan(d, &bn, &grid, &rounds, &zero);
+  if (p.mn4d) {
+    {
+      uint64_t dims[4] = {64, (uint64_t)d->T_out, (uint64_t)d->ldy / 64, (uint64_t)d->B};
+      uint64_t str[3] = {(uint64_t)d->ldy * 2, 128, (uint64_t)d->y_rows * d->ldy * 2};
+      uint32_t box[4] = {64, kBlockK, 2, 1};
+      rc = make_tensor_map(&p.tmA, dy_base, 2, 4, dims, str, box, true);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {64, (uint64_t)d->x_rows, (uint64_t)d->Cin / 64, (uint64_t)d->B};
+      uint64_t str[3] = {(uint64_t)d->Cin * 2, 128, (uint64_t)d->x_rows * d->Cin * 2};
+      uint32_t box[4] = {64, kBlockK, (uint32_t)((bn + 63) / 64), 1};
+      rc = make_tensor_map(&p.tmB, x, 2, 4, dims, str, box, true);
+      if (rc) return rc;
+    }
+  } else {
+    {
+      uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->T_out, (uint64_t)d->B};   // columns >= Cout read as zero
+      uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
+      uint32_t box[3] = {64, kBlockK, 1};
+      rc = make_tensor_map(&p.tmA, dy_base, 2, 3, dims, str, box, true);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
+      uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
+      uint32_t box[3] = {64, kBlockK, 1};
+      rc = make_tensor_map(&p.tmB, x, 2, 3, dims, str, box, true);
+      if (rc) return rc;
+    }
   }
-  {
-    uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
-    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
-    uint32_t box[3] = {64, kBlockK, 1};
-    rc = make_tensor_map(&p.tmB, x, 2, 3, dims, str, box, true);
-    if (rc) return rc;
-  }
-  int bn = 0, grid = 0, zero = 0;
-  wgrad_plan(d, &bn, &grid, &zero);
   p.BN = bn;
   p.splits = zero ? 2 : 1;
+  p.wg_rounds = rounds;
   const int n_pad = (d->Cin + 15) / 16 * 16;
   p.B = d->B;
   p.m_tiles = (d->Cout + kBlockM - 1) / kBlockM;

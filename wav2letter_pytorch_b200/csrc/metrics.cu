@@ -1,0 +1,181 @@
+// GPU-side WER/CER bookkeeping for the training step.
+// The reference decodes and scores every step on the host (base_asr_models.py:53-69: GreedyDecoder.decode, then
+// Levenshtein per utterance), which on a GPU means a device sync plus milliseconds of idle accelerator per step.  Here the
+// collapsed token ids never leave the device: they are split into the character stream without spaces (CER) and a stream of
+// 64-bit word hashes (WER), scored against the encoded reference by a wavefront Levenshtein kernel, and reduced to the three
+// logged ratios.  The host only reads the result when (if) it formats the log.
+#include "common.cuh"
+
+namespace w2l {
+
+__device__ __forceinline__ unsigned long long hash_step(unsigned long long h, int sym) {
+  return (h ^ (unsigned long long)(unsigned)(sym + 1)) * 1099511628211ull;     // FNV-1a over symbol ids
+}
+constexpr unsigned long long kHashSeed = 1469598103934665603ull;
+
+// one thread per utterance: tokens[n, :counts[n]] -> chars (ids != space) and word hashes (runs of ids != space)
+__global__ void metrics_split_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ counts, int N, int T, int space,
+                                     int32_t* __restrict__ chars, int32_t* __restrict__ n_chars, long long* __restrict__ words,
+                                     int32_t* __restrict__ n_words) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int32_t* tk = tokens + (int64_t)n * T;
+  int32_t* ch = chars + (int64_t)n * T;
+  long long* wd = words + (int64_t)n * T;
+  const int cnt = max(0, min(T, counts[n]));
+  int nc = 0, nw = 0;
+  bool in_word = false;
+  unsigned long long h = kHashSeed;
+  for (int i = 0; i < cnt; ++i) {
+    const int s = tk[i];
+    if (s == space) {
+      if (in_word) wd[nw++] = (long long)h;
+      in_word = false;
+      h = kHashSeed;
+    } else {
+      ch[nc++] = s;
+      h = hash_step(h, s);
+      in_word = true;
+    }
+  }
+  if (in_word) wd[nw++] = (long long)h;
+  n_chars[n] = nc;
+  n_words[n] = nw;
+}
+
+// Wavefront Levenshtein: one CTA per pair; thread j owns column j+1 of the DP table (reference symbol j); anti-diagonals are
+// swept with three rolling buffers in shared memory.  dist(a[0:m], b[0:n]); n <= blockDim.x.
+template <typename Sym>
+__global__ void edit_distance_kernel(const Sym* __restrict__ hyp, const int32_t* __restrict__ hyp_len, int64_t hyp_stride,
+                                     const Sym* __restrict__ ref, const int32_t* __restrict__ ref_len, int64_t ref_stride,
+                                     int32_t* __restrict__ out) {
+  extern __shared__ int32_t diag[];                 // [3][blockDim.x + 1]
+  const int pair = blockIdx.x;
+  const int m = hyp_len[pair], n = ref_len[pair];
+  const Sym* a = hyp + (int64_t)pair * hyp_stride;
+  const Sym* b = ref + (int64_t)pair * ref_stride;
+  if (m == 0 || n == 0) {
+    if (threadIdx.x == 0) out[pair] = m + n;
+    return;
+  }
+  const int W = blockDim.x + 1;
+  const int j = threadIdx.x;                         // column j+1 (1-based), valid when j < n
+  const Sym bj = j < n ? b[j] : Sym(0);
+  // D[i][c] with i = row (0..m), c = column (0..n); diagonal d = i + c.  buffers hold D[d - c][c] indexed by c.
+  int32_t* d2 = diag;            // diagonal d-2
+  int32_t* d1 = diag + W;        // diagonal d-1
+  int32_t* d0 = diag + 2 * W;    // diagonal d
+  if (threadIdx.x == 0) {
+    d2[0] = 0;                   // D[0][0]   (diag 0)
+    d1[0] = 1;                   // D[1][0]   (diag 1)
+    d1[1] = 1;                   // D[0][1]
+  }
+  __syncthreads();
+  for (int d = 2; d <= m + n; ++d) {
+    const int c = j + 1, i = d - c;
+    if (c <= n) {
+      if (i == 0) {
+        d0[c] = c;                                                   // first row
+      } else if (i > 0 && i <= m) {
+        const int sub = d2[c - 1] + (a[i - 1] != bj);                // D[i-1][c-1]
+        const int del = d1[c] + 1;                                   // D[i-1][c]
+        const int ins = d1[c - 1] + 1;                               // D[i][c-1]
+        d0[c] = min(sub, min(del, ins));
+      }
+    }
+    if (threadIdx.x == 0 && d <= m) d0[0] = d;                       // first column
+    __syncthreads();
+    int32_t* t = d2;
+    d2 = d1;
+    d1 = d0;
+    d0 = t;
+  }
+  if (threadIdx.x == 0) out[pair] = d1[n];                           // D[m][n] lives on the last diagonal
+}
+
+// ratios[0] = cer, [1] = wer, [2] = len_ratio
+__global__ void metrics_finalize_kernel(const int32_t* __restrict__ cer_d, const int32_t* __restrict__ wer_d,
+                                        const int32_t* __restrict__ counts, int N, float cer_den, float wer_den, float len_den,
+                                        float* __restrict__ ratios) {
+  __shared__ long long s[3][32];
+  long long c = 0, w = 0, l = 0;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    c += cer_d[n];
+    w += wer_d[n];
+    l += counts[n];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    w += __shfl_xor_sync(0xffffffffu, w, o);
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s[0][threadIdx.x >> 5] = c;
+    s[1][threadIdx.x >> 5] = w;
+    s[2][threadIdx.x >> 5] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tc = 0, tw = 0, tl = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      tc += s[0][i];
+      tw += s[1][i];
+      tl += s[2][i];
+    }
+    ratios[0] = (float)((double)tc / (double)cer_den);
+    ratios[1] = (float)((double)tw / (double)wer_den);
+    ratios[2] = (float)((double)tl / (double)len_den);
+  }
+}
+
+}  // namespace w2l
+
+extern "C" {
+
+size_t w2l_string_metrics_workspace_bytes(int64_t N, int64_t T, int64_t ref_stride) {
+  // words (hyp [N,T] + ref [N,S]) i64, chars (hyp + ref) i32, 6 x [N] i32 counters
+  return (size_t)((N * T + N * ref_stride) * 12 + 6 * N * 4 + 256);
+}
+
+int w2l_string_metrics(const int32_t* tokens, const int32_t* counts, int64_t N, int64_t T, int32_t space_index,
+                       const int32_t* ref_ids, const int32_t* ref_lens, int64_t ref_stride, float cer_den, float wer_den,
+                       float len_den, float* ratios, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(tokens && counts && ref_ids && ref_lens && ratios && workspace, "string_metrics: null pointer");
+  W2L_REQUIRE(N >= 1 && T >= 1, "string_metrics: bad shape");
+  W2L_REQUIRE(ref_stride >= 1 && ref_stride <= 1023, "string_metrics: references longer than 1023 symbols are not supported on the device path");
+  W2L_REQUIRE(workspace_bytes >= w2l_string_metrics_workspace_bytes(N, T, ref_stride), "string_metrics: workspace too small");
+  W2L_REQUIRE(((uintptr_t)workspace & 7) == 0, "string_metrics: workspace must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  long long* h_words = (long long*)ws;
+  long long* r_words = h_words + N * T;
+  int32_t* h_chars = (int32_t*)(r_words + N * ref_stride);
+  int32_t* r_chars = h_chars + N * T;
+  int32_t* h_nc = r_chars + N * ref_stride;
+  int32_t* h_nw = h_nc + N;
+  int32_t* r_nc = h_nw + N;
+  int32_t* r_nw = r_nc + N;
+  int32_t* cer_d = r_nw + N;
+  int32_t* wer_d = cer_d + N;
+  const unsigned blocks = (unsigned)((N + 63) / 64);
+  metrics_split_kernel<<<blocks, 64, 0, st>>>(tokens, counts, (int)N, (int)T, space_index, h_chars, h_nc, h_words, h_nw);
+  int rc = after_launch("metrics_split_kernel<hyp>");
+  if (rc) return rc;
+  metrics_split_kernel<<<blocks, 64, 0, st>>>(ref_ids, ref_lens, (int)N, (int)ref_stride, space_index, r_chars, r_nc, r_words, r_nw);
+  rc = after_launch("metrics_split_kernel<ref>");
+  if (rc) return rc;
+  const int threads = (int)((ref_stride + 31) / 32 * 32);
+  const size_t smem = 3 * (size_t)(threads + 1) * sizeof(int32_t);
+  edit_distance_kernel<int32_t><<<(unsigned)N, threads, smem, st>>>(h_chars, h_nc, T, r_chars, r_nc, ref_stride, cer_d);
+  rc = after_launch("edit_distance_kernel<chars>");
+  if (rc) return rc;
+  edit_distance_kernel<long long><<<(unsigned)N, threads, smem, st>>>(h_words, h_nw, T, r_words, r_nw, ref_stride, wer_d);
+  rc = after_launch("edit_distance_kernel<words>");
+  if (rc) return rc;
+  metrics_finalize_kernel<<<1, 256, 0, st>>>(cer_d, wer_d, counts, (int)N, cer_den, wer_den, len_den, ratios);
+  return after_launch("metrics_finalize_kernel");
+}
+
+}  // extern "C"

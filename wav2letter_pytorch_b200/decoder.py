@@ -99,6 +99,76 @@ class GreedyDecoder(Decoder):
         _, tokens, offsets, counts = F.greedy_decode(probs.detach(), sizes, self.blank_index)
         return tokens, offsets, counts
 
+    # ---- device-side scoring (no host sync): CER / WER / length ratio as a CUDA tensor
+    def _encode_refs(self, texts):
+        """texts -> (ids [N,S] int32 pinned, lens [N] int32 pinned, cer_den, wer_den, len_den) or None when the device path
+        does not apply (multi-character labels, exotic whitespace, references longer than 1023)."""
+        C = len(self.labels)
+        if getattr(self, "_lut", None) is None:
+            if any(len(l) != 1 for l in self.labels) or " " not in self.labels:
+                self._lut = False
+            else:
+                lut = np.arange(0x10000, dtype=np.int64) + C
+                for i, ch in enumerate(self.labels):
+                    if ord(ch) < 0x10000:
+                        lut[ord(ch)] = i
+                self._lut = lut.astype(np.int32)
+                self._pins = []
+        if self._lut is False:
+            return None
+        n = len(texts)
+        smax = max(1, max(len(t) for t in texts))
+        if smax > 1023:
+            return None
+        words = 0
+        for t in texts:
+            w = len(t.split())
+            if w != sum(1 for x in t.split(" ") if x):          # whitespace other than ' ' present: host path
+                return None
+            words += w
+        slot = None
+        for s in self._pins:                                    # rotate pinned staging buffers (CPU may run ahead of the GPU)
+            if s[0].shape[0] >= n and s[0].shape[1] >= smax and (s[2] is None or s[2].query()):
+                slot = s
+                break
+        if slot is None:
+            slot = [torch.zeros((n, max(smax, 256)), dtype=torch.int32).pin_memory(), torch.zeros((n,), dtype=torch.int32).pin_memory(), None]
+            self._pins.append(slot)
+        ids, lens = slot[0].numpy(), slot[1].numpy()
+        for i, t in enumerate(texts):
+            cp = np.frombuffer(t.encode("utf-32-le"), dtype=np.int32)
+            lens[i] = len(cp)
+            ids[i, :len(cp)] = np.where(cp < 0x10000, self._lut[np.minimum(cp, 0xFFFF)], cp + C)
+        cer_den = sum(len(t) - t.count(" ") for t in texts)
+        return slot, smax, cer_den, words, sum(len(t) for t in texts)
+
+    def error_ratios_device(self, probs, sizes, texts):
+        """Greedy-decodes ``probs`` and scores the transcripts against ``texts`` entirely on the device.  Returns a CUDA
+        fp32 tensor [3] = (cer, wer, len_ratio) -- the three numbers ConvCTCASR.add_string_metrics logs -- or None when the
+        device path does not apply.  No device->host synchronisation."""
+        enc = self._encode_refs(texts)
+        if enc is None:
+            return None
+        slot, smax, cer_den, wer_den, len_den = enc
+        if cer_den == 0 or wer_den == 0 or len_den == 0:
+            raise ZeroDivisionError("division by zero")            # what the reference's host arithmetic raises
+        tokens, _offsets, counts = self.decode_tokens(probs, sizes)
+        dev = tokens.device
+        N, T = tokens.shape
+        S = slot[0].shape[1]
+        ref_ids = slot[0].to(dev, non_blocking=True)
+        ref_lens = slot[1].to(dev, non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record()
+        lib = _lib.load()
+        ws = torch.empty((lib.w2l_string_metrics_workspace_bytes(N, T, S) + 7) // 8, dtype=torch.int64, device=dev)
+        ratios = torch.empty(3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.w2l_string_metrics(F._ptr(tokens), F._ptr(counts), N, T, self.space_index, F._ptr(ref_ids), F._ptr(ref_lens), S,
+                                              float(cer_den), float(wer_den), float(len_den), F._ptr(ratios), F._ptr(ws), ws.numel() * 8,
+                                              F._stream()), "string_metrics")
+        return ratios
+
     def decode(self, probs, sizes=None, return_offsets=False):
         """probs [N,T,C] (or [T,C]) -> list[str] (and list[[IntTensor]] of frame offsets), decoder.py:121-145."""
         tokens, offsets, counts = self.decode_tokens(probs, sizes)
