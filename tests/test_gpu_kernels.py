@@ -181,6 +181,9 @@ CONV_CASES = [
     (2, 150, 64, 96, 7, 2, (6, 6)),
     (1, 128, 704, 256, 1, 1, (0, 0)),
     (2, 97, 256, 384, 3, 1, (1, 1)),
+    (1, 200, 640, 640, 3, 1, (1, 1)),          # N = 640: 256-wide tiles with a partly empty last tile
+    (2, 140, 896, 896, 2, 2, (1, 1)),          # N = 896: 224-wide tiles (fwd/dgrad), 256-wide 4-D chunked tiles (wgrad)
+    (1, 150, 704, 320, 1, 1, (0, 0)),
 ]
 
 

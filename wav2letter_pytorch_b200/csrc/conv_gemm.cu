@@ -295,10 +295,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const int m = tc.m0 + row;
       const bool row_ok = m < p.M_valid;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int nbase = tc.n0 + c0;
+        if (nbase >= p.N_valid) break;                       // padded part of a last N tile
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c0, r);
         tmem_ld_wait();
-        const int nbase = tc.n0 + c0;
         if (MODE == MODE_WGRAD) {
           if (row_ok) {
             float* dst = reinterpret_cast<float*>(p.y) + (int64_t)tc.j * p.dw_tap_stride + (int64_t)m * p.ldy + nbase;
@@ -391,11 +392,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 }
 
 // ---------------------------------------------------------------- host side
-static int pick_bn(int n_pad16) {
-  // largest multiple of 16 (<= 256) dividing the padded N extent
-  for (int bn = 256; bn >= 16; bn -= 16)
-    if (n_pad16 % bn == 0) return bn;
-  return 16;
+// N-tile width: a multiple of `multiple` (16 = UMMA granularity; 64 when operands come through 4-D chunked TMA maps).
+// Narrow tiles run the tensor pipe below peak (the A tile is re-read from shared memory per MMA whatever N is; measured
+// 1.55 / 1.40 / 1.11 PFLOP/s at N = 256 / 224 / 160), so a wider tile with a partly empty last tile can win: minimise
+// (tiles * bn) / eff(bn) with the linear fit eff = 1 - 0.75 * (256 - bn) / 256.
+static int pick_bn(int n, int multiple) {
+  const int n_round = (n + multiple - 1) / multiple * multiple;
+  int best = multiple;
+  double best_cost = 1e30;
+  for (int bn = multiple; bn <= 256; bn += multiple) {
+    if (bn > n_round) break;
+    const int tiles = (n + bn - 1) / bn;
+    const double eff = 1.0 - 0.75 * (256 - bn) / 256.0;
+    const double cost = (double)tiles * bn / eff;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 template <int MODE>
@@ -422,12 +437,17 @@ static int check_desc(const w2l_conv_desc* d, const char* who) {
   return W2L_OK;
 }
 
+// 4-D chunked maps need whole 64-channel chunks (a chunk that ran past the row end would alias the next row)
+static bool wgrad_mn4d(const w2l_conv_desc* d) {
+  return (d->ldy % 64 == 0) && (d->Cin % 64 == 0) && (d->Cout == d->ldy || d->Cout_pad == d->ldy);
+}
+
 // Launch plan for wgrad: `rounds` whole tiles per CTA (data parallel, all CTAs sweep (b, t) in step -> L2 reuse), then the
 // remaining tiles*iters iterations are cut into equal contiguous ranges (stream-K).  zero != 0 => dw must be pre-zeroed.
 static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* rounds_out, int* zero_out) {
   const int n_pad = (d->Cin + 15) / 16 * 16;
-  const int bn = pick_bn(n_pad);
-  const int64_t tiles = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * (n_pad / bn);
+  const int bn = pick_bn(n_pad, wgrad_mn4d(d) ? 64 : 16);
+  const int64_t tiles = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * ((n_pad + bn - 1) / bn);
   const int64_t iters = (int64_t)d->B * ((d->T_out + kBlockK - 1) / kBlockK);
   int64_t grid = num_sms();
   const int64_t min_iters = 32;                       // keep the per-CTA mainloop long enough to amortise the epilogue
@@ -461,7 +481,7 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
     rc = make_tensor_map(&p.tmA, x, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
-  p.BN = pick_bn(d->Cout_pad);
+  p.BN = pick_bn(d->Cout_pad, 16);
   {
     const char* e = getenv("W2L_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -475,7 +495,7 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   }
   p.B = d->B;
   p.m_tiles = (d->T_out + kBlockM - 1) / kBlockM;
-  p.n_tiles = d->Cout_pad / p.BN;
+  p.n_tiles = (d->Cout_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
   p.kc_steps = (d->Cin + kBlockK - 1) / kBlockK;
@@ -516,7 +536,7 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
     if (rc) return rc;
   }
   const int n_pad = (d->Cin + 15) / 16 * 16;
-  p.BN = pick_bn(n_pad);
+  p.BN = pick_bn(n_pad, 16);
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
@@ -526,7 +546,7 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
   }
   p.B = d->B;
   p.m_tiles = (d->x_rows + kBlockM - 1) / kBlockM;
-  p.n_tiles = n_pad / p.BN;
+  p.n_tiles = (n_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
   p.kc_steps = (d->Cout_pad + kBlockK - 1) / kBlockK;
@@ -565,7 +585,7 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
     if (rc) return rc;
   }
   const int n_pad = (d->Cin + 15) / 16 * 16;
-  p.BN = pick_bn(n_pad);
+  p.BN = pick_bn(n_pad, 16);
   {
     uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)n_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cout_pad * 2, (uint64_t)n_pad * d->Cout_pad * 2};
@@ -575,7 +595,7 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   }
   p.B = d->B;
   p.m_tiles = (d->x_rows + kBlockM - 1) / kBlockM;
-  p.n_tiles = n_pad / p.BN;
+  p.n_tiles = (n_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
   p.kc_steps = (d->Cout_pad + kBlockK - 1) / kBlockK;
@@ -610,8 +630,7 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const __nv_bfloat16* dy_base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
-  // 4-D maps need whole 64-channel chunks (a chunk that ran past the row end would alias the next row)
-  p.mn4d = (d->ldy % 64 == 0) && (d->Cin % 64 == 0) && (d->Cout == d->ldy || d->Cout_pad == d->ldy);
+  p.mn4d = wgrad_mn4d(d);
   int bn = 0, grid = 0, rounds = 0, zero = 0;
   wgrad_plan(d, &bn, &grid, &rounds, &zero);
   if (p.mn4d) {
@@ -651,7 +670,7 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
   const int n_pad = (d->Cin + 15) / 16 * 16;
   p.B = d->B;
   p.m_tiles = (d->Cout + kBlockM - 1) / kBlockM;
-  p.n_tiles = n_pad / p.BN;
+  p.n_tiles = (n_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
   p.kc_steps = (d->T_out + kBlockK - 1) / kBlockK;
