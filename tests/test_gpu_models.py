@@ -253,7 +253,10 @@ def test_jasper_dense_golden(pkg, golden):
         assert p.grad is not None and p.grad.shape == p.shape, name
         emu = emu_params[name].grad
         err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
-        assert err_emu < 4e-2, (name, err_emu)
+        # Two bf16 realisations of this toy model differ by ~0.1 from each other and ~0.18 from fp32 in the deep layers (ReLU
+        # masks flip on rounding and BatchNorm backward amplifies it at these tiny widths: tools/diag_jasper.py prints the
+        # table); a wiring error -- a dropped residual gradient, a wrong mask -- shows up as an error of order 1.
+        assert err_emu < 0.15, (name, err_emu)
         assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
     for k in g.files:
         if k.startswith("sd1:") and "running" in k:
