@@ -195,7 +195,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        from wav2letter_pytorch_b200.distributed import init_process_group
+        init_process_group("nccl", device=dev, max_ctas=int(os.environ.get("W2L_NCCL_MAX_CTAS", "8")))
 
     def build(mid_layers):
         cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers, "optimizer=novograd"]).model

@@ -28,37 +28,67 @@ def dense_view(t):
 
 
 class GradientReducer:
-    def __init__(self, model, process_group=None):
+    """``small_numel``: gradients below this size (biases, BatchNorm affine parameters) are packed into one flat buffer
+    and reduced with a single collective in ``finish()`` instead of ~60 latency-bound launches per step."""
+
+    def __init__(self, model, process_group=None, small_numel=65536):
         if not dist.is_initialized():
             raise RuntimeError("GradientReducer needs an initialised torch.distributed process group")
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.use_avg = dist.get_backend(process_group) == "nccl"
-        self.pending = []
-        self.hooks = []
+        self.small_numel = small_numel
+        self.pending, self.small, self.hooks = [], [], []
         for p in model.parameters():
             if p.requires_grad:
                 self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
+    def _reduce(self, t):
+        op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM      # gloo (CPU tests): sum now, scale in finish()
+        return dist.all_reduce(t, op=op, group=self.group, async_op=True)
+
     def _on_grad(self, p):
         g = dense_view(p.grad)
-        if self.use_avg:
-            work = dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        else:                       # gloo (CPU tests): sum now, scale in finish()
-            work = dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append((work, g))
+        if g.numel() < self.small_numel:
+            self.small.append(g)
+        else:
+            self.pending.append((self._reduce(g), g))
 
     def finish(self):
+        flat = None
+        if self.small:
+            flat = torch.cat([g.reshape(-1) for g in self.small])
+            self.pending.append((self._reduce(flat), flat))
         for work, g in self.pending:
             work.wait()
             if not self.use_avg:
                 g.div_(self.world)
+        if flat is not None:
+            torch._foreach_copy_([g.reshape(-1) for g in self.small], list(torch.split(flat, [g.numel() for g in self.small])))
         self.pending.clear()
+        self.small.clear()
 
     def remove(self):
         for h in self.hooks:
             h.remove()
         self.hooks.clear()
+
+
+def init_process_group(backend="nccl", device=None, max_ctas=8, **kwargs):
+    """``dist.init_process_group`` with NCCL limited to a few CTAs per collective: the gradient all-reduce of one layer
+    (<= 93 MB) has the whole remaining backward pass to hide behind, while every SM it occupies slows the persistent
+    one-CTA-per-SM GEMM kernels running next to it."""
+    if backend == "nccl" and max_ctas:
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = int(max_ctas)
+            opts.config.min_ctas = 1
+            kwargs.setdefault("pg_options", opts)
+        except Exception:  # noqa: BLE001  (older torch: fall back to NCCL's defaults)
+            pass
+    if device is not None:
+        kwargs.setdefault("device_id", device)
+    return dist.init_process_group(backend, **kwargs)
 
 
 def broadcast_buffers(model, src=0, process_group=None):
