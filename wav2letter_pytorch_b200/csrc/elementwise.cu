@@ -195,105 +195,137 @@ struct BnActArgs {
   const int32_t* lens;
 };
 
-struct ChanConsts {
-  float sc[8], sh[8], rsc[8], rsh[8];
+// Each thread walks its rows four at a time (rows r, r+8, r+16, r+24 of the block's range) and issues all 16-byte loads of
+// the four rows before touching any of them: with ~2 x 256 threads resident per SM that keeps ~64 KB in flight, which is
+// what HBM3e needs to stream (a one-row-at-a-time loop measured 17% of peak, profiles/).
+constexpr int kRowsPerIter = 4;
+
+struct RowIn {
+  uint4 z, r, d0;              // conv output, residual, upstream gradient row (mirror rows are fetched on demand: <8% of rows)
+  int b, t;
+  bool live;
 };
 
-__device__ __forceinline__ void load_consts(const BnActArgs& a, int c, ChanConsts& k) {
-  load8f(a.scale + c, k.sc);
-  load8f(a.shift + c, k.sh);
-  if (a.res) {
-    load8f(a.res_scale + c, k.rsc);
-    load8f(a.res_shift + c, k.rsh);
-  }
+__device__ __forceinline__ void row_bt(int r, int T, int& b, int& t) {
+  b = r / T;
+  t = r - b * T;
 }
 
-// value entering the activation ("pre": BN output [+ residual], dropout applied) for 8 channels of row (b, t)
-__device__ __forceinline__ void bn_pre8(const BnActArgs& a, const ChanConsts& k, int64_t e, float (&pre)[8], float (&mult)[8],
-                                        float (&zv)[8]) {
-  unpack8(__ldg(reinterpret_cast<const uint4*>(a.z + e)), zv);
+template <bool HAS_RES>
+__device__ __forceinline__ void load_fwd_row(const BnActArgs& a, int r, int r_end, int c, RowIn& in) {
+  in.live = r < r_end;
+  if (!in.live) return;
+  row_bt(r, a.T, in.b, in.t);
+  const int64_t e = (int64_t)r * a.C + c;
+  in.z = __ldg(reinterpret_cast<const uint4*>(a.z + e));
+  if (HAS_RES) in.r = __ldg(reinterpret_cast<const uint4*>(a.res + e));
+}
+
+template <bool HAS_RES>
+__device__ __forceinline__ void load_bwd_row(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, int r, int r_end, int c, RowIn& in) {
+  load_fwd_row<HAS_RES>(a, r, r_end, c, in);
+  if (!in.live) return;
+  const int Tp = a.pl + a.T + a.pr;
+  in.d0 = __ldg(reinterpret_cast<const uint4*>(dyp + ((int64_t)in.b * Tp + a.pl + in.t) * a.C + c));
+}
+
+// BN output [+ residual] with dropout applied ("pre"), the dropout multipliers and z for one staged row
+template <bool HAS_RES>
+__device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&sc)[8], const float (&sh)[8], const float (&rsc)[8],
+                                             const float (&rsh)[8], const RowIn& in, int r, int c, float (&pre)[8], float (&mult)[8],
+                                             float (&zv)[8]) {
+  unpack8(in.z, zv);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], k.sc[i], k.sh[i]);
-  if (a.res) {
+  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], sc[i], sh[i]);
+  if (HAS_RES) {
     float rv[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.res + e)), rv);
+    unpack8(in.r, rv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], k.rsc[i], k.rsh[i]);
+    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], rsc[i], rsh[i]);
   }
-  dropout_mult8(a.seed, (uint64_t)e, a.drop_p, mult);
+  dropout_mult8(a.seed, (uint64_t)((int64_t)r * a.C + c), a.drop_p, mult);
 #pragma unroll
   for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
 }
 
-__global__ void __launch_bounds__(256) bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y, int rows_per_block) {
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
-  if (c >= a.C) return;
-  ChanConsts k;
-  load_consts(a, c, k);
-  const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
-  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
-    const int b = r / a.T, t = r - b * a.T;
-    float pre[8], mult[8], zv[8];
-    bn_pre8(a, k, (int64_t)r * a.C + c, pre, mult, zv);
-    const bool masked = a.lens && t >= a.lens[b];
+// masked upstream gradient g for one staged row (reflect halo folded, activation + dropout + length mask applied)
+__device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, int c, const RowIn& in,
+                                           const float (&pre)[8], const float (&mult)[8], float (&g)[8]) {
+  unpack8(in.d0, g);
+  const int dr = a.T - 1 - in.t;
+  if ((in.t >= 1 && in.t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo
+    const __nv_bfloat16* base = dyp + (int64_t)in.b * (a.pl + a.T + a.pr) * a.C + c;
+    float h[8];
+    if (in.t >= 1 && in.t <= a.pl) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl - in.t) * a.C)), h);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = pre[i];
-      if (a.act == W2L_ACT_RELU) v = fmaxf(v, 0.f);
-      else if (a.act == W2L_ACT_CLAMP20) v = fminf(fmaxf(v, 0.f), 20.f);
-      pre[i] = masked ? 0.f : v;
+      for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
-    const uint4 q = pack8(pre);
-    __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
-    *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
-    if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
-    const int d = a.T - 1 - t;
-    if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
-  }
-}
-
-// upstream gradient of output row (b,t): fold of the reflect halo of the padded gradient
-__device__ __forceinline__ void fold_grad8(const __nv_bfloat16* __restrict__ dyp, int b, int t, int c, int T, int C, int pl, int pr,
-                                           float (&g)[8]) {
-  const int Tp = pl + T + pr;
-  const __nv_bfloat16* base = dyp + (int64_t)b * Tp * C + c;
-  unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl + t) * C)), g);
-  if (t >= 1 && t <= pl) {
-    float h[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl - t) * C)), h);
+    if (dr >= 1 && dr <= a.pr) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl + a.T - 1 + dr) * a.C)), h);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] += h[i];
+      for (int i = 0; i < 8; ++i) g[i] += h[i];
+    }
   }
-  const int d = T - 1 - t;
-  if (d >= 1 && d <= pr) {
-    float h[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pl + T - 1 + d) * C)), h);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] += h[i];
-  }
-}
-
-// g (masked upstream gradient wrt the BN output) and xhat for 8 channels of row r
-__device__ __forceinline__ void bwd_g8(const BnActArgs& a, const ChanConsts& k, const float (&mu)[8], const float (&is)[8],
-                                       const __nv_bfloat16* __restrict__ dyp, int r, int c, float (&g)[8], float (&xhat)[8]) {
-  const int b = r / a.T, t = r - b * a.T;
-  float pre[8], mult[8], zv[8];
-  bn_pre8(a, k, (int64_t)r * a.C + c, pre, mult, zv);
-  fold_grad8(dyp, b, t, c, a.T, a.C, a.pl, a.pr, g);
-  const bool masked = a.lens && t >= a.lens[b];
+  const bool masked = a.lens && in.t >= a.lens[in.b];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     bool pass = true;
     if (a.act == W2L_ACT_RELU) pass = pre[i] > 0.f;
     else if (a.act == W2L_ACT_CLAMP20) pass = pre[i] >= 0.f && pre[i] <= 20.f;
     g[i] = (pass && !masked) ? g[i] * mult[i] : 0.f;
-    xhat[i] = (zv[i] - mu[i]) * is[i];
   }
 }
 
-// red[0:C] += sum g, red[C:2C] += sum g*xhat
-__global__ void __launch_bounds__(256)
+#define W2L_LOAD_AFFINE(a, c)                          \
+  float sc[8], sh[8], rsc[8], rsh[8];                  \
+  load8f((a).scale + (c), sc);                         \
+  load8f((a).shift + (c), sh);                         \
+  if (HAS_RES) {                                       \
+    load8f((a).res_scale + (c), rsc);                  \
+    load8f((a).res_shift + (c), rsh);                  \
+  } else {                                             \
+    _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) rsc[i_] = rsh[i_] = 0.f; \
+  }
+
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y, int rows_per_block) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  if (c >= a.C) return;
+  W2L_LOAD_AFFINE(a, c)
+  const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
+    RowIn in[kRowsPerIter];
+#pragma unroll
+    for (int u = 0; u < kRowsPerIter; ++u) load_fwd_row<HAS_RES>(a, r0 + 8 * u, r_end, c, in[u]);
+#pragma unroll
+    for (int u = 0; u < kRowsPerIter; ++u) {
+      if (!in[u].live) continue;
+      float pre[8], mult[8], zv[8];
+      pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      const int b = in[u].b, t = in[u].t;
+      const bool masked = a.lens && t >= a.lens[b];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = pre[i];
+        if (a.act == W2L_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (a.act == W2L_ACT_CLAMP20) v = fminf(fmaxf(v, 0.f), 20.f);
+        pre[i] = masked ? 0.f : v;
+      }
+      const uint4 q = pack8(pre);
+      __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
+      *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
+      if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
+      const int d = a.T - 1 - t;
+      if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
+    }
+  }
+}
+
+// red[0:C] += sum g, red[C:2C] += sum g*xhat   (accumulated as sum g*(z-mean), scaled by invstd once per block)
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
                          const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
   __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
@@ -302,22 +334,32 @@ bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, con
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
   if (c < a.C) {
-    ChanConsts k;
-    float mu[8], is[8];
-    load_consts(a, c, k);
+    W2L_LOAD_AFFINE(a, c)
+    float mu[8];
     load8f(mean + c, mu);
-    load8f(invstd + c, is);
     const int rows = a.B * a.T;
     const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
-      float g[8], xh[8];
-      bwd_g8(a, k, mu, is, dyp, r, c, g, xh);
+    for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
+      RowIn in[kRowsPerIter];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sg[i] += g[i];
-        sx[i] = fmaf(g[i], xh[i], sx[i]);
+      for (int u = 0; u < kRowsPerIter; ++u) load_bwd_row<HAS_RES>(a, dyp, r0 + 8 * u, r_end, c, in[u]);
+#pragma unroll
+      for (int u = 0; u < kRowsPerIter; ++u) {
+        if (!in[u].live) continue;
+        float pre[8], mult[8], zv[8], g[8];
+        pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+        g_from_row(a, dyp, c, in[u], pre, mult, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sg[i] += g[i];
+          sx[i] = fmaf(g[i], zv[i] - mu[i], sx[i]);
+        }
       }
     }
+    float is[8];
+    load8f(invstd + c, is);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sx[i] *= is[i];
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -339,41 +381,52 @@ bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, con
   }
 }
 
+// dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = A*g + Bz*z + Cc with per-channel A, Bz, Cc.
 // dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the
 // zero padding between utterances)
-__global__ void __launch_bounds__(256)
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ red,
                         __nv_bfloat16* __restrict__ dz, int dz_rows, __nv_bfloat16* __restrict__ g_out, int rows_per_block) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   if (c >= a.C) return;
-  ChanConsts k;
-  float mu[8], is[8], sg[8], sx[8], coef[8];
-  load_consts(a, c, k);
-  load8f(mean + c, mu);
-  load8f(invstd + c, is);
-  load8f(red + c, sg);
-  load8f(red + a.C + c, sx);
-  const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
-  if (gamma) load8f(gamma + c, coef);
+  W2L_LOAD_AFFINE(a, c)
+  float kA[8], kB[8], kC[8];
+  {
+    float mu[8], is[8], sg[8], sx[8], ga[8];
+    load8f(mean + c, mu);
+    load8f(invstd + c, is);
+    load8f(red + c, sg);
+    load8f(red + a.C + c, sx);
+    if (gamma) load8f(gamma + c, ga);
+    const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    coef[i] = (gamma ? coef[i] : 1.f) * is[i];
-    sg[i] *= inv_m;
-    sx[i] *= inv_m;
+    for (int i = 0; i < 8; ++i) {
+      const float coef = (gamma ? ga[i] : 1.f) * is[i];
+      kA[i] = coef;
+      kB[i] = -coef * sx[i] * inv_m * is[i];
+      kC[i] = -coef * sg[i] * inv_m - kB[i] * mu[i];
+    }
   }
   const int rows = a.B * a.T;
   const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
-    float g[8], xh[8], o[8];
-    bwd_g8(a, k, mu, is, dyp, r, c, g, xh);
+  for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
+    RowIn in[kRowsPerIter];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = coef[i] * (g[i] - sg[i] - xh[i] * sx[i]);
-    const int b = r / a.T, t = r - b * a.T;
-    *reinterpret_cast<uint4*>(dz + ((int64_t)b * dz_rows + t) * a.C + c) = pack8(o);
-    if (g_out) *reinterpret_cast<uint4*>(g_out + (int64_t)r * a.C + c) = pack8(g);
+    for (int u = 0; u < kRowsPerIter; ++u) load_bwd_row<HAS_RES>(a, dyp, r0 + 8 * u, r_end, c, in[u]);
+#pragma unroll
+    for (int u = 0; u < kRowsPerIter; ++u) {
+      if (!in[u].live) continue;
+      float pre[8], mult[8], zv[8], g[8], o[8];
+      pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      g_from_row(a, dyp, c, in[u], pre, mult, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
+      *reinterpret_cast<uint4*>(dz + ((int64_t)in[u].b * dz_rows + in[u].t) * a.C + c) = pack8(o);
+      if (g_out) *reinterpret_cast<uint4*>(g_out + (int64_t)(r0 + 8 * u) * a.C + c) = pack8(g);
+    }
   }
-  // zero tails
   const int tail = dz_rows - a.T;
   if (tail > 0) {
     const int trows = a.B * tail;
@@ -584,7 +637,8 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  bn_act_pad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
+  if (res) bn_act_pad_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
+  else bn_act_pad_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
   return after_launch("bn_act_pad_kernel");
 }
 
@@ -601,7 +655,8 @@ int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  bn_act_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
+  if (res) bn_act_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
+  else bn_act_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
   return after_launch("bn_act_bwd_reduce_kernel");
 }
 
@@ -620,8 +675,12 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  bn_act_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
-                                                                   (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
+  if (res)
+    bn_act_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
+                                                                           (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
+  else
+    bn_act_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
+                                                                            (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
   return after_launch("bn_act_bwd_apply_kernel");
 }
 
