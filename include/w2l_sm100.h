@@ -152,6 +152,21 @@ int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d);
 int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Depthwise Conv1d (groups = channels): the first half of the separable sub-blocks of the shipped model/jasper.yaml
+ * (jasper.py:318-341; the pointwise half is w2l_conv1d_* with k = 1).  Time-major bf16 activations, fp32 weights
+ * stored [k, C]; zero padding `pad` on both sides.
+ *   fwd:   y [B,T_out,C];  rows t >= out_lens[b] are written as 0 (the consumer MaskedConv1d's masked_fill)
+ *   dgrad: dx [B,T,C] (stride 1 only); dy rows t >= dy_lens[b] are read as 0
+ *   wgrad: dw [k,C] fp32, ACCUMULATED with atomics (zero it first)
+ */
+int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                      int32_t stride, int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream);
+int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Memory-bound companions of the conv kernels (all time-major).
  */
 /* [B, F, T] fp32 NCW (the collated batch, data_loader.py:149-158) -> [B, rows, k*F] bf16 with

@@ -169,8 +169,9 @@ def _jasper_conv_bn(x, lens, sd, prefix, idx, spec, cin, k, stride, pad, dilatio
     ``emu``: bf16 weights / bf16-stored conv outputs (the CUDA path's storage precision), fp32 accumulation."""
     Wq, Rz = (_bf16_weight, _RoundBF16.apply) if emu else (_ident, _ident)
     if separable:
-        x, lens = masked_conv1d(x, lens, Wq(sd["%s%d.conv.weight" % (prefix, idx)]), stride, pad, dilation,
-                                cin, spec["conv_mask"])
+        x, lens = masked_conv1d(x, lens, sd["%s%d.conv.weight" % (prefix, idx)], stride, pad, dilation,
+                                cin, spec["conv_mask"])           # depthwise weights stay fp32 in the CUDA path
+        x = Rz(x)                                                  # ... and its output is stored as bf16
         idx += 1
         x, lens = masked_conv1d(x, lens, Wq(sd["%s%d.conv.weight" % (prefix, idx)]), 1, 0, 1, 1, spec["conv_mask"])
         idx += 1

@@ -391,3 +391,32 @@ def test_string_metrics_device(F):
     assert dec.error_ratios_device(probs.cuda(), sizes.cuda(), ["tab\there"] * N) is None     # exotic whitespace -> host path
     with pytest.raises(ZeroDivisionError):
         dec.error_ratios_device(probs.cuda(), sizes.cuda(), [" "] * N)
+
+
+@pytest.mark.parametrize("B,T,C,k,s,d", [(3, 97, 64, 33, 1, 1), (2, 201, 256, 13, 2, 1), (2, 60, 128, 7, 1, 2), (1, 40, 72, 1, 1, 1)])
+def test_depthwise_conv(F, B, T, C, k, s, d):
+    """depthwise (groups=C) conv fwd / dgrad / wgrad vs torch fp32 on the same bf16-rounded operands, with the length masks"""
+    g = torch.Generator().manual_seed(B * T + k)
+    p = (d * k) // 2 - 1 if d > 1 else k // 2                      # jasper.py:61-66
+    x = _bf(torch.randn(B, T, C, generator=g))
+    w = torch.randn(C, 1, k, generator=g) / k ** 0.5
+    T_out = (T + 2 * p - d * (k - 1) - 1) // s + 1
+    lens = torch.randint(T_out // 2, T_out + 1, (B,), generator=g, dtype=torch.int32)
+    lens[0] = T_out
+    xr = x.transpose(1, 2).clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    y_ref = TF.conv1d(xr, wr, stride=s, padding=p, dilation=d, groups=C)
+    mask = (torch.arange(T_out)[None] < lens[:, None]).float()[:, None]
+    y_ref = y_ref * mask
+    dy = _bf(torch.randn(B, C, T_out, generator=g))
+    y_ref.backward(dy)
+    ws = w.permute(2, 1, 0).reshape(k, C).contiguous().cuda()
+    xc = x.to(torch.bfloat16).cuda()
+    y = F.depthwise_fwd(xc, ws, T_out, k, s, d, p, lens.cuda())
+    assert rel_l2(y.float().cpu(), y_ref.detach().transpose(1, 2)) < 6e-3
+    dyc = dy.transpose(1, 2).to(torch.bfloat16).contiguous().cuda()
+    dw = F.depthwise_wgrad(dyc, xc, k, s, d, p, lens.cuda())
+    assert rel_l2(dw.cpu(), wr.grad.permute(2, 1, 0).reshape(k, C)) < 1e-4
+    if s == 1:
+        dx = F.depthwise_dgrad(dyc, ws, T, k, d, p, lens.cuda())
+        assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3

@@ -216,15 +216,17 @@ def test_training_step_end_to_end(pkg):
     assert torch.equal(conv.packed().float(), conv.storage().to(torch.bfloat16).float())
 
 
-def test_jasper_dense_golden(pkg, golden):
-    """Jasper with masks, stride-2 prologue, repeats, residual 1x1+BN branches, dilation, unmasked head, softmax in eval."""
+@pytest.mark.parametrize("fixture", ["jasper_dense", "jasper_small"])
+def test_jasper_dense_golden(pkg, golden, fixture):
+    """Jasper with masks, stride-2 prologue, repeats, residual 1x1+BN branches, dilation, unmasked head, softmax in eval;
+    ``jasper_small`` additionally has a separable (depthwise + pointwise) block as in the shipped model/jasper.yaml."""
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
-    g = golden("jasper_dense")
+    g = golden(fixture)
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=5"]).model
     cfg["jasper_blocks"] = config.to_attr(blocks)
-    torch.manual_seed(4)
+    torch.manual_seed(4 if fixture == "jasper_dense" else 2)
     model = Jasper(cfg)
     for k in g.files:                                                   # seeded construction == the reference's
         if k.startswith("sd_init:"):

@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libw2l_sm100.so")
-SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu", "metrics.cu"]
+SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu", "metrics.cu", "depthwise.cu"]
 _lock = threading.Lock()
 _lib = None
 
@@ -89,6 +89,9 @@ SIGNATURES = {
     "w2l_pack_wt": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_conv1d_wgrad_splits": (c_i32, [ctypes.POINTER(ConvDesc)]),
     "w2l_conv1d_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_depthwise_fwd": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
+    "w2l_depthwise_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr, c_ptr]),
+    "w2l_depthwise_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_im2col_ncw": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_tm_to_ncw": (c_i32, [c_ptr, c_i32, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_ncw_to_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),

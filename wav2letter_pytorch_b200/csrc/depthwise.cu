@@ -1,0 +1,164 @@
+// Depthwise Conv1d (groups = channels) for the separable Jasper sub-blocks of the shipped model/jasper.yaml
+// (jasper.py:318-341: depthwise k-tap conv + pointwise 1x1; the pointwise half runs on the tensor-core GEMM kernel).
+// Memory/L1-bound CUDA-core kernels over time-major bf16: a thread owns 8 channels (one 16-byte vector) of one output row;
+// neighbouring threads in y walk neighbouring rows, so the k input rows each thread reads are L1 hits after the first.
+//   fwd   y[b,t,c]  = sum_j x[b, t*s + j*d - p, c] * w[j,c]            rows >= out_lens[b] written as 0 (consumer's mask)
+//   dgrad dx[b,u,c] = sum_j dy[b, u + p - j*d, c] * w[j,c]             (stride 1), dy rows >= dy_lens[b] read as 0
+//   wgrad dw[j,c]  += sum_{b,t} dy[b,t,c] * x[b, t*s + j*d - p, c]
+// Weights are fp32 [k, C] (the [C,1,k] Parameter is a permuted view of this storage).
+#include "common.cuh"
+
+namespace w2l {
+
+__device__ __forceinline__ void dw_unpack8(const uint4& q, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+// Generic correlation: out[b,t,c] = sum_j in[b, t*stride + j*dil*dir + off, c] * w[jw(j), c], jw(j) = flip ? k-1-j : j.
+// Rows of `in` outside [0, in_rows) or >= in_lens[b] read as zero; rows of `out` >= out_lens[b] are written as zero.
+__global__ void __launch_bounds__(256)
+depthwise_corr_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int B,
+                      int in_rows, int out_rows, int C, int k, int stride, int dil, int off, int flip,
+                      const int32_t* __restrict__ in_lens, const int32_t* __restrict__ out_lens) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r = blockIdx.y * 8 + threadIdx.y;            // flattened (b, t)
+  if (c >= C || r >= B * out_rows) return;
+  const int b = r / out_rows, t = r - b * out_rows;
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  if (!out_lens || t < out_lens[b]) {
+    const int lim = in_lens ? min(in_rows, max(0, in_lens[b])) : in_rows;
+    const __nv_bfloat16* ib = in + (int64_t)b * in_rows * C + c;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int u = t * stride + j * dil + off;
+      if (u < 0 || u >= lim) continue;
+      float xv[8];
+      dw_unpack8(__ldg(reinterpret_cast<const uint4*>(ib + (int64_t)u * C)), xv);
+      const float* wj = w + (int64_t)(flip ? k - 1 - j : j) * C + c;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wj)), w1 = __ldg(reinterpret_cast<const float4*>(wj) + 1);
+      acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
+      acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
+      acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
+      acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+    }
+    q.x = pack_bf16x2(acc[0], acc[1]);
+    q.y = pack_bf16x2(acc[2], acc[3]);
+    q.z = pack_bf16x2(acc[4], acc[5]);
+    q.w = pack_bf16x2(acc[6], acc[7]);
+  }
+  *reinterpret_cast<uint4*>(out + (int64_t)r * C + c) = q;
+}
+
+// block (32, 8); grid (channel blocks, row chunks, tap groups of 4)
+__global__ void __launch_bounds__(256)
+depthwise_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, float* __restrict__ dw, int B,
+                       int x_rows, int y_rows, int C, int k, int stride, int dil, int pad, const int32_t* __restrict__ dy_lens,
+                       int rows_per_block) {
+  __shared__ float s_acc[8][4][256 + 8];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int j0 = blockIdx.z * 4;
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  if (c < C) {
+    const int rows = B * y_rows;
+    const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const int b = r / y_rows, t = r - b * y_rows;
+      if (dy_lens && t >= dy_lens[b]) continue;
+      float g[8];
+      dw_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (int64_t)r * C + c)), g);
+      const __nv_bfloat16* xb = x + (int64_t)b * x_rows * C + c;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int j = j0 + a, u = t * stride + j * dil - pad;
+        if (j < k && u >= 0 && u < x_rows) {
+          float xv[8];
+          dw_unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (int64_t)u * C)), xv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[a][i] = fmaf(g[i], xv[i], acc[a][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_acc[threadIdx.y][a][threadIdx.x * 8 + i] = acc[a][i];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int cc = blockIdx.x * 256 + tid;
+  if (cc < C) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      if (j0 + a >= k) break;
+      float v = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) v += s_acc[y][a][tid];
+      atomicAdd(dw + (int64_t)(j0 + a) * C + cc, v);
+    }
+  }
+}
+
+static int dw_check(const char* who, int B, int T, int C, int T_out, int k, int stride, int dil, int pad) {
+  W2L_REQUIRE(B >= 1 && T >= 1 && T_out >= 1 && k >= 1 && stride >= 1 && dil >= 1 && pad >= 0, "%s: bad geometry", who);
+  W2L_REQUIRE(C >= 8 && C % 8 == 0, "%s: C=%d must be a multiple of 8", who, C);
+  W2L_REQUIRE((int64_t)B * (T > T_out ? T : T_out) < (1ll << 28), "%s: B*T too large", who);
+  return W2L_OK;
+}
+
+}  // namespace w2l
+
+extern "C" {
+
+int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                      int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream) {
+  using namespace w2l;
+  int rc = dw_check("depthwise_fwd", B, T, C, T_out, k, stride, dilation, pad);
+  if (rc) return rc;
+  W2L_REQUIRE(x && w && y, "depthwise_fwd: null pointer");
+  dim3 grid((C / 8 + 31) / 32, (B * T_out + 7) / 8), block(32, 8);
+  depthwise_corr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, B, T, T_out, C, k, stride,
+                                                                  dilation, -pad, 0, nullptr, out_lens);
+  return after_launch("depthwise_corr_kernel<fwd>");
+}
+
+int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  using namespace w2l;
+  int rc = dw_check("depthwise_dgrad", B, T, C, T_out, k, 1, dilation, pad);
+  if (rc) return rc;
+  W2L_REQUIRE(dy && w && dx, "depthwise_dgrad: null pointer");
+  // dx[u] = sum_j dy[u + p - j*d] w[j] = sum_j' dy[u + p - (k-1)d + j'*d] w[k-1-j']
+  dim3 grid((C / 8 + 31) / 32, (B * T + 7) / 8), block(32, 8);
+  depthwise_corr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T_out, T, C, k, 1,
+                                                                  dilation, pad - (k - 1) * dilation, 1, dy_lens, nullptr);
+  return after_launch("depthwise_corr_kernel<dgrad>");
+}
+
+int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  using namespace w2l;
+  int rc = dw_check("depthwise_wgrad", B, T, C, T_out, k, stride, dilation, pad);
+  if (rc) return rc;
+  W2L_REQUIRE(dy && x && dw, "depthwise_wgrad: null pointer");
+  const int rows = B * T_out;
+  int rpb = (rows + num_sms() - 1) / num_sms();
+  if (rpb < 64) rpb = 64;
+  dim3 grid((C / 8 + 31) / 32, (rows + rpb - 1) / rpb, (k + 3) / 4), block(32, 8);
+  depthwise_wgrad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, B, T, T_out, C, k,
+                                                                   stride, dilation, pad, dy_lens, rpb);
+  return after_launch("depthwise_wgrad_kernel");
+}
+
+}  // extern "C"

@@ -139,6 +139,37 @@ def conv1d_wgrad(dy, x, desc, dw):
     return dw
 
 
+# --------------------------------------------------------------------------------------------- depthwise
+def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
+    """x [B,T,C] bf16, w fp32 [k,C] -> y [B,T_out,C] bf16"""
+    _need_cuda(x, w)
+    B, T, C = x.shape
+    y = torch.empty((B, T_out, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_depthwise_fwd(_ptr(x), _ptr(w), _ptr(y), B, T, C, T_out, k, stride, dilation, pad, _ptr(out_lens), _stream()),
+                   "depthwise_fwd")
+    return y
+
+
+def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None):
+    B, T_out, C = dy.shape
+    dx = torch.empty((B, T, C), dtype=torch.bfloat16, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().w2l_depthwise_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens), _stream()),
+                   "depthwise_dgrad")
+    return dx
+
+
+def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
+    B, T_out, C = dy.shape
+    T = x.shape[1]
+    dw = torch.zeros((k, C), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().w2l_depthwise_wgrad(_ptr(dy), _ptr(x), _ptr(dw), B, T, C, T_out, k, stride, dilation, pad, _ptr(dy_lens),
+                                                   _stream()), "depthwise_wgrad")
+    return dw
+
+
 # --------------------------------------------------------------------------------------------- elementwise
 def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
     """x [B,F,T] fp32 -> [B, rows, k*F] bf16 (unfold + pad + transpose + cast)."""

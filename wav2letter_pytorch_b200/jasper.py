@@ -10,15 +10,18 @@ through a 1x1 conv + BN, groups=1, length masking, ``repeat`` sub-blocks, dense 
   * conv -> BN -> (+ BN(conv1x1(block input))) -> ReLU -> dropout is one GEMM plus one fused elementwise pass
     (two GEMMs with a residual), instead of the reference's 8-10 separate library kernels per sub-block.
 
-Not implemented (raise NotImplementedError at construction): separable/depthwise sub-blocks (the shipped
-model/jasper.yaml), group/instance/layer norm, groups > 1, heads, residual_mode='max', dense residuals."""
+Separable sub-blocks (the shipped model/jasper.yaml: depthwise k-tap + pointwise 1x1, jasper.py:318-341) run the depthwise
+half on a CUDA-core kernel (csrc/depthwise.cu) and the pointwise half on the tensor-core GEMM.
+Not implemented (raise NotImplementedError at construction): group/instance/layer norm, groups > 1 with shuffle, heads,
+residual_mode='max', dense residuals -- none of which Jasper._build_encoder can produce."""
 import numpy as np
 import torch
 import torch.nn as nn
 
 from . import functional as F
 from .base_asr_models import ConvCTCASR
-from .layers import BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, ResidualBranchFn, conv_bn_act_eval, conv_desc
+from .layers import (BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, DepthwiseFn, DepthwiseParams, ResidualBranchFn,
+                     conv_bn_act_eval, conv_desc)
 
 jasper_activations = {"hardtanh": nn.Hardtanh, "relu": nn.ReLU, "selu": nn.SELU}
 
@@ -43,8 +46,8 @@ def init_weights(m, mode="xavier_uniform"):
     into a reference-shaped contiguous tensor and copied into the kernel-layout storage)."""
     if isinstance(m, MaskedConv1d):
         init_weights(m.conv, mode)
-    if isinstance(m, ConvParams):
-        w = torch.empty(m.out_channels, m.in_channels, m.kernel_size[0])
+    if isinstance(m, (ConvParams, DepthwiseParams)):
+        w = torch.empty(m.out_channels, m.in_channels // m.groups, m.kernel_size[0])
         if mode == "xavier_uniform":
             nn.init.xavier_uniform_(w, gain=1.0)
         elif mode == "xavier_normal":
@@ -74,11 +77,14 @@ class MaskedConv1d(nn.Module):
         super().__init__()
         if not (heads == -1 or groups == in_channels):
             raise ValueError("Only use heads for depthwise convolutions")
-        if groups != 1 or heads != -1:
-            raise NotImplementedError("grouped / depthwise MaskedConv1d is not implemented on the tensor-core path")
+        if heads != -1 or groups not in (1, in_channels) or (groups != 1 and (out_channels != in_channels or bias)):
+            raise NotImplementedError("only dense (groups=1) and depthwise (groups=channels) MaskedConv1d are implemented")
         self.real_out_channels = out_channels
-        self.conv = ConvParams(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation, bias=bias,
-                               unfold=stride > 1)
+        if groups == 1:
+            self.conv = ConvParams(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation, bias=bias,
+                                   unfold=stride > 1)
+        else:
+            self.conv = DepthwiseParams(in_channels, kernel_size, stride=stride, padding=padding, dilation=dilation)
         self.use_mask = use_mask
         self.heads = heads
 
@@ -96,8 +102,8 @@ class JasperBlock(nn.Module):
             raise ValueError("currently only 'same' padding is supported")
         if normalization != "batch":
             raise NotImplementedError("only batch normalisation is reachable from Jasper._build_encoder and implemented")
-        if separable or groups != 1 or heads != -1:
-            raise NotImplementedError("separable / grouped Jasper sub-blocks need the depthwise kernel (not implemented yet)")
+        if groups != 1 or heads != -1:
+            raise NotImplementedError("grouped (shuffled) Jasper sub-blocks are not reachable from Jasper._build_encoder and not implemented")
         if residual_mode != "add" or len(residual_panes) != 0:
             raise NotImplementedError("only the plain 'add' residual is implemented")
         if planes % 16 or planes < 64 or (inplanes % 8) or inplanes < 64:
@@ -114,10 +120,15 @@ class JasperBlock(nn.Module):
             self.act = F.ACT_CLAMP20
         else:
             raise NotImplementedError("activation %r is not implemented in the fused epilogues" % (activation,))
-        # ModuleList positions mirror the reference so that checkpoints load: [conv, bn, act, drop] * (repeat-1) + [conv, bn]
+        # ModuleList positions mirror the reference so that checkpoints load:
+        # [conv | depthwise, pointwise][bn][act, drop] * (repeat-1) + [conv | depthwise, pointwise][bn]
         mods, cin = [], inplanes
         for r in range(repeat):
-            mods.append(MaskedConv1d(cin, planes, kernel_size, stride=stride, dilation=dilation, padding=pad, use_mask=conv_mask))
+            if separable:
+                mods.append(MaskedConv1d(cin, cin, kernel_size, stride=stride, dilation=dilation, padding=pad, groups=cin, use_mask=conv_mask))
+                mods.append(MaskedConv1d(cin, planes, 1, use_mask=conv_mask))
+            else:
+                mods.append(MaskedConv1d(cin, planes, kernel_size, stride=stride, dilation=dilation, padding=pad, use_mask=conv_mask))
             mods.append(BatchNormParams(planes, eps=1e-3, momentum=0.1))
             if r != repeat - 1:
                 mods.extend([type(activation)() if not isinstance(activation, nn.Hardtanh) else nn.Hardtanh(0.0, 20.0), nn.Dropout(p=dropout)])
@@ -133,23 +144,30 @@ class JasperBlock(nn.Module):
         self.repeat, self.stride, self.pad = repeat, stride, pad
 
     def sub_blocks(self):
-        return [(self.mconv[i], self.mconv[i + 1]) for i in range(0, len(self.mconv), 4)]
+        """[(depthwise MaskedConv1d | None, conv MaskedConv1d, BatchNormParams)] in execution order"""
+        out, step = [], 5 if self.separable else 4
+        for i in range(0, len(self.mconv), step):
+            if self.separable:
+                out.append((self.mconv[i], self.mconv[i + 1], self.mconv[i + 2]))
+            else:
+                out.append((None, self.mconv[i], self.mconv[i + 1]))
+        return out
 
     def forward_tm(self, h, t, lens, from_ncw, mask_output):
         """h: NCW fp32 (first block, ``from_ncw``) or time-major bf16 [B, t, C] whose rows >= len are already zero.
         Returns (time-major bf16 output, t_out, lens_out)."""
         subs = self.sub_blocks()
-        lens_in = lens
+        first = subs[0][0] if self.separable else subs[0][1]
         if from_ncw:
-            m0 = subs[0][0].conv
+            m0 = first.conv
             k, s, d, p = m0.kernel_size[0], m0.stride[0], m0.dilation[0], m0.padding[0]
             mask = lens.to(torch.int32) if (self.conv_mask and lens is not None) else None
-            if m0.unfold:
+            if not self.separable and m0.unfold:
                 t_first = (t + 2 * p - d * (k - 1) - 1) // s + 1
                 h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask)        # masked, zero padded, unfolded
             else:
-                h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask)
-        elif subs[0][0].conv.unfold:
+                h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask)              # masked time-major copy
+        elif first.conv.stride[0] != 1:
             raise NotImplementedError("stride > 1 is only supported on the first Jasper block")
         block_in, res_pair = h, None
         training = self.training
@@ -161,9 +179,25 @@ class JasperBlock(nn.Module):
                 zr = torch.empty((h.shape[0], t, rconv.out_channels), dtype=torch.bfloat16, device=h.device)
                 F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
                 res_pair = (zr, rbn.eval_scale_shift(None))
-        for r, (mc, bn) in enumerate(subs):
+
+        def as_i32(l):
+            return l.to(dtype=torch.long).to(torch.int32)                        # the consumer truncates with .to(long)
+
+        for r, (dwm, mc, bn) in enumerate(subs):
             conv = mc.conv
             last = r == len(subs) - 1
+            if dwm is not None:                                                  # separable: depthwise k-tap, then pointwise 1x1
+                dc = dwm.conv
+                k, s, d, p = dc.kernel_size[0], dc.stride[0], dc.dilation[0], dc.padding[0]
+                t_dw = (t + 2 * p - d * (k - 1) - 1) // s + 1
+                if self.conv_mask and lens is not None:
+                    lens = dwm.get_seq_len(lens.to(dtype=torch.long))
+                dmask = as_i32(lens) if (self.conv_mask and lens is not None) else None
+                if training:
+                    h = DepthwiseFn.apply(h, dc.weight, dc, t_dw, dmask)
+                else:
+                    h = F.depthwise_fwd(h, dc.storage(), t_dw, k, s, d, p, dmask)
+                t = t_dw
             if conv.unfold:
                 t_out, x_off = h.shape[1], 0
             else:
@@ -173,7 +207,7 @@ class JasperBlock(nn.Module):
                 lens = mc.get_seq_len(lens.to(dtype=torch.long))                 # float after true division, as the reference
             out_mask = None
             if self.conv_mask and lens is not None and (not last or mask_output):
-                out_mask = lens.to(dtype=torch.long).to(torch.int32)            # the consumer truncates with .to(long)
+                out_mask = as_i32(lens)
             geo = {"T_out": t_out, "x_row_offset": x_off, "out_pad": (0, 0), "act": self.act,
                    "drop_p": self.dropout_p if training else 0.0, "lens": out_mask}
             use_res = res_pair if last else None

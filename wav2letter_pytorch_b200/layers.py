@@ -132,6 +132,58 @@ class ConvParams(nn.Module):
                                                                   self.stride, self.dilation)
 
 
+class DepthwiseParams(nn.Module):
+    """Stands where the reference has ``nn.Conv1d(C, C, k, groups=C, bias=False)`` (the depthwise half of a separable
+    Jasper sub-block, jasper.py:318-330): weight ``[C, 1, k]``, stored in memory as fp32 ``[k, C]``."""
+
+    def __init__(self, channels, kernel_size, stride=1, padding=0, dilation=1):
+        super().__init__()
+        k = kernel_size[0] if isinstance(kernel_size, (tuple, list)) else kernel_size
+        self.in_channels = self.out_channels = self.groups = channels
+        self.kernel_size, self.stride, self.dilation, self.padding = (k,), (stride,), (dilation,), (padding,)
+        w = torch.empty(channels, 1, k)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))                     # nn.Conv1d's default, same RNG consumption
+        self.weight = nn.Parameter(w.permute(2, 1, 0).contiguous().permute(2, 1, 0))
+        self.bias = None
+
+    def storage(self):
+        v = self.weight.detach().permute(2, 1, 0)
+        if not v.is_contiguous():
+            v = v.contiguous()
+            self.weight.data = v.permute(2, 1, 0)
+        return v.reshape(self.kernel_size[0], self.in_channels)
+
+    def grad_view(self, dw_store):
+        return dw_store.view(self.kernel_size[0], 1, self.in_channels).permute(2, 1, 0)
+
+
+class DepthwiseFn(torch.autograd.Function):
+    """depthwise conv over time-major bf16 (zero 'same' padding); rows >= out_lens are written as zeros because the
+    consumer is a MaskedConv1d (jasper.py:116-119), and their gradient is ignored accordingly."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, conv, T_out, out_lens):
+        k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+        y = F.depthwise_fwd(xin, conv.storage(), T_out, k, s, d, p, out_lens)
+        ctx.conv, ctx.out_lens = conv, out_lens
+        ctx.save_for_backward(xin)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xin,) = ctx.saved_tensors
+        conv = ctx.conv
+        k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+        dy = dy.contiguous()
+        dw = F.depthwise_wgrad(dy, xin, k, s, d, p, ctx.out_lens)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if s != 1:
+                raise NotImplementedError("depthwise backward-data with stride > 1 (only the first block is strided)")
+            dx = F.depthwise_dgrad(dy, conv.storage(), xin.shape[1], k, d, p, ctx.out_lens)
+        return dx, conv.grad_view(dw), None, None, None
+
+
 class BatchNormParams(nn.Module):
     """Stands where the reference has ``nn.BatchNorm1d`` (wav2letter.py:37, jasper.py:363)."""
 
