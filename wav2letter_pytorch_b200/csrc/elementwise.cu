@@ -230,7 +230,7 @@ __device__ __forceinline__ void load_bwd_row(const BnActArgs& a, const __nv_bflo
 }
 
 // BN output [+ residual] with dropout applied ("pre"), the dropout multipliers and z for one staged row
-template <bool HAS_RES>
+template <bool HAS_RES, bool DROP>
 __device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&sc)[8], const float (&sh)[8], const float (&rsc)[8],
                                              const float (&rsh)[8], const RowIn& in, int r, int c, float (&pre)[8], float (&mult)[8],
                                              float (&zv)[8]) {
@@ -243,12 +243,30 @@ __device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&s
 #pragma unroll
     for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], rsc[i], rsh[i]);
   }
-  dropout_mult8(a.seed, (uint64_t)((int64_t)r * a.C + c), a.drop_p, mult);
+  if (DROP) {
+    dropout_mult8(a.seed, (uint64_t)((int64_t)r * a.C + c), a.drop_p, mult);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
+    for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
+  }
+}
+
+// activation as a compile-time switch: the per-element code is straight-line (a runtime `act` costs a compare+branch per
+// element; profiles/ shows these kernels were instruction-issue bound before this)
+template <int ACT>
+__device__ __forceinline__ float act_fwd(float v) {
+  if (ACT == W2L_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == W2L_ACT_CLAMP20) return fminf(fmaxf(v, 0.f), 20.f);
+  return v;
+}
+template <int ACT>
+__device__ __forceinline__ bool act_pass(float pre) {
+  if (ACT == W2L_ACT_RELU) return pre > 0.f;
+  if (ACT == W2L_ACT_CLAMP20) return pre >= 0.f && pre <= 20.f;
+  return true;
 }
 
 // masked upstream gradient g for one staged row (reflect halo folded, activation + dropout + length mask applied)
+template <int ACT, bool DROP>
 __device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, int c, const RowIn& in,
                                            const float (&pre)[8], const float (&mult)[8], float (&g)[8]) {
   unpack8(in.d0, g);
@@ -270,10 +288,8 @@ __device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat
   const bool masked = a.lens && in.t >= a.lens[in.b];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    bool pass = true;
-    if (a.act == W2L_ACT_RELU) pass = pre[i] > 0.f;
-    else if (a.act == W2L_ACT_CLAMP20) pass = pre[i] >= 0.f && pre[i] <= 20.f;
-    g[i] = (pass && !masked) ? g[i] * mult[i] : 0.f;
+    const float gi = DROP ? g[i] * mult[i] : g[i];
+    g[i] = (act_pass<ACT>(pre[i]) && !masked) ? gi : 0.f;
   }
 }
 
@@ -288,7 +304,7 @@ __device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat
     _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) rsc[i_] = rsh[i_] = 0.f; \
   }
 
-template <bool HAS_RES>
+template <int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y, int rows_per_block) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   if (c >= a.C) return;
@@ -303,16 +319,11 @@ __global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bf
     for (int u = 0; u < kRowsPerIter; ++u) {
       if (!in[u].live) continue;
       float pre[8], mult[8], zv[8];
-      pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
       const int b = in[u].b, t = in[u].t;
       const bool masked = a.lens && t >= a.lens[b];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = pre[i];
-        if (a.act == W2L_ACT_RELU) v = fmaxf(v, 0.f);
-        else if (a.act == W2L_ACT_CLAMP20) v = fminf(fmaxf(v, 0.f), 20.f);
-        pre[i] = masked ? 0.f : v;
-      }
+      for (int i = 0; i < 8; ++i) pre[i] = masked ? 0.f : act_fwd<ACT>(pre[i]);
       const uint4 q = pack8(pre);
       __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
       *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bf
 }
 
 // red[0:C] += sum g, red[C:2C] += sum g*xhat   (accumulated as sum g*(z-mean), scaled by invstd once per block)
-template <bool HAS_RES>
+template <int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
                          const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
@@ -347,8 +358,8 @@ bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, con
       for (int u = 0; u < kRowsPerIter; ++u) {
         if (!in[u].live) continue;
         float pre[8], mult[8], zv[8], g[8];
-        pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
-        g_from_row(a, dyp, c, in[u], pre, mult, g);
+        pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+        g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           sg[i] += g[i];
@@ -384,7 +395,7 @@ bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, con
 // dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = A*g + Bz*z + Cc with per-channel A, Bz, Cc.
 // dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the
 // zero padding between utterances)
-template <bool HAS_RES>
+template <int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ red,
@@ -419,8 +430,8 @@ bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, cons
     for (int u = 0; u < kRowsPerIter; ++u) {
       if (!in[u].live) continue;
       float pre[8], mult[8], zv[8], g[8], o[8];
-      pre_from_row<HAS_RES>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
-      g_from_row(a, dyp, c, in[u], pre, mult, g);
+      pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
       *reinterpret_cast<uint4*>(dz + ((int64_t)in[u].b * dz_rows + in[u].t) * a.C + c) = pack8(o);
@@ -541,6 +552,26 @@ static BnActArgs make_args(const void* z, const float* scale, const float* shift
   return a;
 }
 
+// compile-time (activation, dropout, residual) variants of the three kernels above
+#define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                         \
+  do {                                                                                                          \
+    const int key_ = (act) * 4 + ((drop) ? 2 : 0) + ((has_res) ? 1 : 0);                                        \
+    switch (key_) {                                                                                             \
+      case 0: KERNEL<W2L_ACT_NONE, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 1: KERNEL<W2L_ACT_NONE, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 2: KERNEL<W2L_ACT_NONE, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 3: KERNEL<W2L_ACT_NONE, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                     \
+      case 4: KERNEL<W2L_ACT_RELU, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 5: KERNEL<W2L_ACT_RELU, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 6: KERNEL<W2L_ACT_RELU, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 7: KERNEL<W2L_ACT_RELU, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                     \
+      case 8: KERNEL<W2L_ACT_CLAMP20, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                \
+      case 9: KERNEL<W2L_ACT_CLAMP20, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                 \
+      case 10: KERNEL<W2L_ACT_CLAMP20, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                \
+      default: KERNEL<W2L_ACT_CLAMP20, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                 \
+    }                                                                                                           \
+  } while (0)
+
 static int check_bn_args(const char* who, const void* z, const float* scale, const float* shift, const void* res,
                          const float* res_scale, const float* res_shift, int B, int T, int C, int pl, int pr, float drop_p) {
   W2L_REQUIRE(z && scale && shift, "%s: null pointer", who);
@@ -637,8 +668,9 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  if (res) bn_act_pad_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
-  else bn_act_pad_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (__nv_bfloat16*)y, rpb);
+  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_pad: unknown activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  W2L_BN_DISPATCH(bn_act_pad_kernel, act, drop_p > 0.f, res != nullptr, a, (__nv_bfloat16*)y, rpb);
   return after_launch("bn_act_pad_kernel");
 }
 
@@ -655,8 +687,9 @@ int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  if (res) bn_act_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
-  else bn_act_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
+  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_bwd_reduce: unknown activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  W2L_BN_DISPATCH(bn_act_bwd_reduce_kernel, act, drop_p > 0.f, res != nullptr, a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
   return after_launch("bn_act_bwd_reduce_kernel");
 }
 
@@ -675,12 +708,10 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  if (res)
-    bn_act_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
-                                                                           (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
-  else
-    bn_act_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
-                                                                            (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
+  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_bwd_apply: unknown activation %d", act);
+  cudaStream_t st = (cudaStream_t)stream;
+  W2L_BN_DISPATCH(bn_act_bwd_apply_kernel, act, drop_p > 0.f, res != nullptr, a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
+                  (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
   return after_launch("bn_act_bwd_apply_kernel");
 }
 
