@@ -193,10 +193,13 @@ int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* ga
  * buffer: y[b, pad_left + t, c]; reflect halos of pad_left / pad_right rows are filled from the
  * interior (nn.ReflectionPad1d of the NEXT layer, wav2letter.py:28-34,41); rows t >= lens[b] are zeroed
  * when lens != NULL (the masked_fill of the consumer MaskedConv1d, jasper.py:116-119).
- * dropout: keep-mask from Philox(seed, element index), p = drop_p (0 disables). */
+ * dropout: keep-bits from Philox4x32-10(seed, element index / 8), 16 bits per element, p = drop_p (0 disables);
+ * drop_mask (nullable, B*T*C/8 bytes) receives the keep-bits so that the backward passes read them back instead
+ * of re-deriving them (they fall back to Philox when it is NULL). */
 int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
-                   int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream);
+                   int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask,
+                   void* stream);
 /* In-place reflect halo for a buffer whose interior rows [pad_left, pad_left+T) were written by the fused
  * conv epilogue (inference: BatchNorm folded into scale/shift, wav2letter.py:41-46). */
 int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream);
@@ -207,13 +210,13 @@ int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
 int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                           const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
                           float* red, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act,
-                          float drop_p, uint64_t seed, const int32_t* lens, void* stream);
+                          float drop_p, uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream);
 int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
                          const float* gamma, const float* red, void* dz /* [B, dz_rows, C]; rows >= T zero-filled */,
                          int32_t dz_rows, void* g_out /* nullable: masked g, bf16 [B,T,C] */,
                          int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
-                         uint64_t seed, const int32_t* lens, void* stream);
+                         uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream);
 
 /* logits [rows, ld] fp32 -> log_softmax / softmax over the first C columns -> out [rows, C] fp32
  * (wav2letter.py:87, jasper.py:470-473).  mode 0 = log_softmax, 1 = softmax. */

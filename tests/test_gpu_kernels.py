@@ -340,6 +340,13 @@ def test_bn_act_forward_backward(F, act, drop):
                               B, T, C, pl, pr, act, drop, seed)
     assert rel_l2(dz.float().cpu(), zr.grad.transpose(1, 2)) < 1e-2
     assert rel_l2(red[:C].cpu(), br.grad) < 5e-3 and rel_l2(red[C:].cpu(), gr.grad) < 5e-3
+    if drop > 0:   # keep-bits stored by the forward pass and read back by the backward passes == re-derived Philox bits
+        bits = torch.zeros(B * T * C // 8, dtype=torch.uint8, device="cuda")
+        yp2 = F.bn_act_pad(zc, scale, shift, B, T, C, pl, pr, act, drop, seed, drop_mask=bits)
+        assert torch.equal(yp2, yp)
+        dz2, red2, _ = F.bn_act_bwd(dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda(), zc, scale, shift, mean, invstd,
+                                    gamma.cuda(), B, T, C, pl, pr, act, drop, seed, drop_mask=bits)
+        assert rel_l2(dz2.float(), dz.float()) < 1e-3 and rel_l2(red2, red) < 1e-4
     dzp, _, _ = F.bn_act_bwd(dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda(), zc, scale, shift, mean, invstd, gamma.cuda(),
                              B, T, C, pl, pr, act, drop, seed, dz_rows=T + 7)
     assert rel_l2(dzp[:, :T].float(), dz.float()) < 1e-3 and (dzp[:, T:] == 0).all()      # reductions use fp32 atomics: last-bit noise

@@ -31,13 +31,24 @@ constexpr int kRenorm = 32;
 // shared-memory integer atomics are native (fp32 ones compile to CAS loops) and make the gradient deterministic.
 constexpr float kFix = 1073741824.f;         // 2^30
 
+// Raw MUFU ops (no denormal fix-up code on the serial critical path): arguments are <= 0, results in (0, 1] resp. [0, log2 3].
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lse2_2(float a, float b) {
-  float m = fmaxf(a, b);
-  return m + __log2f(exp2f(a - m) + exp2f(b - m));
+  const float m = fmaxf(a, b);
+  return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m));
 }
 __device__ __forceinline__ float lse2_3(float a, float b, float c) {
-  float m = fmaxf(a, fmaxf(b, c));
-  return m + __log2f(exp2f(a - m) + exp2f(b - m) + exp2f(c - m));
+  const float m = fmaxf(a, fmaxf(b, c));
+  return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m) + fast_ex2(c - m));
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
@@ -98,13 +109,13 @@ struct LaneLabels {
 };
 
 template <int R>
-__device__ __forceinline__ void load_labels(LaneLabels<R>& lb, const int32_t* __restrict__ tg, int S, int s0, int blank) {
+__device__ __forceinline__ void load_labels(LaneLabels<R>& lb, const int32_t* __restrict__ tg, int S, int s0, int dead_col) {
   lb.skip = 0;
   lb.skip_next = 0;
 #pragma unroll
   for (int j = 0; j < R / 2; ++j) {
     int i = (s0 >> 1) + j;  // label index of state s0 + 2j + 1
-    int l = blank;
+    int l = dead_col;       // states past the lattice read a column that holds log(0): they stay dead without a select
     if (i < S) {
       l = tg[i];
       if (i > 0 && l != tg[i - 1]) lb.skip |= 1u << j;
@@ -150,7 +161,7 @@ ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __
     return;
   }
   LaneLabels<R> lb;
-  load_labels<R>(lb, targets + (int64_t)n * tstride, S, s0, blank);
+  load_labels<R>(lb, targets + (int64_t)n * tstride, S, s0, Cp - 1);
   const float* lp_n = lp2 + (int64_t)n * T * Cp;
   float* arow = alpha_ws + (int64_t)n * T * Lp + s0;
   double* aoff = alpha_off + (int64_t)n * T;
@@ -206,7 +217,7 @@ ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __
       } else {
         v = lse2_2(a[r], am1) + lpb;
       }
-      a[r] = (s0 + r < L) ? fmaxf(v, 2.f * kNeg) : kNeg;
+      a[r] = v;
     }
     if ((t % kRenorm) == 0) {   // re-centre on the lattice maximum (uniform branch)
       float m = a[0];
@@ -284,7 +295,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const 
   const double ll2 = meta[n].ll2;
 
   LaneLabels<R> lb;
-  load_labels<R>(lb, targets + (int64_t)n * tstride, S, s0, blank);
+  load_labels<R>(lb, targets + (int64_t)n * tstride, S, s0, Cp - 1);
   const float* lp_n = lp2 + (int64_t)n * T * Cp;
   const float* arow = alpha_ws + (int64_t)n * T * Lp + s0;
   const double* aoff = alpha_off + (int64_t)n * T;
@@ -353,7 +364,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const 
         } else {
           v = lse2_2(b[r], bp1) + lpb;
         }
-        b[r] = (s0 + r < L) ? fmaxf(v, 2.f * kNeg) : kNeg;
+        b[r] = v;
       }
       if (((Tn - 1 - t) % kRenorm) == 0) {
         float m = b[0];
@@ -447,7 +458,7 @@ static bool make_plan(int64_t N, int64_t T, int64_t S_max, int64_t C, CtcPlan* p
   p->R = R;
   p->threads = (int)((L + 32 * R - 1) / (32 * R)) * 32;
   p->Lp = p->threads * R;
-  p->Cp = (int)((C + 31) / 32) * 32;
+  p->Cp = (int)((C + 32) / 32) * 32;            // > C: the last column always holds log(0) (dead lattice states read it)
   size_t o = 0;
   auto take = [&](size_t bytes) {
     size_t at = o;

@@ -17,21 +17,26 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
-// keep-multipliers (0 or 1/(1-p)) for the 8 consecutive elements starting at element index e (e % 8 == 0)
-__device__ __forceinline__ void dropout_mult8(uint64_t seed, uint64_t e, float p, float (&m)[8]) {
-  if (p <= 0.f) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = 1.f;
-    return;
-  }
+// keep-bits for the 8 consecutive elements starting at element index e (e % 8 == 0): ONE Philox call, 16 random bits per
+// element (keep iff u16 >= p * 65536, i.e. p is resolved to 1/65536)
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t e, float p) {
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint64_t c0 = e >> 2;
-  const uint4 r0 = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
-  const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(c0 + 1), (uint32_t)((c0 + 1) >> 32), 0u, 0u), key);
-  const uint32_t u[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  const uint64_t c0 = e >> 3;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
+  const uint32_t thr = (uint32_t)(p * 65536.f);
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= ((u[i] & 0xFFFFu) >= thr ? 1u : 0u) << (2 * i);
+    bits |= ((u[i] >> 16) >= thr ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
+}
+__device__ __forceinline__ void dropout_mult8(uint32_t bits, float p, float (&m)[8]) {
   const float inv = 1.f / (1.f - p);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = ((float)(u[i] >> 8) * (1.f / 16777216.f) >= p) ? inv : 0.f;
+  for (int i = 0; i < 8; ++i) m[i] = ((bits >> i) & 1u) ? inv : 0.f;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
@@ -193,6 +198,7 @@ struct BnActArgs {
   float drop_p;
   uint64_t seed;
   const int32_t* lens;
+  uint8_t* drop_mask;          // [B*T*C/8] keep-bits: written by the forward pass, read back by the backward passes
 };
 
 // Each thread walks its rows four at a time (rows r, r+8, r+16, r+24 of the block's range) and issues all 16-byte loads of
@@ -230,7 +236,7 @@ __device__ __forceinline__ void load_bwd_row(const BnActArgs& a, const __nv_bflo
 }
 
 // BN output [+ residual] with dropout applied ("pre"), the dropout multipliers and z for one staged row
-template <bool HAS_RES, bool DROP>
+template <bool HAS_RES, bool DROP, bool WRITE_MASK>
 __device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&sc)[8], const float (&sh)[8], const float (&rsc)[8],
                                              const float (&rsh)[8], const RowIn& in, int r, int c, float (&pre)[8], float (&mult)[8],
                                              float (&zv)[8]) {
@@ -244,7 +250,15 @@ __device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&s
     for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], rsc[i], rsh[i]);
   }
   if (DROP) {
-    dropout_mult8(a.seed, (uint64_t)((int64_t)r * a.C + c), a.drop_p, mult);
+    const int64_t e = (int64_t)r * a.C + c;
+    uint32_t bits;
+    if (WRITE_MASK) {
+      bits = dropout_keep8(a.seed, (uint64_t)e, a.drop_p);
+      if (a.drop_mask) a.drop_mask[e >> 3] = (uint8_t)bits;
+    } else {
+      bits = a.drop_mask ? (uint32_t)a.drop_mask[e >> 3] : dropout_keep8(a.seed, (uint64_t)e, a.drop_p);
+    }
+    dropout_mult8(bits, a.drop_p, mult);
 #pragma unroll
     for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
   }
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bf
     for (int u = 0; u < kRowsPerIter; ++u) {
       if (!in[u].live) continue;
       float pre[8], mult[8], zv[8];
-      pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      pre_from_row<HAS_RES, DROP, true>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
       const int b = in[u].b, t = in[u].t;
       const bool masked = a.lens && t >= a.lens[b];
 #pragma unroll
@@ -358,7 +372,7 @@ bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, con
       for (int u = 0; u < kRowsPerIter; ++u) {
         if (!in[u].live) continue;
         float pre[8], mult[8], zv[8], g[8];
-        pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+        pre_from_row<HAS_RES, DROP, false>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
         g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -430,7 +444,7 @@ bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, cons
     for (int u = 0; u < kRowsPerIter; ++u) {
       if (!in[u].live) continue;
       float pre[8], mult[8], zv[8], g[8], o[8];
-      pre_from_row<HAS_RES, DROP>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
+      pre_from_row<HAS_RES, DROP, false>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
       g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
@@ -532,7 +546,7 @@ static inline int grid_for(int64_t items, int threads) {
 
 static BnActArgs make_args(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                            const float* res_shift, int B, int T, int C, int pl, int pr, int act, float drop_p, uint64_t seed,
-                           const int32_t* lens) {
+                           const int32_t* lens, void* drop_mask) {
   BnActArgs a;
   a.z = (const __nv_bfloat16*)z;
   a.res = (const __nv_bfloat16*)res;
@@ -549,6 +563,7 @@ static BnActArgs make_args(const void* z, const float* scale, const float* shift
   a.drop_p = drop_p;
   a.seed = seed;
   a.lens = lens;
+  a.drop_mask = (uint8_t*)drop_mask;
   return a;
 }
 
@@ -658,12 +673,12 @@ int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* ga
 
 int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right,
-                   int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* stream) {
+                   int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask, void* stream) {
   using namespace w2l;
   int rc = check_bn_args("bn_act_pad", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
   if (rc) return rc;
   W2L_REQUIRE(y != nullptr, "bn_act_pad: null output");
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
   const int64_t rows = (int64_t)B * T;
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
@@ -677,12 +692,13 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
 int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                           const float* res_scale, const float* res_shift, const float* mean, const float* invstd, float* red,
                           int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
-                          uint64_t seed, const int32_t* lens, void* stream) {
+                          uint64_t seed, const int32_t* lens, const void* drop_mask_in, void* stream) {
   using namespace w2l;
+  void* drop_mask = const_cast<void*>(drop_mask_in);
   int rc = check_bn_args("bn_act_bwd_reduce", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
   if (rc) return rc;
   W2L_REQUIRE(dyp && mean && invstd && red, "bn_act_bwd_reduce: null pointer");
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
   const int64_t rows = (int64_t)B * T;
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);
@@ -697,13 +713,14 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd, const float* gamma,
                          const float* red, void* dz, int32_t dz_rows, void* g_out, int32_t B, int32_t T, int32_t C,
                          int32_t pad_left, int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens,
-                         void* stream) {
+                         const void* drop_mask_in, void* stream) {
   using namespace w2l;
+  void* drop_mask = const_cast<void*>(drop_mask_in);
   int rc = check_bn_args("bn_act_bwd_apply", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
   if (rc) return rc;
   W2L_REQUIRE(dyp && mean && invstd && red && dz, "bn_act_bwd_apply: null pointer");
   W2L_REQUIRE(dz_rows >= T, "bn_act_bwd_apply: dz_rows %d < T %d", dz_rows, T);
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens);
+  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
   const int64_t rows = (int64_t)B * T;
   const int col_blocks = (C + 255) / 256;
   const int rpb = rows_per_block_for(rows, col_blocks);

@@ -213,13 +213,14 @@ def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_m
 
 
 def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None,
-               res_shift=None, out=None):
+               res_shift=None, out=None, drop_mask=None):
+    """``drop_mask`` (uint8 [B*T*C/8], optional) receives the dropout keep-bits for the backward pass."""
     if out is None:
         out = torch.empty((B, pad_left + T + pad_right, C), dtype=torch.bfloat16, device=z.device)
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().w2l_bn_act_pad(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
-                                              B, T, C, pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()),
-                   "bn_act_pad")
+                                              B, T, C, pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask),
+                                              _stream()), "bn_act_pad")
     return out
 
 
@@ -231,7 +232,7 @@ def reflect_halo(y, T, pad_left, pad_right):
 
 
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None):
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None):
     """Returns (dz bf16 [B, dz_rows, C] (rows >= T zero), red fp32 [2C] = (dbeta, dgamma), g bf16 [B,T,C] | None)."""
     dev = z.device
     dz_rows = T if dz_rows is None else dz_rows
@@ -242,10 +243,10 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
     with torch.cuda.device(dev):
         _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
                                              _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
-                                             int(seed), _ptr(lens), _stream()), "bn_act_bwd_reduce")
+                                             int(seed), _ptr(lens), _ptr(drop_mask), _stream()), "bn_act_bwd_reduce")
         _lib.check(lib.w2l_bn_act_bwd_apply(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
                                             _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), dz_rows, _ptr(g), B, T, C,
-                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _stream()),
+                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask), _stream()),
                    "bn_act_bwd_apply")
     return dz, red, g
 

@@ -235,18 +235,21 @@ class ConvBNActFn(torch.autograd.Function):
         stats = F.bn_stats(z, Co)
         fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
-        seed = next_dropout_seed() if geo.get("drop_p", 0.0) > 0 else 0
+        drop_p = geo.get("drop_p", 0.0)
+        seed = next_dropout_seed() if drop_p > 0 else 0
+        mask = torch.empty((B * T_out * Co // 8,), dtype=torch.uint8, device=xin.device) if drop_p > 0 else None
         has_res = z_res is not None
-        yp = F.bn_act_pad(z, fin[0], fin[1], B, T_out, Co, pl, pr, geo["act"], geo.get("drop_p", 0.0), seed, geo.get("lens"),
-                          res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None)
+        yp = F.bn_act_pad(z, fin[0], fin[1], B, T_out, Co, pl, pr, geo["act"], drop_p, seed, geo.get("lens"),
+                          res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
+                          drop_mask=mask)
         ctx.conv, ctx.geo, ctx.seed, ctx.desc, ctx.has_res = conv, geo, seed, desc, has_res
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(xin, z, fin, gamma, z_res, fin_res)
+        ctx.save_for_backward(xin, z, fin, gamma, z_res, fin_res, mask)
         return yp
 
     @staticmethod
     def backward(ctx, dyp):
-        xin, z, fin, gamma, z_res, fin_res = ctx.saved_tensors
+        xin, z, fin, gamma, z_res, fin_res, mask = ctx.saved_tensors
         conv, geo, has_res = ctx.conv, ctx.geo, ctx.has_res
         B, T_out, Co = z.shape
         pl, pr = geo.get("out_pad", (0, 0))
@@ -259,7 +262,7 @@ class ConvBNActFn(torch.autograd.Function):
         dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
-                                  want_g=has_res, dz_rows=dz_rows)
+                                  want_g=has_res, dz_rows=dz_rows, drop_mask=mask)
         dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
         F.conv1d_wgrad(dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
         dx = None
