@@ -53,6 +53,33 @@ def conv_flops_per_utt(specs, t_in):
     return fwd, total
 
 
+def conv_flops_model(model, t_in):
+    """Algorithmic conv FLOPs per utterance (fwd, fwd+dgrad+wgrad) of a Wav2Letter / Jasper module tree: every dense conv counts
+    2*T_out*Cout*Cin*k per pass, depthwise convs 2*T_out*C*k; no dgrad for the very first conv."""
+    from wav2letter_pytorch_b200.layers import ConvParams, DepthwiseParams
+    fwd, total, t, first = 0.0, 0.0, t_in, True
+    convs = [m for m in model.modules() if isinstance(m, (ConvParams, DepthwiseParams))]
+    res_ids = {id(m) for n, m in model.named_modules() if ".res." in n and isinstance(m, ConvParams)}
+    for m in convs:
+        k, s, d, p = m.kernel_size[0], m.stride[0], m.dilation[0], m.padding[0]
+        if id(m) in res_ids:
+            t_out = t                                    # 1x1 branch over the block input: same length as the block output
+        elif hasattr(model, "conv1ds"):                  # Wav2Letter: reflection padding rule
+            from oracle.w2l_oracle import reflect_pad_amounts
+            pl, pr = reflect_pad_amounts(m.in_channels, k, s, d)
+            t_out = (t + pl + pr - d * (k - 1) - 1) // s + 1
+        else:
+            t_out = (t + 2 * p - d * (k - 1) - 1) // s + 1
+        cin = 1 if isinstance(m, DepthwiseParams) else m.in_channels
+        f = 2.0 * t_out * m.out_channels * cin * k
+        fwd += f
+        total += f * (2 if first else 3)
+        first = False
+        if id(m) not in res_ids:
+            t = t_out
+    return fwd, total
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -198,10 +225,18 @@ def run_gpu_arm(args):
         from wav2letter_pytorch_b200.distributed import init_process_group
         init_process_group("nccl", device=dev, max_ctas=int(os.environ.get("W2L_NCCL_MAX_CTAS", "8")))
 
-    def build(mid_layers):
-        cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers, "optimizer=novograd"]).model
+    def build(mid_layers, arch=None):
+        arch = arch or args.model
+        if arch == "wav2letter":
+            cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers, "optimizer=novograd"]).model
+            cls = Wav2Letter
+        else:                                            # jasper10x5 (BASELINE config 3) | jasper (the shipped separable yaml)
+            from wav2letter_pytorch_b200.jasper import Jasper
+            ov = ["model=%s" % arch, "optimizer=novograd"] + (["model.mid_layers=15"] if arch == "jasper" else [])
+            cfg = config.compose(overrides=ov).model
+            cls = Jasper
         torch.manual_seed(0)
-        model = Wav2Letter(cfg).to(dev).train()
+        model = cls(cfg).to(dev).train()
         (opt,), _ = model.configure_optimizers()
         reducer = None
         if world > 1:
@@ -254,8 +289,11 @@ def run_gpu_arm(args):
         return ms
 
     model, opt, reducer = build(args.mid_layers)
-    specs = O.w2l_layer_specs(args.mid_layers)
-    fwd_flops, train_flops = conv_flops_per_utt(specs, 1 + 100 * UTT_SEC)
+    if args.model == "wav2letter":
+        fwd_flops, train_flops = conv_flops_per_utt(O.w2l_layer_specs(args.mid_layers), 1 + 100 * UTT_SEC)
+        assert abs(conv_flops_model(model, 1 + 100 * UTT_SEC)[1] / train_flops - 1) < 1e-9
+    else:
+        fwd_flops, train_flops = conv_flops_model(model, 1 + 100 * UTT_SEC)
 
     # ---- device-resident throughput (the headline `value`), conv kernels timed live with CUDA events
     timer = KernelTimer()
@@ -275,7 +313,7 @@ def run_gpu_arm(args):
 
     # ---- the literal default config (mid_layers=1), reported beside the full stack
     extra = None
-    if args.mid_layers != 1 and not args.skip_default:
+    if args.model == "wav2letter" and args.mid_layers != 1 and not args.skip_default:
         del model, opt, reducer
         torch.cuda.empty_cache()
         m1, o1, r1 = build(1)
@@ -296,8 +334,11 @@ def run_gpu_arm(args):
         "metric": "audio-sec/sec per train step", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Wav2Letter mid_layers=%d (full layers: list of the default yaml) train step: fwd+CTC+greedy decode+bwd+NovoGrad, "
-                               "B=%d/GPU x %d s utterances, 64 mel bins, 225 labels" % (args.mid_layers, BATCH, UTT_SEC),
+        "config": {"workload": ("Wav2Letter mid_layers=%d (full layers: list of the default yaml)" % args.mid_layers if args.model == "wav2letter"
+                                else {"jasper10x5": "Jasper 10x5 (dense, configuration/model/jasper10x5.yaml)",
+                                      "jasper": "Jasper separable (shipped model/jasper.yaml, mid_layers=15)"}[args.model])
+                               + " train step: fwd+CTC+greedy decode+WER/CER+bwd+NovoGrad, B=%d/GPU x %d s utterances, 64 mel bins, 225 labels"
+                               % (BATCH, UTT_SEC),
                    "global_batch": world * BATCH, "parallelism": "dp%d" % world,
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
@@ -326,6 +367,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mid-layers", dest="mid_layers", type=int, default=20)
+    ap.add_argument("--model", default="wav2letter", choices=["wav2letter", "jasper10x5", "jasper"],
+                    help="wav2letter = BASELINE config 2 (headline); jasper10x5 = config 3; jasper = the shipped separable yaml")
     ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4, help="utterances in the bounded CPU sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-default", action="store_true")

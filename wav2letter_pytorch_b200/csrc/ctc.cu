@@ -16,6 +16,7 @@
 // Every R_RENORM frames the lattice is re-centred on its maximum and the offsets are carried in fp64, so
 // fp32 rounding does not grow with the utterance length.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -142,7 +143,7 @@ template <int R>
 __global__ void __launch_bounds__(1024)
 ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
                  const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
-                 float* __restrict__ alpha_ws, double* __restrict__ alpha_off, CtcMeta* __restrict__ meta, int Lp) {
+                 float* __restrict__ alpha_ws, double* __restrict__ alpha_off, CtcMeta* __restrict__ meta, int Lp, int dbg) {
   extern __shared__ __align__(16) float smem[];
   float* ring = smem;                                   // [kRing][Cp]
   float* s_bnd = ring + kRing * Cp;                     // [2][warps][2]
@@ -234,17 +235,19 @@ ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __
       s_bnd[((t & 1) * 32 + warp) * 2 + 0] = a[R - 1];
       s_bnd[((t & 1) * 32 + warp) * 2 + 1] = a[R - 2];
     }
-    float* dst = arow + (int64_t)t * Lp;
+    if (!(dbg & 1)) {
+      float* dst = arow + (int64_t)t * Lp;
 #pragma unroll
-    for (int r = 0; r < R; ++r) dst[r] = a[r];
-    if (tid == 0) aoff[t] = off;
-    {
+      for (int r = 0; r < R; ++r) dst[r] = a[r];
+      if (tid == 0) aoff[t] = off;
+    }
+    if (!(dbg & 2)) {
       int p = t + kRing - 1;
       if (p < Tn && tid < cp_lanes) cp_async16(ring + (p % kRing) * Cp + tid * 4, lp_n + (int64_t)p * Cp + tid * 4);
       cp_async_commit();
       cp_async_wait<kRing - 2>();
     }
-    __syncthreads();
+    if (!(dbg & 4)) __syncthreads();
   }
   // log-likelihood: lse(alpha[L-1], alpha[L-2])
   if (tid < 2) s_fin[tid] = kNeg;
@@ -486,8 +489,9 @@ static int launch_ctc(const CtcPlan& pl, char* ws, int64_t N, int64_t T, int64_t
   W2L_REQUIRE(smem_b <= 220 * 1024, "ctc: shared memory %zu too large", smem_b);
   W2L_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   W2L_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+  static const int dbg = getenv("W2L_CTC_DBG") ? atoi(getenv("W2L_CTC_DBG")) : 0;      // development knob (timing experiments)
   ctc_alpha_kernel<R><<<(unsigned)N, pl.threads, smem_a, st>>>(lp2, (int)T, pl.Cp, targets, tstride, in_len, tg_len, blank, alpha,
-                                                             aoff, meta, pl.Lp);
+                                                             aoff, meta, pl.Lp, dbg);
   int rc = after_launch("ctc_alpha_kernel");
   if (rc) return rc;
   if (grad) {
