@@ -43,6 +43,11 @@ int w2l_version(void);
 const char* w2l_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t w2l_launch_count(void);
+/* Cap on the SMs the persistent conv GEMM grids occupy (0 = all).  The data-parallel host sets it to
+ * (#SM - collective CTAs) so that the gradient all-reduce running beside backward gets SMs of its own
+ * (Lightning DDP's bucketed all-reduce overlapped with backward, README.md:40 / config.yaml:21). */
+int w2l_set_sm_budget(int32_t sms);
+int32_t w2l_get_sm_budget(void);
 
 /* Host-side Levenshtein distance between two int32 symbol sequences (HOST pointers).  Replaces the
  * python-Levenshtein calls behind Decoder.wer / Decoder.cer (decoder.py:31-60).  Returns -1 on bad input. */
@@ -234,12 +239,15 @@ int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
  * Fused multi-tensor NovoGrad step.  Replaces the per-parameter Python loop of Novograd.step
  * (novograd.py:52-114): layer-wise second moment of ||g||^2, normalised gradient, decoupled weight
  * decay term, first moment, parameter update -- and refreshes the bf16 weight shadow in the same pass.
- * Arrays of device pointers / sizes live in device memory (n_tensors entries).
+ * Arrays of device pointers / sizes live in device memory (n_tensors entries).  The work is cut into chunks of
+ * w2l_novograd_chunk() elements, one CTA each: chunk_prefix[t] (device, int32 [n_tensors]) = index of tensor t's first
+ * chunk, i.e. the exclusive prefix sum of ceil(numel[t] / chunk); n_chunks = the total.
  */
+int32_t w2l_novograd_chunk(void);
 int w2l_novograd_step(float* const* params, float* const* grads, float* const* exp_avg, float* exp_avg_sq /*[n]*/,
-                      void* const* shadow_bf16 /* nullable entries */, const int64_t* numel, int32_t n_tensors,
-                      float lr, float beta1, float beta2, float eps, float weight_decay, int32_t grad_averaging,
-                      float* norms_ws /*[n] scratch*/, void* stream);
+                      void* const* shadow_bf16 /* nullable entries */, const int64_t* numel, const int32_t* chunk_prefix,
+                      int32_t n_tensors, int32_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int32_t grad_averaging, float* norms_ws /*[n] scratch*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     "w2l_version": (c_i32, []),
     "w2l_last_error": (ctypes.c_char_p, []),
     "w2l_launch_count": (c_i64, []),
+    "w2l_set_sm_budget": (c_i32, [c_i32]),
+    "w2l_get_sm_budget": (c_i32, []),
     "w2l_edit_distance_host": (c_i64, [c_ptr, c_i64, c_ptr, c_i64]),
     "w2l_edit_distance_batch_host": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32]),
     "w2l_greedy_decode_workspace_bytes": (c_size, [c_i64, c_i64]),
@@ -107,8 +109,9 @@ SIGNATURES = {
     "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_cast_bf16": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
-    "w2l_novograd_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_ptr,
-                                  c_ptr]),
+    "w2l_novograd_chunk": (c_i32, []),
+    "w2l_novograd_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32,
+                                  c_i32, c_ptr, c_ptr]),
 }
 
 

@@ -90,7 +90,18 @@ class ConvCTCASR(_Base):
         scores, out_lens = self.forward(inputs, input_lengths)
         # the criterion takes [T, N, C]; this is a strided view, the CTC kernel reads it in place
         loss = self.criterion(scores.transpose(0, 1), targets, out_lens, target_lengths)
-        return loss, self.add_string_metrics(scores, out_lens, texts, prefix)
+        from .layers import WgradStream
+        if not (scores.is_cuda and WgradStream.enabled):
+            return loss, self.add_string_metrics(scores, out_lens, texts, prefix)
+        # decode + WER/CER feed only the logger: they run on the side stream beside the CTC recursion (one CTA per utterance
+        # leaves most SMs idle) and are joined before the step returns
+        main, side = torch.cuda.current_stream(scores.device), WgradStream.side(scores.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            metrics = self.add_string_metrics(scores, out_lens, texts, prefix)
+        scores.record_stream(side)
+        main.wait_stream(side)
+        return loss, metrics
 
     def training_step(self, batch, batch_idx):
         loss, metrics = self._step(batch, "train")

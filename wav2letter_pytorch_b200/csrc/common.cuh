@@ -14,6 +14,7 @@ namespace w2l {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int gemm_sms();   // num_sms() capped by w2l_set_sm_budget
 // Call right after a <<<>>> launch: bumps the library-wide launch counter and surfaces launch errors.
 int after_launch(const char* kernel_name);
 

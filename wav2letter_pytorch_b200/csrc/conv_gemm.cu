@@ -420,7 +420,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t st, int grid_override =
     W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     configured = true;
   }
-  int grid = grid_override > 0 ? grid_override : (p.num_tiles < num_sms() ? p.num_tiles : num_sms());
+  int grid = grid_override > 0 ? grid_override : (p.num_tiles < gemm_sms() ? p.num_tiles : gemm_sms());
   if (grid < 1) return W2L_OK;
   conv_gemm_kernel<MODE><<<grid, kGemmThreads, kGemmSmem, st>>>(p);
   return after_launch(MODE == MODE_FWD ? "conv_gemm_kernel<fwd>" : MODE == MODE_DGRAD ? "conv_gemm_kernel<dgrad>" : "conv_gemm_kernel<wgrad>");
@@ -449,7 +449,7 @@ static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* 
   const int bn = pick_bn(n_pad, wgrad_mn4d(d) ? 64 : 16);
   const int64_t tiles = (int64_t)d->k * ((d->Cout + kBlockM - 1) / kBlockM) * ((n_pad + bn - 1) / bn);
   const int64_t iters = (int64_t)d->B * ((d->T_out + kBlockK - 1) / kBlockK);
-  int64_t grid = num_sms();
+  int64_t grid = gemm_sms();
   const int64_t min_iters = 32;                       // keep the per-CTA mainloop long enough to amortise the epilogue
   if (tiles * iters / grid < min_iters) grid = tiles * iters / min_iters > 0 ? tiles * iters / min_iters : 1;
   const int64_t rounds = tiles / grid;

@@ -46,6 +46,15 @@ int num_sms() {
   return cached;
 }
 
+// SMs the persistent GEMM kernels may occupy (w2l_set_sm_budget): the data-parallel host reserves a few SMs for the
+// gradient collective, whose CTAs cannot co-reside with a 197 KB-shared-memory GEMM CTA -- without the reservation a
+// 148-CTA persistent grid runs as two waves whenever a collective holds an SM.
+static std::atomic<int> g_sm_budget{0};
+int gemm_sms() {
+  const int n = num_sms(), b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < n) ? b : n;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -201,3 +210,9 @@ extern "C" int w2l_edit_distance_batch_host(const int32_t* a, const int64_t* a_o
   for (auto& th : pool) th.join();
   return W2L_OK;
 }
+
+extern "C" int w2l_set_sm_budget(int32_t sms) {
+  w2l::g_sm_budget.store(sms > 0 ? sms : 0);
+  return W2L_OK;
+}
+extern "C" int32_t w2l_get_sm_budget(void) { return w2l::gemm_sms(); }

@@ -12,8 +12,12 @@ rank-0 buffer broadcast.  ``GradientReducer`` gives the same semantics for the m
   * conv weights are permuted views over kernel-layout storage; the reducer all-reduces the dense storage view, so no
     gradient is copied or re-laid-out for the wire.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+_comm_ctas = [0]          # CTAs per NCCL collective chosen by init_process_group (0 = NCCL default: nothing reserved)
 
 
 def dense_view(t):
@@ -31,12 +35,21 @@ class GradientReducer:
     """``small_numel``: gradients below this size (biases, BatchNorm affine parameters) are packed into one flat buffer
     and reduced with a single collective in ``finish()`` instead of ~60 latency-bound launches per step."""
 
-    def __init__(self, model, process_group=None, small_numel=65536):
+    def __init__(self, model, process_group=None, small_numel=65536, comm_sms=None):
         if not dist.is_initialized():
             raise RuntimeError("GradientReducer needs an initialised torch.distributed process group")
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.use_avg = dist.get_backend(process_group) == "nccl"
+        # the collective's CTAs need SMs of their own: a persistent GEMM CTA fills an SM's shared memory, so a grid of
+        # #SM CTAs launched while NCCL holds a few SMs runs as two waves (measured: wgrad 11 -> 17 ms/step at 8 GPUs)
+        if comm_sms is None:
+            comm_sms = int(os.environ.get("W2L_COMM_SMS", str(_comm_ctas[0])))
+        if self.use_avg and self.world > 1 and comm_sms > 0:
+            from . import _lib
+            lib = _lib.load()
+            lib.w2l_set_sm_budget(0)
+            lib.w2l_set_sm_budget(max(1, lib.w2l_get_sm_budget() - comm_sms))
         self.small_numel = small_numel
         self.pending, self.small, self.hooks = [], [], []
         for p in model.parameters():
@@ -45,6 +58,13 @@ class GradientReducer:
 
     def _reduce(self, t):
         op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM      # gloo (CPU tests): sum now, scale in finish()
+        if t.is_cuda:
+            from .layers import WgradStream
+            if WgradStream.enabled:                    # weight gradients are produced on the wgrad side stream
+                side = WgradStream.side(t.device)
+                side.wait_stream(torch.cuda.current_stream(t.device))
+                with torch.cuda.stream(side):
+                    return dist.all_reduce(t, op=op, group=self.group, async_op=True)
         return dist.all_reduce(t, op=op, group=self.group, async_op=True)
 
     def _on_grad(self, p):
@@ -74,7 +94,7 @@ class GradientReducer:
         self.hooks.clear()
 
 
-def init_process_group(backend="nccl", device=None, max_ctas=8, **kwargs):
+def init_process_group(backend="nccl", device=None, max_ctas=4, **kwargs):
     """``dist.init_process_group`` with NCCL limited to a few CTAs per collective: the gradient all-reduce of one layer
     (<= 93 MB) has the whole remaining backward pass to hide behind, while every SM it occupies slows the persistent
     one-CTA-per-SM GEMM kernels running next to it."""
@@ -84,6 +104,7 @@ def init_process_group(backend="nccl", device=None, max_ctas=8, **kwargs):
             opts.config.max_ctas = int(max_ctas)
             opts.config.min_ctas = 1
             kwargs.setdefault("pg_options", opts)
+            _comm_ctas[0] = int(max_ctas)
         except Exception:  # noqa: BLE001  (older torch: fall back to NCCL's defaults)
             pass
     if device is not None:

@@ -8,6 +8,7 @@ Conv weights keep the reference's parameter shape ``[Cout, Cin, k]`` but live in
 kernels read (``[k, Cout, Cin]``, or ``[Cout, k, Cin]`` for the unfolded strided first layer): the Parameter is a
 permuted view, so packing a bf16 shadow is a plain cast and weight gradients need no re-layout."""
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -15,6 +16,59 @@ import torch.nn as nn
 from . import functional as F
 
 _seed_counter = [0]
+
+
+class WgradStream:
+    """Weight-gradient kernels run on a per-device side stream.  In backward the critical chain is
+    dgrad_i -> BatchNorm-backward_{i-1} -> dgrad_{i-1}; wgrad_i only feeds the optimizer, so it is launched AFTER dgrad_i on
+    the side stream and the (HBM-bound) BatchNorm-backward kernels of the next layer run beside it instead of serialising with
+    the (tensor-bound) GEMMs.  The compute stream re-joins the side stream when the backward pass ends (engine callback), so
+    ``.grad`` consumers need no extra care; ``GradientReducer`` enqueues its collectives behind the side stream."""
+    enabled = os.environ.get("W2L_WGRAD_STREAM", "1") != "0"
+    _side = {}
+    _pending = {}
+    _task = -1
+
+    @classmethod
+    def side(cls, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        s = cls._side.get(idx)
+        if s is None:
+            s = cls._side[idx] = torch.cuda.Stream(device=idx)
+        return s
+
+    @classmethod
+    def fork(cls, device):
+        """Call after the producers of the wgrad operands were enqueued: the side stream waits for them.  Returns the side
+        stream, or None when disabled / outside a backward pass."""
+        task = torch._C._current_graph_task_id()
+        if not cls.enabled or task < 0:
+            return None
+        main, side = torch.cuda.current_stream(device), cls.side(device)
+        side.wait_stream(main)
+        if task != cls._task:                          # first fork of this backward pass: join when the pass ends
+            cls._task = task
+            cls._pending.clear()
+            torch.autograd.Variable._execution_engine.queue_callback(cls._join)
+        cls._pending[(main.device.index, main.cuda_stream)] = main
+        return side
+
+    @classmethod
+    def _join(cls):
+        for main in cls._pending.values():
+            main.wait_stream(cls.side(main.device))
+        cls._pending.clear()
+
+
+def wgrad_async(side, dy, x, desc, dw):
+    """conv1d_wgrad on the side stream returned by ``WgradStream.fork`` (plain call when it is None)."""
+    if side is None:
+        return F.conv1d_wgrad(dy, x, desc, dw)
+    with torch.cuda.stream(side):
+        F.conv1d_wgrad(dy, x, desc, dw)
+    for t in (dy, x, dw):
+        t.record_stream(side)
+    return dw
 
 
 def next_dropout_seed():
@@ -122,6 +176,28 @@ class ConvParams(nn.Module):
             F.pack_wt(self.storage(), self._shadow_t, self.out_channels, self.cin_eff)
             self._shadow_t_version = ver
         return self._shadow_t
+
+    def prefetch_packed_t(self):
+        """Called from the forward pass: re-pack the backward-data shadow on the side stream, where it runs beside the forward
+        GEMMs instead of sitting on the backward critical path."""
+        if not WgradStream.enabled or not self.weight.is_cuda:
+            return
+        if getattr(self, "_shadow_t", None) is not None and self._shadow_t_version == (self.weight._version, self.weight.data_ptr()):
+            return
+        dev = self.weight.device
+        side = WgradStream.side(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.packed_t()
+            self._shadow_t_event = side.record_event()
+
+    def packed_t_synced(self):
+        """``packed_t()`` for the compute stream: waits (on the device) for a prefetch in flight."""
+        ev = getattr(self, "_shadow_t_event", None)
+        if ev is not None:
+            torch.cuda.current_stream(self.weight.device).wait_event(ev)
+            self._shadow_t_event = None
+        return self.packed_t()
 
     def mark_shadow_fresh(self):
         """Called by the fused optimizer, which rewrites the shadow itself."""
@@ -231,6 +307,8 @@ class ConvBNActFn(torch.autograd.Function):
         pl, pr = geo.get("out_pad", (0, 0))
         z = torch.empty((B, T_out, Co), dtype=torch.bfloat16, device=xin.device)
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
+        if ctx.needs_input_grad[0]:
+            conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
         F.conv1d_fwd(xin, conv.packed(), desc, z)          # conv bias is folded into the BN statistics below
         stats = F.bn_stats(z, Co)
         fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
@@ -264,14 +342,15 @@ class ConvBNActFn(torch.autograd.Function):
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
                                   want_g=has_res, dz_rows=dz_rows, drop_mask=mask)
         dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
-        F.conv1d_wgrad(dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
+        side = WgradStream.fork(z.device)              # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
             if flat:
-                F.conv1d_dgrad_wt(dz, conv.packed_t(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx)
+                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx)
             else:
-                F.conv1d_dgrad_wt(dz, conv.packed_t(), ctx.desc, dx)
+                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx)
+        wgrad_async(side, dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
         dbias = torch.zeros(Co, dtype=torch.float32, device=z.device) if ctx.has_bias else None   # exactly 0 under train BN
         return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
 
@@ -287,6 +366,8 @@ class ResidualBranchFn(torch.autograd.Function):
         Co = conv.out_channels
         z = torch.empty((B, T, Co), dtype=torch.bfloat16, device=xin.device)
         desc = conv_desc(conv, B, T, T, 0)
+        if ctx.needs_input_grad[0]:
+            conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, z)
         stats = F.bn_stats(z, Co)
         fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
@@ -303,11 +384,12 @@ class ResidualBranchFn(torch.autograd.Function):
         B, T, Co = z.shape
         dz, red, _ = F.bn_act_bwd(g.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, Co, 0, 0, F.ACT_NONE)
         dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
-        F.conv1d_wgrad(dz, xin, ctx.desc, dw)
+        side = WgradStream.fork(z.device)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad_wt(dz, conv.packed_t(), ctx.desc, dx)
+            F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx)
+        wgrad_async(side, dz, xin, ctx.desc, dw)
         return dx, conv.grad_view(dw), red[Co:], red[:Co], None, None
 
 
@@ -322,6 +404,8 @@ class ConvHeadFn(torch.autograd.Function):
         ld = (Co + 7) // 8 * 8
         logits = torch.empty((B, T, ld), dtype=torch.float32, device=xin.device)
         desc = conv_desc(conv, B, T, T, 0, ldy=ld, y_dtype=F.DT_F32)
+        if ctx.needs_input_grad[0]:
+            conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
         out = F.log_softmax(logits, Co, mode)
         ctx.conv, ctx.mode = conv, mode
@@ -340,12 +424,13 @@ class ConvHeadFn(torch.autograd.Function):
         dl = F.log_softmax_bwd(dout.contiguous(), out, cp)            # bf16 [B,T,cout_pad], zero padded
         desc = conv_desc(conv, B, T, T, 0, ldy=cp)
         dw = torch.empty((1, Co, conv.cin_eff), dtype=torch.float32, device=xin.device)
-        F.conv1d_wgrad(dl, xin, desc, dw)
-        dbias = F.colsum(dl, Co) if ctx.has_bias else None
+        side = WgradStream.fork(xin.device)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad_wt(dl, conv.packed_t(), desc, dx)
+            F.conv1d_dgrad_wt(dl, conv.packed_t_synced(), desc, dx)
+        wgrad_async(side, dl, xin, desc, dw)
+        dbias = F.colsum(dl, Co) if ctx.has_bias else None
         return dx, conv.grad_view(dw), dbias, None, None
 
 

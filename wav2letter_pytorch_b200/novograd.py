@@ -75,7 +75,11 @@ class Novograd(Optimizer):
             host[3] = torch.tensor(shadows, dtype=torch.int64)
             host[4] = torch.tensor([p.numel() for p in params], dtype=torch.int64)
             hosts.append([host, None])
+        chunk = _lib.load().w2l_novograd_chunk()
+        counts = torch.tensor([(p.numel() + chunk - 1) // chunk for p in params], dtype=torch.int64)
+        prefix = (torch.cumsum(counts, 0) - counts).to(torch.int32)
         plan = dict(hosts=hosts, turn=0, dev=torch.empty((5, n), dtype=torch.int64, device=dev), v=v,
+                    chunk_prefix=prefix.to(dev), n_chunks=int(counts.sum()),
                     ws=torch.empty(n, dtype=torch.float32, device=dev), convs=[c for c in convs if c is not None])
         self._plans[key] = plan
         return plan
@@ -114,8 +118,8 @@ class Novograd(Optimizer):
             b1, b2 = group["betas"]
             P = F._ptr
             with torch.cuda.device(dev.device):
-                _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]), P(dev[3]), P(dev[4]), len(params),
-                                                 float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]), P(dev[3]), P(dev[4]), P(plan["chunk_prefix"]),
+                                                 len(params), plan["n_chunks"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                                  float(group["weight_decay"]), int(bool(group["grad_averaging"])), P(plan["ws"]),
                                                  F._stream()), "novograd_step")
             for p in params:
