@@ -123,6 +123,9 @@ int w2l_ctc_loss(const float* x, int32_t from_logits, int64_t N, int64_t T, int6
  *   y  [B, y_rows, ldy] (bf16 or fp32): rows t in [0, T_out) are written at y row (t + y_row_offset),
  *      columns [0, Cout)
  *   epilogue: v = acc + bias;  if scale: v = v*scale[co] + shift[co];  act(v)
+ *   bn_stats (nullable) [2*Cout] fp32, zeroed by the caller: the epilogue adds the per-channel sum and sum of
+ *      squares of the values it stores (after bf16 rounding) -- BatchNorm1d's training statistics
+ *      (wav2letter.py:37, jasper.py:363) without a second pass over y; w2l_bn_finalize consumes it
  * w2l_conv1d_dgrad: dx[b, u, ci] = sum_j sum_co dy[b, u + dy_row_offset - j*dilation, co] * w[j, co, ci]
  *   (same packed weights, read as an MN-major operand; no transposed copy is kept)
  * w2l_conv1d_wgrad: dw[j, co, ci] (+)= sum_b sum_t dy[b, t, co] * x[b, t + x_row_offset + j*dilation, ci]
@@ -144,8 +147,8 @@ typedef struct {
   int32_t act;          /* W2L_ACT_*                                   */
 } w2l_conv_desc;
 
-int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, void* y,
-                   const w2l_conv_desc* d, void* stream);
+int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, float* bn_stats,
+                   void* y, const w2l_conv_desc* d, void* stream);
 int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream);
 /* Backward-data with a second, transposed bf16 shadow wt [k, Cin_pad16, Cout_pad] (wt[k-1-j][ci][co] = w[j][co][ci],
  * written by w2l_pack_wt): both GEMM operands are then K-major, which the tensor pipe consumes ~30% faster than the

@@ -129,6 +129,18 @@ def test_ctc_random(F, N, T, S, C, from_logits):
     _check_ctc(F, lp, tg, il, tl, from_logits=from_logits)
 
 
+def test_ctc_serial_schedule(F, monkeypatch):
+    """the large-lattice schedule (alpha, then beta fused with the gradient) must agree with the oracle too"""
+    monkeypatch.setenv("W2L_CTC_DBG", "8")
+    g = torch.Generator().manual_seed(11)
+    N, T, S, C = 5, 90, 20, 29
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g), -1)
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    il = torch.tensor([90, 64, 41, 90, 12], dtype=torch.int32)
+    tl = torch.tensor([20, 7, 20, 0, 11], dtype=torch.int32)
+    _check_ctc(F, lp, tg, il, tl)
+
+
 def test_ctc_transposed_view(F):
     """the reference passes out.transpose(0,1): a [T,N,C] view of the contiguous [N,T,C] tensor."""
     g = torch.Generator().manual_seed(9)
@@ -219,6 +231,15 @@ def test_conv_fwd_dgrad_wgrad(F, B, T, Cin, Cout, k, d, pad):
     want2 = torch.clamp(want * sc + sh, 0, 20)
     assert rel_l2(y2[:, 2:2 + T_out, :Cout].float().cpu(), want2) < 6e-3
     assert (y2[:, :2] == 7.0).all() and (y2[:, 2 + T_out:] == 7.0).all()      # rows outside [off, off+T_out) untouched
+    # BatchNorm statistics from the epilogue: sum / sum of squares of exactly the bf16 values it stored
+    desc_s = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, ldy, F.DT_BF16, F.ACT_NONE)
+    ys = torch.zeros(B, T_out, ldy, dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * Cout, dtype=torch.float32, device="cuda")
+    F.conv1d_fwd(xc, wc, desc_s, ys, bn_stats=st)
+    yd = ys[:, :, :Cout].double().reshape(-1, Cout)
+    assert torch.allclose(st[:Cout].double(), yd.sum(0), rtol=1e-4, atol=1e-3 * float(yd.abs().sum(0).max()) / 100)
+    assert torch.allclose(st[Cout:].double(), (yd * yd).sum(0), rtol=1e-4)
+    assert torch.equal(F.bn_stats(ys[:, :, :Cout].contiguous(), Cout)[Cout:] > 0, st[Cout:] > 0) if Cout % 8 == 0 else True
     # ---- dgrad
     dyc = torch.zeros(B, T_out, cout_pad, dtype=torch.bfloat16, device="cuda")
     dyc[:, :, :Cout] = dy.transpose(1, 2).to(torch.bfloat16).cuda()

@@ -41,9 +41,9 @@ def test_abi_argument_validation_without_gpu(lib):
     from wav2letter_pytorch_b200._lib import ConvDesc
     d = ConvDesc(2, 100, 60, 64, 64, 3, 1, 100, 0, 100, 0, 64, 0, 0)       # Cin = 60 < 64
     buf = ctypes.c_void_p(0x1000)
-    rc = lib.w2l_conv1d_fwd(buf, buf, None, None, None, buf, ctypes.byref(d), None)
+    rc = lib.w2l_conv1d_fwd(buf, buf, None, None, None, None, buf, ctypes.byref(d), None)
     assert rc == 1 and b"Cin" in lib.w2l_last_error()
-    assert lib.w2l_conv1d_fwd(buf, buf, None, None, None, buf, None, None) == 1
+    assert lib.w2l_conv1d_fwd(buf, buf, None, None, None, None, buf, None, None) == 1
     assert lib.w2l_greedy_decode(None, 2, 10, 29, 290, 29, None, 0, None, None, None, None, None, 0, None) == 1
     assert lib.w2l_ctc_loss(buf, 0, 2, 10, 500, 5000, 500, buf, 4, buf, buf, 0, 1, 1, None, None, None, buf, 1 << 20, None) == 1
     assert lib.w2l_ctc_loss_workspace_bytes(64, 750, 225) > 64 * 750 * 451 * 4

@@ -85,7 +85,7 @@ SIGNATURES = {
     "w2l_ctc_loss_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "w2l_ctc_loss": (c_i32, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_i32, c_i32,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
-    "w2l_conv1d_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_conv1d_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_conv1d_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_conv1d_dgrad_wt": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_pack_wt": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),

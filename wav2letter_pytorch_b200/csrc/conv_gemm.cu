@@ -53,6 +53,7 @@ struct GemmParams {
   const float* bias;
   const float* scale;
   const float* shift;
+  float* bn_stats;          // fwd: [2*N_valid] per-channel sum / sum of squares of the STORED (bf16-rounded) output, or null
   int32_t act;
   int32_t y_dtype;
   void* y;
@@ -137,6 +138,23 @@ struct UnitIter {
     return false;
   }
 };
+
+// Column sums over the 32 rows a warp holds (one row per lane, 32 columns per lane): recursive halving -- at each step a lane
+// keeps the half of its columns selected by one bit of its lane id and receives the partner's sums for that half -- 31
+// shuffles leave lane i with the sum of column i.
+__device__ __forceinline__ float warp_column_sum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool upper = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float keep = upper ? x[i + w] : x[i];
+      const float send = upper ? x[i] : x[i + w];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return x[0];
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -343,6 +361,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = (v[i] != v[i]) ? v[i] : fminf(fmaxf(v[i], 0.f), act_hi);
           }
+          if (MODE == MODE_FWD && p.bn_stats != nullptr) {   // BatchNorm batch statistics of what is stored (kernel-uniform branch)
+            float s1[32], s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float q = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+              s1[i] = q;
+              s2[i] = q * q;
+            }
+            const float c1 = warp_column_sum32(s1, lane), c2 = warp_column_sum32(s2, lane);
+            if (c0 + lane < p.BN && nbase + lane < p.N_valid) {
+              atomicAdd(p.bn_stats + nbase + lane, c1);
+              atomicAdd(p.bn_stats + p.N_valid + nbase + lane, c2);
+            }
+          }
           if (row_ok && !(p.dbg & 2)) {
             const int64_t off = (int64_t)tc.b * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
             const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
@@ -464,8 +496,8 @@ static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* 
 
 extern "C" {
 
-int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, void* y,
-                   const w2l_conv_desc* d, void* stream) {
+int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, float* bn_stats,
+                   void* y, const w2l_conv_desc* d, void* stream) {
   using namespace w2l;
   int rc = check_desc(d, "conv1d_fwd");
   if (rc) return rc;
@@ -507,6 +539,7 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   p.bias = bias;
   p.scale = scale;
   p.shift = shift;
+  p.bn_stats = bn_stats;
   p.act = d->act;
   p.y_dtype = d->y_dtype;
   p.y = y;

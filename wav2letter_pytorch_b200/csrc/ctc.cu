@@ -43,13 +43,17 @@ __device__ __forceinline__ float fast_lg2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// log2-sum-exp2 with the maximum's term folded to the constant 1: one MUFU op fewer than exponentiating every argument
+// (the recursion is MUFU- and latency-bound: 2 / 3 instead of 3 / 4 special-function ops per lattice state)
 __device__ __forceinline__ float lse2_2(float a, float b) {
   const float m = fmaxf(a, b);
-  return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m));
+  return m + fast_lg2(1.f + fast_ex2(fminf(a, b) - m));
 }
 __device__ __forceinline__ float lse2_3(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  return m + fast_lg2(fast_ex2(a - m) + fast_ex2(b - m) + fast_ex2(c - m));
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  const float m = fmaxf(hi, c);
+  const float mid = fmaxf(lo, fminf(hi, c)), low = fminf(lo, c);
+  return m + fast_lg2(1.f + fast_ex2(mid - m) + fast_ex2(low - m));
 }
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
@@ -140,16 +144,15 @@ __device__ __forceinline__ float block_max(float v, float* s_red) {
 
 // ------------------------------------------------------------------------------------------------
 template <int R>
-__global__ void __launch_bounds__(1024)
-ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                 const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
-                 float* __restrict__ alpha_ws, double* __restrict__ alpha_off, CtcMeta* __restrict__ meta, int Lp, int dbg) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void
+ctc_alpha_body(float* smem, int n, const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
+               const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
+               float* __restrict__ alpha_ws, double* __restrict__ alpha_off, CtcMeta* __restrict__ meta, int Lp, int dbg) {
   float* ring = smem;                                   // [kRing][Cp]
   float* s_bnd = ring + kRing * Cp;                     // [2][warps][2]
   float* s_red = s_bnd + 2 * 32 * 2;                    // [32]
   float* s_fin = s_red + 32;                            // [2]
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tn = max(0, min(T, in_len[n]));
   const int S = max(0, min((int)tstride, tg_len[n]));
   const int L = 2 * S + 1;
@@ -262,6 +265,337 @@ ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __
     float ll = lse2_2(s_fin[0], s_fin[1]);
     meta[n].feasible = ll > kDead;
     meta[n].ll2 = off + (double)ll;
+  }
+}
+
+
+// ---- parallel schedule: alpha and beta recursions in separate CTAs, both spilled, gradient in a third, fully parallel pass.
+// The recursion is a serial chain of T dependent steps, so everything in the per-frame body is trimmed to the chain:
+//   * frames are processed in blocks of kBlk: the block's lp rows arrive by cp.async (double-buffered), the lattice is re-centred
+//     on its maximum once per block (offsets carried in fp64, one per block), the CTA synchronises twice per block;
+//   * inside a block there is NO CTA barrier: the one (alpha) / two (beta) lattice values that cross a warp boundary per frame
+//     travel through a shared-memory slot tagged with the frame number, polled by the consuming lane -- lower warps run ahead,
+//     so the poll normally hits at once (a wavefront over the warps);
+//   * skip-transition masks are additive (0 / -inf) constants, spills are one vector store per thread.
+constexpr int kBlk = 32;
+
+template <int R>
+__device__ __forceinline__ void spill_states(float* dst, const float (&v)[R]) {
+  if (R == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; r += 4) *reinterpret_cast<float4*>(dst + r) = make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+  }
+}
+
+__device__ __forceinline__ void slot_put(float4* slot, float v0, float v1, int tag) {
+  asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(slot)), "f"(v0), "f"(v1), "f"(__int_as_float(tag)), "f"(0.f)
+               : "memory");
+}
+// Every lane of the warp reads the same address (a broadcast), so the retry branch is warp-uniform.  Tags only grow, and the
+// slot for step i holds tag i or (stale) i - kBlk: "tag >= wanted" means ready.  The load for step i is issued one iteration
+// early (slot_load), when the feeding warp -- one step ahead in the wavefront -- has normally published it already, so its
+// latency hides behind the current step's arithmetic; slot_ready re-polls only if that speculative read came too soon.
+__device__ __forceinline__ float4 slot_load(const float4* slot) {
+  float4 q;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(smem_u32(slot)) : "memory");
+  return q;
+}
+__device__ __forceinline__ void slot_ready(float4& q, const float4* slot, int tag) {
+  uint32_t spins = 0;
+  while (__float_as_int(q.z) < tag) {
+    q = slot_load(slot);
+    if (++spins > (1u << 24)) __trap();                 // protocol bug: trap instead of hanging the GPU
+  }
+}
+
+// One frame of the recursion on a thread's R states.  x1 (, x2): the neighbouring lane's boundary value(s) of the previous frame.
+template <int R, bool BETA>
+__device__ __forceinline__ void lattice_step(float (&v)[R], float x1, float x2, float lpb, const float (&lpl)[R / 2],
+                                             const float (&skadd)[R / 2]) {
+  if (!BETA) {
+    // a lane's first state is a blank (needs s-1), its second a label whose s-2 is the previous lane's LAST state
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+      const float am1 = (r >= 1) ? v[(r >= 1) ? r - 1 : 0] : x1;
+      if (r & 1) {
+        const float am2 = (r >= 2) ? v[(r >= 2) ? r - 2 : 0] : x1;
+        v[r] = lse2_3(v[r], am1, am2 + skadd[r >> 1]) + lpl[r >> 1];
+      } else {
+        v[r] = lse2_2(v[r], am1) + lpb;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float bp1 = (r + 1 < R) ? v[(r + 1 < R) ? r + 1 : 0] : x1;
+      if (r & 1) {
+        const float bp2 = (r + 2 < R) ? v[(r + 2 < R) ? r + 2 : 0] : x2;
+        v[r] = lse2_3(v[r], bp1, bp2 + skadd[r >> 1]) + lpl[r >> 1];
+      } else {
+        v[r] = lse2_2(v[r], bp1) + lpb;
+      }
+    }
+  }
+}
+
+// One direction of the lattice recursion for utterance n.  BETA = false: alpha_t(s) = lse(a(s), a(s-1), [skip] a(s-2)) + lp_t(l_s),
+// t ascending.  BETA = true: beta_t(s) = lse(b(s), b(s+1), [skip] b(s+2)) + lp_t(l_s), t descending (ATen convention: beta
+// includes the emission at t).  Step i is frame t = BETA ? Tn-1-i : i; rows are spilled at ws[n][t][s]; off_blk[n][i / kBlk]
+// is the fp64 offset of the values spilled during block i / kBlk.
+template <int R, bool BETA>
+__device__ __forceinline__ void
+lattice_pass(float* smem, int n, const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
+             const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank, float* __restrict__ ws,
+             double* __restrict__ off_blk, int n_blk, CtcMeta* __restrict__ meta, int Lp) {
+  float* lpbuf = smem;                                                    // [2][kBlk][Cp]
+  float4* slots = reinterpret_cast<float4*>(lpbuf + 2 * kBlk * Cp);       // [33][kBlk]: one ring per warp + an always-ready dummy ring
+  float* s_red = reinterpret_cast<float*>(slots + 33 * kBlk);             // [32]
+  float* s_fin = s_red + 32;                                              // [2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int Tn = max(0, min(T, in_len[n]));
+  const int S = max(0, min((int)tstride, tg_len[n]));
+  const int L = 2 * S + 1;
+  const int s0 = tid * R;
+  if (Tn == 0) {
+    if (!BETA && tid == 0) {
+      meta[n].ll2 = 0.0;
+      meta[n].feasible = (S == 0);
+    }
+    return;
+  }
+  // per-thread lattice constants: column (byte offset in an lp row) of each odd (label) state, additive skip mask
+  int lab_b[R / 2];
+  float skadd[R / 2];
+  {
+    const int32_t* tg = targets + (int64_t)n * tstride;
+#pragma unroll
+    for (int j = 0; j < R / 2; ++j) {
+      const int i = (s0 >> 1) + j;                // label index of state s0 + 2j + 1
+      int l = Cp - 1;                              // states past the lattice read the column that holds log(0): they stay dead
+      bool skip = false;
+      if (i < S) {
+        l = tg[i];
+        skip = BETA ? (i + 1 < S && tg[i + 1] != l) : (i > 0 && tg[i - 1] != l);
+      }
+      lab_b[j] = l * 4;
+      skadd[j] = skip ? 0.f : kNeg;
+    }
+  }
+  const int blank_b = blank * 4;
+  for (int i = tid; i < 33 * kBlk; i += nthreads)   // ring 32 feeds the warp that has no neighbour: log(0), tag = "always ready"
+    slots[i] = i < 32 * kBlk ? make_float4(0.f, 0.f, __int_as_float(-1), 0.f) : make_float4(kNeg, kNeg, __int_as_float(0x7fffffff), 0.f);
+  const float* lp_n = lp2 + (int64_t)n * T * Cp;
+  const int blocks = (Tn + kBlk - 1) / kBlk;
+  // rows of block k: steps [k*kBlk, k*kBlk + cnt) = frames [f_lo, f_lo + cnt), ascending in memory for both directions
+  auto prefetch_block = [&](int k) {
+    if (k < blocks) {
+      const int i0 = k * kBlk, cnt = min(kBlk, Tn - i0);
+      const int f_lo = BETA ? Tn - i0 - cnt : i0;
+      const float* src = lp_n + (int64_t)f_lo * Cp;
+      float* dst = lpbuf + (k & 1) * kBlk * Cp;
+      for (int q = tid; q < cnt * (Cp >> 2); q += nthreads) cp_async16(dst + q * 4, src + q * 4);
+    }
+    cp_async_commit();
+  };
+  prefetch_block(0);
+  prefetch_block(1);
+
+  float v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = kNeg;
+  double off = 0.0;
+  double* offs = off_blk + (int64_t)n * n_blk;
+  const int64_t wstep = BETA ? -(int64_t)Lp : (int64_t)Lp;
+  float* wp = ws + ((int64_t)n * T + (BETA ? Tn - 1 : 0)) * Lp + s0;     // spill row of the current step
+  const bool has_nb = BETA ? (warp < nwarps - 1) : (warp > 0);            // a neighbouring warp feeds this warp's boundary lane
+  const bool edge = BETA ? (lane == 31) : (lane == 0);                    // the lane that takes the neighbouring warp's values
+  const bool pub = BETA ? (lane == 0) : (lane == 31);                     // the lane that publishes this warp's boundary values
+  const float4* slot_in = slots + (has_nb ? (BETA ? warp + 1 : warp - 1) : 32) * kBlk;
+  float4* slot_out = slots + warp * kBlk;
+  const int row_b = BETA ? -Cp * 4 : Cp * 4;
+
+  for (int k = 0; k < blocks; ++k) {
+    cp_async_wait<1>();                       // block k's rows have landed (block k+1 may still be in flight)
+    __syncthreads();
+    const int i0 = k * kBlk, cnt = min(kBlk, Tn - i0);
+    float shift = 0.f;                        // this block's re-centring, also owed by the boundary values published before it
+    if (k > 0) {                              // re-centre the carried lattice on its maximum
+      float m = v[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) m = fmaxf(m, v[r]);
+      m = block_max(m, s_red);
+      if (m > kDead) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = fmaxf(v[r] - m, kNeg);
+        off += (double)m;
+        shift = m;
+      }
+    }
+    if (tid == 0) offs[k] = off;
+    // first row of the block in step order: ascending frames sit at rows 0.., descending ones at rows cnt-1..
+    const char* rowp = reinterpret_cast<const char*>(lpbuf + (k & 1) * kBlk * Cp) + (BETA ? (cnt - 1) * Cp * 4 : 0);
+    int ii = 0;
+    if (k == 0) {                             // step 0: initial lattice column
+      const float lpb = *reinterpret_cast<const float*>(rowp + blank_b);
+      if (!BETA) {
+        if (tid == 0) {
+          v[0] = lpb;
+          if (L > 1) v[1] = *reinterpret_cast<const float*>(rowp + lab_b[0]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int s = s0 + r;
+          if (s == L - 1) v[r] = lpb;
+          if (s == L - 2 && (r & 1)) v[r] = *reinterpret_cast<const float*>(rowp + lab_b[r >> 1]);
+        }
+      }
+      if (pub) slot_put(slot_out, v[BETA ? 0 : R - 1], BETA ? v[1] : 0.f, 0);
+      spill_states<R>(wp, v);
+      wp += wstep;
+      rowp += row_b;
+      ii = 1;
+    }
+    float4 q = slot_load(slot_in + ((ii + kBlk - 1) & (kBlk - 1)));
+    for (; ii < cnt; ++ii) {
+      const int i = i0 + ii;
+      // the neighbouring warp's boundary values of step i-1 (read one iteration ago), then the speculative read for step i
+      slot_ready(q, slot_in + ((ii + kBlk - 1) & (kBlk - 1)), i - 1);
+      const float y1 = fmaxf(q.x - shift, kNeg);
+      const float y2 = BETA ? fmaxf(q.y - shift, kNeg) : kNeg;
+      q = slot_load(slot_in + ii);
+      shift = 0.f;
+      const float lpb = *reinterpret_cast<const float*>(rowp + blank_b);
+      float lpl[R / 2];
+#pragma unroll
+      for (int j = 0; j < R / 2; ++j) lpl[j] = *reinterpret_cast<const float*>(rowp + lab_b[j]);
+      float x1, x2 = kNeg;
+      if (!BETA) {
+        x1 = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+      } else {
+        x1 = __shfl_down_sync(0xffffffffu, v[0], 1);
+        x2 = __shfl_down_sync(0xffffffffu, v[1], 1);
+      }
+      x1 = edge ? y1 : x1;
+      if (BETA) x2 = edge ? y2 : x2;
+      lattice_step<R, BETA>(v, x1, x2, lpb, lpl, skadd);
+      if (pub) slot_put(slot_out + ii, v[BETA ? 0 : R - 1], BETA ? v[1] : 0.f, i);
+      spill_states<R>(wp, v);
+      wp += wstep;
+      rowp += row_b;
+    }
+    __syncthreads();                          // every warp is done with block k's rows and slots
+    prefetch_block(k + 2);
+  }
+  if (!BETA) {                                // log-likelihood: lse(alpha[L-1], alpha[L-2])
+    if (tid < 2) s_fin[tid] = kNeg;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (s0 + r == L - 1) s_fin[0] = v[r];
+      if (s0 + r == L - 2) s_fin[1] = v[r];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float ll = lse2_2(s_fin[0], s_fin[1]);
+      meta[n].feasible = ll > kDead;
+      meta[n].ll2 = off + (double)ll;
+    }
+  }
+}
+
+// One launch, 2N CTAs: CTA n runs utterance n's alpha recursion, CTA N+n its beta recursion -- the two serial chains of T
+// frames run side by side (they are independent until the gradient), halving the critical path of the loss+gradient.
+template <int R>
+__global__ void __launch_bounds__(1024)
+ctc_lattice_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
+                   const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank, float* __restrict__ alpha_ws,
+                   double* __restrict__ alpha_off, float* __restrict__ beta_ws, double* __restrict__ beta_off, int n_blk,
+                   CtcMeta* __restrict__ meta, int Lp) {
+  extern __shared__ __align__(16) float smem[];
+  if ((int)blockIdx.x < N)
+    lattice_pass<R, false>(smem, blockIdx.x, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_off, n_blk, meta, Lp);
+  else
+    lattice_pass<R, true>(smem, blockIdx.x - N, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, beta_ws, beta_off, n_blk, meta, Lp);
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024)
+ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
+                 const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
+                 float* __restrict__ alpha_ws, double* __restrict__ alpha_off, CtcMeta* __restrict__ meta, int Lp, int dbg) {
+  extern __shared__ __align__(16) float smem[];
+  ctc_alpha_body<R>(smem, blockIdx.x, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_off, meta, Lp, dbg);
+}
+
+// Gradient from the spilled lattices, fully parallel over (utterance, frame): one warp per frame bins the occupancies
+// gamma_t(s) = 2^(alpha + beta - lp - ll) per class (fixed-point shared-memory integer atomics: deterministic) and emits
+// softmax - occupancy.  grid (ceil(T / kGradFrames), N), 8 warps, each warp walks kGradFrames/8 frames.
+constexpr int kGradFrames = 32;
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
+                const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
+                const float* __restrict__ alpha_ws, const double* __restrict__ alpha_off, const float* __restrict__ beta_ws,
+                const double* __restrict__ beta_off, int n_blk, const CtcMeta* __restrict__ meta, int Lp, int zero_infinity,
+                int reduction_mean, int N, float* __restrict__ grad) {
+  extern __shared__ __align__(16) float smem[];
+  const int nwarps = blockDim.x >> 5;
+  float* rows = smem;                                               // [nwarps][Cp]
+  uint32_t* bins = reinterpret_cast<uint32_t*>(rows + nwarps * Cp);  // [nwarps][Cp]
+  uint8_t* lab = reinterpret_cast<uint8_t*>(bins + nwarps * Cp);     // [L] class of every lattice state
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Tn = max(0, min(T, in_len[n]));
+  const int S = max(0, min((int)tstride, tg_len[n]));
+  const int L = 2 * S + 1;
+  const bool feasible = meta[n].feasible != 0;
+  const int t_begin = blockIdx.x * kGradFrames, t_end = min(T, t_begin + kGradFrames);
+  float* g_n = grad + (int64_t)n * T * C;
+  if (!feasible || Tn == 0 || t_begin >= Tn) {   // exact zeros past the utterance / for an infeasible one (NaN without zero_infinity)
+    const float fill = (!feasible && !zero_infinity) ? NAN : 0.f;
+    for (int i = t_begin * C + tid; i < t_end * C; i += blockDim.x) g_n[i] = (i < Tn * C) ? fill : 0.f;
+    return;
+  }
+  const int32_t* tg = targets + (int64_t)n * tstride;
+  for (int s = tid; s < L; s += blockDim.x) lab[s] = (uint8_t)((s & 1) ? tg[s >> 1] : blank);
+  __syncthreads();
+  const float gscale = reduction_mean ? 1.f / ((float)N * (float)max(S, 1)) : 1.f;
+  const double ll2 = meta[n].ll2;
+  float* row = rows + warp * Cp;
+  uint32_t* bin = bins + warp * Cp;
+  for (int t = t_begin + warp; t < t_end; t += nwarps) {
+    float* g_t = g_n + (int64_t)t * C;
+    if (t >= Tn) {
+      for (int c = lane; c < C; c += 32) g_t[c] = 0.f;
+      continue;
+    }
+    const float* lp_t = lp2 + ((int64_t)n * T + t) * Cp;
+    for (int c = lane; c < Cp; c += 32) {
+      row[c] = lp_t[c];
+      bin[c] = 0u;
+    }
+    __syncwarp();
+    const float cst = (float)(alpha_off[(int64_t)n * n_blk + t / kBlk] + beta_off[(int64_t)n * n_blk + (Tn - 1 - t) / kBlk] - ll2);
+    const float* a_t = alpha_ws + ((int64_t)n * T + t) * Lp;
+    const float* b_t = beta_ws + ((int64_t)n * T + t) * Lp;
+    float gb = 0.f;
+    for (int s = lane; s < L; s += 32) {
+      const int l = lab[s];
+      const float g = exp2f(a_t[s] + b_t[s] - row[l] + cst);
+      if (s & 1) {
+        if (g > 0.f) atomicAdd(bin + l, __float2uint_rn(fminf(g, 1.5f) * kFix));
+      } else {
+        gb += g;
+      }
+    }
+    // blank states: lanes hold disjoint partial sums; fold them in a fixed order
+#pragma unroll
+    for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+    if (lane == 0 && gb > 0.f) atomicAdd(bin + blank, __float2uint_rn(fminf(gb, 1.5f) * kFix));
+    __syncwarp();
+    for (int c = lane; c < C; c += 32) g_t[c] = (exp2f(row[c]) - (float)bin[c] * (1.f / kFix)) * gscale;
+    __syncwarp();
   }
 }
 
@@ -447,17 +781,20 @@ __global__ void ctc_finish_kernel(const CtcMeta* __restrict__ meta, const int32_
 // ---------------------------------------------------------------- host side
 struct CtcPlan {
   int R, threads, Lp, Cp;
-  size_t off_lp2, off_alpha, off_aoff, off_meta, total;
+  bool parallel;   // alpha and beta in parallel CTAs + a parallel gradient pass (beta is spilled too); else alpha, then beta+grad fused
+  size_t off_lp2, off_alpha, off_aoff, off_beta, off_boff, off_meta, total;
 };
+
+// the parallel schedule doubles the lattice spill; beyond this size the serial (fused beta+gradient) schedule is used
+constexpr size_t kCtcParallelSpillLimit = (size_t)3 << 30;
 
 static bool make_plan(int64_t N, int64_t T, int64_t S_max, int64_t C, CtcPlan* p) {
   const int64_t L = 2 * S_max + 1;
+  // one warp per SM sub-partition when the lattice allows it (the recursion is a latency chain: fewer, fatter warps keep the
+  // per-frame exchange between warps short and give each warp more independent states to interleave)
   int R = 2;
-  while (R <= 8 && (L + 32 * R - 1) / (32 * R) > 16) R *= 2;
-  if (R > 8) {
-    R = 8;
-    if ((L + 32 * R - 1) / (32 * R) > 32) return false;
-  }
+  while (R < 8 && (L + 32 * R - 1) / (32 * R) > 4) R *= 2;
+  if ((L + 32 * R - 1) / (32 * R) > 32) return false;
   p->R = R;
   p->threads = (int)((L + 32 * R - 1) / (32 * R)) * 32;
   p->Lp = p->threads * R;
@@ -469,8 +806,12 @@ static bool make_plan(int64_t N, int64_t T, int64_t S_max, int64_t C, CtcPlan* p
     return at;
   };
   p->off_lp2 = take((size_t)N * T * p->Cp * sizeof(float));
-  p->off_alpha = take((size_t)N * T * p->Lp * sizeof(float));
-  p->off_aoff = take((size_t)N * T * sizeof(double));
+  const size_t lattice = (size_t)N * T * p->Lp * sizeof(float);
+  p->parallel = 2 * lattice <= kCtcParallelSpillLimit;
+  p->off_alpha = take(lattice);
+  p->off_aoff = take((size_t)N * T * sizeof(double));          // serial schedule: one per frame; parallel: one per kBlk frames
+  p->off_beta = p->parallel ? take(lattice) : 0;
+  p->off_boff = p->parallel ? take((size_t)N * T * sizeof(double)) : 0;
   p->off_meta = take((size_t)N * sizeof(CtcMeta));
   p->total = o;
   return true;
@@ -489,7 +830,27 @@ static int launch_ctc(const CtcPlan& pl, char* ws, int64_t N, int64_t T, int64_t
   W2L_REQUIRE(smem_b <= 220 * 1024, "ctc: shared memory %zu too large", smem_b);
   W2L_CUDA(cudaFuncSetAttribute(ctc_alpha_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
   W2L_CUDA(cudaFuncSetAttribute(ctc_beta_grad_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-  static const int dbg = getenv("W2L_CTC_DBG") ? atoi(getenv("W2L_CTC_DBG")) : 0;      // development knob (timing experiments)
+  const char* dbg_env = getenv("W2L_CTC_DBG");            // development knob: 1/2/4 timing experiments, 8 = force the serial schedule
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  W2L_REQUIRE(N <= 65535, "ctc: batch %lld exceeds the grid limit", (long long)N);
+  if (pl.parallel && grad && !(dbg & 8)) {
+    float* beta = (float*)(ws + pl.off_beta);
+    double* boff = (double*)(ws + pl.off_boff);
+    const int n_blk = (int)((T + kBlk - 1) / kBlk);
+    const size_t smem_l = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + (32 + 2) * sizeof(float);
+    W2L_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+    ctc_lattice_kernel<R><<<(unsigned)(2 * N), pl.threads, smem_l, st>>>(lp2, (int)N, (int)T, pl.Cp, targets, tstride, in_len, tg_len,
+                                                                        blank, alpha, aoff, beta, boff, n_blk, meta, pl.Lp);
+    int rc = after_launch("ctc_lattice_kernel");
+    if (rc) return rc;
+    const int gw = 8;
+    const size_t smem_g = (size_t)gw * pl.Cp * 8 + (size_t)(2 * tstride + 1 + 15);
+    W2L_REQUIRE(smem_g <= 48 * 1024, "ctc: gradient pass shared memory %zu too large", smem_g);
+    dim3 grid((unsigned)((T + kGradFrames - 1) / kGradFrames), (unsigned)N);
+    ctc_grad_kernel<<<grid, gw * 32, smem_g, st>>>(lp2, (int)T, (int)C, pl.Cp, targets, tstride, in_len, tg_len, blank, alpha, aoff, beta,
+                                                   boff, n_blk, meta, pl.Lp, zero_infinity, reduction_mean, (int)N, grad);
+    return after_launch("ctc_grad_kernel");
+  }
   ctc_alpha_kernel<R><<<(unsigned)N, pl.threads, smem_a, st>>>(lp2, (int)T, pl.Cp, targets, tstride, in_len, tg_len, blank, alpha,
                                                              aoff, meta, pl.Lp, dbg);
   int rc = after_launch("ctc_alpha_kernel");

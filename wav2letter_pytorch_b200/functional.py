@@ -97,11 +97,12 @@ def make_desc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, 
     return ConvDesc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype, act)
 
 
-def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None):
+def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
+    """``bn_stats`` (fp32 [2*Cout], zero-filled): receives the per-channel sum / sum of squares of the stored output."""
     _need_cuda(x, w, y)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().w2l_conv1d_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(y), ctypes.byref(desc),
-                                              _stream()), "conv1d_fwd")
+        _lib.check(_lib.load().w2l_conv1d_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(bn_stats), _ptr(y),
+                                              ctypes.byref(desc), _stream()), "conv1d_fwd")
     return y
 
 

@@ -289,6 +289,19 @@ def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0,
                        T_out if y_rows is None else y_rows, y_row_offset, conv.out_channels if ldy is None else ldy, y_dtype, act)
 
 
+_EPILOGUE_STATS = os.environ.get("W2L_EPILOGUE_STATS", "1") != "0"      # 0: separate bn_stats pass over z (A/B measurements)
+
+
+def conv_fwd_with_stats(xin, conv, desc, z):
+    """conv forward into ``z`` + BatchNorm batch statistics [2*Cout] (sum, sum of squares of the stored bf16 values)."""
+    if not _EPILOGUE_STATS:
+        F.conv1d_fwd(xin, conv.packed(), desc, z)
+        return F.bn_stats(z, conv.out_channels)
+    stats = torch.zeros((2 * conv.out_channels,), dtype=torch.float32, device=xin.device)
+    F.conv1d_fwd(xin, conv.packed(), desc, z, bn_stats=stats)
+    return stats
+
+
 class ConvBNActFn(torch.autograd.Function):
     """conv (+bias) -> BatchNorm(train statistics) [+ residual branch] -> dropout -> activation, written into the
     consumer's padded buffer.  Inputs: time-major bf16 ``xin`` ([B, x_rows, cin_eff]), the conv/BN parameters, the
@@ -309,8 +322,7 @@ class ConvBNActFn(torch.autograd.Function):
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
-        F.conv1d_fwd(xin, conv.packed(), desc, z)          # conv bias is folded into the BN statistics below
-        stats = F.bn_stats(z, Co)
+        stats = conv_fwd_with_stats(xin, conv, desc, z)        # batch statistics from the epilogue; conv bias folded below
         fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
         drop_p = geo.get("drop_p", 0.0)
@@ -368,8 +380,7 @@ class ResidualBranchFn(torch.autograd.Function):
         desc = conv_desc(conv, B, T, T, 0)
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
-        F.conv1d_fwd(xin, conv.packed(), desc, z)
-        stats = F.bn_stats(z, Co)
+        stats = conv_fwd_with_stats(xin, conv, desc, z)
         fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
         bn.num_batches_tracked += 1
         ctx.conv, ctx.desc = conv, desc
