@@ -337,6 +337,20 @@ def run_gpu_arm(args):
     timer.unwrap()
     all_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     conv_ms = {k: v for k, v in all_ms.items() if k.startswith("conv1d")}
+    # ---- the same GEMM launches without overlap (wgrad back on the compute stream): per-kernel quality, spans do not overlap
+    iso_ms = None
+    if not args.profile:
+        from wav2letter_pytorch_b200.layers import WgradStream
+        was = WgradStream.enabled
+        WgradStream.enabled = False
+        iso_timer = KernelTimer()
+        timed(model, opt, reducer, 0, 1, False)
+        iso_timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad"])
+        iso_steps = max(3, min(args.steps, 6))
+        timed(model, opt, reducer, iso_steps, 0, False)
+        iso_timer.unwrap()
+        WgradStream.enabled = was
+        iso_ms = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
     # ---- end to end: pinned host inputs in, loss out, every step
     ms_e2e = ms if args.profile else timed(model, opt, reducer, args.steps, 1, True)
 
@@ -395,6 +409,11 @@ def run_gpu_arm(args):
     if os.path.exists(tr):                                # dram bytes per launch from the committed ncu --set full capture
         with open(tr) as f:
             line["roofline"]["traffic"] = json.load(f).get(args.model)
+    if iso_ms:
+        tot = sum(iso_ms.values())
+        a = train_flops * BATCH / (tot / 1e3) / 1e12
+        line["roofline"]["serialized"] = {"achieved": a, "frac": a / peaks["tf_sustained"], "kernel_ms_per_step": tot, "by_pass_ms": iso_ms,
+                                          "note": "same launches with wgrad on the compute stream (no overlap): sum of per-launch CUDA-event spans"}
     if extra:
         line["default_config"] = extra
     if world == 1 and not args.skip_cpu:
