@@ -268,8 +268,8 @@ def run_gpu_arm(args):
         (opt,), _ = model.configure_optimizers()
         reducer = None
         if world > 1:
-            from wav2letter_pytorch_b200.distributed import GradientReducer
-            reducer = GradientReducer(model)
+            from wav2letter_pytorch_b200.distributed import make_gradient_reducer
+            reducer = make_gradient_reducer(model)
         return model, opt, reducer
 
     x, il, tg, tl, texts = synthetic_batch(BATCH, UTT_SEC, seed=rank)
@@ -291,6 +291,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_spread = []                                      # (min, median, max) per-step ms of every timed region, in call order
+
     def timed(model, opt, reducer, steps, warmup, from_host):
         def batch():
             return tuple(t.to(dev, non_blocking=True) for t in host) if from_host else resident
@@ -302,20 +304,28 @@ def run_gpu_arm(args):
         if steps == 0:
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
         for it in range(steps):
             l = one_step(model, opt, reducer, batch(), it)
             if from_host:
                 l.item()                                  # device->host read of the step's loss
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) / steps
+        per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        step_spread.append((min(per_step), sorted(per_step)[len(per_step) // 2], max(per_step)))
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
+    from wav2letter_pytorch_b200 import reserve_device_memory
+    reserve_device_memory(dev, gib=int(os.environ.get("W2L_RESERVE_GIB", "64")))      # no cudaMalloc inside the timed steps
     model, opt, reducer = build(args.mid_layers)
     if args.model == "wav2letter":
         fwd_flops, train_flops = conv_flops_per_utt(O.w2l_layer_specs(args.mid_layers), 1 + 100 * UTT_SEC)
@@ -331,7 +341,9 @@ def run_gpu_arm(args):
     launches0 = _lib.launch_count()
     if rank == 0:
         sampler.start()
+    seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     ms = timed(model, opt, reducer, args.steps, 0, False)
+    new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0    # cudaMalloc calls inside the timed region
     clocks = sampler.stop() if rank == 0 else None
     launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
     timer.unwrap()
@@ -387,6 +399,8 @@ def run_gpu_arm(args):
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
         "gpu_launches": int(launches),
+        "step_ms_min_median_max": {"value": step_spread[0], "e2e": step_spread[2] if len(step_spread) > 2 else None},
+        "cuda_mallocs_in_timed_region": int(new_segments),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<fwd|dgrad|wgrad> (tcgen05 implicit GEMM)", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained", "unit": "TFLOP/s",

@@ -252,6 +252,20 @@ int w2l_novograd_step(float* const* params, float* const* grads, float* const* e
                       int32_t n_tensors, int32_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int32_t grad_averaging, float* norms_ws /*[n] scratch*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient averaging over NVLink peer memory.  Replaces the bucketed NCCL all-reduce that Lightning DDP
+ * performs for the reference (README.md:40 `--gpus`, config.yaml:21) on the hot path's only exchange.
+ * All ranks keep their gradients in a symmetric arena (same byte offsets everywhere).  HOST tables:
+ *   peer_data_host[r]   this process's mapping of rank r's arena (r == rank: the local arena)
+ *   peer_flags_host[r]  this process's mapping of rank r's flag block, ctas*world uint32, zero-initialised once
+ *   multicast_base      NVLS multicast mapping of the arena (in-switch reduction), or NULL for the peer-to-peer path
+ * Averages arena[offset : offset+numel] (floats, both multiples of 4) across ranks in place; every rank ends up with
+ * bit-identical values.  seq: the same, strictly increasing EVEN number on every rank for successive calls (seq and
+ * seq+1 tag the two barriers).  Every rank must enqueue the same calls in the same order.
+ */
+int w2l_grad_allreduce(void* const* peer_data_host, void* const* peer_flags_host, void* multicast_base, int64_t offset,
+                       int64_t numel, int32_t rank, int32_t world, uint32_t seq, int32_t ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

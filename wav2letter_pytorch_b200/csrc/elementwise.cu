@@ -91,6 +91,21 @@ __global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __
   __syncthreads();
   const int KF = k * F;
   __nv_bfloat16* ob = out + ((int64_t)b * rows + r0) * KF;
+  if ((F & 7) == 0) {                     // 16-byte stores: one thread packs 8 consecutive features of one (row, tap)
+    const int F8 = F >> 3, KF8 = k * F8;
+    for (int i = threadIdx.x; i < nrows * KF8; i += blockDim.x) {
+      const int r = i / KF8, c = i - r * KF8;
+      const int j = c / F8, f0 = (c - j * F8) << 3;
+      const float* src = tile + f0 * pitch + r * stride + j * dil;
+      uint4 q;
+      q.x = pack_bf16x2(src[0], src[pitch]);
+      q.y = pack_bf16x2(src[2 * pitch], src[3 * pitch]);
+      q.z = pack_bf16x2(src[4 * pitch], src[5 * pitch]);
+      q.w = pack_bf16x2(src[6 * pitch], src[7 * pitch]);
+      *reinterpret_cast<uint4*>(ob + (int64_t)r * KF + j * F + f0) = q;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < nrows * KF; i += blockDim.x) {
     const int r = i / KF, c = i - r * KF;
     const int j = c / F, f = c - j * F;

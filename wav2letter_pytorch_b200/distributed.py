@@ -123,3 +123,155 @@ def shard_batch(batch, rank, world):
     n = batch[0].shape[0]
     lo, hi = rank * n // world, (rank + 1) * n // world
     return tuple(b[lo:hi] if b is not None else None for b in batch)
+
+
+class PeerGradientReducer:
+    """Gradient averaging over NVLink peer memory with the library's own kernel (csrc/comm.cu) instead of NCCL collectives.
+
+    All large gradients live in ONE symmetric arena (same offsets on every rank; allocated and exchanged through
+    ``torch.distributed._symmetric_memory``, which is plumbing only): every conv layer's wgrad kernel writes straight into its slice
+    (``ConvParams._grad_buffer``), so the tensor autograd stores in ``.grad`` *is* the arena slice and nothing is copied.  From the
+    post-accumulate-grad hook -- i.e. right behind that layer's wgrad on the side stream -- one ``w2l_grad_allreduce`` launch per
+    layer is enqueued on a communication stream: barrier, in-switch reduction of the slice this rank owns (NVLS ``multimem``; or
+    peer loads in rank order when no multicast mapping exists), broadcast of the mean, barrier.  The kernel uses a few CTAs and no
+    shared memory, so it co-resides with the persistent GEMM CTAs of the remaining backward pass.  Small gradients (biases,
+    BatchNorm affine parameters) are staged through one packed region in ``finish()``.  Semantics = ``GradientReducer`` (DDP
+    mean); every rank ends with bit-identical gradients."""
+
+    def __init__(self, model, process_group=None, small_numel=65536, ctas=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        if not dist.is_initialized():
+            raise RuntimeError("PeerGradientReducer needs an initialised torch.distributed process group")
+        self.group = process_group if process_group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.lib = _lib.load()
+        self.ctas = int(os.environ.get("W2L_COMM_CTAS", "4")) if ctas is None else int(ctas)
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("PeerGradientReducer: CUDA parameters required")
+        self.device = params[0].device
+        # ---- arena layout: [large tensors, 512-byte aligned][packed small tensors]
+        self.entries, self.small_params, off = {}, [], 0
+        for p in params:
+            if p.numel() >= small_numel:
+                self.entries[id(p)] = (off, p.numel())
+                off = (off + p.numel() + 127) // 128 * 128
+            else:
+                self.small_params.append(p)
+        self.small_off = off
+        self.small_slices, so = {}, 0
+        for p in self.small_params:
+            self.small_slices[id(p)] = (so, p.numel())
+            so += (p.numel() + 3) // 4 * 4
+        self.small_numel = so
+        total = max(off + so, 4)
+        with torch.cuda.device(self.device):
+            self.arena = symm_mem.empty(total, dtype=torch.float32, device=self.device)
+            self.flags = symm_mem.empty(64 * 16, dtype=torch.int32, device=self.device)
+            self.arena.zero_()
+            self.flags.zero_()
+            torch.cuda.synchronize(self.device)
+            self.h_arena = symm_mem.rendezvous(self.arena, group=self.group)
+            self.h_flags = symm_mem.rendezvous(self.flags, group=self.group)
+        dist.barrier(group=self.group)                                     # every rank's flags are zero before the first kernel
+        import ctypes
+        Arr = ctypes.c_void_p * self.world
+        self._peer_data = Arr(*[int(p) for p in self.h_arena.buffer_ptrs])
+        self._peer_flags = Arr(*[int(p) for p in self.h_flags.buffer_ptrs])
+        mc = int(getattr(self.h_arena, "multicast_ptr", 0) or 0)
+        self.multicast = ctypes.c_void_p(mc) if (use_multicast and mc and os.environ.get("W2L_COMM_P2P", "0") != "1") else None
+        self.seq = 0
+        self.comm = torch.cuda.Stream(device=self.device)
+        # ---- hand the conv layers their arena slices; views shaped like the parameters for everything else
+        from .layers import ConvParams
+        conv_of = {id(m.weight): m for m in model.modules() if isinstance(m, ConvParams)}
+        self.views = {}
+        for p in params:
+            ent = self.entries.get(id(p))
+            if ent is None:
+                continue
+            flat = self.arena[ent[0]:ent[0] + ent[1]]
+            conv = conv_of.get(id(p))
+            if conv is not None:
+                buf = flat.view(conv.k_eff, conv.out_channels, conv.cin_eff)
+                buf._w2l_arena = True
+                conv._grad_buffer = buf
+                self.views[id(p)] = conv.grad_view(buf)
+            else:
+                self.views[id(p)] = flat.view(dense_view(p).shape)
+        self.pending_small, self.hooks = [], []
+        for p in params:
+            self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._model = model
+
+    # ---- one library call: average arena[offset : offset+numel] over the ranks, on the communication stream
+    def _allreduce(self, offset, numel):
+        numel = (numel + 3) // 4 * 4
+        self.seq = (self.seq + 2) & 0xFFFFFFFF
+        from . import _lib
+        import ctypes
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.w2l_grad_allreduce(self._peer_data, self._peer_flags, self.multicast, offset, numel, self.rank, self.world,
+                                                   self.seq, self.ctas, ctypes.c_void_p(self.comm.cuda_stream)), "grad_allreduce")
+
+    def _on_grad(self, p):
+        ent = self.entries.get(id(p))
+        if ent is None:
+            self.pending_small.append(p)
+            return
+        from .layers import WgradStream
+        main = torch.cuda.current_stream(self.device)
+        self.comm.wait_stream(main)
+        if WgradStream.enabled:
+            self.comm.wait_stream(WgradStream.side(self.device))           # the wgrad that produced this gradient
+        view = self.views[id(p)]
+        g = p.grad if p.grad.shape == view.shape else dense_view(p.grad)
+        staged = g.data_ptr() != view.data_ptr()                           # not produced in place (e.g. accumulated gradients)
+        with torch.cuda.stream(self.comm):
+            if staged:
+                view.copy_(g)
+            self._allreduce(ent[0], ent[1])
+            if staged:
+                g.copy_(view)
+
+    def finish(self):
+        """Call before ``optimizer.step()``: reduces the packed small gradients and joins the communication stream."""
+        main = torch.cuda.current_stream(self.device)
+        if self.pending_small:
+            smalls = self.pending_small
+            dst = [self.arena[self.small_off + self.small_slices[id(p)][0]: self.small_off + self.small_slices[id(p)][0] + p.numel()]
+                   for p in smalls]
+            src = [p.grad.reshape(-1) for p in smalls]
+            self.arena[self.small_off:self.small_off + self.small_numel].zero_()
+            torch._foreach_copy_(dst, src)
+            self.comm.wait_stream(main)
+            self._allreduce(self.small_off, self.small_numel)
+            main.wait_stream(self.comm)
+            torch._foreach_copy_(src, dst)
+            self.pending_small = []
+        else:
+            main.wait_stream(self.comm)
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks.clear()
+        from .layers import ConvParams
+        for m in self._model.modules():
+            if isinstance(m, ConvParams) and hasattr(m, "_grad_buffer"):
+                del m._grad_buffer
+
+
+def make_gradient_reducer(model, process_group=None, **kwargs):
+    """``PeerGradientReducer`` on CUDA with an NCCL group (falls back to the NCCL ``GradientReducer`` when symmetric memory cannot
+    be set up, and for CPU/gloo groups); ``W2L_REDUCER=nccl`` forces the NCCL path."""
+    want = os.environ.get("W2L_REDUCER", "peer")
+    cuda = any(p.is_cuda for p in model.parameters())
+    if want == "peer" and cuda and dist.get_backend(process_group) == "nccl":
+        try:
+            return PeerGradientReducer(model, process_group, **kwargs)
+        except Exception as e:  # noqa: BLE001
+            import warnings
+            warnings.warn("PeerGradientReducer unavailable (%r); using the NCCL GradientReducer" % (e,))
+    return GradientReducer(model, process_group)

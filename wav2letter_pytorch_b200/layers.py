@@ -66,9 +66,18 @@ def wgrad_async(side, dy, x, desc, dw):
         return F.conv1d_wgrad(dy, x, desc, dw)
     with torch.cuda.stream(side):
         F.conv1d_wgrad(dy, x, desc, dw)
-    for t in (dy, x, dw):
+    for t in (dy, x) if getattr(dw, "_w2l_arena", False) else (dy, x, dw):
         t.record_stream(side)
     return dw
+
+
+def alloc_dw(conv, device):
+    """fp32 [k_eff, Cout, cin_eff] buffer for the weight gradient: the layer's slice of the data-parallel gradient arena when a
+    ``PeerGradientReducer`` owns one (wgrad then writes where the NVLink all-reduce reads: no copy), else a fresh tensor."""
+    buf = getattr(conv, "_grad_buffer", None)
+    if buf is not None and conv.weight.grad is None and buf.device == device:
+        return buf
+    return torch.empty((conv.k_eff, conv.out_channels, conv.cin_eff), dtype=torch.float32, device=device)
 
 
 def next_dropout_seed():
@@ -353,7 +362,7 @@ class ConvBNActFn(torch.autograd.Function):
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
                                   want_g=has_res, dz_rows=dz_rows, drop_mask=mask)
-        dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
+        dw = alloc_dw(conv, z.device)
         side = WgradStream.fork(z.device)              # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
         if ctx.needs_input_grad[0]:
@@ -394,7 +403,7 @@ class ResidualBranchFn(torch.autograd.Function):
         conv = ctx.conv
         B, T, Co = z.shape
         dz, red, _ = F.bn_act_bwd(g.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, Co, 0, 0, F.ACT_NONE)
-        dw = torch.empty((conv.k_eff, Co, conv.cin_eff), dtype=torch.float32, device=z.device)
+        dw = alloc_dw(conv, z.device)
         side = WgradStream.fork(z.device)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -434,7 +443,7 @@ class ConvHeadFn(torch.autograd.Function):
         Co, cp = conv.out_channels, conv.cout_pad
         dl = F.log_softmax_bwd(dout.contiguous(), out, cp)            # bf16 [B,T,cout_pad], zero padded
         desc = conv_desc(conv, B, T, T, 0, ldy=cp)
-        dw = torch.empty((1, Co, conv.cin_eff), dtype=torch.float32, device=xin.device)
+        dw = alloc_dw(conv, xin.device)
         side = WgradStream.fork(xin.device)
         dx = None
         if ctx.needs_input_grad[0]:
