@@ -266,6 +266,23 @@ int w2l_novograd_step(float* const* params, float* const* grads, float* const* e
 int w2l_grad_allreduce(void* const* peer_data_host, void* const* peer_flags_host, void* multicast_base, int64_t offset,
                        int64_t numel, int32_t rank, int32_t world, uint32_t seq, int32_t ctas, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Feature front-end for a collated batch.  Replaces SpectrogramExtractor._get_spect / extract (data/data_loader.py:33-88)
+ * and the zero padding of _collator (data_loader.py:149-158):
+ *   x = audio + dither * noise;  y[0] = x[0], y[i] = x[i] - preemph * x[i-1];  centred STFT (reflect padding n_fft/2, hop,
+ *   `window` [win_length] centred inside n_fft), power = |X|^2, mel = mel_fb [n_mels, n_fft/2+1] @ power,
+ *   log1p(mel + log_guard), then per utterance and feature: (v - mean_t) / (std_t(unbiased) + norm_eps).
+ *   audio        [B, audio_stride] fp32, audio_lens[b] valid samples (>= 2); frames_b = 1 + audio_lens[b] / hop
+ *   dither_noise [B, audio_stride] fp32 standard-normal noise or NULL (the reference draws torch.randn on the host)
+ *   out          [B, n_mels, T_max] fp32; frames t >= frames_b are zero (the collator's padding)
+ * workspace: w2l_logmel_workspace_bytes(B, T_max, n_mels).
+ */
+size_t w2l_logmel_workspace_bytes(int32_t B, int32_t T_max, int32_t n_mels);
+int w2l_logmel_features(const float* audio, int64_t audio_stride, const float* dither_noise, const int32_t* audio_lens, int32_t B,
+                        int32_t n_fft, int32_t win_length, int32_t hop, const float* window, const float* mel_fb, int32_t n_mels,
+                        float dither, float preemph, float log_guard, float norm_eps, float* out, int32_t T_max, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

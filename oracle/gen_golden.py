@@ -258,8 +258,33 @@ def gen_novograd(ref):
     np.savez_compressed(os.path.join(OUT, "novograd.npz"), **_np(out))
 
 
+def gen_features(ref):
+    """SpectrogramExtractor.extract of the reference on seeded synthetic audio (two lengths); the dither noise it drew is
+    reproduced from the same torch seed and stored, so that consumers can feed it explicitly."""
+    from oracle.ref_loader import load_reference_features, to_attr
+    dl = load_reference_features()
+    conf = to_attr(dict(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming"))
+    ex = dl.SpectrogramExtractor(conf, mel_spec=64)
+    out = {"fb": ex.fb[0].numpy()}
+    rs = np.random.RandomState(7)
+    for name, n in (("a", 16000), ("b", 11237)):
+        t = np.arange(n) / 16000.0
+        sig = (0.3 * np.sin(2 * np.pi * (200 + 900 * t) * t) + 0.05 * rs.randn(n)).astype(np.float32)
+        torch.manual_seed(11 + n)
+        feats = ex.extract(sig)
+        torch.manual_seed(11 + n)
+        noise = torch.randn(sig.shape)
+        out[name + ":signal"], out[name + ":noise"], out[name + ":feats"] = sig, noise.numpy(), feats.numpy()
+    np.savez_compressed(os.path.join(OUT, "features.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "features":      # regenerate one fixture without touching the others
+        rl.load_reference()
+        torch.set_num_threads(1)
+        gen_features(None)
+        return
     ref = rl.load_reference()
     torch.set_num_threads(1)
     gen_decoder(ref)
@@ -269,6 +294,7 @@ def main():
     gen_jasper_dense(ref)
     gen_ctc(ref)
     gen_novograd(ref)
+    gen_features(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -112,6 +112,29 @@ def load_reference():
     return ns
 
 
+def load_reference_features():
+    """``data.data_loader`` of the reference, imported verbatim.  Extra stand-ins it needs here: ``scipy.signal.hamming`` & co
+    (moved to scipy.signal.windows in current scipy), an empty ``soundfile``, and ``librosa.filters.mel`` -- librosa is absent,
+    so the filterbank comes from the oracle's restatement of its published algorithm (the only part of the feature path whose
+    parity is therefore unpinned; everything downstream of the filter weights is the reference's own code)."""
+    import scipy.signal
+    import scipy.signal.windows as W
+    from oracle.w2l_oracle import mel_filterbank_slaney
+
+    install_stubs()
+    for n in ("hamming", "hann", "blackman", "bartlett"):
+        if not hasattr(scipy.signal, n):
+            setattr(scipy.signal, n, getattr(W, n))
+    sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))
+    filters = types.ModuleType("librosa.filters")
+    filters.mel = lambda sr, n_fft, n_mels=128, fmin=0.0, fmax=None, **kw: mel_filterbank_slaney(sr, n_fft, n_mels, fmin, fmax)
+    sys.modules["librosa"].filters = filters
+    sys.modules["librosa.filters"] = filters
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    return importlib.import_module("data.data_loader")
+
+
 def reference_model_cfg(model="wav2letter", mid_layers=None, dropout=None, labels="english_lowercase",
                         jasper_blocks=None):
     """Compose ``cfg.model`` the way Hydra would from the reference's yaml files (PyYAML only)."""

@@ -490,3 +490,63 @@ def w2l_forward_bf16emu(x, input_lengths, sd, specs, training=True):
     lp = F.log_softmax(h.transpose(1, 2), dim=-1)
     scaling = int(np.prod([s["stride"] for s in specs]))
     return lp, (None if input_lengths is None else input_lengths // scaling)
+
+
+# ------------------------------------------------------------------------------------------------ feature front-end
+def mel_filterbank_slaney(sample_rate, n_fft, n_mels, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (htk=False, norm='slaney'), the call at
+    data/data_loader.py:40-44.  librosa is NOT installed here: this restates its published algorithm (Slaney's Auditory
+    Toolbox mel scale: linear 200/3 Hz per mel below 1 kHz, log spacing ln(6.4)/27 above; triangles between neighbouring
+    centre frequencies; each filter scaled by 2 / bandwidth).  PARITY UNPINNED for the filter weights themselves."""
+    fmax = sample_rate / 2.0 if fmax is None else fmax
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        return min_log_mel + np.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    def mel_to_hz(m):
+        return min_log_hz * np.exp(logstep * (m - min_log_mel)) if m >= min_log_mel else f_sp * m
+
+    n_bins = 1 + n_fft // 2
+    freqs = [k * (sample_rate / 2.0) / (n_bins - 1) for k in range(n_bins)]
+    lo, hi = hz_to_mel(fmin), hz_to_mel(fmax)
+    centres = [mel_to_hz(lo + (hi - lo) * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    fb = np.zeros((n_mels, n_bins), dtype=np.float64)
+    for i in range(n_mels):
+        left, mid, right = centres[i], centres[i + 1], centres[i + 2]
+        for k, f in enumerate(freqs):
+            fb[i, k] = max(0.0, min((f - left) / (mid - left), (right - f) / (right - mid))) * 2.0 / (right - left)
+    return fb.astype(np.float32)
+
+
+def spectrogram_extract(signal, sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming", n_mels=64, noise=None,
+                        fb=None):
+    """SpectrogramExtractor._get_spect + extract (data/data_loader.py:64-88) on the CPU: dither with the given standard-normal
+    ``noise`` (the reference draws torch.randn(audio.shape)), pre-emphasis 0.97, torch.stft(center=True), magnitude -> power,
+    mel filterbank, log1p(. + 2^-24), per-feature (v - mean) / (std_unbiased + 1e-5).  Returns [n_mels, T] fp32."""
+    win, hop = int(sample_rate * window_size), int(sample_rate * window_stride)
+    n_fft = 2 ** int(np.ceil(np.log2(win)))
+    wfn = {"hann": torch.hann_window, "hamming": torch.hamming_window, "blackman": torch.blackman_window, "bartlett": torch.bartlett_window}[window]
+    x = torch.as_tensor(np.asarray(signal), dtype=torch.float32)
+    if noise is not None:
+        x = x + torch.as_tensor(np.asarray(noise), dtype=torch.float32) * 1e-5
+    x = torch.cat((x[0].unsqueeze(0), x[1:] - 0.97 * x[:-1]), dim=0)
+    X = torch.view_as_real(torch.stft(x, n_fft=n_fft, hop_length=hop, win_length=win, center=True,
+                                      window=wfn(win, periodic=False).float(), return_complex=True))
+    mag = torch.sqrt(X.pow(2).sum(-1))
+    power = mag.pow(2)
+    fbt = torch.as_tensor(mel_filterbank_slaney(sample_rate, n_fft, n_mels, 0.0, sample_rate / 2) if fb is None else fb, dtype=torch.float32)
+    spect = torch.log1p(torch.matmul(fbt, power) + 2 ** -24)
+    mean = spect.mean(dim=1, keepdim=True)
+    std = spect.std(dim=1, keepdim=True) + 1e-5
+    return (spect - mean) / std
+
+
+def collate_features(feats):
+    """_collator (data/data_loader.py:149-158) for the inputs: zero padding to the longest utterance + lengths."""
+    T = max(f.shape[1] for f in feats)
+    out = torch.zeros((len(feats), feats[0].shape[0], T), dtype=torch.float32)
+    for i, f in enumerate(feats):
+        out[i, :, :f.shape[1]] = f
+    return out, torch.tensor([f.shape[1] for f in feats], dtype=torch.int32)

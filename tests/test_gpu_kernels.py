@@ -448,3 +448,34 @@ def test_depthwise_conv(F, B, T, C, k, s, d):
     if s == 1:
         dx = F.depthwise_dgrad(dyc, ws, T, k, d, p, lens.cuda())
         assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------- feature front-end
+def test_features_golden_and_ragged_batch(golden):
+    """GPU front-end vs the reference's SpectrogramExtractor (golden, same dither noise) and vs the oracle on a ragged batch"""
+    from wav2letter_pytorch_b200.features import SpectrogramExtractor
+    conf = dict(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming")
+    ex = SpectrogramExtractor(conf, mel_spec=64).cuda()
+    g = golden("features")
+    assert np.allclose(ex.fb[0].cpu().numpy(), g["fb"], atol=1e-7)
+    for name in ("a", "b"):
+        got = ex.extract(g[name + ":signal"], noise=g[name + ":noise"]).cpu().numpy()
+        want = g[name + ":feats"]
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 2e-4, (name, np.abs(got - want).max())     # fp32 FFT / matmul summation order
+    # ragged batch: per-utterance reflect padding at each utterance's own end, zero padding past its last frame
+    rs = np.random.RandomState(3)
+    sigs = [(0.2 * rs.randn(n)).astype(np.float32) for n in (24000, 8011, 16000, 400)]
+    noise = torch.randn(len(sigs), 24000, generator=torch.Generator().manual_seed(5))
+    out, lens = ex.extract_batch(sigs, noise=noise)
+    want, want_lens = O.collate_features([O.spectrogram_extract(s, noise=noise[i, :len(s)].numpy()) for i, s in enumerate(sigs)])
+    assert lens.cpu().tolist() == want_lens.tolist() == [151, 51, 101, 3]
+    assert out.shape == want.shape
+    assert (out.cpu() - want).abs().max() < 2e-4
+    for i, n in enumerate(lens.cpu().tolist()):
+        assert (out[i, :, n:] == 0).all()
+    # without explicit noise the dither is drawn on the device: same features to within the dither's effect
+    out2, _ = ex.extract_batch(sigs)
+    assert (out2 - out).abs().max() < 0.2
+    with pytest.raises(RuntimeError):
+        ex.extract(np.zeros(200, dtype=np.float32))

@@ -212,3 +212,25 @@ def test_gradient_reducer_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "rank %d ok" % r in o, o
+
+
+def test_mel_filterbank_matches_oracle_restatement():
+    """two independent restatements of librosa.filters.mel (vectorised in the package, scalar loops in the oracle)"""
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200.features import mel_filterbank
+    for sr, n_fft, n_mels in ((16000, 512, 64), (8000, 256, 40), (22050, 2048, 128)):
+        a, b = mel_filterbank(sr, n_fft, n_mels, 0.0, sr / 2), O.mel_filterbank_slaney(sr, n_fft, n_mels, 0.0, sr / 2)
+        assert a.shape == (n_mels, n_fft // 2 + 1) and a.dtype == np.float32
+        assert np.allclose(a, b, rtol=0, atol=1e-7)
+        assert (a >= 0).all() and (a.sum(1) > 0).all()          # every filter has support
+
+
+def test_spectrogram_extractor_needs_cuda():
+    import torch
+    from wav2letter_pytorch_b200.features import SpectrogramExtractor
+    ex = SpectrogramExtractor(dict(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming"), mel_spec=64)
+    assert ex.n_fft == 512 and ex.win_length == 320 and ex.hop_length == 160 and ex.fb.shape == (1, 64, 257)
+    assert ex.n_frames(16000) == 101
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            ex.extract(np.zeros(16000, dtype=np.float32))
