@@ -267,6 +267,25 @@ int w2l_grad_allreduce(void* const* peer_data_host, void* const* peer_flags_host
                        int64_t numel, int32_t rank, int32_t world, uint32_t seq, int32_t ctas, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * CTC prefix beam search on the HOST.  Replaces prefix_beam_search / PrefixBeamSearchLMDecoder.decode (decoder.py:147-267).
+ *   probs_host   [n_utt, T_max, F] float64 probabilities (>= 0); frames_host[u] frames are used (NULL: T_max)
+ *   blank        index of the blank label; space_id / end_id: index of ' ' / the end character ('>') or -1 if not a label
+ *   is_word_host / is_term_host [F]: label matches the regex class \w / [\s|>] (the reference counts words with
+ *                r'\w+[\s|>]' for the (words+1)**beta prior)
+ *   k, alpha, beta, prune: beam width, LM weight, word-count exponent, per-frame emission threshold
+ *   lm           optional language-model callback (label ids of the stripped prefix -> probability), or NULL (== 1)
+ *   out_ids_host [n_utt, out_stride] int32 best prefix per utterance, out_len_host [n_utt] its length,
+ *   out_score_host [n_utt] (optional) A_next[best] * (words+1)**beta of the last frame
+ * Same float64 arithmetic, candidate order and tie-breaking as the reference: identical transcripts.
+ */
+typedef double (*w2l_lm_callback)(const int32_t* ids, int64_t n, void* user);
+int w2l_prefix_beam_search_host(const double* probs_host, const int64_t* frames_host, int64_t n_utt, int64_t T_max, int64_t F,
+                                int32_t blank, int32_t space_id, int32_t end_id, const uint8_t* is_word_host,
+                                const uint8_t* is_term_host, int32_t k, double alpha, double beta, double prune,
+                                w2l_lm_callback lm, void* lm_user, int32_t* out_ids_host, int64_t out_stride,
+                                int64_t* out_len_host, double* out_score_host, int32_t threads);
+
+/* ---------------------------------------------------------------------------------------------
  * Feature front-end for a collated batch.  Replaces SpectrogramExtractor._get_spect / extract (data/data_loader.py:33-88)
  * and the zero padding of _collator (data_loader.py:149-158):
  *   x = audio + dither * noise;  y[0] = x[0], y[i] = x[i] - preemph * x[i-1];  centred STFT (reflect padding n_fft/2, hop,

@@ -278,12 +278,33 @@ def gen_features(ref):
     np.savez_compressed(os.path.join(OUT, "features.npz"), **out)
 
 
+def gen_beam(ref):
+    """prefix_beam_search of the reference (decoder.py:147-231) on seeded random posteriors: string and score."""
+    labels = list(ref.label_sets.labels_map["english_lowercase"])
+    rs = np.random.RandomState(21)
+    out = {"labels": np.array(labels)}
+    cases = [("sharp", 40, 4.0, 5, 5, 1e-3, False), ("flat", 25, 0.5, 20, 5, 1e-3, False), ("k1", 30, 2.0, 1, 5, 1e-3, False),
+             ("beta0", 30, 2.0, 5, 0, 0.0, False), ("betaf", 30, 2.0, 5, 2.5, 0.05, False), ("f32", 35, 3.0, 5, 5, 1e-3, True),
+             ("lm", 30, 3.0, 5, 5, 1e-3, False)]
+    for name, T, temp, k, beta, prune, f32 in cases:
+        x = rs.randn(T, len(labels)) * temp
+        x[:, 28] += 1.0
+        p = np.exp(x) / np.exp(x).sum(1, keepdims=True)
+        if f32:
+            p = p.astype(np.float32)
+        lm = (lambda s: 1.0 / (1.0 + len(s))) if name == "lm" else None
+        string, score = ref.decoder.prefix_beam_search(p, labels, 0, lm, k, 0.3, beta, prune, return_weights=True)
+        out[name + ":probs"], out[name + ":params"] = p, np.array([k, beta, prune], dtype=np.float64)
+        out[name + ":string"], out[name + ":score"] = np.array(string), np.float64(score)
+    np.savez_compressed(os.path.join(OUT, "beam.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "features":      # regenerate one fixture without touching the others
-        rl.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam"):      # regenerate one fixture without touching the others
+        ref = rl.load_reference()
         torch.set_num_threads(1)
-        gen_features(None)
+        {"features": gen_features, "beam": gen_beam}[sys.argv[1]](ref)
         return
     ref = rl.load_reference()
     torch.set_num_threads(1)
@@ -295,6 +316,7 @@ def main():
     gen_ctc(ref)
     gen_novograd(ref)
     gen_features(ref)
+    gen_beam(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

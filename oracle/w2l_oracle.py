@@ -550,3 +550,64 @@ def collate_features(feats):
     for i, f in enumerate(feats):
         out[i, :, :f.shape[1]] = f
     return out, torch.tensor([f.shape[1] for f in feats], dtype=torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------ prefix beam search
+def prefix_beam_search(ctc, labels, blank_index=0, lm=None, k=5, alpha=0.3, beta=5, prune=0.001, end_char=">"):
+    """decoder.py:147-231 restated with plain dicts (small cases only: pure Python).  Returns (best prefix, its score).
+    Kept faithful where it matters for exact agreement: float64 arithmetic in the reference's association order (the reference
+    vstack()s a float64 zero frame in front, which promotes any input to float64), Counter semantics (missing key = 0, `+=`
+    inserts, Counter addition keeps Pb's keys first and drops non-positive sums), stable descending sort, and the word-count
+    prior (len(re.findall(r'\\w+[\\s|>]', l)) + 1) ** beta."""
+    import re
+    ctc = np.asarray(ctc, dtype=np.float64)
+    T, F = ctc.shape
+    lm = (lambda l: 1) if lm is None else lm
+    words = lambda l: len(re.findall(r"\w+[\s|>]", l))
+    blank_char = labels[blank_index]
+    pb_prev, pnb_prev, beam = {"": 1}, {"": 0}, [""]
+    best_score = 0.0
+    for t in range(T):
+        row = ctc[t]
+        alphabet = [labels[i] for i in range(F) if row[i] > prune]
+        pb, pnb = {}, {}
+
+        def add(d, key, v):
+            d[key] = d.get(key, 0) + v
+        for l in beam:
+            if len(l) > 0 and l[-1] == end_char:
+                pb[l] = pb_prev.get(l, 0)
+                pnb[l] = pnb_prev.get(l, 0)
+                continue
+            for c in alphabet:
+                ci = labels.index(c)
+                if c == blank_char:
+                    add(pb, l, row[blank_index] * (pb_prev.get(l, 0) + pnb_prev.get(l, 0)))
+                    continue
+                lp = l + c
+                if len(l) > 0 and c == l[-1]:
+                    add(pnb, lp, row[ci] * pb_prev.get(l, 0))
+                    add(pnb, l, row[ci] * pnb_prev.get(l, 0))
+                elif len(l.replace(" ", "")) > 0 and c in (" ", end_char):
+                    lm_prob = lm(lp.strip(" " + end_char)) ** alpha
+                    add(pnb, lp, lm_prob * row[ci] * (pb_prev.get(l, 0) + pnb_prev.get(l, 0)))
+                else:
+                    add(pnb, lp, row[ci] * (pb_prev.get(l, 0) + pnb_prev.get(l, 0)))
+                if lp not in beam:
+                    add(pb, lp, row[blank_index] * (pb_prev.get(lp, 0) + pnb_prev.get(lp, 0)))
+                    add(pnb, lp, row[ci] * pnb_prev.get(lp, 0))
+        nxt = {}
+        for key, v in pb.items():
+            s = v + pnb.get(key, 0)
+            if s > 0:
+                nxt[key] = s
+        for key, v in pnb.items():
+            if key not in pb and v > 0:
+                nxt[key] = v
+        score = lambda l: nxt[l] * (words(l) + 1) ** beta
+        beam = sorted(nxt, key=score, reverse=True)[:k]
+        best_score = score(beam[0]) if beam else 0.0
+        pb_prev, pnb_prev = pb, pnb
+    if not beam:
+        beam = [""]
+    return beam[0], float(best_score)

@@ -234,3 +234,48 @@ def test_spectrogram_extractor_needs_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             ex.extract(np.zeros(16000, dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- prefix beam search (host routine)
+@pytest.mark.parametrize("name", ["sharp", "flat", "k1", "beta0", "betaf", "f32", "lm"])
+def test_beam_search_library_golden(golden, name):
+    """library routine vs the reference's own outputs: identical transcript AND identical float64 score"""
+    from wav2letter_pytorch_b200.decoder import prefix_beam_search
+    g = golden("beam")
+    labels = [str(s) for s in g["labels"]]
+    k, beta, prune = g[name + ":params"]
+    beta = int(beta) if float(beta).is_integer() else float(beta)
+    lm = (lambda s: 1.0 / (1.0 + len(s))) if name == "lm" else None
+    string, score = prefix_beam_search(g[name + ":probs"], labels, 0, lm, int(k), 0.3, beta, float(prune), return_weights=True)
+    assert string == str(g[name + ":string"])
+    assert score == float(g[name + ":score"])
+
+
+def test_beam_search_library_vs_oracle_random():
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200.decoder import PrefixBeamSearchLMDecoder, prefix_beam_search
+    rs = np.random.RandomState(5)
+    labels = ["_", "'", "a", "b", "c", " ", ">"]                      # includes the end character: prefixes that end are frozen
+    batch = []
+    for trial in range(25):
+        T = int(rs.randint(2, 40))
+        x = rs.randn(T, len(labels)) * rs.choice([0.7, 2.0, 4.0])
+        p = np.exp(x) / np.exp(x).sum(1, keepdims=True)
+        k, beta, prune = int(rs.choice([1, 2, 5, 12])), rs.choice([5, 1, 0.5]), float(rs.choice([1e-3, 0.1, 0.0]))
+        beta = int(beta) if float(beta).is_integer() else float(beta)
+        lm = (lambda s: 0.5 + 0.1 * (len(s) % 3)) if trial % 5 == 0 else None
+        want = O.prefix_beam_search(p, labels, 0, lm, k, 0.3, beta, prune)
+        got = prefix_beam_search(p, labels, 0, lm, k, 0.3, beta, prune, return_weights=True)
+        assert got[0] == want[0] and got[1] == want[1], (trial, got, want)
+        if T == 17 or len(batch) < 3:
+            batch.append(p)
+    # batch through the Decoder interface (threads inside the library): same strings as utterance by utterance
+    T = min(b.shape[0] for b in batch)
+    probs = np.stack([b[:T] for b in batch])
+    dec = PrefixBeamSearchLMDecoder(None, labels, blank_index=0, k=4, alpha=0.3, beta=5, prune=1e-3)
+    assert dec.decode(probs) == [O.prefix_beam_search(b, labels, 0, None, 4, 0.3, 5, 1e-3)[0] for b in probs]
+    assert dec.decode(torch.from_numpy(probs[0]).float()) == O.prefix_beam_search(probs[0].astype(np.float32), labels, 0, None, 4, 0.3, 5, 1e-3)[0]
+    with pytest.raises(NotImplementedError):
+        dec.decode(probs, return_offsets=True)
+    with pytest.raises(AssertionError):
+        prefix_beam_search(-probs[0], labels)

@@ -11,7 +11,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libw2l_sm100.so")
-SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu", "metrics.cu", "depthwise.cu", "comm.cu", "features.cu"]
+SOURCES = ["runtime.cu", "decode.cu", "ctc.cu", "conv_gemm.cu", "elementwise.cu", "novograd.cu", "metrics.cu", "depthwise.cu", "comm.cu", "features.cu", "beam_search.cu"]
 _lock = threading.Lock()
 _lib = None
 
@@ -109,6 +109,8 @@ SIGNATURES = {
     "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_cast_bf16": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
+    "w2l_prefix_beam_search_host": (c_i32, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_i32, ctypes.c_double,
+                                            ctypes.c_double, ctypes.c_double, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32]),
     "w2l_logmel_workspace_bytes": (c_size, [c_i32, c_i32, c_i32]),
     "w2l_logmel_features": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_i32, c_f32, c_f32, c_f32, c_f32,
                                     c_ptr, c_i32, c_ptr, c_size, c_ptr]),

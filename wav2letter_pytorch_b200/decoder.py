@@ -188,3 +188,85 @@ class GreedyDecoder(Decoder):
         if return_offsets:
             return strings, offs
         return strings
+
+
+# ------------------------------------------------------------------------------------------------ prefix beam search
+_LM_CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_int32), ctypes.c_int64, ctypes.c_void_p)
+
+
+def _beam_search_batch(probs, frames, labels, blank_index, lm, k, alpha, beta, prune, end_char, threads=0):
+    """probs [N, T, F] float64 numpy (C-contiguous), frames [N] or None -> (list[str], list[float])."""
+    import re
+    if any(len(l) != 1 for l in labels):
+        raise NotImplementedError("prefix beam search: multi-character labels are not supported")
+    N, T, F_ = probs.shape
+    word = np.array([1 if re.fullmatch(r"\w", c) else 0 for c in labels], dtype=np.uint8)
+    term = np.array([1 if re.fullmatch(r"[\s|>]", c) else 0 for c in labels], dtype=np.uint8)
+    space_id = labels.index(" ") if " " in labels else -1
+    end_id = labels.index(end_char) if end_char in labels else -1
+    out_ids = np.zeros((N, max(T, 1)), dtype=np.int32)
+    out_len = np.zeros(N, dtype=np.int64)
+    out_score = np.zeros(N, dtype=np.float64)
+    fr = None if frames is None else np.ascontiguousarray(frames, dtype=np.int64)
+    cb = ctypes.cast(None, _LM_CB)
+    if lm is not None:
+        def _call(ids, n, _user):
+            return float(lm("".join(labels[ids[i]] for i in range(n))))
+        cb = _LM_CB(_call)
+    P = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    rc = _lib.load().w2l_prefix_beam_search_host(P(probs), P(fr), N, T, F_, blank_index, space_id, end_id, P(word), P(term), int(k),
+                                                float(alpha), float(beta), float(prune), ctypes.cast(cb, ctypes.c_void_p), None,
+                                                P(out_ids), out_ids.shape[1], P(out_len), P(out_score), threads)
+    if rc != 0:
+        raise RuntimeError("w2l_prefix_beam_search_host failed (code %d)" % rc)
+    strings = ["".join(labels[i] for i in out_ids[n, :out_len[n]]) for n in range(N)]
+    return strings, out_score.tolist()
+
+
+def prefix_beam_search(ctc, labels, blank_index=0, lm=None, k=5, alpha=0.3, beta=5, prune=0.001, end_char=">", return_weights=False):
+    """Drop-in for the reference function (decoder.py:147-231): ``ctc`` [T, F] probabilities -> best prefix (and its score).
+    Same float64 arithmetic, candidate order and tie-breaking, run by the library's host routine."""
+    if torch.is_tensor(ctc):
+        ctc = ctc.detach().cpu().numpy()
+    ctc = np.asarray(ctc)
+    assert (ctc.shape[1] == len(labels)), "ctc size:%d, labels: %d" % (ctc.shape[1], len(labels))
+    assert ctc.shape[0] > 1, "ctc length: %d was too short" % ctc.shape[0]
+    assert (ctc >= 0).all(), "ctc output contains negative numbers"
+    probs = np.ascontiguousarray(ctc, dtype=np.float64)[None]
+    strings, scores = _beam_search_batch(probs, None, list(labels), blank_index, lm, k, alpha, beta, prune, end_char)
+    if return_weights:
+        return strings[0], scores[0]
+    return strings[0]
+
+
+class PrefixBeamSearchLMDecoder(Decoder):
+    """decoder.py:233-267: same constructor and ``decode``; a batch is decoded by ONE library call spread over host threads
+    (the reference loops over utterances in Python)."""
+
+    def __init__(self, lm_path, labels, blank_index=0, k=5, alpha=0.3, beta=5, prune=1e-3):
+        super(PrefixBeamSearchLMDecoder, self).__init__(labels, blank_index)
+        if lm_path:
+            import kenlm                                   # same optional dependency as the reference
+            self.lm = kenlm.Model(lm_path)
+            self.lm_weigh = lambda f: 10 ** (self.lm.score(f))
+        else:
+            self.lm_weigh = None                           # the reference's `lambda s: 1`: no callback needed
+        self.k, self.alpha, self.beta, self.prune = k, alpha, beta, prune
+
+    def decode(self, probs, sizes=None, return_offsets=False):
+        if return_offsets:
+            raise NotImplementedError("Prefix beam search does not support offsets (yet).")
+        if torch.is_tensor(probs):
+            probs = probs.detach().float().cpu().numpy()
+        probs = np.asarray(probs)
+        if len(probs.shape) == 2:
+            return prefix_beam_search(probs, self.labels, self.blank_index, self.lm_weigh, self.k, self.alpha, self.beta, self.prune)
+        if len(probs.shape) == 3:
+            assert probs.shape[2] == len(self.labels), "ctc size:%d, labels: %d" % (probs.shape[2], len(self.labels))
+            assert probs.shape[1] > 1, "ctc length: %d was too short" % probs.shape[1]
+            assert (probs >= 0).all(), "ctc output contains negative numbers"
+            # NB the reference ignores `sizes` here (every utterance is decoded over all T frames); so does this class
+            strings, _ = _beam_search_batch(np.ascontiguousarray(probs, dtype=np.float64), None, list(self.labels), self.blank_index,
+                                            self.lm_weigh, self.k, self.alpha, self.beta, self.prune, ">")
+            return strings
+        raise RuntimeError("Decoding with wrong shape: %s, expected either [Batch X Frames X Labels] or [Frames X Labels]" % str(probs.shape))
