@@ -244,6 +244,9 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    global BATCH
+    if args.strong:                                      # strong scaling: the global batch stays 64, every rank takes 64 / world
+        BATCH = max(1, BATCH // world)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
@@ -387,7 +390,7 @@ def run_gpu_arm(args):
     value = world * BATCH * UTT_SEC / (ms / 1e3)
     line = {
         "metric": "audio-sec/sec per train step", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": ("Wav2Letter mid_layers=%d (full layers: list of the default yaml)" % args.mid_layers if args.model == "wav2letter"
                                 else {"jasper10x5": "Jasper 10x5 (dense, configuration/model/jasper10x5.yaml)",
@@ -447,6 +450,7 @@ def main():
     ap.add_argument("--model", default="wav2letter", choices=["wav2letter", "jasper10x5", "jasper"],
                     help="wav2letter = BASELINE config 2 (headline); jasper10x5 = config 3; jasper = the shipped separable yaml")
     ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4, help="utterances in the bounded CPU sample")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: global batch 64 split over the ranks (default: weak, 64 per GPU)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-default", action="store_true")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: no warm-up floor, no e2e/default/CPU passes")

@@ -267,3 +267,44 @@ def test_jasper_dense_golden(pkg, golden, fixture):
     with torch.no_grad():
         o, ol = model(x, il)
     assert rel_l2(o, g["eval:out"]) < 2e-2 and abs(float(o.sum(-1).mean()) - 1.0) < 1e-5    # probabilities in eval
+
+
+@pytest.mark.parametrize("mid_layers", [1, 20])
+def test_baseline_config1_forward_ctc_decode(pkg, mid_layers):
+    """BASELINE.json configs[0]: Wav2Letter default config, forward + CTCLoss + greedy decode, batch 8, synthetic 10 s utterances
+    (T=1001 frames -> T'=500), English labels -- the CUDA path against the CPU oracle (fp32 torch) on the same weights and batch.
+    Stated tolerances: log-probs rel-L2 <= 1e-2 for the literal default (mid_layers=1) and <= 3e-2 through the 20-block stack
+    (bf16 operands / bf16-stored activations, fp32 accumulation); CTC loss <= 1e-4 relative on identical log-probs; transcripts
+    and offsets bit-exact on identical scores."""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers]).model
+    torch.manual_seed(3)
+    model = Wav2Letter(cfg)
+    # give the BatchNorm buffers non-trivial values, as after training
+    g = torch.Generator().manual_seed(4)
+    for n, b in model.named_buffers():
+        if n.endswith("running_mean"):
+            b.copy_(0.1 * torch.randn(b.shape, generator=g))
+        if n.endswith("running_var"):
+            b.copy_(0.5 + torch.rand(b.shape, generator=g))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.cuda().eval()
+    x, il, tg, tl = O.synthetic_batch(8, 10, seed=2, ragged=True)
+    assert x.shape == (8, 64, 1001)
+    with torch.no_grad():
+        out, ol = model(x.cuda(), il.cuda())
+    specs = O.w2l_layer_specs(mid_layers)
+    ref, ref_ol = O.w2l_forward(x, il, sd, specs, training=False)
+    assert out.shape == ref.shape == (8, 500, 29) and np.array_equal(ol.cpu().numpy(), ref_ol.numpy())
+    assert rel_l2(out, ref) < (1e-2 if mid_layers == 1 else 3e-2), rel_l2(out, ref)
+    # CTC loss of the reference's criterion vs ours on IDENTICAL log-probs
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)
+    want = crit(out.detach().cpu().transpose(0, 1), tg, ol.cpu(), tl)
+    got = model.criterion(out.transpose(0, 1), tg.cuda(), ol, tl.cuda())
+    assert abs(got.item() - want.item()) <= 1e-4 * abs(want.item()), (got.item(), want.item())
+    # greedy transcripts on identical scores: the reference's per-frame loop (oracle) vs the CUDA argmax+collapse
+    hyp, offs = model.ctc_decoder.decode(out, ol, return_offsets=True)
+    ref_hyp, ref_offs = O.greedy_decode(out.cpu().numpy(), ol.cpu().numpy())
+    assert hyp == ref_hyp
+    assert [o[0].tolist() for o in offs] == [list(o) for o in ref_offs]
