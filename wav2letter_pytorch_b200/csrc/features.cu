@@ -41,6 +41,7 @@ logmel_kernel(const float* __restrict__ audio, int64_t audio_stride, const float
   float2* s_tw = reinterpret_cast<float2*>(s_fb + n_mels * fb_pitch + ((n_mels * fb_pitch) & 1));   // [n_fft/2] twiddles
   float* s_win = reinterpret_cast<float*>(s_tw + n_fft / 2);      // [win_length]
   float2* s_buf = reinterpret_cast<float2*>(s_win + win_length + (win_length & 1));                  // [warps][n_fft]
+  int* s_rng = reinterpret_cast<int*>(s_buf + kFeatWarps * n_fft);                                   // [n_mels][2] support of each filter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < n_mels * n_bins; i += blockDim.x) {
     const int f = i / n_bins, k = i - f * n_bins;
@@ -52,6 +53,19 @@ logmel_kernel(const float* __restrict__ audio, int64_t audio_stride, const float
     s_tw[i] = make_float2(c, s);
   }
   for (int i = tid; i < win_length; i += blockDim.x) s_win[i] = window[i];
+  __syncthreads();
+  // the filters are narrow triangles: find each one's support once, the dot products below only walk [lo, hi)
+  for (int f = tid; f < n_mels; f += blockDim.x) {
+    const float* row = s_fb + f * fb_pitch;
+    int lo = n_bins, hi = 0;
+    for (int k = 0; k < n_bins; ++k)
+      if (row[k] != 0.f) {
+        lo = min(lo, k);
+        hi = k + 1;
+      }
+    s_rng[2 * f] = lo;
+    s_rng[2 * f + 1] = hi;
+  }
   __syncthreads();
 
   const int b = blockIdx.y;
@@ -101,7 +115,7 @@ logmel_kernel(const float* __restrict__ audio, int64_t audio_stride, const float
     for (int f = lane; f < n_mels; f += 32) {
       const float* row = s_fb + f * fb_pitch;
       float acc = 0.f;
-      for (int k = 0; k < n_bins; ++k) acc = fmaf(row[k], buf[k].x, acc);
+      for (int k = s_rng[2 * f]; k < s_rng[2 * f + 1]; ++k) acc = fmaf(row[k], buf[k].x, acc);
       out[f] = log1pf(acc + log_guard);                           // np.log1p(spect + 2**-24), data_loader.py:79
     }
     __syncwarp();
@@ -177,7 +191,7 @@ int w2l_logmel_features(const float* audio, int64_t audio_stride, const float* d
   while ((1 << log2_fft) < n_fft) ++log2_fft;
   const int n_bins = n_fft / 2 + 1, fb_pitch = n_bins | 1;
   size_t smem = (size_t)(n_mels * fb_pitch + ((n_mels * fb_pitch) & 1)) * 4 + (size_t)(n_fft / 2) * 8 + (size_t)(win_length + (win_length & 1)) * 4 +
-                (size_t)kFeatWarps * n_fft * 8;
+                (size_t)kFeatWarps * n_fft * 8 + (size_t)n_mels * 8;
   W2L_REQUIRE(smem <= 200 * 1024, "logmel_features: n_mels=%d x n_fft=%d needs %zu bytes of shared memory", n_mels, n_fft, smem);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
