@@ -348,7 +348,8 @@ def run_gpu_arm(args):
     ms = timed(model, opt, reducer, args.steps, 0, False)
     new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0    # cudaMalloc calls inside the timed region
     clocks = sampler.stop() if rank == 0 else None
-    launches = (_lib.launch_count() - launches0) // max(args.steps, 1)
+    launches_total = _lib.launch_count() - launches0
+    launches = launches_total // max(args.steps, 1)
     timer.unwrap()
     all_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     conv_ms = {k: v for k, v in all_ms.items() if k.startswith("conv1d")}
@@ -401,7 +402,7 @@ def run_gpu_arm(args):
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "step_ms_min_median_max": {"value": step_spread[0], "e2e": step_spread[2] if len(step_spread) > 2 else None},
         "cuda_mallocs_in_timed_region": int(new_segments),
         "clocks": clocks,
