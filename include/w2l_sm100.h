@@ -227,8 +227,10 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
                          uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream);
 
 /* logits [rows, ld] fp32 -> log_softmax / softmax over the first C columns -> out [rows, C] fp32
- * (wav2letter.py:87, jasper.py:470-473).  mode 0 = log_softmax, 1 = softmax. */
-int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, void* stream);
+ * (wav2letter.py:87, jasper.py:470-473).  mode 0 = log_softmax, 1 = softmax.  nan_flag (nullable, device int32, zeroed
+ * by the caller) is OR-ed with 1 when an output is NaN: the device half of Jasper's `assert not NaN` (jasper.py:474). */
+int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, int32_t* nan_flag,
+                    void* stream);
 /* d logits = g - exp(lp) * sum_c g  (log_softmax backward), scaled by *gscale (device scalar, nullable),
  * written as bf16 into [rows, ld_out] with zero padding in columns >= C. */
 int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out,
@@ -248,7 +250,7 @@ int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
  */
 int32_t w2l_novograd_chunk(void);
 int w2l_novograd_step(float* const* params, float* const* grads, float* const* exp_avg, float* exp_avg_sq /*[n]*/,
-                      void* const* shadow_bf16 /* nullable entries */, const int64_t* numel, const int32_t* chunk_prefix,
+                      float* max_exp_avg_sq /*[n] or NULL: amsgrad=True*/, void* const* shadow_bf16 /* nullable entries */, const int64_t* numel, const int32_t* chunk_prefix,
                       int32_t n_tensors, int32_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                       int32_t grad_averaging, float* norms_ws /*[n] scratch*/, void* stream);
 

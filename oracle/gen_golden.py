@@ -255,6 +255,17 @@ def gen_novograd(ref):
             opt.step()
             for i, q in enumerate(p):
                 out["p%d:%d" % (step + 1, i)] = q.detach().clone()
+    # amsgrad=True variant with gradients that shrink, so that the running maximum differs from the moving average
+    q = [torch.nn.Parameter(out["p0:0"].clone()), torch.nn.Parameter(out["p0:1"].clone())]
+    opt = ref.novograd.Novograd(q, lr=0.01, betas=(0.95, 0.5), weight_decay=1e-3, amsgrad=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(3):
+            for i, t in enumerate(q):
+                t.grad = out["g%d:%d" % (step, i)].clone() * (0.5 ** step)
+            opt.step()
+            for i, t in enumerate(q):
+                out["ams_p%d:%d" % (step + 1, i)] = t.detach().clone()
     np.savez_compressed(os.path.join(OUT, "novograd.npz"), **_np(out))
 
 
@@ -301,10 +312,10 @@ def gen_beam(ref):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam"):      # regenerate one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd"):      # regenerate one fixture without touching the others
         ref = rl.load_reference()
         torch.set_num_threads(1)
-        {"features": gen_features, "beam": gen_beam}[sys.argv[1]](ref)
+        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd}[sys.argv[1]](ref)
         return
     ref = rl.load_reference()
     torch.set_num_threads(1)

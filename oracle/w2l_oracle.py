@@ -383,7 +383,7 @@ def greedy_decode(probs, sizes=None, labels=ENGLISH_LOWERCASE, blank=0):
 # Novograd (novograd.py:52-114), betas=(0.95, 0) default, no amsgrad
 # --------------------------------------------------------------------------------------------
 def novograd_step(params, grads, state, lr=1e-3, betas=(0.95, 0.0), eps=1e-8, weight_decay=0.0,
-                  grad_averaging=False):
+                  grad_averaging=False, amsgrad=False):
     """In-place on ``params`` (list of tensors); ``state`` is a list of dicts carried across steps."""
     b1, b2 = betas
     for p, g, st in zip(params, grads, state):
@@ -395,7 +395,11 @@ def novograd_step(params, grads, state, lr=1e-3, betas=(0.95, 0.0), eps=1e-8, we
             st["exp_avg_sq"] = norm.clone()
         else:
             st["exp_avg_sq"] = st["exp_avg_sq"] * b2 + (1 - b2) * norm
-        g = g / (st["exp_avg_sq"].sqrt() + eps)
+        second = st["exp_avg_sq"]
+        if amsgrad:                                   # novograd.py:98-102: running maximum of the second moment
+            st["max_exp_avg_sq"] = torch.maximum(st.get("max_exp_avg_sq", torch.zeros((), dtype=p.dtype)), second)
+            second = st["max_exp_avg_sq"]
+        g = g / (second.sqrt() + eps)
         if weight_decay != 0:
             g = g + weight_decay * p
         if grad_averaging:

@@ -182,6 +182,16 @@ def test_novograd_golden(pkg, golden):
         for i, q in enumerate(p):
             np.testing.assert_allclose(q.detach().cpu().numpy(), g["p%d:%d" % (step + 1, i)], rtol=1e-5, atol=1e-6)
     assert opt.state[p[0]]["exp_avg_sq"].dim() == 0 and opt.state[p[0]]["step"] == 3
+    # amsgrad=True (novograd.py:98-102)
+    p = [torch.nn.Parameter(torch.from_numpy(g["p0:0"]).cuda()), torch.nn.Parameter(torch.from_numpy(g["p0:1"]).cuda())]
+    opt = Novograd(p, lr=0.01, betas=(0.95, 0.5), weight_decay=1e-3, amsgrad=True)
+    for step in range(3):
+        for i, q in enumerate(p):
+            q.grad = torch.from_numpy(g["g%d:%d" % (step, i)]).cuda() * (0.5 ** step)
+        opt.step()
+        for i, q in enumerate(p):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), g["ams_p%d:%d" % (step + 1, i)], rtol=1e-5, atol=1e-6)
+    assert float(opt.state[p[0]]["max_exp_avg_sq"]) >= float(opt.state[p[0]]["exp_avg_sq"])
 
 
 def test_training_step_end_to_end(pkg):
@@ -308,3 +318,30 @@ def test_baseline_config1_forward_ctc_decode(pkg, mid_layers):
     ref_hyp, ref_offs = O.greedy_decode(out.cpu().numpy(), ol.cpu().numpy())
     assert hyp == ref_hyp
     assert [o[0].tolist() for o in offs] == [list(o) for o in ref_offs]
+
+
+def test_jasper_nan_assert(pkg, golden):
+    """jasper.py:474 `assert not (jasper_res != jasper_res).any()`: AssertionError on NaN scores, in each of the three modes"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    g = golden("jasper_dense")
+    blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=5"]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    torch.manual_seed(4)
+    model = Jasper(cfg).cuda().eval()
+    x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
+    with torch.no_grad():
+        model(x, il)                                         # clean input: no assertion
+        bad = x.clone()
+        bad[0, 3, 5] = float("nan")
+        with pytest.raises(AssertionError):
+            model(bad, il)                                   # default: checked at once, like the reference
+        model.nan_check = "deferred"
+        model(bad, il)                                       # no sync here ...
+        with pytest.raises(AssertionError):
+            model.check_nan()                                # ... raised when the flag is looked at
+        model(x, il)
+        model.check_nan()
+        model.nan_check = "off"
+        model(bad, il)

@@ -105,7 +105,7 @@ SIGNATURES = {
     "w2l_reflect_halo": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_bn_act_bwd_reduce": (c_i32, [c_ptr] * 10 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
     "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 12 + [c_i32, c_ptr] + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
-    "w2l_log_softmax": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr]),
+    "w2l_log_softmax": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_cast_bf16": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr]),
@@ -116,7 +116,7 @@ SIGNATURES = {
                                     c_ptr, c_i32, c_ptr, c_size, c_ptr]),
     "w2l_grad_allreduce": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i32, c_i32, ctypes.c_uint32, c_i32, c_ptr]),
     "w2l_novograd_chunk": (c_i32, []),
-    "w2l_novograd_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32,
+    "w2l_novograd_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32,
                                   c_i32, c_ptr, c_ptr]),
 }
 

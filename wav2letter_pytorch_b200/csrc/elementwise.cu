@@ -281,10 +281,14 @@ __device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&s
 
 // activation as a compile-time switch: the per-element code is straight-line (a runtime `act` costs a compare+branch per
 // element; profiles/ shows these kernels were instruction-issue bound before this)
+// NaN passes through, as torch.relu / torch.clamp do (fmaxf / fminf would swallow it): compare-and-select, not min/max
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float v) {
-  if (ACT == W2L_ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == W2L_ACT_CLAMP20) return fminf(fmaxf(v, 0.f), 20.f);
+  if (ACT == W2L_ACT_RELU) return v < 0.f ? 0.f : v;
+  if (ACT == W2L_ACT_CLAMP20) {
+    const float t = v < 0.f ? 0.f : v;
+    return t > 20.f ? 20.f : t;
+  }
   return v;
 }
 template <int ACT>
@@ -480,7 +484,8 @@ bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, cons
 }
 
 // ---------------------------------------------------------------- log_softmax fwd / bwd (one warp per row)
-__global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int64_t rows, int C, int mode) {
+__global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int64_t rows, int C, int mode,
+                                   int32_t* __restrict__ nan_flag) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -494,7 +499,14 @@ __global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, flo
 #pragma unroll
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float lse = m + logf(s);
-  for (int c = lane; c < C; c += 32) out[row * C + c] = mode == 0 ? src[c] - lse : expf(src[c] - lse);
+  bool bad = false;
+  for (int c = lane; c < C; c += 32) {
+    const float v = mode == 0 ? src[c] - lse : expf(src[c] - lse);
+    bad |= v != v;
+    out[row * C + c] = v;
+  }
+  // jasper.py:474 asserts that the scores hold no NaN: raise a flag here instead of a second full pass over them
+  if (nan_flag && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nan_flag, 1);
 }
 
 __global__ void log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp, const float* __restrict__ gscale,
@@ -747,10 +759,10 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   return after_launch("bn_act_bwd_apply_kernel");
 }
 
-int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, void* stream) {
+int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, int32_t C, int32_t mode, int32_t* nan_flag, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(logits && out && rows >= 1 && C >= 1 && ld >= C, "log_softmax: bad arguments");
-  log_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, out, rows, C, mode);
+  log_softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, ld, out, rows, C, mode, nan_flag);
   return after_launch("log_softmax_kernel");
 }
 

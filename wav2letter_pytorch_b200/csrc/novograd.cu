@@ -54,14 +54,19 @@ novograd_norm_kernel(float* const* __restrict__ grads, const int64_t* __restrict
   }
 }
 
-__global__ void novograd_moment_kernel(float* __restrict__ exp_avg_sq, float* __restrict__ norms, int n_tensors, float beta2, float eps) {
+__global__ void novograd_moment_kernel(float* __restrict__ exp_avg_sq, float* __restrict__ max_exp_avg_sq, float* __restrict__ norms,
+                                       int n_tensors, float beta2, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_tensors) return;
   const float nrm = norms[i];
   float v = exp_avg_sq[i];
   v = (v == 0.f) ? nrm : v * beta2 + (1.f - beta2) * nrm;     // novograd.py:93-96
   exp_avg_sq[i] = v;
-  norms[i] = sqrtf(v) + eps;                                   // denominator, novograd.py:104
+  if (max_exp_avg_sq) {                                        // amsgrad: running maximum of the second moment, novograd.py:98-102
+    v = fmaxf(max_exp_avg_sq[i], v);
+    max_exp_avg_sq[i] = v;
+  }
+  norms[i] = sqrtf(v) + eps;                                   // denominator, novograd.py:102,104
 }
 
 __device__ __forceinline__ float ng_update1(float pv, float gv, float& mv, float inv, float ga, float lr, float beta1, float wd) {
@@ -119,7 +124,7 @@ novograd_update_kernel(float* const* __restrict__ params, float* const* __restri
 extern "C" int32_t w2l_novograd_chunk(void) { return w2l::kNgChunk; }
 
 extern "C" int w2l_novograd_step(float* const* params, float* const* grads, float* const* exp_avg, float* exp_avg_sq,
-                                 void* const* shadow_bf16, const int64_t* numel, const int32_t* chunk_prefix, int32_t n_tensors,
+                                 float* max_exp_avg_sq, void* const* shadow_bf16, const int64_t* numel, const int32_t* chunk_prefix, int32_t n_tensors,
                                  int32_t n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay,
                                  int32_t grad_averaging, float* norms_ws, void* stream) {
   using namespace w2l;
@@ -131,7 +136,7 @@ extern "C" int w2l_novograd_step(float* const* params, float* const* grads, floa
   novograd_norm_kernel<<<n_chunks, kNgThreads, 0, st>>>(grads, numel, chunk_prefix, n_tensors, norms_ws);
   int rc = after_launch("novograd_norm_kernel");
   if (rc) return rc;
-  novograd_moment_kernel<<<(n_tensors + 127) / 128, 128, 0, st>>>(exp_avg_sq, norms_ws, n_tensors, beta2, eps);
+  novograd_moment_kernel<<<(n_tensors + 127) / 128, 128, 0, st>>>(exp_avg_sq, max_exp_avg_sq, norms_ws, n_tensors, beta2, eps);
   rc = after_launch("novograd_moment_kernel");
   if (rc) return rc;
   novograd_update_kernel<<<n_chunks, kNgThreads, 0, st>>>(params, grads, exp_avg, norms_ws, shadow_bf16, numel, chunk_prefix, n_tensors,

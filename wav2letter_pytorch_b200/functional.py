@@ -252,13 +252,14 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
     return dz, red, g
 
 
-def log_softmax(logits, C, mode=0):
-    """logits [..., ld] fp32 -> [..., C] fp32 (mode 0 log_softmax, 1 softmax) over the first C columns."""
+def log_softmax(logits, C, mode=0, nan_flag=None):
+    """logits [..., ld] fp32 -> [..., C] fp32 (mode 0 log_softmax, 1 softmax) over the first C columns.  ``nan_flag`` (int32 [1],
+    zero) is set to 1 when an output is NaN."""
     ld = logits.shape[-1]
     rows = logits.numel() // ld
     out = torch.empty(logits.shape[:-1] + (C,), dtype=torch.float32, device=logits.device)
     with torch.cuda.device(logits.device):
-        _lib.check(_lib.load().w2l_log_softmax(_ptr(logits), ld, _ptr(out), rows, C, mode, _stream()), "log_softmax")
+        _lib.check(_lib.load().w2l_log_softmax(_ptr(logits), ld, _ptr(out), rows, C, mode, _ptr(nan_flag), _stream()), "log_softmax")
     return out
 
 

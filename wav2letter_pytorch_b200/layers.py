@@ -418,7 +418,7 @@ class ConvHeadFn(torch.autograd.Function):
     jasper.py:433,468-473).  Returns [B, T, n_labels] fp32 contiguous."""
 
     @staticmethod
-    def forward(ctx, xin, weight, bias, conv, mode):
+    def forward(ctx, xin, weight, bias, conv, mode, nan_flag=None):
         B, T, _ = xin.shape
         Co = conv.out_channels
         ld = (Co + 7) // 8 * 8
@@ -427,7 +427,7 @@ class ConvHeadFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
-        out = F.log_softmax(logits, Co, mode)
+        out = F.log_softmax(logits, Co, mode, nan_flag)
         ctx.conv, ctx.mode = conv, mode
         ctx.has_bias = bias is not None
         ctx.save_for_backward(xin, out)
@@ -451,7 +451,7 @@ class ConvHeadFn(torch.autograd.Function):
             F.conv1d_dgrad_wt(dl, conv.packed_t_synced(), desc, dx)
         wgrad_async(side, dl, xin, desc, dw)
         dbias = F.colsum(dl, Co) if ctx.has_bias else None
-        return dx, conv.grad_view(dw), dbias, None, None
+        return dx, conv.grad_view(dw), dbias, None, None, None
 
 
 def conv_bn_act_eval(xin, conv, bn, geo, res=None):

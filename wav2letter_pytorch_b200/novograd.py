@@ -24,8 +24,6 @@ class Novograd(Optimizer):
             raise ValueError("Invalid beta parameter at index 0: {}".format(betas[0]))
         if not 0.0 <= betas[1] < 1.0:
             raise ValueError("Invalid beta parameter at index 1: {}".format(betas[1]))
-        if amsgrad:
-            raise NotImplementedError("amsgrad is not implemented by the fused NovoGrad step")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay,
                                       grad_averaging=grad_averaging, amsgrad=amsgrad))
         self._conv_of = {}         # id(weight param) -> ConvParams module (bf16 shadow owner)
@@ -48,6 +46,7 @@ class Novograd(Optimizer):
         dev = params[0].device
         n = len(params)
         v = torch.zeros(n, dtype=torch.float32, device=dev)
+        vmax = torch.zeros(n, dtype=torch.float32, device=dev)
         shadows, convs = [], []
         for i, p in enumerate(params):
             st = self.state[p]
@@ -57,6 +56,10 @@ class Novograd(Optimizer):
             elif "exp_avg_sq" in st:
                 v[i] = st["exp_avg_sq"]
             st["exp_avg_sq"] = v[i]                      # 0-dim view, as in the reference's state layout
+            if self.param_groups[gi]["amsgrad"]:
+                if "max_exp_avg_sq" in st:
+                    vmax[i] = st["max_exp_avg_sq"]
+                st["max_exp_avg_sq"] = vmax[i]
             conv = self._conv_of.get(id(p))
             if conv is not None and conv.cout_pad == conv.out_channels:
                 shadows.append(conv.packed().data_ptr())
@@ -79,7 +82,7 @@ class Novograd(Optimizer):
         counts = torch.tensor([(p.numel() + chunk - 1) // chunk for p in params], dtype=torch.int64)
         prefix = (torch.cumsum(counts, 0) - counts).to(torch.int32)
         plan = dict(hosts=hosts, turn=0, dev=torch.empty((5, n), dtype=torch.int64, device=dev), v=v,
-                    chunk_prefix=prefix.to(dev), n_chunks=int(counts.sum()),
+                    chunk_prefix=prefix.to(dev), n_chunks=int(counts.sum()), vmax=vmax,
                     ws=torch.empty(n, dtype=torch.float32, device=dev), convs=[c for c in convs if c is not None])
         self._plans[key] = plan
         return plan
@@ -118,7 +121,8 @@ class Novograd(Optimizer):
             b1, b2 = group["betas"]
             P = F._ptr
             with torch.cuda.device(dev.device):
-                _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]), P(dev[3]), P(dev[4]), P(plan["chunk_prefix"]),
+                _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]),
+                                                 P(plan["vmax"]) if group["amsgrad"] else None, P(dev[3]), P(dev[4]), P(plan["chunk_prefix"]),
                                                  len(params), plan["n_chunks"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                                                  float(group["weight_decay"]), int(bool(group["grad_averaging"])), P(plan["ws"]),
                                                  F._stream()), "novograd_step")
