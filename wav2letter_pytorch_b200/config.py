@@ -119,6 +119,7 @@ def compose(config_dir=None, overrides=(), resolve_labels=True):
 
 _TARGET_ALIASES = {
     "decoder.GreedyDecoder": "wav2letter_pytorch_b200.decoder.GreedyDecoder",
+    "decoder.PrefixBeamSearchLMDecoder": "wav2letter_pytorch_b200.decoder.PrefixBeamSearchLMDecoder",
     "novograd.Novograd": "wav2letter_pytorch_b200.novograd.Novograd",
 }
 
