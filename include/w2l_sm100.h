@@ -196,7 +196,15 @@ int w2l_bn_stats(const void* z, int64_t rows, int32_t C, float* stats, void* str
 int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* gamma, const float* beta,
                     const float* conv_bias /* nullable: added to the mean for running_mean only when z excludes it */,
                     float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                    float* mean, float* invstd, void* stream);
+                    float* mean, float* invstd, int64_t* num_batches_tracked /* nullable: += 1 */, void* stream);
+/* Jasper's sequence-length bookkeeping for a whole encoder in one launch (MaskedConv1d.get_seq_len / forward,
+ * jasper.py:91-95,107-119): conv j truncates the incoming lengths to integers, masks with them, and hands on
+ * (len + 2*pad - dil*(k-1) - 1) / stride + 1 in float32.  conv_params_host: HOST int32 [n_convs][4] =
+ * (kernel, stride, dilation, padding); stride 0 = a conv built with use_mask=False (lengths pass through).
+ * lens_out [n_convs+1][B] int32: row j = truncated lengths entering conv j, row n_convs = output lengths (also written
+ * as int64 to final_out when given). */
+int w2l_lens_chain(const void* lens_in, int32_t lens_is_int64, int32_t B, const int32_t* conv_params_host, int32_t n_convs,
+                   int32_t* lens_out, int64_t* final_out, void* stream);
 /* y = act(dropout(z*scale + shift [+ res*res_scale + res_shift])), written into a (possibly halo'd)
  * buffer: y[b, pad_left + t, c]; reflect halos of pad_left / pad_right rows are filled from the
  * interior (nn.ReflectionPad1d of the NEXT layer, wav2letter.py:28-34,41); rows t >= lens[b] are zeroed

@@ -479,3 +479,22 @@ def test_features_golden_and_ragged_batch(golden):
     assert (out2 - out).abs().max() < 0.2
     with pytest.raises(RuntimeError):
         ex.extract(np.zeros(200, dtype=np.float32))
+
+
+def test_lens_chain_matches_reference_arithmetic(F):
+    """one launch vs the reference's per-conv tensor arithmetic (jasper.py:91-95,107-119): lens.to(long), then
+    (lens + 2p - d(k-1) - 1) / stride + 1 as a float tensor handed to the next conv"""
+    g = torch.Generator().manual_seed(9)
+    lens0 = torch.randint(1, 3000, (37,), generator=g, dtype=torch.int64)
+    chain = [(11, 2, 1, 5), (11, 1, 1, 5), (13, 1, 1, 6), (29, 1, 2, 28), (1, 1, 1, 0), (33, 2, 1, 16), (7, 3, 1, 3), (5, 0, 1, 2), (9, 1, 1, 4)]
+    want_rows, lens = [lens0.clone()], lens0
+    for k, s, d, p in chain:
+        if s != 0:
+            lens = lens.to(dtype=torch.long)
+            lens = (lens + 2 * p - d * (k - 1) - 1) / s + 1
+        want_rows.append(lens.to(dtype=torch.long))
+    for dt in (torch.int64, torch.int32):
+        rows, final = F.lens_chain(lens0.to(dt).cuda(), chain)
+        assert rows.dtype == torch.int32 and final.dtype == torch.int64
+        assert torch.equal(rows.cpu().long(), torch.stack(want_rows))
+        assert torch.equal(final.cpu(), want_rows[-1])

@@ -99,7 +99,8 @@ SIGNATURES = {
     "w2l_ncw_to_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_bn_stats": (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     "w2l_bn_finalize": (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                c_ptr]),
+                                c_ptr, c_ptr]),
+    "w2l_lens_chain": (c_i32, [c_ptr, c_i32, c_i32, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
     "w2l_bn_act_pad": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32,
                                c_u64, c_ptr, c_ptr, c_ptr]),
     "w2l_reflect_halo": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),

@@ -177,8 +177,10 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t row
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t rows, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   int64_t* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;     // BatchNorm1d's counter buffer, without a launch of its own
   if (c >= C) return;
   const double n = (double)rows;
   const double mean = (double)stats[c] / n;
@@ -563,6 +565,33 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
     for (int64_t i = n8 * 8; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// ---------------------------------------------------------------- Jasper length bookkeeping (jasper.py:91-95, 107-119)
+// Every MaskedConv1d truncates the incoming lengths to integers (lens.to(long)), masks with them, and hands on
+// (lens + 2p - d(k-1) - 1) / stride + 1 as a FLOAT tensor (true division); the reference spends ~6 tiny kernels per conv on
+// this.  One thread per utterance walks the whole chain: out[j][b] = truncated length entering conv j (row n = the output
+// lengths).  stride 0 marks a conv that does not mask (lengths pass through untouched).
+constexpr int kMaxChain = 192;
+struct LensChain {
+  int32_t n;
+  int16_t k[kMaxChain], s[kMaxChain], d[kMaxChain], p[kMaxChain];
+};
+__global__ void lens_chain_kernel(const void* __restrict__ lens_in, int is64, int B, LensChain c, int32_t* __restrict__ out,
+                                  int64_t* __restrict__ final_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long li = is64 ? reinterpret_cast<const long long*>(lens_in)[b] : (long long)reinterpret_cast<const int32_t*>(lens_in)[b];
+  out[b] = (int32_t)li;
+  for (int j = 0; j < c.n; ++j) {
+    if (c.s[j] != 0) {
+      const long long v = li + 2 * c.p[j] - c.d[j] * (c.k[j] - 1) - 1;
+      const float lf = __fdiv_rn((float)v, (float)c.s[j]) + 1.f;       // int64 tensor / int -> float32 true division, then + 1
+      li = (long long)lf;                                               // the next conv's lens.to(dtype=torch.long)
+    }
+    out[(int64_t)(j + 1) * B + b] = (int32_t)li;
+  }
+  if (final_out) final_out[b] = li;
+}
+
 static inline int grid_for(int64_t items, int threads) {
   int64_t blocks = (items + threads - 1) / threads;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -689,12 +718,13 @@ int w2l_bn_stats(const void* z, int64_t rows, int32_t C, float* stats, void* str
 
 int w2l_bn_finalize(const float* stats, int64_t rows, int32_t C, const float* gamma, const float* beta, const float* conv_bias,
                     float eps, float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
-                    float* invstd, void* stream) {
+                    float* invstd, int64_t* num_batches_tracked, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(stats && scale && shift && rows >= 1 && C >= 1, "bn_finalize: bad arguments");
   W2L_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats must be given together");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, rows, C, gamma, beta, conv_bias, eps, momentum,
-                                                                        running_mean, running_var, scale, shift, mean, invstd);
+                                                                        running_mean, running_var, scale, shift, mean, invstd,
+                                                                        num_batches_tracked);
   return after_launch("bn_finalize_kernel");
 }
 
@@ -853,4 +883,24 @@ extern "C" int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, in
   dim3 grid((Cin_pad + 31) / 32, (Cout_pad + 31) / 32, k), block(32, 8);
   pack_wt_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wt, k, Cout, Cin, Cout_pad, Cin_pad);
   return after_launch("pack_wt_kernel");
+}
+
+extern "C" int w2l_lens_chain(const void* lens_in, int32_t lens_is_int64, int32_t B, const int32_t* conv_params_host, int32_t n_convs,
+                              int32_t* lens_out, int64_t* final_out, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(lens_in && lens_out && B >= 1 && n_convs >= 0 && n_convs <= kMaxChain, "lens_chain: bad arguments (at most %d convs)", kMaxChain);
+  W2L_REQUIRE(n_convs == 0 || conv_params_host, "lens_chain: null conv table");
+  LensChain c;
+  c.n = n_convs;
+  for (int j = 0; j < n_convs; ++j) {
+    const int32_t* q = conv_params_host + 4 * j;            // (kernel, stride [0 = unmasked pass-through], dilation, padding)
+    W2L_REQUIRE(q[0] >= 1 && q[0] < 32768 && q[1] >= 0 && q[1] < 32768 && q[2] >= 1 && q[2] < 32768 && q[3] >= 0 && q[3] < 32768,
+                "lens_chain: conv %d has out-of-range geometry", j);
+    c.k[j] = (int16_t)q[0];
+    c.s[j] = (int16_t)q[1];
+    c.d[j] = (int16_t)q[2];
+    c.p[j] = (int16_t)q[3];
+  }
+  lens_chain_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(lens_in, lens_is_int64, B, c, lens_out, final_out);
+  return after_launch("lens_chain_kernel");
 }

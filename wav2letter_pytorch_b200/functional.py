@@ -203,14 +203,32 @@ def bn_stats(z, C):
     return stats
 
 
-def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var):
+def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked=None):
+    """``num_batches_tracked`` (int64 0-dim CUDA buffer): incremented by the same kernel."""
     dev = stats.device
     out = torch.empty((4, C), dtype=torch.float32, device=dev)     # scale, shift, mean, invstd
     with torch.cuda.device(dev):
         _lib.check(_lib.load().w2l_bn_finalize(_ptr(stats), rows, C, _ptr(gamma), _ptr(beta), _ptr(conv_bias), eps, momentum,
                                                _ptr(running_mean), _ptr(running_var), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                               _ptr(out[3]), _stream()), "bn_finalize")
+                                               _ptr(out[3]), _ptr(num_batches_tracked), _stream()), "bn_finalize")
     return out
+
+
+def lens_chain(lens, conv_params):
+    """lens [B] int32/int64 CUDA, conv_params: list of (kernel, stride|0, dilation, padding) per masked conv in execution order
+    -> (rows int32 [n+1, B], output lengths int64 [B]); see w2l_lens_chain."""
+    _need_cuda(lens)
+    if lens.dtype not in (torch.int32, torch.int64):
+        lens = lens.to(torch.int64)                                  # the reference's lens.to(dtype=torch.long)
+    lens = lens.contiguous()
+    B, n = lens.numel(), len(conv_params)
+    rows = torch.empty((n + 1, B), dtype=torch.int32, device=lens.device)
+    final = torch.empty((B,), dtype=torch.int64, device=lens.device)
+    table = (ctypes.c_int32 * (4 * max(n, 1)))(*[int(v) for q in conv_params for v in q])
+    with torch.cuda.device(lens.device):
+        _lib.check(_lib.load().w2l_lens_chain(_ptr(lens), int(lens.dtype == torch.int64), B, table, n, _ptr(rows), _ptr(final), _stream()),
+                   "lens_chain")
+    return rows, final
 
 
 def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None,

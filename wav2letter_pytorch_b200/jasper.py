@@ -153,15 +153,26 @@ class JasperBlock(nn.Module):
                 out.append((None, self.mconv[i], self.mconv[i + 1]))
         return out
 
-    def forward_tm(self, h, t, lens, from_ncw, mask_output):
+    def chain_params(self):
+        """(kernel, stride | 0 when unmasked, dilation, padding) of this block's MaskedConv1d modules in execution order -- the
+        table ``F.lens_chain`` walks (the residual 1x1 conv masks with the block's INPUT lengths and hands nothing on)."""
+        out = []
+        for dwm, mc, _bn in self.sub_blocks():
+            for m in ((dwm, mc) if dwm is not None else (mc,)):
+                c = m.conv
+                out.append((c.kernel_size[0], c.stride[0] if self.conv_mask else 0, c.dilation[0], c.padding[0]))
+        return out
+
+    def forward_tm(self, h, t, rows, ri, from_ncw, mask_output):
         """h: NCW fp32 (first block, ``from_ncw``) or time-major bf16 [B, t, C] whose rows >= len are already zero.
-        Returns (time-major bf16 output, t_out, lens_out)."""
+        ``rows`` [n+1, B] int32 = truncated lengths entering every masked conv of the encoder (``F.lens_chain``), ``ri`` = index of
+        this block's first conv in it (``rows`` is None when no lengths were given).  Returns (time-major bf16 output, t_out, ri)."""
         subs = self.sub_blocks()
         first = subs[0][0] if self.separable else subs[0][1]
         if from_ncw:
             m0 = first.conv
             k, s, d, p = m0.kernel_size[0], m0.stride[0], m0.dilation[0], m0.padding[0]
-            mask = lens.to(torch.int32) if (self.conv_mask and lens is not None) else None
+            mask = rows[ri] if (self.conv_mask and rows is not None) else None
             if not self.separable and m0.unfold:
                 t_first = (t + 2 * p - d * (k - 1) - 1) // s + 1
                 h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask)        # masked, zero padded, unfolded
@@ -180,9 +191,6 @@ class JasperBlock(nn.Module):
                 F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
                 res_pair = (zr, rbn.eval_scale_shift(None))
 
-        def as_i32(l):
-            return l.to(dtype=torch.long).to(torch.int32)                        # the consumer truncates with .to(long)
-
         for r, (dwm, mc, bn) in enumerate(subs):
             conv = mc.conv
             last = r == len(subs) - 1
@@ -190,9 +198,8 @@ class JasperBlock(nn.Module):
                 dc = dwm.conv
                 k, s, d, p = dc.kernel_size[0], dc.stride[0], dc.dilation[0], dc.padding[0]
                 t_dw = (t + 2 * p - d * (k - 1) - 1) // s + 1
-                if self.conv_mask and lens is not None:
-                    lens = dwm.get_seq_len(lens.to(dtype=torch.long))
-                dmask = as_i32(lens) if (self.conv_mask and lens is not None) else None
+                ri += 1                                                          # lengths after the depthwise conv
+                dmask = rows[ri] if (self.conv_mask and rows is not None) else None
                 if training:
                     h = DepthwiseFn.apply(h, dc.weight, dc, t_dw, dmask)
                 else:
@@ -203,11 +210,10 @@ class JasperBlock(nn.Module):
             else:
                 k, d, p = conv.kernel_size[0], conv.dilation[0], conv.padding[0]
                 t_out, x_off = t + 2 * p - d * (k - 1), -p
-            if self.conv_mask and lens is not None:
-                lens = mc.get_seq_len(lens.to(dtype=torch.long))                 # float after true division, as the reference
+            ri += 1                                                              # lengths after this conv (truncated, as its consumer sees them)
             out_mask = None
-            if self.conv_mask and lens is not None and (not last or mask_output):
-                out_mask = as_i32(lens)
+            if self.conv_mask and rows is not None and (not last or mask_output):
+                out_mask = rows[ri]
             geo = {"T_out": t_out, "x_row_offset": x_off, "out_pad": (0, 0), "act": self.act,
                    "drop_p": self.dropout_p if training else 0.0, "lens": out_mask}
             use_res = res_pair if last else None
@@ -217,7 +223,7 @@ class JasperBlock(nn.Module):
             else:
                 h = conv_bn_act_eval(h, conv, bn, geo, res=use_res)
             t = t_out
-        return h, t, lens
+        return h, t, ri
 
 
 class Jasper(ConvCTCASR):
@@ -256,13 +262,17 @@ class Jasper(ConvCTCASR):
         the reference's behaviour, jasper.py:470-473 -- , output lengths int64 [B])."""
         if not xs.is_cuda:
             raise RuntimeError("Jasper: CUDA input required (this build has no CPU path)")
-        lens = input_lengths.to(xs.device) if input_lengths is not None else None
-        h, t = xs, xs.shape[2]
         blocks = list(self.jasper_encoder)
+        rows, out_lens = None, None
+        if input_lengths is not None:
+            # every MaskedConv1d's length arithmetic (truncate, mask, (len + 2p - d(k-1) - 1) / stride + 1) in ONE launch
+            if getattr(self, "_chain", None) is None:
+                self._chain = [q for blk in blocks for q in blk.chain_params()]
+            rows, out_lens = F.lens_chain(input_lengths.to(xs.device), self._chain)
+        h, t, ri = xs, xs.shape[2], 0
         for i, blk in enumerate(blocks):
             # the head (final_layer) is NOT masked in the reference (jasper.py:468): the last block keeps its padded rows
-            h, t, lens = blk.forward_tm(h, t, lens, from_ncw=(i == 0), mask_output=(i != len(blocks) - 1))
-        out_lens = lens.to(dtype=int) if lens is not None else None
+            h, t, ri = blk.forward_tm(h, t, rows, ri, from_ncw=(i == 0), mask_output=(i != len(blocks) - 1))
         head = self.final_layer[0]
         mode = getattr(self, "nan_check", "sync")
         flag = torch.zeros(1, dtype=torch.int32, device=xs.device) if mode != "off" else None

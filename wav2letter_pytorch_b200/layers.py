@@ -332,8 +332,8 @@ class ConvBNActFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
         stats = conv_fwd_with_stats(xin, conv, desc, z)        # batch statistics from the epilogue; conv bias folded below
-        fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
-        bn.num_batches_tracked += 1
+        fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                            bn.num_batches_tracked)
         drop_p = geo.get("drop_p", 0.0)
         seed = next_dropout_seed() if drop_p > 0 else 0
         mask = torch.empty((B * T_out * Co // 8,), dtype=torch.uint8, device=xin.device) if drop_p > 0 else None
@@ -390,8 +390,8 @@ class ResidualBranchFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
         stats = conv_fwd_with_stats(xin, conv, desc, z)
-        fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
-        bn.num_batches_tracked += 1
+        fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                            bn.num_batches_tracked)
         ctx.conv, ctx.desc = conv, desc
         ctx.save_for_backward(xin, z, fin, gamma)
         ctx.mark_non_differentiable(fin)
