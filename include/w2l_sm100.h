@@ -149,6 +149,13 @@ typedef struct {
 
 int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, float* bn_stats,
                    void* y, const w2l_conv_desc* d, void* stream);
+/* Optional fp32 scratch for w2l_conv1d_fwd (caller-owned, ZERO-filled once, >= 4096 + 148*128*256*4 bytes, 256-byte aligned).
+ * With it, a forward launch whose last wave of 128 x BN tiles is less than 3/4 full cuts those tiles along K over the idle SMs;
+ * the pieces meet in the scratch and the last one to arrive runs the epilogue (fixed summation order: deterministic).  Forward
+ * launches that use it must be stream-ordered with respect to each other.  NULL/0 unregisters. */
+int w2l_set_gemm_scratch(void* scratch, size_t bytes);
+/* K pieces per tile of the last wave that w2l_conv1d_fwd would use for this descriptor right now (0/1 = no split) */
+int32_t w2l_conv1d_fwd_tail_parts(const w2l_conv_desc* d);
 int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream);
 /* Backward-data with a second, transposed bf16 shadow wt [k, Cin_pad16, Cout_pad] (wt[k-1-j][ci][co] = w[j][co][ci],
  * written by w2l_pack_wt): both GEMM operands are then K-major, which the tensor pipe consumes ~30% faster than the

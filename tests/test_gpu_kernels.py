@@ -498,3 +498,39 @@ def test_lens_chain_matches_reference_arithmetic(F):
         assert rows.dtype == torch.int32 and final.dtype == torch.int64
         assert torch.equal(rows.cpu().long(), torch.stack(want_rows))
         assert torch.equal(final.cpu(), want_rows[-1])
+
+
+def test_conv_fwd_tail_split(F):
+    """the forward tail split (last wave of tiles cut along K, pieces summed in an fp32 scratch by the last arriver), forced on
+    a small problem by capping the persistent grid at 8 SMs: 18 tiles = 2 full waves + 2 tiles -> 4 K-pieces each.  Checked for
+    the plain store, the fused affine+clamp bf16 epilogue and the BatchNorm statistics, twice (the arrival counters self-clean)."""
+    import ctypes
+    from wav2letter_pytorch_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(12)
+    B, T, Cin, Cout, k = 9, 200, 256, 256, 11
+    pad = k // 2
+    x = _bf(torch.randn(B, T, Cin, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    want = TF.conv1d(x.transpose(1, 2), w, padding=pad).transpose(1, 2)
+    xc, wc = x.to(torch.bfloat16).cuda(), _pack_w(w, Cout).cuda()
+    F.ensure_gemm_scratch(xc.device)
+    try:
+        lib.w2l_set_sm_budget(8)
+        desc = F.make_desc(B, T, Cin, Cout, Cout, k, 1, T, -pad, T, 0, Cout, F.DT_F32, F.ACT_NONE)
+        assert lib.w2l_conv1d_fwd_tail_parts(ctypes.byref(desc)) == 4
+        for rep in range(2):
+            y = torch.zeros(B, T, Cout, dtype=torch.float32, device="cuda")
+            F.conv1d_fwd(xc, wc, desc, y)
+            assert rel_l2(y.cpu(), want) < 2e-5
+        sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+        desc2 = F.make_desc(B, T, Cin, Cout, Cout, k, 1, T, -pad, T, 0, Cout, F.DT_BF16, F.ACT_CLAMP20)
+        y2 = torch.zeros(B, T, Cout, dtype=torch.bfloat16, device="cuda")
+        st = torch.zeros(2 * Cout, dtype=torch.float32, device="cuda")
+        F.conv1d_fwd(xc, wc, desc2, y2, scale=sc.cuda(), shift=sh.cuda(), bn_stats=st)
+        assert rel_l2(y2.float().cpu(), torch.clamp(want * sc + sh, 0, 20)) < 6e-3
+        yd = y2.double().reshape(-1, Cout)
+        assert torch.allclose(st[:Cout].double(), yd.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(st[Cout:].double(), (yd * yd).sum(0), rtol=1e-4)
+    finally:
+        lib.w2l_set_sm_budget(0)
+    assert lib.w2l_conv1d_fwd_tail_parts(ctypes.byref(desc)) <= 1          # 18 tiles fit one wave of the full machine

@@ -66,6 +66,13 @@ struct GemmParams {
   int32_t mn4d;             // wgrad: operands are loaded through 4-D maps (64 x rows x chunks x B), one TMA op each
   int32_t dbg;              // development knobs (env W2L_DBG): 1 = fwd B tile as 64-row TMA boxes, 2 = skip epilogue stores
   int64_t dw_tap_stride;    // Cout*Cin
+  // fwd tail split (wave quantisation): the last, partly filled wave of tiles is cut along K into `tail_parts` pieces per tile;
+  // pieces meet in an fp32 scratch tile and the last one to arrive runs the epilogue
+  int32_t tail_first;       // index of the first tile of the last wave (== num_tiles: no split)
+  int32_t tail_tiles;       // tiles in the last wave
+  int32_t tail_parts;       // K pieces per tail tile (<= 1: no split)
+  float* scratch;           // [tail_tiles * tail_parts][128][BN] fp32
+  int32_t* counters;        // [tail_tiles] arrival counters, zero between launches
 };
 
 // A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
@@ -76,6 +83,7 @@ struct Unit {
   int m0, n0, b, j;      // b: utterance (fwd/dgrad); j: tap (wgrad)
   int it_begin, it_end;  // K iterations of the tile covered by this unit
   bool partial;
+  int slot, tail;        // fwd tail split: scratch slot of this piece, index of the tile within the last wave
 };
 
 template <int MODE>
@@ -95,7 +103,8 @@ struct UnitIter {
       g_end = rem * (blockIdx.x + 1) / gridDim.x;
     } else {
       iters = p.k * p.kc_steps;
-      tile_end = p.num_tiles;
+      tile_end = p.tail_parts > 1 ? p.tail_first : p.num_tiles;
+      g = 0;                                      // fwd/dgrad: 0 = the tail piece of this CTA is still to come
     }
   }
   __device__ void decode_wgrad(int t, Unit& u) const {      // tap fastest: neighbouring CTAs share dy and (shifted) x rows
@@ -104,6 +113,14 @@ struct UnitIter {
     u.n0 = (t % p.n_tiles) * p.BN;
     u.m0 = (t / p.n_tiles) * kBlockM;
     u.b = 0;
+  }
+  __device__ void decode_fwd(int t, Unit& u) const {
+    const int mt = t % p.m_tiles;
+    t /= p.m_tiles;
+    u.b = t % p.B;
+    u.n0 = (t / p.B) * p.BN;
+    u.m0 = mt * kBlockM;
+    u.j = 0;
   }
   __device__ bool next(Unit& u) {
     if (tile < tile_end) {
@@ -115,13 +132,22 @@ struct UnitIter {
       if (MODE == MODE_WGRAD) {
         decode_wgrad(t, u);
       } else {
-        const int mt = t % p.m_tiles;
-        t /= p.m_tiles;
-        u.b = t % p.B;
-        u.n0 = (t / p.B) * p.BN;
-        u.m0 = mt * kBlockM;
-        u.j = 0;
+        decode_fwd(t, u);
       }
+      return true;
+    }
+    if (MODE != MODE_WGRAD) {
+      if (p.tail_parts <= 1 || g != 0) return false;
+      g = 1;
+      const int c = blockIdx.x;
+      if (c >= p.tail_tiles * p.tail_parts) return false;
+      u.tail = c / p.tail_parts;
+      const int part = c - u.tail * p.tail_parts;
+      u.slot = c;
+      u.it_begin = (int)((int64_t)iters * part / p.tail_parts);
+      u.it_end = (int)((int64_t)iters * (part + 1) / p.tail_parts);
+      u.partial = true;
+      decode_fwd(p.tail_first + u.tail, u);
       return true;
     }
     if (MODE == MODE_WGRAD) {
@@ -167,6 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint32_t* s_flag = tmem_slot + 1;           // fwd tail split: arrival order of this CTA's piece
   float2* s_aff = reinterpret_cast<float2*>(smem + kStages * kStageBytes + 256);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -312,50 +339,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
       const int m = tc.m0 + row;
       const bool row_ok = m < p.M_valid;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        const int nbase = tc.n0 + c0;
-        if (nbase >= p.N_valid) break;                       // padded part of a last N tile
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c0, r);
-        tmem_ld_wait();
-        if (MODE == MODE_WGRAD) {
-          if (row_ok) {
-            float* dst = reinterpret_cast<float*>(p.y) + (int64_t)tc.j * p.dw_tap_stride + (int64_t)m * p.ldy + nbase;
-            if (tc.partial) {
-              if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
-                               "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
-                               : "memory");
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (c0 + i < p.BN && nbase + i < p.N_valid) atomicAdd(dst + i, __uint_as_float(r[i]));
-              }
-            } else if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
-                                                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __uint_as_float(r[i]);
-            }
-          }
-        } else {
-          float v[32];
+      // fwd/dgrad: one 32-column chunk of this thread's row, accumulator values in v -> affine / activation / BN statistics / store
+      auto finish_chunk = [&](float (&v)[32], int c0, int nbase) {
           if (has_aff) {
             const float2* aff = s_aff + acc * 256 + c0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float2 a = aff[i];
-              v[i] = fmaf(__uint_as_float(r[i]), a.x, a.y);
+              v[i] = fmaf(v[i], a.x, a.y);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           }
           if (has_act) {   // NaN passes through, as torch.clamp / relu do
 #pragma unroll
@@ -407,6 +399,94 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
               }
             }
           }
+      };
+      if (MODE != MODE_WGRAD && tc.partial) {
+        // ---- fwd tail split: this CTA computed one K piece of the tile.  Park the fp32 partial in the scratch slot, free the
+        // accumulator, and let the LAST piece to arrive add the pieces in a fixed order and run the epilogue.
+        float* mine = p.scratch + ((int64_t)tc.slot * kBlockM + row) * p.BN;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            if (c0 + i < p.BN)
+              *reinterpret_cast<float4*>(mine + c0 + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                      __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ep_tid == 0) *s_flag = (uint32_t)atomicAdd(p.counters + tc.tail, 1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if ((int)*s_flag == p.tail_parts - 1) {
+          __threadfence();
+          const float* first = p.scratch + ((int64_t)tc.tail * p.tail_parts * kBlockM + row) * p.BN;
+          for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            const int nbase = tc.n0 + c0;
+            if (nbase >= p.N_valid) break;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int q = 0; q < p.tail_parts; ++q) {
+              const float* src = first + (int64_t)q * kBlockM * p.BN + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                if (c0 + i < p.BN) {
+                  const float4 t4 = __ldcg(reinterpret_cast<const float4*>(src + i));
+                  v[i] += t4.x;
+                  v[i + 1] += t4.y;
+                  v[i + 2] += t4.z;
+                  v[i + 3] += t4.w;
+                }
+            }
+            finish_chunk(v, c0, nbase);
+          }
+          if (ep_tid == 0) p.counters[tc.tail] = 0;          // clean for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // s_flag is reused by the next unit
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        continue;
+      }
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int nbase = tc.n0 + c0;
+        if (nbase >= p.N_valid) break;                       // padded part of a last N tile
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (MODE == MODE_WGRAD) {
+          if (row_ok) {
+            float* dst = reinterpret_cast<float*>(p.y) + (int64_t)tc.j * p.dw_tap_stride + (int64_t)m * p.ldy + nbase;
+            if (tc.partial) {
+              if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
+                               "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                               : "memory");
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c0 + i < p.BN && nbase + i < p.N_valid) atomicAdd(dst + i, __uint_as_float(r[i]));
+              }
+            } else if (c0 + 32 <= p.BN && nbase + 32 <= p.N_valid) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __uint_as_float(r[i]);
+            }
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          finish_chunk(v, c0, nbase);
         }
       }
       tc_fence_before();
@@ -443,6 +523,32 @@ static int pick_bn(int n, int multiple) {
     }
   }
   return best;
+}
+
+// fp32 scratch for the forward tail split, registered by the host (w2l_set_gemm_scratch): [4096 bytes of arrival counters][slots]
+static void* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+constexpr size_t kScratchCounterBytes = 4096;
+
+// Cut the last, partly filled wave of forward tiles along K when that shortens it (see GemmParams::tail_*).
+static void plan_tail_split(GemmParams& p) {
+  const int grid = p.num_tiles < gemm_sms() ? p.num_tiles : gemm_sms();
+  const int iters = p.k * p.kc_steps;
+  static const bool enabled = !(getenv("W2L_FWD_TAIL_SPLIT") && atoi(getenv("W2L_FWD_TAIL_SPLIT")) == 0);
+  p.tail_first = p.num_tiles;
+  if (!enabled || !g_scratch || grid < 2 || p.num_tiles <= grid || iters < 32) return;
+  const int full = (p.num_tiles / grid) * grid, rem = p.num_tiles - full;
+  if (rem == 0 || rem * 4 > grid * 3) return;                       // the last wave is (nearly) full anyway
+  int parts = grid / rem;
+  if (parts > 8) parts = 8;
+  while (parts > 1 && iters / parts < 8) --parts;
+  const size_t need = kScratchCounterBytes + (size_t)rem * parts * kBlockM * p.BN * sizeof(float);
+  if (parts < 2 || need > g_scratch_bytes || (size_t)rem * sizeof(int32_t) > kScratchCounterBytes) return;
+  p.tail_first = full;
+  p.tail_tiles = rem;
+  p.tail_parts = parts;
+  p.counters = reinterpret_cast<int32_t*>(g_scratch);
+  p.scratch = reinterpret_cast<float*>(reinterpret_cast<char*>(g_scratch) + kScratchCounterBytes);
 }
 
 template <int MODE>
@@ -547,7 +653,31 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   p.y_row_off = d->y_row_offset;
   p.ldy = d->ldy;
   p.splits = 1;
+  plan_tail_split(p);
   return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
+}
+
+int32_t w2l_conv1d_fwd_tail_parts(const w2l_conv_desc* d) {
+  using namespace w2l;
+  if (!d || d->B < 1 || d->T_out < 1 || d->k < 1 || d->Cin < 1 || d->Cout_pad < 16) return 0;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.BN = pick_bn(d->Cout_pad, 16);
+  p.k = d->k;
+  p.kc_steps = (d->Cin + kBlockK - 1) / kBlockK;
+  p.num_tiles = ((d->T_out + kBlockM - 1) / kBlockM) * ((d->Cout_pad + p.BN - 1) / p.BN) * d->B;
+  plan_tail_split(p);
+  return p.tail_parts;
+}
+
+int w2l_set_gemm_scratch(void* scratch, size_t bytes) {
+  using namespace w2l;
+  W2L_REQUIRE((scratch == nullptr) == (bytes == 0), "set_gemm_scratch: pointer and size must be given together");
+  W2L_REQUIRE(scratch == nullptr || (bytes > kScratchCounterBytes && ((uintptr_t)scratch & 255) == 0), "set_gemm_scratch: need > %zu bytes, 256-byte aligned",
+              kScratchCounterBytes);
+  g_scratch = scratch;
+  g_scratch_bytes = bytes;
+  return W2L_OK;
 }
 
 int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_desc* d, void* stream) {
@@ -644,6 +774,7 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   p.y_row_off = 0;
   p.ldy = d->Cin;
   p.splits = 1;
+  p.tail_first = p.num_tiles;          // backward-data overlaps with wgrad, whose CTAs fill its last wave: no tail split here
   return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
 }
 

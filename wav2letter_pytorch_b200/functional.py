@@ -97,9 +97,23 @@ def make_desc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, 
     return ConvDesc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype, act)
 
 
+_gemm_scratch = {}
+
+
+def ensure_gemm_scratch(device):
+    """Registers (once per process) the zero-filled fp32 scratch the forward GEMM uses to split its last wave of tiles along K."""
+    if _gemm_scratch:
+        return
+    nbytes = 4096 + 148 * 128 * 256 * 4
+    buf = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().w2l_set_gemm_scratch(_ptr(buf), nbytes), "set_gemm_scratch")
+    _gemm_scratch[device] = buf
+
+
 def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
     """``bn_stats`` (fp32 [2*Cout], zero-filled): receives the per-channel sum / sum of squares of the stored output."""
     _need_cuda(x, w, y)
+    ensure_gemm_scratch(x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().w2l_conv1d_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(bn_stats), _ptr(y),
                                               ctypes.byref(desc), _stream()), "conv1d_fwd")
