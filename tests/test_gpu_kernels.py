@@ -534,3 +534,15 @@ def test_conv_fwd_tail_split(F):
     finally:
         lib.w2l_set_sm_budget(0)
     assert lib.w2l_conv1d_fwd_tail_parts(ctypes.byref(desc)) <= 1          # 18 tiles fit one wave of the full machine
+
+
+def test_conv_slab_mode_opt_in():
+    """the opt-in resident-slab forward path (W2L_SLAB=1, read once per process): the conv parity cases in a fresh interpreter"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, W2L_SLAB="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
+                        "conv_fwd_dgrad_wgrad or conv_dgrad_flat or conv_fwd_tail_split", "-p", "no:cacheprovider"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]

@@ -34,6 +34,8 @@ constexpr int kAccCols = 256;
 constexpr int kGemmThreads = 192;
 constexpr int kAffBytes = 2 * 256 * 8;          // per-accumulator (scale, shift) of the tile's columns for the epilogue
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kAffBytes;
+constexpr int kSlabBufs = 3;                    // slab mode: the next chunk's slab is requested a whole chunk ahead
+constexpr size_t kGemmSmemMax = 227 * 1024;     // opt-in limit per CTA on sm_100
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
@@ -73,6 +75,13 @@ struct GemmParams {
   int32_t tail_parts;       // K pieces per tail tile (<= 1: no split)
   float* scratch;           // [tail_tiles * tail_parts][128][BN] fp32
   int32_t* counters;        // [tail_tiles] arrival counters, zero between launches
+  // fwd resident activation slab: rows [m0 + a_row_off, + 128 + (k-1)*dil) of one 64-channel chunk are fetched ONCE and every
+  // tap's A operand is a row-shifted view of it (tcgen05 applies the 128B swizzle on absolute shared-memory address bits, so
+  // a descriptor may start at any row: tools/probe_umma_row_offset.cu); only the weight tile is fetched per (tap, chunk)
+  int32_t slab_rows;        // 0: per-tap A tiles (the K loop is tap-major); > 0: slab mode (the K loop is chunk-major)
+  int32_t slab_bytes;       // one slab buffer (slab_rows * 128 rounded up to the 1024-byte swizzle atom); three of them
+  int32_t b_stages;         // weight-tile ring depth in slab mode (4, or 3 when the slabs are large)
+  int32_t ring_bytes;       // operand rings occupy [0, ring_bytes) of the (1024-aligned) dynamic shared memory; barriers follow
 };
 
 // A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
@@ -187,14 +196,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
   uint64_t* full_bar = bars;                  // [kStages]
   uint64_t* empty_bar = bars + kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* slab_full = tempty_bar + 2;       // [kSlabBufs]  slab mode
+  uint64_t* slab_empty = slab_full + kSlabBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_empty + kSlabBufs);
   uint32_t* s_flag = tmem_slot + 1;           // fwd tail split: arrival order of this CTA's piece
-  float2* s_aff = reinterpret_cast<float2*>(smem + kStages * kStageBytes + 256);   // [2][256]
+  // slab mode smem map: [kSlabBufs slabs of slab_bytes][b_stages weight tiles of 32 KB]
+  const bool slab_mode = (MODE == MODE_FWD) && p.slab_rows > 0;
+  const uint32_t slab_bytes = (uint32_t)p.slab_bytes, b_ring_off = kSlabBufs * slab_bytes;
+  float2* s_aff = reinterpret_cast<float2*>(smem + p.ring_bytes + 256);   // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool kAMN = (MODE == MODE_WGRAD);
@@ -212,6 +226,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 128);
+    }
+    for (int i = 0; i < kSlabBufs; ++i) {
+      mbar_init(&slab_full[i], 1);
+      mbar_init(&slab_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -231,6 +249,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       uint32_t phase = 0;
       UnitIter<MODE> units(p);
       Unit u;
+      if (slab_mode) {
+        int sidx = 0;
+        uint32_t sphase = 0;
+        while (units.next(u)) {
+          const int kc_last = (u.it_end - 1) / p.k;
+          int kc_issued = u.it_begin / p.k;                     // next chunk whose slab has not been requested yet
+          for (int it = u.it_begin; it < u.it_end; ++it) {
+            const int kc = it / p.k, j = it - kc * p.k;
+            // keep the slab of the NEXT chunk in flight while this chunk's weight tiles stream: with three buffers the one it
+            // lands in was released a whole chunk ago, so this never waits
+            while (kc_issued <= kc_last && kc_issued <= kc + 1) {
+              mbar_wait(&slab_empty[sidx], sphase ^ 1u);
+              mbar_expect_tx(&slab_full[sidx], (uint32_t)p.slab_rows * 128u);
+              tma_load_3d(smem + sidx * slab_bytes, &p.tmA, &slab_full[sidx], kc_issued * kBlockK, u.m0 + p.a_row_off, u.b);
+              ++kc_issued;
+              if (++sidx == kSlabBufs) {
+                sidx = 0;
+                sphase ^= 1u;
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_expect_tx(&full_bar[stage], (uint32_t)p.BN * 128u);
+            tma_load_3d(smem + b_ring_off + stage * kBBytesMax, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0, j);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      } else
       while (units.next(u)) {
         for (int it = u.it_begin; it < u.it_end; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -283,6 +331,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       uint32_t acc_phase = 0;
       UnitIter<MODE> units(p);
       Unit u;
+      if (slab_mode) {
+        int sidx = 0;
+        uint32_t sphase = 0;
+        while (units.next(u)) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+          uint32_t accumulate = 0;
+          int cur_kc = -1, cur_s = 0;
+          uint32_t a_base = 0;
+          for (int it = u.it_begin; it < u.it_end; ++it) {
+            const int kc = it / p.k, j = it - kc * p.k;
+            if (kc != cur_kc) {
+              if (cur_kc >= 0) umma_commit(&slab_empty[cur_s]);   // every MMA that read the previous slab has been issued
+              cur_kc = kc;
+              cur_s = sidx;
+              mbar_wait(&slab_full[sidx], sphase);
+              tc_fence_after();
+              a_base = smem_u32(smem + sidx * slab_bytes);
+              if (++sidx == kSlabBufs) {
+                sidx = 0;
+                sphase ^= 1u;
+              }
+            }
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)(j * p.dil) * 128u;      // tap j = the slab shifted by j*dilation rows
+            const uint32_t b_addr = smem_u32(smem + b_ring_off + stage * kBBytesMax);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / 16; ++kk) {
+              const uint64_t adesc = make_smem_desc(a_addr + kk * 32u, 16u, 1024u);
+              const uint64_t bdesc = make_smem_desc(b_addr + kk * 32u, 16u, 1024u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.b_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(&slab_empty[cur_s]);
+          umma_commit(&tfull_bar[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      } else
       while (units.next(u)) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -525,6 +620,36 @@ static int pick_bn(int n, int multiple) {
   return best;
 }
 
+// rows of the resident activation slab for a (k, dilation) conv, or 0 when slab mode does not apply.  OPT-IN (W2L_SLAB=1):
+// measured on B200 it lowers power (SM clock under the cap 1.53 -> 1.66 GHz: a third less L2->smem traffic) but costs ~17 % more
+// tensor-pipe cycles -- a tap's view starts at a row that is not a multiple of the 8-row swizzle atom, and the operand fetch of
+// such a view is slower -- so the step is 43.3 ms instead of 40.8 (tools/ab.sh W2L_SLAB 0 1).  Kept as a validated experiment
+// (all parity tests pass with it on); the per-tap A tiles stay the default.
+static int slab_rows_for(int k, int dil) {
+  static const bool enabled = getenv("W2L_SLAB") && atoi(getenv("W2L_SLAB")) == 1;
+  const int rows = kBlockM + (k - 1) * dil;
+  return (enabled && rows <= 256) ? rows : 0;          // one TMA box holds at most 256 rows
+}
+
+// operand-ring geometry of a launch: slab mode (three slabs + a weight-tile ring) when it applies and fits, else the 4-stage A+B ring
+static void plan_rings(GemmParams& p, int k, int dil, bool allow_slab) {
+  p.ring_bytes = kStages * kStageBytes;
+  p.slab_rows = 0;
+  const int rows = allow_slab ? slab_rows_for(k, dil) : 0;
+  if (!rows) return;
+  const int slab_bytes = (rows * 128 + 1023) / 1024 * 1024;
+  for (int bs = kStages; bs >= 3; --bs) {
+    const size_t ring = (size_t)kSlabBufs * slab_bytes + (size_t)bs * kBBytesMax;
+    if (ring + 1024 + 256 + kAffBytes <= kGemmSmemMax) {
+      p.slab_rows = rows;
+      p.slab_bytes = slab_bytes;
+      p.b_stages = bs;
+      p.ring_bytes = (int32_t)ring;
+      return;
+    }
+  }
+}
+
 // fp32 scratch for the forward tail split, registered by the host (w2l_set_gemm_scratch): [4096 bytes of arrival counters][slots]
 static void* g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
@@ -552,15 +677,18 @@ static void plan_tail_split(GemmParams& p) {
 }
 
 template <int MODE>
-static int launch_gemm(const GemmParams& p, cudaStream_t st, int grid_override = 0) {
+static int launch_gemm(const GemmParams& p_in, cudaStream_t st, int grid_override = 0) {
+  GemmParams p = p_in;
+  if (p.ring_bytes == 0) p.ring_bytes = kStages * kStageBytes;      // launchers that do not plan rings: the A+B stage ring
   static bool configured = false;
   if (!configured) {
-    W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemMax));
     configured = true;
   }
   int grid = grid_override > 0 ? grid_override : (p.num_tiles < gemm_sms() ? p.num_tiles : gemm_sms());
   if (grid < 1) return W2L_OK;
-  conv_gemm_kernel<MODE><<<grid, kGemmThreads, kGemmSmem, st>>>(p);
+  const size_t smem_bytes = (size_t)p.ring_bytes + 1024 /*align*/ + 256 /*barriers*/ + kAffBytes;
+  conv_gemm_kernel<MODE><<<grid, kGemmThreads, smem_bytes, st>>>(p);
   return after_launch(MODE == MODE_FWD ? "conv_gemm_kernel<fwd>" : MODE == MODE_DGRAD ? "conv_gemm_kernel<dgrad>" : "conv_gemm_kernel<wgrad>");
 }
 
@@ -612,10 +740,11 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_fwd: ldy < Cout");
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  plan_rings(p, d->k, d->dilation, true);
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
-    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    uint32_t box[3] = {kBlockK, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
     rc = make_tensor_map(&p.tmA, x, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
@@ -739,11 +868,12 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   W2L_REQUIRE(d->ldy >= d->Cout_pad, "conv1d_dgrad_wt: dy row pitch %d < Cout_pad %d", d->ldy, d->Cout_pad);
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  plan_rings(p, d->k, d->dilation, true);
   {
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
     uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)d->T_out, (uint64_t)d->B};
     uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
-    uint32_t box[3] = {kBlockK, kBlockM, 1};
+    uint32_t box[3] = {kBlockK, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
     rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
