@@ -308,3 +308,19 @@ def test_bench_gpu_arm_fails_loudly_without_cuda():
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                        text=True, timeout=120)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_get_time_per_word_matches_reference_semantics():
+    from wav2letter_pytorch_b200.decoder import get_time_per_word
+    pred = "hi  there a"
+    offs = [3, 5, 9, 10, 12, 13, 15, 18, 20, 22, 30]
+    assert get_time_per_word(pred, offs, ratio=0.02) == [("hi", 3 * 0.02, 5 * 0.02), ("there", 12 * 0.02, 20 * 0.02), ("a", 30 * 0.02, 30 * 0.02)]
+    assert get_time_per_word("", []) == [] and get_time_per_word("  ", [1, 2]) == []
+    try:                                                       # the reference function itself, where its tree is mounted
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            ref = ref_loader.load_reference()
+            for p, o in ((pred, offs), ("a b", [0, 1, 2]), (" x", [4, 7]), ("ab", [1, 2])):
+                assert get_time_per_word(p, o, 0.5) == ref.decoder.get_time_per_word(p, o, 0.5)
+    except ImportError:
+        pass

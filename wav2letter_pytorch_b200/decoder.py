@@ -270,3 +270,25 @@ class PrefixBeamSearchLMDecoder(Decoder):
                                             self.lm_weigh, self.k, self.alpha, self.beta, self.prune, ">")
             return strings
         raise RuntimeError("Decoding with wrong shape: %s, expected either [Batch X Frames X Labels] or [Frames X Labels]" % str(probs.shape))
+
+
+def get_time_per_word(predictions, offsets, ratio=1.0):
+    """(word, start, end) for every word of a greedy transcript, from the per-character frame offsets that
+    ``GreedyDecoder.decode(..., return_offsets=True)`` returns (decoder.py:269-300; ``ratio`` = seconds per output frame).
+    As upstream, a word's end is the FIRST frame of its last character."""
+    assert len(predictions) == len(offsets)
+    words, current, start, end = [], "", -1, -1
+    for letter, offset in zip(predictions, offsets):
+        if letter == " ":
+            if current:
+                words.append((current, start, end))
+                current, start, end = "", -1, -1
+            continue
+        t = offset * ratio
+        if current:
+            current, end = current + letter, t
+        else:
+            current, start, end = letter, t, t
+    if current:
+        words.append((current, start, end))
+    return words
