@@ -29,6 +29,9 @@ def reserve_device_memory(device=None, gib=64, fraction=0.6):
     free, _total = torch.cuda.mem_get_info(device)
     n = min(int(gib) << 30, int(free * fraction))
     if n > 0:
-        block = torch.empty(n, dtype=torch.uint8, device=device)
-        del block
+        try:
+            block = torch.empty(n, dtype=torch.uint8, device=device)
+            del block
+        except RuntimeError:                      # not enough contiguous memory: run without the reservation
+            return 0
     return n
