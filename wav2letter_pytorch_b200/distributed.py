@@ -242,7 +242,7 @@ class PeerGradientReducer:
             smalls = self.pending_small
             dst = [self.arena[self.small_off + self.small_slices[id(p)][0]: self.small_off + self.small_slices[id(p)][0] + p.numel()]
                    for p in smalls]
-            src = [p.grad.reshape(-1) for p in smalls]
+            src = [dense_view(p.grad).reshape(-1) for p in smalls]     # views (depthwise weights are permuted over dense storage)
             self.arena[self.small_off:self.small_off + self.small_numel].zero_()
             torch._foreach_copy_(dst, src)
             self.comm.wait_stream(main)
