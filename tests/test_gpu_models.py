@@ -345,3 +345,36 @@ def test_jasper_nan_assert(pkg, golden):
         model.check_nan()
         model.nan_check = "off"
         model(bad, il)
+
+
+def test_gradient_accumulation_and_zero_grad_in_place(pkg):
+    """two backward passes into existing .grad tensors (gradient accumulation, zero_grad(set_to_none=False)): autograd adds the new
+    weight gradient on the compute stream right after backward() returns, so those wgrads must not run on the side stream"""
+    from wav2letter_pytorch_b200 import config, layers
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    cfg = config.compose(overrides=["model.mid_layers=3"]).model
+    for l in cfg.layers:
+        l["dropout"] = 0.0
+    torch.manual_seed(0)
+    model = Wav2Letter(cfg).cuda().train()
+    x, il, tg, tl = (t.cuda() for t in O.synthetic_batch(6, 4, seed=5))
+
+    def backward_once():
+        out, ol = model(x, il)
+        model.criterion(out.transpose(0, 1), tg, ol, tl).backward()
+
+    model.zero_grad(set_to_none=True)
+    backward_once()
+    torch.cuda.synchronize()
+    single = [p.grad.detach().clone() for p in model.parameters()]
+    backward_once()                                            # accumulates into the existing tensors
+    torch.cuda.synchronize()
+    for p, g1 in zip(model.parameters(), single):
+        if g1.abs().max() > 0:
+            assert rel_l2(p.grad, 2 * g1) < 2e-2
+    model.zero_grad(set_to_none=False)                         # grads stay allocated (zeros): the next backward adds in place
+    backward_once()
+    torch.cuda.synchronize()
+    for p, g1 in zip(model.parameters(), single):
+        if g1.abs().max() > 0:
+            assert rel_l2(p.grad, g1) < 2e-2

@@ -38,11 +38,13 @@ class WgradStream:
         return s
 
     @classmethod
-    def fork(cls, device):
+    def fork(cls, device, param=None):
         """Call after the producers of the wgrad operands were enqueued: the side stream waits for them.  Returns the side
-        stream, or None when disabled / outside a backward pass."""
+        stream, or None when disabled / outside a backward pass / when ``param`` already holds a gradient -- autograd then ADDS
+        the new gradient into it on the compute stream as soon as backward() returns (gradient accumulation,
+        ``zero_grad(set_to_none=False)``), so that wgrad has to be ordered on the compute stream."""
         task = torch._C._current_graph_task_id()
-        if not cls.enabled or task < 0:
+        if not cls.enabled or task < 0 or (param is not None and param.grad is not None):
             return None
         main, side = torch.cuda.current_stream(device), cls.side(device)
         side.wait_stream(main)
@@ -363,7 +365,7 @@ class ConvBNActFn(torch.autograd.Function):
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
                                   want_g=has_res, dz_rows=dz_rows, drop_mask=mask)
         dw = alloc_dw(conv, z.device)
-        side = WgradStream.fork(z.device)              # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
+        side = WgradStream.fork(z.device, conv.weight)   # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
@@ -404,7 +406,7 @@ class ResidualBranchFn(torch.autograd.Function):
         B, T, Co = z.shape
         dz, red, _ = F.bn_act_bwd(g.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, Co, 0, 0, F.ACT_NONE)
         dw = alloc_dw(conv, z.device)
-        side = WgradStream.fork(z.device)
+        side = WgradStream.fork(z.device, conv.weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
@@ -444,7 +446,7 @@ class ConvHeadFn(torch.autograd.Function):
         dl = F.log_softmax_bwd(dout.contiguous(), out, cp)            # bf16 [B,T,cout_pad], zero padded
         desc = conv_desc(conv, B, T, T, 0, ldy=cp)
         dw = alloc_dw(conv, xin.device)
-        side = WgradStream.fork(xin.device)
+        side = WgradStream.fork(xin.device, conv.weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
