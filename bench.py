@@ -416,7 +416,7 @@ def run_gpu_arm(args):
     }
     # the two HBM-side kernels BASELINE.json's metric names, timed live inside the same steps (CUDA events around the library call)
     line["hbm_kernels"] = {}
-    for tag, label in (("ctc_loss_raw", "ctc_prep+alpha+beta_grad+finish (CTC loss + gradient)"), ("greedy_decode", "greedy_argmax+compact")):
+    for tag, label in (("ctc_loss_raw", "ctc_prep + ctc_lattice (alpha || beta) + ctc_grad + ctc_finish (CTC loss + gradient)"), ("greedy_decode", "greedy_argmax+compact")):
         if all_ms.get(tag):
             gbs = timer.bytes[tag] / args.steps / (all_ms[tag] / 1e3) / 1e9
             line["hbm_kernels"][tag] = {"kernel": label, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
