@@ -156,6 +156,26 @@ def cpu_train_step_factory(mid_layers, B, seconds, seed=0):
     return step
 
 
+def config1_cpu_ms(mid_layers, reps=3):
+    """BASELINE configs[0] on the host: Wav2Letter default config, eval-mode forward + CTCLoss + greedy decode, batch 8,
+    synthetic 10 s utterances -- the oracle port of the reference's CPU path, best of ``reps`` after one warm-up."""
+    from oracle import w2l_oracle as O
+    specs = O.w2l_layer_specs(mid_layers)
+    sd = O.w2l_init_state_dict(specs, seed=0)
+    x, il, tg, tl, _texts = synthetic_batch(8, 10, seed=0)
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)
+    best = 1e30
+    with torch.no_grad():
+        for r in range(reps + 1):
+            t0 = time.perf_counter()
+            lp, ol = O.w2l_forward(x, il, sd, specs, training=False)
+            crit(lp.transpose(0, 1), tg, ol, tl)
+            O.greedy_decode(lp.numpy(), ol.numpy())
+            if r > 0:
+                best = min(best, time.perf_counter() - t0)
+    return best * 1e3
+
+
 def run_cpu_arm(args, as_reference):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -381,6 +401,34 @@ def run_gpu_arm(args):
                  "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s"}
         del m1, o1, r1
 
+    # ---- BASELINE configs[0] (the reference's own CPU-runnable case): forward + CTCLoss + greedy decode to strings, batch 8 x 10 s,
+    # eval mode, mid_layers 1 (literal default) and 20; ours on the GPU (host tensors in, strings out) next to the oracle port on the CPU
+    config1 = None
+    if world == 1 and not args.skip_cpu and args.model == "wav2letter":
+        try:
+            config1 = {"workload": "Wav2Letter default config, eval forward + CTCLoss + greedy decode (strings), B=8 x 10 s", "gpu_ms": {},
+                       "cpu_ms": {}, "cpu_cores": os.cpu_count()}
+            x1, il1, tg1, tl1, _t1 = synthetic_batch(8, 10, seed=0)
+            for mid in (1, 20):
+                m1, _o1, _r1 = build(mid, "wav2letter")
+                m1.eval()
+                best = 1e30
+                with torch.no_grad():
+                    for r in range(6):
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        out, ol = m1(x1.to(dev, non_blocking=True), il1.to(dev, non_blocking=True))
+                        m1.criterion(out.transpose(0, 1), tg1.to(dev), ol, tl1.to(dev)).item()
+                        m1.ctc_decoder.decode(out, ol)
+                        torch.cuda.synchronize()
+                        if r > 0:
+                            best = min(best, time.perf_counter() - t0)
+                config1["gpu_ms"][str(mid)] = best * 1e3
+                config1["cpu_ms"][str(mid)] = config1_cpu_ms(mid)
+                del m1
+        except Exception as e:  # noqa: BLE001  (a secondary table must never take the headline line down)
+            config1 = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -432,6 +480,8 @@ def run_gpu_arm(args):
         a = train_flops * BATCH / (tot / 1e3) / 1e12
         line["roofline"]["serialized"] = {"achieved": a, "frac": a / peaks["tf_sustained"], "kernel_ms_per_step": tot, "by_pass_ms": iso_ms,
                                           "note": "same launches with wgrad on the compute stream (no overlap): sum of per-launch CUDA-event spans"}
+    if config1:
+        line["config1"] = config1
     if extra:
         line["default_config"] = extra
     if world == 1 and not args.skip_cpu:
