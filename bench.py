@@ -81,41 +81,97 @@ def conv_flops_model(model, t_in):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed regions.  A thread polls NVML in-process every 10 ms (nvidia-smi's
+    start-up alone outlasts a short timed region); without NVML it reads a `nvidia-smi -lms 50` pipe.  Every sample carries a host
+    timestamp and only those inside a window handed to ``mark()`` (the host interval that brackets a timed region, GPU idle on both
+    sides) count: ``sm_mhz`` is their median."""
 
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index=0, pci_bus_id=None, period_s=0.010):
+        self.rows, self.windows = [], []               # rows: (host time, sm MHz, reason names)
+        self.gpu, self.bus, self.period = gpu_index, pci_bus_id, period_s
+        self.proc = self.thread = self.nvml = None
+        self.sm_max, self.source, self._stop = None, None, threading.Event()
+
+    # ---- NVML, in-process
+    def _nvml_open(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByPciBusId(self.bus.encode() if hasattr(self.bus, "encode") else self.bus) if self.bus else None
+        except Exception:  # noqa: BLE001
+            h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get(h))       # fail here, not in the thread
+        return nv, h, get
+
+    def _nvml_loop(self, nv, h, get):
+        while not self._stop.is_set():
+            try:
+                t = time.perf_counter()
+                sm, mask = int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get(h))
+                self.rows.append((t, sm, tuple(n for bit, n in self.REASONS if mask & bit)))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    # ---- nvidia-smi pipe
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            if len(r) >= 9 and r[1].replace(".", "").isdigit():
+                if r[2].replace(".", "").isdigit():
+                    self.sm_max = int(float(r[2]))
+                self.rows.append((time.perf_counter(), int(float(r[1])),
+                                  tuple(n for i, n in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                                        if r[5 + i].lower() == "active")))
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            args = self._nvml_open()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=args, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            pass
+        try:
+            sel = ["-i", str(self.bus or self.gpu)]
+            self.proc = subprocess.Popen(["nvidia-smi"] + sel + ["--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable (no NVML, no nvidia-smi)"], "samples": 0}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        self.thread.join(timeout=2)
+        rows = list(self.rows)
+        inside = [r for r in rows if any(a <= r[0] <= b for a, b in self.windows)]
+        sm = sorted(r[1] for r in inside)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted({n for r in inside for n in r[2]}),
+                "samples": len(inside), "samples_total": len(rows), "source": self.source,
+                "sm_mhz_min_max": [sm[0], sm[-1]] if sm else None,
+                "window": "samples inside the timed regions of this run (device-resident, serialized-roofline and e2e legs)"}
 
 
 def synthetic_batch(B, seconds, seed):
@@ -314,6 +370,11 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    props = torch.cuda.get_device_properties(local)
+    bus = None
+    if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):   # NVML/nvidia-smi order ignores CUDA_VISIBLE_DEVICES
+        bus = "%08X:%02X:%02X.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    sampler, sampling = ClockSampler(local, bus), [True]
     step_spread = []                                      # (min, median, max) per-step ms of every timed region, in call order
 
     def timed(model, opt, reducer, steps, warmup, from_host):
@@ -328,6 +389,7 @@ def run_gpu_arm(args):
             return 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
+        host_t0 = time.perf_counter()                     # GPU idle here (barrier above) and again after the barrier below
         e0.record()
         for it in range(steps):
             l = one_step(model, opt, reducer, batch(), it)
@@ -338,6 +400,8 @@ def run_gpu_arm(args):
             marks.append(m)
         e1.record()
         barrier()
+        if sampling[0]:
+            sampler.mark(host_t0, time.perf_counter())
         ms = e0.elapsed_time(e1) / steps
         per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         step_spread.append((min(per_step), sorted(per_step)[len(per_step) // 2], max(per_step)))
@@ -358,16 +422,14 @@ def run_gpu_arm(args):
 
     # ---- device-resident throughput (the headline `value`), conv kernels timed live with CUDA events
     timer = KernelTimer()
-    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                   # polls from here on; only samples inside the timed windows are kept
     timed(model, opt, reducer, 0, args.warmup, False)
     timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "ctc_loss_raw", "greedy_decode"])
     launches0 = _lib.launch_count()
-    if rank == 0:
-        sampler.start()
     seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     ms = timed(model, opt, reducer, args.steps, 0, False)
     new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0    # cudaMalloc calls inside the timed region
-    clocks = sampler.stop() if rank == 0 else None
     launches_total = _lib.launch_count() - launches0
     launches = launches_total // max(args.steps, 1)
     timer.unwrap()
@@ -389,6 +451,8 @@ def run_gpu_arm(args):
         iso_ms = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
     # ---- end to end: pinned host inputs in, loss out, every step
     ms_e2e = ms if args.profile else timed(model, opt, reducer, args.steps, 1, True)
+    sampling[0] = False                                   # the secondary tables below are launch-bound: not "under load"
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- the literal default config (mid_layers=1), reported beside the full stack
     extra = None

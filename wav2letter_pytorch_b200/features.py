@@ -98,10 +98,21 @@ class SpectrogramExtractor(torch.nn.Module):
         else:
             sigs = [torch.as_tensor(np.asarray(s) if not torch.is_tensor(s) else s, dtype=torch.float32).reshape(-1) for s in signals]
             lens = torch.tensor([s.numel() for s in sigs], dtype=torch.int32)
-            host = torch.zeros((len(sigs), int(lens.max())), dtype=torch.float32).pin_memory()
+            # pinned staging buffer, kept across calls (cudaHostAlloc per batch would cost more than the kernels); the previous
+            # upload must have finished before it is overwritten
+            need = (len(sigs), int(lens.max()))
+            stage = getattr(self, "_host_stage", None)
+            if stage is None or stage[0].numel() < need[0] * need[1]:
+                stage = [torch.zeros((need[0] * need[1],), dtype=torch.float32).pin_memory(), None]
+                self._host_stage = stage
+            if stage[1] is not None:
+                stage[1].synchronize()
+            host = stage[0][:need[0] * need[1]].view(need)          # contiguous [B, Lmax] view of the flat buffer
+            host.zero_()
             for i, s in enumerate(sigs):
                 host[i, :s.numel()] = s
             audio = host.to(dev, non_blocking=True)
+            stage[1] = torch.cuda.current_stream(dev).record_event()
         if int(lens.min()) <= self.n_fft // 2:
             raise RuntimeError("SpectrogramExtractor: every signal must be longer than n_fft/2 = %d samples (reflect padding, as torch.stft)"
                                % (self.n_fft // 2))
