@@ -171,13 +171,16 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
  * (jasper.py:318-341; the pointwise half is w2l_conv1d_* with k = 1).  Time-major bf16 activations, fp32 weights
  * stored [k, C]; zero padding `pad` on both sides.
  *   fwd:   y [B,T_out,C];  rows t >= out_lens[b] are written as 0 (the consumer MaskedConv1d's masked_fill)
- *   dgrad: dx [B,T,C] (stride 1 only); dy rows t >= dy_lens[b] are read as 0
+ *   dgrad: dx [B,T,C] (stride 1; w2l_depthwise_dgrad_strided for stride > 1); dy rows t >= dy_lens[b] are read as 0
  *   wgrad: dw [k,C] fp32, ACCUMULATED with atomics (zero it first)
  */
 int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
                       int32_t stride, int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream);
 int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
                         int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+/* backward-data of a depthwise conv with stride >= 1 (gather over the taps that land on a multiple of the stride) */
+int w2l_depthwise_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
 int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
                         int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
 
@@ -189,6 +192,14 @@ int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int
  * k=1, stride=1 gives the plain padded time-major copy.  wav2letter.py:41 + the layer-0 unfold. */
 int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
                    int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream);
+/* Strided layers beyond the first (Conv1dBlock with stride > 1, wav2letter.py:24-38; strided JasperBlock, jasper.py:289-298):
+ * time-major bf16 x [B, x_rows, C] -> out [B, T_out, k*C] with out[b, t, j*C + c] = x[b, t*stride + j*dilation - pad_left, c]
+ * (zero outside [0, x_rows)); the conv then runs as a k=1 GEMM over `out` with weights stored [Cout, k, Cin]. */
+int w2l_im2col_tm(const void* x, void* out, int32_t B, int32_t x_rows, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                  int32_t dilation, int32_t pad_left, void* stream);
+/* adjoint of w2l_im2col_tm: dcol [B, T_out, k*C] bf16 -> dx [B, x_rows, C] bf16 (every row written; fp32 accumulation) */
+int w2l_col2im_tm(const void* dcol, void* dx, int32_t B, int32_t x_rows, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                  int32_t dilation, int32_t pad_left, void* stream);
 /* time-major bf16/fp32 [B, T, C] (row pitch ld) -> NCW fp32 [B, C, T] */
 int w2l_tm_to_ncw(const void* x, int32_t x_dtype, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows,
                   int32_t x_row_offset, int32_t ld, void* stream);

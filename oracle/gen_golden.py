@@ -209,6 +209,77 @@ def gen_jasper_dense(ref):
     np.savez_compressed(os.path.join(OUT, "jasper_dense.npz"), **_np(out))
 
 
+def gen_strided(ref):
+    """stride > 1 beyond the first layer (not in the shipped yamls, but legal in both model classes): a Wav2Letter with two
+    stride-2 blocks, and a Jasper with a strided dense block (repeat 2: every repeat strides, jasper.py:193-208) and a strided
+    separable block; strided Jasper blocks carry no residual (the reference's add would fail on the time dimension)."""
+    import json
+    torch.manual_seed(9)
+    cfg = rl.reference_model_cfg("wav2letter", mid_layers=3, dropout=-1)
+    small = [dict(output_size=64, kernel_size=11, stride=2, dilation=1, dropout=-1),
+             dict(output_size=128, kernel_size=7, stride=2, dilation=1, dropout=-1),
+             dict(output_size=64, kernel_size=5, stride=1, dilation=2, dropout=-1)]
+    cfg["layers"] = rl.to_attr(small)
+    model = ref.wav2letter.Wav2Letter(cfg)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 64, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tl = torch.tensor([14, 9, 5], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 14), dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "layers": np.array([[l["output_size"], l["kernel_size"], l["stride"],
+                                                                     l["dilation"]] for l in small])}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update(_sd(model, "sd1:"))
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["eval:decoded"] = np.array(model.ctc_decoder.decode(o, ol))
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "w2l_strided.npz"), **_np(out))
+
+    torch.manual_seed(10)
+    blocks = [dict(layer_size=64, kernel_size=10, stride=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=64, kernel_size=5, stride=2, residual=False, separable=False, repeat=2),
+              dict(layer_size=128, kernel_size=6, stride=2, residual=False, separable=True, repeat=1),
+              dict(layer_size=64, kernel_size=3, stride=1, residual=True, separable=False, repeat=2)]
+    cfg = rl.reference_model_cfg("jasper", mid_layers=4, dropout=0, jasper_blocks=blocks)
+    model = ref.jasper.Jasper(cfg)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 64, 401)
+    il = torch.tensor([401, 320, 241], dtype=torch.int32)
+    tl = torch.tensor([10, 7, 4], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 10), dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+        x[n, :, il[n]:] = 0
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "blocks_json": np.array(json.dumps(blocks))}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update({k: v for k, v in _sd(model, "sd1:").items() if "running" in k or "num_batches" in k})
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "jasper_strided.npz"), **_np(out))
+
+
 def gen_ctc(ref):
     g = torch.Generator().manual_seed(5)
     crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)    # base_asr_models.py:23
@@ -312,10 +383,10 @@ def gen_beam(ref):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd"):      # regenerate one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd", "strided"):      # regenerate one fixture without touching the others
         ref = rl.load_reference()
         torch.set_num_threads(1)
-        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd}[sys.argv[1]](ref)
+        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd, "strided": gen_strided}[sys.argv[1]](ref)
         return
     ref = rl.load_reference()
     torch.set_num_threads(1)
@@ -324,6 +395,7 @@ def main():
     gen_w2l(ref)
     gen_jasper(ref)
     gen_jasper_dense(ref)
+    gen_strided(ref)
     gen_ctc(ref)
     gen_novograd(ref)
     gen_features(ref)

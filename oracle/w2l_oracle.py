@@ -496,6 +496,60 @@ def w2l_forward_bf16emu(x, input_lengths, sd, specs, training=True):
     return lp, (None if input_lengths is None else input_lengths // scaling)
 
 
+# ------------------------------------------------------------------------------------------------ strided layers: unfold / fold
+# Restatement (numpy loops, the same index arithmetic the CUDA kernels use) of the layout steps around a strided layer that is
+# not the first one: the strided Conv1d of wav2letter.py:35-36 / jasper.py:96-105 equals a k=1 contraction of the unfolded rows
+# with the weights stored [Cout, k, Cin]; backward-data is the fold (adjoint) of the column gradient.
+def im2col_tm(x, T_out, k, stride, dilation, pad_left):
+    """x [B, rows, C] (time-major) -> [B, T_out, k*C], out[b, t, j*C + c] = x[b, t*stride + j*dilation - pad_left, c] (0 outside)."""
+    x = np.asarray(x)
+    B, rows, C = x.shape
+    out = np.zeros((B, T_out, k * C), dtype=x.dtype)
+    for t in range(T_out):
+        for j in range(k):
+            r = t * stride + j * dilation - pad_left
+            if 0 <= r < rows:
+                out[:, t, j * C:(j + 1) * C] = x[:, r, :]
+    return out
+
+
+def col2im_tm(dcol, x_rows, C, k, stride, dilation, pad_left):
+    """adjoint of ``im2col_tm`` in gather form: for every input row the taps j with r + pad_left - j*dilation = t*stride."""
+    dcol = np.asarray(dcol)
+    B, T_out, _ = dcol.shape
+    dx = np.zeros((B, x_rows, C), dtype=np.float64)
+    for r in range(x_rows):
+        for j in range(k):
+            u = r + pad_left - j * dilation
+            if u < 0:
+                break
+            t = u // stride
+            if t * stride != u or t >= T_out:
+                continue
+            dx[:, r, :] += dcol[:, t, j * C:(j + 1) * C]
+    return dx
+
+
+def depthwise_dgrad_strided(dy, w_kc, x_rows, stride, dilation, pad, dy_lens=None):
+    """dy [B, T_out, C], w [k, C] -> dx [B, x_rows, C]: backward-data of a depthwise conv with stride >= 1 (gather form)."""
+    dy, w_kc = np.asarray(dy, dtype=np.float64), np.asarray(w_kc, dtype=np.float64)
+    B, T_out, C = dy.shape
+    k = w_kc.shape[0]
+    dx = np.zeros((B, x_rows, C), dtype=np.float64)
+    for b in range(B):
+        lim = T_out if dy_lens is None else min(T_out, max(0, int(dy_lens[b])))
+        for u in range(x_rows):
+            for j in range(k):
+                v = u + pad - j * dilation
+                if v < 0:
+                    break
+                t = v // stride
+                if t * stride != v or t >= lim:
+                    continue
+                dx[b, u] += dy[b, t] * w_kc[j]
+    return dx
+
+
 # ------------------------------------------------------------------------------------------------ feature front-end
 def mel_filterbank_slaney(sample_rate, n_fft, n_mels, fmin=0.0, fmax=None):
     """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (htk=False, norm='slaney'), the call at

@@ -95,8 +95,11 @@ SIGNATURES = {
     "w2l_conv1d_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_depthwise_fwd": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_depthwise_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr, c_ptr]),
+    "w2l_depthwise_dgrad_strided": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_depthwise_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_im2col_ncw": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "w2l_im2col_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_col2im_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_tm_to_ncw": (c_i32, [c_ptr, c_i32, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_ncw_to_tm": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_bn_stats": (c_i32, [c_ptr, c_i64, c_i32, c_ptr, c_ptr]),

@@ -4,6 +4,7 @@
 // neighbouring threads in y walk neighbouring rows, so the k input rows each thread reads are L1 hits after the first.
 //   fwd   y[b,t,c]  = sum_j x[b, t*s + j*d - p, c] * w[j,c]            rows >= out_lens[b] written as 0 (consumer's mask)
 //   dgrad dx[b,u,c] = sum_j dy[b, u + p - j*d, c] * w[j,c]             (stride 1), dy rows >= dy_lens[b] read as 0
+//         dx[b,u,c] = sum_{j : s | u + p - j*d} dy[b, (u + p - j*d)/s, c] * w[j,c]      (stride s > 1, own kernel)
 //   wgrad dw[j,c]  += sum_{b,t} dy[b,t,c] * x[b, t*s + j*d - p, c]
 // Weights are fp32 [k, C] (the [C,1,k] Parameter is a permuted view of this storage).
 #include "common.cuh"
@@ -55,6 +56,42 @@ depthwise_corr_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
     q.w = pack_bf16x2(acc[6], acc[7]);
   }
   *reinterpret_cast<uint4*>(out + (int64_t)r * C + c) = q;
+}
+
+// Backward-data of a STRIDED depthwise conv (a strided separable block that is not the encoder's first one):
+// dx[b,u,c] = sum over taps j with u + pad - j*dil = t*stride, 0 <= t < min(y_rows, dy_lens[b]), of dy[b,t,c] * w[j,c].
+__global__ void __launch_bounds__(256)
+depthwise_dgrad_strided_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int B,
+                               int x_rows, int y_rows, int C, int k, int stride, int dil, int pad, const int32_t* __restrict__ dy_lens) {
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r = blockIdx.y * 8 + threadIdx.y;            // flattened (b, u)
+  if (c >= C || r >= B * x_rows) return;
+  const int b = r / x_rows, u = r - b * x_rows;
+  const int lim = dy_lens ? min(y_rows, max(0, dy_lens[b])) : y_rows;
+  const __nv_bfloat16* gb = dy + (int64_t)b * y_rows * C + c;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int j = 0; j < k; ++j) {
+    const int v = u + pad - j * dil;
+    if (v < 0) break;                                    // v only decreases with j
+    const int t = v / stride;
+    if (t * stride != v || t >= lim) continue;
+    float g[8];
+    dw_unpack8(__ldg(reinterpret_cast<const uint4*>(gb + (int64_t)t * C)), g);
+    const float* wj = w + (int64_t)j * C + c;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wj)), w1 = __ldg(reinterpret_cast<const float4*>(wj) + 1);
+    acc[0] = fmaf(g[0], w0.x, acc[0]); acc[1] = fmaf(g[1], w0.y, acc[1]);
+    acc[2] = fmaf(g[2], w0.z, acc[2]); acc[3] = fmaf(g[3], w0.w, acc[3]);
+    acc[4] = fmaf(g[4], w1.x, acc[4]); acc[5] = fmaf(g[5], w1.y, acc[5]);
+    acc[6] = fmaf(g[6], w1.z, acc[6]); acc[7] = fmaf(g[7], w1.w, acc[7]);
+  }
+  uint4 q;
+  q.x = pack_bf16x2(acc[0], acc[1]);
+  q.y = pack_bf16x2(acc[2], acc[3]);
+  q.z = pack_bf16x2(acc[4], acc[5]);
+  q.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(dx + (int64_t)r * C + c) = q;
 }
 
 // block (32, 8); grid (channel blocks, row chunks, tap groups of 4)
@@ -144,6 +181,18 @@ int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int
   depthwise_corr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T_out, T, C, k, 1,
                                                                   dilation, pad - (k - 1) * dilation, 1, dy_lens, nullptr);
   return after_launch("depthwise_corr_kernel<dgrad>");
+}
+
+int w2l_depthwise_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  using namespace w2l;
+  int rc = dw_check("depthwise_dgrad_strided", B, T, C, T_out, k, stride, dilation, pad);
+  if (rc) return rc;
+  W2L_REQUIRE(dy && w && dx, "depthwise_dgrad_strided: null pointer");
+  dim3 grid((C / 8 + 31) / 32, (B * T + 7) / 8), block(32, 8);
+  depthwise_dgrad_strided_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T, T_out, C, k,
+                                                                           stride, dilation, pad, dy_lens);
+  return after_launch("depthwise_dgrad_strided_kernel");
 }
 
 int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,

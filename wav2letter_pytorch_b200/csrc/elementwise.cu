@@ -113,6 +113,50 @@ __global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
 }
 
+// ---------------------------------------------------------------- time-major unfold / fold (strided layers beyond the first)
+// out[b, t, j*C + c] = x[b, t*stride + j*dil - pad_left, c] (zero outside [0, x_rows)): the strided conv becomes a k=1 GEMM over
+// out.  One thread moves 16 bytes (8 channels) of one (row, tap).
+__global__ void im2col_tm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int x_rows, int C,
+                                 int T_out, int k, int stride, int dil, int pad_left) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)B * T_out * k * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    int64_t q = i / c8;
+    const int j = (int)(q % k);
+    q /= k;
+    const int t = (int)(q % T_out), b = (int)(q / T_out);
+    const int r = t * stride + j * dil - pad_left;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r >= 0 && r < x_rows) v = __ldg(reinterpret_cast<const uint4*>(x + ((int64_t)b * x_rows + r) * C + c));
+    *reinterpret_cast<uint4*>(out + (((int64_t)b * T_out + t) * k + j) * C + c) = v;
+  }
+}
+// The adjoint (gather form, fp32 accumulation, no atomics): dx[b, r, c] = sum over taps j with (r + pad_left - j*dil) = t*stride,
+// 0 <= t < T_out, of dcol[b, t, j*C + c].
+__global__ void col2im_tm_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int B, int x_rows, int C,
+                                 int T_out, int k, int stride, int dil, int pad_left) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)B * x_rows * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c8) * 8;
+    const int64_t q = i / c8;
+    const int r = (int)(q % x_rows), b = (int)(q / x_rows);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < k; ++j) {
+      const int u = r + pad_left - j * dil;
+      if (u < 0) break;                                   // u only decreases with j
+      const int t = u / stride;
+      if (t * stride != u || t >= T_out) continue;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dcol + (((int64_t)b * T_out + t) * k + j) * C + c)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+    *reinterpret_cast<uint4*>(dx + ((int64_t)b * x_rows + r) * C + c) = pack8(acc);
+  }
+}
+
 // time-major (bf16 | f32) -> NCW fp32, 32x32 shared-memory transpose
 template <typename TIn>
 __global__ void tm_to_ncw_kernel(const TIn* __restrict__ x, float* __restrict__ out, int T, int C, int64_t x_batch_stride,
@@ -686,6 +730,32 @@ int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, i
   im2col_ncw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, F, T, rows, k, stride, dilation, pad_left,
                                                                pad_mode, lens, span, pitch);
   return after_launch("im2col_ncw_kernel");
+}
+
+int w2l_im2col_tm(const void* x, void* out, int32_t B, int32_t x_rows, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                  int32_t dilation, int32_t pad_left, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(x && out, "im2col_tm: null pointer");
+  W2L_REQUIRE(B >= 1 && x_rows >= 1 && T_out >= 1 && k >= 1 && stride >= 1 && dilation >= 1 && pad_left >= 0, "im2col_tm: bad geometry");
+  W2L_REQUIRE(C >= 8 && C % 8 == 0, "im2col_tm: C=%d must be a multiple of 8", C);
+  W2L_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "im2col_tm: pointers must be 16-byte aligned");
+  const int64_t total = (int64_t)B * T_out * k * (C / 8);
+  im2col_tm_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, x_rows, C,
+                                                                         T_out, k, stride, dilation, pad_left);
+  return after_launch("im2col_tm_kernel");
+}
+
+int w2l_col2im_tm(const void* dcol, void* dx, int32_t B, int32_t x_rows, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                  int32_t dilation, int32_t pad_left, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(dcol && dx, "col2im_tm: null pointer");
+  W2L_REQUIRE(B >= 1 && x_rows >= 1 && T_out >= 1 && k >= 1 && stride >= 1 && dilation >= 1 && pad_left >= 0, "col2im_tm: bad geometry");
+  W2L_REQUIRE(C >= 8 && C % 8 == 0, "col2im_tm: C=%d must be a multiple of 8", C);
+  W2L_REQUIRE(((uintptr_t)dcol & 15) == 0 && ((uintptr_t)dx & 15) == 0, "col2im_tm: pointers must be 16-byte aligned");
+  const int64_t total = (int64_t)B * x_rows * (C / 8);
+  col2im_tm_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, B, x_rows, C,
+                                                                         T_out, k, stride, dilation, pad_left);
+  return after_launch("col2im_tm_kernel");
 }
 
 int w2l_ncw_to_tm(const float* x, void* out, int32_t B, int32_t C, int32_t T, void* stream) {

@@ -166,12 +166,16 @@ def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
     return y
 
 
-def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None):
+def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None, stride=1):
     B, T_out, C = dy.shape
     dx = torch.empty((B, T, C), dtype=torch.bfloat16, device=dy.device)
     with torch.cuda.device(dy.device):
-        _lib.check(_lib.load().w2l_depthwise_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens), _stream()),
-                   "depthwise_dgrad")
+        if stride == 1:
+            _lib.check(_lib.load().w2l_depthwise_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens),
+                                                       _stream()), "depthwise_dgrad")
+        else:
+            _lib.check(_lib.load().w2l_depthwise_dgrad_strided(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, stride, dilation, pad,
+                                                               _ptr(dy_lens), _stream()), "depthwise_dgrad_strided")
     return dx
 
 
@@ -196,6 +200,33 @@ def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
         _lib.check(_lib.load().w2l_im2col_ncw(_ptr(x), _ptr(out), B, F, T, rows, k, stride, dilation, pad_left, pad_mode, _ptr(lens),
                                               _stream()), "im2col_ncw")
     return out
+
+
+def im2col_tm(x, T_out, k, stride, dilation, pad_left):
+    """time-major bf16 x [B, x_rows, C] -> [B, T_out, k*C] with out[b, t, j*C + c] = x[b, t*stride + j*dilation - pad_left, c]
+    (zero outside the buffer): the unfold in front of a strided layer that is not the first one."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise RuntimeError("im2col_tm: contiguous bf16 [B, rows, C] required")
+    B, rows, C = x.shape
+    out = torch.empty((B, T_out, k * C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_im2col_tm(_ptr(x), _ptr(out), B, rows, C, T_out, k, stride, dilation, pad_left, _stream()), "im2col_tm")
+    return out
+
+
+def col2im_tm(dcol, x_rows, C, k, stride, dilation, pad_left):
+    """adjoint of ``im2col_tm``: dcol [B, T_out, k*C] bf16 -> dx [B, x_rows, C] bf16."""
+    _need_cuda(dcol)
+    if dcol.dtype != torch.bfloat16 or not dcol.is_contiguous():
+        raise RuntimeError("col2im_tm: contiguous bf16 [B, T_out, k*C] required")
+    B, T_out, KC = dcol.shape
+    if KC != k * C:
+        raise RuntimeError("col2im_tm: dcol has %d columns, expected k*C = %d" % (KC, k * C))
+    dx = torch.empty((B, x_rows, C), dtype=torch.bfloat16, device=dcol.device)
+    with torch.cuda.device(dcol.device):
+        _lib.check(_lib.load().w2l_col2im_tm(_ptr(dcol), _ptr(dx), B, x_rows, C, T_out, k, stride, dilation, pad_left, _stream()), "col2im_tm")
+    return dx
 
 
 def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):

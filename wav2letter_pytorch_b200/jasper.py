@@ -21,7 +21,7 @@ import torch.nn as nn
 from . import functional as F
 from .base_asr_models import ConvCTCASR
 from .layers import (BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, DepthwiseFn, DepthwiseParams, ResidualBranchFn,
-                     conv_bn_act_eval, conv_desc)
+                     UnfoldTmFn, conv_bn_act_eval, conv_desc)
 
 jasper_activations = {"hardtanh": nn.Hardtanh, "relu": nn.ReLU, "selu": nn.SELU}
 
@@ -178,11 +178,12 @@ class JasperBlock(nn.Module):
                 h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask)        # masked, zero padded, unfolded
             else:
                 h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask)              # masked time-major copy
-        elif first.conv.stride[0] != 1:
-            raise NotImplementedError("stride > 1 is only supported on the first Jasper block")
         block_in, res_pair = h, None
         training = self.training
         if self.res is not None:
+            if self.stride != 1:                                                 # jasper.py:400-415: the 1x1 residual conv is not strided
+                raise RuntimeError("JasperBlock: a strided block cannot carry a residual branch (the reference's `out + res_out` "
+                                   "fails on the time dimension, jasper.py:412)")
             rconv, rbn = self.res[0][0].conv, self.res[0][1]
             if training:
                 res_pair = ResidualBranchFn.apply(block_in, rconv.weight, rbn.weight, rbn.bias, rconv, rbn)
@@ -206,6 +207,9 @@ class JasperBlock(nn.Module):
                     h = F.depthwise_fwd(h, dc.storage(), t_dw, k, s, d, p, dmask)
                 t = t_dw
             if conv.unfold:
+                if not (from_ncw and r == 0):                                    # (the encoder's first conv was unfolded from NCW above)
+                    k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
+                    h = UnfoldTmFn.apply(h, (t + 2 * p - d * (k - 1) - 1) // s + 1, k, s, d, p)
                 t_out, x_off = h.shape[1], 0
             else:
                 k, d, p = conv.kernel_size[0], conv.dilation[0], conv.padding[0]

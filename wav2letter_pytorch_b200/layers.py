@@ -265,10 +265,24 @@ class DepthwiseFn(torch.autograd.Function):
         dw = F.depthwise_wgrad(dy, xin, k, s, d, p, ctx.out_lens)
         dx = None
         if ctx.needs_input_grad[0]:
-            if s != 1:
-                raise NotImplementedError("depthwise backward-data with stride > 1 (only the first block is strided)")
-            dx = F.depthwise_dgrad(dy, conv.storage(), xin.shape[1], k, d, p, ctx.out_lens)
+            dx = F.depthwise_dgrad(dy, conv.storage(), xin.shape[1], k, d, p, ctx.out_lens, stride=s)
         return dx, conv.grad_view(dw), None, None, None
+
+
+class UnfoldTmFn(torch.autograd.Function):
+    """Unfold in front of a strided layer that is not the first one (Conv1dBlock stride > 1, wav2letter.py:24-38; a strided dense
+    JasperBlock, jasper.py:289-298): time-major bf16 [B, rows, C] -> [B, T_out, k*C]; the conv then runs as a k=1 GEMM with weights
+    stored [Cout, k, Cin] (``ConvParams(unfold=True)``).  backward folds the column gradient back onto the rows (fp32 sums)."""
+
+    @staticmethod
+    def forward(ctx, xin, T_out, k, stride, dilation, pad_left):
+        ctx.geo = (xin.shape[1], xin.shape[2], k, stride, dilation, pad_left)
+        return F.im2col_tm(xin, T_out, k, stride, dilation, pad_left)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        rows, C, k, stride, dilation, pad_left = ctx.geo
+        return F.col2im_tm(dcol.contiguous(), rows, C, k, stride, dilation, pad_left), None, None, None, None, None
 
 
 class BatchNormParams(nn.Module):

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import functional as F
 from .base_asr_models import ConvCTCASR
-from .layers import BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, conv_bn_act_eval
+from .layers import BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, UnfoldTmFn, conv_bn_act_eval
 
 
 def reflect_padding(input_channels, kernel, stride, dilation):
@@ -65,8 +65,8 @@ class Conv1dBlock(nn.Module):
                 xin = F.im2col_ncw(xin, t_out, self.kernel_size[0], self.stride, self.dilation, pl, F.PAD_REFLECT)
             else:
                 xin = F.im2col_ncw(xin, t_in + pl + pr, 1, 1, 1, pl, F.PAD_REFLECT)
-        elif conv.unfold:
-            raise NotImplementedError("stride > 1 is only supported on the first block (as in the shipped configs)")
+        elif conv.unfold:                                 # strided block inside the stack: unfold the halo-carrying input
+            xin = UnfoldTmFn.apply(xin, t_out, self.kernel_size[0], self.stride, self.dilation, 0)
         if not self.has_bn:
             return ConvHeadFn.apply(xin, conv.weight, conv.bias, conv, 0), t_out
         geo = {"T_out": t_out, "x_row_offset": 0, "out_pad": self.next_pad, "drop_p": self.drop_p if self.training else 0.0,
