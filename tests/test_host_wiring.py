@@ -1,0 +1,145 @@
+"""Host logic above the C ABI, on a machine WITHOUT a GPU: the drop-in modules (Wav2Letter, Jasper, CTCLoss) run their real
+autograd Functions, descriptor geometry, halo / mask / unfold / residual wiring and length bookkeeping, with every C-ABI call
+answered by the torch restatement in tests/_host_sim.py (test infrastructure; the product itself has no CPU path).  Results are
+held to the same fixtures frozen from the unmodified reference, and the same tolerances, as the `-m gpu` model tests: a wiring
+error (a dropped residual gradient, a wrong row offset, a halo folded onto the wrong row) shows up as an error of order 1."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import _host_sim
+from oracle import w2l_oracle as O
+
+
+def rel_l2(a, b):
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _load_sd(model, g, prefix):
+    sd = {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("running" in m or "num_batches" in m or True for m in missing)
+    return sd
+
+
+@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided"])
+def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture):
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    _host_sim.install(monkeypatch)
+    g = golden(fixture)
+    layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
+    cfg = config.compose(overrides=["model.mid_layers=3"]).model
+    cfg["layers"] = config.to_attr(layers)
+    model = Wav2Letter(cfg)
+    assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0:"))
+    _load_sd(model, g, "sd0:")
+    model.train()
+    x, il, tg, tl = (torch.from_numpy(g[k]) for k in ("x", "il", "tg", "tl"))
+    out, ol = model(x, il)
+    assert out.shape == tuple(g["train:out"].shape) and out.dtype == torch.float32 and out.is_contiguous()
+    assert ol.dtype == il.dtype and np.array_equal(ol.numpy(), g["train:out_len"])
+    assert rel_l2(out.detach(), g["train:out"]) < 2e-2
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    assert abs(loss.item() - float(g["train:loss"])) < 2e-2 * abs(float(g["train:loss"]))
+    loss.backward()
+    # yard-stick: the oracle with the stated bf16 storage points emulated (see tests/test_gpu_models.py for the rationale)
+    specs, cin = [], 64
+    for l in layers:
+        specs.append(dict(cin=cin, cout=l["output_size"], k=l["kernel_size"], stride=l["stride"], dilation=l["dilation"], dropout=-1,
+                          bn=True, act=True))
+        cin = l["output_size"]
+    specs.append(dict(cin=cin, cout=29, k=1, stride=1, dilation=1, dropout=-1, bn=False, act=False))
+    sd = {k[4:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("sd0:")}
+    emu_params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    e_out, e_ol = O.w2l_forward_bf16emu(x, il, sd, specs, True)
+    e_loss = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(e_out.transpose(0, 1), tg, e_ol, tl)
+    e_loss.backward()
+    assert rel_l2(out.detach(), e_out.detach()) < 5e-3
+    assert abs(loss.item() - e_loss.item()) < 2e-3 * abs(e_loss.item())
+    for name, p in model.named_parameters():
+        ref = g["train:grad:" + name]
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        if name.endswith("conv1.bias") and "conv1d_3" not in name:      # analytically zero under train-mode BN
+            assert p.grad.abs().max().item() == 0.0
+            continue
+        emu = emu_params[name].grad
+        err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
+        assert err_emu < 3e-2, (name, err_emu)
+        assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
+    sd1 = {k[4:]: g[k] for k in g.files if k.startswith("sd1:")}
+    for k, v in model.state_dict().items():
+        if "running" in k:
+            np.testing.assert_allclose(v.numpy(), sd1[k], rtol=2e-2, atol=2e-3, err_msg=k)
+        if "num_batches_tracked" in k:
+            assert int(v) == int(sd1[k])
+    _load_sd(model, g, "sd1:")
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    assert rel_l2(o, g["eval:out"]) < 2e-2 and np.array_equal(ol.numpy(), g["eval:out_len"])
+    assert model.scaling_factor == int(g["scaling_factor"])
+
+
+@pytest.mark.parametrize("fixture,seed,emu_tol", [("jasper_dense", 4, 0.15), ("jasper_small", 2, 0.15), ("jasper_strided", 10, 0.25)])
+def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, seed, emu_tol):
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    _host_sim.install(monkeypatch)
+    g = golden(fixture)
+    blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    torch.manual_seed(seed)
+    model = Jasper(cfg)
+    for k in g.files:                                                   # seeded construction == the reference's
+        if k.startswith("sd_init:"):
+            assert np.array_equal(model.state_dict()[k[8:]].numpy(), g[k]), k
+    assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0:"))
+    _load_sd(model, g, "sd0:")
+    model.train()
+    x, il, tg, tl = (torch.from_numpy(g[k]) for k in ("x", "il", "tg", "tl"))
+    out, ol = model(x, il)
+    assert np.array_equal(ol.numpy(), g["train:out_len"]) and ol.dtype == torch.int64
+    assert rel_l2(out.detach(), g["train:out"]) < 2e-2
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    assert abs(loss.item() - float(g["train:loss"])) < 2e-2 * abs(float(g["train:loss"]))
+    loss.backward()
+    specs = O.jasper_block_specs(blocks)
+    sd = {k[4:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("sd0:")}
+    emu_params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    e_out, e_ol = O.jasper_forward(x, il, sd, specs, True, emu=True)
+    e_loss = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(e_out.transpose(0, 1), tg, e_ol, tl)
+    e_loss.backward()
+    assert rel_l2(out.detach(), e_out.detach()) < 5e-3 and abs(loss.item() - e_loss.item()) < 2e-3 * abs(e_loss.item())
+    for name, p in model.named_parameters():
+        ref = torch.from_numpy(g["train:grad:" + name])
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        emu = emu_params[name].grad
+        err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
+        assert err_emu < emu_tol, (name, err_emu)
+        assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
+    for k in g.files:
+        if k.startswith("sd1:") and "running" in k:
+            np.testing.assert_allclose(model.state_dict()[k[4:]].numpy(), g[k], rtol=2e-2, atol=2e-3, err_msg=k)
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    assert rel_l2(o, g["eval:out"]) < 2e-2 and abs(float(o.sum(-1).mean()) - 1.0) < 1e-5    # probabilities in eval
+
+
+def test_strided_jasper_block_with_residual_raises(monkeypatch):
+    """jasper.py:412: `out + res_out` cannot be formed when the block strides (the 1x1 residual conv does not)"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    _host_sim.install(monkeypatch)
+    blocks = [dict(layer_size=64, kernel_size=5, stride=1, residual=False, separable=False, repeat=1, dropout=0),
+              dict(layer_size=64, kernel_size=5, stride=2, residual=True, separable=False, repeat=1, dropout=0)]
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=2"]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    model = Jasper(cfg).train()
+    with pytest.raises(RuntimeError):
+        model(torch.randn(2, 64, 50), torch.tensor([50, 40]))

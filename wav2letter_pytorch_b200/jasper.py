@@ -264,8 +264,7 @@ class Jasper(ConvCTCASR):
     def forward(self, xs, input_lengths):
         """[B, F, T] fp32 CUDA, lengths [B] -> ([B, T', n_labels] log-probs in training / probabilities in eval --
         the reference's behaviour, jasper.py:470-473 -- , output lengths int64 [B])."""
-        if not xs.is_cuda:
-            raise RuntimeError("Jasper: CUDA input required (this build has no CPU path)")
+        F._need_cuda(xs)                                 # RuntimeError on a CPU tensor: this build has no CPU path
         blocks = list(self.jasper_encoder)
         rows, out_lens = None, None
         if input_lengths is not None:

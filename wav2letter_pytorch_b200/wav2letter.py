@@ -132,8 +132,7 @@ class Wav2Letter(ConvCTCASR):
         return self._scaling_factor
 
     def forward(self, x, input_lengths=None):
-        if not x.is_cuda:
-            raise RuntimeError("Wav2Letter: CUDA input required (this build has no CPU path)")
+        F._need_cuda(x)                                  # RuntimeError on a CPU tensor: this build has no CPU path
         t = x.shape[2]
         h, first = x, True
         for block in self.conv1ds.children():
