@@ -69,7 +69,8 @@ def test_depthwise_dgrad_strided(F, B, T, C, k, s, d, pad):
         b = torch.empty_like(a)
         F._lib.check(lib.w2l_depthwise_dgrad_strided(F._ptr(dy.cuda()), F._ptr(w.cuda()), F._ptr(b), B, T, C, T_out, k, 1, d, pad,
                                                      F._ptr(lens.cuda()), F._stream()), "depthwise_dgrad_strided")
-        assert torch.equal(a, b)
+        # same sums, taps visited in the opposite order: equal up to one bf16 rounding of an fp32 sum
+        torch.testing.assert_close(a.float(), b.float(), rtol=2.0 ** -7, atol=2.0 ** -9 * float(a.float().abs().max()))
 
 
 def test_unfold_fn_gradient(F):
