@@ -109,3 +109,22 @@ def test_strided_block_with_residual_raises(pkg):
     x = torch.randn(2, 64, 50, device="cuda")
     with pytest.raises(RuntimeError):
         model(x, torch.tensor([50, 40], device="cuda"))
+
+
+def test_head_block_standalone(pkg):
+    """Conv1dBlock(..., bn=False, activation_use=False) called on its own (wav2letter.py:40-47, 69): conv + bias, NCW in / NCW out"""
+    from wav2letter_pytorch_b200.wav2letter import Conv1dBlock
+    torch.manual_seed(0)
+    blk = Conv1dBlock(64, 29, (1,), 1, bn=False, activation_use=False).cuda()
+    x = torch.randn(2, 64, 37)
+    y = blk(x.cuda())
+    w, b = blk.conv1.weight.detach().cpu(), blk.conv1.bias.detach().cpu()
+    want = torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b)
+    assert y.shape == (2, 29, 37) and y.dtype == torch.float32
+    assert float((y.detach().cpu() - want).norm() / want.norm()) < 1e-5
+    g = torch.randn(y.shape)
+    y.backward(g.cuda())
+    wref, bref = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), wref, bref).backward(g)
+    assert float((blk.conv1.weight.grad.cpu() - wref.grad).norm() / wref.grad.norm()) < 1e-2
+    assert float((blk.conv1.bias.grad.cpu() - bref.grad).norm() / bref.grad.norm()) < 1e-2

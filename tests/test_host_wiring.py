@@ -20,8 +20,8 @@ def rel_l2(a, b):
 
 def _load_sd(model, g, prefix):
     sd = {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    assert not unexpected and all("running" in m or "num_batches" in m or True for m in missing)
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
     return sd
 
 
@@ -143,3 +143,23 @@ def test_strided_jasper_block_with_residual_raises(monkeypatch):
     model = Jasper(cfg).train()
     with pytest.raises(RuntimeError):
         model(torch.randn(2, 64, 50), torch.tensor([50, 40]))
+
+
+def test_head_block_standalone(monkeypatch):
+    """Conv1dBlock(..., bn=False, activation_use=False) called on its own (wav2letter.py:40-47, 69): conv + bias, NCW in / NCW out"""
+    from wav2letter_pytorch_b200.wav2letter import Conv1dBlock
+    _host_sim.install(monkeypatch)
+    torch.manual_seed(0)
+    blk = Conv1dBlock(64, 29, (1,), 1, bn=False, activation_use=False)
+    x = torch.randn(2, 64, 37)
+    y = blk(x)
+    w, b = blk.conv1.weight.detach(), blk.conv1.bias.detach()
+    want = torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), b)
+    assert y.shape == (2, 29, 37) and y.dtype == torch.float32
+    assert rel_l2(y.detach(), want) < 1e-5
+    g = torch.randn(y.shape)
+    y.backward(g)
+    wref = w.clone().requires_grad_(True)
+    bref = b.clone().requires_grad_(True)
+    torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), wref, bref).backward(g)
+    assert rel_l2(blk.conv1.weight.grad, wref.grad) < 1e-2 and rel_l2(blk.conv1.bias.grad, bref.grad) < 1e-2

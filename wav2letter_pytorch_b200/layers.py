@@ -430,8 +430,9 @@ class ResidualBranchFn(torch.autograd.Function):
 
 
 class ConvHeadFn(torch.autograd.Function):
-    """k=1 conv with bias to the label logits (fp32), then log_softmax / softmax (wav2letter.py:66,86-87;
-    jasper.py:433,468-473).  Returns [B, T, n_labels] fp32 contiguous."""
+    """k=1 conv with bias to the label logits (fp32), then log_softmax (mode 0) / softmax (mode 1) (wav2letter.py:66,86-87;
+    jasper.py:433,468-473), or the raw logits (mode 2: the head block called on its own).  Returns [B, T, n_labels] fp32
+    contiguous."""
 
     @staticmethod
     def forward(ctx, xin, weight, bias, conv, mode, nan_flag=None):
@@ -443,7 +444,7 @@ class ConvHeadFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
-        out = F.log_softmax(logits, Co, mode, nan_flag)
+        out = logits[..., :Co].contiguous() if mode == 2 else F.log_softmax(logits, Co, mode, nan_flag)     # 2: raw logits
         ctx.conv, ctx.mode = conv, mode
         ctx.has_bias = bias is not None
         ctx.save_for_backward(xin, out)
@@ -453,11 +454,11 @@ class ConvHeadFn(torch.autograd.Function):
     def backward(ctx, dout):
         xin, out = ctx.saved_tensors
         conv = ctx.conv
-        if ctx.mode != 0:
+        if ctx.mode == 1:
             raise NotImplementedError("backward through the eval-mode softmax head is not supported")
         B, T, _ = xin.shape
         Co, cp = conv.out_channels, conv.cout_pad
-        dl = F.log_softmax_bwd(dout.contiguous(), out, cp)            # bf16 [B,T,cout_pad], zero padded
+        dl = F.log_softmax_bwd(dout.contiguous(), out, cp, fused_identity=ctx.mode == 2)    # bf16 [B,T,cout_pad], zero padded
         desc = conv_desc(conv, B, T, T, 0, ldy=cp)
         dw = alloc_dw(conv, xin.device)
         side = WgradStream.fork(xin.device, conv.weight)

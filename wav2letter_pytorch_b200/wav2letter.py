@@ -54,9 +54,10 @@ class Conv1dBlock(nn.Module):
         return float(self.drop_out_prob) if self.drop_out_prob != -1 and self.drop_out_prob > 0 else 0.0
 
     # ---- time-major fast path (used by Wav2Letter.forward)
-    def forward_tm(self, xin, t_in, from_ncw):
+    def forward_tm(self, xin, t_in, from_ncw, head_mode=0):
         """xin: NCW fp32 [B,C,T] when ``from_ncw`` (first block) else time-major bf16 already carrying this block's
-        reflection halo ([B, pl+T+pr, C]).  Returns the next block's padded input (or log-prob scores for the head)."""
+        reflection halo ([B, pl+T+pr, C]).  Returns the next block's padded input (or, for the head, fp32 scores [B,T',labels]:
+        log-probs when ``head_mode`` is 0, raw logits when 2)."""
         conv = self.conv1
         t_out = self.out_rows(t_in)
         pl, pr = self.pad_lr
@@ -68,7 +69,9 @@ class Conv1dBlock(nn.Module):
         elif conv.unfold:                                 # strided block inside the stack: unfold the halo-carrying input
             xin = UnfoldTmFn.apply(xin, t_out, self.kernel_size[0], self.stride, self.dilation, 0)
         if not self.has_bn:
-            return ConvHeadFn.apply(xin, conv.weight, conv.bias, conv, 0), t_out
+            if self.activation_use or self.drop_p > 0:
+                raise NotImplementedError("a block without BatchNorm is implemented as the bias-only head (activation_use=False, no dropout)")
+            return ConvHeadFn.apply(xin, conv.weight, conv.bias, conv, head_mode), t_out
         geo = {"T_out": t_out, "x_row_offset": 0, "out_pad": self.next_pad, "drop_p": self.drop_p if self.training else 0.0,
                "act": F.ACT_CLAMP20 if self.activation_use else F.ACT_NONE}
         if self.training:
@@ -82,11 +85,11 @@ class Conv1dBlock(nn.Module):
     def forward(self, xs):
         saved, self.next_pad = self.next_pad, (0, 0)
         try:
-            y, t_out = self.forward_tm(xs, xs.shape[2], from_ncw=True)
+            y, t_out = self.forward_tm(xs, xs.shape[2], from_ncw=True, head_mode=2)
         finally:
             self.next_pad = saved
-        if not self.has_bn:                  # head: logits are not exposed on the fused path; undo the log_softmax is not possible
-            raise NotImplementedError("the bias-only head block is only available through Wav2Letter.forward")
+        if not self.has_bn:                  # the head on its own returns conv + bias (wav2letter.py:40-47 with bn=False, no clamp)
+            return y.transpose(1, 2)         # [B, labels, T'] view of the fp32 logits
         return _TmToNcw.apply(y, t_out, self.output_channels)
 
 
