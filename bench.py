@@ -237,15 +237,16 @@ def run_cpu_arm(args, as_reference):
     torch.set_num_threads(cores)
     B = args.cpu_batch
     step = cpu_train_step_factory(args.mid_layers, B, UTT_SEC)
-    for _ in range(args.warmup if as_reference else 0):
+    for _ in range(args.warmup if as_reference else 1):
         step()
-    n = args.steps if as_reference else 1
+    n = args.steps if as_reference else 4                 # cpu_baseline leg of the GPU arm: 1 warm-up + 4 steps, about 10 s of CPU work
     t0 = time.perf_counter()
     for _ in range(n):
         step()
     dt = (time.perf_counter() - t0) / n
     value = B * UTT_SEC / dt
-    sample = "oracle port (torch CPU fp32 + Python greedy loop): Wav2Letter mid_layers=%d train step, B=%d x %d s" % (args.mid_layers, B, UTT_SEC)
+    sample = ("oracle port (torch CPU fp32 + Python greedy loop): Wav2Letter mid_layers=%d train step, B=%d x %d s, mean of %d steps "
+              "after %d warm-up" % (args.mid_layers, B, UTT_SEC, n, args.warmup if as_reference else 1))
     return dict(value=value, unit="audio-s/s", cores=cores, kind="port", sample=sample, ms_per_step=dt * 1e3)
 
 
