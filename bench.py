@@ -207,7 +207,7 @@ def cpu_train_step_factory(mid_layers, B, seconds, seed=0):
         grads = torch.autograd.grad(loss, [sd[k] for k in names])
         with torch.no_grad():
             O.novograd_step([sd[k] for k in names], list(grads), state, lr=1e-3, weight_decay=1e-3)
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
