@@ -103,6 +103,9 @@ _gemm_scratch = {}
 def ensure_gemm_scratch(device):
     """Registers (once per process) the zero-filled fp32 scratch the forward GEMM uses to split its last wave of tiles along K."""
     if _gemm_scratch:
+        if device not in _gemm_scratch:                  # the library keeps per-process state for ONE device (scratch, kernel attributes)
+            raise RuntimeError("wav2letter_pytorch_b200 runs one process per GPU: this process already uses %s, got a tensor on %s"
+                               % (next(iter(_gemm_scratch)), device))
         return
     nbytes = 4096 + 148 * 128 * 256 * 4
     buf = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
