@@ -1,15 +1,17 @@
-"""TEST INFRASTRUCTURE, not product code: runs the *source text* of thread-independent CUDA kernels on the host.
+"""TEST INFRASTRUCTURE, not product code: runs the *source text* of the library's CUDA-core kernels on the host.
 
-A kernel whose threads never talk to each other (no shared memory, barriers, shuffles or atomics) is a plain C++ function of
-(blockIdx, threadIdx).  ``build()`` cuts such kernels -- and the ``__device__`` helpers they call -- verbatim out of the
-``.cu`` / ``.cuh`` files under wav2letter_pytorch_b200/csrc, puts a small shim in front (thread-local blockIdx / threadIdx,
-``__ldg``; the vector types and bf16 conversions are CUDA's own headers, which compile for the host), adds one launcher per
-kernel that walks the grid sequentially, compiles the lot with g++ and loads it through ctypes.  The index arithmetic, masks,
-tap loops and bf16 roundings that execute are therefore exactly the ones nvcc compiles for sm_100a; what is NOT covered is
-everything device-specific (launch geometry computed by the C wrappers, alignment faults, memory-model effects).
+``build()`` takes whole ``namespace w2l { ... }`` sections out of the ``.cu`` files under wav2letter_pytorch_b200/csrc --
+kernels, ``__device__`` helpers, constants and structs exactly as nvcc sees them -- compiles them with g++ against
+tests/kernel_emu_runtime.h (a fiber-per-CUDA-thread stand-in for blocks, warps, shared memory, barriers, shuffles and
+atomics; CUDA's own vector-type and bf16 headers compile for the host) and adds one launcher per requested kernel, loaded
+through ctypes.  Functions written in inline PTX cannot be compiled for the host: the caller names them in ``drop`` and
+supplies host replacements in ``extra`` (each replacement cites the PTX it stands for).
 
-Used by tests/test_kernel_emu.py so that kernels added when no GPU session was available are still executed, against the
-oracle, before they first meet hardware.  Nothing under wav2letter_pytorch_b200/ imports this module."""
+What executes is therefore the kernels' own index arithmetic, masks, reductions, synchronisation protocol and roundings;
+what is NOT covered is everything device-specific (launch geometry chosen by the C wrappers, alignment faults, memory
+ordering, the approximate SFU functions, tensor cores / TMA / TMEM -- conv_gemm.cu is out of reach by construction).
+
+Used by tests/test_kernel_emu*.py.  Nothing under wav2letter_pytorch_b200/ imports this module."""
 import ctypes
 import hashlib
 import os
@@ -19,133 +21,156 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "wav2letter_pytorch_b200", "csrc")
+HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
 
-SHIM = r"""
-#include <cuda_runtime.h>
-#include <cuda_bf16.h>
-#include <cstdint>
-#include <cmath>
-#include <algorithm>
-using std::min;
-using std::max;
-#define __launch_bounds__(...)
-static thread_local uint3 emu_tid, emu_bid;
-static thread_local dim3 emu_bdim, emu_gdim;
-#define threadIdx emu_tid
-#define blockIdx emu_bid
-#define blockDim emu_bdim
-#define gridDim emu_gdim
-template <typename T> static inline T __ldg(const T* p) { return *p; }
-#define W2L_PAD_ZERO 0
-#define W2L_PAD_REFLECT 1
-"""
 
-FORBIDDEN = ("__shared__", "__syncthreads", "__shfl", "atomic", "__syncwarp", "__ballot", "asm volatile", "asm(")
-
-
-def _match_brace(text, open_pos):
+def _match(text, open_pos, open_ch, close_ch):
     depth = 0
     for i in range(open_pos, len(text)):
-        if text[i] == "{":
+        if text[i] == open_ch:
             depth += 1
-        elif text[i] == "}":
+        elif text[i] == close_ch:
             depth -= 1
             if depth == 0:
                 return i
-    raise ValueError("unbalanced braces")
+    raise ValueError("unbalanced %s%s" % (open_ch, close_ch))
 
 
-def extract_function(path, name):
-    """the full definition (qualifiers, signature, body) of the function called ``name`` in ``path``"""
-    text = open(path).read()
+def _strip_comments(text):
+    text = re.sub(r"//[^\n]*", "", text)
+    return re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+
+
+def find_function(text, name):
+    """(start, end, parameter text) of the definition of ``name`` in ``text``: from its ``template <...>`` / ``__global__`` /
+    ``__device__`` qualifier to the closing brace of its body"""
     for m in re.finditer(r"\b%s\s*\(" % re.escape(name), text):
-        # walk back to the start of the declaration: the nearest preceding __global__ / __device__ qualifier
-        starts = [text.rfind(q, 0, m.start()) for q in ("__global__", "__device__")]
-        start = max(starts)
+        start = max(text.rfind(q, 0, m.start()) for q in ("__global__", "__device__"))
         if start < 0:
             continue
         between = text[start:m.start()]
-        if ";" in between or "}" in between or "{" in between:     # a call site, not the definition
+        if ";" in between or "}" in between or "{" in between:         # a call site, not the definition
             continue
-        depth, i = 1, m.end()
-        while depth:                                              # parameter lists may hold parentheses, e.g. float (&v)[8]
-            if text[i] == "(":
-                depth += 1
-            elif text[i] == ")":
-                depth -= 1
-            i += 1
-        close_paren = i - 1
+        close_paren = _match(text, m.end() - 1, "(", ")")
         brace = text.index("{", close_paren)
         if text[close_paren + 1:brace].strip():
             continue
-        end = _match_brace(text, brace)
-        return text[start:end + 1], text[m.end():close_paren]
-    raise KeyError("%s not found in %s" % (name, path))
+        tm = re.search(r"template\s*<[^>]*>\s*$", text[:start])
+        if tm:
+            start = tm.start()
+        return start, _match(text, brace, "{", "}") + 1, text[m.end():close_paren]
+    raise KeyError("definition of %s not found" % name)
+
+
+def namespace_sections(path):
+    """the contents of every ``namespace w2l { ... }`` section of a .cu file, concatenated"""
+    text = open(path).read()
+    out = []
+    for m in re.finditer(r"^namespace w2l \{", text, flags=re.M):
+        end = _match(text, m.end() - 1, "{", "}")
+        out.append(text[m.end():end])
+    if not out:
+        raise ValueError("no namespace w2l section in " + path)
+    return "\n".join(out)
 
 
 _CTYPES = (("int64_t", ctypes.c_int64), ("uint64_t", ctypes.c_uint64), ("int32_t", ctypes.c_int32), ("uint32_t", ctypes.c_uint32),
-           ("float", ctypes.c_float), ("int", ctypes.c_int))
+           ("size_t", ctypes.c_size_t), ("double", ctypes.c_double), ("float", ctypes.c_float), ("unsigned", ctypes.c_uint),
+           ("int", ctypes.c_int))
 
 
 def _params(param_text):
-    out = []
-    for p in param_text.split(","):
-        p = " ".join(p.split())
-        name = re.findall(r"[A-Za-z_][A-Za-z_0-9]*", p)[-1]
-        if "*" in p:
-            ct = ctypes.c_void_p
-        else:
-            ct = next(c for key, c in _CTYPES if re.search(r"\b%s\b" % key, p))
-        out.append((p, name, ct))
+    out, depth, cur = [], 0, ""
+    for ch in param_text + ",":
+        if ch == "," and depth == 0:
+            p = " ".join(cur.split())
+            cur = ""
+            if not p:
+                continue
+            name = re.findall(r"[A-Za-z_][A-Za-z_0-9]*", p)[-1]
+            if "*" in p:
+                ct = ctypes.c_void_p
+            else:
+                hit = [c for key, c in _CTYPES if re.search(r"\b%s\b" % key, p)]
+                if not hit:
+                    raise ValueError("kernel parameter %r: pass-by-value structs are not supported by the launcher" % p)
+                ct = hit[0]
+            out.append((p, name, ct))
+            continue
+        depth += ch in "(<["
+        depth -= ch in ")>]"
+        cur += ch
     return out
+
+
+class EmuError(RuntimeError):
+    pass
 
 
 class Emu:
     def __init__(self, lib, sigs):
         self._lib, self._sigs = lib, sigs
 
-    def launch(self, kernel, grid, block, *args):
-        """grid / block: int or up-to-3 tuples, as in ``kernel<<<grid, block>>>(args...)``; pointers are ints (data_ptr())"""
+    def launch(self, kernel, grid, block, *args, smem=0):
+        """as ``kernel<<<grid, block, smem>>>(args...)``: grid / block are ints or up-to-3 tuples, pointers are ints (data_ptr())"""
         g = tuple(grid) if isinstance(grid, (tuple, list)) else (grid,)
         b = tuple(block) if isinstance(block, (tuple, list)) else (block,)
         g, b = g + (1,) * (3 - len(g)), b + (1,) * (3 - len(b))
-        sig = self._sigs[kernel]
-        assert len(args) == len(sig), "%s takes %d arguments" % (kernel, len(sig))
-        conv = [ct(a if a is not None else 0) if ct is not ctypes.c_void_p else ctypes.c_void_p(a or 0) for a, (_, _, ct) in zip(args, sig)]
-        getattr(self._lib, "emu_" + kernel)(*(ctypes.c_int(v) for v in g + b), *conv)
+        sym, sig = self._sigs[kernel]
+        assert len(args) == len(sig), "%s takes %d arguments, got %d" % (kernel, len(sig), len(args))
+        conv = [ctypes.c_void_p(a or 0) if ct is ctypes.c_void_p else ct(a) for a, (_, _, ct) in zip(args, sig)]
+        fn = getattr(self._lib, sym)
+        fn.restype = ctypes.c_int
+        rc = fn(*(ctypes.c_int(int(v)) for v in g + b), ctypes.c_size_t(int(smem)), *conv)
+        if rc:
+            raise EmuError("%s: %s" % (kernel, {1: "deadlock: every live thread waits at a barrier / warp collective that cannot complete",
+                                                2: "a polling loop did not finish within the yield budget"}.get(rc, "error %d" % rc)))
 
 
-def build(kernels, helpers=()):
-    """kernels: [(file, kernel_name)], helpers: [(file, device_function_name)] in dependency order"""
-    parts, sigs = [SHIM], {}
-    for f, name in helpers:
-        src, _ = extract_function(os.path.join(CSRC, f), name)
-        parts.append(src)
-    for f, name in kernels:
-        src, ptext = extract_function(os.path.join(CSRC, f), name)
-        bad = [w for w in FORBIDDEN if w in src]
-        if bad:
-            raise ValueError("%s is not thread-independent (%s): it cannot be emulated by a sequential walk" % (name, bad))
+def build(sources, kernels, drop=(), extra="", helpers_from_common=("pack_bf16x2",)):
+    """sources: .cu file names under csrc/; kernels: kernel names (``name<float>`` instantiates a template); drop: functions cut
+    from the sources (inline PTX); extra: C++ placed inside namespace w2l ahead of the sources (their host replacements)"""
+    common = open(os.path.join(CSRC, "common.cuh")).read()
+    parts = ['#include "kernel_emu_runtime.h"', "namespace w2l {"]
+    for h in helpers_from_common:
+        s, e, _ = find_function(common, h)
+        parts.append(common[s:e])
+    parts.append(extra)
+    body = "\n".join(namespace_sections(os.path.join(CSRC, f)) for f in sources)
+    for name in drop:
+        s, e, _ = find_function(body, name)
+        body = body[:s] + body[e:]
+    # dynamic shared memory: `extern __shared__ [__align__(n)] T name[];` -> a typed view of the launch's buffer
+    body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][A-Za-z_0-9:]*)\s+([A-Za-z_][A-Za-z_0-9]*)\s*\[\s*\]\s*;",
+                  r"\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem);", body)
+    left = re.findall(r"\basm\b", _strip_comments(body))
+    if left:
+        raise ValueError("inline PTX left in %s: name the functions that hold it in `drop` and replace them in `extra`" % (sources,))
+    parts.append(body)
+    parts.append("}  // namespace w2l")
+    sigs = {}
+    for spec in kernels:
+        m = re.match(r"([A-Za-z_0-9]+)(?:<(.*)>)?$", spec)
+        name, targs = m.group(1), m.group(2)
+        s, e, ptext = find_function(body, name)
+        if "__global__" not in body[s:e].split("(")[0]:
+            raise ValueError("%s is not a __global__ function" % name)
+        if targs:
+            tnames = re.findall(r"(?:typename|class|int|bool)\s+([A-Za-z_][A-Za-z_0-9]*)", re.match(r"template\s*<([^>]*)>", body[s:e]).group(1))
+            for tn, ta in zip(tnames, [t.strip() for t in targs.split(",")]):
+                ptext = re.sub(r"\b%s\b" % tn, ta, ptext)
         ps = _params(ptext)
-        sigs[name] = ps
-        parts.append(src)
+        sym = "emu_" + re.sub(r"[^A-Za-z0-9_]", "_", spec)
+        sigs[spec] = (sym, ps)
         parts.append("""
-extern "C" void emu_%s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, int emu_bz, %s) {
-  emu_gdim = dim3(emu_gx, emu_gy, emu_gz);
-  emu_bdim = dim3(emu_bx, emu_by, emu_bz);
-  for (unsigned emu_z = 0; emu_z < (unsigned)emu_gz; ++emu_z) for (unsigned emu_y = 0; emu_y < (unsigned)emu_gy; ++emu_y)
-    for (unsigned emu_x = 0; emu_x < (unsigned)emu_gx; ++emu_x)
-      for (unsigned emu_c = 0; emu_c < (unsigned)emu_bz; ++emu_c) for (unsigned emu_b = 0; emu_b < (unsigned)emu_by; ++emu_b)
-        for (unsigned emu_a = 0; emu_a < (unsigned)emu_bx; ++emu_a) {
-      emu_bid = make_uint3(emu_x, emu_y, emu_z);
-      emu_tid = make_uint3(emu_a, emu_b, emu_c);
-      %s(%s);
-    }
+extern "C" int %s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, int emu_bz, size_t emu_smem%s) {
+  return emu::launch(emu_gx, emu_gy, emu_gz, emu_bx, emu_by, emu_bz, emu_smem, [=]() { w2l::%s(%s); });
 }
-""" % (name, ", ".join(p for p, _, _ in ps), name, ", ".join(n for _, n, _ in ps)))
+""" % (sym, "".join(", " + p for p, _, _ in ps), spec, ", ".join(n for _, n, _ in ps)))
     code = "\n".join(parts)
-    tag = hashlib.sha1(code.encode()).hexdigest()[:16]
+    runtime = open(os.path.join(HERE, "kernel_emu_runtime.h")).read()
+    tag = hashlib.sha1((code + runtime).encode()).hexdigest()[:16]
     out_dir = os.path.join(tempfile.gettempdir(), "w2l_kernel_emu")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "emu_%s.so" % tag)
@@ -154,10 +179,10 @@ extern "C" void emu_%s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_b
         with open(cpp, "w") as fh:
             fh.write(code)
         tmp = so + ".%d.tmp" % os.getpid()
-        r = subprocess.run(["g++", "-O1", "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, cpp, "-o", tmp],
+        r = subprocess.run(["g++", "-O1", "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + HERE, cpp, "-o", tmp],
                            capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("host compilation of the kernel sources failed:\n" + r.stderr[-4000:])
+            raise RuntimeError("host compilation of the kernel sources failed (%s):\n%s" % (cpp, r.stderr[-6000:]))
         os.replace(tmp, so)
     return Emu(ctypes.CDLL(so), sigs)
 

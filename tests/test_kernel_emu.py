@@ -15,12 +15,20 @@ from oracle import w2l_oracle as O
 pytestmark = pytest.mark.skipif(not KE.available(), reason="needs g++ and the CUDA headers")
 
 
+class _Both:
+    """the two builds behind one launch(): elementwise.cu and depthwise.cu are separate translation units in the library too"""
+
+    def __init__(self):
+        self.parts = [KE.build(["elementwise.cu"], ["im2col_tm_kernel", "col2im_tm_kernel"]),
+                      KE.build(["depthwise.cu"], ["depthwise_corr_kernel", "depthwise_dgrad_strided_kernel", "depthwise_wgrad_kernel"])]
+
+    def launch(self, kernel, *a, **k):
+        next(p for p in self.parts if kernel in p._sigs).launch(kernel, *a, **k)
+
+
 @pytest.fixture(scope="module")
 def emu():
-    return KE.build(
-        kernels=[("elementwise.cu", "im2col_tm_kernel"), ("elementwise.cu", "col2im_tm_kernel"),
-                 ("depthwise.cu", "depthwise_corr_kernel"), ("depthwise.cu", "depthwise_dgrad_strided_kernel")],
-        helpers=[("common.cuh", "pack_bf16x2"), ("elementwise.cu", "unpack8"), ("elementwise.cu", "pack8"), ("depthwise.cu", "dw_unpack8")])
+    return _Both()
 
 
 def grid_for(items, threads, sms=148):
@@ -122,6 +130,41 @@ def test_depthwise_fwd_source_is_adjoint_of_strided_dgrad(emu, B, T, C, k, s, d,
     assert abs(lhs - rhs) <= 2.0 ** -7 * norm
 
 
-def test_emulation_refuses_cooperative_kernels():
-    with pytest.raises(ValueError):
-        KE.build(kernels=[("depthwise.cu", "depthwise_wgrad_kernel")], helpers=[("depthwise.cu", "dw_unpack8")])
+@pytest.mark.parametrize("B,T,C,k,s,d,pad", [(2, 40, 64, 5, 1, 1, 2), (3, 41, 72, 6, 2, 1, 3), (2, 300, 264, 33, 1, 1, 16)])
+def test_depthwise_wgrad_source(emu, B, T, C, k, s, d, pad):
+    """the cooperative one (shared-memory reduction over the 8 row-threads, barrier, atomics into dw) under the fiber scheduler"""
+    gen = torch.Generator().manual_seed(T + k)
+    T_out = (T + 2 * pad - d * (k - 1) - 1) // s + 1
+    x, dy = bf16(torch.randn(B, T, C, generator=gen)), bf16(torch.randn(B, T_out, C, generator=gen))
+    lens = torch.tensor([T_out] + [max(1, T_out - 3 - i) for i in range(B - 1)], dtype=torch.int32)
+    rows = B * T_out
+    rpb = max(64, (rows + 147) // 148)                                          # csrc/depthwise.cu w2l_depthwise_wgrad
+    grid = ((C // 8 + 31) // 32, (rows + rpb - 1) // rpb, (k + 3) // 4)
+    for dl in (None, lens):
+        dw = torch.zeros(k, C)
+        emu.launch("depthwise_wgrad_kernel", grid, (32, 8), dy.data_ptr(), x.data_ptr(), dw.data_ptr(), B, T, T_out, C, k, s, d, pad,
+                   None if dl is None else dl.data_ptr(), rpb)
+        g = dy.float().clone()
+        if dl is not None:
+            for b in range(B):
+                g[b, int(dl[b]):] = 0
+        xr = x.float().transpose(1, 2).requires_grad_(False)
+        w = torch.zeros(C, 1, k, requires_grad=True)
+        torch.nn.functional.conv1d(xr, w, stride=s, padding=pad, dilation=d, groups=C).backward(g.transpose(1, 2))
+        want = w.grad[:, 0, :].t()
+        torch.testing.assert_close(dw, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
+
+
+def test_scheduler_reports_deadlock_instead_of_hanging():
+    """a barrier only half the block reaches: on hardware a hang, here an error"""
+    import tempfile
+    import os
+    src = "namespace w2l {\n__global__ void half_barrier_kernel(int* out) {\n  if (threadIdx.x < 16) { __syncthreads(); out[0] = 1; }\n"
+    src += "  else { __syncwarp(); out[1] = 1; }\n}\n}\n"
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "probe.cu")
+    open(path, "w").write(src)
+    e = KE.build([path], ["half_barrier_kernel"])
+    out = torch.zeros(2, dtype=torch.int32)
+    with pytest.raises(KE.EmuError, match="deadlock"):
+        e.launch("half_barrier_kernel", 1, 32, out.data_ptr())
