@@ -46,7 +46,7 @@ def find_function(text, name):
     """(start, end, parameter text) of the definition of ``name`` in ``text``: from its ``template <...>`` / ``__global__`` /
     ``__device__`` qualifier to the closing brace of its body"""
     for m in re.finditer(r"\b%s\s*\(" % re.escape(name), text):
-        start = max(text.rfind(q, 0, m.start()) for q in ("__global__", "__device__"))
+        start = max(text.rfind(q, 0, m.start()) for q in ("__global__", "__device__", "\nstatic "))
         if start < 0:
             continue
         between = text[start:m.start()]
@@ -128,9 +128,10 @@ class Emu:
                                                 2: "a polling loop did not finish within the yield budget"}.get(rc, "error %d" % rc)))
 
 
-def build(sources, kernels, drop=(), extra="", helpers_from_common=("pack_bf16x2",)):
+def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pack_bf16x2",)):
     """sources: .cu file names under csrc/; kernels: kernel names (``name<float>`` instantiates a template); drop: functions cut
-    from the sources (inline PTX); extra: C++ placed inside namespace w2l ahead of the sources (their host replacements)"""
+    from the sources (inline PTX, host functions that launch kernels); extra: C++ placed inside namespace w2l ahead of the sources
+    (host replacements for dropped functions); post: C++ appended at file scope (e.g. extern "C" access to host planning code)"""
     common = open(os.path.join(CSRC, "common.cuh")).read()
     parts = ['#include "kernel_emu_runtime.h"', "namespace w2l {"]
     for h in helpers_from_common:
@@ -149,6 +150,8 @@ def build(sources, kernels, drop=(), extra="", helpers_from_common=("pack_bf16x2
         raise ValueError("inline PTX left in %s: name the functions that hold it in `drop` and replace them in `extra`" % (sources,))
     parts.append(body)
     parts.append("}  // namespace w2l")
+    parts.append("using namespace w2l;       // launcher signatures name the library's own types")
+    parts.append(post)
     sigs = {}
     for spec in kernels:
         m = re.match(r"([A-Za-z_0-9]+)(?:<(.*)>)?$", spec)
@@ -184,7 +187,9 @@ extern "C" int %s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, in
         if r.returncode != 0:
             raise RuntimeError("host compilation of the kernel sources failed (%s):\n%s" % (cpp, r.stderr[-6000:]))
         os.replace(tmp, so)
-    return Emu(ctypes.CDLL(so), sigs)
+    emu = Emu(ctypes.CDLL(so), sigs)
+    emu.lib = emu._lib
+    return emu
 
 
 def available():

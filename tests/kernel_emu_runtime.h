@@ -41,7 +41,8 @@ struct Warp {
   uint64_t buf[32], snap[32];
   int arrived = 0, nlanes = 0;
   unsigned long gen = 0;
-  unsigned live_mask = 0;
+  unsigned live_mask = 0;       // lanes that have not exited
+  unsigned snap_mask = 0;       // live_mask when the last collective completed (a lane may exit before its peers read the snapshot)
 };
 
 static std::vector<Fiber> fibers;
@@ -76,6 +77,7 @@ static void release_warp_if_complete(Warp& w) {
   if (w.nlanes > 0 && w.arrived == w.nlanes) {
     w.arrived = 0;
     std::memcpy(w.snap, w.buf, sizeof(w.snap));
+    w.snap_mask = w.live_mask;
     ++w.gen;
     ++n_events;
   }
@@ -128,7 +130,7 @@ template <typename T>
 static inline T shfl_from(T v, int src) {
   const int lane = fibers[cur].lane, warp = fibers[cur].warp;
   const uint64_t* snap = warp_exchange(to_bits(v));
-  if (src < 0 || src > 31 || !((warps[warp].live_mask >> src) & 1u)) src = lane;     // inactive source: undefined on hardware
+  if (src < 0 || src > 31 || !((warps[warp].snap_mask >> src) & 1u)) src = lane;     // inactive source: undefined on hardware
   return from_bits<T>(snap[src]);
 }
 
@@ -240,13 +242,14 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
   const uint64_t* snap = emu::warp_exchange(pred ? 1 : 0);
   unsigned r = 0;
   for (int i = 0; i < 32; ++i)
-    if (((emu::warps[warp].live_mask & mask) >> i) & 1u) r |= (snap[i] ? 1u : 0u) << i;
+    if (((emu::warps[warp].snap_mask & mask) >> i) & 1u) r |= (snap[i] ? 1u : 0u) << i;
   return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) {
-  const unsigned live = emu::warps[emu::fibers[emu::cur].warp].live_mask & mask;
-  return (__ballot_sync(mask, pred) & live) == live;
+  const unsigned votes = __ballot_sync(mask, pred);
+  const unsigned live = emu::warps[emu::fibers[emu::cur].warp].snap_mask & mask;
+  return (votes & live) == live;
 }
 
 template <typename T>

@@ -155,16 +155,45 @@ def test_depthwise_wgrad_source(emu, B, T, C, k, s, d, pad):
         torch.testing.assert_close(dw, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))
 
 
+def _probe(src, kernel):
+    import os
+    import tempfile
+    path = os.path.join(tempfile.mkdtemp(), "probe.cu")
+    open(path, "w").write("namespace w2l {\n" + src + "\n}\n")
+    return KE.build([path], [kernel])
+
+
+def test_runtime_warp_collectives():
+    """the emulation's own shuffles / ballots: butterfly reduction, scan neighbours, partial last warp, lanes that exit right
+    after the last collective (their deposit must stay readable)"""
+    e = _probe("""
+__global__ void collectives_kernel(const float* x, float* red, float* up, float* down, unsigned* ballot, int n) {
+  const int i = threadIdx.x;
+  float m = x[i];
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  red[i] = m;
+  up[i] = __shfl_up_sync(0xffffffffu, x[i], 1);
+  down[i] = __shfl_down_sync(0xffffffffu, x[i], 2);
+  ballot[i] = __ballot_sync(0xffffffffu, x[i] > 10.f);
+}""", "collectives_kernel")
+    n = 80                                                               # two full warps and a 16-lane one
+    x = torch.randn(n, generator=torch.Generator().manual_seed(0)) * 20
+    red, up, down = torch.zeros(n), torch.zeros(n), torch.zeros(n)
+    ballot = torch.zeros(n, dtype=torch.int32)
+    e.launch("collectives_kernel", 1, n, x.data_ptr(), red.data_ptr(), up.data_ptr(), down.data_ptr(), ballot.data_ptr(), n)
+    for w0 in (0, 32, 64):
+        w1 = min(n, w0 + 32)
+        assert (red[w0:w1] == x[w0:w1].max()).all()
+        assert up[w0] == x[w0] and torch.equal(up[w0 + 1:w1], x[w0:w1 - 1])
+        assert torch.equal(down[w0:w1 - 2], x[w0 + 2:w1]) and torch.equal(down[w1 - 2:w1], x[w1 - 2:w1])
+        want = sum(1 << j for j in range(w1 - w0) if x[w0 + j] > 10)
+        assert all((int(b) & 0xFFFFFFFF) == want for b in ballot[w0:w1])
+
+
 def test_scheduler_reports_deadlock_instead_of_hanging():
     """a barrier only half the block reaches: on hardware a hang, here an error"""
-    import tempfile
-    import os
-    src = "namespace w2l {\n__global__ void half_barrier_kernel(int* out) {\n  if (threadIdx.x < 16) { __syncthreads(); out[0] = 1; }\n"
-    src += "  else { __syncwarp(); out[1] = 1; }\n}\n}\n"
-    d = tempfile.mkdtemp()
-    path = os.path.join(d, "probe.cu")
-    open(path, "w").write(src)
-    e = KE.build([path], ["half_barrier_kernel"])
+    e = _probe("__global__ void half_barrier_kernel(int* out) {\n  if (threadIdx.x < 16) { __syncthreads(); out[0] = 1; }\n"
+               "  else { __syncwarp(); out[1] = 1; }\n}", "half_barrier_kernel")
     out = torch.zeros(2, dtype=torch.int32)
     with pytest.raises(KE.EmuError, match="deadlock"):
         e.launch("half_barrier_kernel", 1, 32, out.data_ptr())
