@@ -1,0 +1,429 @@
+"""TEST INFRASTRUCTURE ONLY -- ``wav2letter_pytorch_b200.functional`` entry points answered by the library's own CUDA-core
+kernels executed on the host (tests/_kernel_emu.py), on CPU tensors.
+
+Every function below has the signature of its namesake in functional.py and repeats, launch for launch, what the C wrapper
+behind it does (grid / block / shared-memory arithmetic cited per function); the kernels themselves are compiled from the
+.cu sources.  ``install(monkeypatch)`` layers these over tests/_host_sim.py, so that the real modules run on a machine
+without a GPU with ONLY the tcgen05 GEMMs restated in torch -- layout changes, BatchNorm statistics / apply / backward,
+dropout, halos, masks, depthwise convs, log_softmax, CTC and greedy decode are the shipped kernel code.
+
+Nothing under wav2letter_pytorch_b200/ imports this module; the `-m gpu` suite never uses it."""
+import ctypes
+import functools
+
+import torch
+
+import _kernel_emu as KE
+
+BF16 = torch.bfloat16
+SMS = 148
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _grid_for(items, threads):
+    """csrc/elementwise.cu grid_for"""
+    return int(max(1, min((items + threads - 1) // threads, SMS * 16)))
+
+
+def _rows_per_block_for(rows, col_blocks):
+    """csrc/elementwise.cu rows_per_block_for"""
+    target = max(1, SMS * 8 // max(col_blocks, 1))
+    return int(max(32, (rows + target - 1) // target))
+
+
+_BN_VARIANTS = ["%d, %s, %s" % (a, d, r) for a in (0, 1, 2) for d in ("false", "true") for r in ("false", "true")]
+
+
+@functools.lru_cache(maxsize=None)
+def elementwise():
+    kernels = ["im2col_ncw_kernel", "im2col_tm_kernel", "col2im_tm_kernel", "tm_to_ncw_kernel<__nv_bfloat16>", "tm_to_ncw_kernel<float>",
+               "bn_stats_kernel", "bn_finalize_kernel", "log_softmax_kernel", "log_softmax_bwd_kernel", "colsum_kernel", "cast_bf16_kernel",
+               "lens_chain_kernel", "reflect_halo_kernel", "pack_wt_kernel"]
+    for v in _BN_VARIANTS:
+        kernels += ["bn_act_pad_kernel<%s>" % v, "bn_act_bwd_reduce_kernel<%s>" % v, "bn_act_bwd_apply_kernel<%s>" % v]
+    return KE.build(["elementwise.cu"], kernels)
+
+
+@functools.lru_cache(maxsize=None)
+def depthwise():
+    return KE.build(["depthwise.cu"], ["depthwise_corr_kernel", "depthwise_dgrad_strided_kernel", "depthwise_wgrad_kernel"])
+
+
+@functools.lru_cache(maxsize=None)
+def decode():
+    return KE.build(["decode.cu"], ["greedy_argmax_kernel", "greedy_compact_kernel"])
+
+
+# host stand-ins for the inline PTX of csrc/ctc.cu (file:line of what each replaces)
+CTC_PTX = r"""
+static inline float fast_ex2(float x) { return std::exp2(x); }                                   // ctc.cu:36  ex2.approx.ftz.f32
+static inline float fast_lg2(float x) { return std::log2(x); }                                   // ctc.cu:41  lg2.approx.ftz.f32
+static inline void cp_async4(void* smem, const void* gmem) { std::memcpy(smem, gmem, 4); }       // ctc.cu:58  cp.async.ca 4 B (eager)
+static inline void cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }     // ctc.cu:61  cp.async.cg 16 B (eager)
+static inline void cp_async_commit() {}                                                          // ctc.cu:64
+template <int N> static inline void cp_async_wait() {}                                           // ctc.cu:65
+static inline void slot_put(float4* slot, float v0, float v1, int tag) {                         // ctc.cu:292 st.volatile.shared.v4
+  *slot = make_float4(v0, v1, __int_as_float(tag), 0.f);
+}
+static inline float4 slot_load(const float4* slot) {                                             // ctc.cu:300 ld.volatile.shared.v4
+  emu::yield_poll();                       // a poll lets the producing warp run (the hardware's warps run concurrently)
+  return *slot;
+}
+"""
+CTC_POST = r"""
+extern "C" int emu_ctc_plan(long long N, long long T, long long S, long long C, long long* out) {
+  w2l::CtcPlan p;
+  if (!w2l::make_plan(N, T, S, C, &p)) return 1;
+  long long v[] = {p.R, p.threads, p.Lp, p.Cp, p.parallel, (long long)p.off_lp2, (long long)p.off_alpha, (long long)p.off_aoff,
+                   (long long)p.off_beta, (long long)p.off_boff, (long long)p.off_meta, (long long)p.total, w2l::kRing, w2l::kBlk,
+                   w2l::kGradFrames, (long long)sizeof(w2l::CtcMeta)};
+  for (int i = 0; i < 16; ++i) out[i] = v[i];
+  return 0;
+}
+"""
+
+
+@functools.lru_cache(maxsize=None)
+def ctc():
+    kernels = ["ctc_prep_kernel", "ctc_grad_kernel", "ctc_finish_kernel"]
+    for r in (2, 4, 8):
+        kernels += ["ctc_lattice_kernel<%d>" % r, "ctc_alpha_kernel<%d>" % r, "ctc_beta_grad_kernel<%d>" % r]
+    return KE.build(["ctc.cu"], kernels, drop=["fast_ex2", "fast_lg2", "cp_async4", "cp_async16", "cp_async_commit", "cp_async_wait",
+                                               "slot_put", "slot_load", "launch_ctc"], extra=CTC_PTX, post=CTC_POST)
+
+
+# ------------------------------------------------------------------------------------------------ layout (elementwise.cu)
+def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
+    """w2l_im2col_ncw (elementwise.cu:713-733)"""
+    x = x.contiguous().float()
+    B, F, T = x.shape
+    out = torch.full((B, rows, k * F), float("nan"), dtype=BF16)
+    span = 31 * stride + (k - 1) * dilation + 1
+    pitch = span | 1
+    lens = None if lens is None else lens.to(torch.int32).contiguous()
+    elementwise().launch("im2col_ncw_kernel", ((rows + 31) // 32, B), 256, _p(x), _p(out), F, T, rows, k, stride, dilation, pad_left, pad_mode,
+                         _p(lens), span, pitch, smem=F * pitch * 4)
+    return out
+
+
+def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
+    """w2l_tm_to_ncw (elementwise.cu:765-777)"""
+    x = x.contiguous()
+    B, rows, ld = x.shape
+    out = torch.full((B, C, T), float("nan"))
+    name = "tm_to_ncw_kernel<__nv_bfloat16>" if x.dtype == BF16 else "tm_to_ncw_kernel<float>"
+    elementwise().launch(name, ((T + 31) // 32, (C + 31) // 32, B), (32, 8), _p(x), _p(out), T, C, rows * ld, x_row_offset, ld)
+    return out
+
+
+def im2col_tm(x, T_out, k, stride, dilation, pad_left):
+    """w2l_im2col_tm (elementwise.cu:735-746)"""
+    assert x.dtype == BF16 and x.is_contiguous()
+    B, rows, C = x.shape
+    out = torch.full((B, T_out, k * C), float("nan"), dtype=BF16)
+    elementwise().launch("im2col_tm_kernel", _grid_for(B * T_out * k * (C // 8), 256), 256, _p(x), _p(out), B, rows, C, T_out, k, stride,
+                         dilation, pad_left)
+    return out
+
+
+def col2im_tm(dcol, x_rows, C, k, stride, dilation, pad_left):
+    """w2l_col2im_tm (elementwise.cu:748-759)"""
+    assert dcol.dtype == BF16 and dcol.is_contiguous()
+    B, T_out, _ = dcol.shape
+    dx = torch.full((B, x_rows, C), float("nan"), dtype=BF16)
+    elementwise().launch("col2im_tm_kernel", _grid_for(B * x_rows * (C // 8), 256), 256, _p(dcol), _p(dx), B, x_rows, C, T_out, k, stride,
+                         dilation, pad_left)
+    return dx
+
+
+def cast_bf16(src, dst=None):
+    """w2l_cast_bf16 (elementwise.cu:889-896)"""
+    src = src.contiguous().float()
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=BF16)
+    assert dst.is_contiguous()
+    n = src.numel()
+    if n:
+        elementwise().launch("cast_bf16_kernel", _grid_for(n // 8 + 1, 256), 256, _p(src), _p(dst), n)
+    return dst
+
+
+def pack_wt(w_store, wt, cout, cin):
+    """w2l_pack_wt (elementwise.cu:949-956)"""
+    w_store = w_store.contiguous()
+    k = w_store.shape[0]
+    co_pad, ci_pad = wt.shape[2], wt.shape[1]
+    elementwise().launch("pack_wt_kernel", ((ci_pad + 31) // 32, (co_pad + 31) // 32, k), (32, 8), _p(w_store), _p(wt), k, cout, cin, co_pad,
+                         ci_pad)
+    return wt
+
+
+def reflect_halo(y, T, pad_left, pad_right):
+    """w2l_reflect_halo (elementwise.cu:919-928)"""
+    B, rows, C = y.shape
+    if pad_left + pad_right:
+        elementwise().launch("reflect_halo_kernel", _grid_for(B * (pad_left + pad_right) * (C // 8), 256), 256, _p(y), B, T, C, pad_left,
+                             pad_right)
+    return y
+
+
+class _LensChain(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("k", ctypes.c_int16 * 192), ("s", ctypes.c_int16 * 192), ("d", ctypes.c_int16 * 192),
+                ("p", ctypes.c_int16 * 192)]
+
+
+def lens_chain(lens, conv_params):
+    """w2l_lens_chain (elementwise.cu:958-976)"""
+    if lens.dtype not in (torch.int32, torch.int64):
+        lens = lens.to(torch.int64)
+    lens = lens.contiguous()
+    B, n = lens.numel(), len(conv_params)
+    rows = torch.full((n + 1, B), -1, dtype=torch.int32)
+    final = torch.full((B,), -1, dtype=torch.int64)
+    c = _LensChain()
+    c.n = n
+    for j, (k, s, d, p) in enumerate(conv_params):
+        c.k[j], c.s[j], c.d[j], c.p[j] = int(k), int(s), int(d), int(p)
+    elementwise().launch("lens_chain_kernel", (B + 127) // 128, 128, _p(lens), int(lens.dtype == torch.int64), B, ctypes.addressof(c),
+                         _p(rows), _p(final))
+    return rows, final
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm + activation
+def bn_stats(z, C):
+    """w2l_bn_stats (elementwise.cu:779-787)"""
+    z = z.contiguous()
+    rows = z.numel() // C
+    stats = torch.zeros((2 * C,))
+    col_blocks = (C + 255) // 256
+    rpb = _rows_per_block_for(rows, col_blocks)
+    elementwise().launch("bn_stats_kernel", (col_blocks, (rows + rpb - 1) // rpb), (32, 8), _p(z), rows, C, _p(stats), rpb)
+    return stats
+
+
+def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked=None):
+    """w2l_bn_finalize (elementwise.cu:789-800)"""
+    out = torch.full((4, C), float("nan"))
+    f32 = lambda t: None if t is None else t.detach()                       # noqa: E731
+    elementwise().launch("bn_finalize_kernel", (C + 127) // 128, 128, _p(stats), rows, C, _p(f32(gamma)), _p(f32(beta)), _p(f32(conv_bias)),
+                         float(eps), float(momentum), _p(running_mean), _p(running_var), _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]),
+                         _p(num_batches_tracked))
+    return out
+
+
+class _BnActArgs(ctypes.Structure):
+    _fields_ = [("z", ctypes.c_void_p), ("res", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("res_scale", ctypes.c_void_p), ("res_shift", ctypes.c_void_p), ("B", ctypes.c_int), ("T", ctypes.c_int), ("C", ctypes.c_int),
+                ("pl", ctypes.c_int), ("pr", ctypes.c_int), ("act", ctypes.c_int), ("drop_p", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("lens", ctypes.c_void_p), ("drop_mask", ctypes.c_void_p)]
+
+
+def _bn_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pl, pr, act, drop_p, seed, lens, drop_mask):
+    """make_args (elementwise.cu:647-668); returns the struct plus the tensors it points at (kept alive by the caller)"""
+    keep = [z.contiguous(), scale.contiguous(), shift.contiguous(), None if res is None else res.contiguous(),
+            None if res_scale is None else res_scale.contiguous(), None if res_shift is None else res_shift.contiguous(),
+            None if lens is None else lens.to(torch.int32).contiguous(), drop_mask]
+    a = _BnActArgs(_p(keep[0]), _p(keep[3]), _p(keep[1]), _p(keep[2]), _p(keep[4]), _p(keep[5]), B, T, C, pl, pr, act, float(drop_p),
+                   int(seed) & 0xFFFFFFFFFFFFFFFF, _p(keep[6]), _p(keep[7]))
+    variant = "%d, %s, %s" % (act, "true" if drop_p > 0 else "false", "true" if res is not None else "false")
+    col_blocks = (C + 255) // 256
+    rpb = _rows_per_block_for(B * T, col_blocks)
+    return a, keep, variant, (col_blocks, (B * T + rpb - 1) // rpb), rpb
+
+
+def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None,
+               res_shift=None, out=None, drop_mask=None):
+    """w2l_bn_act_pad (elementwise.cu:802-818)"""
+    if out is None:
+        out = torch.full((B, pad_left + T + pad_right, C), float("nan"), dtype=BF16)
+    a, keep, variant, grid, rpb = _bn_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens,
+                                           drop_mask)
+    elementwise().launch("bn_act_pad_kernel<%s>" % variant, grid, (32, 8), ctypes.addressof(a), _p(out), rpb)
+    return out
+
+
+def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None):
+    """w2l_bn_act_bwd_reduce + w2l_bn_act_bwd_apply (elementwise.cu:820-866)"""
+    dz_rows = T if dz_rows is None else dz_rows
+    dyp = dyp.contiguous()
+    red = torch.zeros((2 * C,))
+    dz = torch.full((B, dz_rows, C), float("nan"), dtype=BF16)
+    g = torch.full((B, T, C), float("nan"), dtype=BF16) if want_g else None
+    a, keep, variant, grid, rpb = _bn_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens,
+                                           drop_mask)
+    mean, invstd = mean.contiguous(), invstd.contiguous()
+    gamma = None if gamma is None else gamma.detach().contiguous()
+    E = elementwise()
+    E.launch("bn_act_bwd_reduce_kernel<%s>" % variant, grid, (32, 8), ctypes.addressof(a), _p(dyp), _p(mean), _p(invstd), _p(red), rpb)
+    E.launch("bn_act_bwd_apply_kernel<%s>" % variant, grid, (32, 8), ctypes.addressof(a), _p(dyp), _p(mean), _p(invstd), _p(gamma), _p(red),
+             _p(dz), dz_rows, _p(g), rpb)
+    return dz, red, g
+
+
+# ------------------------------------------------------------------------------------------------ head
+def log_softmax(logits, C, mode=0, nan_flag=None):
+    """w2l_log_softmax (elementwise.cu:868-873)"""
+    logits = logits.contiguous()
+    ld = logits.shape[-1]
+    rows = logits.numel() // ld
+    out = torch.full(logits.shape[:-1] + (C,), float("nan"))
+    elementwise().launch("log_softmax_kernel", (rows + 7) // 8, 256, _p(logits), ld, _p(out), rows, C, mode, _p(nan_flag))
+    return out
+
+
+def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
+    """w2l_log_softmax_bwd (elementwise.cu:875-883)"""
+    C = g.shape[-1]
+    rows = g.numel() // C
+    g = g.contiguous()
+    lp = None if lp is None else lp.contiguous()
+    out = torch.full(g.shape[:-1] + (ld_out,), float("nan"), dtype=BF16)
+    elementwise().launch("log_softmax_bwd_kernel", (rows + 7) // 8, 256, _p(g), _p(lp), _p(gscale), _p(out), ld_out, rows, C,
+                         int(fused_identity))
+    return out
+
+
+def colsum(x, C):
+    """w2l_colsum (elementwise.cu:885-893)"""
+    x = x.contiguous()
+    ld = x.shape[-1]
+    rows = x.numel() // ld
+    out = torch.zeros((C,))
+    col_blocks = (C + 31) // 32
+    rpb = _rows_per_block_for(rows, col_blocks)
+    elementwise().launch("colsum_kernel", (col_blocks, (rows + rpb - 1) // rpb), (32, 8), _p(x), rows, C, ld, _p(out), rpb)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ depthwise (depthwise.cu)
+def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
+    """w2l_depthwise_fwd (depthwise.cu:161-171)"""
+    x, w = x.contiguous(), w.contiguous()
+    B, T, C = x.shape
+    y = torch.full((B, T_out, C), float("nan"), dtype=BF16)
+    ol = None if out_lens is None else out_lens.to(torch.int32).contiguous()
+    depthwise().launch("depthwise_corr_kernel", ((C // 8 + 31) // 32, (B * T_out + 7) // 8), (32, 8), _p(x), _p(w), _p(y), B, T, T_out, C, k,
+                       stride, dilation, -pad, 0, None, _p(ol))
+    return y
+
+
+def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None, stride=1):
+    """w2l_depthwise_dgrad / w2l_depthwise_dgrad_strided (depthwise.cu:173-196)"""
+    dy, w = dy.contiguous(), w.contiguous()
+    B, T_out, C = dy.shape
+    dx = torch.full((B, T, C), float("nan"), dtype=BF16)
+    dl = None if dy_lens is None else dy_lens.to(torch.int32).contiguous()
+    grid = ((C // 8 + 31) // 32, (B * T + 7) // 8)
+    if stride == 1:
+        depthwise().launch("depthwise_corr_kernel", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T_out, T, C, k, 1, dilation,
+                           pad - (k - 1) * dilation, 1, _p(dl), None)
+    else:
+        depthwise().launch("depthwise_dgrad_strided_kernel", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T, T_out, C, k, stride, dilation, pad,
+                           _p(dl))
+    return dx
+
+
+def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
+    """w2l_depthwise_wgrad (depthwise.cu:198-211)"""
+    dy, x = dy.contiguous(), x.contiguous()
+    B, T_out, C = dy.shape
+    T = x.shape[1]
+    dw = torch.zeros((k, C))
+    dl = None if dy_lens is None else dy_lens.to(torch.int32).contiguous()
+    rows = B * T_out
+    rpb = max(64, (rows + SMS - 1) // SMS)
+    depthwise().launch("depthwise_wgrad_kernel", ((C // 8 + 31) // 32, (rows + rpb - 1) // rpb, (k + 3) // 4), (32, 8), _p(dy), _p(x), _p(dw),
+                       B, T, T_out, C, k, stride, dilation, pad, _p(dl), rpb)
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------ CTC (ctc.cu)
+def ctc_loss_raw(x, targets, input_lengths, target_lengths, blank=0, zero_infinity=True, reduction_mean=True, from_logits=False,
+                 need_grad=True, serial=False, return_plan=False):
+    """w2l_ctc_loss + launch_ctc (ctc.cu:820-918), launch for launch.  ``serial`` forces the alpha -> beta+grad schedule."""
+    x = x.float()
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    N, T, C = x.shape
+    targets = targets.to(torch.int32).contiguous()
+    il, tl = input_lengths.to(torch.int32).contiguous(), target_lengths.to(torch.int32).contiguous()
+    S = targets.shape[1]
+    K = ctc()
+    out = (ctypes.c_longlong * 16)()
+    if K.lib.emu_ctc_plan(ctypes.c_longlong(N), ctypes.c_longlong(T), ctypes.c_longlong(S), ctypes.c_longlong(C), out) != 0:
+        raise RuntimeError("ctc_loss: target length %d not supported" % S)
+    R, threads, Lp, Cp, parallel, o_lp2, o_alpha, o_aoff, o_beta, o_boff, o_meta, total, kRing, kBlk, kGradFrames, meta_sz = list(out)
+    assert meta_sz == 16
+    ws = torch.full((total + 256,), 0xFF, dtype=torch.uint8)              # poisoned workspace, 256-byte aligned base
+    base = (ws.data_ptr() + 255) // 256 * 256
+    nll, loss = torch.full((N,), float("nan")), torch.full((1,), float("nan"))
+    grad = torch.full((N, T, C), float("nan")) if need_grad else None
+    p = lambda off: base + off                                            # noqa: E731
+    zi, rm = int(zero_infinity), int(reduction_mean)
+    K.launch("ctc_prep_kernel", (N * T + 7) // 8, 256, _p(x), int(from_logits), N, T, C, x.stride(0), x.stride(1), _p(il), p(o_lp2), Cp)
+    tgp = _p(targets) if S > 0 else None
+    if parallel and need_grad and not serial:
+        n_blk = (T + kBlk - 1) // kBlk
+        smem_l = 2 * kBlk * Cp * 4 + 33 * kBlk * 16 + (32 + 2) * 4
+        K.launch("ctc_lattice_kernel<%d>" % R, 2 * N, threads, p(o_lp2), N, T, Cp, tgp, S, _p(il), _p(tl), blank, p(o_alpha), p(o_aoff),
+                 p(o_beta), p(o_boff), n_blk, p(o_meta), Lp, smem=smem_l)
+        smem_g = 8 * Cp * 8 + (2 * S + 1 + 15)
+        K.launch("ctc_grad_kernel", ((T + kGradFrames - 1) // kGradFrames, N), 256, p(o_lp2), T, C, Cp, tgp, S, _p(il), _p(tl), blank,
+                 p(o_alpha), p(o_aoff), p(o_beta), p(o_boff), n_blk, p(o_meta), Lp, zi, rm, N, _p(grad), smem=smem_g)
+    else:
+        smem_a = (kRing * Cp + 2 * 32 * 2 + 32 + 2) * 4
+        smem_b = (kRing * Cp + kRing * threads * R + 2 * 32 * 2 + 32 + 2 * Cp) * 4
+        K.launch("ctc_alpha_kernel<%d>" % R, N, threads, p(o_lp2), T, Cp, tgp, S, _p(il), _p(tl), blank, p(o_alpha), p(o_aoff), p(o_meta), Lp,
+                 0, smem=smem_a)
+        if need_grad:
+            K.launch("ctc_beta_grad_kernel<%d>" % R, N, threads, p(o_lp2), T, C, Cp, tgp, S, _p(il), _p(tl), blank, p(o_alpha), p(o_aoff),
+                     p(o_meta), Lp, zi, rm, N, _p(grad), smem=smem_b)
+    K.launch("ctc_finish_kernel", 1, 256, p(o_meta), _p(tl), S, N, zi, rm, _p(nll), _p(loss))
+    if return_plan:
+        return loss, nll, grad, dict(R=R, threads=threads, parallel=bool(parallel))
+    return loss, nll, grad
+
+
+# ------------------------------------------------------------------------------------------------ greedy decode (decode.cu)
+def greedy_decode(scores, sizes=None, blank=0):
+    """w2l_greedy_decode (decode.cu:148-177), launch for launch; any [N, T, C] view with unit class stride"""
+    scores = scores.float()
+    if scores.stride(2) != 1:
+        scores = scores.contiguous()
+    N, T, C = scores.shape
+    chunk = 256
+    nchunks = max(1, (T + chunk - 1) // chunk)
+    am = torch.full((N, T), -7, dtype=torch.int32)
+    tok, off = torch.full((N, T), -7, dtype=torch.int32), torch.full((N, T), -7, dtype=torch.int32)
+    cnt, cc = torch.full((N,), -7, dtype=torch.int32), torch.full((N * nchunks,), -7, dtype=torch.int32)
+    sz = None if sizes is None else torch.as_tensor(sizes).to(torch.int32).contiguous()
+    if N == 0:
+        return am, tok, off, cnt
+    if T == 0:
+        cnt.zero_()
+        return am, tok, off, cnt
+    D = decode()
+    D.launch("greedy_argmax_kernel", (nchunks, N), chunk, _p(scores), T, C, scores.stride(0), scores.stride(1), _p(sz), blank, _p(am), _p(cc),
+             nchunks, smem=(4 + chunk * C) * 4)
+    D.launch("greedy_compact_kernel", (nchunks, N), chunk, _p(am), T, _p(sz), blank, _p(cc), nchunks, _p(tok), _p(off), _p(cnt))
+    return am, tok, off, cnt
+
+
+# ------------------------------------------------------------------------------------------------ install
+_NAMES = ["im2col_ncw", "tm_to_ncw", "im2col_tm", "col2im_tm", "cast_bf16", "pack_wt", "bn_stats", "bn_finalize", "lens_chain",
+          "bn_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "depthwise_fwd", "depthwise_dgrad",
+          "depthwise_wgrad", "ctc_loss_raw", "greedy_decode"]
+
+
+def install(monkeypatch):
+    """tests/_host_sim.py for the GEMMs, the emulated kernels for everything else"""
+    import _host_sim
+    F = _host_sim.install(monkeypatch)
+    for n in _NAMES:
+        assert hasattr(F, n), n
+        monkeypatch.setattr(F, n, globals()[n])
+    return F

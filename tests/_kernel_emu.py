@@ -89,14 +89,18 @@ def _params(param_text):
             if not p:
                 continue
             name = re.findall(r"[A-Za-z_][A-Za-z_0-9]*", p)[-1]
+            call = name
             if "*" in p:
                 ct = ctypes.c_void_p
             else:
                 hit = [c for key, c in _CTYPES if re.search(r"\b%s\b" % key, p)]
-                if not hit:
-                    raise ValueError("kernel parameter %r: pass-by-value structs are not supported by the launcher" % p)
-                ct = hit[0]
-            out.append((p, name, ct))
+                if hit:
+                    ct = hit[0]
+                else:                          # a struct passed by value: the launcher takes its address (ctypes.addressof / data_ptr)
+                    ct = ctypes.c_void_p
+                    p = "const %s* %s" % (p[:p.rindex(name)].strip(), name)
+                    call = "*" + name
+            out.append((p, call, ct))
             continue
         depth += ch in "(<["
         depth -= ch in ")>]"
@@ -125,7 +129,8 @@ class Emu:
         rc = fn(*(ctypes.c_int(int(v)) for v in g + b), ctypes.c_size_t(int(smem)), *conv)
         if rc:
             raise EmuError("%s: %s" % (kernel, {1: "deadlock: every live thread waits at a barrier / warp collective that cannot complete",
-                                                2: "a polling loop did not finish within the yield budget"}.get(rc, "error %d" % rc)))
+                                                2: "a polling loop did not finish within the yield budget",
+                                                3: "a block wrote past the end of its dynamic shared memory"}.get(rc, "error %d" % rc)))
 
 
 def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pack_bf16x2",)):

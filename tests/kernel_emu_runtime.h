@@ -134,7 +134,8 @@ static inline T shfl_from(T v, int src) {
   return from_bits<T>(snap[src]);
 }
 
-// returns 0 on success, 1 on deadlock, 2 when the yield budget is exhausted (a polling loop that never ends)
+// returns 0 on success, 1 on deadlock, 2 when the yield budget is exhausted (a polling loop that never ends); launch() adds
+// 3: a block wrote past the end of its dynamic shared memory (the 256 guard bytes behind it changed)
 static int run_block(unsigned nthreads) {
   fibers.resize(nthreads);
   warps.assign((nthreads + 31) / 32, Warp());
@@ -184,6 +185,8 @@ static int launch(int gx, int gy, int gz, int bx, int by, int bz, size_t smem_by
         std::memset(dyn_smem, 0xFF, n);              // NaN poison: a read of unwritten shared memory shows up in the result
         bid = make_uint3(x, y, z);
         rc = run_block((unsigned)(bx * by * bz));
+        for (size_t i = smem_bytes; i < n && !rc; ++i)
+          if (dyn_smem[i] != 0xFF) rc = 3;           // a write past the dynamic shared memory the launch asked for
       }
   std::free(raw);
   dyn_smem = nullptr;

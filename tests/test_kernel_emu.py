@@ -190,6 +190,13 @@ __global__ void collectives_kernel(const float* x, float* red, float* up, float*
         assert all((int(b) & 0xFFFFFFFF) == want for b in ballot[w0:w1])
 
 
+def test_runtime_flags_shared_memory_overrun():
+    e = _probe("__global__ void overrun_kernel(int n) {\n  extern __shared__ float buf[];\n  buf[threadIdx.x] = 1.f;\n}", "overrun_kernel")
+    e.launch("overrun_kernel", 2, 32, 0, smem=32 * 4)
+    with pytest.raises(KE.EmuError, match="past the end of its dynamic shared memory"):
+        e.launch("overrun_kernel", 2, 32, 0, smem=31 * 4)
+
+
 def test_scheduler_reports_deadlock_instead_of_hanging():
     """a barrier only half the block reaches: on hardware a hang, here an error"""
     e = _probe("__global__ void half_barrier_kernel(int* out) {\n  if (threadIdx.x < 16) { __syncthreads(); out[0] = 1; }\n"

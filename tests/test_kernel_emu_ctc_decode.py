@@ -5,92 +5,27 @@ the `-m gpu` tests in tests/test_gpu_kernels.py, on cases small enough for a fib
 
 Both CTC schedules run: the parallel one (alpha and beta lattices in separate CTAs with the tagged-slot wavefront across
 warps, then the per-frame gradient kernel) and the serial one (alpha, then beta fused with the gradient).  The inline-PTX
-helpers of ctc.cu are replaced by host functions below; everything else is the library's code, including ``make_plan``."""
-import ctypes
-
+helpers of ctc.cu are replaced by host functions (tests/_emu_backend.py CTC_PTX); everything else is the library's code,
+including ``make_plan``."""
 import numpy as np
 import pytest
 import torch
 
+import _emu_backend as E
 import _kernel_emu as KE
 from oracle import w2l_oracle as O
 
 pytestmark = pytest.mark.skipif(not KE.available(), reason="needs g++ and the CUDA headers")
 
-# host stand-ins for the inline PTX of csrc/ctc.cu (file:line of what each replaces)
-CTC_PTX = r"""
-static inline float fast_ex2(float x) { return std::exp2(x); }                                   // ctc.cu:36  ex2.approx.ftz.f32
-static inline float fast_lg2(float x) { return std::log2(x); }                                   // ctc.cu:41  lg2.approx.ftz.f32
-static inline void cp_async4(void* smem, const void* gmem) { std::memcpy(smem, gmem, 4); }       // ctc.cu:58  cp.async.ca 4 B (eager)
-static inline void cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }     // ctc.cu:61  cp.async.cg 16 B (eager)
-static inline void cp_async_commit() {}                                                          // ctc.cu:64
-template <int N> static inline void cp_async_wait() {}                                           // ctc.cu:65
-static inline void slot_put(float4* slot, float v0, float v1, int tag) {                         // ctc.cu:292 st.volatile.shared.v4
-  *slot = make_float4(v0, v1, __int_as_float(tag), 0.f);
-}
-static inline float4 slot_load(const float4* slot) {                                             // ctc.cu:300 ld.volatile.shared.v4
-  emu::yield_poll();                       // a poll lets the producing warp run (the hardware's warps run concurrently)
-  return *slot;
-}
-"""
-CTC_POST = r"""
-extern "C" int emu_ctc_plan(long long N, long long T, long long S, long long C, long long* out) {
-  w2l::CtcPlan p;
-  if (!w2l::make_plan(N, T, S, C, &p)) return 1;
-  long long v[] = {p.R, p.threads, p.Lp, p.Cp, p.parallel, (long long)p.off_lp2, (long long)p.off_alpha, (long long)p.off_aoff,
-                   (long long)p.off_beta, (long long)p.off_boff, (long long)p.off_meta, (long long)p.total, w2l::kRing, w2l::kBlk,
-                   w2l::kGradFrames, (long long)sizeof(w2l::CtcMeta)};
-  for (int i = 0; i < 16; ++i) out[i] = v[i];
-  return 0;
-}
-"""
-
 
 @pytest.fixture(scope="module")
 def ctc():
-    kernels = ["ctc_prep_kernel", "ctc_grad_kernel", "ctc_finish_kernel"]
-    for r in (2, 4, 8):
-        kernels += ["ctc_lattice_kernel<%d>" % r, "ctc_alpha_kernel<%d>" % r, "ctc_beta_grad_kernel<%d>" % r]
-    return KE.build(["ctc.cu"], kernels, drop=["fast_ex2", "fast_lg2", "cp_async4", "cp_async16", "cp_async_commit", "cp_async_wait",
-                                               "slot_put", "slot_load", "launch_ctc"], extra=CTC_PTX, post=CTC_POST)
+    return E.ctc()
 
 
-def emu_ctc_loss(ctc, x, targets, il, tl, from_logits=False, serial=False, blank=0, zero_infinity=1, reduction_mean=1):
-    """csrc/ctc.cu w2l_ctc_loss + launch_ctc, launch for launch"""
-    x = x.float().contiguous()
-    N, T, C = x.shape
-    targets, il, tl = targets.int().contiguous(), il.int().contiguous(), tl.int().contiguous()
-    S = targets.shape[1]
-    out = (ctypes.c_longlong * 16)()
-    assert ctc.lib.emu_ctc_plan(ctypes.c_longlong(N), ctypes.c_longlong(T), ctypes.c_longlong(S), ctypes.c_longlong(C), out) == 0
-    R, threads, Lp, Cp, parallel, o_lp2, o_alpha, o_aoff, o_beta, o_boff, o_meta, total, kRing, kBlk, kGradFrames, meta_sz = list(out)
-    assert meta_sz == 16
-    ws = torch.full((total + 256,), 0xFF, dtype=torch.uint8)              # poisoned workspace, 256-byte aligned base
-    base = (ws.data_ptr() + 255) // 256 * 256
-    nll, loss = torch.full((N,), float("nan")), torch.full((1,), float("nan"))
-    grad = torch.full((N, T, C), float("nan"))
-    p = lambda off: base + off                                            # noqa: E731
-    ctc.launch("ctc_prep_kernel", (N * T + 7) // 8, 256, x.data_ptr(), int(from_logits), N, T, C, x.stride(0), x.stride(1), il.data_ptr(),
-               p(o_lp2), Cp)
-    tgp = targets.data_ptr() if S > 0 else None
-    if parallel and not serial:
-        n_blk = (T + kBlk - 1) // kBlk
-        smem_l = 2 * kBlk * Cp * 4 + 33 * kBlk * 16 + (32 + 2) * 4
-        ctc.launch("ctc_lattice_kernel<%d>" % R, 2 * N, threads, p(o_lp2), N, T, Cp, tgp, S, il.data_ptr(), tl.data_ptr(), blank,
-                   p(o_alpha), p(o_aoff), p(o_beta), p(o_boff), n_blk, p(o_meta), Lp, smem=smem_l)
-        smem_g = 8 * Cp * 8 + (2 * S + 1 + 15)
-        ctc.launch("ctc_grad_kernel", ((T + kGradFrames - 1) // kGradFrames, N), 256, p(o_lp2), T, C, Cp, tgp, S, il.data_ptr(), tl.data_ptr(),
-                   blank, p(o_alpha), p(o_aoff), p(o_beta), p(o_boff), n_blk, p(o_meta), Lp, zero_infinity, reduction_mean, N,
-                   grad.data_ptr(), smem=smem_g)
-    else:
-        smem_a = (kRing * Cp + 2 * 32 * 2 + 32 + 2) * 4
-        smem_b = (kRing * Cp + kRing * threads * R + 2 * 32 * 2 + 32 + 2 * Cp) * 4
-        ctc.launch("ctc_alpha_kernel<%d>" % R, N, threads, p(o_lp2), T, Cp, tgp, S, il.data_ptr(), tl.data_ptr(), blank, p(o_alpha), p(o_aoff),
-                   p(o_meta), Lp, 0, smem=smem_a)
-        ctc.launch("ctc_beta_grad_kernel<%d>" % R, N, threads, p(o_lp2), T, C, Cp, tgp, S, il.data_ptr(), tl.data_ptr(), blank, p(o_alpha),
-                   p(o_aoff), p(o_meta), Lp, zero_infinity, reduction_mean, N, grad.data_ptr(), smem=smem_b)
-    ctc.launch("ctc_finish_kernel", 1, 256, p(o_meta), tl.data_ptr(), S, N, zero_infinity, reduction_mean, nll.data_ptr(), loss.data_ptr())
-    return loss, nll, grad, dict(R=R, threads=threads, parallel=bool(parallel))
+def emu_ctc_loss(ctc, x, targets, il, tl, from_logits=False, serial=False):
+    """tests/_emu_backend.py ctc_loss_raw: csrc/ctc.cu w2l_ctc_loss + launch_ctc, launch for launch"""
+    return E.ctc_loss_raw(x, targets, il, tl, from_logits=from_logits, serial=serial, return_plan=True)
 
 
 def check_ctc(ctc, lp, tg, il, tl, from_logits=False, serial=False, loss_tol=1e-4, grad_tol=2e-3):
@@ -167,25 +102,12 @@ def test_ctc_source_zero_length_input_and_renorm(ctc):
 # ------------------------------------------------------------------------------------------------ greedy decode
 @pytest.fixture(scope="module")
 def dec():
-    return KE.build(["decode.cu"], ["greedy_argmax_kernel", "greedy_compact_kernel"])
+    return E.decode()
 
 
 def emu_greedy_decode(dec, scores, sizes=None, blank=0):
-    """csrc/decode.cu w2l_greedy_decode, launch for launch; scores may be any [N, T, C] view with unit class stride"""
-    N, T, C = scores.shape
-    assert scores.stride(2) == 1
-    chunk = 256
-    nchunks = max(1, (T + chunk - 1) // chunk)
-    am = torch.full((N, T), -7, dtype=torch.int32)
-    tok, off = torch.full((N, T), -7, dtype=torch.int32), torch.full((N, T), -7, dtype=torch.int32)
-    cnt, cc = torch.full((N,), -7, dtype=torch.int32), torch.full((N * nchunks,), -7, dtype=torch.int32)
-    sz = None if sizes is None else torch.as_tensor(sizes, dtype=torch.int32)
-    szp = None if sz is None else sz.data_ptr()
-    dec.launch("greedy_argmax_kernel", (nchunks, N), chunk, scores.data_ptr(), T, C, scores.stride(0), scores.stride(1), szp, blank,
-               am.data_ptr(), cc.data_ptr(), nchunks, smem=(4 + chunk * C) * 4)
-    dec.launch("greedy_compact_kernel", (nchunks, N), chunk, am.data_ptr(), T, szp, blank, cc.data_ptr(), nchunks, tok.data_ptr(),
-               off.data_ptr(), cnt.data_ptr())
-    return am, tok, off, cnt
+    """tests/_emu_backend.py greedy_decode: csrc/decode.cu w2l_greedy_decode, launch for launch"""
+    return E.greedy_decode(scores, sizes, blank)
 
 
 def check_decode(dec, lp, sizes):
