@@ -413,6 +413,95 @@ def greedy_decode(scores, sizes=None, blank=0):
     return am, tok, off, cnt
 
 
+# ------------------------------------------------------------------------------------------------ NovoGrad (novograd.cu)
+@functools.lru_cache(maxsize=None)
+def novograd():
+    return KE.build(["novograd.cu"], ["novograd_norm_kernel", "novograd_moment_kernel", "novograd_update_kernel"])
+
+
+def novograd_step(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, shadows, lr, beta1, beta2, eps, weight_decay, grad_averaging):
+    """w2l_novograd_step (novograd.cu:126-145) over lists of fp32 tensors; ``exp_avg_sq`` / ``max_exp_avg_sq`` are fp32 [n_tensors]
+    (one second moment per tensor), ``shadows`` an optional list of bf16 tensors refreshed with the new parameters.  The chunk
+    table is built as novograd.py's ``_plan`` builds it: kNgChunk elements per CTA."""
+    chunk = 16384
+    n = len(params)
+    numel = torch.tensor([p.numel() for p in params], dtype=torch.int64)
+    per = [(int(c) + chunk - 1) // chunk for c in numel]
+    prefix = torch.tensor([sum(per[:i]) for i in range(n)], dtype=torch.int32)
+    table = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64)      # noqa: E731
+    tp, tg, tm = table(params), table(grads), table(exp_avg)
+    ts = None if shadows is None else table(shadows)
+    norms = torch.zeros(n)
+    K = novograd()
+    K.launch("novograd_norm_kernel", sum(per), 256, _p(tg), _p(numel), _p(prefix), n, _p(norms))
+    K.launch("novograd_moment_kernel", (n + 127) // 128, 128, _p(exp_avg_sq), _p(max_exp_avg_sq), _p(norms), n, float(beta2), float(eps))
+    K.launch("novograd_update_kernel", sum(per), 256, _p(tp), _p(tg), _p(tm), _p(norms), _p(ts), _p(numel), _p(prefix), n, float(lr),
+             float(beta1), float(weight_decay), int(grad_averaging))
+
+
+# ------------------------------------------------------------------------------------------------ WER / CER (metrics.cu)
+@functools.lru_cache(maxsize=None)
+def metrics():
+    return KE.build(["metrics.cu"], ["metrics_split_kernel", "edit_distance_kernel<int32_t>", "edit_distance_kernel<long long>",
+                                     "metrics_finalize_kernel"])
+
+
+def string_metrics(tokens, counts, space_index, ref_ids, ref_lens, cer_den, wer_den, len_den):
+    """w2l_string_metrics (metrics.cu:141-181): tokens [N, T] / ref_ids [N, S] int32 -> fp32 [3] = (cer, wer, len_ratio)"""
+    tokens, counts = tokens.to(torch.int32).contiguous(), counts.to(torch.int32).contiguous()
+    ref_ids, ref_lens = ref_ids.to(torch.int32).contiguous(), ref_lens.to(torch.int32).contiguous()
+    N, T = tokens.shape
+    S = ref_ids.shape[1]
+    assert 1 <= S <= 1023
+    i64 = lambda *shape: torch.full(shape, -1, dtype=torch.int64)          # noqa: E731
+    i32 = lambda *shape: torch.full(shape, -1, dtype=torch.int32)          # noqa: E731
+    h_words, r_words, h_chars, r_chars = i64(N, T), i64(N, S), i32(N, T), i32(N, S)
+    h_nc, h_nw, r_nc, r_nw, cer_d, wer_d = (i32(N) for _ in range(6))
+    ratios = torch.full((3,), float("nan"))
+    K = metrics()
+    blocks = (N + 63) // 64
+    K.launch("metrics_split_kernel", blocks, 64, _p(tokens), _p(counts), N, T, space_index, _p(h_chars), _p(h_nc), _p(h_words), _p(h_nw))
+    K.launch("metrics_split_kernel", blocks, 64, _p(ref_ids), _p(ref_lens), N, S, space_index, _p(r_chars), _p(r_nc), _p(r_words), _p(r_nw))
+    threads = (S + 31) // 32 * 32
+    smem = 3 * (threads + 1) * 4
+    K.launch("edit_distance_kernel<int32_t>", N, threads, _p(h_chars), _p(h_nc), T, _p(r_chars), _p(r_nc), S, _p(cer_d), smem=smem)
+    K.launch("edit_distance_kernel<long long>", N, threads, _p(h_words), _p(h_nw), T, _p(r_words), _p(r_nw), S, _p(wer_d), smem=smem)
+    K.launch("metrics_finalize_kernel", 1, 256, _p(cer_d), _p(wer_d), _p(counts), N, float(cer_den), float(wer_den), float(len_den),
+             _p(ratios))
+    return ratios, cer_d, wer_d
+
+
+# ------------------------------------------------------------------------------------------------ feature front-end (features.cu)
+@functools.lru_cache(maxsize=None)
+def features():
+    return KE.build(["features.cu"], ["logmel_kernel", "feat_norm_kernel"])
+
+
+def logmel_features(audio, lens, noise, window, fb, n_fft, win_length, hop, dither=1e-5, preemph=0.97, log_guard=2.0 ** -24, eps=1e-5):
+    """w2l_logmel_features (features.cu:180-214): audio [B, Lmax] fp32 zero padded, lens int32 [B], noise [B, Lmax] | None, window
+    [win_length], fb [n_mels, n_fft/2+1] -> (features [B, n_mels, T_max] fp32 zero padded, frames per utterance)"""
+    audio = audio.float().contiguous()
+    lens = lens.to(torch.int32).contiguous()
+    noise = None if noise is None else noise.float().contiguous()
+    window, fb = window.float().contiguous(), fb.float().contiguous()
+    B, Lmax = audio.shape
+    n_mels = fb.shape[-2]
+    T_max = 1 + int(lens.max()) // hop
+    feats = torch.full((B, T_max, n_mels), float("nan"))
+    out = torch.full((B, n_mels, T_max), float("nan"))
+    log2_fft = n_fft.bit_length() - 1
+    n_bins = n_fft // 2 + 1
+    fb_pitch = n_bins | 1
+    warps = 8
+    smem = (n_mels * fb_pitch + ((n_mels * fb_pitch) & 1)) * 4 + (n_fft // 2) * 8 + (win_length + (win_length & 1)) * 4 + warps * n_fft * 8 + n_mels * 8
+    bx = max(1, min((2 * SMS + B - 1) // B, (T_max + 4 * warps - 1) // (4 * warps)))
+    K = features()
+    K.launch("logmel_kernel", (bx, B), warps * 32, _p(audio), audio.stride(0), _p(noise), _p(lens), n_fft, log2_fft, win_length, hop,
+             _p(window), _p(fb), n_mels, float(dither), float(preemph), float(log_guard), _p(feats), T_max, smem=smem)
+    K.launch("feat_norm_kernel", ((n_mels + 31) // 32, B), (32, 8), _p(feats), _p(lens), hop, T_max, n_mels, float(eps), _p(out))
+    return out, (lens // hop + 1).to(torch.int32)
+
+
 # ------------------------------------------------------------------------------------------------ install
 _NAMES = ["im2col_ncw", "tm_to_ncw", "im2col_tm", "col2im_tm", "cast_bf16", "pack_wt", "bn_stats", "bn_finalize", "lens_chain",
           "bn_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "depthwise_fwd", "depthwise_dgrad",

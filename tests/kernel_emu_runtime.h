@@ -319,7 +319,10 @@ static inline float emu_log2f(float x) { return std::log2(x); }
 static inline float emu_sinf(float x) { return std::sin(x); }
 static inline float emu_cosf(float x) { return std::cos(x); }
 static inline void emu_sincosf(float x, float* s, float* c) { *s = std::sin(x); *c = std::cos(x); }
-static inline void emu_sincospif(float x, float* s, float* c) { emu_sincosf(x * 3.14159265358979323846f, s, c); }
+static inline void emu_sincospif(float x, float* s, float* c) {
+  *s = (float)std::sin((double)x * 3.14159265358979323846);
+  *c = (float)std::cos((double)x * 3.14159265358979323846);
+}
 static inline float emu_rsqrtf(float x) { return 1.f / std::sqrt(x); }
 static inline float emu_saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 #define __expf(x) emu_expf(x)

@@ -10,7 +10,19 @@ import pytest
 import torch
 
 import _host_sim
+import _kernel_emu
 from oracle import w2l_oracle as O
+
+# "sim": every C-ABI call answered by the torch restatement; "emu": only the tcgen05 GEMMs restated, every other call runs the
+# library's own kernel source on the host (tests/_emu_backend.py)
+BACKENDS = ["sim", pytest.param("emu", marks=pytest.mark.skipif(not _kernel_emu.available(), reason="needs g++ and the CUDA headers"))]
+
+
+def _install(monkeypatch, backend):
+    if backend == "emu":
+        import _emu_backend
+        return _emu_backend.install(monkeypatch)
+    return _host_sim.install(monkeypatch)
 
 
 def rel_l2(a, b):
@@ -25,11 +37,12 @@ def _load_sd(model, g, prefix):
     return sd
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided"])
-def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture):
+def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, backend):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
-    _host_sim.install(monkeypatch)
+    _install(monkeypatch, backend)
     g = golden(fixture)
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
     cfg = config.compose(overrides=["model.mid_layers=3"]).model
@@ -84,11 +97,12 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture):
     assert model.scaling_factor == int(g["scaling_factor"])
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("fixture,seed,emu_tol", [("jasper_dense", 4, 0.15), ("jasper_small", 2, 0.15), ("jasper_strided", 10, 0.25)])
-def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, seed, emu_tol):
+def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, seed, emu_tol, backend):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
-    _host_sim.install(monkeypatch)
+    _install(monkeypatch, backend)
     g = golden(fixture)
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
