@@ -502,6 +502,79 @@ def logmel_features(audio, lens, noise, window, fb, n_fft, win_length, hop, dith
     return out, (lens // hop + 1).to(torch.int32)
 
 
+# ------------------------------------------------------------------------------------------------ conv GEMM (conv_gemm.cu)
+# the two inline-PTX statements inside conv_gemm_kernel's body, replaced textually (everything else in that kernel is C++ over the
+# wrappers of common.cuh, whose functional stand-ins live in tests/kernel_emu_runtime.h)
+GEMM_SUBS = [(r'asm volatile\("bar\.sync 1, 128;" ::: "memory"\);', "emu::named_barrier(1, 128);"),
+             (r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};" ::"l"\((.*?)\), "f"\((.*?)\),\s*"f"\((.*?)\), '
+              r'"f"\((.*?)\), "f"\((.*?)\)\s*: "memory"\);', r"emu_red_add_v4(\1, \2, \3, \4, \5);")]
+GEMM_POST = r"""
+extern "C" const char* emu_last_error() { return w2l::g_err; }
+extern "C" long long emu_launch_count() { return w2l::g_launches; }
+"""
+
+
+@functools.lru_cache(maxsize=None)
+def gemm():
+    """conv_gemm.cu WITH its extern "C" wrappers (descriptor checks, tile / ring / stream-K / tail-split planning, tensor maps):
+    the emulated library exports w2l_conv1d_fwd / _dgrad / _dgrad_wt / _wgrad / _wgrad_splits / w2l_set_gemm_scratch themselves"""
+    from wav2letter_pytorch_b200 import _lib
+    K = KE.build(["conv_gemm.cu"], [], helpers_from_common=("pack_bf16x2", "make_smem_desc", "make_idesc_bf16"), subs=GEMM_SUBS,
+                 c_abi=True, post=GEMM_POST, opt="-O2")
+    for name in ("w2l_conv1d_fwd", "w2l_conv1d_dgrad", "w2l_conv1d_dgrad_wt", "w2l_conv1d_wgrad", "w2l_conv1d_wgrad_splits",
+                 "w2l_set_gemm_scratch", "w2l_conv1d_fwd_tail_parts"):
+        res, args = _lib.SIGNATURES[name]
+        fn = getattr(K.lib, name)
+        fn.restype, fn.argtypes = res, args
+    K.lib.emu_last_error.restype = ctypes.c_char_p
+    K.lib.emu_launch_count.restype = ctypes.c_longlong
+    return K
+
+
+def _gemm_check(rc, what):
+    if rc:
+        raise RuntimeError("emulated %s failed (code %d): %s" % (what, rc, gemm().lib.emu_last_error().decode()))
+
+
+_scratch = []
+
+
+def ensure_gemm_scratch(device=None):
+    """functional.ensure_gemm_scratch: the zero-filled fp32 scratch of the forward tail split"""
+    if not _scratch:
+        nbytes = 4096 + 148 * 128 * 256 * 4
+        buf = torch.zeros((nbytes + 256,), dtype=torch.uint8)
+        base = (buf.data_ptr() + 255) // 256 * 256
+        _gemm_check(gemm().lib.w2l_set_gemm_scratch(base, nbytes), "set_gemm_scratch")
+        _scratch.append(buf)
+
+
+def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
+    ensure_gemm_scratch()
+    det = lambda t: None if t is None else t.detach()                       # noqa: E731
+    _gemm_check(gemm().lib.w2l_conv1d_fwd(_p(x), _p(w), _p(det(bias)), _p(det(scale)), _p(det(shift)), _p(bn_stats), _p(y), ctypes.byref(desc),
+                                          None), "conv1d_fwd")
+    return y
+
+
+def conv1d_dgrad(dy, w, desc, dx):
+    _gemm_check(gemm().lib.w2l_conv1d_dgrad(_p(dy), _p(w), _p(dx), ctypes.byref(desc), None), "conv1d_dgrad")
+    return dx
+
+
+def conv1d_dgrad_wt(dy, wt, desc, dx):
+    _gemm_check(gemm().lib.w2l_conv1d_dgrad_wt(_p(dy), _p(wt), _p(dx), ctypes.byref(desc), None), "conv1d_dgrad_wt")
+    return dx
+
+
+def conv1d_wgrad(dy, x, desc, dw):
+    lib = gemm().lib
+    if lib.w2l_conv1d_wgrad_splits(ctypes.byref(desc)) > 1:
+        dw.zero_()
+    _gemm_check(lib.w2l_conv1d_wgrad(_p(dy), _p(x), _p(dw), ctypes.byref(desc), None), "conv1d_wgrad")
+    return dw
+
+
 # ------------------------------------------------------------------------------------------------ install
 _NAMES = ["im2col_ncw", "tm_to_ncw", "im2col_tm", "col2im_tm", "cast_bf16", "pack_wt", "bn_stats", "bn_finalize", "lens_chain",
           "bn_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "depthwise_fwd", "depthwise_dgrad",

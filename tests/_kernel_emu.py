@@ -46,7 +46,7 @@ def find_function(text, name):
     """(start, end, parameter text) of the definition of ``name`` in ``text``: from its ``template <...>`` / ``__global__`` /
     ``__device__`` qualifier to the closing brace of its body"""
     for m in re.finditer(r"\b%s\s*\(" % re.escape(name), text):
-        start = max(text.rfind(q, 0, m.start()) for q in ("__global__", "__device__", "\nstatic "))
+        start = max(text.rfind(q, 0, m.start()) for q in ("__global__", "__device__", "\nstatic ", "\nint "))
         if start < 0:
             continue
         between = text[start:m.start()]
@@ -73,6 +73,73 @@ def namespace_sections(path):
     if not out:
         raise ValueError("no namespace w2l section in " + path)
     return "\n".join(out)
+
+
+def extern_c_sections(path):
+    """the bodies of the ``extern "C" { ... }`` blocks of a .cu file plus its single ``extern "C" T f(...) { ... }`` definitions, as
+    one ``extern "C" { ... }`` text: the C-ABI wrappers (argument checks, launch planning) exactly as the library compiles them"""
+    text = open(path).read()
+    out = []
+    for m in re.finditer(r'^extern "C"\s*(\{)?', text, flags=re.M):
+        if m.group(1):
+            end = _match(text, m.end() - 1, "{", "}")
+            out.append(text[m.end():end])
+        else:
+            brace = text.index("{", m.end())
+            end = _match(text, brace, "{", "}")
+            out.append(text[m.end():end + 1])
+    return 'extern "C" {\n' + "\n".join(out) + "\n}\n"
+
+
+def _split_top(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+            continue
+        depth += ch in "(<[{"
+        depth -= ch in ")>]}"
+        cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+def transform_launches(text):
+    """``kernel<<<grid, block[, smem[, stream]]>>>(args);`` -> a call of the fiber runtime (the enclosing function returns
+    W2L_ERR_CUDA when the emulation reports a deadlock / overrun, as a failed launch would)"""
+    out, pos = "", 0
+    while True:
+        i = text.find("<<<", pos)
+        if i < 0:
+            return out + text[pos:]
+        j = i                                                   # walk back over the kernel name (identifier + template arguments)
+        while j > 0 and text[j - 1].isspace():
+            j -= 1
+        if text[j - 1] == ">":
+            depth, j = 0, j - 1
+            while True:
+                depth += text[j] == ">"
+                depth -= text[j] == "<"
+                if depth == 0:
+                    break
+                j -= 1
+        while j > 0 and (text[j - 1].isalnum() or text[j - 1] in "_:"):
+            j -= 1
+        name = text[j:i].strip()
+        k = text.index(">>>", i)
+        cfg = _split_top(text[i + 3:k])
+        op = text.index("(", k)
+        cl = _match(text, op, "(", ")")
+        semi = text.index(";", cl)
+        assert not text[cl + 1:semi].strip(), "unexpected text after a kernel launch"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        call = ("{ const dim3 emu_g_(%s), emu_b_(%s); if (emu::launch(emu_g_.x, emu_g_.y, emu_g_.z, emu_b_.x, emu_b_.y, emu_b_.z, (size_t)(%s), "
+                "[=]() { %s(%s); })) { w2l::set_error(\"emulated launch of %s failed\"); return W2L_ERR_CUDA; } }"
+                % (cfg[0], cfg[1], smem, name, text[op + 1:cl], name.replace('"', "")))
+        out += text[pos:j] + call
+        pos = semi + 1
 
 
 _CTYPES = (("int64_t", ctypes.c_int64), ("uint64_t", ctypes.c_uint64), ("int32_t", ctypes.c_int32), ("uint32_t", ctypes.c_uint32),
@@ -133,10 +200,13 @@ class Emu:
                                                 3: "a block wrote past the end of its dynamic shared memory"}.get(rc, "error %d" % rc)))
 
 
-def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pack_bf16x2",)):
+def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pack_bf16x2",), subs=(), c_abi=False, opt="-O1"):
     """sources: .cu file names under csrc/; kernels: kernel names (``name<float>`` instantiates a template); drop: functions cut
     from the sources (inline PTX, host functions that launch kernels); extra: C++ placed inside namespace w2l ahead of the sources
-    (host replacements for dropped functions); post: C++ appended at file scope (e.g. extern "C" access to host planning code)"""
+    (host replacements for dropped functions); post: C++ appended at file scope (e.g. extern "C" access to host planning code);
+    drop may be a dict name -> replacement text (put where the function stood); subs: (regex, replacement) pairs applied to the
+    source text (inline PTX statements inside a kernel body); c_abi: also compile the files' extern "C" wrappers, with their
+    ``<<<...>>>`` launches turned into calls of the fiber runtime -- the result exports the library's own entry points"""
     common = open(os.path.join(CSRC, "common.cuh")).read()
     parts = ['#include "kernel_emu_runtime.h"', "namespace w2l {"]
     for h in helpers_from_common:
@@ -146,7 +216,12 @@ def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pa
     body = "\n".join(namespace_sections(os.path.join(CSRC, f)) for f in sources)
     for name in drop:
         s, e, _ = find_function(body, name)
-        body = body[:s] + body[e:]
+        body = body[:s] + (drop[name] if isinstance(drop, dict) else "") + body[e:]
+    for pat, rep in subs:
+        body, n_sub = re.subn(pat, rep, body, flags=re.S)
+        if n_sub == 0:
+            raise ValueError("substitution %r matched nothing" % pat)
+    body = transform_launches(body)
     # dynamic shared memory: `extern __shared__ [__align__(n)] T name[];` -> a typed view of the launch's buffer
     body = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][A-Za-z_0-9:]*)\s+([A-Za-z_][A-Za-z_0-9]*)\s*\[\s*\]\s*;",
                   r"\1* \2 = reinterpret_cast<\1*>(emu::dyn_smem);", body)
@@ -156,6 +231,8 @@ def build(sources, kernels, drop=(), extra="", post="", helpers_from_common=("pa
     parts.append(body)
     parts.append("}  // namespace w2l")
     parts.append("using namespace w2l;       // launcher signatures name the library's own types")
+    if c_abi:
+        parts.extend(transform_launches(extern_c_sections(os.path.join(CSRC, f))) for f in sources)
     parts.append(post)
     sigs = {}
     for spec in kernels:
@@ -187,7 +264,7 @@ extern "C" int %s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, in
         with open(cpp, "w") as fh:
             fh.write(code)
         tmp = so + ".%d.tmp" % os.getpid()
-        r = subprocess.run(["g++", "-O1", "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + HERE, cpp, "-o", tmp],
+        r = subprocess.run(["g++", opt, "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + HERE, cpp, "-o", tmp],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host compilation of the kernel sources failed (%s):\n%s" % (cpp, r.stderr[-6000:]))

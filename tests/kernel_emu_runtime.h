@@ -96,6 +96,22 @@ static void trampoline() {
   swapcontext(&f.ctx, &sched_ctx);
 }
 
+struct NamedBar {
+  int arrived = 0;
+  unsigned long gen = 0;
+};
+static NamedBar named[16];
+static inline void named_barrier(int id, int count) {      // bar.sync id, count
+  NamedBar& b = named[id & 15];
+  const unsigned long g = b.gen;
+  if (++b.arrived == count) {
+    b.arrived = 0;
+    ++b.gen;
+    ++n_events;
+  }
+  while (b.gen == g) yield_wait();
+}
+
 static inline void syncthreads() {
   ++bar_arrived;
   const unsigned long g = bar_gen;
@@ -141,6 +157,7 @@ static int run_block(unsigned nthreads) {
   warps.assign((nthreads + 31) / 32, Warp());
   live = (int)nthreads;
   bar_arrived = 0;
+  for (auto& nb : named) nb.arrived = 0;
   for (unsigned i = 0; i < nthreads; ++i) {
     Fiber& f = fibers[i];
     if (!f.stack) f.stack = (char*)std::malloc(kStack);
@@ -176,8 +193,8 @@ static int launch(int gx, int gy, int gz, int bx, int by, int bz, size_t smem_by
   bdim = dim3(bx, by, bz);
   body = fn;
   const size_t n = smem_bytes + 256;
-  unsigned char* raw = (unsigned char*)std::malloc(n + 128);
-  dyn_smem = (unsigned char*)(((uintptr_t)raw + 127) & ~(uintptr_t)127);
+  unsigned char* raw = (unsigned char*)std::malloc(n + 1024);
+  dyn_smem = (unsigned char*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   int rc = 0;
   for (int z = 0; z < gz && !rc; ++z)
     for (int y = 0; y < gy && !rc; ++y)
@@ -346,19 +363,228 @@ static inline float emu_saturatef(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1
 
 // ------------------------------------------------------------------------------------------------ library host surface
 // what the kernels' translation units expect from common.cuh / runtime.cu (host helpers that sit beside the kernels)
+#include <cuda.h>
+#include <cstdarg>
 #include "../include/w2l_sm100.h"
+
+// CUDA runtime calls made by the C wrappers: memsets are performed, attribute settings succeed
+#define cudaMemsetAsync(p, v, n, st) (std::memset((p), (v), (n)), cudaSuccess)
+#define cudaFuncSetAttribute(...) cudaSuccess
+#define cudaPeekAtLastError() cudaSuccess
+#define cudaGetLastError() cudaSuccess
+
 namespace w2l {
-static inline void set_error(const char*, ...) {}
+static char g_err[512] = "";
+static long long g_launches = 0;
+static inline void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
 static inline int num_sms() { return 148; }
 static inline int gemm_sms() { return 148; }
-static inline int after_launch(const char*) { return 0; }
-static inline int check_cuda(cudaError_t, const char*) { return 0; }
-#define W2L_REQUIRE(cond, ...) \
-  do {                         \
-    if (!(cond)) return W2L_ERR_INVALID_ARGUMENT; \
+static inline int after_launch(const char*) {
+  ++g_launches;
+  return 0;
+}
+static inline int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return W2L_OK;
+  set_error("CUDA error %d at %s", (int)e, what);
+  return W2L_ERR_CUDA;
+}
+#define W2L_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      w2l::set_error(__VA_ARGS__);             \
+      return W2L_ERR_INVALID_ARGUMENT;         \
+    }                                          \
   } while (0)
-#define W2L_CUDA(expr) \
-  do {                 \
-    (void)0;           \
+#define W2L_CUDA(expr)                                     \
+  do {                                                     \
+    int _rc = w2l::check_cuda((expr), #expr);              \
+    if (_rc != W2L_OK) return _rc;                         \
   } while (0)
+
+// ---- TMA: the tensor map is opaque to the kernels; here its 128 bytes hold what make_tensor_map was given
+struct EmuTensorMap {
+  const unsigned char* base;
+  int32_t elem_bytes, rank, swizzle128;
+  uint64_t dims[4];
+  uint64_t strides[3];          // bytes, for dims 1..
+  uint32_t box[4];
+};
+static_assert(sizeof(EmuTensorMap) <= sizeof(CUtensorMap), "emulated tensor map must fit the opaque CUtensorMap");
+static inline int make_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  // the documented constraints of cuTensorMapEncodeTiled that the library's call sites must meet
+  W2L_REQUIRE(rank >= 1 && rank <= 4 && ((uintptr_t)base & 15) == 0, "tensor map: rank %d / base alignment", rank);
+  for (int i = 0; i + 1 < rank; ++i) W2L_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map: stride %d = %llu not a multiple of 16", i, (unsigned long long)strides_bytes[i]);
+  for (int i = 0; i < rank; ++i) W2L_REQUIRE(box[i] >= 1 && box[i] <= 256 && dims[i] >= 1, "tensor map: box/dim %d", i);
+  W2L_REQUIRE(!swizzle128 || box[0] * (uint32_t)elem_bytes <= 128, "tensor map: 128B swizzle needs an inner box of at most 128 bytes");
+  EmuTensorMap m;
+  std::memset(&m, 0, sizeof(m));
+  m.base = (const unsigned char*)base;
+  m.elem_bytes = elem_bytes;
+  m.rank = rank;
+  m.swizzle128 = swizzle128;
+  for (int i = 0; i < 4; ++i) {
+    m.dims[i] = i < rank ? dims[i] : 1;
+    m.box[i] = i < rank ? box[i] : 1;
+    if (i > 0) m.strides[i - 1] = i < rank ? strides_bytes[i - 1] : 0;
+  }
+  std::memset(map, 0, sizeof(*map));
+  std::memcpy(map, &m, sizeof(m));
+  return W2L_OK;
+}
+}  // namespace w2l
+
+// ------------------------------------------------------------------------------------------------ sm_100 device surface
+// Functional stand-ins for the inline-PTX wrappers of common.cuh (mbarrier, TMA, tcgen05 / TMEM).  Everything is synchronous:
+// a TMA load lands before the call returns, an MMA has completed when it is issued, so tcgen05.commit is a plain arrive.
+#define __grid_constant__
+template <typename T>
+static inline T __ldcg(const T* p) { return *p; }
+
+namespace w2l {
+// shared-memory "addresses" are offsets into the launch's dynamic shared memory (1024-byte aligned, like the hardware's window)
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - emu::dyn_smem); }
+static inline unsigned char* smem_ptr(uint32_t a) { return emu::dyn_smem + a; }
+// 128-byte swizzle: address bits [4,7) ^= bits [7,10) of the ABSOLUTE shared-memory address (TMA writes and tcgen05 reads agree on it)
+static inline uint32_t swz128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+static inline uint32_t elect_one_sync() { return emu::fibers[emu::cur].lane == 0; }
+
+struct EmuMbar {                 // mbarrier.shared::cta.b64
+  uint32_t phase : 1, expected : 15, pending : 16;
+  int32_t tx;
+};
+static_assert(sizeof(EmuMbar) == 8, "mbarrier is a 64-bit object");
+static inline void mbar_check(EmuMbar* b) {
+  if (b->pending == 0 && b->tx == 0) {
+    b->phase ^= 1u;
+    b->pending = b->expected;
+    ++emu::n_events;
+  }
+}
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
+  EmuMbar* b = (EmuMbar*)bar;
+  b->phase = 0;
+  b->expected = count;
+  b->pending = count;
+  b->tx = 0;
+}
+static inline void fence_barrier_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {      // mbarrier.arrive.expect_tx
+  EmuMbar* b = (EmuMbar*)bar;
+  b->tx += (int32_t)bytes;
+  b->pending -= 1;
+  mbar_check(b);
+}
+static inline void mbar_arrive(uint64_t* bar) {
+  EmuMbar* b = (EmuMbar*)bar;
+  if (b->pending == 0) {
+    std::fprintf(stderr, "emu: mbarrier over-arrival\n");
+    std::abort();
+  }
+  b->pending -= 1;
+  mbar_check(b);
+}
+static inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  EmuMbar* b = (EmuMbar*)bar;
+  b->tx -= (int32_t)bytes;
+  mbar_check(b);
+}
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return ((EmuMbar*)bar)->phase != (parity & 1u); }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) emu::yield_poll();
+}
+
+// cp.async.bulk.tensor.{3,4}d: box [b3][b2][b1][b0] lands densely (inner row = box0 elements), out-of-range elements as zero,
+// the whole box is credited to the barrier
+static inline void tma_load_nd(void* smem_dst, const CUtensorMap* mp, uint64_t* bar, const int (&c)[4]) {
+  EmuTensorMap m;
+  std::memcpy(&m, mp, sizeof(m));
+  const uint32_t dst = smem_u32(smem_dst);
+  const uint32_t row_bytes = m.box[0] * (uint32_t)m.elem_bytes;
+  uint32_t lin = 0;
+  for (uint32_t i3 = 0; i3 < m.box[3]; ++i3)
+    for (uint32_t i2 = 0; i2 < m.box[2]; ++i2)
+      for (uint32_t i1 = 0; i1 < m.box[1]; ++i1) {
+        const long long g3 = (long long)c[3] + i3, g2 = (long long)c[2] + i2, g1 = (long long)c[1] + i1;
+        const bool row_in = g3 >= 0 && g3 < (long long)m.dims[3] && g2 >= 0 && g2 < (long long)m.dims[2] && g1 >= 0 && g1 < (long long)m.dims[1];
+        const unsigned char* src = m.base + g1 * (long long)m.strides[0] + g2 * (long long)m.strides[1] + g3 * (long long)m.strides[2];
+        for (uint32_t i0 = 0; i0 < m.box[0]; ++i0) {
+          const long long g0 = (long long)c[0] + i0;
+          const uint32_t a = dst + lin + i0 * (uint32_t)m.elem_bytes;
+          unsigned char* d = smem_ptr(m.swizzle128 ? swz128(a) : a);
+          if (row_in && g0 >= 0 && g0 < (long long)m.dims[0]) std::memcpy(d, src + g0 * m.elem_bytes, m.elem_bytes);
+          else std::memset(d, 0, m.elem_bytes);
+        }
+        lin += row_bytes;
+      }
+  mbar_complete_tx(bar, lin);
+}
+static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  const int c[4] = {c0, c1, c2, 0};
+  tma_load_nd(smem_dst, m, bar, c);
+}
+static inline void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  const int c[4] = {c0, c1, c2, c3};
+  tma_load_nd(smem_dst, m, bar, c);
+}
+
+// TMEM: 128 lanes x 512 32-bit columns per SM; addresses are (lane << 16) | column
+static uint32_t emu_tmem[128][512];
+static inline void tmem_alloc(uint32_t* smem_result, uint32_t) { *smem_result = 0; }
+static inline void tmem_relinquish() {}
+static inline void tmem_dealloc(uint32_t, uint32_t) {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void tmem_ld_wait() {}
+static inline void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {      // tcgen05.ld.32x32b.x32: thread i reads lane base+i
+  const uint32_t lane = (taddr >> 16) + (uint32_t)emu::fibers[emu::cur].lane, col = taddr & 0xFFFFu;
+  for (int i = 0; i < 32; ++i) r[i] = emu_tmem[lane][col + i];
+}
+static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+
+// one operand element of a 128B-swizzled shared-memory matrix descriptor (sm_100 "version 1", see common.cuh make_smem_desc):
+//   K-major : row r, contraction index k (0..15) at start + (r / 8) * SBO + (r % 8) * 128 + k * 2
+//   MN-major: mn index, contraction index k at start + (mn / 64) * LBO + (k / 8) * SBO + (k % 8) * 128 + (mn % 64) * 2
+static inline float umma_operand(uint64_t desc, bool mn_major, int r, int k) {
+  const uint32_t start = (uint32_t)(desc & 0x3FFF) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+  const uint32_t a = mn_major ? start + (uint32_t)(r / 64) * lbo + (uint32_t)(k / 8) * sbo + (uint32_t)(k % 8) * 128u + (uint32_t)(r % 64) * 2u
+                              : start + (uint32_t)(r / 8) * sbo + (uint32_t)(r % 8) * 128u + (uint32_t)k * 2u;
+  uint16_t bits;
+  std::memcpy(&bits, smem_ptr(swz128(a)), 2);
+  return emu::from_bits<float>((uint64_t)bits << 16);
+}
+// tcgen05.mma.cta_group::1.kind::f16, bf16 x bf16 -> fp32: D[128 x N] (+)= A[128 x 16] * B[N x 16]^T
+static inline void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  if (M != 128 || N < 16 || N > 256 || ((a_desc >> 61) & 7) != 2 || ((b_desc >> 61) & 7) != 2) {
+    std::fprintf(stderr, "emu: unsupported tcgen05.mma shape / swizzle (M=%d N=%d)\n", M, N);
+    std::abort();
+  }
+  static float A[128][16], B[256][16];
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 16; ++k) A[m][k] = umma_operand(a_desc, a_mn, m, k);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) B[n][k] = umma_operand(b_desc, b_mn, n, k);
+  const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xFFFFu;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? emu::from_bits<float>(emu_tmem[lane0 + m][col0 + n]) : 0.f;
+      for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      emu_tmem[lane0 + m][col0 + n] = (uint32_t)emu::to_bits(acc);
+    }
+}
+static inline void emu_red_add_v4(float* dst, float a, float b, float c, float d) {     // red.global.add.v4.f32
+  dst[0] += a;
+  dst[1] += b;
+  dst[2] += c;
+  dst[3] += d;
+}
 }  // namespace w2l
