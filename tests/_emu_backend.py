@@ -511,6 +511,7 @@ GEMM_SUBS = [(r'asm volatile\("bar\.sync 1, 128;" ::: "memory"\);', "emu::named_
 GEMM_POST = r"""
 extern "C" const char* emu_last_error() { return w2l::g_err; }
 extern "C" long long emu_launch_count() { return w2l::g_launches; }
+extern "C" void emu_set_sm_budget(int sms) { w2l::g_sm_budget = sms; }
 """
 
 
@@ -579,13 +580,15 @@ def conv1d_wgrad(dy, x, desc, dw):
 _NAMES = ["im2col_ncw", "tm_to_ncw", "im2col_tm", "col2im_tm", "cast_bf16", "pack_wt", "bn_stats", "bn_finalize", "lens_chain",
           "bn_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "depthwise_fwd", "depthwise_dgrad",
           "depthwise_wgrad", "ctc_loss_raw", "greedy_decode"]
+_GEMM_NAMES = ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "ensure_gemm_scratch"]
 
 
-def install(monkeypatch):
-    """tests/_host_sim.py for the GEMMs, the emulated kernels for everything else"""
+def install(monkeypatch, gemm_too=True):
+    """Every ``functional`` entry point the models call answered by the library's own kernel source on the host; with
+    ``gemm_too=False`` the tcgen05 GEMMs stay with the torch restatement of tests/_host_sim.py"""
     import _host_sim
     F = _host_sim.install(monkeypatch)
-    for n in _NAMES:
+    for n in _NAMES + (_GEMM_NAMES if gemm_too else []):
         assert hasattr(F, n), n
         monkeypatch.setattr(F, n, globals()[n])
     return F

@@ -382,8 +382,9 @@ static inline void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static int g_sm_budget = 0;                                  // w2l_set_sm_budget stand-in (emu_set_sm_budget)
 static inline int num_sms() { return 148; }
-static inline int gemm_sms() { return 148; }
+static inline int gemm_sms() { return (g_sm_budget > 0 && g_sm_budget < 148) ? g_sm_budget : 148; }
 static inline int after_launch(const char*) {
   ++g_launches;
   return 0;

@@ -13,9 +13,16 @@ import _host_sim
 import _kernel_emu
 from oracle import w2l_oracle as O
 
-# "sim": every C-ABI call answered by the torch restatement; "emu": only the tcgen05 GEMMs restated, every other call runs the
-# library's own kernel source on the host (tests/_emu_backend.py)
+# "sim": every C-ABI call answered by the torch restatement of tests/_host_sim.py; "emu": every call runs the library's own
+# kernel source on the host (tests/_emu_backend.py) -- the tcgen05 implicit GEMMs included, through their own C wrappers
 BACKENDS = ["sim", pytest.param("emu", marks=pytest.mark.skipif(not _kernel_emu.available(), reason="needs g++ and the CUDA headers"))]
+
+
+def _gemm_launches(backend):
+    if backend != "emu":
+        return 0
+    import _emu_backend
+    return int(_emu_backend.gemm().lib.emu_launch_count())
 
 
 def _install(monkeypatch, backend):
@@ -43,6 +50,7 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
     _install(monkeypatch, backend)
+    launches0 = _gemm_launches(backend)
     g = golden(fixture)
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
     cfg = config.compose(overrides=["model.mid_layers=3"]).model
@@ -95,6 +103,8 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
         o, ol = model(x, il)
     assert rel_l2(o, g["eval:out"]) < 2e-2 and np.array_equal(ol.numpy(), g["eval:out_len"])
     assert model.scaling_factor == int(g["scaling_factor"])
+    if backend == "emu":                          # the GEMMs really went through the emulated conv_gemm_kernel: fwd + dgrad + wgrad per layer
+        assert _gemm_launches(backend) - launches0 >= 3 * len(layers)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)

@@ -118,3 +118,50 @@ def test_conv_fwd_dgrad_wgrad_source(B, T, Cin, Cout, k, d, pad):
     dw = torch.full((k, Cout, Cin), 3.0)
     E.conv1d_wgrad(dyc, xc, desc3, dw)
     assert rel_l2(dw, wr.grad.permute(2, 0, 1)) < 2e-5
+
+
+def test_conv_fwd_tail_split_source():
+    """the forward tail split (last wave of tiles cut along K, pieces summed in an fp32 scratch by the last arriver), forced on a
+    small problem by capping the persistent grid at 8 CTAs: 18 tiles = 2 full waves + 2 tiles -> 4 K-pieces each; plain store,
+    fused affine + clamp + BatchNorm statistics, twice (the arrival counters clean themselves)"""
+    import ctypes
+    lib = E.gemm().lib
+    g = torch.Generator().manual_seed(12)
+    B, T, Cin, Cout, k = 9, 200, 192, 256, 11
+    pad = k // 2
+    x = _bf(torch.randn(B, T, Cin, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    want = TF.conv1d(x.transpose(1, 2), w, padding=pad).transpose(1, 2)
+    xc, wc = x.to(torch.bfloat16), _pack_w(w, Cout)
+    E.ensure_gemm_scratch()
+    try:
+        lib.emu_set_sm_budget(8)
+        desc = make_desc(B, T, Cin, Cout, Cout, k, 1, T, -pad, T, 0, Cout, DT_F32, ACT_NONE)
+        assert lib.w2l_conv1d_fwd_tail_parts(ctypes.byref(desc)) == 4
+        for rep in range(2):
+            y = torch.zeros(B, T, Cout)
+            E.conv1d_fwd(xc, wc, desc, y)
+            assert rel_l2(y, want) < 2e-5
+        sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+        desc2 = make_desc(B, T, Cin, Cout, Cout, k, 1, T, -pad, T, 0, Cout, DT_BF16, ACT_CLAMP20)
+        y2 = torch.zeros(B, T, Cout, dtype=torch.bfloat16)
+        st = torch.zeros(2 * Cout)
+        E.conv1d_fwd(xc, wc, desc2, y2, scale=sc, shift=sh, bn_stats=st)
+        assert rel_l2(y2.float(), torch.clamp(want * sc + sh, 0, 20)) < 6e-3
+        yd = y2.double().reshape(-1, Cout)
+        assert torch.allclose(st[:Cout].double(), yd.sum(0), rtol=1e-4, atol=1e-2) and torch.allclose(st[Cout:].double(), (yd * yd).sum(0), rtol=1e-4)
+    finally:
+        lib.emu_set_sm_budget(0)
+    assert lib.w2l_conv1d_fwd_tail_parts(ctypes.byref(desc)) <= 1          # 18 tiles fit one wave of the full machine
+
+
+def test_conv_slab_mode_source():
+    """the opt-in resident-slab forward path (W2L_SLAB=1, read once per process): tap j's A operand is a descriptor that starts j*d
+    rows into a slab fetched once per channel chunk -- the conv cases above in a fresh interpreter"""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, W2L_SLAB="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-k", "conv_fwd_dgrad_wgrad_source or tail_split",
+                        "-p", "no:cacheprovider"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
