@@ -15,10 +15,15 @@ from oracle import w2l_oracle as O
 
 # "sim": every C-ABI call answered by the torch restatement of tests/_host_sim.py; "emu": every call runs the library's own
 # kernel source on the host (tests/_emu_backend.py) -- the tcgen05 implicit GEMMs included, through their own C wrappers
-BACKENDS = ["sim", pytest.param("emu", marks=pytest.mark.skipif(not _kernel_emu.available(), reason="needs g++ and the CUDA headers"))]
+# "cabi": the unmodified functional.py over the library's own extern "C" wrappers + kernels compiled for the host (tests/_emu_cabi.py)
+_NEEDS_GXX = pytest.mark.skipif(not _kernel_emu.available(), reason="needs g++ and the CUDA headers")
+BACKENDS = ["sim", pytest.param("emu", marks=_NEEDS_GXX), pytest.param("cabi", marks=_NEEDS_GXX)]
 
 
 def _gemm_launches(backend):
+    if backend == "cabi":
+        import _emu_cabi
+        return int(_emu_cabi.builds()[-1].lib.emu_launch_count())
     if backend != "emu":
         return 0
     import _emu_backend
@@ -26,6 +31,9 @@ def _gemm_launches(backend):
 
 
 def _install(monkeypatch, backend):
+    if backend == "cabi":
+        import _emu_cabi
+        return _emu_cabi.install(monkeypatch)
     if backend == "emu":
         import _emu_backend
         return _emu_backend.install(monkeypatch)
@@ -103,7 +111,7 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
         o, ol = model(x, il)
     assert rel_l2(o, g["eval:out"]) < 2e-2 and np.array_equal(ol.numpy(), g["eval:out_len"])
     assert model.scaling_factor == int(g["scaling_factor"])
-    if backend == "emu":                          # the GEMMs really went through the emulated conv_gemm_kernel: fwd + dgrad + wgrad per layer
+    if backend != "sim":                          # the GEMMs really went through the emulated conv_gemm_kernel: fwd + dgrad + wgrad per layer
         assert _gemm_launches(backend) - launches0 >= 3 * len(layers)
 
 
