@@ -129,6 +129,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_lib, "load", lambda: lib)
     monkeypatch.setattr(F, "_need_cuda", lambda *ts: None)
     monkeypatch.setattr(F, "_stream", lambda: None)
+    monkeypatch.setattr(F, "to_cuda", lambda t, who=None: t)
     monkeypatch.setattr(F, "torch", _TorchProxy())
     _keep.append({})                                   # the scratch registered with the emulated library must outlive the test
     monkeypatch.setattr(F, "_gemm_scratch", _keep[-1])

@@ -195,3 +195,36 @@ def test_head_block_standalone(monkeypatch):
     bref = b.clone().requires_grad_(True)
     torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), wref, bref).backward(g)
     assert rel_l2(blk.conv1.weight.grad, wref.grad) < 1e-2 and rel_l2(blk.conv1.bias.grad, bref.grad) < 1e-2
+
+
+@pytest.mark.skipif(not _kernel_emu.available(), reason="needs g++ and the CUDA headers")
+def test_training_step_and_decode_over_emulated_abi(monkeypatch):
+    """what __graft_entry__.smoke() does on cuda:0, on the host over the emulated C ABI: training_step (conv stack, CTC loss from the
+    library's kernels, greedy decode + WER/CER for the log), backward, then an eval forward whose transcripts must equal the oracle's
+    greedy decode of the same scores bit for bit"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    _install(monkeypatch, "cabi")
+    torch.manual_seed(0)
+    cfg = config.compose(overrides=["model.mid_layers=3", "optimizer=novograd"]).model
+    for l in cfg.layers:
+        l["dropout"] = 0.0
+    model = Wav2Letter(cfg).train()
+    model._optimizer = torch.optim.SGD(model.parameters(), lr=0.0)              # training_step logs the learning rate
+    x, il, tg, tl = O.synthetic_batch(3, 1, seed=1, ragged=True)
+    texts = ["".join(O.ENGLISH_LOWERCASE[c] for c in row[: int(n)].tolist()) for row, n in zip(tg, tl)]
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    loss = model.training_step((x, il, tg, tl, None, texts), 0)
+    loss.backward()
+    assert set(model.logged) >= {"train_loss", "train_cer", "train_wer", "train_len_ratio", "learning_rate"}
+    specs = O.w2l_layer_specs(3, dropout=0.0)
+    lp, ol = O.w2l_forward_bf16emu(x, il, sd0, specs, training=True)
+    ref = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(lp.transpose(0, 1), tg, ol, tl)
+    assert abs(loss.item() - ref.item()) < 5e-3 * abs(ref.item()), (loss.item(), ref.item())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    model.eval()
+    with torch.no_grad():
+        out, out_len = model(x, il)
+    hyp = model.ctc_decoder.decode(out, out_len)
+    want, _ = O.greedy_decode(out.numpy(), out_len.numpy())
+    assert hyp == want

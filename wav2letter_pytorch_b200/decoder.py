@@ -89,9 +89,7 @@ class GreedyDecoder(Decoder):
         if probs.dim() == 2:
             probs = probs.unsqueeze(0)
         if not probs.is_cuda:
-            if not torch.cuda.is_available():
-                raise RuntimeError("GreedyDecoder: a CUDA device is required (no CPU fallback)")
-            probs = probs.cuda()
+            probs = F.to_cuda(probs, "GreedyDecoder")              # host scores are uploaded; without a CUDA device this raises
         if sizes is not None and not torch.is_tensor(sizes):
             sizes = torch.as_tensor([int(s) for s in sizes], dtype=torch.int32)
         if sizes is not None:

@@ -30,6 +30,13 @@ def _need_cuda(*ts):
                                % t.device.type)
 
 
+def to_cuda(t, who="wav2letter_pytorch_b200"):
+    """host tensor -> current CUDA device; there is no CPU fallback, so without a device this raises"""
+    if not torch.cuda.is_available():
+        raise RuntimeError("%s: a CUDA device is required (no CPU fallback)" % who)
+    return t.cuda()
+
+
 # --------------------------------------------------------------------------------------------- decode
 def greedy_decode(scores, sizes=None, blank=0):
     """scores [N,T,C] fp32 cuda -> (argmax [N,T], tokens [N,T], offsets [N,T], counts [N]) int32 cuda.
