@@ -81,6 +81,22 @@ def test_ctc_source_random(ctc, N, T, S, C, want_threads, from_logits):
         check_ctc(ctc, lp, tg, il, tl, serial=True)
 
 
+@pytest.mark.parametrize("C", [33, 100, 128])
+def test_ctc_source_wide_alphabet_small_lattice(ctc, C):
+    """more classes than the CTA has threads (one warp for a short target): the serial schedule used to emit only the first
+    blockDim.x gradient columns and to stage only blockDim.x * 4 columns of each frame (found by running it here; C = 29, the
+    shipped label sets, was never affected)"""
+    g = torch.Generator().manual_seed(C)
+    N, T, S = 2, 40, 5
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g) * 1.5, -1)
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    il, tl = torch.tensor([40, 31], dtype=torch.int32), torch.tensor([5, 3], dtype=torch.int32)
+    tg[1, 3:] = 0
+    for serial in (False, True):
+        _, plan = check_ctc(ctc, lp, tg, il, tl, serial=serial)
+        assert plan["threads"] == 32
+
+
 def test_ctc_source_zero_length_input_and_renorm(ctc):
     """an utterance with input length 0 (grad exactly 0, feasible only for an empty target) and peaked frames long enough to
     cross several re-centring blocks"""

@@ -152,7 +152,7 @@ ctc_alpha_body(float* smem, int n, const float* __restrict__ lp2, int T, int Cp,
   float* s_bnd = ring + kRing * Cp;                     // [2][warps][2]
   float* s_red = s_bnd + 2 * 32 * 2;                    // [32]
   float* s_fin = s_red + 32;                            // [2]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const int Tn = max(0, min(T, in_len[n]));
   const int S = max(0, min((int)tstride, tg_len[n]));
   const int L = 2 * S + 1;
@@ -174,7 +174,8 @@ ctc_alpha_body(float* smem, int n, const float* __restrict__ lp2, int T, int Cp,
   const int cp_lanes = Cp >> 2;
 #pragma unroll
   for (int p = 0; p < kRing - 1; ++p) {
-    if (p < Tn && tid < cp_lanes) cp_async16(ring + p * Cp + tid * 4, lp_n + (int64_t)p * Cp + tid * 4);
+    if (p < Tn)
+      for (int q = tid; q < cp_lanes; q += nthreads) cp_async16(ring + p * Cp + q * 4, lp_n + (int64_t)p * Cp + q * 4);
     cp_async_commit();
   }
   cp_async_wait<kRing - 2>();
@@ -197,7 +198,8 @@ ctc_alpha_body(float* smem, int n, const float* __restrict__ lp2, int T, int Cp,
   }
   {  // keep the ring full
     int p = kRing - 1;
-    if (p < Tn && tid < cp_lanes) cp_async16(ring + (p % kRing) * Cp + tid * 4, lp_n + (int64_t)p * Cp + tid * 4);
+    if (p < Tn)
+      for (int q = tid; q < cp_lanes; q += nthreads) cp_async16(ring + (p % kRing) * Cp + q * 4, lp_n + (int64_t)p * Cp + q * 4);
     cp_async_commit();
     cp_async_wait<kRing - 2>();
   }
@@ -246,7 +248,8 @@ ctc_alpha_body(float* smem, int n, const float* __restrict__ lp2, int T, int Cp,
     }
     if (!(dbg & 2)) {
       int p = t + kRing - 1;
-      if (p < Tn && tid < cp_lanes) cp_async16(ring + (p % kRing) * Cp + tid * 4, lp_n + (int64_t)p * Cp + tid * 4);
+      if (p < Tn)
+        for (int q = tid; q < cp_lanes; q += nthreads) cp_async16(ring + (p % kRing) * Cp + q * 4, lp_n + (int64_t)p * Cp + q * 4);
       cp_async_commit();
       cp_async_wait<kRing - 2>();
     }
@@ -640,7 +643,7 @@ ctc_beta_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const 
 
   auto prefetch = [&](int p) {   // frame p -> ring slot p % kRing (lp2 row + this thread's alpha states)
     if (p >= 0) {
-      if (tid < cp_lanes) cp_async16(ring + (p % kRing) * Cp + tid * 4, lp_n + (int64_t)p * Cp + tid * 4);
+      for (int q = tid; q < cp_lanes; q += nthreads) cp_async16(ring + (p % kRing) * Cp + q * 4, lp_n + (int64_t)p * Cp + q * 4);
       float* adst = aring + (p % kRing) * nthreads * R + s0;
       const float* asrc = arow + (int64_t)p * Lp;
       if (R % 4 == 0) {
@@ -661,7 +664,10 @@ ctc_beta_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const 
 
   float b[R];
   double off = 0.0;
-  float soft_prev = 0.f;   // softmax value of the row emitted one step later (threads tid < C)
+  // softmax values of the row emitted one step later: thread tid owns columns tid, tid + nthreads, ... (C <= 128 and a CTA has at
+  // least 32 threads, so at most kEmitCols of them; with the usual 29 labels only the first is live)
+  constexpr int kEmitCols = 4;
+  float soft_prev[kEmitCols] = {0.f, 0.f, 0.f, 0.f};
 
   double aoff_t = aoff[Tn - 1], aoff_next = 0.0;   // software-pipelined: the load for t-1 is issued at step t
   for (int t = Tn - 1; t >= 0; --t) {
@@ -742,19 +748,27 @@ ctc_beta_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const 
       if (lane == 0 && gb > 0.f) atomicAdd(bin + blank, __float2uint_rn(fminf(gb, 1.5f) * kFix));
     }
     // emit the row completed at the previous step (t+1), then remember this row's softmax
-    if (tid < C) {
-      if (t < Tn - 1) {
-        uint32_t* bprev = bins + ((t + 1) & 1) * Cp;
-        g_n[(int64_t)(t + 1) * C + tid] = (soft_prev - (float)bprev[tid] * (1.f / kFix)) * gscale;
-        bprev[tid] = 0u;
+#pragma unroll
+    for (int q = 0; q < kEmitCols; ++q) {
+      const int c = tid + q * nthreads;
+      if (c < C) {
+        if (t < Tn - 1) {
+          uint32_t* bprev = bins + ((t + 1) & 1) * Cp;
+          g_n[(int64_t)(t + 1) * C + c] = (soft_prev[q] - (float)bprev[c] * (1.f / kFix)) * gscale;
+          bprev[c] = 0u;
+        }
+        soft_prev[q] = exp2f(row[c]);
       }
-      soft_prev = exp2f(row[tid]);
     }
     prefetch(t - (kRing - 1));
     cp_async_wait<kRing - 2>();
     __syncthreads();
   }
-  if (tid < C) g_n[tid] = (soft_prev - (float)bins[tid] * (1.f / kFix)) * gscale;   // row 0 (parity 0)
+#pragma unroll
+  for (int q = 0; q < kEmitCols; ++q) {                                              // row 0 (parity 0)
+    const int c = tid + q * nthreads;
+    if (c < C) g_n[c] = (soft_prev[q] - (float)bins[c] * (1.f / kFix)) * gscale;
+  }
 }
 
 __global__ void ctc_finish_kernel(const CtcMeta* __restrict__ meta, const int32_t* __restrict__ tg_len, int64_t tstride, int N,
