@@ -10,8 +10,27 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emulate-gpu", action="store_true", default=False,
+                     help="run the `-m gpu` tests on CPU tensors over the library's sources compiled for the host (tests/_fake_cuda.py)")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if config.getoption("--emulate-gpu"):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import _fake_cuda
+        _fake_cuda.enable()
+
+
+def pytest_collection_modifyitems(config, items):
+    if not config.getoption("--emulate-gpu"):
+        return
+    import _fake_cuda
+    skip = pytest.mark.skip(reason="sized for the real machine: not run under --emulate-gpu")
+    for item in items:
+        if any(s in item.nodeid for s in _fake_cuda.TOO_LARGE):
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")
