@@ -16,6 +16,8 @@ streams), and every kernel's source execute; only the hardware is missing.  Purp
 left must not meet the hardware with a typo in it, and the whole `-m gpu` suite doubles as a CPU regression suite for kernel work.
 Tests sized for the real machine are skipped (``TOO_LARGE``).  Nothing under wav2letter_pytorch_b200/ imports this module."""
 import contextlib
+import time
+import types
 
 import torch
 from torch.overrides import TorchFunctionMode
@@ -24,6 +26,8 @@ from torch.overrides import TorchFunctionMode
 TOO_LARGE = ["test_ctc_full_size_properties", "test_decode_full_size_properties", "test_conv_full_size_layer",
              "test_baseline_config1_forward_ctc_decode", "test_conv_slab_mode_opt_in", "test_ctc_random[False-64-750-225-29]",
              "test_ctc_random[True-64-750-225-29]", "test_peer_gradient_reducer_two_ranks"]
+# `-m gpu` tests that assert the ABSENCE of a CPU path (here every tensor answers is_cuda = True)
+NOT_APPLICABLE = ["test_ctc_module_matches_torch"]
 
 
 def _is_cuda_dev(d):
@@ -35,10 +39,13 @@ def _is_cuda_dev(d):
 
 
 class _FakeEvent:
+    """host clock instead of the device's: elapsed times are those of the emulation (meaningless as measurements, non-zero as numbers)"""
+
     def __init__(self, *a, **k):
-        pass
+        self.t = time.perf_counter()
 
     def record(self, *a, **k):
+        self.t = time.perf_counter()
         return self
 
     def synchronize(self):
@@ -51,7 +58,7 @@ class _FakeEvent:
         return True
 
     def elapsed_time(self, other):
-        return 0.0
+        return (other.t - self.t) * 1e3
 
 
 class _FakeStream:
@@ -130,7 +137,10 @@ def enable():
     c.current_stream = lambda *a, **k: _STREAM
     c.Stream = _FakeStream
     c.Event = _FakeEvent
-    c.mem_get_info = lambda *a, **k: (64 << 30, 180 << 30)
+    c.mem_get_info = lambda *a, **k: (1 << 20, 2 << 20)
+    c.get_device_properties = lambda *a, **k: types.SimpleNamespace(name="emulated sm_100a", multi_processor_count=148, total_memory=180 << 30,
+                                                                    major=10, minor=0)
+    c.get_device_name = lambda *a, **k: "emulated sm_100a"
     c.memory_stats = lambda *a, **k: {}
     c.empty_cache = lambda: None
     c.manual_seed_all = lambda *a, **k: None

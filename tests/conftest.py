@@ -31,6 +31,8 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if any(s in item.nodeid for s in _fake_cuda.TOO_LARGE):
             item.add_marker(skip)
+        if any(s in item.nodeid for s in _fake_cuda.NOT_APPLICABLE):
+            item.add_marker(pytest.mark.skip(reason="asserts that CPU tensors are rejected: not applicable under --emulate-gpu"))
 
 
 @pytest.fixture(scope="session")
