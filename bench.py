@@ -174,6 +174,9 @@ class ClockSampler:
                 "window": "samples inside the timed regions of this run (device-resident, serialized-roofline and e2e legs)"}
 
 
+RAGGED = False                                           # --ragged: SURVEY 8d's second run (masks / lengths exercised)
+
+
 def synthetic_batch(B, seconds, seed):
     from oracle.w2l_oracle import ENGLISH_LOWERCASE
     g = torch.Generator().manual_seed(seed)
@@ -182,14 +185,23 @@ def synthetic_batch(B, seconds, seed):
     tg = torch.randint(1, 29, (B, S), generator=g, dtype=torch.int32)
     il = torch.full((B,), T, dtype=torch.int32)
     tl = torch.full((B,), S, dtype=torch.int32)
-    texts = ["".join(ENGLISH_LOWERCASE[c] for c in row.tolist()) for row in tg]
+    if RAGGED:                                           # input lengths uniform in [0.6 T, T], targets in [S/2, S], zero padded as the collator does
+        il = torch.randint(int(0.6 * T), T + 1, (B,), generator=g, dtype=torch.int32)
+        tl = torch.randint(S // 2, S + 1, (B,), generator=g, dtype=torch.int32)
+        il[0], tl[0] = T, S
+        for n in range(B):
+            x[n, :, il[n]:] = 0
+            tg[n, tl[n]:] = 0
+    texts = ["".join(ENGLISH_LOWERCASE[c] for c in row[:int(n)].tolist()) for row, n in zip(tg, tl)]
     return x, il, tg, tl, texts
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_train_step_factory(mid_layers, B, seconds, seed=0):
+def cpu_train_step_factory(mid_layers, B, seconds, seed=0, arch="wav2letter"):
     """The reference's CPU path restated (oracle/w2l_oracle.py): fwd + CTC + greedy decode + backward + NovoGrad."""
     from oracle import w2l_oracle as O
+    if arch != "wav2letter":
+        return cpu_jasper_step_factory(arch, B, seconds, seed)
     specs = O.w2l_layer_specs(mid_layers)
     sd = O.w2l_init_state_dict(specs, seed=seed)
     names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
@@ -207,6 +219,42 @@ def cpu_train_step_factory(mid_layers, B, seconds, seed=0):
         grads = torch.autograd.grad(loss, [sd[k] for k in names])
         with torch.no_grad():
             O.novograd_step([sd[k] for k in names], list(grads), state, lr=1e-3, weight_decay=1e-3)
+        return float(loss.detach())
+
+    return step
+
+
+def cpu_jasper_step_factory(arch, B, seconds, seed=0):
+    """Same for Jasper (jasper.py:154-475 as restated by oracle.jasper_forward): the weights are those of this package's module
+    constructed on the host (reference-shaped state_dict, xavier-uniform init), the arithmetic is plain torch CPU fp32."""
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    ov = ["model=%s" % arch, "optimizer=novograd"] + (["model.mid_layers=15"] if arch == "jasper" else [])
+    cfg = config.compose(overrides=ov).model
+    torch.manual_seed(seed)
+    module = Jasper(cfg)
+    blocks = [dict(b) for b in list(cfg.jasper_blocks)[:int(cfg.mid_layers)]]
+    for b in blocks:
+        b["dropout"] = 0
+    specs = O.jasper_block_specs(blocks)
+    sd = {k: v.detach().clone().contiguous() for k, v in module.state_dict().items()}
+    del module
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    for k in names:
+        sd[k].requires_grad_(True)
+    x, il, tg, tl, _texts = synthetic_batch(B, seconds, seed)
+    crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)
+    state = [{} for _ in names]
+
+    def step():
+        lp, ol = O.jasper_forward(x, il, sd, specs, True)
+        loss = crit(lp.transpose(0, 1), tg, ol, tl)
+        O.greedy_collapse(lp.detach().argmax(-1).numpy(), ol.numpy())
+        grads = torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)
+        live = [(sd[k], g) for k, g in zip(names, grads) if g is not None]
+        with torch.no_grad():
+            O.novograd_step([p for p, _ in live], [g for _, g in live], state[:len(live)], lr=1e-3, weight_decay=1e-3)
         return float(loss.detach())
 
     return step
@@ -236,7 +284,7 @@ def run_cpu_arm(args, as_reference):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B = args.cpu_batch
-    step = cpu_train_step_factory(args.mid_layers, B, UTT_SEC)
+    step = cpu_train_step_factory(args.mid_layers, B, UTT_SEC, arch=args.model)
     for _ in range(args.warmup if as_reference else 1):
         step()
     n = args.steps if as_reference else 4                 # cpu_baseline leg of the GPU arm: 1 warm-up + 4 steps, about 10 s of CPU work
@@ -245,8 +293,9 @@ def run_cpu_arm(args, as_reference):
         step()
     dt = (time.perf_counter() - t0) / n
     value = B * UTT_SEC / dt
-    sample = ("oracle port (torch CPU fp32 + Python greedy loop): Wav2Letter mid_layers=%d train step, B=%d x %d s, mean of %d steps "
-              "after %d warm-up" % (args.mid_layers, B, UTT_SEC, n, args.warmup if as_reference else 1))
+    what = "Wav2Letter mid_layers=%d" % args.mid_layers if args.model == "wav2letter" else args.model
+    sample = ("oracle port (torch CPU fp32 + Python greedy loop): %s train step, B=%d x %d s%s, mean of %d steps after %d warm-up"
+              % (what, B, UTT_SEC, ", ragged lengths" if RAGGED else "", n, args.warmup if as_reference else 1))
     return dict(value=value, unit="audio-s/s", cores=cores, kind="port", sample=sample, ms_per_step=dt * 1e3)
 
 
@@ -512,6 +561,7 @@ def run_gpu_arm(args):
                                + " train step: fwd+CTC+greedy decode+WER/CER+bwd+NovoGrad, B=%d/GPU x %d s utterances, 64 mel bins, 225 labels"
                                % (BATCH, UTT_SEC),
                    "global_batch": world * BATCH, "parallelism": "dp%d" % world,
+                   "lengths": "ragged: inputs uniform in [0.6 T, T], targets in [S/2, S]; audio seconds counted as padded" if RAGGED else "full",
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
@@ -567,10 +617,13 @@ def main():
                     help="wav2letter = BASELINE config 2 (headline); jasper10x5 = config 3; jasper = the shipped separable yaml")
     ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=4, help="utterances in the bounded CPU sample")
     ap.add_argument("--strong", action="store_true", help="strong scaling: global batch 64 split over the ranks (default: weak, 64 per GPU)")
+    ap.add_argument("--ragged", action="store_true", help="input lengths uniform in [0.6 T, T], target lengths in [S/2, S] (default: all full)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-default", action="store_true")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: no warm-up floor, no e2e/default/CPU passes")
     args = ap.parse_args()
+    global RAGGED
+    RAGGED = bool(args.ragged)
     if args.profile:
         args.skip_cpu = args.skip_default = True
     else:
@@ -582,8 +635,10 @@ def main():
         line = {"impl": "reference", "metric": "audio-sec/sec per train step", "value": r["value"], "unit": "audio-s/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "Wav2Letter mid_layers=%d train step on the host CPU (bounded sample B=%d x %d s)"
-                                       % (args.mid_layers, args.cpu_batch, UTT_SEC)},
+                "config": {"workload": "%s train step on the host CPU (bounded sample B=%d x %d s)"
+                                       % ("Wav2Letter mid_layers=%d" % args.mid_layers if args.model == "wav2letter" else args.model,
+                                          args.cpu_batch, UTT_SEC),
+                           "lengths": "ragged" if RAGGED else "full"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
