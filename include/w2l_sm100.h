@@ -160,7 +160,9 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
 /* Backward-data with a second, transposed bf16 shadow wt [k, Cin_pad16, Cout_pad] (wt[k-1-j][ci][co] = w[j][co][ci],
  * written by w2l_pack_wt): both GEMM operands are then K-major, which the tensor pipe consumes ~30% faster than the
  * MN-major read of w2l_conv1d_dgrad (profiles/).  Passing B=1 with T_out = x_rows = y_rows = B*(T+pad) over a dy buffer
- * whose per-utterance tail rows are zero runs the whole batch as ONE flat row space (no per-utterance tile padding). */
+ * whose per-utterance tail rows are zero runs the whole batch as ONE flat row space (no per-utterance tile padding).
+ * dy rows hold Cout_pad columns (ldy >= Cout_pad, zero padded) or just Cout columns (Cout <= ldy < Cout_pad: hidden widths
+ * that are multiples of 8 but not of 16); in the latter case the tail of the last contraction chunk reads as zero. */
 int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream);
 int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d);

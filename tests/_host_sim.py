@@ -256,12 +256,13 @@ def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
 def conv1d_dgrad_wt(dy, wt, desc, dx):
     """dx[b, u, ci] = sum_j sum_co dy[b, u - off - j*dil, co] * w[j][co][ci]; wt [k, Cin_pad16, Cout_pad] = tap-reversed transpose"""
     d = desc
-    assert dy.dtype == BF16 and wt.dtype == BF16 and dy.shape[-1] == d.ldy and d.ldy >= d.Cout_pad >= 64
+    assert dy.dtype == BF16 and wt.dtype == BF16 and dy.shape[-1] == d.ldy and d.ldy >= d.Cout and d.Cout_pad >= 64
     assert wt.shape[0] == d.k and wt.shape[2] == d.Cout_pad and wt.shape[1] >= d.Cin
     assert dy.numel() == d.B * d.y_rows * d.ldy and dx.numel() == d.B * d.x_rows * d.Cin
-    g = dy.reshape(d.B, d.y_rows, d.ldy)[:, d.y_row_offset:d.y_row_offset + d.T_out, :d.Cout_pad]
-    a = _gather_taps(g.contiguous(), d.x_rows, d.k, d.dilation, -d.x_row_offset - (d.k - 1) * d.dilation)   # [B, x_rows, k, Cout_pad]
-    out = torch.einsum("bujo,jco->buc", a, wt[:, :d.Cin].float())
+    cols = d.Cout_pad if d.ldy >= d.Cout_pad else d.Cout      # rows narrower than Cout_pad: the missing columns read as zero
+    g = dy.reshape(d.B, d.y_rows, d.ldy)[:, d.y_row_offset:d.y_row_offset + d.T_out, :cols]
+    a = _gather_taps(g.contiguous(), d.x_rows, d.k, d.dilation, -d.x_row_offset - (d.k - 1) * d.dilation)   # [B, x_rows, k, cols]
+    out = torch.einsum("bujo,jco->buc", a, wt[:, :d.Cin, :cols].float())
     dx.view(d.B, d.x_rows, d.Cin).copy_(_r(out))
     return dx
 

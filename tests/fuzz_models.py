@@ -50,7 +50,7 @@ def w2l_case(ref, rnd):
     layers = []
     for i in range(n):
         k = rnd.choice([1, 3, 5, 7, 11, 13])
-        layers.append(dict(output_size=rnd.choice([64, 64, 80, 128, 144]), kernel_size=k, stride=2 if (i == 0 or rnd.random() < 0.2) else 1,
+        layers.append(dict(output_size=rnd.choice([64, 64, 72, 80, 128, 136]), kernel_size=k, stride=2 if (i == 0 or rnd.random() < 0.2) else 1,
                            dilation=rnd.choice([1, 1, 1, 2]) if k > 1 else 1, dropout=-1))
     cfg = rl.reference_model_cfg("wav2letter", mid_layers=n, dropout=-1)
     cfg["layers"] = rl.to_attr(layers)
@@ -79,7 +79,7 @@ def jasper_case(ref, rnd, seed):
         stride = 2 if (i == 0 or rnd.random() < 0.15) else 1
         sep = rnd.random() < 0.3
         k = rnd.choice([3, 5, 6, 10, 11]) if not sep else rnd.choice([5, 11, 12, 33])
-        b = dict(layer_size=rnd.choice([64, 64, 80, 128]), kernel_size=k, stride=stride, residual=(stride == 1 and i > 0 and rnd.random() < 0.6),
+        b = dict(layer_size=rnd.choice([64, 64, 72, 80, 128, 136]), kernel_size=k, stride=stride, residual=(stride == 1 and i > 0 and rnd.random() < 0.6),
                  separable=sep, repeat=rnd.choice([1, 1, 2, 3]))
         if stride == 1 and not sep and rnd.random() < 0.2:
             b["dilation"] = 2
@@ -136,7 +136,9 @@ def main():
             continue
         try:
             if a.family == "w2l":
-                T.check_w2l_golden(pkg, _Npz(g))
+                # bf16 storage error grows with depth (the committed 3-block fixture holds 3e-2 against the bf16-emulating oracle); the
+                # checker's second criterion -- no worse against the fp32 reference than 1.5x the emulation's own error -- stays as is
+                T.check_w2l_golden(pkg, _Npz(g), emu_tol=3e-2 * 2 ** max(0, len(conf) - 2))
             else:
                 T.check_jasper_golden(pkg, _Npz(g), seed=1000 * a.seed + c, emu_tol=0.25)
             print("ok  ", conf, flush=True)

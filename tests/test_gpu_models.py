@@ -46,7 +46,7 @@ def test_w2l_golden_train_eval(pkg, golden):
     check_w2l_golden(pkg, golden("w2l_small"))
 
 
-def check_w2l_golden(pkg, g):
+def check_w2l_golden(pkg, g, emu_tol=3e-2):
     """train step + eval forward of a small Wav2Letter against a fixture frozen from the unmodified reference"""
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
@@ -89,7 +89,7 @@ def check_w2l_golden(pkg, g):
             continue
         emu = emu_params[name].grad
         err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
-        assert err_emu < 3e-2, (name, err_emu)
+        assert err_emu < emu_tol, (name, err_emu)
         assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
     sd1 = {k[4:]: g[k] for k in g.files if k.startswith("sd1:")}
     for k, v in model.state_dict().items():

@@ -91,6 +91,12 @@ def test_w2l_strided_golden(pkg, golden):
     check_w2l_golden(pkg, golden("w2l_strided"))
 
 
+def test_w2l_narrow_golden(pkg, golden):
+    """Wav2Letter with hidden widths 72 / 136 / 72 (multiples of 8, not of 16) against the unmodified reference"""
+    from test_gpu_models import check_w2l_golden
+    check_w2l_golden(pkg, golden("w2l_narrow"))
+
+
 def test_jasper_strided_golden(pkg, golden):
     """Jasper with a strided dense block (repeat 2: both repeats stride) and a strided separable block after the prologue"""
     from test_gpu_models import check_jasper_golden
@@ -128,3 +134,10 @@ def test_head_block_standalone(pkg):
     torch.nn.functional.conv1d(x.to(torch.bfloat16).float(), wref, bref).backward(g)
     assert float((blk.conv1.weight.grad.cpu() - wref.grad).norm() / wref.grad.norm()) < 1e-2
     assert float((blk.conv1.bias.grad.cpu() - bref.grad).norm() / bref.grad.norm()) < 1e-2
+
+
+def test_conv_backward_narrow_rows(F):
+    """hidden widths that are multiples of 8 but not of 16 (e.g. 72): backward-data reads dy rows of Cout columns against weights
+    packed with Cout_pad columns -- the tail of the last contraction chunk comes from TMA's out-of-bounds zero fill"""
+    from test_kernel_emu_gemm import _narrow_rows_case
+    _narrow_rows_case(F.conv1d_dgrad_wt, F.conv1d_wgrad, F.pack_wt, "cuda")

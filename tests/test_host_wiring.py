@@ -53,7 +53,7 @@ def _load_sd(model, g, prefix):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided"])
+@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided", "w2l_narrow"])
 def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, backend):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter

@@ -120,6 +120,33 @@ def test_conv_fwd_dgrad_wgrad_source(B, T, Cin, Cout, k, d, pad):
     assert rel_l2(dw, wr.grad.permute(2, 0, 1)) < 2e-5
 
 
+def _narrow_rows_case(conv1d_dgrad_wt, conv1d_wgrad, pack_wt, dev):
+    """hidden width 72 (a multiple of 8, not of 16): dy rows carry 72 columns while the weights are packed with Cout_pad = 80"""
+    g = torch.Generator().manual_seed(72)
+    B, T, Cin, Cout, k, d, pad = 2, 90, 136, 72, 5, 1, 2
+    x = _bf(torch.randn(B, T, Cin, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    xr, wr = x.transpose(1, 2).clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y = TF.conv1d(TF.pad(xr, (pad, pad)), wr, dilation=d)
+    dy = _bf(torch.randn(B, Cout, T, generator=g))
+    y.backward(dy)
+    cout_pad, cin_pad = 80, 144
+    dyc = dy.transpose(1, 2).to(torch.bfloat16).contiguous().to(dev)                 # [B, T, 72]: row pitch == Cout < Cout_pad
+    desc = make_desc(B, T, Cin, Cout, cout_pad, k, d, T, -pad, T, 0, Cout)
+    wt = torch.full((k, cin_pad, cout_pad), 9.0, dtype=torch.bfloat16, device=dev)
+    pack_wt(w.permute(2, 0, 1).contiguous().to(dev), wt, Cout, Cin)
+    dx = torch.full((B, T, Cin), float("nan"), dtype=torch.bfloat16, device=dev)
+    conv1d_dgrad_wt(dyc, wt, desc, dx)
+    assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 6e-3
+    dw = torch.full((k, Cout, Cin), 3.0, device=dev)
+    conv1d_wgrad(dyc, x.to(torch.bfloat16).to(dev), desc, dw)
+    assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
+
+
+def test_conv_backward_narrow_rows_source():
+    _narrow_rows_case(E.conv1d_dgrad_wt, E.conv1d_wgrad, E.pack_wt, "cpu")
+
+
 def test_conv_fwd_tail_split_source():
     """the forward tail split (last wave of tiles cut along K, pieces summed in an fp32 scratch by the last arriver), forced on a
     small problem by capping the persistent grid at 8 CTAs: 18 tiles = 2 full waves + 2 tiles -> 4 K-pieces each; plain store,

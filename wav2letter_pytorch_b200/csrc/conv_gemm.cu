@@ -865,13 +865,16 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   if (rc) return rc;
   W2L_REQUIRE(dy && wt && dx, "conv1d_dgrad_wt: null pointer");
   W2L_REQUIRE(d->Cout_pad >= 64 && d->Cout_pad % 8 == 0, "conv1d_dgrad_wt: Cout_pad=%d must be >= 64", d->Cout_pad);
-  W2L_REQUIRE(d->ldy >= d->Cout_pad, "conv1d_dgrad_wt: dy row pitch %d < Cout_pad %d", d->ldy, d->Cout_pad);
+  W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_dgrad_wt: dy row pitch %d < Cout %d", d->ldy, d->Cout);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   plan_rings(p, d->k, d->dilation, true);
   {
+    // dy rows normally carry Cout_pad columns (zero padded); a row of only Cout columns (a hidden width that is a multiple of 8 but
+    // not of 16) is declared as such, and the tail of the last contraction chunk reads as zero (TMA out-of-bounds fill)
     const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
-    uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)d->T_out, (uint64_t)d->B};
+    const int a_cols = d->ldy >= d->Cout_pad ? d->Cout_pad : d->Cout;
+    uint64_t dims[3] = {(uint64_t)a_cols, (uint64_t)d->T_out, (uint64_t)d->B};
     uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
     uint32_t box[3] = {kBlockK, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
     rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);

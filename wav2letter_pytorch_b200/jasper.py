@@ -106,8 +106,8 @@ class JasperBlock(nn.Module):
             raise NotImplementedError("grouped (shuffled) Jasper sub-blocks are not reachable from Jasper._build_encoder and not implemented")
         if residual_mode != "add" or len(residual_panes) != 0:
             raise NotImplementedError("only the plain 'add' residual is implemented")
-        if planes % 16 or planes < 64 or (inplanes % 8) or inplanes < 64:
-            raise ValueError("JasperBlock: widths (%d -> %d) must be >= 64, multiples of 8 / 16 for the tensor-core path" % (inplanes, planes))
+        if planes % 8 or planes < 64 or (inplanes % 8) or inplanes < 64:
+            raise ValueError("JasperBlock: widths (%d -> %d) must be >= 64 and multiples of 8 for the tensor-core path" % (inplanes, planes))
         kernel_size = compute_new_kernel_size(kernel_size, float(kernel_size_factor))
         pad = get_same_padding(kernel_size, stride, dilation)
         self.conv_mask, self.separable, self.residual_mode = conv_mask, separable, residual_mode

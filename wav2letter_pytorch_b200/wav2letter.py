@@ -41,8 +41,8 @@ class Conv1dBlock(nn.Module):
         self.batch_norm = BatchNormParams(output_channels, eps=0.001, momentum=0.9) if bn else nn.Identity()
         self.has_bn = bn
         self.next_pad = (0, 0)       # reflect halo the consumer block wants; set by the owning model
-        if bn and (output_channels % 16 or output_channels < 64):
-            raise ValueError("Conv1dBlock: hidden width %d must be a multiple of 16 and >= 64 for the tensor-core path" % output_channels)
+        if bn and (output_channels % 8 or output_channels < 64):         # 16-byte (8 x bf16) vectors in every memory-bound pass
+            raise ValueError("Conv1dBlock: hidden width %d must be a multiple of 8 and >= 64 for the tensor-core path" % output_channels)
 
     # ---- geometry
     def out_rows(self, t_in):
