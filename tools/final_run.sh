@@ -7,6 +7,9 @@ timeout 600 python bench.py --steps 20 --warmup 4 2>/dev/null | tail -1 > $O/fin
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $O/final_bench_reference.json
 timeout 600 python bench.py --model jasper10x5 --steps 8 --warmup 3 --skip-cpu 2>/dev/null | tail -1 > $O/final_bench_jasper10x5.json
 timeout 600 python bench.py --model jasper --steps 10 --warmup 3 --skip-cpu 2>/dev/null | tail -1 > $O/final_bench_jasper_sep.json
+# SURVEY 8d's second run: ragged lengths (Jasper's masks and the CTC length handling do real work)
+timeout 600 python bench.py --ragged --steps 20 --warmup 4 --skip-cpu --skip-default 2>/dev/null | tail -1 > $O/final_bench_w2l_ragged.json
+timeout 600 python bench.py --model jasper10x5 --ragged --steps 8 --warmup 3 --skip-cpu 2>/dev/null | tail -1 > $O/final_bench_jasper10x5_ragged.json
 timeout 300 python tools/yardstick_torch_cuda.py 2>&1 | tail -2 > $O/final_yardstick.txt
 timeout 120 python tools/microbench_features.py 2>&1 | tail -1 > $O/final_features.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/final_launches.csv python bench.py --profile --steps 1 --warmup 1 > /dev/null 2>&1
