@@ -1,9 +1,11 @@
-"""Strided layers beyond the first one (legal in the reference's Conv1dBlock / JasperBlock, absent from its shipped yamls):
-the unfold / fold kernels against the oracle's restatement of the same index arithmetic, and whole models against fixtures
-frozen from the unmodified reference (tests/golden/{w2l,jasper}_strided.npz, oracle/gen_golden.py:gen_strided).
+"""GPU tests written after round 1's last GPU session (they sort last on purpose, so that a surprise here cannot mask the rest of the
+suite): strided layers beyond the first one (legal in the reference's Conv1dBlock / JasperBlock, absent from its shipped yamls) --
+the unfold / fold kernels against the oracle's restatement of the same index arithmetic and whole models against fixtures frozen
+from the unmodified reference (tests/golden/{w2l,jasper}_strided.npz) --, the stand-alone head block, hidden widths that are
+multiples of 8 (w2l_narrow.npz), the CTC schedules with alphabets wider than a CTA, and conv shapes at the edges of the tiling.
 
-This file sorts last on purpose: these kernels were added after the last GPU session of round 1 and had not run on hardware
-when they were committed (they are exercised by no default config), so a failure here must not mask the rest of the suite."""
+None of them had run on hardware when committed; all of them run, through the unmodified host package and the library's own C
+wrappers and kernels compiled for the host, under `pytest -m gpu --emulate-gpu` (tests/_fake_cuda.py), which the CPU suite does."""
 import numpy as np
 import pytest
 import torch
@@ -141,3 +143,52 @@ def test_conv_backward_narrow_rows(F):
     packed with Cout_pad columns -- the tail of the last contraction chunk comes from TMA's out-of-bounds zero fill"""
     from test_kernel_emu_gemm import _narrow_rows_case
     _narrow_rows_case(F.conv1d_dgrad_wt, F.conv1d_wgrad, F.pack_wt, "cuda")
+
+
+@pytest.mark.parametrize("C", [33, 100, 128])
+def test_ctc_wide_alphabet_small_lattice(F, C, monkeypatch):
+    """more classes than the CTC CTA has threads (a one-warp lattice for a short target), both schedules: the serial one used to emit
+    only the first blockDim.x gradient columns (found on the host emulation, tests/test_kernel_emu_ctc_decode.py)"""
+    from test_gpu_kernels import _check_ctc
+    g = torch.Generator().manual_seed(C)
+    N, T, S = 2, 40, 5
+    lp = torch.log_softmax(torch.randn(N, T, C, generator=g) * 1.5, -1)
+    tg = torch.randint(1, C, (N, S), generator=g, dtype=torch.int32)
+    il, tl = torch.tensor([40, 31], dtype=torch.int32), torch.tensor([5, 3], dtype=torch.int32)
+    tg[1, 3:] = 0
+    _check_ctc(F, lp, tg, il, tl)
+    monkeypatch.setenv("W2L_CTC_DBG", "8")                      # the alpha -> beta+gradient schedule of very large lattices
+    _check_ctc(F, lp, tg, il, tl)
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,k,d,pl,pr", [(1, 1, 64, 1, 1, 1, 0, 0), (2, 2, 72, 8, 3, 1, 1, 1), (1, 5, 64, 130, 5, 2, 8, 0),
+                                                    (3, 17, 136, 29, 7, 1, 0, 6), (2, 129, 80, 272, 2, 3, 3, 0)])
+def test_conv_small_and_ragged_shapes(F, B, T, Cin, Cout, k, d, pl, pr):
+    """shapes at the edges of the tiling (one output row, one output channel, partial channel chunks, asymmetric zero padding) drawn
+    from the host-emulation fuzzer (tests/fuzz_kernels.py), against torch conv1d autograd on the same bf16-rounded operands"""
+    import torch.nn.functional as TF
+    from test_gpu_kernels import _bf, _pack_w, rel_l2
+    g = torch.Generator().manual_seed(B * T + Cin + k)
+    T_out = T + pl + pr - d * (k - 1)
+    x = _bf(torch.randn(B, T, Cin, generator=g))
+    w = _bf(torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5)
+    xr, wr = x.transpose(1, 2).clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y_ref = TF.conv1d(TF.pad(xr, (pl, pr)), wr, dilation=d)
+    dy = _bf(torch.randn(B, Cout, T_out, generator=g))
+    y_ref.backward(dy)
+    cout_pad, ldy, cin_pad = max(64, (Cout + 15) // 16 * 16), (Cout + 7) // 8 * 8, (Cin + 15) // 16 * 16
+    xc, wc = x.to(torch.bfloat16).cuda(), _pack_w(w, cout_pad).cuda()
+    y = torch.zeros(B, T_out, ldy, dtype=torch.float32, device="cuda")
+    F.conv1d_fwd(xc, wc, F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, ldy, F.DT_F32, F.ACT_NONE), y)
+    assert rel_l2(y[:, :, :Cout].cpu(), y_ref.detach().transpose(1, 2)) < 2e-5
+    dyc = torch.zeros(B, T_out, cout_pad, dtype=torch.bfloat16, device="cuda")
+    dyc[:, :, :Cout] = dy.transpose(1, 2).to(torch.bfloat16).cuda()
+    desc = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, cout_pad)
+    wt = torch.full((k, cin_pad, cout_pad), 9.0, dtype=torch.bfloat16, device="cuda")
+    F.pack_wt(w.permute(2, 0, 1).contiguous().cuda(), wt, Cout, Cin)
+    dx = torch.empty(B, T, Cin, dtype=torch.bfloat16, device="cuda")
+    F.conv1d_dgrad_wt(dyc, wt, desc, dx)
+    assert rel_l2(dx.float().cpu(), xr.grad.transpose(1, 2)) < 8e-3
+    dw = torch.full((k, Cout, Cin), 3.0, dtype=torch.float32, device="cuda")
+    F.conv1d_wgrad(dyc, xc, desc, dw)
+    assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
