@@ -108,9 +108,28 @@ class _TorchProxy:
         return raw[off:off + n]
 
     def empty(self, *shape, **kw):
+        """``torch.empty`` as functional.py calls it for outputs and workspaces -- POISONED (NaN / 0xFF bytes / a large negative
+        integer), so that a kernel which reads memory nobody wrote, or a wrapper that leaves part of an output unwritten, shows up in
+        the results instead of depending on what the allocator happened to hand back (compute-sanitizer's initcheck, on the host)"""
         if kw.get("dtype") is torch.uint8 and len(shape) == 1:
-            return self._aligned(torch.empty, shape[0], kw)
-        return torch.empty(*shape, **kw)
+            t = self._aligned(torch.empty, shape[0], kw)
+        else:
+            t = torch.empty(*shape, **kw)
+        if t.is_floating_point():
+            t.fill_(float("nan"))
+        elif t.dtype is torch.uint8:
+            t.fill_(0xFF)
+        elif t.dtype in (torch.int32, torch.int64, torch.int16):
+            t.fill_(-0x01010102)
+        return t
+
+    def empty_like(self, t, **kw):
+        out = torch.empty_like(t, **kw)
+        if out.is_floating_point():
+            out.fill_(float("nan"))
+        elif out.dtype is not torch.bool:
+            out.fill_(-0x01010102 if out.dtype is not torch.uint8 else 0xFF)
+        return out
 
     def zeros(self, *shape, **kw):
         if kw.get("dtype") is torch.uint8 and len(shape) == 1:

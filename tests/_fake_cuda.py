@@ -124,7 +124,18 @@ def enable():
     _GETTERS["is_cuda"] = torch._C.TensorBase.__dict__["is_cuda"]
     lib = _emu_cabi.library()
     _lib.load = lambda: lib
-    F.torch = _emu_cabi._TorchProxy()                    # 256-byte aligned byte buffers, as cudaMalloc gives and the C wrappers require
+    # every module of the package sees a `torch` whose empty() is poisoned (an unwritten output / a read of memory nobody wrote
+    # shows in the results) and hands out 256-byte aligned byte buffers (as cudaMalloc does and the C wrappers require)
+    import importlib
+    import pkgutil
+    import wav2letter_pytorch_b200 as pkg
+    proxy = _emu_cabi._TorchProxy()
+    for m in pkgutil.iter_modules(pkg.__path__):
+        if m.name.startswith("lib") or m.ispkg:            # the shared library sits in the package directory too
+            continue
+        mod = importlib.import_module("wav2letter_pytorch_b200." + m.name)
+        if getattr(mod, "torch", None) is torch:
+            mod.torch = proxy
     F._need_cuda = lambda *ts: None                      # (the function mode is not active inside autograd's backward calls)
     c = torch.cuda
     c.is_available = lambda: True
