@@ -23,6 +23,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "wav2letter_pytorch_b200", "csrc")
 HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+# W2L_EMU_ASAN=1: AddressSanitizer in the emulated kernels (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so) and
+# ASAN_OPTIONS=detect_leaks=0): tensors then come from ASan's allocator with red zones around them, so a kernel that reads or
+# writes past a buffer -- a vector access over the end of a row, an off-by-one tail -- aborts with a report (memcheck on the host)
+SANITIZE = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("W2L_EMU_ASAN") == "1" else []
+# W2L_EMU_UBSAN=1: UndefinedBehaviorSanitizer, above all its alignment check -- CUDA's vector types keep their alignment on the host,
+# so a 16-byte load / store through a pointer that is not 16-byte aligned (a misaligned-address fault on the GPU) is reported, as are
+# signed overflows and out-of-range shifts in the index arithmetic.  Reports go to stderr and abort (-fno-sanitize-recover).
+if os.environ.get("W2L_EMU_UBSAN") == "1":
+    SANITIZE += ["-fsanitize=undefined", "-fno-sanitize-recover=all", "-fno-sanitize=vptr,float-cast-overflow,float-divide-by-zero", "-g"]
 
 
 def _match(text, open_pos, open_ch, close_ch):
@@ -255,7 +264,7 @@ extern "C" int %s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, in
 """ % (sym, "".join(", " + p for p, _, _ in ps), spec, ", ".join(n for _, n, _ in ps)))
     code = "\n".join(parts)
     runtime = open(os.path.join(HERE, "kernel_emu_runtime.h")).read()
-    tag = hashlib.sha1((code + runtime).encode()).hexdigest()[:16]
+    tag = hashlib.sha1((code + runtime + " ".join(SANITIZE)).encode()).hexdigest()[:16]
     out_dir = os.path.join(tempfile.gettempdir(), "w2l_kernel_emu")
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "emu_%s.so" % tag)
@@ -264,8 +273,8 @@ extern "C" int %s(int emu_gx, int emu_gy, int emu_gz, int emu_bx, int emu_by, in
         with open(cpp, "w") as fh:
             fh.write(code)
         tmp = so + ".%d.tmp" % os.getpid()
-        r = subprocess.run(["g++", opt, "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + HERE, cpp, "-o", tmp],
-                           capture_output=True, text=True)
+        r = subprocess.run(["g++", opt, "-w", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + CUDA_INC, "-I" + HERE] + SANITIZE
+                           + [cpp, "-o", tmp], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host compilation of the kernel sources failed (%s):\n%s" % (cpp, r.stderr[-6000:]))
         os.replace(tmp, so)

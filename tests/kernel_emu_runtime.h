@@ -174,9 +174,28 @@ static int run_block(unsigned nthreads) {
     makecontext(&f.ctx, trampoline, 0);
   }
   const long long budget = n_yields + yield_budget;
+  // W2L_EMU_SCHEDULE=reverse | random[:seed]: the order in which the fibers of a block are resumed in every round.  A kernel whose
+  // result depends on it has a race (a missing barrier, or code that counts on a warp running in lockstep): racecheck, on the host.
+  static int sched_mode = -1;
+  static unsigned long long rng = 0x9E3779B97F4A7C15ull;
+  if (sched_mode < 0) {
+    const char* e = std::getenv("W2L_EMU_SCHEDULE");
+    sched_mode = !e ? 0 : (std::strncmp(e, "reverse", 7) == 0 ? 1 : (std::strncmp(e, "random", 6) == 0 ? 2 : 0));
+    if (sched_mode == 2 && e[6] == ':') rng ^= std::strtoull(e + 7, nullptr, 10) * 0xD1B54A32D192ED03ull;
+  }
+  std::vector<unsigned> order(nthreads);
+  for (unsigned i = 0; i < nthreads; ++i) order[i] = sched_mode == 1 ? nthreads - 1 - i : i;
   while (live > 0) {
     const long long ev0 = n_events;
-    for (unsigned i = 0; i < nthreads; ++i) {
+    if (sched_mode == 2)
+      for (unsigned i = nthreads - 1; i > 0; --i) {            // Fisher-Yates with a xorshift generator
+        rng ^= rng << 13;
+        rng ^= rng >> 7;
+        rng ^= rng << 17;
+        std::swap(order[i], order[rng % (i + 1)]);
+      }
+    for (unsigned k = 0; k < nthreads; ++k) {
+      const unsigned i = order[k];
       if (fibers[i].done) continue;
       cur = (int)i;
       tid = fibers[i].tid;

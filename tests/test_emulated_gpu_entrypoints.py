@@ -58,3 +58,15 @@ def test_bench_line_contract_on_the_emulated_gpu():
     # (--skip-cpu: the cpu_baseline / config1 legs run BASELINE-sized CPU work; tests/test_host_cpu.py covers that arm's contract)
     assert set(line["hbm_kernels"]) == {"ctc_loss_raw", "greedy_decode"} and all(v["achieved"] > 0 for v in line["hbm_kernels"].values())
     assert "default_config" in line and line["default_config"]["value"] > 0          # the literal mid_layers=1 config beside the stack
+
+
+def test_kernels_do_not_depend_on_the_thread_schedule():
+    """racecheck on the host: the CTC wavefront (tagged shared-memory slots polled across warps), the GEMM's mbarrier pipeline and the
+    block reductions must give the same answers when the fibers of a block are resumed in a random order every round
+    (W2L_EMU_SCHEDULE, tests/kernel_emu_runtime.h) -- a missing barrier, or code counting on a warp running in lockstep, would not"""
+    env = dict(os.environ, W2L_EMU_SCHEDULE="random:7")
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_kernel_emu_ctc_decode.py", "tests/test_kernel_emu_gemm.py",
+                        "tests/test_kernel_emu_elementwise.py", "-q", "-p", "no:cacheprovider", "-k", "not slab_mode"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT, env=env)
+    tail = r.stdout.strip().splitlines()[-1]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
