@@ -6,8 +6,8 @@
 conv: w2l_conv1d_fwd / _dgrad / _dgrad_wt / _wgrad through their own C wrappers vs torch conv1d autograd (T down to 1, Cout down
 to 1, partial channel chunks, asymmetric zero padding, dilation); ctc: both schedules vs nn.CTCLoss in fp64 (zero-length inputs
 and targets, infeasible pairs, repeated labels, 2..128 classes, logits or log-probs); elementwise: BatchNorm / activation / halo /
-mask forward + backward, layout kernels, depthwise conv, log_softmax, colsum vs the restatements.  A case with a single BatchNorm
-row (B*T = 1) fails `dz` by construction (both sides compute ~0 from cancelling terms)."""
+mask forward + backward, layout kernels, depthwise conv, log_softmax, colsum vs the restatements.  Combine with the sanitizer builds
+(tools/host_sanitizers.sh shows the environment) to look for out-of-bounds / misaligned accesses on odd shapes."""
 import argparse
 import os
 import random
@@ -132,7 +132,8 @@ def fuzz_elementwise(rnd, cases):
         dz_rows=T+rnd.choice([0,0,3])
         da=E.bn_act_bwd(dyp,z,fb[0],fb[1],fb[2],fb[3],gam,B,T,C,pl,pr,act,0.0,0,want_g=True,dz_rows=dz_rows,**kw)
         db=H.bn_act_bwd(dyp,z,fb[0],fb[1],fb[2],fb[3],gam,B,T,C,pl,pr,act,0.0,0,want_g=True,dz_rows=dz_rows,**kw)
-        nf+=close(da[0],db[0],1e-2,"dz",tag); nf+=close(da[1],db[1],1e-3,"red",tag); nf+=close(da[2],db[2],4e-3,"g",tag)
+        if B*T>1: nf+=close(da[0],db[0],1e-2,"dz",tag)      # one BatchNorm row: both sides compute ~0 from cancelling terms, no relative error to speak of
+    nf+=close(da[1],db[1],1e-3,"red",tag); nf+=close(da[2],db[2],4e-3,"g",tag)
         # layout
         F_=rnd.choice([5,8,64,80]); Tn=rnd.choice([3,17,64,201]); k=rnd.choice([1,3,11]); s=rnd.choice([1,2,3]); d=rnd.choice([1,2]); pad=rnd.randint(0,min(5,Tn-1)); mode=rnd.choice([0,1])
         x=torch.randn(B,F_,Tn,generator=g); rows=(Tn+2*pad-d*(k-1)-1)//s+1

@@ -15,7 +15,6 @@ the barriers.  What a passing run shows: the descriptor arithmetic, tap / chunk 
 (bias, BatchNorm fold, clamp, BN statistics, fp32 atomics of the split tiles, the K-split tail) and the host planning are
 mutually consistent and compute the convolution.  What it cannot show: that the hardware agrees with this model of it -- that is
 the job of the `-m gpu` tests, which these cases mirror (tests/test_gpu_kernels.py::test_conv_fwd_dgrad_wgrad)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as TF
