@@ -133,7 +133,7 @@ def fuzz_elementwise(rnd, cases):
         da=E.bn_act_bwd(dyp,z,fb[0],fb[1],fb[2],fb[3],gam,B,T,C,pl,pr,act,0.0,0,want_g=True,dz_rows=dz_rows,**kw)
         db=H.bn_act_bwd(dyp,z,fb[0],fb[1],fb[2],fb[3],gam,B,T,C,pl,pr,act,0.0,0,want_g=True,dz_rows=dz_rows,**kw)
         if B*T>1: nf+=close(da[0],db[0],1e-2,"dz",tag)      # one BatchNorm row: both sides compute ~0 from cancelling terms, no relative error to speak of
-    nf+=close(da[1],db[1],1e-3,"red",tag); nf+=close(da[2],db[2],4e-3,"g",tag)
+        nf+=close(da[1],db[1],1e-3,"red",tag); nf+=close(da[2],db[2],4e-3,"g",tag)
         # layout
         F_=rnd.choice([5,8,64,80]); Tn=rnd.choice([3,17,64,201]); k=rnd.choice([1,3,11]); s=rnd.choice([1,2,3]); d=rnd.choice([1,2]); pad=rnd.randint(0,min(5,Tn-1)); mode=rnd.choice([0,1])
         x=torch.randn(B,F_,Tn,generator=g); rows=(Tn+2*pad-d*(k-1)-1)//s+1
