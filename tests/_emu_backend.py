@@ -65,8 +65,8 @@ static inline void cp_async4(void* smem, const void* gmem) { std::memcpy(smem, g
 static inline void cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }     // ctc.cu:61  cp.async.cg 16 B (eager)
 static inline void cp_async_commit() {}                                                          // ctc.cu:64
 template <int N> static inline void cp_async_wait() {}                                           // ctc.cu:65
-static inline void slot_put(float4* slot, float v0, float v1, int tag) {                         // ctc.cu:292 st.volatile.shared.v4
-  *slot = make_float4(v0, v1, __int_as_float(tag), 0.f);
+static inline void slot_put(float4* slot, float v0, float v1, int tag, float w = 0.f) {          // ctc.cu:295 st.volatile.shared.v4
+  *slot = make_float4(v0, v1, __int_as_float(tag), w);
 }
 static inline float4 slot_load(const float4* slot) {                                             // ctc.cu:300 ld.volatile.shared.v4
   emu::yield_poll();                       // a poll lets the producing warp run (the hardware's warps run concurrently)
