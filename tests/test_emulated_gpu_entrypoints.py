@@ -65,8 +65,8 @@ def test_kernels_do_not_depend_on_the_thread_schedule():
     block reductions must give the same answers when the fibers of a block are resumed in a random order every round
     (W2L_EMU_SCHEDULE, tests/kernel_emu_runtime.h) -- a missing barrier, or code counting on a warp running in lockstep, would not"""
     env = dict(os.environ, W2L_EMU_SCHEDULE="random:7")
-    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_kernel_emu_ctc_decode.py", "tests/test_kernel_emu_gemm.py",
-                        "tests/test_kernel_emu_elementwise.py", "-q", "-p", "no:cacheprovider", "-k", "not slab_mode"],
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_kernel_emu_ctc_decode.py", "tests/test_kernel_emu_ctc_linear.py",
+                        "tests/test_kernel_emu_gemm.py", "tests/test_kernel_emu_elementwise.py", "-q", "-p", "no:cacheprovider", "-k", "not slab_mode"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=ROOT, env=env)
     tail = r.stdout.strip().splitlines()[-1]
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
