@@ -4,6 +4,7 @@ O=gpurun_out
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -4
 # experimental, opt-in paths (first hardware contact): the linear-domain CTC schedule (W2L_CTC_LINEAR)
 W2L_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zzz_ctc_linear.py -q -m gpu 2>&1 | tail -4
+W2L_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zzz_dw_tiled.py -q -m gpu 2>&1 | tail -4
 timeout 300 python __graft_entry__.py 2>&1 | tail -1
 timeout 600 python bench.py --steps 20 --warmup 4 2>/dev/null | tail -1 > $O/final_bench_w2l.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $O/final_bench_reference.json
@@ -12,6 +13,8 @@ timeout 600 python bench.py --model jasper --steps 10 --warmup 3 --skip-cpu 2>/d
 # SURVEY 8d's second run: ragged lengths (Jasper's masks and the CTC length handling do real work)
 timeout 600 python bench.py --ragged --steps 20 --warmup 4 --skip-cpu --skip-default 2>/dev/null | tail -1 > $O/final_bench_w2l_ragged.json
 timeout 600 python bench.py --model jasper10x5 --ragged --steps 8 --warmup 3 --skip-cpu 2>/dev/null | tail -1 > $O/final_bench_jasper10x5_ragged.json
+# register-tiled depthwise kernels (W2L_DW_TILED) on the shipped separable jasper.yaml: A/B on the same GPU
+bash tools/ab.sh W2L_DW_TILED 0 1 --model jasper > $O/final_ab_dw_tiled.txt 2>&1
 # CTC schedules side by side (same GPU, same call): log space (default) vs linear domain with / without the log-space redo
 for m in 0 1 2; do W2L_CTC_LINEAR=$m timeout 600 python tools/sweep_ctc_decode.py > $O/final_ctc_sweep_lin$m.md 2>&1; done
 timeout 300 python tools/yardstick_torch_cuda.py 2>&1 | tail -2 > $O/final_yardstick.txt
