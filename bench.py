@@ -14,6 +14,7 @@ conv implicit-GEMM kernels' achieved TFLOP/s (algorithmic FLOPs / CUDA-event tim
 region) against the measured bf16 peak; cpu_baseline = the oracle port timed on this box's host cores.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -323,7 +324,8 @@ class KernelTimer:
                     e0.record()
                     r = fn(*a, **k)
                     e1.record()
-                    self.spans.append((tag, e0, e1))
+                    d = a[2] if len(a) > 2 and isinstance(a[2], ctypes.Structure) else None   # the conv calls' w2l_conv_desc
+                    self.spans.append((tag, e0, e1, (d.B, d.T_out, d.Cin, d.Cout, d.k, d.dilation) if d is not None else None))
                     return r
                 return timed
             setattr(F, n, make(self._orig[n], n))
@@ -335,9 +337,29 @@ class KernelTimer:
 
     def totals_ms(self):
         out = {}
-        for tag, e0, e1 in self.spans:
+        for tag, e0, e1, _shape in self.spans:
             out[tag] = out.get(tag, 0.0) + e0.elapsed_time(e1)
         return out
+
+    def by_layer(self, steps, peak_tf):
+        """Per (pass, layer shape): calls, ms and TFLOP/s per step from the per-launch spans -- meaningful when nothing overlaps (the
+        serialized run).  FLOPs = 2*B*T_out*Cout*Cin*k of the call's own descriptor (the unfolded first layer has k folded into Cin;
+        backward-data over the flat row space counts its halo rows, +2..3 %)."""
+        acc = {}
+        for tag, e0, e1, shape in self.spans:
+            if shape is None:
+                continue
+            B, T_out, Cin, Cout, k, dil = shape
+            a = acc.setdefault((tag, Cin, Cout, k, dil), [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += 2.0 * B * T_out * Cout * Cin * k
+        rows = []
+        for (tag, Cin, Cout, k, dil), (n, ms, flops) in sorted(acc.items(), key=lambda kv: (kv[0][0], kv[0][1] * kv[0][3], kv[0][2])):
+            tf = flops / (ms / 1e3) / 1e12 if ms > 0 else 0.0
+            rows.append({"pass": tag, "Cin": Cin, "Cout": Cout, "k": k, "dilation": dil, "calls_per_step": n / steps, "ms_per_step": ms / steps,
+                         "tflops": tf, "frac": tf / peak_tf if peak_tf else None})
+        return rows
 
     def union_ms(self, prefix):
         """Time during which at least one call whose name starts with ``prefix`` was in flight.  Weight-gradient GEMMs run on
@@ -346,7 +368,7 @@ class KernelTimer:
         if not self.spans:
             return 0.0
         base = self.spans[0][1]
-        iv = sorted((base.elapsed_time(e0), base.elapsed_time(e1)) for tag, e0, e1 in self.spans if tag.startswith(prefix))
+        iv = sorted((base.elapsed_time(e0), base.elapsed_time(e1)) for tag, e0, e1, _shape in self.spans if tag.startswith(prefix))
         total, cur0, cur1 = 0.0, None, None
         for a, b in iv:
             if cur1 is None or a > cur1:
@@ -486,7 +508,7 @@ def run_gpu_arm(args):
     all_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     conv_ms = {k: v for k, v in all_ms.items() if k.startswith("conv1d")}
     # ---- the same GEMM launches without overlap (wgrad back on the compute stream): per-kernel quality, spans do not overlap
-    iso_ms = None
+    iso_ms, iso_layers = None, None
     if not args.profile:
         from wav2letter_pytorch_b200.layers import WgradStream
         was = WgradStream.enabled
@@ -499,6 +521,10 @@ def run_gpu_arm(args):
         iso_timer.unwrap()
         WgradStream.enabled = was
         iso_ms = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
+        try:                                               # a secondary table must never take the headline line down
+            iso_layers = iso_timer.by_layer(iso_steps, None)
+        except Exception as e:  # noqa: BLE001
+            iso_layers = {"error": repr(e)[:200]}
     # ---- end to end: pinned host inputs in, loss out, every step
     ms_e2e = ms if args.profile else timed(model, opt, reducer, args.steps, 1, True)
     sampling[0] = False                                   # the secondary tables below are launch-bound: not "under load"
@@ -598,6 +624,10 @@ def run_gpu_arm(args):
         a = train_flops * BATCH / (tot / 1e3) / 1e12
         line["roofline"]["serialized"] = {"achieved": a, "frac": a / peaks["tf_sustained"], "kernel_ms_per_step": tot, "by_pass_ms": iso_ms,
                                           "note": "same launches with wgrad on the compute stream (no overlap): sum of per-launch CUDA-event spans"}
+        if isinstance(iso_layers, list):                   # per layer shape and pass: L0 (k folded into Cin) and the k=1 head stand apart
+            for row in iso_layers:
+                row["frac"] = row["tflops"] / peaks["tf_sustained"]
+        line["roofline"]["serialized"]["by_layer"] = iso_layers
     if config1:
         line["config1"] = config1
     if extra:

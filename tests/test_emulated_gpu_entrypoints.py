@@ -54,7 +54,12 @@ def test_bench_line_contract_on_the_emulated_gpu():
     roof = line["roofline"]
     assert set(roof) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s"
     assert roof["achieved"] > 0 and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and "serialized" in roof
+    layers = roof["serialized"]["by_layer"]                                           # per (pass, layer shape): L0 and the head stand apart
+    assert isinstance(layers, list) and {r["pass"] for r in layers} >= {"conv1d_fwd", "conv1d_dgrad_wt", "conv1d_wgrad"}
+    assert all(r["tflops"] > 0 and r["ms_per_step"] > 0 and r["calls_per_step"] >= 1 for r in layers)
+    assert abs(sum(r["ms_per_step"] for r in layers) - roof["serialized"]["kernel_ms_per_step"]) < 1e-6 * roof["serialized"]["kernel_ms_per_step"] + 1e-9
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert line["config"]["ctc_schedule"] == "log-space"
     # (--skip-cpu: the cpu_baseline / config1 legs run BASELINE-sized CPU work; tests/test_host_cpu.py covers that arm's contract)
     assert set(line["hbm_kernels"]) == {"ctc_loss_raw", "greedy_decode"} and all(v["achieved"] > 0 for v in line["hbm_kernels"].values())
     assert "default_config" in line and line["default_config"]["value"] > 0          # the literal mid_layers=1 config beside the stack
