@@ -15,6 +15,7 @@ region) against the measured bf16 peak; cpu_baseline = the oracle port timed on 
 """
 import argparse
 import ctypes
+import inspect
 import json
 import os
 import subprocess
@@ -301,6 +302,13 @@ def run_cpu_arm(args, as_reference):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _bound(fn, a, k):
+    """the call's arguments by name, defaults filled in"""
+    ba = inspect.signature(fn).bind(*a, **k)
+    ba.apply_defaults()
+    return ba.arguments
+
+
 class KernelTimer:
     """CUDA-event timing of individual library calls on the launching stream (recorded inside the timed region)."""
 
@@ -308,6 +316,15 @@ class KernelTimer:
     # nll); greedy decode reads N*T*C fp32 and writes <= T int32 tokens + a count per utterance
     BYTES = {"ctc_loss_raw": lambda a: a[0].numel() * 8 + a[1].numel() * 4 + 12 * a[0].shape[0],
              "greedy_decode": lambda a: a[0].numel() * 4 + a[0].shape[0] * a[0].shape[1] * 4 + a[0].shape[0] * 4}
+
+    # elementwise companions of the GEMMs, from the call's bound arguments: BatchNorm apply + dropout + clamp/ReLU
+    # + next layer's halo reads z (+ the residual) and writes the padded activation; its backward reads dy (padded) and z twice (reduce,
+    # apply) and writes dz (+ the residual branch's gradient)
+    BYTES_BOUND = {
+        "bn_act_pad": lambda b: 2 * b["B"] * b["C"] * (b["T"] * (2 if b["res"] is not None else 1) + b["pad_left"] + b["T"] + b["pad_right"]),
+        "bn_act_bwd": lambda b: 2 * b["B"] * b["C"] * (2 * (b["pad_left"] + b["T"] + b["pad_right"] + b["T"])
+                                                     + (b["dz_rows"] or b["T"]) + (b["T"] if b["want_g"] else 0)),
+    }
 
     def __init__(self):
         self.spans = []
@@ -321,6 +338,8 @@ class KernelTimer:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     if tag in self.BYTES:
                         self.bytes[tag] = self.bytes.get(tag, 0) + self.BYTES[tag](a)
+                    elif tag in self.BYTES_BOUND:
+                        self.bytes[tag] = self.bytes.get(tag, 0) + self.BYTES_BOUND[tag](_bound(fn, a, k))
                     e0.record()
                     r = fn(*a, **k)
                     e1.record()
@@ -508,19 +527,21 @@ def run_gpu_arm(args):
     all_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
     conv_ms = {k: v for k, v in all_ms.items() if k.startswith("conv1d")}
     # ---- the same GEMM launches without overlap (wgrad back on the compute stream): per-kernel quality, spans do not overlap
-    iso_ms, iso_layers = None, None
+    iso_ms, iso_layers, iso_elem = None, None, {}
     if not args.profile:
         from wav2letter_pytorch_b200.layers import WgradStream
         was = WgradStream.enabled
         WgradStream.enabled = False
         iso_timer = KernelTimer()
         timed(model, opt, reducer, 0, 1, False)
-        iso_timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad"])
+        iso_timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "bn_act_pad", "bn_act_bwd"])
         iso_steps = max(3, min(args.steps, 6))
         timed(model, opt, reducer, iso_steps, 0, False)
         iso_timer.unwrap()
         WgradStream.enabled = was
-        iso_ms = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
+        iso_all = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
+        iso_ms = {k: v for k, v in iso_all.items() if k.startswith("conv1d")}
+        iso_elem = {k: (v, iso_timer.bytes.get(k, 0) / iso_steps) for k, v in iso_all.items() if not k.startswith("conv1d")}
         try:                                               # a secondary table must never take the headline line down
             iso_layers = iso_timer.by_layer(iso_steps, None)
         except Exception as e:  # noqa: BLE001
@@ -615,6 +636,14 @@ def run_gpu_arm(args):
                                         "ms_per_step": all_ms[tag], "algorithmic_bytes_per_step": timer.bytes[tag] // args.steps,
                                         "note": "CTC is serial in T (latency/MUFU bound at this batch), see DESIGN.md 3.2" if tag == "ctc_loss_raw" else
                                                 "5.6 MB per call: launch-latency bound at this size; profiles/ has the size sweep"}
+    for tag, label in (("bn_act_pad", "bn_act_pad_kernel x layers (BatchNorm apply + dropout + clamp/ReLU + residual + next layer's halo)"),
+                       ("bn_act_bwd", "bn_act_bwd_reduce + bn_act_bwd_apply x layers (activation/dropout/BatchNorm backward + halo fold)")):
+        if tag in iso_elem and iso_elem[tag][0] > 0:       # timed in the serialized run (nothing overlaps them there), all layers together
+            ms_t, by_t = iso_elem[tag]
+            gbs = by_t / (ms_t / 1e3) / 1e9
+            line["hbm_kernels"][tag] = {"kernel": label, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                        "ms_per_step": ms_t, "algorithmic_bytes_per_step": int(by_t),
+                                        "note": "spans of the host calls in the serialized run (the call also launches its small torch fills)"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):                                # dram bytes per launch from the committed ncu --set full capture
         with open(tr) as f:

@@ -61,7 +61,8 @@ def test_bench_line_contract_on_the_emulated_gpu():
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert line["config"]["ctc_schedule"] == "log-space"
     # (--skip-cpu: the cpu_baseline / config1 legs run BASELINE-sized CPU work; tests/test_host_cpu.py covers that arm's contract)
-    assert set(line["hbm_kernels"]) == {"ctc_loss_raw", "greedy_decode"} and all(v["achieved"] > 0 for v in line["hbm_kernels"].values())
+    assert set(line["hbm_kernels"]) == {"ctc_loss_raw", "greedy_decode", "bn_act_pad", "bn_act_bwd"}
+    assert all(v["achieved"] > 0 and v["algorithmic_bytes_per_step"] > 0 for v in line["hbm_kernels"].values())
     assert "default_config" in line and line["default_config"]["value"] > 0          # the literal mid_layers=1 config beside the stack
 
 
