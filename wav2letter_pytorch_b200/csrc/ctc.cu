@@ -540,12 +540,14 @@ ctc_lattice_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const in
 // Rows are spilled as mantissas plus one int32 exponent per thread and frame; the gradient pass multiplies them back together.
 // A state more than 2^126 below its own lane's maximum flushes to zero (in log space it would survive).  Two checks catch the cases
 // where that matters, and the utterance is then redone by the log-space kernels (CtcMeta::redo_*, predicated launches):
-//   * emissions of one lane's classes more than 2^120 apart in a single frame (the same loss in both recursions, so invisible below);
-//   * in the gradient pass the occupancies of every frame must sum to 1 -- mass that one recursion lost and the other still counts
-//     (or a likelihood that lost paths) shows up as a sum off 1.
+// (both in the gradient pass, which is parallel over frames -- the recursion's serial loop carries no checking code):
+//   * a frame in which a class of the utterance's lattice is live but more than 2^120 below the frame's largest emission (the same
+//     loss in both recursions, so invisible to the next check);
+//   * the occupancies of every frame must sum to 1 -- mass that one recursion lost and the other still counts (or a likelihood that
+//     lost paths) shows up as a sum off 1.
 // The log-space kernels stay the default.
 constexpr int kEmptyExp = -(1 << 28);
-constexpr float kLinSpread = -120.f;        // a live class this far (log2) below the largest emission of its lane in one frame: not held
+constexpr float kLinSpread = -120.f;        // a live class this far (log2) below the largest emission of its frame: not held
 
 __device__ __forceinline__ float pow2i(int x) {             // 2^x, x in [-127, 127]; -127 gives 0
   return __int_as_float((x + 127) << 23);
@@ -625,7 +627,6 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
   float* pbuf = smem;                                                     // [2][kBlk][Cp] log2-domain rows
   float4* slots = reinterpret_cast<float4*>(pbuf + 2 * kBlk * Cp);        // [33][kBlk]: one ring per warp + an always-ready dummy ring
   float* s_fin = reinterpret_cast<float*>(slots + 33 * kBlk);             // [4]: mantissa, exponent of alpha_T(L-1), alpha_T(L-2)
-  int* s_lost = reinterpret_cast<int*>(s_fin + 4);                        // [1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
   const int Tn = max(0, min(T, in_len[n]));
   const int S = max(0, min((int)tstride, tg_len[n]));
@@ -643,8 +644,6 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
     }
     return;
   }
-  if (tid == 0) *s_lost = 0;                  // (ordered before its use by the barriers of the block loop)
-  bool lost = false;
   int lab_b[R / 2];
   float skm[R / 2];
   {
@@ -738,8 +737,6 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
 #pragma unroll
       for (int r = 1; r < R; ++r) m = fmaxf(m, v[r]);
       const int ef = exp_field(m);
-#pragma unroll
-      for (int r = 0; r < R; ++r) lost |= (l0[r] > kDead) & (l0[r] - (float)ip < kLinSpread);
       e_pub = (mine && ef) ? ip : kEmptyExp;
       kpend = (mine && ef) ? ef - 127 : 0;
       e_eff = (mine && ef) ? e_pub + kpend : kEmptyExp;
@@ -771,14 +768,8 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
       const int ip = (int)floorf(fmaxf(mx, -1.0e6f));
       const float fip = (float)ip;
       const float pb = fast_ex2(lb - fip);
-      // range check: the smallest live emission of the lane (dead classes sit at kNeg, far below kDead)
-      float mn = lb > kDead ? lb : mx;
 #pragma unroll
-      for (int j = 0; j < R / 2; ++j) {
-        mn = fminf(mn, pl[j] > kDead ? pl[j] : mx);
-        pl[j] = fast_ex2(pl[j] - fip);
-      }
-      lost |= mn - fip < kLinSpread;
+      for (int j = 0; j < R / 2; ++j) pl[j] = fast_ex2(pl[j] - fip);
       float x1, x2 = 0.f;
       int xe;
       if (!BETA) {
@@ -804,7 +795,6 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
     __syncthreads();                          // every warp is done with block k's rows and slots
     prefetch_block(k + 2);
   }
-  if (lost) *s_lost = 1;
   if (!BETA) {                                // likelihood: alpha_T(L-1) + alpha_T(L-2), possibly held by two lanes with two exponents
     if (tid < 4) s_fin[tid] = (tid & 1) ? __int_as_float(kEmptyExp) : 0.f;
     __syncthreads();
@@ -827,11 +817,10 @@ lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int C
       const bool ok = sum > 0.0 && E > kEmptyExp / 2;
       meta[n].feasible = ok;
       meta[n].ll2 = ok ? log2(sum) + (double)E : 0.0;
-      meta[n].redo_a = (int16_t)(*s_lost || !ok);   // "infeasible" is the log-space kernels' call (rare: costs one utterance's redo)
+      meta[n].redo_a = (int16_t)!ok;          // "infeasible" is the log-space kernels' call (rare: costs one utterance's redo)
     }
-  } else {
-    __syncthreads();
-    if (tid == 0) meta[n].redo_b = (int16_t)*s_lost;
+  } else if (tid == 0) {
+    meta[n].redo_b = 0;                       // (the gradient pass raises the flags: see ctc_grad_lin_kernel)
   }
 }
 
@@ -990,7 +979,13 @@ ctc_grad_lin_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const i
     return;
   }
   const int32_t* tg = targets + (int64_t)n * tstride;
-  for (int s = tid; s < L; s += blockDim.x) lab[s] = (uint8_t)((s & 1) ? tg[s >> 1] : blank);
+  uint8_t* used = lab + ((L + 15) & ~15);                            // [Cp] 1 for the classes this utterance's lattice emits
+  for (int c = tid; c < Cp; c += blockDim.x) used[c] = (c == blank);
+  __syncthreads();
+  for (int s = tid; s < L; s += blockDim.x) {
+    lab[s] = (uint8_t)((s & 1) ? tg[s >> 1] : blank);
+    used[lab[s]] = 1;
+  }
   __syncthreads();
   const float gscale = reduction_mean ? 1.f / ((float)N * (float)max(S, 1)) : 1.f;
   const double ll2 = meta[n].ll2, ll_floor = floor(ll2);
@@ -1005,10 +1000,20 @@ ctc_grad_lin_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const i
       continue;
     }
     const float* lp_t = lp2 + ((int64_t)n * T + t) * Cp;
+    float rmax = kNeg, rmin = 0.f;            // the row's largest emission and the smallest LIVE one among the lattice's classes
     for (int c = lane; c < Cp; c += 32) {
-      row[c] = lp_t[c];
+      const float v = lp_t[c];
+      row[c] = v;
       bin[c] = 0u;
+      rmax = fmaxf(rmax, v);
+      rmin = fminf(rmin, (used[c] && v > kDead) ? v : 0.f);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+      rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    }
+    if (lane == 0 && rmin - rmax < kLinSpread) meta[n].redo_b = 1;
     __syncwarp();
     const float* a_t = alpha_ws + ((int64_t)n * T + t) * Lp;
     const float* b_t = beta_ws + ((int64_t)n * T + t) * Lp;
@@ -1305,13 +1310,13 @@ static int launch_ctc(const CtcPlan& pl, char* ws, int64_t N, int64_t T, int64_t
     float* beta = (float*)(ws + pl.off_beta);
     double* boff = (double*)(ws + pl.off_boff);
     const int gw = 8;
-    const size_t smem_g = (size_t)gw * pl.Cp * 8 + (size_t)(2 * tstride + 1 + 15);
+    const size_t smem_g = (size_t)gw * pl.Cp * 8 + (size_t)(2 * tstride + 1 + 15) + 16 + pl.Cp;   // rows, bins, lab (+ used, linear pass)
     W2L_REQUIRE(smem_g <= 48 * 1024, "ctc: gradient pass shared memory %zu too large", smem_g);
     dim3 grid((unsigned)((T + kGradFrames - 1) / kGradFrames), (unsigned)N);
     if (pl.linear) {
       int32_t* aexp = (int32_t*)(ws + pl.off_aexp);
       int32_t* bexp = (int32_t*)(ws + pl.off_bexp);
-      const size_t smem_ll = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + 8 * sizeof(float);
+      const size_t smem_ll = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + 4 * sizeof(float);
       W2L_CUDA(cudaFuncSetAttribute(ctc_lattice_lin_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
       ctc_lattice_lin_kernel<R><<<(unsigned)(2 * N), pl.threads, smem_ll, st>>>(lp2, (int)N, (int)T, pl.Cp, targets, tstride, in_len,
                                                                                tg_len, blank, alpha, aexp, beta, bexp, meta, pl.Lp);
