@@ -47,7 +47,9 @@ def sass(obj):
 
 
 def demangle(names):
-    out = subprocess.run(["c++filt"] + list(names), capture_output=True, text=True).stdout.splitlines()
+    if not names:
+        return {}
+    out = subprocess.run(["c++filt"] + list(names), capture_output=True, text=True, stdin=subprocess.DEVNULL).stdout.splitlines()
     return dict(zip(names, (re.sub(r"\(.*", "", o)[:70] for o in out)))
 
 
