@@ -539,8 +539,8 @@ ctc_lattice_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const in
 //     into the next step's scale factor, so it never sits on the chain; exponents are absolute integers: nothing drifts with T.
 // Rows are spilled as mantissas plus one int32 exponent per thread and frame; the gradient pass multiplies them back together.
 // A state more than 2^126 below its own lane's maximum flushes to zero (in log space it would survive).  Two checks catch the cases
-// where that matters, and the utterance is then redone by the log-space kernels (CtcMeta::redo_*, predicated launches):
-// (both in the gradient pass, which is parallel over frames -- the recursion's serial loop carries no checking code):
+// where that matters, and the utterance is then redone by the log-space kernels (CtcMeta::redo_*, predicated launches).  Both sit in
+// the gradient pass, which is parallel over frames, so the recursion's serial loop carries no checking code:
 //   * a frame in which a class of the utterance's lattice is live but more than 2^120 below the frame's largest emission (the same
 //     loss in both recursions, so invisible to the next check);
 //   * the occupancies of every frame must sum to 1 -- mass that one recursion lost and the other still counts (or a likelihood that
