@@ -43,6 +43,8 @@ int w2l_version(void);
 const char* w2l_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t w2l_launch_count(void);
+/* hash of the sources the library was built from (csrc/ + this header); wav2letter_pytorch_b200/_lib.py compares it with the tree */
+const char* w2l_source_hash(void);
 /* Cap on the SMs the persistent conv GEMM grids occupy (0 = all).  The data-parallel host sets it to
  * (#SM - collective CTAs) so that the gradient all-reduce running beside backward gets SMs of its own
  * (Lightning DDP's bucketed all-reduce overlapped with backward, README.md:40 / config.yaml:21). */

@@ -99,7 +99,9 @@ class FakeCudaMode(TorchFunctionMode):
                 return True
             return func(*args, **kwargs)
         if name == "cuda" and args and isinstance(args[0], torch.Tensor):
-            return args[0]
+            # a COPY, like the real thing: a raw pointer taken from a `.cuda()` temporary then dangles here too (the CPU allocator hands
+            # the freed block to the next temporary), which is how round 1's red GPU test would have been caught on the host
+            return args[0].clone()
         if name == "pin_memory" and args and isinstance(args[0], torch.Tensor):
             return args[0]
         if name == "is_pinned":

@@ -451,7 +451,7 @@ def test_depthwise_conv(F, B, T, C, k, s, d):
 
 
 # ------------------------------------------------------------------------------------------- feature front-end
-def test_features_golden_and_ragged_batch(golden):
+def test_features_golden_and_ragged_batch(F, golden):
     """GPU front-end vs the reference's SpectrogramExtractor (golden, same dither noise) and vs the oracle on a ragged batch"""
     from wav2letter_pytorch_b200.features import SpectrogramExtractor
     conf = dict(sample_rate=16000, window_size=0.02, window_stride=0.01, window="hamming")

@@ -199,6 +199,52 @@ def test_novograd_golden(pkg, golden):
     assert float(opt.state[p[0]]["max_exp_avg_sq"]) >= float(opt.state[p[0]]["exp_avg_sq"])
 
 
+def test_novograd_state_reload(pkg, golden):
+    """load_state_dict after a step must drop the cached fused-step plan (it aliases the OLD moments), and moments that arrive in
+    another memory layout than the parameter's (a checkpoint of the reference: contiguous [Cout,Cin,k]) are re-laid out"""
+    import copy
+    from wav2letter_pytorch_b200.novograd import Novograd
+    g = golden("novograd")
+    # parameter 0 is a permuted view over other-order storage, like the conv weights of this package
+    base = torch.from_numpy(g["p0:0"]).cuda()
+    perm = list(range(base.dim()))[::-1]
+    store = base.permute(*perm).contiguous()
+    p = [torch.nn.Parameter(store.permute(*perm)), torch.nn.Parameter(torch.from_numpy(g["p0:1"]).cuda())]
+    assert p[0].shape == base.shape and (base.dim() < 2 or not p[0].is_contiguous())
+    opt = Novograd(p, lr=0.01, betas=(0.95, 0.5), weight_decay=1e-3)
+
+    def run(step):
+        for i, q in enumerate(p):
+            q.grad = torch.from_numpy(g["g%d:%d" % (step, i)]).cuda()
+        opt.step()
+
+    run(0)
+    saved = copy.deepcopy(opt.state_dict())
+    for st in saved["state"].values():                       # what a checkpoint of the reference holds: contiguous moments
+        st["exp_avg"] = st["exp_avg"].contiguous().cpu()
+        st["exp_avg_sq"] = st["exp_avg_sq"].clone().cpu()
+    p1 = [q.detach().clone() for q in p]
+    run(1)
+    run(2)
+    with torch.no_grad():
+        for q, q1 in zip(p, p1):
+            q.copy_(q1)
+    opt.load_state_dict(saved)
+    run(1)
+    run(2)
+    for i, q in enumerate(p):
+        np.testing.assert_allclose(q.detach().cpu().numpy(), g["p3:%d" % i], rtol=1e-5, atol=1e-6)
+    assert opt.state[p[0]]["exp_avg"].stride() == p[0].stride()
+    # a gradient set that alternates (parameter 1 without a gradient for one step) must not revive a stale plan either
+    p[1].grad = None
+    p[0].grad = torch.ones_like(p[0])
+    opt.step()
+    v_before = float(opt.state[p[1]]["exp_avg_sq"])
+    run(2)
+    assert float(opt.state[p[1]]["exp_avg_sq"]) != v_before or v_before == 0.0
+    assert all(torch.isfinite(q).all() for q in p)
+
+
 def test_training_step_end_to_end(pkg):
     """training_step on a synthetic collated batch (data_loader.py:149-158 layout) with fused NovoGrad: loss decreases,
     weights and bf16 shadows move together, and the step matches the CPU oracle's first loss within the bf16 tolerance."""

@@ -66,11 +66,14 @@ def test_depthwise_dgrad_strided(F, B, T, C, k, s, d, pad):
         scale = np.abs(want).max() + 1e-6
         np.testing.assert_allclose(dx.float().cpu().numpy(), want, rtol=2.0 ** -7, atol=2.0 ** -9 * scale)
     if s == 1:                                                                   # the stride-1 kernel and the strided one agree
-        a = F.depthwise_dgrad(dy.cuda(), w.cuda(), T, k, d, pad, lens.cuda(), stride=1)
+        # device tensors are bound to names: a raw pointer taken from a `.cuda()` temporary dangles as soon as the temporary dies
+        dy_c, w_c, lens_c = dy.cuda(), w.cuda(), lens.cuda()
+        a = F.depthwise_dgrad(dy_c, w_c, T, k, d, pad, lens_c, stride=1)
         lib = F._lib.load()
         b = torch.empty_like(a)
-        F._lib.check(lib.w2l_depthwise_dgrad_strided(F._ptr(dy.cuda()), F._ptr(w.cuda()), F._ptr(b), B, T, C, T_out, k, 1, d, pad,
-                                                     F._ptr(lens.cuda()), F._stream()), "depthwise_dgrad_strided")
+        F._lib.check(lib.w2l_depthwise_dgrad_strided(F._ptr(dy_c), F._ptr(w_c), F._ptr(b), B, T, C, T_out, k, 1, d, pad,
+                                                     F._ptr(lens_c), F._stream()), "depthwise_dgrad_strided")
+        torch.cuda.synchronize()
         # same sums, taps visited in the opposite order: equal up to one bf16 rounding of an fp32 sum
         torch.testing.assert_close(a.float(), b.float(), rtol=2.0 ** -7, atol=2.0 ** -9 * float(a.float().abs().max()))
 

@@ -324,3 +324,20 @@ def test_get_time_per_word_matches_reference_semantics():
                 assert get_time_per_word(p, o, 0.5) == ref.decoder.get_time_per_word(p, o, 0.5)
     except ImportError:
         pass
+
+
+def test_jasper_unmasked_block_speaks_reference_state_dict_keys():
+    """conv_mask=False: the reference holds a bare nn.Conv1d (jasper.py:289-298), key `mconv.N.weight`; masked blocks say
+    `mconv.N.conv.weight` (jasper.py:96-105).  Checkpoints must load and save under those names."""
+    from wav2letter_pytorch_b200.jasper import JasperBlock
+    blk = JasperBlock(64, 64, repeat=2, kernel_size=5, residual=True, separable=False, conv_mask=False, activation=torch.nn.ReLU())
+    keys = set(blk.state_dict().keys())
+    assert {"mconv.0.weight", "mconv.4.weight", "res.0.0.weight"} <= keys and not any(".conv.weight" in k for k in keys)
+    sd = {k: torch.randn_like(v) if v.is_floating_point() else v for k, v in blk.state_dict().items()}
+    missing, unexpected = blk.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    assert torch.equal(blk.mconv[0].conv.weight.detach(), sd["mconv.0.weight"])
+    masked = JasperBlock(64, 64, repeat=1, kernel_size=5, residual=False, separable=True, conv_mask=True, activation=torch.nn.ReLU())
+    assert {"mconv.0.conv.weight", "mconv.1.conv.weight"} <= set(masked.state_dict().keys())
+    with pytest.raises(NotImplementedError):                 # activation-then-dropout differs from the fused order for a clamp
+        JasperBlock(64, 64, repeat=1, kernel_size=5, dropout=0.2)

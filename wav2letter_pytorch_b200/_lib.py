@@ -16,12 +16,38 @@ _lock = threading.Lock()
 _lib = None
 
 
+_HASH_TAG = b"W2L_SRC_HASH="
+
+
+def source_hash():
+    """sha256 (16 hex digits) over csrc/* and include/w2l_sm100.h: what the shared library was built from"""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(os.path.dirname(_HERE), "include", "w2l_sm100.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def built_hash(path=None):
+    """the source hash embedded in an existing shared library (read from the file, without loading it), or None"""
+    path = path or LIB_PATH
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return None
+    i = blob.find(_HASH_TAG)
+    return blob[i + len(_HASH_TAG): i + len(_HASH_TAG) + 16].decode(errors="replace") if i >= 0 else None
+
+
 def _needs_build():
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "w2l_sm100.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+    """a library is current only if it was built from exactly the sources in the tree (the prebuilt .so travels to the GPU box,
+    and the number measured there must come from HEAD's kernels)"""
+    return built_hash() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -33,16 +59,17 @@ def build(force=False, verbose=False):
     builddir = os.path.join(_HERE, "build")
     os.makedirs(builddir, exist_ok=True)
     procs = []
+    src_hash = source_hash()
     for src in SOURCES:
         obj = os.path.join(builddir, src.replace(".cu", ".o"))
         objs.append(obj)
         srcp = os.path.join(CSRC, src)
-        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
+        if not force and src != "runtime.cu" and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(srcp), os.path.getmtime(os.path.join(CSRC, "common.cuh")),
                 os.path.getmtime(os.path.join(os.path.dirname(_HERE), "include", "w2l_sm100.h"))):
             continue
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-               "-c", srcp, "-o", obj]
+               "-DW2L_SRC_HASH=\"%s\"" % src_hash, "-c", srcp, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -50,10 +77,14 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out.decode()))
         if verbose and out:
             print(out.decode())
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed: %s\n%s" % (" ".join(cmd), r.stdout.decode()))
+    os.replace(tmp, LIB_PATH)                   # a new inode: a process that has the old library mapped keeps a valid mapping
+    if built_hash() != src_hash:
+        raise RuntimeError("libw2l_sm100.so does not carry the hash of the sources it was just built from")
     return LIB_PATH
 
 
@@ -72,6 +103,7 @@ SIGNATURES = {
     "w2l_version": (c_i32, []),
     "w2l_last_error": (ctypes.c_char_p, []),
     "w2l_launch_count": (c_i64, []),
+    "w2l_source_hash": (ctypes.c_char_p, []),
     "w2l_set_sm_budget": (c_i32, [c_i32]),
     "w2l_get_sm_budget": (c_i32, []),
     "w2l_edit_distance_host": (c_i64, [c_ptr, c_i64, c_ptr, c_i64]),
@@ -134,6 +166,13 @@ def load():
         if _lib is None:
             if not os.path.exists(LIB_PATH):
                 build()
+            elif os.environ.get("W2L_ALLOW_STALE_LIB", "0") != "1" and _needs_build():
+                # never run (or measure) kernels that are not the ones in the tree: rebuild where nvcc exists, else fail loudly
+                try:
+                    build()
+                except Exception as e:  # noqa: BLE001
+                    raise RuntimeError("libw2l_sm100.so was built from other sources (%s) than the tree holds (%s) and could not be "
+                                       "rebuilt here: %s" % (built_hash(), source_hash(), e)) from e
             lib = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in SIGNATURES.items():
                 fn = getattr(lib, name)

@@ -54,16 +54,33 @@ struct CommPeers {
 
 // Flag slot [cta][src] of rank `dst` is written only by CTA `cta` of rank `src`.  Sequence numbers are compared as wrapped
 // differences so that the 32-bit counter may roll over.
-__device__ __forceinline__ void cta_barrier(const CommPeers& peers, int rank, int world, uint32_t seq) {
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Ranks must reach the same call within `timeout_ns` of each other (default 10 minutes, W2L_COMM_TIMEOUT_S): rank-0-only work
+// such as writing a checkpoint belongs between two host-side barriers, not between two training steps of the other ranks.
+// A waiting thread backs off with __nanosleep so that the polling CTAs leave the SM's issue slots to the GEMM CTAs beside them.
+__device__ __forceinline__ void cta_barrier(const CommPeers& peers, int rank, int world, uint32_t seq, uint64_t timeout_ns) {
   __syncthreads();
   if ((int)threadIdx.x < world) {
     const int r = threadIdx.x;
     __threadfence_system();
     st_release_sys(peers.flags[r] + blockIdx.x * world + rank, seq);
     const uint32_t* mine = peers.flags[rank] + blockIdx.x * world + r;
-    uint32_t spins = 0;
+    uint32_t spins = 0, nap = 32;
+    uint64_t t0 = 0;
     while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
-      if (++spins > (1u << 26)) __trap();        // a peer never arrived: fail the launch instead of hanging the box
+      if (++spins < 64) continue;                 // the common case: the peer is a few hundred nanoseconds away
+      __nanosleep(nap);
+      if (nap < 2048) nap <<= 1;
+      if ((spins & 1023u) == 0) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) __trap();  // a peer never arrived: fail the launch instead of hanging the box
+      }
     }
   }
   __syncthreads();
@@ -71,8 +88,9 @@ __device__ __forceinline__ void cta_barrier(const CommPeers& peers, int rank, in
 
 template <bool NVLS>
 __global__ void __launch_bounds__(kCommThreads)
-grad_allreduce_kernel(CommPeers peers, float* __restrict__ mc, int64_t offset, int64_t numel, int rank, int world, uint32_t seq) {
-  cta_barrier(peers, rank, world, seq);
+grad_allreduce_kernel(CommPeers peers, float* __restrict__ mc, int64_t offset, int64_t numel, int rank, int world, uint32_t seq,
+                      uint64_t timeout_ns) {
+  cta_barrier(peers, rank, world, seq, timeout_ns);
   const int64_t vecs = numel >> 2;                                    // 16-byte units; numel % 4 == 0 (host pads)
   const int64_t lo = vecs * rank / world, hi = vecs * (rank + 1) / world;
   const float inv = 1.f / (float)world;
@@ -115,7 +133,7 @@ grad_allreduce_kernel(CommPeers peers, float* __restrict__ mc, int64_t offset, i
         if (r < world) *reinterpret_cast<float4*>(peers.data[r] + offset + 4 * i) = acc;
     }
   }
-  cta_barrier(peers, rank, world, seq + 1);
+  cta_barrier(peers, rank, world, seq + 1, timeout_ns);
 }
 
 }  // namespace w2l
@@ -135,9 +153,14 @@ extern "C" int w2l_grad_allreduce(void* const* peer_data_host, void* const* peer
     W2L_REQUIRE(r >= world || (peers.data[r] && peers.flags[r]), "grad_allreduce: null pointer for peer %d", r);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static const uint64_t timeout_ns = [] {
+    const char* e = getenv("W2L_COMM_TIMEOUT_S");
+    const double sec = e && atof(e) > 0 ? atof(e) : 600.0;
+    return (uint64_t)(sec * 1e9);
+  }();
   if (multicast_base)
-    grad_allreduce_kernel<true><<<ctas, kCommThreads, 0, st>>>(peers, (float*)multicast_base, offset, numel, rank, world, seq);
+    grad_allreduce_kernel<true><<<ctas, kCommThreads, 0, st>>>(peers, (float*)multicast_base, offset, numel, rank, world, seq, timeout_ns);
   else
-    grad_allreduce_kernel<false><<<ctas, kCommThreads, 0, st>>>(peers, nullptr, offset, numel, rank, world, seq);
+    grad_allreduce_kernel<false><<<ctas, kCommThreads, 0, st>>>(peers, nullptr, offset, numel, rank, world, seq, timeout_ns);
   return after_launch("grad_allreduce_kernel");
 }

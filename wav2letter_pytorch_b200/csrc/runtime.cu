@@ -104,6 +104,13 @@ int make_tensor_map(CUtensorMap* map, const void* base, int elem_bytes, int rank
 
 extern "C" {
 int w2l_version(void) { return 100; }
+#ifndef W2L_SRC_HASH
+#define W2L_SRC_HASH "unknown"
+#endif
+// sha256 prefix of csrc/* + include/w2l_sm100.h at build time (_lib.source_hash): the loader refuses a library whose
+// sources are not the ones in the tree, so a measured number always belongs to the kernels of the commit that reports it
+static const char kSrcHash[] = "W2L_SRC_HASH=" W2L_SRC_HASH;
+const char* w2l_source_hash(void) { return kSrcHash + 13; }
 const char* w2l_last_error(void) { return w2l::g_err; }
 int64_t w2l_launch_count(void) { return w2l::g_launches.load(); }
 }

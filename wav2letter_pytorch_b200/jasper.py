@@ -87,6 +87,23 @@ class MaskedConv1d(nn.Module):
             self.conv = DepthwiseParams(in_channels, kernel_size, stride=stride, padding=padding, dilation=dilation)
         self.use_mask = use_mask
         self.heads = heads
+        if not use_mask:
+            # conv_mask=False: the reference builds a bare nn.Conv1d here (jasper.py:289-298), so its checkpoints say
+            # `mconv.N.weight` where this holder has `mconv.N.conv.weight` -- speak the reference's keys on both ways
+            self._register_state_dict_hook(self._flat_keys_out)
+            self._register_load_state_dict_pre_hook(self._flat_keys_in)
+
+    @staticmethod
+    def _flat_keys_out(module, state_dict, prefix, local_metadata):
+        for name in ("weight", "bias"):
+            if prefix + "conv." + name in state_dict:
+                state_dict[prefix + name] = state_dict.pop(prefix + "conv." + name)
+
+    @staticmethod
+    def _flat_keys_in(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for name in ("weight", "bias"):
+            if prefix + name in state_dict:
+                state_dict[prefix + "conv." + name] = state_dict.pop(prefix + name)
 
     def get_seq_len(self, lens):
         c = self.conv
@@ -120,6 +137,10 @@ class JasperBlock(nn.Module):
             self.act = F.ACT_CLAMP20
         else:
             raise NotImplementedError("activation %r is not implemented in the fused epilogues" % (activation,))
+        if self.act == F.ACT_CLAMP20 and self.dropout_p > 0:
+            # the reference applies activation THEN dropout (jasper.py:389-393); the fused pass applies dropout then activation,
+            # which is the same thing for ReLU (what Jasper._build_encoder always passes) but not for a clamp at 20
+            raise NotImplementedError("JasperBlock: Hardtanh(0, 20) with dropout > 0 is not implemented (use ReLU, or dropout=0)")
         # ModuleList positions mirror the reference so that checkpoints load:
         # [conv | depthwise, pointwise][bn][act, drop] * (repeat-1) + [conv | depthwise, pointwise][bn]
         mods, cin = [], inplanes

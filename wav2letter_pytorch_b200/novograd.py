@@ -38,34 +38,76 @@ class Novograd(Optimizer):
         self._plans.clear()
         return self
 
+    def load_state_dict(self, state_dict):
+        """Replaced optimizer state invalidates every cached step plan (they alias the old moments)."""
+        self._plans.clear()
+        super().load_state_dict(state_dict)
+        self._plans.clear()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__.setdefault("_conv_of", {})
+        self._plans = {}
+
+    def _plan_is_current(self, gi, plan, params):
+        """a cached plan may only be reused while the optimizer state it aliases is still the state: same exp_avg tensors, and
+        exp_avg_sq / max_exp_avg_sq still the 0-dim views into the plan's own vectors (a plan for another gradient set, or
+        state replaced by hand, breaks that)"""
+        ams = self.param_groups[gi]["amsgrad"]
+        for i, p in enumerate(params):
+            st = self.state.get(p)
+            if st is None or st.get("exp_avg") is not plan["m"][i]:
+                return False
+            sq = st.get("exp_avg_sq")
+            if not torch.is_tensor(sq) or sq.data_ptr() != plan["v"].data_ptr() + 4 * i:
+                return False
+            if ams:
+                mx = st.get("max_exp_avg_sq")
+                if not torch.is_tensor(mx) or mx.data_ptr() != plan["vmax"].data_ptr() + 4 * i:
+                    return False
+            sh = plan["shadow_of"][i]
+            if sh is not None and sh.packed().data_ptr() != plan["shadow_ptr"][i]:
+                return False
+        return True
+
     def _plan(self, gi, params):
         key = (gi, tuple(id(p) for p in params))
         plan = self._plans.get(key)
         if plan is not None:
-            return plan
+            if self._plan_is_current(gi, plan, params):
+                return plan
+            del self._plans[key]
         dev = params[0].device
         n = len(params)
         v = torch.zeros(n, dtype=torch.float32, device=dev)
         vmax = torch.zeros(n, dtype=torch.float32, device=dev)
-        shadows, convs = [], []
+        shadows, convs, shadow_of = [], [], []
         for i, p in enumerate(params):
             st = self.state[p]
             if "exp_avg" not in st:
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            elif "exp_avg_sq" in st:
-                v[i] = st["exp_avg_sq"]
+            else:
+                m = st["exp_avg"]
+                if m.stride() != p.stride() or m.dtype != torch.float32 or m.device != p.device:
+                    # e.g. a checkpoint written by the reference: contiguous [Cout,Cin,k] moments, while the kernel walks the
+                    # parameter's own (kernel-layout) storage order -- re-lay the moments out like the parameter
+                    st["exp_avg"] = torch.empty_like(p, memory_format=torch.preserve_format).copy_(m)
+                if "exp_avg_sq" in st:
+                    v[i] = torch.as_tensor(st["exp_avg_sq"], dtype=torch.float32).to(dev)
             st["exp_avg_sq"] = v[i]                      # 0-dim view, as in the reference's state layout
             if self.param_groups[gi]["amsgrad"]:
                 if "max_exp_avg_sq" in st:
-                    vmax[i] = st["max_exp_avg_sq"]
+                    vmax[i] = torch.as_tensor(st["max_exp_avg_sq"], dtype=torch.float32).to(dev)
                 st["max_exp_avg_sq"] = vmax[i]
             conv = self._conv_of.get(id(p))
             if conv is not None and conv.cout_pad == conv.out_channels:
                 shadows.append(conv.packed().data_ptr())
                 convs.append(conv)
+                shadow_of.append(conv)
             else:
                 shadows.append(0)
+                shadow_of.append(None)
                 if conv is not None:
                     convs.append(None)
         # pointer table rows: params, grads (rewritten every step), exp_avg, bf16 shadows, numel.  The pinned host
@@ -83,7 +125,8 @@ class Novograd(Optimizer):
         prefix = (torch.cumsum(counts, 0) - counts).to(torch.int32)
         plan = dict(hosts=hosts, turn=0, dev=torch.empty((5, n), dtype=torch.int64, device=dev), v=v,
                     chunk_prefix=prefix.to(dev), n_chunks=int(counts.sum()), vmax=vmax,
-                    ws=torch.empty(n, dtype=torch.float32, device=dev), convs=[c for c in convs if c is not None])
+                    ws=torch.empty(n, dtype=torch.float32, device=dev), convs=[c for c in convs if c is not None],
+                    m=[self.state[p]["exp_avg"] for p in params], shadow_of=shadow_of, shadow_ptr=shadows)
         self._plans[key] = plan
         return plan
 
