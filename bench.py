@@ -30,6 +30,8 @@ sys.path.insert(0, ROOT)
 
 UTT_SEC = 15
 BATCH = 64
+LEGS = None                    # test hook: [(key, arch, mid_layers, ragged)] instead of the config3 + ragged legs
+CONFIG5_POINTS = ((1, 200, 50), (512, 200, 50), (64, 750, 225), (64, 3000, 600), (512, 3000, 50), (512, 3000, 600))   # (N, T, S)
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -302,6 +304,44 @@ def run_cpu_arm(args, as_reference):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def reducer_report(reducer, dev, world, rank):
+    """Which gradient exchange this run uses, and -- for the library's own NVLink kernel -- a parity statement made on the very
+    reducer that is timed afterwards: the arena is filled with rank-dependent integers, every region goes through
+    ``w2l_grad_allreduce``, and the result must equal the exact mean bit for bit on every rank (DDP semantics, README.md:40)."""
+    import torch.distributed as dist
+    from wav2letter_pytorch_b200.distributed import PeerGradientReducer
+    if not isinstance(reducer, PeerGradientReducer):
+        return "nccl", "not applicable (NCCL all-reduce)"
+    kind = "peer-nvls" if reducer.multicast is not None else "peer-p2p"
+    try:
+        regions = list(reducer.entries.values()) + ([(reducer.small_off, reducer.small_numel)] if reducer.small_numel else [])
+        n = reducer.arena.numel()
+        idx = torch.arange(n, device=dev, dtype=torch.float32)
+        covered = torch.zeros(n, dtype=torch.bool, device=dev)
+        for off, numel in regions:
+            covered[off:off + numel] = True
+        bad = 0
+        for rep in range(2):
+            reducer.arena.copy_(((idx * 7 + rep) % 1021 - 510) * (rank + 1) * world)
+            torch.cuda.synchronize()
+            dist.barrier()
+            for off, numel in regions:
+                reducer.comm.wait_stream(torch.cuda.current_stream())
+                reducer._allreduce(off, numel)
+            reducer.comm.synchronize()
+            dist.barrier()
+            want = ((idx * 7 + rep) % 1021 - 510) * float(sum(range(1, world + 1)))
+            bad += int(((reducer.arena != want) & covered).sum())
+        reducer.arena.zero_()
+        t = torch.tensor([bad], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        bad = int(t.item())
+        return kind, ("ok: exact integer mean over %d ranks, %d arena regions, 2 rounds, bitwise on every rank" % (world, len(regions))
+                      if bad == 0 else "FAILED: %d elements differ from the exact mean" % bad)
+    except Exception as e:  # noqa: BLE001
+        return kind, "check raised: %r" % (e,)
+
+
 def _bound(fn, a, k):
     """the call's arguments by name, defaults filled in"""
     ba = inspect.signature(fn).bind(*a, **k)
@@ -401,6 +441,155 @@ class KernelTimer:
         return total
 
 
+def quick_leg(env, arch, mid, ragged, steps):
+    """A short secondary measurement inside the same process: ms/step and audio-s/s of a train step, the conv kernels' roofline
+    fraction (union of the CUDA-event spans, as the headline computes it) and -- from a serialized re-run -- the BatchNorm / activation
+    passes' achieved HBM GB/s."""
+    global RAGGED
+    from wav2letter_pytorch_b200.layers import WgradStream
+    F, build, one_step, barrier, dev, rank = (env[k] for k in ("F", "build", "one_step", "barrier", "dev", "rank"))
+    was, RAGGED = RAGGED, ragged
+    try:
+        xb, ilb, tgb, tlb, txt = synthetic_batch(BATCH, UTT_SEC, seed=rank)
+    finally:
+        RAGGED = was
+    batch = tuple(t.to(dev) for t in (xb, ilb, tgb, tlb))
+    model, opt, reducer = build(mid, arch)
+    flops = conv_flops_model(model, 1 + 100 * UTT_SEC)[1] * BATCH
+    peaks = measured_peaks()
+    conv_names = ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad"]
+
+    def run(n, names):
+        kt = KernelTimer()
+        kt.wrap(F, names)
+        try:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(n):
+                loss = one_step(model, opt, reducer, batch, it, txt)
+            e1.record()
+            barrier()
+        finally:
+            kt.unwrap()
+        return kt, e0.elapsed_time(e1) / n, float(loss.item())
+
+    for it in range(3):
+        one_step(model, opt, reducer, batch, it, txt)
+    barrier()
+    kt, ms, loss = run(steps, conv_names + ["ctc_loss_raw", "greedy_decode"])
+    if not (loss == loss and abs(loss) < 1e30):
+        raise RuntimeError("non-finite loss %r" % loss)
+    conv_ms = kt.union_ms("conv1d") / steps
+    tot = {k: v / steps for k, v in kt.totals_ms().items()}
+    out = {"workload": "%s train step, B=%d x %d s, %s lengths" % (arch if arch != "wav2letter" else "Wav2Letter mid_layers=%d" % mid, BATCH, UTT_SEC,
+                                                                   "ragged [0.6T, T] / [S/2, S]" if ragged else "full"),
+           "steps": steps, "warmup": 3, "ms_per_step": ms, "value": BATCH * UTT_SEC / (ms / 1e3), "unit": "audio-s/s", "loss_last_step": loss,
+           "conv": {"flops_per_step": flops, "kernel_ms_per_step": conv_ms, "achieved_tflops": flops / (conv_ms / 1e3) / 1e12 if conv_ms else None,
+                    "frac_sustained": flops / (conv_ms / 1e3) / 1e12 / peaks["tf_sustained"] if conv_ms else None,
+                    "frac_burst": flops / (conv_ms / 1e3) / 1e12 / peaks["tf_burst"] if conv_ms else None}}
+    for tag in ("ctc_loss_raw", "greedy_decode"):
+        if tot.get(tag):
+            out[tag] = {"ms_per_step": tot[tag], "GBps": kt.bytes[tag] / steps / (tot[tag] / 1e3) / 1e9,
+                        "frac_hbm": kt.bytes[tag] / steps / (tot[tag] / 1e3) / 1e9 / peaks["hbm"]}
+    enabled = WgradStream.enabled
+    WgradStream.enabled = False                            # serialized: the BatchNorm passes' spans overlap nothing
+    try:
+        one_step(model, opt, reducer, batch, 0, txt)
+        barrier()
+        kt2, _ms2, _ = run(3, ["bn_act_pad", "bn_act_bwd"])
+    finally:
+        WgradStream.enabled = enabled
+    for tag, v in kt2.totals_ms().items():
+        by = kt2.bytes.get(tag, 0) / 3
+        out[tag] = {"ms_per_step": v / 3, "GBps": by / (v / 3 / 1e3) / 1e9, "frac_hbm": by / (v / 3 / 1e3) / 1e9 / peaks["hbm"]}
+    del model, opt, reducer
+    torch.cuda.empty_cache()
+    return out
+
+
+def config5_corners(F, dev):
+    """Six corners of BASELINE config 5 (standalone CTC loss+grad and greedy decode over T x S x N, C=29, fp32 log-probs): this
+    library's kernels (ms, algorithmic GB/s of SURVEY 8d against the measured HBM peak) next to torch's own CUDA ``ctc_loss`` fwd+bwd
+    as the library yard-stick; L2 flushed between repetitions, best of 3."""
+    import torch.nn.functional as TF
+    peaks = measured_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    C = 29
+
+    def best_ms(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    rows = []
+    for N, T, S in CONFIG5_POINTS:
+        g = torch.Generator(device=dev).manual_seed(N + T)
+        lp = torch.log_softmax(torch.randn(N, T, C, generator=g, device=dev), -1)
+        il = torch.full((N,), T, dtype=torch.int32, device=dev)
+        tg = torch.randint(1, C, (N, S), generator=g, device=dev, dtype=torch.int32)
+        tl = torch.full((N,), S, dtype=torch.int32, device=dev)
+        t_ctc = best_ms(lambda: F.ctc_loss_raw(lp, tg, il, tl))
+        t_dec = best_ms(lambda: F.greedy_decode(lp, il))
+        lpr = lp.detach().clone().requires_grad_(True)
+
+        def torch_ctc():
+            lpr.grad = None
+            TF.ctc_loss(lpr.transpose(0, 1), tg, il, tl, blank=0, reduction="mean", zero_infinity=True).backward()
+        try:
+            t_torch = best_ms(torch_ctc)
+        except RuntimeError:
+            t_torch = None
+        ctc_b, dec_b = N * T * C * 8 + N * S * 4 + 12 * N, N * T * C * 4 + N * T * 4 + N * 4
+        rows.append({"N": N, "T": T, "S": S, "ctc_ms": t_ctc, "ctc_GBps": ctc_b / t_ctc / 1e6, "ctc_frac_hbm": ctc_b / t_ctc / 1e6 / peaks["hbm"],
+                     "torch_cuda_ctc_ms": t_torch, "ctc_speedup_vs_torch_cuda": (t_torch / t_ctc) if t_torch else None,
+                     "decode_ms": t_dec, "decode_GBps": dec_b / t_dec / 1e6, "decode_frac_hbm": dec_b / t_dec / 1e6 / peaks["hbm"]})
+        del lp, lpr
+    return {"workload": "CTC loss+grad and greedy decode, C=29 fp32, six corners of T x S x N", "hbm_peak_GBps": peaks["hbm"], "rows": rows}
+
+
+def loss_check(args, build, dev):
+    """Step-0 loss of the benchmarked architecture (same seed-0 weights, dropout off, train-mode BatchNorm) on two 15 s utterances:
+    the CUDA path against the CPU oracle with the same storage precision emulated.  Bound 1e-2 relative; a mismatch ends the run."""
+    from oracle import w2l_oracle as O
+    from wav2letter_pytorch_b200 import config
+    model, _opt, _red = build(args.mid_layers)
+    for m in model.modules():                              # dropout off for the check (the timed steps keep the yaml values)
+        if hasattr(m, "drop_out_prob"):
+            m.drop_out_prob = -1.0
+        if hasattr(m, "dropout_p"):
+            m.dropout_p = 0.0
+    sd = {k: v.detach().cpu().clone().contiguous() for k, v in model.state_dict().items()}
+    x, il, tg, tl = O.synthetic_batch(2, UTT_SEC, seed=123, ragged=True)
+    out, ol = model(x.to(dev), il.to(dev))
+    got = float(model.criterion(out.transpose(0, 1), tg.to(dev), ol, tl.to(dev)).item())
+    with torch.no_grad():
+        if args.model == "wav2letter":
+            lp, ol_ref = O.w2l_forward_bf16emu(x, il, sd, O.w2l_layer_specs(args.mid_layers, dropout=0.0), True)
+        else:
+            cfg = config.compose(overrides=["model=%s" % args.model] + (["model.mid_layers=15"] if args.model == "jasper" else [])).model
+            blocks = [dict(b) for b in list(cfg.jasper_blocks)[:int(cfg.mid_layers)]]
+            for b in blocks:
+                b["dropout"] = 0
+            lp, ol_ref = O.jasper_forward(x, il, sd, O.jasper_block_specs(blocks), True, emu=True)
+        want = float(torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(lp.transpose(0, 1), tg, ol_ref, tl))
+    rel = abs(got - want) / abs(want)
+    del model
+    torch.cuda.empty_cache()
+    if not rel < 1e-2:
+        raise SystemExit("bench.py: step-0 loss %.6f differs from the oracle's %.6f (rel %.2e > 1e-2)" % (got, want, rel))
+    return {"cuda": got, "oracle_bf16emu": want, "rel": rel, "bound": 1e-2,
+            "what": "train-mode forward + CTC loss, 2 x %d s ragged utterances, seed-0 weights, dropout off" % UTT_SEC}
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from oracle import w2l_oracle as O
@@ -447,9 +636,9 @@ def run_gpu_arm(args):
     resident = tuple(t.to(dev) for t in host)
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
 
-    def one_step(model, opt, reducer, batch, it):
+    def one_step(model, opt, reducer, batch, it, txt=None):
         opt.zero_grad(set_to_none=True)
-        loss = model.training_step(batch + (None, texts), it)
+        loss = model.training_step(batch + (None, texts if txt is None else txt), it)
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -467,6 +656,7 @@ def run_gpu_arm(args):
         bus = "%08X:%02X:%02X.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
     sampler, sampling = ClockSampler(local, bus), [True]
     step_spread = []                                      # (min, median, max) per-step ms of every timed region, in call order
+    loss_trace = []                                       # loss of the last step of every timed region (asserted finite)
 
     def timed(model, opt, reducer, steps, warmup, from_host):
         def batch():
@@ -493,6 +683,10 @@ def run_gpu_arm(args):
         barrier()
         if sampling[0]:
             sampler.mark(host_t0, time.perf_counter())
+        last = float(l.item())                            # after the timed region: a step that went numerically wrong must not print a number
+        if not (last == last and abs(last) < 1e30):
+            raise SystemExit("bench.py: non-finite loss %r inside a timed region" % last)
+        loss_trace.append(last)
         ms = e0.elapsed_time(e1) / steps
         per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         step_spread.append((min(per_step), sorted(per_step)[len(per_step) // 2], max(per_step)))
@@ -505,6 +699,7 @@ def run_gpu_arm(args):
     from wav2letter_pytorch_b200 import reserve_device_memory
     reserve_device_memory(dev, gib=int(os.environ.get("W2L_RESERVE_GIB", "64")))      # no cudaMalloc inside the timed steps
     model, opt, reducer = build(args.mid_layers)
+    reducer_kind, reducer_parity = reducer_report(reducer, dev, world, rank) if world > 1 else ("none (single GPU)", None)
     if args.model == "wav2letter":
         fwd_flops, train_flops = conv_flops_per_utt(O.w2l_layer_specs(args.mid_layers), 1 + 100 * UTT_SEC)
         assert abs(conv_flops_model(model, 1 + 100 * UTT_SEC)[1] / train_flops - 1) < 1e-9
@@ -561,6 +756,33 @@ def run_gpu_arm(args):
         extra = {"workload": "Wav2Letter mid_layers=1 (literal yaml default) train step, B=%d/GPU x %d s" % (BATCH, UTT_SEC),
                  "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s"}
         del m1, o1, r1
+
+    # ---- secondary legs the driver's single line must carry (N=1 only: the scaling runs stay lean): BASELINE config 3 (Jasper 10x5),
+    # SURVEY 8d's ragged run of the headline model, six corners of config 5's CTC / decode sweep, and the step-0 loss against the oracle
+    legs = {}
+    if world == 1 and not args.profile and not args.skip_legs:
+        try:
+            del model, opt, reducer
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        want = [("ragged", args.model, args.mid_layers, True)]
+        if args.model == "wav2letter":
+            want.insert(0, ("config3", "jasper10x5", 0, False))
+        if LEGS is not None:
+            want = LEGS
+        for key, arch, mid, ragged in want:
+            try:
+                legs[key] = quick_leg(dict(F=F, build=build, one_step=one_step, barrier=barrier, dev=dev, rank=rank), arch, mid, ragged,
+                                      steps=5)
+            except Exception as e:  # noqa: BLE001  (a secondary table must never take the headline line down)
+                legs[key] = {"error": repr(e)[:300]}
+        try:
+            legs["config5"] = config5_corners(F, dev)
+        except Exception as e:  # noqa: BLE001
+            legs["config5"] = {"error": repr(e)[:300]}
+        if not args.skip_cpu:
+            legs["loss_check"] = loss_check(args, build, dev)     # raises SystemExit on a mismatch: no number without parity
 
     # ---- BASELINE configs[0] (the reference's own CPU-runnable case): forward + CTCLoss + greedy decode to strings, batch 8 x 10 s,
     # eval mode, mid_layers 1 (literal default) and 20; ours on the GPU (host tensors in, strings out) next to the oracle port on the CPU
@@ -657,6 +879,19 @@ def run_gpu_arm(args):
             for row in iso_layers:
                 row["frac"] = row["tflops"] / peaks["tf_sustained"]
         line["roofline"]["serialized"]["by_layer"] = iso_layers
+        line["roofline"]["serialized"]["frac_vs_burst"] = a / peaks["tf_burst"]
+        if isinstance(iso_layers, list):                   # the record the driver keeps truncates long tails: worst rows up front
+            big = [r for r in iso_layers if r["ms_per_step"] > 0.05]
+            line["worst_layers"] = sorted(big, key=lambda r: r["tflops"])[:3]
+    line["reducer"] = reducer_kind
+    if reducer_parity is not None:
+        line["reducer_parity"] = reducer_parity
+    line["loss_last_step"] = {"value_leg": loss_trace[0] if loss_trace else None, "all_timed_regions": loss_trace}
+    line["roofline"]["frac_vs_burst"] = achieved / peaks["tf_burst"]
+    line["roofline"]["peak_burst"] = peaks["tf_burst"]
+    for key in ("config3", "ragged", "config5", "loss_check"):
+        if key in legs:
+            line[key] = legs[key]
     if config1:
         line["config1"] = config1
     if extra:
@@ -682,12 +917,13 @@ def main():
     ap.add_argument("--ragged", action="store_true", help="input lengths uniform in [0.6 T, T], target lengths in [S/2, S] (default: all full)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-default", action="store_true")
+    ap.add_argument("--skip-legs", dest="skip_legs", action="store_true", help="no config3 / ragged / config5 / loss-check legs")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: no warm-up floor, no e2e/default/CPU passes")
     args = ap.parse_args()
     global RAGGED
     RAGGED = bool(args.ragged)
     if args.profile:
-        args.skip_cpu = args.skip_default = True
+        args.skip_cpu = args.skip_default = args.skip_legs = True
     else:
         args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

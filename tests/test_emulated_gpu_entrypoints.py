@@ -41,7 +41,8 @@ def test_smoke_on_the_emulated_gpu():
 
 
 def test_bench_line_contract_on_the_emulated_gpu():
-    code = ("import bench; bench.BATCH = 2; bench.UTT_SEC = 1; "
+    code = ("import bench; bench.BATCH = 2; bench.UTT_SEC = 1; bench.LEGS = [('ragged', 'wav2letter', 2, True)]; "
+            "bench.CONFIG5_POINTS = ((1, 20, 5), (3, 40, 8)); "
             "sys.argv = ['bench.py', '--steps', '2', '--warmup', '3', '--mid-layers', '2', '--skip-cpu']; bench.main()")
     line = json.loads(_run(code).strip().splitlines()[-1])
     assert line["metric"] == "audio-sec/sec per train step" and line["unit"] == "audio-s/s" and line["higher_is_better"] is True
@@ -64,6 +65,12 @@ def test_bench_line_contract_on_the_emulated_gpu():
     assert set(line["hbm_kernels"]) == {"ctc_loss_raw", "greedy_decode", "bn_act_pad", "bn_act_bwd"}
     assert all(v["achieved"] > 0 and v["algorithmic_bytes_per_step"] > 0 for v in line["hbm_kernels"].values())
     assert "default_config" in line and line["default_config"]["value"] > 0          # the literal mid_layers=1 config beside the stack
+    # secondary legs of the same line (the driver only runs `bench.py --gpus N`): ragged run, config-5 corners, reducer, loss trace
+    rg = line["ragged"]
+    assert rg["value"] > 0 and rg["conv"]["frac_sustained"] > 0 and rg["bn_act_bwd"]["GBps"] > 0 and rg["ctc_loss_raw"]["GBps"] > 0, rg
+    assert len(line["config5"]["rows"]) == 2 and all(r["ctc_GBps"] > 0 and r["decode_GBps"] > 0 for r in line["config5"]["rows"])
+    assert line["reducer"].startswith("none") and all(v == v for v in line["loss_last_step"]["all_timed_regions"])
+    assert roof["frac_vs_burst"] > 0 and len(line["worst_layers"]) >= 1
 
 
 def test_kernels_do_not_depend_on_the_thread_schedule():

@@ -175,6 +175,36 @@ def test_decoder_interface(pkg, golden):
     assert dec.cer_ratio("ab cd", "ab d") == (1, 4) and dec.wer_ratio("ab cd", "ab d") == (1, 2)
 
 
+def test_prefix_beam_search_on_device_scores(pkg, golden):
+    """SURVEY 8f-4 behind the Decoder interface on the box that has the GPU: probabilities produced by the device (Jasper's eval-mode
+    softmax head, jasper.py:470-473) go through PrefixBeamSearchLMDecoder.decode as CUDA tensors; transcripts must equal the oracle's
+    restatement of decoder.py:147-231 on the same numbers, and the reference's golden cases must come out bit for bit (string AND
+    float64 score) from the library routine"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.decoder import PrefixBeamSearchLMDecoder, prefix_beam_search
+    from wav2letter_pytorch_b200.jasper import Jasper
+    g = golden("beam")
+    labels = [str(s) for s in g["labels"]]
+    for name in ("sharp", "flat", "k1", "beta0", "betaf", "f32"):
+        k, beta, prune = g[name + ":params"]
+        beta = int(beta) if float(beta).is_integer() else float(beta)
+        string, score = prefix_beam_search(g[name + ":probs"], labels, 0, None, int(k), 0.3, beta, float(prune), return_weights=True)
+        assert string == str(g[name + ":string"]) and score == float(g[name + ":score"]), name
+    torch.manual_seed(3)
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=3"]).model
+    model = Jasper(cfg).cuda().eval()
+    x, il, _, _ = O.synthetic_batch(3, 1, seed=4)
+    with torch.no_grad():
+        probs, _ = model(x.cuda(), il.cuda())                 # [3, T', 29] probabilities on the device
+    assert probs.is_cuda and abs(float(probs[0, 0].sum()) - 1.0) < 1e-4
+    sharp = torch.softmax(torch.log(probs.clamp_min(1e-30)) * 6.0, -1)          # peaked, so that the beams differ from greedy
+    dec = PrefixBeamSearchLMDecoder(None, model.labels, blank_index=0, k=5, alpha=0.3, beta=5, prune=1e-3)
+    for p in (probs, sharp):
+        got = dec.decode(p)
+        want = [O.prefix_beam_search(u.double().cpu().numpy(), list(model.labels), 0, None, 5, 0.3, 5, 1e-3)[0] for u in p]
+        assert got == want
+
+
 def test_novograd_golden(pkg, golden):
     from wav2letter_pytorch_b200.novograd import Novograd
     g = golden("novograd")

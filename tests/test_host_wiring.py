@@ -228,3 +228,39 @@ def test_training_step_and_decode_over_emulated_abi(monkeypatch):
     hyp = model.ctc_decoder.decode(out, out_len)
     want, _ = O.greedy_decode(out.numpy(), out_len.numpy())
     assert hyp == want
+
+
+def test_layerwise_parity_tables_sim(monkeypatch):
+    """tests/_layerwise.py (the teacher-forced per-block parity of tests/test_gpu_parity_headline.py) on the host backend at a small
+    size: the tables must come out under the GPU test's fixed bounds here too -- which pins the helper itself (row bookkeeping of the
+    taps, residual + first-group input gradients, masks) before it meets the hardware"""
+    import _layerwise as L
+    from test_gpu_parity_headline import TOL_EMU, TOL_REF
+    from wav2letter_pytorch_b200 import config, functional as F
+    from wav2letter_pytorch_b200.jasper import Jasper
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    _install(monkeypatch, "sim")
+    cfg = config.compose(overrides=["model.mid_layers=3"]).model
+    for l in cfg.layers:
+        l["dropout"] = 0.0
+    torch.manual_seed(0)
+    model = Wav2Letter(cfg).train()
+    x, il, tg, tl = O.synthetic_batch(2, 1, seed=5, ragged=True)
+    hs, out, ol, loss = L.w2l_run_blocks(model, x, il, tg, tl)
+    table = L.w2l_layerwise_table(model, hs, out)
+    assert len(table) == 4 and not L.check_table(table, TOL_EMU, TOL_REF), L.format_table(table)
+    blocks = [dict(layer_size=64, kernel_size=11, stride=2, dilation=1, residual=False, repeat=1, separable=False, dropout=0.0),
+              dict(layer_size=128, kernel_size=5, stride=1, dilation=1, residual=True, repeat=3, separable=False, dropout=0.0),
+              dict(layer_size=64, kernel_size=3, stride=1, dilation=2, residual=False, repeat=1, separable=False, dropout=0.0)]
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=3"]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    torch.manual_seed(0)
+    model = Jasper(cfg).train()
+    x, il, tg, tl = O.synthetic_batch(2, 2, seed=6, ragged=True)
+    hs, taps, rows, out, ol, loss = L.jasper_run_blocks(model, x, il, tg, tl, F)
+    table = L.jasper_layerwise_table(model, O.jasper_block_specs(blocks), hs, taps, rows, out)
+    assert len(table) == 6 and not L.check_table(table, TOL_EMU, TOL_REF), L.format_table(table)
+    # a wiring error must show: drop the residual branch's contribution from the block's input gradient
+    hs[1].grad.mul_(0.9)
+    table = L.jasper_layerwise_table(model, O.jasper_block_specs(blocks), hs, taps, rows, out)
+    assert any(q == "d_input" for _, q, _, _ in L.check_table(table, TOL_EMU, TOL_REF))

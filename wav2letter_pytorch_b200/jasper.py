@@ -213,9 +213,14 @@ class JasperBlock(nn.Module):
                 F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
                 res_pair = (zr, rbn.eval_scale_shift(None))
 
+        tap = getattr(self, "_tap", None)           # parity instrumentation (tests/_layerwise.py): every sub-block's input
         for r, (dwm, mc, bn) in enumerate(subs):
             conv = mc.conv
             last = r == len(subs) - 1
+            if tap is not None:
+                if h.requires_grad:
+                    h.retain_grad()
+                tap.append((h, ri))
             if dwm is not None:                                                  # separable: depthwise k-tap, then pointwise 1x1
                 dc = dwm.conv
                 k, s, d, p = dc.kernel_size[0], dc.stride[0], dc.dilation[0], dc.padding[0]
