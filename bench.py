@@ -832,9 +832,7 @@ def run_gpu_arm(args):
                    "global_batch": world * BATCH, "parallelism": "dp%d" % world,
                    "lengths": "ragged: inputs uniform in [0.6 T, T], targets in [S/2, S]; audio seconds counted as padded" if RAGGED else "full",
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
-                   # opt-in kernel variants in effect (A/B lines describe themselves): CTC lattice schedule, DESIGN.md 3.2
-                   "ctc_schedule": {"0": "log-space", "1": "linear-domain + log-space redo", "2": "linear-domain only"}.get(
-                       os.environ.get("W2L_CTC_LINEAR", "0"), "log-space")},
+                   "ctc_schedule": "log-space (alpha || beta CTAs + parallel gradient pass)"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
         "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),

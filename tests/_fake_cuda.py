@@ -26,8 +26,7 @@ from torch.overrides import TorchFunctionMode
 TOO_LARGE = ["test_ctc_full_size_properties", "test_decode_full_size_properties", "test_conv_full_size_layer",
              "test_baseline_config1_forward_ctc_decode", "test_conv_slab_mode_opt_in", "test_ctc_random[False-64-750-225-29]",
              "test_ctc_random[True-64-750-225-29]", "test_peer_gradient_reducer_two_ranks",
-             "test_ctc_linear_random[False-64-750-225-29]", "test_ctc_linear_random[True-64-750-225-29]",
-             "test_ctc_linear_matches_log_space_at_training_shape", "test_dw_tiled_equals_default[64-751-",
+             "test_dw_tiled_equals_default[64-751-",
              "test_w2l20_train_step_parity", "test_jasper10x5_block_shapes_parity", "test_conv_full_size_backward_vs_torch",
              "test_ctc_full_size_gradient_vs_torch"]
 # `-m gpu` tests that assert the ABSENCE of a CPU path (here every tensor answers is_cuda = True)

@@ -33,18 +33,16 @@ def _bf(t):
 
 # ------------------------------------------------------------------------------------------------ Wav2Letter
 def w2l_run_blocks(model, x, il, tg, tl):
-    """the model's own forward (wav2letter.py:84-92 as wav2letter_pytorch_b200.Wav2Letter.forward runs it), block by block so that
-    every block's input can keep its gradient; then CTC and backward.  Returns (hs, out, out_lens, loss)."""
-    blocks = list(model.conv1ds.children())
-    hs, h, t = [], x, x.shape[2]
-    for i, blk in enumerate(blocks):
-        hs.append(h)
-        h, t = blk.forward_tm(h, t, from_ncw=(i == 0))
-        h.retain_grad()
-    out_lens = model.compute_output_lengths(il)
-    loss = model.criterion(h.transpose(0, 1), tg, out_lens, tl)
+    """the model's own forward (Wav2Letter.forward, with its parity tap switched on so that every block's input keeps its gradient),
+    then CTC and backward.  Returns (hs, out, out_lens, loss): hs[i] = input of block i."""
+    model._tap = []
+    try:
+        out, out_lens = model(x, il)
+    finally:
+        hs = model.__dict__.pop("_tap")
+    loss = model.criterion(out.transpose(0, 1), tg, out_lens, tl)
     loss.backward()
-    return hs, h, out_lens, loss
+    return hs, out, out_lens, loss
 
 
 def w2l_block_oracle(blk, hin, first, last, emu):
@@ -112,31 +110,18 @@ def w2l_layerwise_table(model, hs, out):
 
 
 # ------------------------------------------------------------------------------------------------ Jasper
-def jasper_run_blocks(model, x, il, tg, tl, F):
-    """Jasper.forward (jasper.py:462-475) block by block with every sub-block's input tapped, CTC, backward.
-    Returns (hs, taps, rows, out, out_lens, loss): hs[i] = input of block i (hs[-1] = encoder output), taps[i] = [(input of
-    sub-block r, index into ``rows`` of the lengths entering it)], rows = the truncated lengths entering every masked conv."""
-    from wav2letter_pytorch_b200.layers import ConvHeadFn
-    blocks = list(model.jasper_encoder)
-    chain = [q for blk in blocks for q in blk.chain_params()]
-    rows, out_lens = F.lens_chain(il, chain)
-    hs, taps, h, t, ri = [], [], x, x.shape[2], 0
-    for i, blk in enumerate(blocks):
-        hs.append(h)
-        blk._tap = []
-        try:
-            h, t, ri = blk.forward_tm(h, t, rows, ri, from_ncw=(i == 0), mask_output=(i != len(blocks) - 1))
-        finally:
-            taps.append(blk._tap)
-            del blk._tap
-        h.retain_grad()
-    hs.append(h)
-    head = model.final_layer[0]
-    out = ConvHeadFn.apply(h, head.weight, head.bias, head, 0, None)
-    out.retain_grad()
+def jasper_run_blocks(model, x, il, tg, tl, F=None):
+    """Jasper.forward with its parity tap switched on, CTC, backward.  Returns (hs, taps, rows, out, out_lens, loss): hs[i] = input of
+    block i (hs[-1] = encoder output), taps[i] = [(input of sub-block r, index into ``rows`` of the lengths entering it)], rows = the
+    truncated lengths entering every masked conv (``F.lens_chain``)."""
+    model._tap = {"hs": [], "taps": []}
+    try:
+        out, out_lens = model(x, il)
+    finally:
+        tap = model.__dict__.pop("_tap")
     loss = model.criterion(out.transpose(0, 1), tg, out_lens, tl)
     loss.backward()
-    return hs, taps, rows.detach().cpu().long(), out, out_lens, loss
+    return tap["hs"], tap["taps"], tap["rows"].detach().cpu().long(), out, out_lens, loss
 
 
 def _mask_rows(y_ncw, lens):

@@ -11,9 +11,16 @@ import numpy as np
 import pytest
 import torch
 
+import _layerwise as L
 from oracle import w2l_oracle as O
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+# fixed bounds: teacher-forced per-block parity vs the bf16-emulating oracle / vs the fp32 oracle, and the one
+# end-to-end bound for the toy fixtures' gradients against the reference's frozen ones
+TOL_EMU = {"out": 5e-3, "d_input": 2e-2, "d_param": 2e-2}
+TOL_REF = {"out": 1e-2, "d_input": 1.5e-1, "d_param": 1.5e-1}
+E2E_TOY_BOUND = 0.35
 
 
 @pytest.fixture(scope="module")
@@ -46,7 +53,7 @@ def test_w2l_golden_train_eval(pkg, golden):
     check_w2l_golden(pkg, golden("w2l_small"))
 
 
-def check_w2l_golden(pkg, g, emu_tol=3e-2):
+def check_w2l_golden(pkg, g):
     """train step + eval forward of a small Wav2Letter against a fixture frozen from the unmodified reference"""
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
@@ -57,40 +64,28 @@ def check_w2l_golden(pkg, g, emu_tol=3e-2):
     model.cuda().train()
     x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
     tg, tl = torch.from_numpy(g["tg"]).cuda(), torch.from_numpy(g["tl"]).cuda()
-    out, ol = model(x, il)
+    # ONE training forward (the running statistics are compared below) through the model's own forward(), with its parity tap on
+    hs, out, ol, loss = L.w2l_run_blocks(model, x, il, tg, tl)
     assert out.shape == tuple(g["train:out"].shape) and out.dtype == torch.float32 and out.is_contiguous()
     assert ol.dtype == il.dtype and np.array_equal(ol.cpu().numpy(), g["train:out_len"])
     assert rel_l2(out, g["train:out"]) < 2e-2
-    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
     assert abs(loss.item() - float(g["train:loss"])) < 2e-2 * abs(float(g["train:loss"]))
-    loss.backward()
-    # fairness yard-stick: the CPU oracle with the implementation's stated storage precision emulated (bf16 operands and
-    # bf16-stored activations / activation gradients, fp32 accumulation).  The CUDA path must match THAT tightly; against the
-    # fp32 reference it may be off only by about as much as the emulation itself is (this tiny, freshly initialised model is
-    # badly conditioned: BatchNorm backward cancels most of the upstream gradient, which amplifies bf16 rounding to ~10%).
-    specs, cin = [], 64
-    for l in layers:
-        specs.append(dict(cin=cin, cout=l["output_size"], k=l["kernel_size"], stride=l["stride"], dilation=l["dilation"], dropout=-1,
-                          bn=True, act=True))
-        cin = l["output_size"]
-    specs.append(dict(cin=cin, cout=29, k=1, stride=1, dilation=1, dropout=-1, bn=False, act=False))
-    sd = {k[4:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("sd0:")}
-    emu_params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
-    e_out, e_ol = O.w2l_forward_bf16emu(x.cpu(), il.cpu(), sd, specs, True)
-    e_loss = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(e_out.transpose(0, 1), tg.cpu(), e_ol, tl.cpu())
-    e_loss.backward()
-    assert rel_l2(out, e_out.detach()) < 5e-3
-    assert abs(loss.item() - e_loss.item()) < 2e-3 * abs(e_loss.item())
+    # ---- gradients, closed tolerances: every block on its own (teacher-forced: the oracle block gets the activations / gradients the
+    # device fed into that block, tests/_layerwise.py) against the oracle with the device's bf16 storage emulated AND against plain fp32
+    table = L.w2l_layerwise_table(model, hs, out)
+    bad = L.check_table(table, TOL_EMU, TOL_REF)
+    assert not bad, (bad, L.format_table(table))
+    # ---- end to end against the gradients the unmodified reference produced (frozen in the fixture): one fixed bound.  It is loose
+    # because a freshly initialised BatchNorm stack amplifies every rounding by ~1.2x per layer (the host emulation of the same
+    # bf16 storage sits 0.1-0.2 from fp32 on these toy models); the per-block table above is what catches a wiring error
     for name, p in model.named_parameters():
         ref = g["train:grad:" + name]
         assert p.grad is not None and p.grad.shape == p.shape, name
         if name.endswith("conv1.bias") and head not in name:           # analytically zero under train-mode BN
             assert p.grad.abs().max().item() == 0.0
             continue
-        emu = emu_params[name].grad
-        err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
-        assert err_emu < emu_tol, (name, err_emu)
-        assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
+        err_ref = rel_l2(p.grad, ref)
+        assert err_ref < E2E_TOY_BOUND, (name, err_ref)
     sd1 = {k[4:]: g[k] for k in g.files if k.startswith("sd1:")}
     for k, v in model.state_dict().items():
         if "running" in k:
@@ -314,7 +309,7 @@ def test_jasper_dense_golden(pkg, golden, fixture):
     check_jasper_golden(pkg, golden(fixture), seed=4 if fixture == "jasper_dense" else 2)
 
 
-def check_jasper_golden(pkg, g, seed, emu_tol=0.15):
+def check_jasper_golden(pkg, g, seed):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
@@ -330,30 +325,19 @@ def check_jasper_golden(pkg, g, seed, emu_tol=0.15):
     model.cuda().train()
     x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
     tg, tl = torch.from_numpy(g["tg"]).cuda(), torch.from_numpy(g["tl"]).cuda()
-    out, ol = model(x, il)
+    hs, taps, rows, out, ol, loss = L.jasper_run_blocks(model, x, il, tg, tl)       # ONE training forward through Jasper.forward
     assert np.array_equal(ol.cpu().numpy(), g["train:out_len"]) and ol.dtype == torch.int64
     assert rel_l2(out.detach(), g["train:out"]) < 2e-2
-    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
     assert abs(loss.item() - float(g["train:loss"])) < 2e-2 * abs(float(g["train:loss"]))
-    loss.backward()
-    # yard-stick: the oracle with bf16 storage emulated (see test_w2l_golden_train_eval for the rationale)
-    specs = O.jasper_block_specs(blocks)
-    sd = {k[4:]: torch.from_numpy(g[k]).clone() for k in g.files if k.startswith("sd0:")}
-    emu_params = {k: v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
-    e_out, e_ol = O.jasper_forward(x.cpu(), il.cpu(), sd, specs, True, emu=True)
-    e_loss = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)(e_out.transpose(0, 1), tg.cpu(), e_ol, tl.cpu())
-    e_loss.backward()
-    assert rel_l2(out.detach(), e_out.detach()) < 5e-3 and abs(loss.item() - e_loss.item()) < 2e-3 * abs(e_loss.item())
+    # gradients, closed tolerances: every conv+BN group on its own (see check_w2l_golden), then one fixed end-to-end bound
+    table = L.jasper_layerwise_table(model, O.jasper_block_specs(blocks), hs, taps, rows, out)
+    bad = L.check_table(table, TOL_EMU, TOL_REF)
+    assert not bad, (bad, L.format_table(table))
     for name, p in model.named_parameters():
         ref = torch.from_numpy(g["train:grad:" + name])
         assert p.grad is not None and p.grad.shape == p.shape, name
-        emu = emu_params[name].grad
-        err_emu, err_ref, emu_ref = rel_l2(p.grad, emu), rel_l2(p.grad, ref), rel_l2(emu, ref)
-        # Two bf16 realisations of this toy model differ by ~0.1 from each other and ~0.18 from fp32 in the deep layers (ReLU
-        # masks flip on rounding and BatchNorm backward amplifies it at these tiny widths: tools/diag_jasper.py prints the
-        # table); a wiring error -- a dropped residual gradient, a wrong mask -- shows up as an error of order 1.
-        assert err_emu < emu_tol, (name, err_emu)
-        assert err_ref < max(6e-2, 1.5 * emu_ref), (name, err_ref, emu_ref)
+        err_ref = rel_l2(p.grad, ref)
+        assert err_ref < E2E_TOY_BOUND, (name, err_ref)
     for k in g.files:
         if k.startswith("sd1:") and "running" in k:
             np.testing.assert_allclose(model.state_dict()[k[4:]].cpu().numpy(), g[k], rtol=2e-2, atol=2e-3, err_msg=k)

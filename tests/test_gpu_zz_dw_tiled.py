@@ -1,8 +1,5 @@
-"""GPU tests of the register-tiled depthwise kernels (csrc/depthwise.cu, W2L_DW_TILED=1).  EXPERIMENTAL and opt-in like the code path
-itself (written after round 1's GPU budget was spent; on the host they run in tests/test_kernel_emu_depthwise_tiled.py and under
-`pytest -m gpu --emulate-gpu`): on a real GPU only with W2L_TEST_EXPERIMENTAL=1 (tools/final_run.sh sets it).  Sorts last."""
-import os
-
+"""GPU tests of the register-tiled depthwise kernels (csrc/depthwise.cu): the default for stride 1 / dilation 1 since round 2's A/B on
+hardware (profiles/r2_dw_ab.md); W2L_DW_TILED=0 selects the plain kernels they are compared with here."""
 import pytest
 import torch
 
@@ -10,11 +7,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 @pytest.fixture
-def F(request):
+def F():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    if not (os.environ.get("W2L_TEST_EXPERIMENTAL") or request.config.getoption("--emulate-gpu")):
-        pytest.skip("experimental path: set W2L_TEST_EXPERIMENTAL=1 to run it on the GPU")
     from wav2letter_pytorch_b200 import functional
     return functional
 
@@ -44,13 +39,12 @@ def test_dw_tiled_equals_default(F, monkeypatch, B, T, C, k):
     assert float((dw0 - dw1).norm() / dw0.norm()) < 1e-5
 
 
-def test_dw_tiled_jasper_separable_golden(request, monkeypatch, golden):
-    """whole separable Jasper (fixture frozen from the unmodified reference) with the tiled kernels in place"""
+def test_plain_depthwise_jasper_separable_golden(monkeypatch, golden):
+    """whole separable Jasper (fixture frozen from the unmodified reference) with the PLAIN depthwise kernels in place
+    (W2L_DW_TILED=0); the default (tiled) path is what tests/test_gpu_models.py::test_jasper_dense_golden[jasper_small] runs"""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    if not (os.environ.get("W2L_TEST_EXPERIMENTAL") or request.config.getoption("--emulate-gpu")):
-        pytest.skip("experimental path: set W2L_TEST_EXPERIMENTAL=1 to run it on the GPU")
     import wav2letter_pytorch_b200 as pkg
     from test_gpu_models import check_jasper_golden
-    monkeypatch.setenv("W2L_DW_TILED", "1")
+    monkeypatch.setenv("W2L_DW_TILED", "0")
     check_jasper_golden(pkg, golden("jasper_small"), seed=2)

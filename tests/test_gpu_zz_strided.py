@@ -105,7 +105,7 @@ def test_w2l_narrow_golden(pkg, golden):
 def test_jasper_strided_golden(pkg, golden):
     """Jasper with a strided dense block (repeat 2: both repeats stride) and a strided separable block after the prologue"""
     from test_gpu_models import check_jasper_golden
-    check_jasper_golden(pkg, golden("jasper_strided"), seed=10, emu_tol=0.25)
+    check_jasper_golden(pkg, golden("jasper_strided"), seed=10)
 
 
 def test_strided_block_with_residual_raises(pkg):

@@ -103,7 +103,6 @@ __global__ void ctc_prep_kernel(const float* __restrict__ x, int from_logits, in
 struct CtcMeta {          // per-utterance results of the alpha pass (workspace)
   double ll2;             // log2 likelihood (valid when feasible)
   int32_t feasible;
-  int16_t redo_a, redo_b;  // linear-domain schedule: the alpha / beta recursion lost a live state to the fp32 range (redo in log space)
 };
 
 template <int R>
@@ -524,319 +523,6 @@ ctc_lattice_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const in
     lattice_pass<R, true>(smem, blockIdx.x - N, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, beta_ws, beta_off, n_blk, meta, Lp);
 }
 
-// ---- linear-domain variant of the parallel schedule (opt-in: W2L_CTC_LINEAR=1) ---------------------------------------------------
-// The log-space step costs 2-3 MUFU ops per lattice state and a ~100-cycle dependent chain per frame.  Here a thread keeps its R
-// states as fp32 MANTISSAS v[r] >= 0 with ONE integer exponent per thread (block floating point): alpha_t(s0 + r) = v[r] * 2^e.
-// A step is 2 adds + 1 multiply per state; the only special-function ops are the R/2 + 1 emission probabilities of the thread's
-// classes, which do not depend on the recursion and so sit off the frame-to-frame chain:
-//   * the in-lane sums v[r] + v[r-1] (+ skip * v[r-2]) do not depend on the neighbouring lane and are formed before its value lands;
-//   * the neighbour's boundary value arrives as a mantissa in [1, 2) plus the exponent that says how large it is; d = e_nb - e aligns
-//     the two sides, the larger one wins and the other is scaled down by an exact power of two; an all-zero lane carries kEmptyExp and
-//     adopts whatever arrives, so each lane's exponent follows the magnitude of ITS part of the lattice;
-//   * a frame's emission log-probs are split as lp2 = ip + f with ip = floor(max over the thread's classes): the mantissas are
-//     multiplied by 2^f' in (0, 2) and ip goes into the exponent, so rows with probabilities far below 2^-126 cost no range;
-//   * re-normalisation (bring the lane maximum to [1, 2)) is LAZY: the exponent of the maximum is taken after the step and folded
-//     into the next step's scale factor, so it never sits on the chain; exponents are absolute integers: nothing drifts with T.
-// Rows are spilled as mantissas plus one int32 exponent per thread and frame; the gradient pass multiplies them back together.
-// A state more than 2^126 below its own lane's maximum flushes to zero (in log space it would survive).  Two checks catch the cases
-// where that matters, and the utterance is then redone by the log-space kernels (CtcMeta::redo_*, predicated launches).  Both sit in
-// the gradient pass, which is parallel over frames, so the recursion's serial loop carries no checking code:
-//   * a frame in which a class of the utterance's lattice is live but more than 2^120 below the frame's largest emission (the same
-//     loss in both recursions, so invisible to the next check);
-//   * the occupancies of every frame must sum to 1 -- mass that one recursion lost and the other still counts (or a likelihood that
-//     lost paths) shows up as a sum off 1.
-// The log-space kernels stay the default.
-constexpr int kEmptyExp = -(1 << 28);
-constexpr float kLinSpread = -120.f;        // a live class this far (log2) below the largest emission of its frame: not held
-
-__device__ __forceinline__ float pow2i(int x) {             // 2^x, x in [-127, 127]; -127 gives 0
-  return __int_as_float((x + 127) << 23);
-}
-__device__ __forceinline__ int exp_field(float x) { return (__float_as_int(x) >> 23) & 0xff; }   // x >= 0; 0: zero or denormal
-
-// One frame on a thread's R states.  (xv1, xv2, xe): the neighbouring lane's boundary mantissa(s) and exponent of the previous frame;
-// (pb, pl, ip): this frame's emission probabilities of the thread's classes, divided by 2^ip.  e_eff: exponent of v with the pending
-// shift kpend already counted.  Returns the exponent the new v[] are stated in.
-template <int R, bool BETA>
-__device__ __forceinline__ int lattice_step_lin(float (&v)[R], int& e_eff, int& kpend, float xv1, float xv2, int xe, float pb,
-                                                const float (&pl)[R / 2], int ip, const float (&skm)[R / 2]) {
-  float s[R];
-  if (!BETA) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      s[r] = (r >= 1) ? v[r] + v[(r >= 1) ? r - 1 : 0] : v[r];
-      if ((r & 1) && r >= 2) s[r] = fmaf(skm[r >> 1], v[(r >= 2) ? r - 2 : 0], s[r]);
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      s[r] = (r + 1 < R) ? v[r] + v[(r + 1 < R) ? r + 1 : 0] : v[r];
-      if ((r & 1) && r + 2 < R) s[r] = fmaf(skm[r >> 1], v[(r + 2 < R) ? r + 2 : 0], s[r]);
-    }
-  }
-  const int d = xe - e_eff;
-  const int up = max(d, 0);
-  const float sc_me = pow2i(max(-kpend - up, -127));
-  const float sc_in = pow2i(max(min(d, 0), -127));
-  const int e_pub = e_eff + up + ip;
-  const float x1 = xv1 * sc_in;
-  if (!BETA) {
-    v[0] = fmaf(s[0], sc_me, x1) * pb;
-    v[1] = fmaf(s[1], sc_me, skm[0] * x1) * pl[0];
-#pragma unroll
-    for (int r = 2; r < R; ++r) v[r] = s[r] * sc_me * ((r & 1) ? pl[r >> 1] : pb);
-  } else {
-    const float x2 = xv2 * sc_in;
-    v[R - 1] = fmaf(s[R - 1], sc_me, fmaf(skm[(R - 1) >> 1], x2, x1)) * pl[(R - 1) >> 1];
-#pragma unroll
-    for (int r = 0; r < R - 1; ++r) v[r] = s[r] * sc_me * ((r & 1) ? pl[r >> 1] : pb);
-  }
-  float m = v[0];
-#pragma unroll
-  for (int r = 1; r < R; ++r) m = fmaxf(m, v[r]);
-  const int ef = exp_field(m);
-  kpend = ef ? ef - 127 : 0;
-  e_eff = ef ? e_pub + kpend : kEmptyExp;
-  return e_pub;
-}
-
-// What the neighbouring lane gets to see of this thread after a step: its boundary mantissa(s) normalised to [1, 2) (beta: the larger of
-// the two) and the exponent that goes with it, i.e. the magnitude of THAT value -- not of the lane, and not of whatever the lane was
-// aligned to: a receiver that took the sender's working exponent would pin every lane downstream to the lattice's largest exponent.
-template <int R, bool BETA>
-__device__ __forceinline__ void lattice_publish_lin(const float (&v)[R], int e_pub, float& pm1, float& pm2, int& pe) {
-  if (!BETA) {
-    const int bits = __float_as_int(v[R - 1]), ef = (bits >> 23) & 0xff;
-    pm1 = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-    pm2 = 0.f;
-    pe = ef ? e_pub + ef - 127 : kEmptyExp;
-  } else {
-    const int ef = exp_field(fmaxf(v[0], v[1]));
-    const float pw = pow2i(127 - max(ef, 1));        // ef in [1, 254] -> 2^(127 - ef)
-    pm1 = v[0] * pw;
-    pm2 = v[1] * pw;
-    pe = ef ? e_pub + ef - 127 : kEmptyExp;
-  }
-}
-
-template <int R, bool BETA>
-__device__ __forceinline__ void
-lattice_pass_lin(float* smem, int n, const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                 const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank, float* __restrict__ ws,
-                 int32_t* __restrict__ ws_exp, CtcMeta* __restrict__ meta, int Lp) {
-  float* pbuf = smem;                                                     // [2][kBlk][Cp] log2-domain rows
-  float4* slots = reinterpret_cast<float4*>(pbuf + 2 * kBlk * Cp);        // [33][kBlk]: one ring per warp + an always-ready dummy ring
-  float* s_fin = reinterpret_cast<float*>(slots + 33 * kBlk);             // [4]: mantissa, exponent of alpha_T(L-1), alpha_T(L-2)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int Tn = max(0, min(T, in_len[n]));
-  const int S = max(0, min((int)tstride, tg_len[n]));
-  const int L = 2 * S + 1;
-  const int s0 = tid * R;
-  if (Tn == 0) {
-    if (tid == 0) {
-      if (!BETA) {
-        meta[n].ll2 = 0.0;
-        meta[n].feasible = (S == 0);
-        meta[n].redo_a = 0;
-      } else {
-        meta[n].redo_b = 0;
-      }
-    }
-    return;
-  }
-  int lab_b[R / 2];
-  float skm[R / 2];
-  {
-    const int32_t* tg = targets + (int64_t)n * tstride;
-#pragma unroll
-    for (int j = 0; j < R / 2; ++j) {
-      const int i = (s0 >> 1) + j;                // label index of state s0 + 2j + 1
-      int l = Cp - 1;                              // states past the lattice read the column that holds probability 0
-      bool skip = false;
-      if (i < S) {
-        l = tg[i];
-        skip = BETA ? (i + 1 < S && tg[i + 1] != l) : (i > 0 && tg[i - 1] != l);
-      }
-      lab_b[j] = l * 4;
-      skm[j] = skip ? 1.f : 0.f;
-    }
-  }
-  const int blank_b = blank * 4;
-  for (int i = tid; i < 33 * kBlk; i += nthreads)   // ring 32 feeds the warp that has no neighbour: zero mass, always ready
-    slots[i] = i < 32 * kBlk ? make_float4(0.f, 0.f, __int_as_float(-1), 0.f)
-                             : make_float4(0.f, 0.f, __int_as_float(0x7fffffff), __int_as_float(kEmptyExp));
-  const float* lp_n = lp2 + (int64_t)n * T * Cp;
-  const int blocks = (Tn + kBlk - 1) / kBlk;
-  auto prefetch_block = [&](int k) {
-    if (k < blocks) {
-      const int i0 = k * kBlk, cnt = min(kBlk, Tn - i0);
-      const int f_lo = BETA ? Tn - i0 - cnt : i0;
-      const float* src = lp_n + (int64_t)f_lo * Cp;
-      float* dst = pbuf + (k & 1) * kBlk * Cp;
-      for (int q = tid; q < cnt * (Cp >> 2); q += nthreads) cp_async16(dst + q * 4, src + q * 4);
-    }
-    cp_async_commit();
-  };
-  prefetch_block(0);
-  prefetch_block(1);
-
-  float v[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) v[r] = 0.f;
-  int e_eff = kEmptyExp, kpend = 0, e_pub = kEmptyExp;
-  int pe = kEmptyExp;                         // published view of the boundary state(s): see lattice_publish_lin
-  float pm1 = 0.f, pm2 = 0.f;
-  const int64_t wstep = BETA ? -(int64_t)Lp : (int64_t)Lp;
-  const int64_t estep = BETA ? -(int64_t)nthreads : (int64_t)nthreads;
-  float* wp = ws + ((int64_t)n * T + (BETA ? Tn - 1 : 0)) * Lp + s0;               // spill row of the current step
-  int32_t* ep = ws_exp + ((int64_t)n * T + (BETA ? Tn - 1 : 0)) * nthreads + tid;
-  const bool has_nb = BETA ? (warp < nwarps - 1) : (warp > 0);
-  const bool edge = BETA ? (lane == 31) : (lane == 0);
-  const bool pub = BETA ? (lane == 0) : (lane == 31);
-  const float4* slot_in = slots + (has_nb ? (BETA ? warp + 1 : warp - 1) : 32) * kBlk;
-  float4* slot_out = slots + warp * kBlk;
-  const int row_b = BETA ? -Cp * 4 : Cp * 4;
-
-  for (int k = 0; k < blocks; ++k) {
-    cp_async_wait<1>();                       // block k's rows have landed (block k+1 may still be in flight)
-    __syncthreads();
-    const int i0 = k * kBlk, cnt = min(kBlk, Tn - i0);
-    const char* rowp = reinterpret_cast<const char*>(pbuf + (k & 1) * kBlk * Cp) + (BETA ? (cnt - 1) * Cp * 4 : 0);
-    int ii = 0;
-    if (k == 0) {                             // step 0: initial lattice column
-      const float lb = *reinterpret_cast<const float*>(rowp + blank_b);
-      bool mine = false;
-      int ip = 0;
-      float l0[R];                                     // raw log2 emissions of the states that start with mass (kNeg elsewhere)
-#pragma unroll
-      for (int r = 0; r < R; ++r) l0[r] = kNeg;
-      if (!BETA) {
-        if (tid == 0) {
-          l0[0] = lb;
-          l0[1] = (L > 1) ? *reinterpret_cast<const float*>(rowp + lab_b[0]) : kNeg;
-          ip = (int)floorf(fmaxf(fmaxf(l0[0], l0[1]), -1.0e6f));
-          v[0] = fast_ex2(l0[0] - (float)ip);
-          v[1] = fast_ex2(l0[1] - (float)ip);
-          mine = true;
-        }
-      } else {
-        float mx = kNeg;                               // the two live states may sit in two lanes: each lane has its own row exponent
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int s = s0 + r;
-          const bool live = s == L - 1 || (s == L - 2 && (r & 1));
-          l0[r] = live ? ((r & 1) ? *reinterpret_cast<const float*>(rowp + lab_b[r >> 1]) : lb) : kNeg;
-          mx = fmaxf(mx, l0[r]);
-          mine = mine || live;
-        }
-        ip = (int)floorf(fmaxf(mx, -1.0e6f));
-#pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = fast_ex2(l0[r] - (float)ip);
-      }
-      float m = v[0];
-#pragma unroll
-      for (int r = 1; r < R; ++r) m = fmaxf(m, v[r]);
-      const int ef = exp_field(m);
-      e_pub = (mine && ef) ? ip : kEmptyExp;
-      kpend = (mine && ef) ? ef - 127 : 0;
-      e_eff = (mine && ef) ? e_pub + kpend : kEmptyExp;
-      lattice_publish_lin<R, BETA>(v, e_pub, pm1, pm2, pe);
-      if (pub) slot_put(slot_out, pm1, pm2, 0, __int_as_float(pe));
-      spill_states<R>(wp, v);
-      *ep = e_pub;
-      wp += wstep;
-      ep += estep;
-      rowp += row_b;
-      ii = 1;
-    }
-    float4 q = slot_load(slot_in + ((ii + kBlk - 1) & (kBlk - 1)));
-    for (; ii < cnt; ++ii) {
-      const int i = i0 + ii;
-      slot_ready(q, slot_in + ((ii + kBlk - 1) & (kBlk - 1)), i - 1);
-      const float y1 = q.x, y2 = q.y;
-      const int ye = __float_as_int(q.w);
-      q = slot_load(slot_in + ii);
-      // this frame's emissions for the thread's classes: lp2 = ip + f, mantissas 2^f' in (0, 2) (independent of the recursion)
-      const float lb = *reinterpret_cast<const float*>(rowp + blank_b);
-      float pl[R / 2];
-      float mx = lb;
-#pragma unroll
-      for (int j = 0; j < R / 2; ++j) {
-        pl[j] = *reinterpret_cast<const float*>(rowp + lab_b[j]);
-        mx = fmaxf(mx, pl[j]);
-      }
-      const int ip = (int)floorf(fmaxf(mx, -1.0e6f));
-      const float fip = (float)ip;
-      const float pb = fast_ex2(lb - fip);
-#pragma unroll
-      for (int j = 0; j < R / 2; ++j) pl[j] = fast_ex2(pl[j] - fip);
-      float x1, x2 = 0.f;
-      int xe;
-      if (!BETA) {
-        x1 = __shfl_up_sync(0xffffffffu, pm1, 1);
-        xe = __shfl_up_sync(0xffffffffu, pe, 1);
-      } else {
-        x1 = __shfl_down_sync(0xffffffffu, pm1, 1);
-        x2 = __shfl_down_sync(0xffffffffu, pm2, 1);
-        xe = __shfl_down_sync(0xffffffffu, pe, 1);
-      }
-      x1 = edge ? y1 : x1;
-      if (BETA) x2 = edge ? y2 : x2;
-      xe = edge ? ye : xe;
-      e_pub = lattice_step_lin<R, BETA>(v, e_eff, kpend, x1, x2, xe, pb, pl, ip, skm);
-      lattice_publish_lin<R, BETA>(v, e_pub, pm1, pm2, pe);
-      if (pub) slot_put(slot_out + ii, pm1, pm2, i, __int_as_float(pe));
-      spill_states<R>(wp, v);
-      *ep = e_pub;
-      wp += wstep;
-      ep += estep;
-      rowp += row_b;
-    }
-    __syncthreads();                          // every warp is done with block k's rows and slots
-    prefetch_block(k + 2);
-  }
-  if (!BETA) {                                // likelihood: alpha_T(L-1) + alpha_T(L-2), possibly held by two lanes with two exponents
-    if (tid < 4) s_fin[tid] = (tid & 1) ? __int_as_float(kEmptyExp) : 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (s0 + r == L - 1) {
-        s_fin[0] = v[r];
-        s_fin[1] = __int_as_float(e_pub);
-      }
-      if (s0 + r == L - 2) {
-        s_fin[2] = v[r];
-        s_fin[3] = __int_as_float(e_pub);
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      const int e1 = __float_as_int(s_fin[1]), e2 = __float_as_int(s_fin[3]);
-      const int E = max(e1, e2);
-      const double sum = ldexp((double)s_fin[0], max(e1 - E, -2000)) + ldexp((double)s_fin[2], max(e2 - E, -2000));
-      const bool ok = sum > 0.0 && E > kEmptyExp / 2;
-      meta[n].feasible = ok;
-      meta[n].ll2 = ok ? log2(sum) + (double)E : 0.0;
-      meta[n].redo_a = (int16_t)!ok;          // "infeasible" is the log-space kernels' call (rare: costs one utterance's redo)
-    }
-  } else if (tid == 0) {
-    meta[n].redo_b = 0;                       // (the gradient pass raises the flags: see ctc_grad_lin_kernel)
-  }
-}
-
-template <int R>
-__global__ void __launch_bounds__(1024)
-ctc_lattice_lin_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                       const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank, float* __restrict__ alpha_ws,
-                       int32_t* __restrict__ alpha_exp, float* __restrict__ beta_ws, int32_t* __restrict__ beta_exp,
-                       CtcMeta* __restrict__ meta, int Lp) {
-  extern __shared__ __align__(16) float smem[];
-  if ((int)blockIdx.x < N)
-    lattice_pass_lin<R, false>(smem, blockIdx.x, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_exp, meta, Lp);
-  else
-    lattice_pass_lin<R, true>(smem, blockIdx.x - N, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, beta_ws, beta_exp, meta, Lp);
-}
-
 template <int R>
 __global__ void __launch_bounds__(1024)
 ctc_alpha_kernel(const float* __restrict__ lp2, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
@@ -923,129 +609,6 @@ ctc_grad_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const int32
   extern __shared__ __align__(16) float smem[];
   ctc_grad_body(smem, lp2, T, C, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_off, beta_ws, beta_off, n_blk, meta, Lp,
                 zero_infinity, reduction_mean, N, grad);
-}
-
-// The log-space kernels again, for the utterances the linear-domain schedule flagged (CtcMeta::redo_*): everyone else's CTAs leave at once.
-template <int R>
-__global__ void __launch_bounds__(1024)
-ctc_lattice_redo_kernel(const float* __restrict__ lp2, int N, int T, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                        const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank, float* __restrict__ alpha_ws,
-                        double* __restrict__ alpha_off, float* __restrict__ beta_ws, double* __restrict__ beta_off, int n_blk,
-                        CtcMeta* __restrict__ meta, int Lp) {
-  extern __shared__ __align__(16) float smem[];
-  const int n = (int)blockIdx.x < N ? blockIdx.x : blockIdx.x - N;
-  if (!(meta[n].redo_a | meta[n].redo_b)) return;
-  if ((int)blockIdx.x < N)
-    lattice_pass<R, false>(smem, n, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_off, n_blk, meta, Lp);
-  else
-    lattice_pass<R, true>(smem, n, lp2, T, Cp, targets, tstride, in_len, tg_len, blank, beta_ws, beta_off, n_blk, meta, Lp);
-}
-__global__ void __launch_bounds__(256)
-ctc_grad_redo_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                     const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
-                     const float* __restrict__ alpha_ws, const double* __restrict__ alpha_off, const float* __restrict__ beta_ws,
-                     const double* __restrict__ beta_off, int n_blk, const CtcMeta* __restrict__ meta, int Lp, int zero_infinity,
-                     int reduction_mean, int N, float* __restrict__ grad) {
-  extern __shared__ __align__(16) float smem[];
-  if (!(meta[blockIdx.y].redo_a | meta[blockIdx.y].redo_b)) return;
-  ctc_grad_body(smem, lp2, T, C, Cp, targets, tstride, in_len, tg_len, blank, alpha_ws, alpha_off, beta_ws, beta_off, n_blk, meta, Lp,
-                zero_infinity, reduction_mean, N, grad);
-}
-
-// Gradient pass of the linear-domain schedule: gamma_t(s) = a * b * 2^(ea + eb - ll2 - lp2_t(l_s)) from the spilled mantissas and the
-// per-thread exponents (thread of state s = s >> lgR).  The power of two is split over the two factors so that neither the product of
-// two small mantissas nor a large scale alone leaves the fp32 range.
-__global__ void __launch_bounds__(256)
-ctc_grad_lin_kernel(const float* __restrict__ lp2, int T, int C, int Cp, const int32_t* __restrict__ targets, int64_t tstride,
-                    const int32_t* __restrict__ in_len, const int32_t* __restrict__ tg_len, int blank,
-                    const float* __restrict__ alpha_ws, const int32_t* __restrict__ alpha_exp, const float* __restrict__ beta_ws,
-                    const int32_t* __restrict__ beta_exp, int nth, int lgR, CtcMeta* __restrict__ meta, int Lp, int zero_infinity,
-                    int reduction_mean, int N, float* __restrict__ grad) {
-  extern __shared__ __align__(16) float smem[];
-  const int nwarps = blockDim.x >> 5;
-  float* rows = smem;                                               // [nwarps][Cp]
-  uint32_t* bins = reinterpret_cast<uint32_t*>(rows + nwarps * Cp);  // [nwarps][Cp]
-  uint8_t* lab = reinterpret_cast<uint8_t*>(bins + nwarps * Cp);     // [L] class of every lattice state
-  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Tn = max(0, min(T, in_len[n]));
-  const int S = max(0, min((int)tstride, tg_len[n]));
-  const int L = 2 * S + 1;
-  const bool feasible = meta[n].feasible != 0;
-  const int t_begin = blockIdx.x * kGradFrames, t_end = min(T, t_begin + kGradFrames);
-  float* g_n = grad + (int64_t)n * T * C;
-  if (!feasible || Tn == 0 || t_begin >= Tn) {
-    const float fill = (!feasible && !zero_infinity) ? NAN : 0.f;
-    for (int i = t_begin * C + tid; i < t_end * C; i += blockDim.x) g_n[i] = (i < Tn * C) ? fill : 0.f;
-    return;
-  }
-  const int32_t* tg = targets + (int64_t)n * tstride;
-  uint8_t* used = lab + ((L + 15) & ~15);                            // [Cp] 1 for the classes this utterance's lattice emits
-  for (int c = tid; c < Cp; c += blockDim.x) used[c] = (c == blank);
-  __syncthreads();
-  for (int s = tid; s < L; s += blockDim.x) {
-    lab[s] = (uint8_t)((s & 1) ? tg[s >> 1] : blank);
-    used[lab[s]] = 1;
-  }
-  __syncthreads();
-  const float gscale = reduction_mean ? 1.f / ((float)N * (float)max(S, 1)) : 1.f;
-  const double ll2 = meta[n].ll2, ll_floor = floor(ll2);
-  const int ll_i = (int)ll_floor;
-  const float ll_f = (float)(ll2 - ll_floor);
-  float* row = rows + warp * Cp;
-  uint32_t* bin = bins + warp * Cp;
-  for (int t = t_begin + warp; t < t_end; t += nwarps) {
-    float* g_t = g_n + (int64_t)t * C;
-    if (t >= Tn) {
-      for (int c = lane; c < C; c += 32) g_t[c] = 0.f;
-      continue;
-    }
-    const float* lp_t = lp2 + ((int64_t)n * T + t) * Cp;
-    float rmax = kNeg, rmin = 0.f;            // the row's largest emission and the smallest LIVE one among the lattice's classes
-    for (int c = lane; c < Cp; c += 32) {
-      const float v = lp_t[c];
-      row[c] = v;
-      bin[c] = 0u;
-      rmax = fmaxf(rmax, v);
-      rmin = fminf(rmin, (used[c] && v > kDead) ? v : 0.f);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-      rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-    }
-    if (lane == 0 && rmin - rmax < kLinSpread) meta[n].redo_b = 1;
-    __syncwarp();
-    const float* a_t = alpha_ws + ((int64_t)n * T + t) * Lp;
-    const float* b_t = beta_ws + ((int64_t)n * T + t) * Lp;
-    const int32_t* ea_t = alpha_exp + ((int64_t)n * T + t) * nth;
-    const int32_t* eb_t = beta_exp + ((int64_t)n * T + t) * nth;
-    float gb = 0.f;
-    for (int s = lane; s < L; s += 32) {
-      const int l = lab[s], th = s >> lgR;
-      const float x = (float)(ea_t[th] + eb_t[th] - ll_i) - ll_f - row[l];
-      const float h = exp2f(0.5f * fminf(x, 240.f));
-      const float g = (a_t[s] * h) * (b_t[s] * h);
-      if (s & 1) {
-        if (g > 0.f) atomicAdd(bin + l, __float2uint_rn(fminf(g, 1.5f) * kFix));
-      } else {
-        gb += g;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
-    if (lane == 0 && gb > 0.f) atomicAdd(bin + blank, __float2uint_rn(fminf(gb, 1.5f) * kFix));
-    __syncwarp();
-    float tot = 0.f;                          // every path crosses exactly one state per frame: the occupancies sum to 1
-    for (int c = lane; c < C; c += 32) {
-      const float occ = (float)bin[c] * (1.f / kFix);
-      tot += occ;
-      g_t[c] = (exp2f(row[c]) - occ) * gscale;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0 && !(fabsf(tot - 1.f) <= 2e-3f)) meta[n].redo_a = 1;
-    __syncwarp();
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1242,17 +805,8 @@ __global__ void ctc_finish_kernel(const CtcMeta* __restrict__ meta, const int32_
 struct CtcPlan {
   int R, threads, Lp, Cp;
   bool parallel;   // alpha and beta in parallel CTAs + a parallel gradient pass (beta is spilled too); else alpha, then beta+grad fused
-  bool linear;     // parallel schedule in the linear domain (mantissas + per-thread exponents), W2L_CTC_LINEAR=1
-  int lin_mode;
-  size_t off_lp2, off_alpha, off_aoff, off_beta, off_boff, off_meta, off_aexp, off_bexp, total;
+  size_t off_lp2, off_alpha, off_aoff, off_beta, off_boff, off_meta, total;
 };
-
-// W2L_CTC_LINEAR: 0 / unset = log-space kernels; 1 = linear-domain schedule, flagged utterances redone in log space; 2 = linear-domain
-// schedule alone (development: what the range check would have caught shows up in the result)
-static int ctc_linear_requested() {
-  const char* e = getenv("W2L_CTC_LINEAR");
-  return e ? atoi(e) : 0;
-}
 
 // the parallel schedule doubles the lattice spill; beyond this size the serial (fused beta+gradient) schedule is used
 constexpr size_t kCtcParallelSpillLimit = (size_t)3 << 30;
@@ -1282,10 +836,6 @@ static bool make_plan(int64_t N, int64_t T, int64_t S_max, int64_t C, CtcPlan* p
   p->off_beta = p->parallel ? take(lattice) : 0;
   p->off_boff = p->parallel ? take((size_t)N * T * sizeof(double)) : 0;
   p->off_meta = take((size_t)N * sizeof(CtcMeta));
-  p->lin_mode = ctc_linear_requested();
-  p->linear = p->parallel && p->lin_mode != 0;
-  p->off_aexp = p->linear ? take((size_t)N * T * p->threads * sizeof(int32_t)) : 0;
-  p->off_bexp = p->linear ? take((size_t)N * T * p->threads * sizeof(int32_t)) : 0;
   p->total = o;
   return true;
 }
@@ -1310,39 +860,9 @@ static int launch_ctc(const CtcPlan& pl, char* ws, int64_t N, int64_t T, int64_t
     float* beta = (float*)(ws + pl.off_beta);
     double* boff = (double*)(ws + pl.off_boff);
     const int gw = 8;
-    const size_t smem_g = (size_t)gw * pl.Cp * 8 + (size_t)(2 * tstride + 1 + 15) + 16 + pl.Cp;   // rows, bins, lab (+ used, linear pass)
+    const size_t smem_g = (size_t)gw * pl.Cp * 8 + (size_t)(2 * tstride + 1 + 15) + 16 + pl.Cp;   // rows, bins, lab
     W2L_REQUIRE(smem_g <= 48 * 1024, "ctc: gradient pass shared memory %zu too large", smem_g);
     dim3 grid((unsigned)((T + kGradFrames - 1) / kGradFrames), (unsigned)N);
-    if (pl.linear) {
-      int32_t* aexp = (int32_t*)(ws + pl.off_aexp);
-      int32_t* bexp = (int32_t*)(ws + pl.off_bexp);
-      const size_t smem_ll = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + 4 * sizeof(float);
-      W2L_CUDA(cudaFuncSetAttribute(ctc_lattice_lin_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ll));
-      ctc_lattice_lin_kernel<R><<<(unsigned)(2 * N), pl.threads, smem_ll, st>>>(lp2, (int)N, (int)T, pl.Cp, targets, tstride, in_len,
-                                                                               tg_len, blank, alpha, aexp, beta, bexp, meta, pl.Lp);
-      int rc = after_launch("ctc_lattice_lin_kernel");
-      if (rc) return rc;
-      const int lgR = R == 2 ? 1 : R == 4 ? 2 : 3;
-      ctc_grad_lin_kernel<<<grid, gw * 32, smem_g, st>>>(lp2, (int)T, (int)C, pl.Cp, targets, tstride, in_len, tg_len, blank, alpha, aexp,
-                                                         beta, bexp, pl.threads, lgR, meta, pl.Lp, zero_infinity, reduction_mean, (int)N,
-                                                         grad);
-      rc = after_launch("ctc_grad_lin_kernel");
-      if (rc || pl.lin_mode == 2) return rc;
-      // utterances whose recursion left the mantissa range (flagged on the device) are done again in log space: same spill buffers
-      float* beta_r = (float*)(ws + pl.off_beta);
-      double* boff_r = (double*)(ws + pl.off_boff);
-      const int n_blk_r = (int)((T + kBlk - 1) / kBlk);
-      const size_t smem_r = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + (32 + 2) * sizeof(float);
-      W2L_CUDA(cudaFuncSetAttribute(ctc_lattice_redo_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-      ctc_lattice_redo_kernel<R><<<(unsigned)(2 * N), pl.threads, smem_r, st>>>(lp2, (int)N, (int)T, pl.Cp, targets, tstride, in_len,
-                                                                                tg_len, blank, alpha, aoff, beta_r, boff_r, n_blk_r, meta,
-                                                                                pl.Lp);
-      rc = after_launch("ctc_lattice_redo_kernel");
-      if (rc) return rc;
-      ctc_grad_redo_kernel<<<grid, gw * 32, smem_g, st>>>(lp2, (int)T, (int)C, pl.Cp, targets, tstride, in_len, tg_len, blank, alpha, aoff,
-                                                          beta_r, boff_r, n_blk_r, meta, pl.Lp, zero_infinity, reduction_mean, (int)N, grad);
-      return after_launch("ctc_grad_redo_kernel");
-    }
     const int n_blk = (int)((T + kBlk - 1) / kBlk);
     const size_t smem_l = (size_t)(2 * kBlk * pl.Cp) * sizeof(float) + (size_t)33 * kBlk * sizeof(float4) + (32 + 2) * sizeof(float);
     W2L_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));

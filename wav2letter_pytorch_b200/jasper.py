@@ -299,13 +299,26 @@ class Jasper(ConvCTCASR):
                 self._chain = [q for blk in blocks for q in blk.chain_params()]
             rows, out_lens = F.lens_chain(input_lengths.to(xs.device), self._chain)
         h, t, ri = xs, xs.shape[2], 0
+        tap = getattr(self, "_tap", None)                # parity instrumentation (tests/_layerwise.py): block / sub-block inputs
         for i, blk in enumerate(blocks):
+            if tap is not None:
+                tap["hs"].append(h)
+                blk._tap = []
             # the head (final_layer) is NOT masked in the reference (jasper.py:468): the last block keeps its padded rows
             h, t, ri = blk.forward_tm(h, t, rows, ri, from_ncw=(i == 0), mask_output=(i != len(blocks) - 1))
+            if tap is not None:
+                tap["taps"].append(blk.__dict__.pop("_tap"))
+                if h.requires_grad:
+                    h.retain_grad()
         head = self.final_layer[0]
         mode = getattr(self, "nan_check", "sync")
         flag = torch.zeros(1, dtype=torch.int32, device=xs.device) if mode != "off" else None
         scores = ConvHeadFn.apply(h, head.weight, head.bias, head, 0 if self.training else 1, flag)
+        if tap is not None:
+            tap["hs"].append(h)
+            tap["rows"] = rows
+            if scores.requires_grad:
+                scores.retain_grad()
         self._assert_no_nan(flag, mode)
         return scores, out_lens
 

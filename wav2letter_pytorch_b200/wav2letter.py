@@ -138,8 +138,13 @@ class Wav2Letter(ConvCTCASR):
         F._need_cuda(x)                                  # RuntimeError on a CPU tensor: this build has no CPU path
         t = x.shape[2]
         h, first = x, True
+        tap = getattr(self, "_tap", None)                # parity instrumentation (tests/_layerwise.py): every block's input
         for block in self.conv1ds.children():
+            if tap is not None:
+                tap.append(h)
             h, t = block.forward_tm(h, t, from_ncw=first)
+            if tap is not None and h.requires_grad:
+                h.retain_grad()
             first = False
         out_lens = self.compute_output_lengths(input_lengths) if input_lengths is not None else None
         return h, out_lens
