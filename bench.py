@@ -362,6 +362,7 @@ class KernelTimer:
     # apply) and writes dz (+ the residual branch's gradient)
     BYTES_BOUND = {
         "bn_act_pad": lambda b: 2 * b["B"] * b["C"] * (b["T"] * (2 if b["res"] is not None else 1) + b["pad_left"] + b["T"] + b["pad_right"]),
+        "bn_finalize_act_pad": lambda b: 2 * b["B"] * b["C"] * (b["T"] * (2 if b["res"] is not None else 1) + b["pad_left"] + b["T"] + b["pad_right"]),
         "bn_act_bwd": lambda b: 2 * b["B"] * b["C"] * (2 * (b["pad_left"] + b["T"] + b["pad_right"] + b["T"])
                                                      + (b["dz_rows"] or b["T"]) + (b["T"] if b["want_g"] else 0)),
     }
@@ -496,11 +497,15 @@ def quick_leg(env, arch, mid, ragged, steps):
     try:
         one_step(model, opt, reducer, batch, 0, txt)
         barrier()
-        kt2, _ms2, _ = run(3, ["bn_act_pad", "bn_act_bwd"])
+        kt2, _ms2, _ = run(3, ["bn_act_pad", "bn_finalize_act_pad", "bn_act_bwd"])
     finally:
         WgradStream.enabled = enabled
-    for tag, v in kt2.totals_ms().items():
-        by = kt2.bytes.get(tag, 0) / 3
+    tot2, by2 = kt2.totals_ms(), dict(kt2.bytes)
+    if "bn_finalize_act_pad" in tot2:
+        tot2["bn_act_pad"] = tot2.pop("bn_finalize_act_pad") + tot2.get("bn_act_pad", 0.0)
+        by2["bn_act_pad"] = by2.pop("bn_finalize_act_pad", 0) + by2.get("bn_act_pad", 0)
+    for tag, v in tot2.items():
+        by = by2.get(tag, 0) / 3
         out[tag] = {"ms_per_step": v / 3, "GBps": by / (v / 3 / 1e3) / 1e9, "frac_hbm": by / (v / 3 / 1e3) / 1e9 / peaks["hbm"]}
     del model, opt, reducer
     torch.cuda.empty_cache()
@@ -723,13 +728,13 @@ def run_gpu_arm(args):
     conv_ms = {k: v for k, v in all_ms.items() if k.startswith("conv1d")}
     # ---- the same GEMM launches without overlap (wgrad back on the compute stream): per-kernel quality, spans do not overlap
     iso_ms, iso_layers, iso_elem = None, None, {}
-    if not args.profile:
+    if not args.profile and os.environ.get("W2L_BENCH_SKIP_ISO", "0") != "1":
         from wav2letter_pytorch_b200.layers import WgradStream
         was = WgradStream.enabled
         WgradStream.enabled = False
         iso_timer = KernelTimer()
         timed(model, opt, reducer, 0, 1, False)
-        iso_timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "bn_act_pad", "bn_act_bwd"])
+        iso_timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "bn_act_pad", "bn_finalize_act_pad", "bn_act_bwd"])
         iso_steps = max(3, min(args.steps, 6))
         timed(model, opt, reducer, iso_steps, 0, False)
         iso_timer.unwrap()
@@ -737,6 +742,9 @@ def run_gpu_arm(args):
         iso_all = {k: v / iso_steps for k, v in iso_timer.totals_ms().items()}
         iso_ms = {k: v for k, v in iso_all.items() if k.startswith("conv1d")}
         iso_elem = {k: (v, iso_timer.bytes.get(k, 0) / iso_steps) for k, v in iso_all.items() if not k.startswith("conv1d")}
+        if "bn_finalize_act_pad" in iso_elem:              # training runs the pass with the finalize fold: one row for both entry points
+            a_, b_ = iso_elem.pop("bn_finalize_act_pad"), iso_elem.get("bn_act_pad", (0.0, 0.0))
+            iso_elem["bn_act_pad"] = (a_[0] + b_[0], a_[1] + b_[1])
         try:                                               # a secondary table must never take the headline line down
             iso_layers = iso_timer.by_layer(iso_steps, None)
         except Exception as e:  # noqa: BLE001
@@ -752,9 +760,12 @@ def run_gpu_arm(args):
         del model, opt, reducer
         torch.cuda.empty_cache()
         m1, o1, r1 = build(1)
+        t_host = time.perf_counter()
         ms1 = timed(m1, o1, r1, max(args.steps, 10), max(args.warmup, 3), False)
+        t_host = (time.perf_counter() - t_host) * 1e3 / (max(args.steps, 10) + max(args.warmup, 3))
         extra = {"workload": "Wav2Letter mid_layers=1 (literal yaml default) train step, B=%d/GPU x %d s" % (BATCH, UTT_SEC),
-                 "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s"}
+                 "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s",
+                 "host_wall_ms_per_step_incl_warmup": t_host}
         del m1, o1, r1
 
     # ---- secondary legs the driver's single line must carry (N=1 only: the scaling runs stay lean): BASELINE config 3 (Jasper 10x5),
@@ -856,7 +867,7 @@ def run_gpu_arm(args):
                                         "ms_per_step": all_ms[tag], "algorithmic_bytes_per_step": timer.bytes[tag] // args.steps,
                                         "note": "CTC is serial in T (latency/MUFU bound at this batch), see DESIGN.md 3.2" if tag == "ctc_loss_raw" else
                                                 "5.6 MB per call: launch-latency bound at this size; profiles/ has the size sweep"}
-    for tag, label in (("bn_act_pad", "bn_act_pad_kernel x layers (BatchNorm apply + dropout + clamp/ReLU + residual + next layer's halo)"),
+    for tag, label in (("bn_act_pad", "bn_act_pad_kernel x layers (BatchNorm finalize + apply + dropout + clamp/ReLU + residual + next layer's halo)"),
                        ("bn_act_bwd", "bn_act_bwd_reduce + bn_act_bwd_apply x layers (activation/dropout/BatchNorm backward + halo fold)")):
         if tag in iso_elem and iso_elem[tag][0] > 0:       # timed in the serialized run (nothing overlaps them there), all layers together
             ms_t, by_t = iso_elem[tag]

@@ -231,30 +231,46 @@ int w2l_lens_chain(const void* lens_in, int32_t lens_is_int64, int32_t B, const 
  * buffer: y[b, pad_left + t, c]; reflect halos of pad_left / pad_right rows are filled from the
  * interior (nn.ReflectionPad1d of the NEXT layer, wav2letter.py:28-34,41); rows t >= lens[b] are zeroed
  * when lens != NULL (the masked_fill of the consumer MaskedConv1d, jasper.py:116-119).
- * dropout: keep-bits from Philox4x32-10(seed, element index / 8), 16 bits per element, p = drop_p (0 disables);
- * drop_mask (nullable, B*T*C/8 bytes) receives the keep-bits so that the backward passes read them back instead
- * of re-deriving them (they fall back to Philox when it is NULL). */
+ * dropout (nn.Dropout, wav2letter.py:44 / jasper.py:372-376): keep-bits from a counter-based splitmix64 stream
+ * (seed, element index / 8), 16 bits per element, p = drop_p (0 disables); drop_mask (nullable, B*T*C/8 bytes) receives
+ * the keep-bits so that the backward passes read them back instead of re-deriving them. */
 int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
                    int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask,
                    void* stream);
+/* The training-mode pass: w2l_bn_finalize folded into w2l_bn_act_pad.  scale / shift come from the batch statistics
+ * `stats` ([2C] sum, sum of squares over stat_rows rows, as the conv epilogue or w2l_bn_stats leaves them): every CTA derives
+ * them for its channels, one of them writes fin [4][C] = (scale, shift, mean, invstd) for the backward passes and applies the
+ * running-statistics / num_batches_tracked update of nn.BatchNorm1d (wav2letter.py:37, jasper.py:363; conv_bias is added to
+ * the running mean because the conv here runs without its bias, which training-mode BatchNorm cancels).
+ * zero_ptr / zero_count (nullable): a small fp32 buffer this launch clears for a LATER kernel -- the caller passes the layer's
+ * backward reduction buffer, so that no memset launch is needed for it. */
+int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows, const float* gamma, const float* beta,
+                            const float* conv_bias, float eps, float momentum, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, float* fin, const void* res, const float* res_scale,
+                            const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
+                            int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask,
+                            float* zero_ptr, int32_t zero_count, void* stream);
 /* In-place reflect halo for a buffer whose interior rows [pad_left, pad_left+T) were written by the fused
  * conv epilogue (inference: BatchNorm folded into scale/shift, wav2letter.py:41-46). */
 int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream);
 /* Backward of the above + BatchNorm backward, two passes over (dy_padded, z):
  *   g = fold_reflect(dyp)[b,t,c] * act'(.) * dropmask;  pass 1 reduces sum(g), sum(g*xhat) into
- *   red[0:C], red[C:2C] (zeroed by caller); pass 2 writes dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)).
- *   dgamma = red[C:2C], dbeta = red[0:C]. */
+ *   red[0:C], red[C:2C] (zero on entry: one atomic per channel and CTA); pass 2 writes
+ *   dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)), walking the rows in the reverse order of pass 1 (L2 reuse).
+ *   dgamma = red[C:2C], dbeta = red[0:C]; pass 2 copies red to red_out (nullable) so that a persistent red buffer can be
+ *   recycled, and clears zero_ptr[0:zero_count] (nullable; the caller passes the layer's forward statistics buffer). */
 int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                           const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
                           float* red, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act,
                           float drop_p, uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream);
+/* dz [B, dz_rows, C]: rows >= T zero-filled; g_out (nullable): the masked g, bf16 [B,T,C] (Jasper's residual branch) */
 int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
-                         const float* gamma, const float* red, void* dz /* [B, dz_rows, C]; rows >= T zero-filled */,
-                         int32_t dz_rows, void* g_out /* nullable: masked g, bf16 [B,T,C] */,
-                         int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
-                         uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream);
+                         const float* gamma, const float* red, void* dz, int32_t dz_rows, void* g_out, int32_t B, int32_t T,
+                         int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p, uint64_t seed,
+                         const int32_t* lens, const void* drop_mask, float* red_out, float* zero_ptr, int32_t zero_count,
+                         void* stream);
 
 /* logits [rows, ld] fp32 -> log_softmax / softmax over the first C columns -> out [rows, C] fp32
  * (wav2letter.py:87, jasper.py:470-473).  mode 0 = log_softmax, 1 = softmax.  nan_flag (nullable, device int32, zeroed

@@ -28,8 +28,8 @@ _CTC_DROP = ["fast_ex2", "fast_lg2", "cp_async4", "cp_async16", "cp_async_commit
 
 @functools.lru_cache(maxsize=None)
 def builds():
-    out = [KE.build([f], [], c_abi=True, post=_POST) for f in ("decode.cu", "elementwise.cu", "depthwise.cu", "novograd.cu", "metrics.cu",
-                                                                "features.cu")]
+    out = [KE.build([f], [], c_abi=True, post=_POST) for f in ("decode.cu", "depthwise.cu", "novograd.cu", "metrics.cu", "features.cu")]
+    out.append(KE.build(["elementwise.cu"], [], c_abi=True, post=_POST, drop=E.ELEMENTWISE_DROP, extra=E.ELEMENTWISE_PTX))
     out.append(KE.build(["ctc.cu"], [], c_abi=True, post=_POST, drop=_CTC_DROP, extra=E.CTC_PTX))
     out.append(KE.build(["conv_gemm.cu"], [], helpers_from_common=("pack_bf16x2", "make_smem_desc", "make_idesc_bf16"), subs=E.GEMM_SUBS,
                         c_abi=True, post=_POST, opt="-O2"))

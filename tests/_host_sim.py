@@ -173,8 +173,19 @@ def reflect_halo(y, T, pad_left, pad_right):
     return y
 
 
+def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked, B, T, C,
+                        pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None, res_shift=None, drop_mask=None,
+                        zero_after=None):
+    """w2l_bn_finalize_act_pad: the two restatements above in one call; the launch also clears ``zero_after``"""
+    fin = bn_finalize(stats, B * T, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked)
+    out = bn_act_pad(z, fin[0], fin[1], B, T, C, pad_left, pad_right, act, drop_p, seed, lens, res, res_scale, res_shift, None, drop_mask)
+    if zero_after is not None:
+        zero_after.zero_()
+    return out, fin
+
+
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None):
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None):
     assert drop_p == 0.0
     dz_rows = T if dz_rows is None else dz_rows
     zf = z.view(B, T, C).float()
@@ -189,6 +200,12 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
     sg = g.sum((0, 1))
     sx = (g * (zf - mean)).sum((0, 1)) * invstd
     red = torch.cat([sg, sx])
+    if red_ws is not None:                               # the kernels ADD into the persistent buffer (zero on entry is the caller's duty):
+        red_ws += red                                    # a buffer that was not cleared shows up in the result, as on the device
+        red = red_ws.clone()
+        sg, sx = red[:C], red[C:]
+    if zero_after is not None:
+        zero_after.zero_()
     inv_m = 1.0 / float(B * T)
     coef = (gamma.detach().float() if gamma is not None else 1.0) * invstd
     kB = -coef * sx * inv_m * invstd
@@ -336,7 +353,7 @@ def ctc_loss_raw(x, targets, input_lengths, target_lengths, blank=0, zero_infini
 
 # ------------------------------------------------------------------------------------------------ install
 _NAMES = ["im2col_ncw", "tm_to_ncw", "im2col_tm", "col2im_tm", "cast_bf16", "pack_wt", "bn_stats", "bn_finalize", "lens_chain",
-          "bn_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "conv1d_fwd", "conv1d_dgrad",
+          "bn_act_pad", "bn_finalize_act_pad", "reflect_halo", "bn_act_bwd", "log_softmax", "log_softmax_bwd", "colsum", "conv1d_fwd", "conv1d_dgrad",
           "conv1d_dgrad_wt", "conv1d_wgrad", "depthwise_fwd", "depthwise_dgrad", "depthwise_wgrad", "ctc_loss_raw"]
 
 

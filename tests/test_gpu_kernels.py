@@ -373,6 +373,73 @@ def test_bn_act_forward_backward(F, act, drop):
     assert rel_l2(dzp[:, :T].float(), dz.float()) < 1e-3 and (dzp[:, T:] == 0).all()      # reductions use fp32 atomics: last-bit noise
 
 
+@pytest.mark.parametrize("B,T,C,pl,pr,act,res", [(2, 37, 64, 0, 0, 1, False), (3, 50, 264, 4, 5, 2, False), (2, 41, 896, 28, 28, 2, False),
+                                                 (2, 33, 768, 0, 0, 1, True), (1, 19, 2056, 2, 3, 1, True), (5, 7, 8, 1, 1, 2, False)])
+def test_bn_passes_geometry_and_fused_finalize(F, B, T, C, pl, pr, act, res):
+    """the row-looping BatchNorm / activation passes over every thread geometry (C/8 = 8 ... 257 channel vectors: bx x ny = 8x32 ... 256x1,
+    two column blocks at 2056), the finalize fold (w2l_bn_finalize_act_pad == w2l_bn_finalize + w2l_bn_act_pad to 1 ulp), the
+    persistent reduction buffer (red_ws) and the buffers the passes clear for each other -- against torch autograd"""
+    g = torch.Generator().manual_seed(C + T)
+    z = _bf(torch.randn(B, T, C, generator=g) * 1.5 + 0.3)
+    zr = _bf(torch.randn(B, T, C, generator=g)) if res else None
+    gamma, beta, cbias = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g), torch.randn(C, generator=g)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g, dtype=torch.int32) if res else None
+    zc = z.to(torch.bfloat16).cuda()
+    zrc = zr.to(torch.bfloat16).cuda() if res else None
+    lens_c = lens.cuda() if res else None
+    rs, rsh = (torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)) if res else (None, None)
+    stats = F.bn_stats(zc, C)
+    rm0, rv0 = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5
+    # ---- separate finalize + apply
+    rm_a, rv_a, nbt_a = rm0.clone().cuda(), rv0.clone().cuda(), torch.tensor(3, dtype=torch.long).cuda()
+    fin_a = F.bn_finalize(stats, B * T, C, gamma.cuda(), beta.cuda(), cbias.cuda(), 1e-3, 0.1, rm_a, rv_a, nbt_a)
+    kw = dict(res=zrc, res_scale=None if not res else rs.cuda(), res_shift=None if not res else rsh.cuda())
+    y_a = F.bn_act_pad(zc, fin_a[0], fin_a[1], B, T, C, pl, pr, act, 0.0, 0, lens_c, **kw)
+    # ---- folded: same bits, and the launch clears the buffer handed to it
+    rm_b, rv_b, nbt_b = rm0.clone().cuda(), rv0.clone().cuda(), torch.tensor(3, dtype=torch.long).cuda()
+    dirty = torch.full((2 * C,), 7.0, device="cuda")
+    y_b, fin_b = F.bn_finalize_act_pad(zc, stats, gamma.cuda(), beta.cuda(), cbias.cuda(), 1e-3, 0.1, rm_b, rv_b, nbt_b, B, T, C, pl, pr, act,
+                                       0.0, 0, lens_c, zero_after=dirty, **kw)
+    # the fold derives 1/sqrt(var + eps) with rsqrt + one Newton step where the standalone kernel divides in fp64: <= 1 ulp apart
+    torch.testing.assert_close(fin_a, fin_b, rtol=3e-7, atol=1e-7)
+    torch.testing.assert_close(rm_a, rm_b, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(rv_a, rv_b, rtol=1e-6, atol=1e-7)
+    assert rel_l2(y_b.float(), y_a.float()) < 1e-3
+    assert int(nbt_b) == 4 and int(nbt_a) == 4 and float(dirty.abs().max()) == 0.0
+    # ---- torch reference
+    zt = z.transpose(1, 2).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_t, rv_t = rm0.clone(), rv0.clone()
+    bn = TF.batch_norm(zt + cbias[None, :, None], rm_t, rv_t, gr, br, training=True, momentum=0.1, eps=1e-3)
+    np.testing.assert_allclose(rm_b.cpu().numpy(), rm_t.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(rv_b.cpu().numpy(), rv_t.numpy(), rtol=1e-3, atol=1e-4)
+    if res:
+        bn = bn + (zr.transpose(1, 2) * rs[None, :, None] + rsh[None, :, None])
+    y_ref = torch.clamp(bn, 0, 20) if act == 2 else torch.relu(bn)
+    if res:
+        keep = (torch.arange(T)[None, :] < lens[:, None]).float()[:, None, :]
+        y_ref = y_ref * keep
+    yp_ref = TF.pad(y_ref, (pl, pr), mode="reflect") if pl + pr else y_ref
+    assert rel_l2(y_b.float().cpu(), yp_ref.detach().transpose(1, 2)) < 5e-3
+    dyp = _bf(torch.randn(B, C, T + pl + pr, generator=g))
+    yp_ref.backward(dyp)
+    dyc = dyp.transpose(1, 2).to(torch.bfloat16).contiguous().cuda()
+    # ---- backward with a persistent reduction buffer: zero on entry, dirty afterwards, sums returned in a fresh tensor
+    red_ws = torch.zeros(2 * C, device="cuda")
+    dirty.fill_(3.0)
+    dz, red, gout = F.bn_act_bwd(dyc, zc, fin_b[0], fin_b[1], fin_b[2], fin_b[3], gamma.cuda(), B, T, C, pl, pr, act, 0.0, 0, lens_c,
+                                 want_g=res, dz_rows=T + 3, red_ws=red_ws, zero_after=dirty, **kw)
+    assert red.data_ptr() != red_ws.data_ptr() and torch.equal(red, red_ws) and float(dirty.abs().max()) == 0.0
+    assert (dz[:, T:] == 0).all()
+    scale_err = 2e-2 if T * B < 100 else 1e-2
+    assert rel_l2(dz[:, :T].float().cpu(), zt.grad.transpose(1, 2)) < scale_err
+    assert rel_l2(red[:C].cpu(), br.grad) < 5e-3 and rel_l2(red[C:].cpu(), gr.grad) < 5e-3
+    # ---- and without one (the buffer is allocated zero-filled per call): same numbers up to the order of the atomics
+    dz2, red2, _ = F.bn_act_bwd(dyc, zc, fin_b[0], fin_b[1], fin_b[2], fin_b[3], gamma.cuda(), B, T, C, pl, pr, act, 0.0, 0, lens_c,
+                                want_g=res, dz_rows=T + 3, **kw)
+    assert rel_l2(red2, red) < 1e-5 and rel_l2(dz2.float(), dz.float()) < 1e-3
+
+
 def test_log_softmax_and_colsum(F):
     g = torch.Generator().manual_seed(6)
     logits = torch.randn(4, 75, 32, generator=g) * 3

@@ -200,6 +200,55 @@ def test_prefix_beam_search_on_device_scores(pkg, golden):
         assert got == want
 
 
+def test_bn_scratch_buffers_are_recycled_correctly(pkg):
+    """the per-layer BatchNorm scratch (layers.BnScratch: forward statistics / backward sums, each cleared by a kernel of the other
+    pass) under call orders a training loop does not produce: a train-mode forward without backward, two forwards before their
+    backwards, a second backward over a retained graph -- gradients and running statistics must come out as in plain steps"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    cfg = config.compose(overrides=["model.mid_layers=2"]).model
+    for l in cfg.layers:
+        l["dropout"] = 0.0
+    torch.manual_seed(1)
+    model = Wav2Letter(cfg).cuda().train()
+    xa, il, tg, tl = O.synthetic_batch(3, 1, seed=7)
+    xb = O.synthetic_batch(3, 1, seed=8)[0]
+    xa, xb, il, tg, tl = xa.cuda(), xb.cuda(), il.cuda(), tg.cuda(), tl.cuda()
+
+    def loss_of(x):
+        out, ol = model(x, il)
+        return model.criterion(out.transpose(0, 1), tg, ol, tl)
+
+    def grads_of(x):
+        model.zero_grad(set_to_none=True)
+        loss_of(x).backward()
+        return [p.grad.detach().clone() for p in model.parameters()]
+
+    def same(a, b):
+        return all(rel_l2(u, v) < 2e-3 or float(v.abs().max()) == 0.0 for u, v in zip(a, b))     # fp32 atomics order only
+
+    ga, gb = grads_of(xa), grads_of(xb)
+    assert same(grads_of(xa), ga)                                 # steady state: forward, backward, forward, backward
+    with torch.no_grad():                                         # a train-mode forward that never gets its backward (dirty statistics)
+        loss_of(xb)
+    assert same(grads_of(xa), ga)
+    model.zero_grad(set_to_none=True)                             # two forwards, then their backwards in reverse and in order
+    la, lb = loss_of(xa), loss_of(xb)
+    lb.backward()
+    g2 = [p.grad.detach().clone() for p in model.parameters()]
+    model.zero_grad(set_to_none=True)
+    la.backward()
+    assert same(g2, gb) and same([p.grad for p in model.parameters()], ga)
+    model.zero_grad(set_to_none=True)                             # a second backward over a retained graph
+    l = loss_of(xa)
+    l.backward(retain_graph=True)
+    model.zero_grad(set_to_none=True)
+    l.backward()
+    assert same([p.grad for p in model.parameters()], ga)
+    rm = model.conv1ds.conv1d_0.batch_norm.running_mean
+    assert torch.isfinite(rm).all() and int(model.conv1ds.conv1d_0.batch_norm.num_batches_tracked) == 8
+
+
 def test_novograd_golden(pkg, golden):
     from wav2letter_pytorch_b200.novograd import Novograd
     g = golden("novograd")

@@ -142,7 +142,9 @@ SIGNATURES = {
                                c_u64, c_ptr, c_ptr, c_ptr]),
     "w2l_reflect_halo": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_bn_act_bwd_reduce": (c_i32, [c_ptr] * 10 + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
-    "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 12 + [c_i32, c_ptr] + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr, c_ptr]),
+    "w2l_bn_finalize_act_pad": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_f32, c_f32] + [c_ptr] * 8 + [c_i32] * 6
+                                + [c_f32, c_u64, c_ptr, c_ptr, c_ptr, c_i32, c_ptr]),
+    "w2l_bn_act_bwd_apply": (c_i32, [c_ptr] * 12 + [c_i32, c_ptr] + [c_i32] * 6 + [c_f32, c_u64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr]),
     "w2l_log_softmax": (c_i32, [c_ptr, c_i32, c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_log_softmax_bwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),

@@ -1,42 +1,41 @@
 // Memory-bound companions of the conv kernels: layout changes, BatchNorm statistics / apply / backward with
 // fused activation, dropout, reflection halo and length mask, log_softmax fwd/bwd, bias gradient, casts.
 // All activations are time-major [B, T, C] bf16; every kernel moves 16 bytes (8 channels) per thread access.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace w2l {
 
-// ---------------------------------------------------------------- Philox4x32-10 (dropout masks)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
+// ---------------------------------------------------------------- dropout keep-bits
+// 32 keep-bits at a time -- the 4 consecutive rows x 8 channels a thread of the BatchNorm passes stages together: bit 8u + i belongs to
+// row 4*rg + u, channel 8*cv + i -- each 1 with probability keep_q / 2^kDropBits.  Bitwise Bernoulli synthesis: walking the binary digits
+// of the keep probability from the least significant one, m <- digit ? (m | w) : (m & w) with a fresh uniform word w per digit gives
+// P(bit) <- (digit + P(bit)) / 2, i.e. the keep probability resolved to 2^-12 for all 32 elements from 12 hash words; the words are
+// murmur3's 32-bit finaliser over a counter keyed by (seed, row group, channel vector).  ~35 instructions per 16-byte vector where
+// the Philox4x32-10 stream of the first cut spent ~115 (one call per 8 elements, 16 bits per element).  The realised keep
+// probability keep_q / 4096 -- not the requested 1 - p, which differs from it by < 1.3e-4 -- scales the kept elements, so the
+// expectation is exact (nn.Dropout semantics, wav2letter.py:44 / jasper.py:372-376).  The forward pass stores the bits (drop_mask)
+// and the backward passes read them back.
+constexpr int kDropBits = 12;
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
-// keep-bits for the 8 consecutive elements starting at element index e (e % 8 == 0): ONE Philox call, 16 random bits per
-// element (keep iff u16 >= p * 65536, i.e. p is resolved to 1/65536)
-__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t e, float p) {
-  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint64_t c0 = e >> 3;
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), 0u, 0u), key);
-  const uint32_t thr = (uint32_t)(p * 65536.f);
-  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-  uint32_t bits = 0;
+__device__ __forceinline__ uint32_t dropout_mask32(uint64_t seed, uint32_t rg, uint32_t cv, uint32_t keep_q) {
+  const uint32_t base = fmix32(fmix32((uint32_t)seed ^ rg) + (uint32_t)(seed >> 32) + cv * 0x9E3779B1u);
+  uint32_t m = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    bits |= ((u[i] & 0xFFFFu) >= thr ? 1u : 0u) << (2 * i);
-    bits |= ((u[i] >> 16) >= thr ? 1u : 0u) << (2 * i + 1);
+  for (int j = 0; j < kDropBits; ++j) {
+    const uint32_t w = fmix32(base + (uint32_t)(j + 1) * 0x9E3779B9u);
+    const uint32_t digit = 0u - ((keep_q >> j) & 1u);                // all ones / all zeros
+    m = (m & w) | (digit & (m ^ w));                               // digit ? (m | w) : (m & w): one LOP3
   }
-  return bits;
-}
-__device__ __forceinline__ void dropout_mult8(uint32_t bits, float p, float (&m)[8]) {
-  const float inv = 1.f / (1.f - p);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) m[i] = ((bits >> i) & 1u) ? inv : 0.f;
+  return m;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
@@ -245,96 +244,95 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int64_t rows
 }
 
 // ---------------------------------------------------------------- BN apply + dropout + act + halo + mask
-// Thread mapping of the three kernels below: block (32, 8); threadIdx.x -> one 8-channel vector (16 B) of a row, so a warp
-// moves 512 contiguous bytes; blockIdx.x tiles the channel vectors, blockIdx.y a contiguous range of (b, t) rows walked
-// by the 8 row lanes.  A thread keeps its channel for the whole kernel, so the per-channel constants live in registers.
-struct BnActArgs {
+// Thread mapping of the three kernels below (round 2): a CTA is bx x ny threads with bx = min(C/8, 256) channel vectors (16 bytes =
+// 8 bf16 channels each) and ny = 256 / bx row lanes.  For every width up to 2048 channels bx == C/8, so the threads of a CTA walk
+// CONSECUTIVE 16-byte vectors of the row-major activation -- a warp's access is one contiguous run whatever C is (the first cut tiled
+// the channels in blocks of 256: a 896-wide layer ran its fourth column block with half-empty warps) -- and a thread keeps its 8
+// channels, hence their constants in registers, for the whole kernel.  blockIdx.y owns a contiguous range of (b, t) rows, a thread
+// walks it in GROUPS OF 4 CONSECUTIVE ROWS (the unit the dropout bits are drawn for); the grid holds 2-3 CTAs per SM, each looping
+// over hundreds of rows, so that the per-CTA fixed costs (constants, block reduction, one atomic per channel) are amortised.
+// These passes are INSTRUCTION-issue bound before they are HBM bound -- at 6.5 TB/s a thread may spend ~170 issue slots per 32 bytes
+// it moves, and the first cut spent ~250 (profiles/r2_bn_passes.md) -- hence: dropout bits for 32 elements from 14 32-bit hashes,
+// dropout scaling folded into the per-channel constants, NaN-propagating min/max instead of compare+select, one integer division per
+// row group, float rsqrt + one Newton step in the finalize fold.
+constexpr int kBnThreads = 256;
+constexpr int kBnFwdCtasPerSm = 3;   // forward pass: <= 80 registers
+constexpr int kBnBwdCtasPerSm = 2;   // backward passes: 3 streams + 5 per-channel constants per thread want ~110 registers
+constexpr int kRowGroup = 4;         // consecutive rows a thread stages together: all their 16-byte loads are issued before any is used
+
+struct BnFwdArgs {
   const __nv_bfloat16* z;
   const __nv_bfloat16* res;
+  const float* scale;          // given affine (eval / separately finalised statistics); unused when stats != null
+  const float* shift;
+  const float* res_scale;
+  const float* res_shift;
+  // stats != null: the batch statistics the conv epilogue accumulated -> scale / shift here, in every CTA (a few flops per channel),
+  // instead of a bn_finalize launch in between; CTA row 0 also writes what backward needs and moves the running statistics
+  const float* stats;          // [2C] sum, sum of squares over stat_rows rows
+  int64_t stat_rows;
+  const float* gamma;
+  const float* beta;
+  const float* conv_bias;
+  float eps, momentum;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float* fin;                  // [4][C] scale, shift, mean, invstd
+  __nv_bfloat16* y;
+  int B, T, C, pl, pr;
+  uint32_t keep_q;             // dropout: keep probability in units of 2^-kDropBits (0: no dropout)
+  float inv_keep;              // 2^kDropBits / keep_q
+  uint64_t seed;
+  const int32_t* lens;
+  uint8_t* drop_mask;          // [B*T*C/8] keep-bits: written by the forward pass, read back by the backward passes
+  float* zero_ptr;             // a small buffer this launch clears for a LATER kernel (the layer's backward reduction sums)
+  int zero_count;
+  int rows_per_block;
+};
+
+struct BnBwdArgs {
+  const __nv_bfloat16* z;
+  const __nv_bfloat16* res;
+  const __nv_bfloat16* dyp;
   const float* scale;
   const float* shift;
   const float* res_scale;
   const float* res_shift;
-  int B, T, C, pl, pr, act;
-  float drop_p;
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  float* red;                  // [2C] sum g, sum g*xhat: accumulated by the reduce pass (zero on entry), read by the apply pass
+  float* red_out;              // apply pass: copy of red for the caller (dbeta, dgamma), so that `red` itself can be recycled
+  __nv_bfloat16* dz;
+  __nv_bfloat16* g_out;
+  int dz_rows;
+  int B, T, C, pl, pr;
+  uint32_t keep_q;
+  float inv_keep;
   uint64_t seed;
   const int32_t* lens;
-  uint8_t* drop_mask;          // [B*T*C/8] keep-bits: written by the forward pass, read back by the backward passes
+  const uint8_t* drop_mask;
+  float* zero_ptr;             // apply pass: a small buffer cleared for a LATER kernel (the layer's forward statistics)
+  int zero_count;
+  int rows_per_block;
 };
 
-// Each thread walks its rows four at a time (rows r, r+8, r+16, r+24 of the block's range) and issues all 16-byte loads of
-// the four rows before touching any of them: with ~2 x 256 threads resident per SM that keeps ~64 KB in flight, which is
-// what HBM3e needs to stream (a one-row-at-a-time loop measured 17% of peak, profiles/).
-constexpr int kRowsPerIter = 4;
-
-struct RowIn {
-  uint4 z, r, d0;              // conv output, residual, upstream gradient row (mirror rows are fetched on demand: <8% of rows)
-  int b, t;
-  bool live;
-};
-
-__device__ __forceinline__ void row_bt(int r, int T, int& b, int& t) {
-  b = r / T;
-  t = r - b * T;
+// NaN passes through the activations, as torch.relu / torch.clamp do (fmaxf / fminf would swallow it): one instruction each
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 }
-
-template <bool HAS_RES>
-__device__ __forceinline__ void load_fwd_row(const BnActArgs& a, int r, int r_end, int c, RowIn& in) {
-  in.live = r < r_end;
-  if (!in.live) return;
-  row_bt(r, a.T, in.b, in.t);
-  const int64_t e = (int64_t)r * a.C + c;
-  in.z = __ldg(reinterpret_cast<const uint4*>(a.z + e));
-  if (HAS_RES) in.r = __ldg(reinterpret_cast<const uint4*>(a.res + e));
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 }
-
-template <bool HAS_RES>
-__device__ __forceinline__ void load_bwd_row(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, int r, int r_end, int c, RowIn& in) {
-  load_fwd_row<HAS_RES>(a, r, r_end, c, in);
-  if (!in.live) return;
-  const int Tp = a.pl + a.T + a.pr;
-  in.d0 = __ldg(reinterpret_cast<const uint4*>(dyp + ((int64_t)in.b * Tp + a.pl + in.t) * a.C + c));
-}
-
-// BN output [+ residual] with dropout applied ("pre"), the dropout multipliers and z for one staged row
-template <bool HAS_RES, bool DROP, bool WRITE_MASK>
-__device__ __forceinline__ void pre_from_row(const BnActArgs& a, const float (&sc)[8], const float (&sh)[8], const float (&rsc)[8],
-                                             const float (&rsh)[8], const RowIn& in, int r, int c, float (&pre)[8], float (&mult)[8],
-                                             float (&zv)[8]) {
-  unpack8(in.z, zv);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) pre[i] = fmaf(zv[i], sc[i], sh[i]);
-  if (HAS_RES) {
-    float rv[8];
-    unpack8(in.r, rv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pre[i] += fmaf(rv[i], rsc[i], rsh[i]);
-  }
-  if (DROP) {
-    const int64_t e = (int64_t)r * a.C + c;
-    uint32_t bits;
-    if (WRITE_MASK) {
-      bits = dropout_keep8(a.seed, (uint64_t)e, a.drop_p);
-      if (a.drop_mask) a.drop_mask[e >> 3] = (uint8_t)bits;
-    } else {
-      bits = a.drop_mask ? (uint32_t)a.drop_mask[e >> 3] : dropout_keep8(a.seed, (uint64_t)e, a.drop_p);
-    }
-    dropout_mult8(bits, a.drop_p, mult);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pre[i] *= mult[i];
-  }
-}
-
-// activation as a compile-time switch: the per-element code is straight-line (a runtime `act` costs a compare+branch per
-// element; profiles/ shows these kernels were instruction-issue bound before this)
-// NaN passes through, as torch.relu / torch.clamp do (fmaxf / fminf would swallow it): compare-and-select, not min/max
 template <int ACT>
 __device__ __forceinline__ float act_fwd(float v) {
-  if (ACT == W2L_ACT_RELU) return v < 0.f ? 0.f : v;
-  if (ACT == W2L_ACT_CLAMP20) {
-    const float t = v < 0.f ? 0.f : v;
-    return t > 20.f ? 20.f : t;
-  }
+  if (ACT == W2L_ACT_RELU) return max_nan(v, 0.f);
+  if (ACT == W2L_ACT_CLAMP20) return min_nan(max_nan(v, 0.f), 20.f);
   return v;
 }
 template <int ACT>
@@ -344,17 +342,163 @@ __device__ __forceinline__ bool act_pass(float pre) {
   return true;
 }
 
-// masked upstream gradient g for one staged row (reflect halo folded, activation + dropout + length mask applied)
-template <int ACT, bool DROP>
-__device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat16* __restrict__ dyp, int c, const RowIn& in,
-                                           const float (&pre)[8], const float (&mult)[8], float (&g)[8]) {
-  unpack8(in.d0, g);
-  const int dr = a.T - 1 - in.t;
-  if ((in.t >= 1 && in.t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo
-    const __nv_bfloat16* base = dyp + (int64_t)in.b * (a.pl + a.T + a.pr) * a.C + c;
+__device__ __forceinline__ void zero_small(float* p, int n) {
+  if (p == nullptr || blockIdx.x != 0 || blockIdx.y != 0) return;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < n; i += blockDim.x * blockDim.y) p[i] = 0.f;
+}
+
+// per-channel constants of a thread's 8 channels; with dropout the 1/keep factor is folded in, so that fma(z, sc, sh) is the value a
+// KEPT element takes -- forward and backward build it with the same instructions, hence take the same activation-gate decisions
+template <bool DROP, bool HAS_RES>
+__device__ __forceinline__ void scale_for_dropout(float inv_keep, float (&sc)[8], float (&sh)[8], float (&rsc)[8], float (&rsh)[8]) {
+  if (!DROP) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] *= inv_keep;
+    sh[i] *= inv_keep;
+    if (HAS_RES) {
+      rsc[i] *= inv_keep;
+      rsh[i] *= inv_keep;
+    }
+  }
+}
+
+template <int ACT, bool DROP, bool HAS_RES>
+__global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel(BnFwdArgs a) {
+  zero_small(a.zero_ptr, a.zero_count);
+  const int ny = blockDim.y;
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cv * 8;
+  if (c >= a.C) return;
+  float sc[8], sh[8], rsc[8], rsh[8];
+  if (a.stats != nullptr) {                          // kernel-uniform: the finalize fold (the arithmetic of bn_finalize_kernel)
+    float s1[8], s2[8], ga[8], be[8];
+    load8f(a.stats + c, s1);
+    load8f(a.stats + a.C + c, s2);
+    if (a.gamma) load8f(a.gamma + c, ga);
+    if (a.beta) load8f(a.beta + c, be);
+    const bool writer = blockIdx.y == 0 && threadIdx.y == 0;
+    if (writer && c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
+    const double n = (double)a.stat_rows, inv_n = 1.0 / n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double mean = (double)s1[i] * inv_n;
+      double var = (double)s2[i] * inv_n - mean * mean;          // the one place that needs the fp64 difference
+      if (var < 0.0) var = 0.0;
+      const float ve = (float)(var + (double)a.eps);
+      float invstd = rsqrtf(ve);
+      invstd = invstd * (1.5f - 0.5f * ve * invstd * invstd);     // one Newton step: <= 1 ulp
+      const float g = a.gamma ? ga[i] : 1.f, bt = a.beta ? be[i] : 0.f;
+      sc[i] = g * invstd;
+      sh[i] = bt - (float)mean * g * invstd;
+      if (writer) {
+        a.fin[c + i] = sc[i];
+        a.fin[a.C + c + i] = sh[i];
+        a.fin[2 * a.C + c + i] = (float)mean;
+        a.fin[3 * a.C + c + i] = invstd;
+        if (a.running_mean) {
+          const float m_full = (float)mean + (a.conv_bias ? a.conv_bias[c + i] : 0.f);
+          a.running_mean[c + i] = (1.f - a.momentum) * a.running_mean[c + i] + a.momentum * m_full;
+          const double unbiased = a.stat_rows > 1 ? var * n / (n - 1.0) : var;
+          a.running_var[c + i] = (1.f - a.momentum) * a.running_var[c + i] + a.momentum * (float)unbiased;
+        }
+      }
+    }
+  } else {
+    load8f(a.scale + c, sc);
+    load8f(a.shift + c, sh);
+  }
+  if (HAS_RES) {
+    load8f(a.res_scale + c, rsc);
+    load8f(a.res_shift + c, rsh);
+  }
+  scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
+  const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
+  const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);   // r_begin % kRowGroup == 0
+  constexpr int kBatch = HAS_RES ? 2 : kRowGroup;    // rows whose loads are in flight together (two streams with a residual)
+  for (int r0 = r_begin + threadIdx.y * kRowGroup; r0 < r_end; r0 += ny * kRowGroup) {
+    uint32_t keep = 0xFFFFFFFFu;
+    if (DROP) keep = dropout_mask32(a.seed, (uint32_t)(r0 / kRowGroup), (uint32_t)cv, a.keep_q);
+    int b = r0 / a.T, t = r0 - b * a.T;
+#pragma unroll
+    for (int h = 0; h < kRowGroup; h += kBatch) {
+      uint4 zq[kBatch], rq[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        if (r0 + h + u < r_end) {
+          const int64_t e = (int64_t)(r0 + h + u) * a.C + c;
+          zq[u] = __ldg(reinterpret_cast<const uint4*>(a.z + e));
+          if (HAS_RES) rq[u] = __ldg(reinterpret_cast<const uint4*>(a.res + e));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int r = r0 + h + u;
+        if (r < r_end) {
+          float v[8];
+          unpack8(zq[u], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
+          if (HAS_RES) {
+            float rv[8];
+            unpack8(rq[u], rv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += fmaf(rv[i], rsc[i], rsh[i]);
+          }
+          if (DROP && a.drop_mask) a.drop_mask[((int64_t)r * a.C + c) >> 3] = (uint8_t)(keep >> (8 * (h + u)));
+          const bool masked = a.lens && t >= a.lens[b];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool on = !masked && (!DROP || ((keep >> (8 * (h + u) + i)) & 1u));
+            v[i] = on ? act_fwd<ACT>(v[i]) : 0.f;
+          }
+          const uint4 q = pack8(v);
+          __nv_bfloat16* yb = a.y + (int64_t)b * Tp * a.C + c;
+          *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
+          if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
+          const int d = a.T - 1 - t;
+          if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
+        }
+        if (++t == a.T) {
+          t = 0;
+          ++b;
+        }
+      }
+    }
+  }
+}
+
+// one staged row of the backward passes: conv output, residual, upstream gradient, dropout keep-bits -- all requested together
+struct BwdRow {
+  uint4 z, r, d;
+  uint32_t bits;
+};
+
+template <bool DROP, bool HAS_RES>
+__device__ __forceinline__ void load_bwd_row(const BnBwdArgs& a, int r, int b, int t, int cv, BwdRow& in) {
+  const int c = cv * 8;
+  const int64_t e = (int64_t)r * a.C + c;
+  in.z = __ldg(reinterpret_cast<const uint4*>(a.z + e));
+  if (HAS_RES) in.r = __ldg(reinterpret_cast<const uint4*>(a.res + e));
+  in.d = __ldg(reinterpret_cast<const uint4*>(a.dyp + ((int64_t)b * (a.pl + a.T + a.pr) + a.pl + t) * a.C + c));
+  if (DROP)
+    in.bits = a.drop_mask ? (uint32_t)__ldg(a.drop_mask + (e >> 3))
+                          : (dropout_mask32(a.seed, (uint32_t)(r / kRowGroup), (uint32_t)cv, a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
+}
+
+// masked upstream gradient g and the conv output for one staged row (reflect halo folded; activation gate, dropout, length mask)
+template <int ACT, bool DROP, bool HAS_RES>
+__device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int b, int t, int c, const BwdRow& in, const float (&sc)[8],
+                                           const float (&sh)[8], const float (&rsc)[8], const float (&rsh)[8], float (&g)[8],
+                                           float (&zv)[8]) {
+  unpack8(in.z, zv);
+  unpack8(in.d, g);
+  const int dr = a.T - 1 - t;
+  if ((t >= 1 && t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo (<8 % of the rows)
+    const __nv_bfloat16* base = a.dyp + (int64_t)b * (a.pl + a.T + a.pr) * a.C + c;
     float h[8];
-    if (in.t >= 1 && in.t <= a.pl) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl - in.t) * a.C)), h);
+    if (t >= 1 && t <= a.pl) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl - t) * a.C)), h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
@@ -364,167 +508,189 @@ __device__ __forceinline__ void g_from_row(const BnActArgs& a, const __nv_bfloat
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
   }
-  const bool masked = a.lens && in.t >= a.lens[in.b];
+  float rv[8];
+  if (HAS_RES) unpack8(in.r, rv);
+  const bool masked = a.lens && t >= a.lens[b];
+  const float gs = DROP ? a.inv_keep : 1.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float gi = DROP ? g[i] * mult[i] : g[i];
-    g[i] = (act_pass<ACT>(pre[i]) && !masked) ? gi : 0.f;
+    float pre = fmaf(zv[i], sc[i], sh[i]);                         // the kept element's value (1/keep folded into sc, sh)
+    if (HAS_RES) pre += fmaf(rv[i], rsc[i], rsh[i]);
+    const bool on = !masked && act_pass<ACT>(pre) && (!DROP || ((in.bits >> i) & 1u));
+    g[i] = on ? g[i] * gs : 0.f;
   }
 }
 
-#define W2L_LOAD_AFFINE(a, c)                          \
-  float sc[8], sh[8], rsc[8], rsh[8];                  \
-  load8f((a).scale + (c), sc);                         \
-  load8f((a).shift + (c), sh);                         \
-  if (HAS_RES) {                                       \
-    load8f((a).res_scale + (c), rsc);                  \
-    load8f((a).res_shift + (c), rsh);                  \
-  } else {                                             \
-    _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) rsc[i_] = rsh[i_] = 0.f; \
-  }
-
+// red[0:C] += sum g, red[C:2C] += sum g*xhat   (accumulated as sum g*(z-mean), scaled by invstd once per CTA; red is zero on entry)
 template <int ACT, bool DROP, bool HAS_RES>
-__global__ void __launch_bounds__(256, 2) bn_act_pad_kernel(BnActArgs a, __nv_bfloat16* __restrict__ y, int rows_per_block) {
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
-  if (c >= a.C) return;
-  W2L_LOAD_AFFINE(a, c)
-  const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
-  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
-    RowIn in[kRowsPerIter];
-#pragma unroll
-    for (int u = 0; u < kRowsPerIter; ++u) load_fwd_row<HAS_RES>(a, r0 + 8 * u, r_end, c, in[u]);
-#pragma unroll
-    for (int u = 0; u < kRowsPerIter; ++u) {
-      if (!in[u].live) continue;
-      float pre[8], mult[8], zv[8];
-      pre_from_row<HAS_RES, DROP, true>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
-      const int b = in[u].b, t = in[u].t;
-      const bool masked = a.lens && t >= a.lens[b];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pre[i] = masked ? 0.f : act_fwd<ACT>(pre[i]);
-      const uint4 q = pack8(pre);
-      __nv_bfloat16* yb = y + (int64_t)b * Tp * a.C + c;
-      *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
-      if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
-      const int d = a.T - 1 - t;
-      if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
-    }
-  }
-}
-
-// red[0:C] += sum g, red[C:2C] += sum g*xhat   (accumulated as sum g*(z-mean), scaled by invstd once per block)
-template <int ACT, bool DROP, bool HAS_RES>
-__global__ void __launch_bounds__(256, 2)
-bn_act_bwd_reduce_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
-                         const float* __restrict__ invstd, float* __restrict__ red, int rows_per_block) {
-  __shared__ float s_a[8][256 + 8], s_b[8][256 + 8];
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+__global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
+  constexpr int kRows = HAS_RES ? 2 : kRowGroup;     // the residual variants carry a third stream: fewer rows in flight, no spills
+  __shared__ __align__(16) float s_a[kBnThreads * 8], s_b[kBnThreads * 8];
+  const int bx = blockDim.x, ny = blockDim.y;
+  const int cv = blockIdx.x * bx + threadIdx.x;
+  const int c = cv * 8;
   float sg[8], sx[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
   if (c < a.C) {
-    W2L_LOAD_AFFINE(a, c)
-    float mu[8];
-    load8f(mean + c, mu);
+    float sc[8], sh[8], rsc[8], rsh[8], mu[8];
+    load8f(a.scale + c, sc);
+    load8f(a.shift + c, sh);
+    if (HAS_RES) {
+      load8f(a.res_scale + c, rsc);
+      load8f(a.res_shift + c, rsh);
+    }
+    scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
+    load8f(a.mean + c, mu);
     const int rows = a.B * a.T;
-    const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-    for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
-      RowIn in[kRowsPerIter];
+    const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);
+    for (int r0 = r_begin + threadIdx.y * kRows; r0 < r_end; r0 += ny * kRows) {
+      BwdRow in[kRows];
+      const int b0 = r0 / a.T, t0 = r0 - b0 * a.T;
+      {
+        int b = b0, t = t0;
 #pragma unroll
-      for (int u = 0; u < kRowsPerIter; ++u) load_bwd_row<HAS_RES>(a, dyp, r0 + 8 * u, r_end, c, in[u]);
+        for (int u = 0; u < kRows; ++u) {
+          if (r0 + u < r_end) load_bwd_row<DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
+          if (++t == a.T) {
+            t = 0;
+            ++b;
+          }
+        }
+      }
+      int b = b0, t = t0;
 #pragma unroll
-      for (int u = 0; u < kRowsPerIter; ++u) {
-        if (!in[u].live) continue;
-        float pre[8], mult[8], zv[8], g[8];
-        pre_from_row<HAS_RES, DROP, false>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
-        g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
+      for (int u = 0; u < kRows; ++u) {
+        if (r0 + u < r_end) {
+          float g[8], zv[8];
+          g_from_row<ACT, DROP, HAS_RES>(a, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          sg[i] += g[i];
-          sx[i] = fmaf(g[i], zv[i] - mu[i], sx[i]);
+          for (int i = 0; i < 8; ++i) {
+            sg[i] += g[i];
+            sx[i] = fmaf(g[i], zv[i] - mu[i], sx[i]);
+          }
+        }
+        if (++t == a.T) {
+          t = 0;
+          ++b;
         }
       }
     }
     float is[8];
-    load8f(invstd + c, is);
+    load8f(a.invstd + c, is);
 #pragma unroll
     for (int i = 0; i < 8; ++i) sx[i] *= is[i];
   }
+  float* pa = s_a + (threadIdx.y * bx + threadIdx.x) * 8;
+  float* pb = s_b + (threadIdx.y * bx + threadIdx.x) * 8;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    s_a[threadIdx.y][threadIdx.x * 8 + i] = sg[i];
-    s_b[threadIdx.y][threadIdx.x * 8 + i] = sx[i];
+    pa[i] = sg[i];
+    pb[i] = sx[i];
   }
   __syncthreads();
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const int cc = blockIdx.x * 256 + tid;
-  if (cc < a.C) {
-    float u = 0.f, v = 0.f;
+  if (threadIdx.y == 0 && c < a.C) {                 // fold the row lanes in a fixed order, then ONE atomic per channel and CTA
 #pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      u += s_a[y][tid];
-      v += s_b[y][tid];
+    for (int i = 0; i < 8; ++i) {
+      float u = 0.f, v = 0.f;
+      for (int y = 0; y < ny; ++y) {
+        u += s_a[(y * bx + threadIdx.x) * 8 + i];
+        v += s_b[(y * bx + threadIdx.x) * 8 + i];
+      }
+      atomicAdd(a.red + c + i, u);
+      atomicAdd(a.red + a.C + c + i, v);
     }
-    atomicAdd(red + cc, u);
-    atomicAdd(red + a.C + cc, v);
   }
 }
 
 // dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) = A*g + Bz*z + Cc with per-channel A, Bz, Cc.
-// dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the
-// zero padding between utterances)
+// dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the zero
+// padding between utterances).  Row ranges are taken in the REVERSE order of the reduce pass (last range first, each range from its
+// end) so that the second read of (dy, z) starts with what the first pass touched last and is still in the 126 MB L2.
 template <int ACT, bool DROP, bool HAS_RES>
-__global__ void __launch_bounds__(256, 2)
-bn_act_bwd_apply_kernel(BnActArgs a, const __nv_bfloat16* __restrict__ dyp, const float* __restrict__ mean,
-                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ red,
-                        __nv_bfloat16* __restrict__ dz, int dz_rows, __nv_bfloat16* __restrict__ g_out, int rows_per_block) {
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+__global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_kernel(BnBwdArgs a) {
+  constexpr int kRows = HAS_RES ? 2 : kRowGroup;
+  zero_small(a.zero_ptr, a.zero_count);
+  const int ny = blockDim.y;
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = cv * 8;
   if (c >= a.C) return;
-  W2L_LOAD_AFFINE(a, c)
+  const int rb = gridDim.y - 1 - blockIdx.y;
+  float sc[8], sh[8], rsc[8], rsh[8];
+  load8f(a.scale + c, sc);
+  load8f(a.shift + c, sh);
+  if (HAS_RES) {
+    load8f(a.res_scale + c, rsc);
+    load8f(a.res_shift + c, rsh);
+  }
+  scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
   float kA[8], kB[8], kC[8];
   {
     float mu[8], is[8], sg[8], sx[8], ga[8];
-    load8f(mean + c, mu);
-    load8f(invstd + c, is);
-    load8f(red + c, sg);
-    load8f(red + a.C + c, sx);
-    if (gamma) load8f(gamma + c, ga);
+    load8f(a.mean + c, mu);
+    load8f(a.invstd + c, is);
+    load8f(a.red + c, sg);
+    load8f(a.red + a.C + c, sx);
+    if (a.gamma) load8f(a.gamma + c, ga);
+    if (a.red_out && rb == 0 && threadIdx.y == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a.red_out[c + i] = sg[i];
+        a.red_out[a.C + c + i] = sx[i];
+      }
+    }
     const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float coef = (gamma ? ga[i] : 1.f) * is[i];
+      const float coef = (a.gamma ? ga[i] : 1.f) * is[i];
       kA[i] = coef;
       kB[i] = -coef * sx[i] * inv_m * is[i];
       kC[i] = -coef * sg[i] * inv_m - kB[i] * mu[i];
     }
   }
   const int rows = a.B * a.T;
-  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  for (int r0 = r_begin + threadIdx.y; r0 < r_end; r0 += 8 * kRowsPerIter) {
-    RowIn in[kRowsPerIter];
+  const int r_begin = rb * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);
+  const int groups = (r_end - r_begin + kRows - 1) / kRows;
+  for (int gi = groups - 1 - (int)threadIdx.y; gi >= 0; gi -= ny) {
+    const int r0 = r_begin + gi * kRows;
+    BwdRow in[kRows];
+    const int b0 = r0 / a.T, t0 = r0 - b0 * a.T;
+    {
+      int b = b0, t = t0;
 #pragma unroll
-    for (int u = 0; u < kRowsPerIter; ++u) load_bwd_row<HAS_RES>(a, dyp, r0 + 8 * u, r_end, c, in[u]);
+      for (int u = 0; u < kRows; ++u) {
+        if (r0 + u < r_end) load_bwd_row<DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
+        if (++t == a.T) {
+          t = 0;
+          ++b;
+        }
+      }
+    }
+    int b = b0, t = t0;
 #pragma unroll
-    for (int u = 0; u < kRowsPerIter; ++u) {
-      if (!in[u].live) continue;
-      float pre[8], mult[8], zv[8], g[8], o[8];
-      pre_from_row<HAS_RES, DROP, false>(a, sc, sh, rsc, rsh, in[u], r0 + 8 * u, c, pre, mult, zv);
-      g_from_row<ACT, DROP>(a, dyp, c, in[u], pre, mult, g);
+    for (int u = 0; u < kRows; ++u) {
+      if (r0 + u < r_end) {
+        float g[8], zv[8], o[8];
+        g_from_row<ACT, DROP, HAS_RES>(a, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
-      *reinterpret_cast<uint4*>(dz + ((int64_t)in[u].b * dz_rows + in[u].t) * a.C + c) = pack8(o);
-      if (g_out) *reinterpret_cast<uint4*>(g_out + (int64_t)(r0 + 8 * u) * a.C + c) = pack8(g);
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
+        *reinterpret_cast<uint4*>(a.dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = pack8(o);
+        if (a.g_out) *reinterpret_cast<uint4*>(a.g_out + (int64_t)(r0 + u) * a.C + c) = pack8(g);
+      }
+      if (++t == a.T) {
+        t = 0;
+        ++b;
+      }
     }
   }
-  const int tail = dz_rows - a.T;
+  const int tail = a.dz_rows - a.T;
   if (tail > 0) {
     const int trows = a.B * tail;
     const int per = (trows + gridDim.y - 1) / gridDim.y;
     const int q_begin = blockIdx.y * per, q_end = min(trows, q_begin + per);
-    for (int q = q_begin + threadIdx.y; q < q_end; q += 8) {
+    for (int q = q_begin + threadIdx.y; q < q_end; q += ny) {
       const int b = q / tail, t = a.T + (q - b * tail);
-      *reinterpret_cast<uint4*>(dz + ((int64_t)b * dz_rows + t) * a.C + c) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(a.dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -644,58 +810,81 @@ static inline int grid_for(int64_t items, int threads) {
   return (int)blocks;
 }
 
-static BnActArgs make_args(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
-                           const float* res_shift, int B, int T, int C, int pl, int pr, int act, float drop_p, uint64_t seed,
-                           const int32_t* lens, void* drop_mask) {
-  BnActArgs a;
-  a.z = (const __nv_bfloat16*)z;
-  a.res = (const __nv_bfloat16*)res;
-  a.scale = scale;
-  a.shift = shift;
-  a.res_scale = res_scale;
-  a.res_shift = res_shift;
-  a.B = B;
-  a.T = T;
-  a.C = C;
-  a.pl = pl;
-  a.pr = pr;
-  a.act = act;
-  a.drop_p = drop_p;
-  a.seed = seed;
-  a.lens = lens;
-  a.drop_mask = (uint8_t*)drop_mask;
-  return a;
+// launch geometry of the three BatchNorm / activation passes (see the comment above their kernels)
+struct BnGeo {
+  dim3 grid, block;
+  int rows_per_block;
+};
+static BnGeo bn_geo(int64_t rows, int C, int ctas_per_sm) {
+  BnGeo g;
+  const int cvecs = C / 8;
+  const int bx = cvecs < kBnThreads ? cvecs : kBnThreads;
+  const int ny = kBnThreads / bx;
+  const int col_blocks = (cvecs + bx - 1) / bx;
+  int64_t target = (int64_t)num_sms() * ctas_per_sm / col_blocks;
+  if (target < 1) target = 1;
+  const int64_t quantum = (int64_t)ny * kRowGroup;                // whole row groups per row lane
+  int64_t rpb = (rows + target - 1) / target;
+  rpb = (rpb + quantum - 1) / quantum * quantum;
+  g.rows_per_block = (int)rpb;
+  g.grid = dim3((unsigned)col_blocks, (unsigned)((rows + rpb - 1) / rpb));
+  g.block = dim3((unsigned)bx, (unsigned)ny);
+  return g;
 }
 
-// compile-time (activation, dropout, residual) variants of the three kernels above
-#define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                         \
-  do {                                                                                                          \
-    const int key_ = (act) * 4 + ((drop) ? 2 : 0) + ((has_res) ? 1 : 0);                                        \
-    switch (key_) {                                                                                             \
-      case 0: KERNEL<W2L_ACT_NONE, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 1: KERNEL<W2L_ACT_NONE, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 2: KERNEL<W2L_ACT_NONE, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 3: KERNEL<W2L_ACT_NONE, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                     \
-      case 4: KERNEL<W2L_ACT_RELU, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 5: KERNEL<W2L_ACT_RELU, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 6: KERNEL<W2L_ACT_RELU, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 7: KERNEL<W2L_ACT_RELU, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                     \
-      case 8: KERNEL<W2L_ACT_CLAMP20, false, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                \
-      case 9: KERNEL<W2L_ACT_CLAMP20, false, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                 \
-      case 10: KERNEL<W2L_ACT_CLAMP20, true, false><<<grid, block, 0, st>>>(__VA_ARGS__); break;                \
-      default: KERNEL<W2L_ACT_CLAMP20, true, true><<<grid, block, 0, st>>>(__VA_ARGS__); break;                 \
-    }                                                                                                           \
+// compile-time (activation, dropout, residual) variants of the kernels above
+#define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                                \
+  do {                                                                                                                 \
+    const int key_ = (act) * 4 + ((drop) ? 2 : 0) + ((has_res) ? 1 : 0);                                               \
+    switch (key_) {                                                                                                    \
+      case 0: KERNEL<W2L_ACT_NONE, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                  \
+      case 1: KERNEL<W2L_ACT_NONE, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 2: KERNEL<W2L_ACT_NONE, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 3: KERNEL<W2L_ACT_NONE, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 4: KERNEL<W2L_ACT_RELU, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                  \
+      case 5: KERNEL<W2L_ACT_RELU, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 6: KERNEL<W2L_ACT_RELU, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
+      case 7: KERNEL<W2L_ACT_RELU, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                    \
+      case 8: KERNEL<W2L_ACT_CLAMP20, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      case 9: KERNEL<W2L_ACT_CLAMP20, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
+      case 10: KERNEL<W2L_ACT_CLAMP20, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      default: KERNEL<W2L_ACT_CLAMP20, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
+    }                                                                                                                  \
   } while (0)
 
-static int check_bn_args(const char* who, const void* z, const float* scale, const float* shift, const void* res,
-                         const float* res_scale, const float* res_shift, int B, int T, int C, int pl, int pr, float drop_p) {
-  W2L_REQUIRE(z && scale && shift, "%s: null pointer", who);
+// dropout probability -> (keep_q, inv_keep) of the kernels' 12-bit keep probability; every pass of a layer derives them the same way
+static void drop_quant(float drop_p, uint32_t* keep_q, float* inv_keep) {
+  if (!(drop_p > 0.f)) {
+    *keep_q = 0;
+    *inv_keep = 1.f;
+    return;
+  }
+  const uint32_t one = 1u << kDropBits;
+  uint32_t q = (uint32_t)((1.0 - (double)drop_p) * (double)one + 0.5);
+  if (q < 1) q = 1;
+  if (q > one - 1) q = one - 1;
+  *keep_q = q;
+  *inv_keep = (float)((double)one / (double)q);
+}
+
+static int check_bn_args(const char* who, const void* z, const void* res, const float* res_scale, const float* res_shift, int B, int T,
+                         int C, int pl, int pr, int act, float drop_p) {
+  W2L_REQUIRE(z != nullptr, "%s: null pointer", who);
   W2L_REQUIRE(!res || (res_scale && res_shift), "%s: residual needs res_scale/res_shift", who);
   W2L_REQUIRE(B >= 1 && T >= 1 && C >= 8 && C % 8 == 0, "%s: bad shape B=%d T=%d C=%d (C must be a multiple of 8)", who, B, T, C);
   W2L_REQUIRE(pl >= 0 && pr >= 0 && pl < T && pr < T, "%s: reflect halo (%d,%d) must be smaller than T=%d", who, pl, pr, T);
   W2L_REQUIRE((int64_t)B * (T + pl + pr) < (1ll << 31) / 8, "%s: B*T too large", who);
   W2L_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p=%f out of [0,1)", who, drop_p);
+  W2L_REQUIRE(act >= 0 && act <= 2, "%s: unknown activation %d", who, act);
   return W2L_OK;
+}
+
+static int launch_bn_fwd(BnFwdArgs& a, int act, const void* res, void* stream) {
+  const BnGeo geo = bn_geo((int64_t)a.B * a.T, a.C, kBnFwdCtasPerSm);
+  a.rows_per_block = geo.rows_per_block;
+  cudaStream_t st = (cudaStream_t)stream;
+  W2L_BN_DISPATCH(bn_act_pad_kernel, act, a.keep_q != 0, res != nullptr, a);
+  return after_launch("bn_act_pad_kernel");
 }
 
 static int rows_per_block_for(int64_t rows, int col_blocks) {
@@ -802,37 +991,105 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right,
                    int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask, void* stream) {
   using namespace w2l;
-  int rc = check_bn_args("bn_act_pad", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  int rc = check_bn_args("bn_act_pad", z, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p);
   if (rc) return rc;
-  W2L_REQUIRE(y != nullptr, "bn_act_pad: null output");
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
-  const int64_t rows = (int64_t)B * T;
-  const int col_blocks = (C + 255) / 256;
-  const int rpb = rows_per_block_for(rows, col_blocks);
-  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_pad: unknown activation %d", act);
-  cudaStream_t st = (cudaStream_t)stream;
-  W2L_BN_DISPATCH(bn_act_pad_kernel, act, drop_p > 0.f, res != nullptr, a, (__nv_bfloat16*)y, rpb);
-  return after_launch("bn_act_pad_kernel");
+  W2L_REQUIRE(y && scale && shift, "bn_act_pad: null pointer");
+  BnFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = (const __nv_bfloat16*)z;
+  a.res = (const __nv_bfloat16*)res;
+  a.scale = scale;
+  a.shift = shift;
+  a.res_scale = res_scale;
+  a.res_shift = res_shift;
+  a.y = (__nv_bfloat16*)y;
+  a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
+  drop_quant(drop_p, &a.keep_q, &a.inv_keep);
+  a.seed = seed;
+  a.lens = lens;
+  a.drop_mask = (uint8_t*)drop_mask;
+  return launch_bn_fwd(a, act, res, stream);
+}
+
+int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows, const float* gamma, const float* beta,
+                            const float* conv_bias, float eps, float momentum, float* running_mean, float* running_var,
+                            int64_t* num_batches_tracked, float* fin, const void* res, const float* res_scale, const float* res_shift,
+                            void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
+                            uint64_t seed, const int32_t* lens, void* drop_mask, float* zero_ptr, int32_t zero_count, void* stream) {
+  using namespace w2l;
+  int rc = check_bn_args("bn_finalize_act_pad", z, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p);
+  if (rc) return rc;
+  W2L_REQUIRE(y && stats && fin && stat_rows >= 1, "bn_finalize_act_pad: null pointer / no rows");
+  W2L_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize_act_pad: running stats must be given together");
+  W2L_REQUIRE(zero_count >= 0 && (zero_ptr != nullptr || zero_count == 0), "bn_finalize_act_pad: bad zero buffer");
+  BnFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.z = (const __nv_bfloat16*)z;
+  a.res = (const __nv_bfloat16*)res;
+  a.res_scale = res_scale;
+  a.res_shift = res_shift;
+  a.stats = stats;
+  a.stat_rows = stat_rows;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.conv_bias = conv_bias;
+  a.eps = eps;
+  a.momentum = momentum;
+  a.running_mean = running_mean;
+  a.running_var = running_var;
+  a.num_batches_tracked = num_batches_tracked;
+  a.fin = fin;
+  a.y = (__nv_bfloat16*)y;
+  a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
+  drop_quant(drop_p, &a.keep_q, &a.inv_keep);
+  a.seed = seed;
+  a.lens = lens;
+  a.drop_mask = (uint8_t*)drop_mask;
+  a.zero_ptr = zero_ptr;
+  a.zero_count = zero_count;
+  return launch_bn_fwd(a, act, res, stream);
+}
+
+static int fill_bwd_args(w2l::BnBwdArgs& a, const char* who, const void* dyp, const void* z, const void* res, const float* scale,
+                         const float* shift, const float* res_scale, const float* res_shift, const float* mean, const float* invstd,
+                         float* red, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
+                         uint64_t seed, const int32_t* lens, const void* drop_mask) {
+  using namespace w2l;
+  int rc = check_bn_args(who, z, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p);
+  if (rc) return rc;
+  W2L_REQUIRE(dyp && scale && shift && mean && invstd && red, "%s: null pointer", who);
+  memset(&a, 0, sizeof(a));
+  a.z = (const __nv_bfloat16*)z;
+  a.res = (const __nv_bfloat16*)res;
+  a.dyp = (const __nv_bfloat16*)dyp;
+  a.scale = scale;
+  a.shift = shift;
+  a.res_scale = res_scale;
+  a.res_shift = res_shift;
+  a.mean = mean;
+  a.invstd = invstd;
+  a.red = red;
+  a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
+  drop_quant(drop_p, &a.keep_q, &a.inv_keep);
+  a.seed = seed;
+  a.lens = lens;
+  a.drop_mask = (const uint8_t*)drop_mask;
+  return W2L_OK;
 }
 
 int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const float* scale, const float* shift,
                           const float* res_scale, const float* res_shift, const float* mean, const float* invstd, float* red,
                           int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, int32_t act, float drop_p,
-                          uint64_t seed, const int32_t* lens, const void* drop_mask_in, void* stream) {
+                          uint64_t seed, const int32_t* lens, const void* drop_mask, void* stream) {
   using namespace w2l;
-  void* drop_mask = const_cast<void*>(drop_mask_in);
-  int rc = check_bn_args("bn_act_bwd_reduce", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  BnBwdArgs a;
+  int rc = fill_bwd_args(a, "bn_act_bwd_reduce", dyp, z, res, scale, shift, res_scale, res_shift, mean, invstd, red, B, T, C, pad_left,
+                         pad_right, act, drop_p, seed, lens, drop_mask);
   if (rc) return rc;
-  W2L_REQUIRE(dyp && mean && invstd && red, "bn_act_bwd_reduce: null pointer");
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
-  const int64_t rows = (int64_t)B * T;
-  const int col_blocks = (C + 255) / 256;
-  const int rpb = rows_per_block_for(rows, col_blocks);
-  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_bwd_reduce: unknown activation %d", act);
+  const BnGeo geo = bn_geo((int64_t)B * T, C, kBnBwdCtasPerSm);
+  a.rows_per_block = geo.rows_per_block;
   cudaStream_t st = (cudaStream_t)stream;
-  W2L_BN_DISPATCH(bn_act_bwd_reduce_kernel, act, drop_p > 0.f, res != nullptr, a, (const __nv_bfloat16*)dyp, mean, invstd, red, rpb);
+  W2L_BN_DISPATCH(bn_act_bwd_reduce_kernel, act, a.keep_q != 0, res != nullptr, a);
   return after_launch("bn_act_bwd_reduce_kernel");
 }
 
@@ -840,22 +1097,26 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
                          const float* res_scale, const float* res_shift, const float* mean, const float* invstd, const float* gamma,
                          const float* red, void* dz, int32_t dz_rows, void* g_out, int32_t B, int32_t T, int32_t C,
                          int32_t pad_left, int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens,
-                         const void* drop_mask_in, void* stream) {
+                         const void* drop_mask, float* red_out, float* zero_ptr, int32_t zero_count, void* stream) {
   using namespace w2l;
-  void* drop_mask = const_cast<void*>(drop_mask_in);
-  int rc = check_bn_args("bn_act_bwd_apply", z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, drop_p);
+  BnBwdArgs a;
+  int rc = fill_bwd_args(a, "bn_act_bwd_apply", dyp, z, res, scale, shift, res_scale, res_shift, mean, invstd, const_cast<float*>(red), B, T,
+                         C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
   if (rc) return rc;
-  W2L_REQUIRE(dyp && mean && invstd && red && dz, "bn_act_bwd_apply: null pointer");
-  W2L_REQUIRE(dz_rows >= T, "bn_act_bwd_apply: dz_rows %d < T %d", dz_rows, T);
-  BnActArgs a = make_args(z, scale, shift, res, res_scale, res_shift, B, T, C, pad_left, pad_right, act, drop_p, seed, lens, drop_mask);
-  const int64_t rows = (int64_t)B * T;
-  const int col_blocks = (C + 255) / 256;
-  const int rpb = rows_per_block_for(rows, col_blocks);
-  dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  W2L_REQUIRE(act >= 0 && act <= 2, "bn_act_bwd_apply: unknown activation %d", act);
+  W2L_REQUIRE(dz != nullptr && dz_rows >= T, "bn_act_bwd_apply: null dz or dz_rows %d < T %d", dz_rows, T);
+  W2L_REQUIRE(zero_count >= 0 && (zero_ptr != nullptr || zero_count == 0), "bn_act_bwd_apply: bad zero buffer");
+  W2L_REQUIRE(zero_ptr == nullptr || zero_ptr != red, "bn_act_bwd_apply: the buffer to clear must not be the reduction this pass reads");
+  a.gamma = gamma;
+  a.dz = (__nv_bfloat16*)dz;
+  a.dz_rows = dz_rows;
+  a.g_out = (__nv_bfloat16*)g_out;
+  a.red_out = red_out;
+  a.zero_ptr = zero_ptr;
+  a.zero_count = zero_count;
+  const BnGeo geo = bn_geo((int64_t)B * T, C, kBnBwdCtasPerSm);
+  a.rows_per_block = geo.rows_per_block;
   cudaStream_t st = (cudaStream_t)stream;
-  W2L_BN_DISPATCH(bn_act_bwd_apply_kernel, act, drop_p > 0.f, res != nullptr, a, (const __nv_bfloat16*)dyp, mean, invstd, gamma, red,
-                  (__nv_bfloat16*)dz, dz_rows, (__nv_bfloat16*)g_out, rpb);
+  W2L_BN_DISPATCH(bn_act_bwd_apply_kernel, act, a.keep_q != 0, res != nullptr, a);
   return after_launch("bn_act_bwd_apply_kernel");
 }
 

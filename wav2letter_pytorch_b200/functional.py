@@ -305,12 +305,37 @@ def reflect_halo(y, T, pad_left, pad_right):
     return y
 
 
+def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked, B, T, C,
+                        pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None, res=None, res_scale=None, res_shift=None, drop_mask=None,
+                        zero_after=None):
+    """The training-mode pass: ``bn_finalize`` folded into ``bn_act_pad`` (one launch instead of two).  ``stats`` [2C] = the batch
+    sums the conv epilogue left.  Returns (y bf16 [B, pl+T+pr, C], fin fp32 [4, C] = scale, shift, mean, invstd).  ``zero_after``
+    (fp32 tensor, optional) is cleared by the same launch for a later kernel."""
+    dev = z.device
+    out = torch.empty((B, pad_left + T + pad_right, C), dtype=torch.bfloat16, device=dev)
+    fin = torch.empty((4, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().w2l_bn_finalize_act_pad(
+            _ptr(z), _ptr(stats), B * T, _ptr(gamma), _ptr(beta), _ptr(conv_bias), float(eps), float(momentum), _ptr(running_mean),
+            _ptr(running_var), _ptr(num_batches_tracked), _ptr(fin), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out), B, T, C,
+            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask), _ptr(zero_after),
+            0 if zero_after is None else zero_after.numel(), _stream()), "bn_finalize_act_pad")
+    return out, fin
+
+
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None):
-    """Returns (dz bf16 [B, dz_rows, C] (rows >= T zero), red fp32 [2C] = (dbeta, dgamma), g bf16 [B,T,C] | None)."""
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None):
+    """Returns (dz bf16 [B, dz_rows, C] (rows >= T zero), red fp32 [2C] = (dbeta, dgamma), g bf16 [B,T,C] | None).
+    ``red_ws`` (fp32 [2C], ZERO on entry, dirty afterwards): a persistent accumulation buffer -- the sums are then returned in a
+    fresh tensor and no memset launch is needed; without it a zero-filled buffer is allocated per call.  ``zero_after`` (fp32
+    tensor, optional) is cleared by the second pass for a later kernel."""
     dev = z.device
     dz_rows = T if dz_rows is None else dz_rows
-    red = torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+    if red_ws is None:
+        red = torch.zeros((2 * C,), dtype=torch.float32, device=dev)
+        red_out = None
+    else:
+        red, red_out = red_ws, torch.empty((2 * C,), dtype=torch.float32, device=dev)
     dz = torch.empty((B, dz_rows, C), dtype=torch.bfloat16, device=dev)
     g = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev) if want_g else None
     lib = _lib.load()
@@ -320,9 +345,10 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
                                              int(seed), _ptr(lens), _ptr(drop_mask), _stream()), "bn_act_bwd_reduce")
         _lib.check(lib.w2l_bn_act_bwd_apply(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
                                             _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), dz_rows, _ptr(g), B, T, C,
-                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask), _stream()),
-                   "bn_act_bwd_apply")
-    return dz, red, g
+                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask),
+                                            _ptr(red_out), _ptr(zero_after), 0 if zero_after is None else zero_after.numel(),
+                                            _stream()), "bn_act_bwd_apply")
+    return dz, (red if red_out is None else red_out), g
 
 
 def log_softmax(logits, C, mode=0, nan_flag=None):

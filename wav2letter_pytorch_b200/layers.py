@@ -299,11 +299,20 @@ class BatchNormParams(nn.Module):
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
 
     def eval_scale_shift(self, conv_bias=None):
+        """inference fold: y = z*scale + shift; computed once per parameter / buffer version (five small launches otherwise, per
+        layer and forward call: the eval-mode forward of config 1 was host-bound on them)"""
+        ts = (self.weight, self.bias, self.running_mean, self.running_var) + ((conv_bias,) if conv_bias is not None else ())
+        key = tuple((t._version, t.data_ptr()) for t in ts)
+        hit = self.__dict__.get("_w2l_eval_fold")
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
         scale = self.weight.detach() * torch.rsqrt(self.running_var + self.eps)
         shift = self.bias.detach() - self.running_mean * scale
         if conv_bias is not None:
             shift = shift + conv_bias.detach() * scale
-        return scale.contiguous(), shift.contiguous()
+        scale, shift = scale.contiguous(), shift.contiguous()
+        self.__dict__["_w2l_eval_fold"] = (key, scale, shift)
+        return scale, shift
 
     def extra_repr(self):
         return "%d, eps=%g, momentum=%g" % (self.num_features, self.eps, self.momentum)
@@ -317,14 +326,61 @@ def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0,
 _EPILOGUE_STATS = os.environ.get("W2L_EPILOGUE_STATS", "1") != "0"      # 0: separate bn_stats pass over z (A/B measurements)
 
 
-def conv_fwd_with_stats(xin, conv, desc, z):
-    """conv forward into ``z`` + BatchNorm batch statistics [2*Cout] (sum, sum of squares of the stored bf16 values)."""
+class BnScratch:
+    """Two small persistent fp32 buffers of a BatchNorm layer that kernels accumulate into with atomics -- ``stats`` [2C] (the conv
+    epilogue's batch sums, forward) and ``red`` [2C] (sum g, sum g*xhat, backward) -- each cleared by a kernel of the OTHER pass that
+    runs anyway (the forward BN/activation pass clears ``red``, the backward apply pass clears ``stats``), so a steady-state training
+    step needs no memset launch for them (round 1 launched one ``torch.zeros`` per buffer, layer and step: 60 of the ~125 fill
+    kernels per step).  The flags track which buffer is known to be zero; a pass that finds its buffer dirty (a forward that was never
+    followed by its backward, two backward passes over one graph) clears it explicitly."""
+
+    def __init__(self, C, device):
+        self.stats = torch.zeros((2 * C,), dtype=torch.float32, device=device)
+        self.red = torch.zeros((2 * C,), dtype=torch.float32, device=device)
+        self.stats_clean = self.red_clean = True
+
+    def take_stats(self):
+        if not self.stats_clean:
+            self.stats.zero_()
+        self.stats_clean = False
+        return self.stats
+
+    def take_red(self):
+        if not self.red_clean:
+            self.red.zero_()
+        self.red_clean = False
+        return self.red
+
+
+def bn_scratch(bn, device):
+    sc = bn.__dict__.get("_w2l_scratch")
+    if sc is None or sc.stats.device != device:
+        sc = bn.__dict__["_w2l_scratch"] = BnScratch(bn.num_features, device)
+    return sc
+
+
+def conv_fwd_with_stats(xin, conv, desc, z, stats=None):
+    """conv forward into ``z`` + BatchNorm batch statistics [2*Cout] (sum, sum of squares of the stored bf16 values), accumulated into
+    ``stats`` (zero on entry) when given."""
     if not _EPILOGUE_STATS:
         F.conv1d_fwd(xin, conv.packed(), desc, z)
-        return F.bn_stats(z, conv.out_channels)
-    stats = torch.zeros((2 * conv.out_channels,), dtype=torch.float32, device=xin.device)
+        st = F.bn_stats(z, conv.out_channels)
+        return st if stats is None else stats.copy_(st)
+    if stats is None:
+        stats = torch.zeros((2 * conv.out_channels,), dtype=torch.float32, device=xin.device)
     F.conv1d_fwd(xin, conv.packed(), desc, z, bn_stats=stats)
     return stats
+
+
+def zero_bias_grad(conv, device):
+    """the conv bias gradient under training-mode BatchNorm is exactly zero: one cached zero tensor per layer instead of a fill
+    kernel per layer and step (a fresh one whenever a gradient is already being accumulated into)"""
+    if conv.bias.grad is not None:
+        return torch.zeros(conv.out_channels, dtype=torch.float32, device=device)
+    z = conv.__dict__.get("_w2l_zero_dbias")
+    if z is None or z.device != device:
+        z = conv.__dict__["_w2l_zero_dbias"] = torch.zeros(conv.out_channels, dtype=torch.float32, device=device)
+    return z
 
 
 class ConvBNActFn(torch.autograd.Function):
@@ -347,16 +403,20 @@ class ConvBNActFn(torch.autograd.Function):
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
-        stats = conv_fwd_with_stats(xin, conv, desc, z)        # batch statistics from the epilogue; conv bias folded below
-        fin = F.bn_finalize(stats, B * T_out, Co, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
-                            bn.num_batches_tracked)
+        sc = bn_scratch(bn, xin.device)
+        stats = conv_fwd_with_stats(xin, conv, desc, z, sc.take_stats())      # batch statistics from the GEMM epilogue
         drop_p = geo.get("drop_p", 0.0)
         seed = next_dropout_seed() if drop_p > 0 else 0
         mask = torch.empty((B * T_out * Co // 8,), dtype=torch.uint8, device=xin.device) if drop_p > 0 else None
         has_res = z_res is not None
-        yp = F.bn_act_pad(z, fin[0], fin[1], B, T_out, Co, pl, pr, geo["act"], drop_p, seed, geo.get("lens"),
-                          res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
-                          drop_mask=mask)
+        # ONE launch: statistics -> scale/shift (+ running statistics, conv bias folded into the running mean), BatchNorm apply,
+        # residual, dropout, activation, the consumer's halo / mask; it also clears this layer's backward reduction buffer
+        yp, fin = F.bn_finalize_act_pad(z, stats, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                                        bn.num_batches_tracked, B, T_out, Co, pl, pr, geo["act"], drop_p, seed, geo.get("lens"),
+                                        res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
+                                        drop_mask=mask, zero_after=sc.red)
+        sc.red_clean = True
+        ctx.bn = bn
         ctx.conv, ctx.geo, ctx.seed, ctx.desc, ctx.has_res = conv, geo, seed, desc, has_res
         ctx.has_bias = bias is not None
         ctx.save_for_backward(xin, z, fin, gamma, z_res, fin_res, mask)
@@ -374,10 +434,12 @@ class ConvBNActFn(torch.autograd.Function):
         # zero tails, so that backward-data runs over one flat [B*x_rows] row space (no per-utterance tile padding).
         flat = ctx.needs_input_grad[0] and geo["x_row_offset"] == 0 and x_rows == T_out + halo
         dz_rows = x_rows if flat else T_out
+        sc = bn_scratch(ctx.bn, z.device)
         dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
-                                  want_g=has_res, dz_rows=dz_rows, drop_mask=mask)
+                                  want_g=has_res, dz_rows=dz_rows, drop_mask=mask, red_ws=sc.take_red(), zero_after=sc.stats)
+        sc.stats_clean = True                            # the apply pass cleared the forward statistics for the next step
         dw = alloc_dw(conv, z.device)
         side = WgradStream.fork(z.device, conv.weight)   # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
@@ -388,7 +450,7 @@ class ConvBNActFn(torch.autograd.Function):
             else:
                 F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx)
         wgrad_async(side, dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
-        dbias = torch.zeros(Co, dtype=torch.float32, device=z.device) if ctx.has_bias else None   # exactly 0 under train BN
+        dbias = zero_bias_grad(conv, z.device) if ctx.has_bias else None                          # exactly 0 under train BN
         return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
 
 
