@@ -32,7 +32,7 @@ def builds():
     out.append(KE.build(["elementwise.cu"], [], c_abi=True, post=_POST, drop=E.ELEMENTWISE_DROP, extra=E.ELEMENTWISE_PTX))
     out.append(KE.build(["ctc.cu"], [], c_abi=True, post=_POST, drop=_CTC_DROP, extra=E.CTC_PTX))
     out.append(KE.build(["conv_gemm.cu"], [], helpers_from_common=("pack_bf16x2", "make_smem_desc", "make_idesc_bf16"), subs=E.GEMM_SUBS,
-                        c_abi=True, post=_POST, opt="-O2"))
+                        drop=E.GEMM_DROP, c_abi=True, post=_POST, opt="-O2"))
     return out
 
 

@@ -199,8 +199,26 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("B,T,Cin,Cout,k,d,pad", CONV_CASES)
-def test_conv_fwd_dgrad_wgrad(F, B, T, Cin, Cout, k, d, pad):
+# the FWD-kind GEMMs (forward, backward-data over the transposed weight shadow) run as CTA pairs (tcgen05 cta_group::2) by default and
+# as the single-CTA kernel under W2L_CG2=0 (read per call): every case under both
+CG2_CASES = CONV_CASES + [
+    (3, 300, 128, 512, 3, 1, (1, 1)),          # 3 M tiles x 3 utterances: pairs along M, the last pair half empty
+    (4, 300, 128, 160, 3, 1, (1, 1)),          # 3 M tiles x 4 utterances: pairs along the batch
+    (1, 100, 64, 29, 1, 1, (0, 0)),            # a single M tile: the peer CTA of the only pair has no rows
+    (2, 520, 256, 1024, 1, 1, (0, 0)),         # 4 N tiles in groups of 4 (small weights)
+]
+
+
+@pytest.fixture(params=["pair", "single"])
+def gemm_kernel(request, monkeypatch):
+    if request.param == "pair" and request.config.getoption("--emulate-gpu"):
+        pytest.skip("the CTA-pair kernel (cluster of 2, cta_group::2) is outside the emulated surface")
+    monkeypatch.setenv("W2L_CG2", "1" if request.param == "pair" else "0")
+    return request.param
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,k,d,pad", CG2_CASES)
+def test_conv_fwd_dgrad_wgrad(F, gemm_kernel, B, T, Cin, Cout, k, d, pad):
     g = torch.Generator().manual_seed(B * T + Cin + k)
     pl, pr = pad
     x = _bf(torch.randn(B, T, Cin, generator=g))                 # time-major, UNpadded: zero padding via TMA OOB fill
@@ -262,7 +280,7 @@ def test_conv_fwd_dgrad_wgrad(F, B, T, Cin, Cout, k, d, pad):
 
 
 @pytest.mark.parametrize("B,T,C,Co,k,d", [(3, 200, 64, 128, 5, 1), (5, 131, 128, 64, 7, 2), (2, 750, 256, 256, 11, 1)])
-def test_conv_dgrad_flat_prepadded(F, B, T, C, Co, k, d):
+def test_conv_dgrad_flat_prepadded(F, gemm_kernel, B, T, C, Co, k, d):
     """Wav2Letter layout: the input carries its own halo (x_rows = T + (k-1)d), dz is stored with the input's row pitch and zero
     tails, and backward-data runs over ONE flat [B*x_rows] row space; wgrad reads the same pitched dz."""
     g = torch.Generator().manual_seed(B + T + k)
@@ -286,7 +304,7 @@ def test_conv_dgrad_flat_prepadded(F, B, T, C, Co, k, d):
     assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
 
 
-def test_conv_full_size_layer(F):
+def test_conv_full_size_layer(F, gemm_kernel):
     """one config-2-sized layer (B=64, T'=750, 896->896, k=29, d=2): linearity + spot-check vs torch fp32 on a slice."""
     g = torch.Generator().manual_seed(3)
     B, T, C, k, d = 64, 750, 896, 29, 2

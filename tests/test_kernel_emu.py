@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+import _emu_backend as E
 import _kernel_emu as KE
 from oracle import w2l_oracle as O
 
@@ -19,7 +20,7 @@ class _Both:
     """the two builds behind one launch(): elementwise.cu and depthwise.cu are separate translation units in the library too"""
 
     def __init__(self):
-        self.parts = [KE.build(["elementwise.cu"], ["im2col_tm_kernel", "col2im_tm_kernel"]),
+        self.parts = [KE.build(["elementwise.cu"], ["im2col_tm_kernel", "col2im_tm_kernel"], drop=E.ELEMENTWISE_DROP, extra=E.ELEMENTWISE_PTX),
                       KE.build(["depthwise.cu"], ["depthwise_corr_kernel", "depthwise_dgrad_strided_kernel", "depthwise_wgrad_kernel"])]
 
     def launch(self, kernel, *a, **k):

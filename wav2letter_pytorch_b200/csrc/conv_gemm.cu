@@ -82,6 +82,11 @@ struct GemmParams {
   int32_t slab_bytes;       // one slab buffer (slab_rows * 128 rounded up to the 1024-byte swizzle atom); three of them
   int32_t b_stages;         // weight-tile ring depth in slab mode (4, or 3 when the slabs are large)
   int32_t ring_bytes;       // operand rings occupy [0, ring_bytes) of the (1024-aligned) dynamic shared memory; barriers follow
+  // CTA-pair kernel (conv_gemm_cg2_kernel): a pair computes 256 x BN -- two M tiles of one utterance (c2_pair_b == 0) or the same
+  // M tile of two consecutive utterances (c2_pair_b == 1) -- and each CTA fetches HALF of every weight tile
+  int32_t c2_pair_b;
+  int32_t c2_mu, c2_bu;     // units along M / along the batch a pair index decodes into
+  int32_t c2_ngroup;        // N tiles that run side by side on the same activation rows (their weight slices stay in L2 together)
 };
 
 // A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
@@ -189,6 +194,70 @@ __device__ __forceinline__ float warp_column_sum32(float (&x)[32], int lane) {
     }
   }
   return x[0];
+}
+
+// fwd/dgrad epilogue of one 32-column chunk of a thread's accumulator row: affine (bias / BatchNorm fold) -> activation -> BatchNorm
+// batch statistics of what is stored -> bf16 / fp32 store.  `aff` = this chunk's (scale, shift) pairs in shared memory.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int c0, int nbase, const float2* aff, bool has_aff,
+                                               bool has_act, float act_hi, bool row_ok, int b, int m, int lane) {
+  if (has_aff) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float2 a = aff[i];
+      v[i] = fmaf(v[i], a.x, a.y);
+    }
+  }
+  if (has_act) {   // NaN passes through, as torch.clamp / relu do
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (v[i] != v[i]) ? v[i] : fminf(fmaxf(v[i], 0.f), act_hi);
+  }
+  if (MODE == MODE_FWD && p.bn_stats != nullptr) {   // BatchNorm batch statistics of what is stored (kernel-uniform branch)
+    float s1[32], s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float q = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+      s1[i] = q;
+      s2[i] = q * q;
+    }
+    const float c1 = warp_column_sum32(s1, lane), c2 = warp_column_sum32(s2, lane);
+    if (c0 + lane < p.BN && nbase + lane < p.N_valid) {
+      atomicAdd(p.bn_stats + nbase + lane, c1);
+      atomicAdd(p.bn_stats + p.N_valid + nbase + lane, c2);
+    }
+  }
+  if (row_ok && !(p.dbg & 2)) {
+    const int64_t off = (int64_t)b * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
+    const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
+    if (p.y_dtype == W2L_DTYPE_BF16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + off;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(v[i], v[i + 1]);
+          q.y = pack_bf16x2(v[i + 2], v[i + 3]);
+          q.z = pack_bf16x2(v[i + 4], v[i + 5]);
+          q.w = pack_bf16x2(v[i + 6], v[i + 7]);
+          *reinterpret_cast<uint4*>(dst + i) = q;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __float2bfloat16_rn(v[i]);
+      }
+    } else {
+      float* dst = reinterpret_cast<float*>(p.y) + off;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = v[i];
+      }
+    }
+  }
 }
 
 template <int MODE>
@@ -434,66 +503,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
       const int m = tc.m0 + row;
       const bool row_ok = m < p.M_valid;
-      // fwd/dgrad: one 32-column chunk of this thread's row, accumulator values in v -> affine / activation / BN statistics / store
       auto finish_chunk = [&](float (&v)[32], int c0, int nbase) {
-          if (has_aff) {
-            const float2* aff = s_aff + acc * 256 + c0;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float2 a = aff[i];
-              v[i] = fmaf(v[i], a.x, a.y);
-            }
-          }
-          if (has_act) {   // NaN passes through, as torch.clamp / relu do
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (v[i] != v[i]) ? v[i] : fminf(fmaxf(v[i], 0.f), act_hi);
-          }
-          if (MODE == MODE_FWD && p.bn_stats != nullptr) {   // BatchNorm batch statistics of what is stored (kernel-uniform branch)
-            float s1[32], s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float q = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
-              s1[i] = q;
-              s2[i] = q * q;
-            }
-            const float c1 = warp_column_sum32(s1, lane), c2 = warp_column_sum32(s2, lane);
-            if (c0 + lane < p.BN && nbase + lane < p.N_valid) {
-              atomicAdd(p.bn_stats + nbase + lane, c1);
-              atomicAdd(p.bn_stats + p.N_valid + nbase + lane, c2);
-            }
-          }
-          if (row_ok && !(p.dbg & 2)) {
-            const int64_t off = (int64_t)tc.b * p.y_batch_stride + (int64_t)(m + p.y_row_off) * p.ldy + nbase;
-            const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
-            if (p.y_dtype == W2L_DTYPE_BF16) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + off;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                  uint4 q;
-                  q.x = pack_bf16x2(v[i], v[i + 1]);
-                  q.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                  q.z = pack_bf16x2(v[i + 4], v[i + 5]);
-                  q.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                  *reinterpret_cast<uint4*>(dst + i) = q;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = __float2bfloat16_rn(v[i]);
-              }
-            } else {
-              float* dst = reinterpret_cast<float*>(p.y) + off;
-              if (full) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (c0 + i < p.BN && nbase + i < p.N_valid) dst[i] = v[i];
-              }
-            }
-          }
+        epilogue_chunk<MODE>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, tc.b, m, lane);
       };
       if (MODE != MODE_WGRAD && tc.partial) {
         // ---- fwd tail split: this CTA computed one K piece of the tile.  Park the fp32 partial in the scratch slot, free the
@@ -598,6 +609,195 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   }
 }
 
+
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2), FWD-kind operands (both K-major)
+// Same roles as conv_gemm_kernel, but the two CTAs of a cluster share every weight tile: each fetches A for its own 128 rows and
+// HALF of the B tile (BN/2 weight rows); the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), which reads both
+// CTAs' shared memory and fills a 128 x BN accumulator in EACH CTA's TMEM.  Per CTA and K-step that is 16 KB + BN*64 B from L2
+// instead of 16 KB + BN*128 B: the single-CTA kernel needs ~17 TB/s of L2->SM traffic at 1.4 PFLOP/s (83 FLOP/B at BN = 224),
+// this one 122 FLOP/B, and the ring holds 6 K-steps instead of 4.
+//   full[s]   (leader)  : 1 arrival (leader's producer, expect_tx of BOTH CTAs' bytes) + the bytes of both CTAs' TMA loads
+//   empty[s]  (each CTA): tcgen05.commit multicast to both CTAs -> each producer re-fills its own stage
+//   tfull[a]  (each CTA): tcgen05.commit multicast -> each CTA's epilogue warps read their own TMEM
+//   tempty[a] (leader)  : 8 arrivals = one per epilogue warp of both CTAs (remote arrive from the peer)
+constexpr int kC2Stages = 6;
+constexpr int kC2BBytes = 128 * kBlockK * 2;            // half of a <= 256-wide weight tile
+constexpr int kC2StageBytes = kABytes + kC2BBytes;      // 32 KB
+constexpr size_t kC2Smem = (size_t)kC2Stages * kC2StageBytes + 1024 + 256 + kAffBytes;
+
+struct PairTile {
+  int m0, n0, b;
+};
+__device__ __forceinline__ void decode_pair(const GemmParams& p, int t, int rank, PairTile& u) {
+  const int ni = t % p.c2_ngroup;
+  t /= p.c2_ngroup;
+  const int mu = t % p.c2_mu;
+  t /= p.c2_mu;
+  const int bu = t % p.c2_bu;
+  const int grp = t / p.c2_bu;
+  u.n0 = (grp * p.c2_ngroup + ni) * p.BN;
+  if (p.c2_pair_b) {
+    u.m0 = mu * kBlockM;
+    u.b = bu * 2 + rank;
+  } else {
+    u.m0 = (mu * 2 + rank) * kBlockM;
+    u.b = bu;
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) conv_gemm_cg2_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);     // same offset in both CTAs (same kernel, same static layout)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kC2Stages * kC2StageBytes);
+  uint64_t* full_bar = bars;                      // [kC2Stages]
+  uint64_t* empty_bar = bars + kC2Stages;         // [kC2Stages]
+  uint64_t* tfull_bar = bars + 2 * kC2Stages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* s_aff = reinterpret_cast<float2*>(smem + kC2Stages * kC2StageBytes + 256);   // [2][256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int iters = p.k * p.kc_steps;
+  const uint32_t half_bn = (uint32_t)p.BN >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < kC2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 2 * kAccCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();                             // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs; bytes land on the LEADER's barrier)
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = 2u * ((uint32_t)kABytes + half_bn * 128u);
+      PairTile u;
+      for (int t = pair; t < p.num_tiles; t += npairs) {
+        decode_pair(p, t, (int)rank, u);
+        for (int it = 0; it < iters; ++it) {
+          const int j = it / p.kc_steps, kc = it - j * p.kc_steps;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * kC2StageBytes;
+          tma_load_3d_cg2(sa, &p.tmA, lead_full, kc * kBlockK, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
+          tma_load_3d_cg2(sa + kABytes, &p.tmB, lead_full, kc * kBlockK, u.n0 + (int)(rank * half_bn), j);
+          if (++stage == kC2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      const uint32_t idesc = make_idesc_bf16(2 * kBlockM, p.BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < p.num_tiles; t += npairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        uint32_t accumulate = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kC2StageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t adesc = make_smem_desc(a_addr + kk * 32u, 16u, 1024u);
+            const uint64_t bdesc = make_smem_desc(b_addr + kk * 32u, 16u, 1024u);
+            umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_cg2(&empty_bar[stage], 3);
+          if (++stage == kC2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5 of both CTAs, each on its own TMEM)
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool has_aff = p.bias != nullptr || p.scale != nullptr;
+    const bool has_act = p.act != W2L_ACT_NONE;
+    const float act_hi = p.act == W2L_ACT_CLAMP20 ? 20.f : INFINITY;
+    const int ep_tid = threadIdx.x - 64;
+    PairTile u;
+    for (int t = pair; t < p.num_tiles; t += npairs) {
+      decode_pair(p, t, (int)rank, u);
+      if (has_aff) {
+        for (int c = ep_tid; c < p.BN; c += 128) {
+          const int n = min(u.n0 + c, p.N_valid - 1);
+          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
+          const float sh = (p.bias ? __ldg(p.bias + n) * sc : 0.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
+          s_aff[acc * 256 + c] = make_float2(sc, sh);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
+      const int m = u.m0 + row;
+      const bool row_ok = m < p.M_valid && u.b < p.B;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        const int nbase = u.n0 + c0;
+        if (nbase >= p.N_valid) break;
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        epilogue_chunk<MODE_FWD>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, u.b, m, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                             // the peer's shared memory and barriers stay alive until every MMA has retired
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 2 * kAccCols);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 // N-tile width: a multiple of `multiple` (16 = UMMA granularity; 64 when operands come through 4-D chunked TMA maps).
 // Narrow tiles run the tensor pipe below peak (the A tile is re-read from shared memory per MMA whatever N is; measured
@@ -692,6 +892,41 @@ static int launch_gemm(const GemmParams& p_in, cudaStream_t st, int grid_overrid
   return after_launch(MODE == MODE_FWD ? "conv_gemm_kernel<fwd>" : MODE == MODE_DGRAD ? "conv_gemm_kernel<dgrad>" : "conv_gemm_kernel<wgrad>");
 }
 
+// CTA-pair kernel: on by default for the FWD-kind GEMMs (forward, backward-data with the transposed weight shadow);
+// W2L_CG2=0 falls back to the single-CTA kernel (the A/B switch of profiles/r2_gemm_cg2.md)
+static bool cg2_wanted() {
+  const char* e = getenv("W2L_CG2");          // read per call: the parity tests run every case under both kernels in one process
+  return !(e && atoi(e) == 0);
+}
+
+// geometry of the pair decomposition for a FWD-kind problem whose p.B / p.m_tiles / p.n_tiles / p.BN / p.k / kc_steps are set
+static void plan_cg2(GemmParams& p, int64_t weight_bytes_per_ntile) {
+  // pair along M when the M tiles pair up (or nothing else does); along the batch when that wastes less
+  const int waste_m = p.m_tiles & 1, waste_b = p.B & 1;
+  p.c2_pair_b = (waste_m && (!waste_b || p.B > p.m_tiles)) ? 1 : 0;
+  p.c2_mu = p.c2_pair_b ? p.m_tiles : (p.m_tiles + 1) / 2;
+  p.c2_bu = p.c2_pair_b ? (p.B + 1) / 2 : p.B;
+  // N tiles of one group run on the same activation rows at the same time (activations cross DRAM once per group instead of once
+  // per N tile) as long as the group's weight slices fit in L2 beside the streams: <= 24 MB
+  int g = 1;
+  while (g * 2 <= p.n_tiles && p.n_tiles % (g * 2) == 0 && (int64_t)(g * 2) * weight_bytes_per_ntile <= (24ll << 20)) g *= 2;
+  p.c2_ngroup = g;
+  p.num_tiles = p.c2_mu * p.c2_bu * p.n_tiles;
+}
+
+static int launch_gemm_cg2(const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA(cudaFuncSetAttribute(conv_gemm_cg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2Smem));
+    configured = true;
+  }
+  const int pairs_max = gemm_sms() / 2;
+  const int pairs = p.num_tiles < pairs_max ? p.num_tiles : pairs_max;
+  if (pairs < 1) return W2L_OK;
+  conv_gemm_cg2_kernel<<<2 * pairs, kGemmThreads, kC2Smem, st>>>(p);
+  return after_launch("conv_gemm_cg2_kernel");
+}
+
 static int check_desc(const w2l_conv_desc* d, const char* who) {
   W2L_REQUIRE(d != nullptr, "%s: null descriptor", who);
   W2L_REQUIRE(d->B >= 1 && d->T_out >= 1 && d->k >= 1 && d->dilation >= 1, "%s: bad B/T_out/k/dilation", who);
@@ -740,7 +975,12 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_fwd: ldy < Cout");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  plan_rings(p, d->k, d->dilation, true);
+  {
+    const char* e = getenv("W2L_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  const bool cg2 = cg2_wanted() && !(p.dbg & 1);
+  if (!cg2) plan_rings(p, d->k, d->dilation, true);
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
@@ -750,13 +990,9 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   }
   p.BN = pick_bn(d->Cout_pad, 16);
   {
-    const char* e = getenv("W2L_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
-  {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
-    uint32_t box[3] = {kBlockK, (p.dbg & 1) ? 64u : (uint32_t)p.BN, 1};
+    uint32_t box[3] = {kBlockK, cg2 ? (uint32_t)p.BN / 2 : (p.dbg & 1) ? 64u : (uint32_t)p.BN, 1};
     rc = make_tensor_map(&p.tmB, w, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
@@ -782,6 +1018,10 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   p.y_row_off = d->y_row_offset;
   p.ldy = d->ldy;
   p.splits = 1;
+  if (cg2) {
+    plan_cg2(p, (int64_t)d->k * p.BN * d->Cin * 2);
+    return launch_gemm_cg2(p, (cudaStream_t)stream);
+  }
   plan_tail_split(p);
   return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
 }
@@ -868,7 +1108,8 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_dgrad_wt: dy row pitch %d < Cout %d", d->ldy, d->Cout);
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  plan_rings(p, d->k, d->dilation, true);
+  const bool cg2 = cg2_wanted();
+  if (!cg2) plan_rings(p, d->k, d->dilation, true);
   {
     // dy rows normally carry Cout_pad columns (zero padded); a row of only Cout columns (a hidden width that is a multiple of 8 but
     // not of 16) is declared as such, and the tail of the last contraction chunk reads as zero (TMA out-of-bounds fill)
@@ -885,7 +1126,7 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   {
     uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)n_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cout_pad * 2, (uint64_t)n_pad * d->Cout_pad * 2};
-    uint32_t box[3] = {kBlockK, (uint32_t)p.BN, 1};
+    uint32_t box[3] = {kBlockK, cg2 ? (uint32_t)p.BN / 2 : (uint32_t)p.BN, 1};
     rc = make_tensor_map(&p.tmB, wt, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
@@ -907,6 +1148,10 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   p.y_row_off = 0;
   p.ldy = d->Cin;
   p.splits = 1;
+  if (cg2) {
+    plan_cg2(p, (int64_t)d->k * p.BN * d->Cout_pad * 2);
+    return launch_gemm_cg2(p, (cudaStream_t)stream);
+  }
   p.tail_first = p.num_tiles;          // backward-data overlaps with wgrad, whose CTAs fill its last wave: no tail split here
   return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
 }

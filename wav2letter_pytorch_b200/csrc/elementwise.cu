@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
 struct BwdRow {
   uint4 z, r, d;
   uint32_t bits;
+  int len;
 };
 
 template <bool DROP, bool HAS_RES>
@@ -481,18 +482,24 @@ __device__ __forceinline__ void load_bwd_row(const BnBwdArgs& a, int r, int b, i
   in.z = __ldg(reinterpret_cast<const uint4*>(a.z + e));
   if (HAS_RES) in.r = __ldg(reinterpret_cast<const uint4*>(a.res + e));
   in.d = __ldg(reinterpret_cast<const uint4*>(a.dyp + ((int64_t)b * (a.pl + a.T + a.pr) + a.pl + t) * a.C + c));
-  if (DROP)
-    in.bits = a.drop_mask ? (uint32_t)__ldg(a.drop_mask + (e >> 3))
-                          : (dropout_mask32(a.seed, (uint32_t)(r / kRowGroup), (uint32_t)cv, a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
+  // only LOADS here: a consumer of a load result between two rows' requests (the merge point of a "mask or hash" select was one)
+  // makes the thread wait out the memory latency once per row instead of once per row group -- the regenerated-mask fallback
+  // therefore lives in g_from_row
+  in.bits = 0;
+  if (DROP && a.drop_mask) in.bits = (uint32_t)__ldg(a.drop_mask + (e >> 3));
+  in.len = a.lens ? __ldg(a.lens + b) : 0x7fffffff;
 }
 
 // masked upstream gradient g and the conv output for one staged row (reflect halo folded; activation gate, dropout, length mask)
 template <int ACT, bool DROP, bool HAS_RES>
-__device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int b, int t, int c, const BwdRow& in, const float (&sc)[8],
+__device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int r, int b, int t, int c, const BwdRow& in, const float (&sc)[8],
                                            const float (&sh)[8], const float (&rsc)[8], const float (&rsh)[8], float (&g)[8],
                                            float (&zv)[8]) {
   unpack8(in.z, zv);
   unpack8(in.d, g);
+  uint32_t bits = in.bits;
+  if (DROP && !a.drop_mask)                                        // no stored keep-bits: regenerate them (kernel-uniform branch)
+    bits = (dropout_mask32(a.seed, (uint32_t)(r / kRowGroup), (uint32_t)(c >> 3), a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
   const int dr = a.T - 1 - t;
   if ((t >= 1 && t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo (<8 % of the rows)
     const __nv_bfloat16* base = a.dyp + (int64_t)b * (a.pl + a.T + a.pr) * a.C + c;
@@ -510,13 +517,13 @@ __device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int b, int t, int
   }
   float rv[8];
   if (HAS_RES) unpack8(in.r, rv);
-  const bool masked = a.lens && t >= a.lens[b];
+  const bool masked = t >= in.len;
   const float gs = DROP ? a.inv_keep : 1.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float pre = fmaf(zv[i], sc[i], sh[i]);                         // the kept element's value (1/keep folded into sc, sh)
     if (HAS_RES) pre += fmaf(rv[i], rsc[i], rsh[i]);
-    const bool on = !masked && act_pass<ACT>(pre) && (!DROP || ((in.bits >> i) & 1u));
+    const bool on = !masked && act_pass<ACT>(pre) && (!DROP || ((bits >> i) & 1u));
     g[i] = on ? g[i] * gs : 0.f;
   }
 }
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce
       for (int u = 0; u < kRows; ++u) {
         if (r0 + u < r_end) {
           float g[8], zv[8];
-          g_from_row<ACT, DROP, HAS_RES>(a, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
+          g_from_row<ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             sg[i] += g[i];
@@ -671,7 +678,7 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
     for (int u = 0; u < kRows; ++u) {
       if (r0 + u < r_end) {
         float g[8], zv[8], o[8];
-        g_from_row<ACT, DROP, HAS_RES>(a, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
+        g_from_row<ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
         *reinterpret_cast<uint4*>(a.dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = pack8(o);
