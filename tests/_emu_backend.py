@@ -498,7 +498,8 @@ GEMM_SUBS = [(r'asm volatile\("bar\.sync 1, 128;" ::: "memory"\);', "emu::named_
               r'"f"\((.*?)\), "f"\((.*?)\)\s*: "memory"\);', r"emu_red_add_v4(\1, \2, \3, \4, \5);")]
 # the CTA-pair kernel (cluster of 2, tcgen05 cta_group::2) is outside the emulated surface: the emulated library always takes the
 # single-CTA kernel, as the real one does under W2L_CG2=0; the pair kernel's parity is the -m gpu tests' job
-GEMM_DROP = {"conv_gemm_cg2_kernel": "",
+GEMM_DROP = {"conv_gemm_cg2_kernel": "", "conv_wgrad_cg2_kernel": "",
+             "launch_wgrad_cg2": "\nstatic int launch_wgrad_cg2(const GemmParams&, int, cudaStream_t) { set_error(\"no CTA-pair kernel on the host\"); return W2L_ERR_CUDA; }",
              "launch_gemm_cg2": "\nstatic int launch_gemm_cg2(const GemmParams&, cudaStream_t) { set_error(\"no CTA-pair kernel on the host\"); return W2L_ERR_CUDA; }",
              "cg2_wanted": "\nstatic bool cg2_wanted() { return false; }"}
 GEMM_POST = r"""

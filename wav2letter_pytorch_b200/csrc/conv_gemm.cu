@@ -87,6 +87,8 @@ struct GemmParams {
   int32_t c2_pair_b;
   int32_t c2_mu, c2_bu;     // units along M / along the batch a pair index decodes into
   int32_t c2_ngroup;        // N tiles that run side by side on the same activation rows (their weight slices stay in L2 together)
+  int32_t c2_k;             // wgrad pair kernel: the real tap count (p.k then counts tap PAIRS)
+  int32_t c2_npad;          // fwd-kind pair kernel: padded column count (the last N tile covers [.., c2_npad))
 };
 
 // A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
@@ -107,14 +109,15 @@ struct UnitIter {
   int tile_end;
   int64_t g, g_end;      // wgrad stream-K cursor in the remainder iteration space
   int iters;             // K iterations per tile
-  __device__ UnitIter(const GemmParams& p_) : p(p_) {
-    tile = blockIdx.x;
+  int cta, ncta;         // this CTA's (or CTA pair's) index among the units of the persistent grid
+  __device__ UnitIter(const GemmParams& p_, int cta_ = blockIdx.x, int ncta_ = gridDim.x) : p(p_), cta(cta_), ncta(ncta_) {
+    tile = cta;
     if (MODE == MODE_WGRAD) {
       iters = p.B * p.kc_steps;
-      tile_end = p.wg_rounds * gridDim.x;
+      tile_end = p.wg_rounds * ncta;
       const int64_t rem = (int64_t)(p.num_tiles - tile_end) * iters;
-      g = rem * blockIdx.x / gridDim.x;
-      g_end = rem * (blockIdx.x + 1) / gridDim.x;
+      g = rem * cta / ncta;
+      g_end = rem * (cta + 1) / ncta;
     } else {
       iters = p.k * p.kc_steps;
       tile_end = p.tail_parts > 1 ? p.tail_first : p.num_tiles;
@@ -139,7 +142,7 @@ struct UnitIter {
   __device__ bool next(Unit& u) {
     if (tile < tile_end) {
       int t = tile;
-      tile += gridDim.x;
+      tile += ncta;
       u.it_begin = 0;
       u.it_end = iters;
       u.partial = false;
@@ -153,7 +156,7 @@ struct UnitIter {
     if (MODE != MODE_WGRAD) {
       if (p.tail_parts <= 1 || g != 0) return false;
       g = 1;
-      const int c = blockIdx.x;
+      const int c = cta;
       if (c >= p.tail_tiles * p.tail_parts) return false;
       u.tail = c / p.tail_parts;
       const int part = c - u.tail * p.tail_parts;
@@ -645,6 +648,14 @@ __device__ __forceinline__ void decode_pair(const GemmParams& p, int t, int rank
   }
 }
 
+// width of the N tile that starts at column n0: BN, except that the LAST tile of a row may be narrower (c2_npad = the padded column
+// count, a multiple of 16): 896 columns run as 3 x 256 + 128 instead of 4 x 224 -- the tensor pipe is ~10 % slower at N = 224 than
+// at 256.  The TMA box stays BN/2 weight rows per CTA; a narrow tile uses the first rows of what each CTA fetched.
+__device__ __forceinline__ int c2_tile_bn(const GemmParams& p, int n0) {
+  const int left = p.c2_npad - n0;
+  return left < p.BN ? left : p.BN;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) conv_gemm_cg2_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -694,6 +705,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
       PairTile u;
       for (int t = pair; t < p.num_tiles; t += npairs) {
         decode_pair(p, t, (int)rank, u);
+        const int half_u = c2_tile_bn(p, u.n0) >> 1;
         for (int it = 0; it < iters; ++it) {
           const int j = it / p.kc_steps, kc = it - j * p.kc_steps;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -701,7 +713,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
           const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * kC2StageBytes;
           tma_load_3d_cg2(sa, &p.tmA, lead_full, kc * kBlockK, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
-          tma_load_3d_cg2(sa + kABytes, &p.tmB, lead_full, kc * kBlockK, u.n0 + (int)(rank * half_bn), j);
+          tma_load_3d_cg2(sa + kABytes, &p.tmB, lead_full, kc * kBlockK, u.n0 + (int)rank * half_u, j);
           if (++stage == kC2Stages) {
             stage = 0;
             phase ^= 1u;
@@ -712,12 +724,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ------------------------------------------------------------ MMA issuer (leader CTA only)
-      const uint32_t idesc = make_idesc_bf16(2 * kBlockM, p.BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      PairTile u;
       for (int t = pair; t < p.num_tiles; t += npairs) {
+        decode_pair(p, t, 0, u);
+        const uint32_t idesc = make_idesc_bf16(2 * kBlockM, c2_tile_bn(p, u.n0), false, false);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
@@ -772,7 +786,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
       const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
       const int m = u.m0 + row;
       const bool row_ok = m < p.M_valid && u.b < p.B;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      const int bn_u = c2_tile_bn(p, u.n0);
+      for (int c0 = 0; c0 < bn_u; c0 += 32) {
         const int nbase = u.n0 + c0;
         if (nbase >= p.N_valid) break;
         uint32_t r[32];
@@ -792,6 +807,173 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
   }
   tc_fence_before();
   cluster_sync_all();                             // the peer's shared memory and barriers stay alive until every MMA has retired
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 2 * kAccCols);
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair weight gradient (cta_group::2)
+// Transposed problem, so that the operand the two CTAs SHARE is the one that does not depend on the tap:
+//   dW_j^T[ci, co] = sum_{b,t} X[b, t + off + j*d, ci] * dY[b, t, co]        A = X (MN-major, shifted per tap)   B = dY (MN-major)
+// The pair works on two consecutive (ci tile, tap) combinations -- tap fastest -- of one BN-wide co tile: each CTA fetches ITS X
+// rows and half of the dY tile.
+// Work units are cut stream-K over the PAIRS (UnitIter with pair index / pair count); a tile shared between pairs is accumulated
+// with fp32 atomics.  The accumulator row is ci, its columns are co: column i of a warp's 32 rows is 128 contiguous bytes of
+// dw[j][co][:], so the scalar stores / reductions below are coalesced.
+// width of the N tile that starts at column n0: the last tile of a row is cut to the next multiple of 128 (896 = 3 x 256 + 128, no
+// padded MMA work); the TMA box stays BN/2 columns per CTA -- a narrow tile just uses the first chunk of what each CTA fetched
+__device__ __forceinline__ int wg2_tile_bn(const GemmParams& p, int n0) {
+  const int left = (p.N_valid - n0 + 127) & ~127;
+  return left < p.BN ? left : p.BN;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) conv_wgrad_cg2_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kC2Stages * kC2StageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kC2Stages;
+  uint64_t* tfull_bar = bars + 2 * kC2Stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t half_bn = (uint32_t)p.BN >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int i = 0; i < kC2Stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_cg2(tmem_slot, 2 * kAccCols);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_tx = 2u * ((uint32_t)kABytes + half_bn * 128u);
+      UnitIter<MODE_WGRAD> units(p, pair, npairs);
+      Unit u;
+      while (units.next(u)) {
+        const int q = u.j * 2 + (int)rank, mt = q / p.c2_k, tap = q - mt * p.c2_k;      // this CTA's (ci tile, tap); past the end: all zero
+        const int half_u = wg2_tile_bn(p, u.n0) >> 1;
+        for (int it = u.it_begin; it < u.it_end; ++it) {
+          const int b = it / p.kc_steps, t0 = (it - b * p.kc_steps) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * kC2StageBytes;
+          tma_load_4d_cg2(sa, &p.tmA, lead_full, 0, t0 + p.b_row_off + tap * p.dil, mt * 2, b);
+          tma_load_4d_cg2(sa + kABytes, &p.tmB, lead_full, 0, t0, (u.n0 + (int)rank * half_u) >> 6, b);
+          if (++stage == kC2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      UnitIter<MODE_WGRAD> units(p, pair, npairs);
+      Unit u;
+      while (units.next(u)) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        const uint32_t idesc = make_idesc_bf16(2 * kBlockM, wg2_tile_bn(p, u.n0), true, true);
+        uint32_t accumulate = 0;
+        for (int it = u.it_begin; it < u.it_end; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kC2StageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / 16; ++kk) {
+            const uint64_t adesc = make_smem_desc(a_addr + kk * 2048u, 8192u, 1024u);
+            const uint64_t bdesc = make_smem_desc(b_addr + kk * 2048u, 8192u, 1024u);
+            umma_bf16_cg2(d_tmem, adesc, bdesc, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_cg2(&empty_bar[stage], 3);
+          if (++stage == kC2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (warps 2..5 of both CTAs)
+    const int lane_base = (warp & 3) * 32;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    UnitIter<MODE_WGRAD> units(p, pair, npairs);
+    Unit u;
+    while (units.next(u)) {
+      const int q = u.j * 2 + (int)rank, mt = q / p.c2_k, tap = q - mt * p.c2_k;
+      const int bn_u = wg2_tile_bn(p, u.n0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)acc * kAccCols;
+      const int ci = mt * kBlockM + lane_base + lane;
+      const bool row_ok = ci < p.M_valid;
+      float* dst0 = reinterpret_cast<float*>(p.y) + (int64_t)tap * p.dw_tap_stride + ci;
+      for (int c0 = 0; c0 < bn_u; c0 += 32) {
+        const int nbase = u.n0 + c0;
+        if (nbase >= p.N_valid) break;
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          float* dst = dst0 + (int64_t)nbase * p.ldy;
+          if (u.partial) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nbase + i < p.N_valid) atomicAdd(dst + (int64_t)i * p.ldy, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (nbase + i < p.N_valid) dst[(int64_t)i * p.ldy] = __uint_as_float(r[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, 2 * kAccCols);
@@ -894,6 +1076,13 @@ static int launch_gemm(const GemmParams& p_in, cudaStream_t st, int grid_overrid
 
 // CTA-pair kernel: on by default for the FWD-kind GEMMs (forward, backward-data with the transposed weight shadow);
 // W2L_CG2=0 falls back to the single-CTA kernel (the A/B switch of profiles/r2_gemm_cg2.md)
+// N tile of the pair kernels: 256-wide tiles with a narrower last one (W2L_CG2_WIDE=0: equal tiles from pick_bn, the A/B switch)
+static int cg2_bn(int npad) {
+  const char* e = getenv("W2L_CG2_WIDE");
+  if (e && atoi(e) == 0) return pick_bn(npad, 16);
+  return npad < 256 ? npad : 256;
+}
+
 static bool cg2_wanted() {
   const char* e = getenv("W2L_CG2");          // read per call: the parity tests run every case under both kernels in one process
   return !(e && atoi(e) == 0);
@@ -961,6 +1150,41 @@ static void wgrad_plan(const w2l_conv_desc* d, int* bn_out, int* grid_out, int* 
   if (zero_out) *zero_out = rem_tiles > 0;
 }
 
+// ---- CTA-pair wgrad: eligibility and plan.  Needs whole 64-channel chunks on both operands (4-D chunked maps) and at least two taps.
+static bool wgrad_cg2_ok(const w2l_conv_desc* d) {
+  const char* e = getenv("W2L_CG2_WGRAD");    // 0: single-CTA wgrad beside the pair fwd/dgrad kernels (A/B switch)
+  return cg2_wanted() && !(e && atoi(e) == 0) && wgrad_mn4d(d) && d->k >= 2;
+}
+// N tile over Cout: 128 or 256 (each CTA holds whole 64-channel chunks of its half); the narrower tile runs the tensor pipe a little
+// below the wide one, so it wins only when it saves padding
+static int wgrad_cg2_bn(int cout) {
+  return cout > 128 ? 256 : 128;           // a narrower LAST tile is chosen per tile inside the kernel (wg2_tile_bn)
+}
+static void wgrad_cg2_plan(const w2l_conv_desc* d, int* bn_out, int* pairs_out, int* rounds_out, int* zero_out) {
+  const int bn = wgrad_cg2_bn(d->Cout);
+  const int64_t tiles = (((int64_t)d->k * ((d->Cin + kBlockM - 1) / kBlockM) + 1) / 2) * ((d->Cout + bn - 1) / bn);
+  const int64_t iters = (int64_t)d->B * ((d->T_out + kBlockK - 1) / kBlockK);
+  int64_t pairs = gemm_sms() / 2;
+  const int64_t min_iters = 32;
+  if (tiles * iters / pairs < min_iters) pairs = tiles * iters / min_iters > 0 ? tiles * iters / min_iters : 1;
+  const int64_t rounds = tiles / pairs;
+  if (bn_out) *bn_out = bn;
+  if (pairs_out) *pairs_out = (int)pairs;
+  if (rounds_out) *rounds_out = (int)rounds;
+  if (zero_out) *zero_out = (tiles - rounds * pairs) > 0;
+}
+
+static int launch_wgrad_cg2(const GemmParams& p, int pairs, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    W2L_CUDA(cudaFuncSetAttribute(conv_wgrad_cg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC2Smem));
+    configured = true;
+  }
+  if (pairs < 1) return W2L_OK;
+  conv_wgrad_cg2_kernel<<<2 * pairs, kGemmThreads, kC2Smem, st>>>(p);
+  return after_launch("conv_wgrad_cg2_kernel");
+}
+
 }  // namespace w2l
 
 extern "C" {
@@ -988,7 +1212,8 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
     rc = make_tensor_map(&p.tmA, x, 2, 3, dims, str, box, true);
     if (rc) return rc;
   }
-  p.BN = pick_bn(d->Cout_pad, 16);
+  p.BN = cg2 ? cg2_bn(d->Cout_pad) : pick_bn(d->Cout_pad, 16);
+  p.c2_npad = d->Cout_pad;
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
@@ -1122,7 +1347,8 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
     if (rc) return rc;
   }
   const int n_pad = (d->Cin + 15) / 16 * 16;
-  p.BN = pick_bn(n_pad, 16);
+  p.BN = cg2 ? cg2_bn(n_pad) : pick_bn(n_pad, 16);
+  p.c2_npad = n_pad;
   {
     uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)n_pad, (uint64_t)d->k};
     uint64_t str[2] = {(uint64_t)d->Cout_pad * 2, (uint64_t)n_pad * d->Cout_pad * 2};
@@ -1159,7 +1385,10 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
   if (!d || d->B < 1 || d->T_out < 1 || d->k < 1) return 1;
   int zero = 0;
-  w2l::wgrad_plan(d, nullptr, nullptr, nullptr, &zero);
+  if (w2l::wgrad_cg2_ok(d))
+    w2l::wgrad_cg2_plan(d, nullptr, nullptr, nullptr, &zero);
+  else
+    w2l::wgrad_plan(d, nullptr, nullptr, nullptr, &zero);
   return zero ? 2 : 1;
 }
 
@@ -1172,6 +1401,43 @@ int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_de
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const __nv_bfloat16* dy_base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+  if (wgrad_cg2_ok(d)) {
+    // CTA-pair kernel on the transposed problem: A = x (128 ci x 64 rows, shifted per tap), B = dy (BN co x 64 rows, half per CTA)
+    int bn = 0, pairs = 0, rounds = 0, zero = 0;
+    wgrad_cg2_plan(d, &bn, &pairs, &rounds, &zero);
+    {
+      uint64_t dims[4] = {64, (uint64_t)d->x_rows, (uint64_t)d->Cin / 64, (uint64_t)d->B};
+      uint64_t str[3] = {(uint64_t)d->Cin * 2, 128, (uint64_t)d->x_rows * d->Cin * 2};
+      uint32_t box[4] = {64, kBlockK, 2, 1};
+      rc = make_tensor_map(&p.tmA, x, 2, 4, dims, str, box, true);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[4] = {64, (uint64_t)d->T_out, (uint64_t)d->ldy / 64, (uint64_t)d->B};
+      uint64_t str[3] = {(uint64_t)d->ldy * 2, 128, (uint64_t)d->y_rows * d->ldy * 2};
+      uint32_t box[4] = {64, kBlockK, (uint32_t)bn / 128, 1};
+      rc = make_tensor_map(&p.tmB, dy_base, 2, 4, dims, str, box, true);
+      if (rc) return rc;
+    }
+    p.BN = bn;
+    p.splits = zero ? 2 : 1;
+    p.wg_rounds = rounds;
+    p.B = d->B;
+    p.m_tiles = 1;                        // the (ci tile, tap) axis is flattened: UnitIter decodes p.k PAIRS of it per co tile
+    p.n_tiles = (d->Cout + bn - 1) / bn;
+    p.k = (d->k * ((d->Cin + kBlockM - 1) / kBlockM) + 1) / 2;
+    p.c2_k = d->k;
+    p.dil = d->dilation;
+    p.kc_steps = (d->T_out + kBlockK - 1) / kBlockK;
+    p.b_row_off = d->x_row_offset;
+    p.M_valid = d->Cin;
+    p.N_valid = d->Cout;
+    p.num_tiles = p.k * p.m_tiles * p.n_tiles;
+    p.y = dw;
+    p.ldy = d->Cin;
+    p.dw_tap_stride = (int64_t)d->Cout * d->Cin;
+    return launch_wgrad_cg2(p, pairs, (cudaStream_t)stream);
+  }
   p.mn4d = wgrad_mn4d(d);
   int bn = 0, grid = 0, rounds = 0, zero = 0;
   wgrad_plan(d, &bn, &grid, &rounds, &zero);
