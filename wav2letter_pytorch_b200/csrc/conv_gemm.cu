@@ -648,9 +648,9 @@ __device__ __forceinline__ void decode_pair(const GemmParams& p, int t, int rank
   }
 }
 
-// width of the N tile that starts at column n0: BN, except that the LAST tile of a row may be narrower (c2_npad = the padded column
-// count, a multiple of 16): 896 columns run as 3 x 256 + 128 instead of 4 x 224 -- the tensor pipe is ~10 % slower at N = 224 than
-// at 256.  The TMA box stays BN/2 weight rows per CTA; a narrow tile uses the first rows of what each CTA fetched.
+// width of the N tile that starts at column n0: BN, except that the LAST tile of a row ends at the padded column count c2_npad (a
+// multiple of 16; 640 columns run as 224 + 224 + 192).  The TMA box stays BN/2 weight rows per CTA; a narrow tile uses the first
+// rows of what each CTA fetched.
 __device__ __forceinline__ int c2_tile_bn(const GemmParams& p, int n0) {
   const int left = p.c2_npad - n0;
   return left < p.BN ? left : p.BN;
@@ -1076,12 +1076,10 @@ static int launch_gemm(const GemmParams& p_in, cudaStream_t st, int grid_overrid
 
 // CTA-pair kernel: on by default for the FWD-kind GEMMs (forward, backward-data with the transposed weight shadow);
 // W2L_CG2=0 falls back to the single-CTA kernel (the A/B switch of profiles/r2_gemm_cg2.md)
-// N tile of the pair kernels: 256-wide tiles with a narrower last one (W2L_CG2_WIDE=0: equal tiles from pick_bn, the A/B switch)
-static int cg2_bn(int npad) {
-  const char* e = getenv("W2L_CG2_WIDE");
-  if (e && atoi(e) == 0) return pick_bn(npad, 16);
-  return npad < 256 ? npad : 256;
-}
+// N tile of the fwd-kind pair kernel: equal tiles from pick_bn (the last one ends at the padded column count).  Measured against
+// 256-wide tiles with a narrow last one (896 = 3 x 256 + 128): 34.1 / 33.6 vs 34.4 / 34.2 ms of conv time per step -- K-major tiles
+// cost in proportion to their width, so fewer-but-wider buys nothing (profiles/r2_gemm_cg2.md).
+static int cg2_bn(int npad) { return pick_bn(npad, 16); }
 
 static bool cg2_wanted() {
   const char* e = getenv("W2L_CG2");          // read per call: the parity tests run every case under both kernels in one process
