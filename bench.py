@@ -512,6 +512,38 @@ def quick_leg(env, arch, mid, ragged, steps):
     return out
 
 
+def tf32_leg(env, mid, steps=3):
+    """The fp32-faithful mode (model precision 'tf32': fp32 activations / weights / gradients in memory, kind::tf32 GEMMs, fp32
+    BatchNorm passes; north_star's "bf16/fp32 activations") on the headline workload: ms/step, and the first step's loss next to the
+    default bf16 model's from the same initialisation and batch (they must agree to 2e-2: same network, different roundings)."""
+    build, one_step, barrier, dev, rank = (env[k] for k in ("build", "one_step", "barrier", "dev", "rank"))
+    xb, ilb, tgb, tlb, txt = synthetic_batch(BATCH, UTT_SEC, seed=rank)
+    batch = tuple(t.to(dev) for t in (xb, ilb, tgb, tlb))
+    first = {}
+    for prec in ("bf16", "tf32"):
+        model, opt, reducer = build(mid, "wav2letter", precision=prec)
+        first[prec] = float(one_step(model, opt, reducer, batch, 0, txt).item())
+        if prec == "tf32":
+            one_step(model, opt, reducer, batch, 1, txt)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(steps):
+                loss = one_step(model, opt, reducer, batch, it, txt)
+            e1.record()
+            barrier()
+            ms, last = e0.elapsed_time(e1) / steps, float(loss.item())
+        del model, opt, reducer
+        torch.cuda.empty_cache()
+    rel = abs(first["tf32"] - first["bf16"]) / abs(first["bf16"])
+    if not (last == last and rel < 2e-2):
+        raise RuntimeError("tf32 leg: first-step loss %r vs bf16 %r (rel %.3g), last %r" % (first["tf32"], first["bf16"], rel, last))
+    return {"workload": "Wav2Letter mid_layers=%d train step, B=%d x %d s, precision=tf32 (fp32 storage, tf32 multiply, fp32 accumulate)" % (mid, BATCH, UTT_SEC),
+            "steps": steps, "ms_per_step": ms, "value": BATCH * UTT_SEC / (ms / 1e3), "unit": "audio-s/s", "loss_first_step": first["tf32"],
+            "loss_first_step_bf16": first["bf16"], "rel_diff": rel,
+            "note": "parity mode: single-CTA kind::tf32 GEMMs, weight gradient over transposed operands -- not the throughput path"}
+
+
 def config5_corners(F, dev):
     """Six corners of BASELINE config 5 (standalone CTC loss+grad and greedy decode over T x S x N, C=29, fp32 log-probs): this
     library's kernels (ms, algorithmic GB/s of SURVEY 8d against the measured HBM peak) next to torch's own CUDA ``ctc_loss`` fwd+bwd
@@ -617,10 +649,12 @@ def run_gpu_arm(args):
         from wav2letter_pytorch_b200.distributed import init_process_group
         init_process_group("nccl", device=dev, max_ctas=int(os.environ.get("W2L_NCCL_MAX_CTAS", "4")))
 
-    def build(mid_layers, arch=None):
+    def build(mid_layers, arch=None, precision=None):
         arch = arch or args.model
         if arch == "wav2letter":
             cfg = config.compose(overrides=["model.mid_layers=%d" % mid_layers, "optimizer=novograd"]).model
+            if precision:
+                cfg["precision"] = precision
             cls = Wav2Letter
         else:                                            # jasper10x5 (BASELINE config 3) | jasper (the shipped separable yaml)
             from wav2letter_pytorch_b200.jasper import Jasper
@@ -788,6 +822,11 @@ def run_gpu_arm(args):
                                       steps=5)
             except Exception as e:  # noqa: BLE001  (a secondary table must never take the headline line down)
                 legs[key] = {"error": repr(e)[:300]}
+        if args.model == "wav2letter":
+            try:
+                legs["precision_tf32"] = tf32_leg(dict(build=build, one_step=one_step, barrier=barrier, dev=dev, rank=rank), args.mid_layers)
+            except Exception as e:  # noqa: BLE001
+                legs["precision_tf32"] = {"error": repr(e)[:300]}
         try:
             legs["config5"] = config5_corners(F, dev)
         except Exception as e:  # noqa: BLE001
@@ -843,14 +882,17 @@ def run_gpu_arm(args):
                    "global_batch": world * BATCH, "parallelism": "dp%d" % world,
                    "lengths": "ragged: inputs uniform in [0.6 T, T], targets in [S/2, S]; audio seconds counted as padded" if RAGGED else "full",
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no explicit flush",
-                   "ctc_schedule": "log-space (alpha || beta CTAs + parallel gradient pass)"},
+                   "ctc_schedule": "log-space (alpha || beta CTAs + parallel gradient pass)",
+                   "precision": "bf16 operands and activations, fp32 accumulation / statistics / master weights (the fp32-faithful tf32 "
+                                "mode is measured in the precision_tf32 leg)",
+                   "gemm": "CTA pairs (tcgen05 cta_group::2): conv_gemm_cg2_kernel fwd/dgrad, conv_wgrad_cg2_kernel; W2L_CG2=0 = single CTA"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
         "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "step_ms_min_median_max": {"value": step_spread[0], "e2e": step_spread[2] if len(step_spread) > 2 else None},
         "cuda_mallocs_in_timed_region": int(new_segments),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<fwd|dgrad|wgrad> (tcgen05 implicit GEMM)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_cg2_kernel (fwd, dgrad) + conv_wgrad_cg2_kernel: tcgen05 cta_group::2 implicit GEMMs", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained", "unit": "TFLOP/s",
                      "frac": achieved / peaks["tf_sustained"], "traffic": None,
                      "flops_per_step": train_flops * BATCH, "kernel_ms_per_step": conv_total_ms, "by_pass_span_ms": conv_ms,
@@ -898,7 +940,7 @@ def run_gpu_arm(args):
     line["loss_last_step"] = {"value_leg": loss_trace[0] if loss_trace else None, "all_timed_regions": loss_trace}
     line["roofline"]["frac_vs_burst"] = achieved / peaks["tf_burst"]
     line["roofline"]["peak_burst"] = peaks["tf_burst"]
-    for key in ("config3", "ragged", "config5", "loss_check"):
+    for key in ("config3", "ragged", "precision_tf32", "config5", "loss_check"):
         if key in legs:
             line[key] = legs[key]
     if config1:

@@ -38,6 +38,10 @@ extern "C" {
 
 #define W2L_DTYPE_BF16 0
 #define W2L_DTYPE_F32 1
+/* OR-ed into the `act` argument of the BatchNorm / activation passes (w2l_bn_act_pad, w2l_bn_finalize_act_pad,
+ * w2l_bn_act_bwd_reduce, w2l_bn_act_bwd_apply): the activation buffers of the call (z, res, y / dyp, dz, g_out) are fp32
+ * instead of bf16 -- the fp32-faithful mode, whose GEMMs run with w2l_conv_desc::x_dtype = W2L_DTYPE_F32 */
+#define W2L_STORE_F32 0x100
 
 int w2l_version(void);
 const char* w2l_last_error(void);
@@ -147,6 +151,9 @@ typedef struct {
   int32_t ldy;          /* output row pitch in elements                */
   int32_t y_dtype;      /* W2L_DTYPE_*                                 */
   int32_t act;          /* W2L_ACT_*                                   */
+  int32_t x_dtype;      /* operand type of activations AND weights: W2L_DTYPE_BF16 (0), or W2L_DTYPE_F32 = fp32 storage
+                           multiplied as tf32 with fp32 accumulation (the fp32-faithful mode; reference arithmetic is
+                           nn.Conv1d in fp32, wav2letter.py:35-36) */
 } w2l_conv_desc;
 
 int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float* scale, const float* shift, float* bn_stats,
@@ -167,8 +174,19 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
  * that are multiples of 8 but not of 16); in the latter case the tail of the last contraction chunk reads as zero. */
 int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream);
 int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);
+/* the same shadow in fp32 (operand of w2l_conv1d_dgrad_wt with x_dtype = F32) */
+int w2l_pack_wt_f32(const float* w, float* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d);
 int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream);
+/* fp32-faithful mode (x_dtype = F32): the weight gradient over TRANSPOSED fp32 operands dyT [B, Cout, dy_pitch] and
+ * xT [B, Cin, x_pitch] (time contiguous, as w2l_tm_to_ct_f32 writes them; pitches in floats, multiples of 4), multiplied as tf32:
+ *   dw[j, co, ci] += sum_b sum_t dyT[b, co, t] * x[b, t + x_row_offset + j*dilation, ci],  t < T_out, rows in [0, x_rows)
+ * TMA needs the time coordinate of a load 16-byte aligned, so x comes as up to four copies DELAYED by s = 0..3 rows:
+ * xT_shifted (HOST array of 4 device pointers), xT_shifted[s][b, ci, u] = x[b, u - s, ci] with s zeros in front
+ * (x_pitch >= x_rows + 3); only the residues (-(x_row_offset + j*dilation)) mod 4 that occur must be non-null.
+ * dw [k, Cout, Cin] fp32 must be ZERO on entry. */
+int w2l_conv1d_wgrad_t(const float* dyT, int64_t dy_pitch, const float* const* xT_shifted, int64_t x_pitch, float* dw,
+                       const w2l_conv_desc* d, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Depthwise Conv1d (groups = channels): the first half of the separable sub-blocks of the shipped model/jasper.yaml
@@ -196,6 +214,9 @@ int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int
  * k=1, stride=1 gives the plain padded time-major copy.  wav2letter.py:41 + the layer-0 unfold. */
 int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
                    int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream);
+/* the same with fp32 output (fp32-faithful mode) */
+int w2l_im2col_ncw_f32(const float* x, float* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                       int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream);
 /* Strided layers beyond the first (Conv1dBlock with stride > 1, wav2letter.py:24-38; strided JasperBlock, jasper.py:289-298):
  * time-major bf16 x [B, x_rows, C] -> out [B, T_out, k*C] with out[b, t, j*C + c] = x[b, t*stride + j*dilation - pad_left, c]
  * (zero outside [0, x_rows)); the conv then runs as a k=1 GEMM over `out` with weights stored [Cout, k, Cin]. */
@@ -207,6 +228,10 @@ int w2l_col2im_tm(const void* dcol, void* dx, int32_t B, int32_t x_rows, int32_t
 /* time-major bf16/fp32 [B, T, C] (row pitch ld) -> NCW fp32 [B, C, T] */
 int w2l_tm_to_ncw(const void* x, int32_t x_dtype, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows,
                   int32_t x_row_offset, int32_t ld, void* stream);
+/* time-major fp32 rows [x_row_offset, x_row_offset + T) of x [B, x_rows, ld] -> channel-major out [B, C, out_pitch] fp32 (the pad
+ * [T, out_pitch) is left untouched): the transposed operands of w2l_conv1d_wgrad_t */
+int w2l_tm_to_ct_f32(const float* x, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows, int32_t x_row_offset, int32_t ld,
+                     int32_t out_pitch, void* stream);
 /* NCW fp32 [B, C, T] -> time-major bf16 [B, T, C] (dense) */
 int w2l_ncw_to_tm(const float* x, void* out, int32_t B, int32_t C, int32_t T, void* stream);
 
@@ -254,6 +279,7 @@ int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows
 /* In-place reflect halo for a buffer whose interior rows [pad_left, pad_left+T) were written by the fused
  * conv epilogue (inference: BatchNorm folded into scale/shift, wav2letter.py:41-46). */
 int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream);
+int w2l_reflect_halo_f32(float* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream);
 /* Backward of the above + BatchNorm backward, two passes over (dy_padded, z):
  *   g = fold_reflect(dyp)[b,t,c] * act'(.) * dropmask;  pass 1 reduces sum(g), sum(g*xhat) into
  *   red[0:C], red[C:2C] (zero on entry: one atomic per channel and CTA); pass 2 writes
@@ -281,8 +307,11 @@ int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, i
  * written as bf16 into [rows, ld_out] with zero padding in columns >= C. */
 int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out,
                         int64_t rows, int32_t C, int32_t fused_identity, void* stream);
+int w2l_log_softmax_bwd_f32(const float* g, const float* lp, const float* gscale, float* dlogits, int32_t ld_out,
+                            int64_t rows, int32_t C, int32_t fused_identity, void* stream);
 /* column sums of a bf16 [rows, ld] matrix -> out[C] fp32 (zeroed by the caller): bias gradient */
 int w2l_colsum(const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream);
+int w2l_colsum_f32(const float* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream);
 /* fp32 -> bf16 cast (packed weight shadow refresh) */
 int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -40,9 +40,9 @@ _BN_VARIANTS = ["%d, %s, %s" % (a, d, r) for a in (0, 1, 2) for d in ("false", "
 
 @functools.lru_cache(maxsize=None)
 def elementwise():
-    kernels = ["im2col_ncw_kernel", "im2col_tm_kernel", "col2im_tm_kernel", "tm_to_ncw_kernel<__nv_bfloat16>", "tm_to_ncw_kernel<float>",
-               "bn_stats_kernel", "bn_finalize_kernel", "log_softmax_kernel", "log_softmax_bwd_kernel", "colsum_kernel", "cast_bf16_kernel",
-               "lens_chain_kernel", "reflect_halo_kernel", "pack_wt_kernel"]
+    kernels = ["im2col_ncw_kernel<__nv_bfloat16>", "im2col_tm_kernel", "col2im_tm_kernel", "tm_to_ncw_kernel<__nv_bfloat16>", "tm_to_ncw_kernel<float>",
+               "bn_stats_kernel", "bn_finalize_kernel", "log_softmax_kernel", "log_softmax_bwd_kernel<__nv_bfloat16>", "colsum_kernel<__nv_bfloat16>", "cast_bf16_kernel",
+               "lens_chain_kernel", "reflect_halo_kernel<__nv_bfloat16>", "pack_wt_kernel<__nv_bfloat16>"]
     # (the BatchNorm / activation passes run through the C wrappers of tests/_emu_cabi.py: see _via_cabi below)
     return KE.build(["elementwise.cu"], kernels, drop=ELEMENTWISE_DROP, extra=ELEMENTWISE_PTX)
 
@@ -111,7 +111,7 @@ def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
     span = 31 * stride + (k - 1) * dilation + 1
     pitch = span | 1
     lens = None if lens is None else lens.to(torch.int32).contiguous()
-    elementwise().launch("im2col_ncw_kernel", ((rows + 31) // 32, B), 256, _p(x), _p(out), F, T, rows, k, stride, dilation, pad_left, pad_mode,
+    elementwise().launch("im2col_ncw_kernel<__nv_bfloat16>", ((rows + 31) // 32, B), 256, _p(x), _p(out), F, T, rows, k, stride, dilation, pad_left, pad_mode,
                          _p(lens), span, pitch, smem=F * pitch * 4)
     return out
 
@@ -122,7 +122,7 @@ def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
     B, rows, ld = x.shape
     out = torch.full((B, C, T), float("nan"))
     name = "tm_to_ncw_kernel<__nv_bfloat16>" if x.dtype == BF16 else "tm_to_ncw_kernel<float>"
-    elementwise().launch(name, ((T + 31) // 32, (C + 31) // 32, B), (32, 8), _p(x), _p(out), T, C, rows * ld, x_row_offset, ld)
+    elementwise().launch(name, ((T + 31) // 32, (C + 31) // 32, B), (32, 8), _p(x), _p(out), T, C, rows * ld, x_row_offset, ld, T)
     return out
 
 
@@ -163,7 +163,7 @@ def pack_wt(w_store, wt, cout, cin):
     w_store = w_store.contiguous()
     k = w_store.shape[0]
     co_pad, ci_pad = wt.shape[2], wt.shape[1]
-    elementwise().launch("pack_wt_kernel", ((ci_pad + 31) // 32, (co_pad + 31) // 32, k), (32, 8), _p(w_store), _p(wt), k, cout, cin, co_pad,
+    elementwise().launch("pack_wt_kernel<__nv_bfloat16>", ((ci_pad + 31) // 32, (co_pad + 31) // 32, k), (32, 8), _p(w_store), _p(wt), k, cout, cin, co_pad,
                          ci_pad)
     return wt
 
@@ -172,7 +172,7 @@ def reflect_halo(y, T, pad_left, pad_right):
     """w2l_reflect_halo (elementwise.cu:919-928)"""
     B, rows, C = y.shape
     if pad_left + pad_right:
-        elementwise().launch("reflect_halo_kernel", _grid_for(B * (pad_left + pad_right) * (C // 8), 256), 256, _p(y), B, T, C, pad_left,
+        elementwise().launch("reflect_halo_kernel<__nv_bfloat16>", _grid_for(B * (pad_left + pad_right) * (C // 8), 256), 256, _p(y), B, T, C, pad_left,
                              pad_right)
     return y
 
@@ -270,7 +270,7 @@ def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
     g = g.contiguous()
     lp = None if lp is None else lp.contiguous()
     out = torch.full(g.shape[:-1] + (ld_out,), float("nan"), dtype=BF16)
-    elementwise().launch("log_softmax_bwd_kernel", (rows + 7) // 8, 256, _p(g), _p(lp), _p(gscale), _p(out), ld_out, rows, C,
+    elementwise().launch("log_softmax_bwd_kernel<__nv_bfloat16>", (rows + 7) // 8, 256, _p(g), _p(lp), _p(gscale), _p(out), ld_out, rows, C,
                          int(fused_identity))
     return out
 
@@ -283,7 +283,7 @@ def colsum(x, C):
     out = torch.zeros((C,))
     col_blocks = (C + 31) // 32
     rpb = _rows_per_block_for(rows, col_blocks)
-    elementwise().launch("colsum_kernel", (col_blocks, (rows + rpb - 1) // rpb), (32, 8), _p(x), rows, C, ld, _p(out), rpb)
+    elementwise().launch("colsum_kernel<__nv_bfloat16>", (col_blocks, (rows + rpb - 1) // rpb), (32, 8), _p(x), rows, C, ld, _p(out), rpb)
     return out
 
 

@@ -527,6 +527,10 @@ static inline void tma_load_nd(void* smem_dst, const CUtensorMap* mp, uint64_t* 
   std::memcpy(&m, mp, sizeof(m));
   const uint32_t dst = smem_u32(smem_dst);
   const uint32_t row_bytes = m.box[0] * (uint32_t)m.elem_bytes;
+  if (((long long)c[0] * m.elem_bytes) & 15) {        // seen on B200 (round 2, call 12): "illegal instruction" from such a load
+    std::fprintf(stderr, "emu: TMA load with an innermost coordinate (%d x %d bytes) that is not 16-byte aligned\n", c[0], m.elem_bytes);
+    std::abort();
+  }
   uint32_t lin = 0;
   for (uint32_t i3 = 0; i3 < m.box[3]; ++i3)
     for (uint32_t i2 = 0; i2 < m.box[2]; ++i2)
@@ -598,6 +602,36 @@ static inline void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
     for (int n = 0; n < N; ++n) {
       float acc = accumulate ? emu::from_bits<float>(emu_tmem[lane0 + m][col0 + n]) : 0.f;
       for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      emu_tmem[lane0 + m][col0 + n] = (uint32_t)emu::to_bits(acc);
+    }
+}
+// tcgen05.mma.cta_group::1.kind::tf32: fp32 operands read with a 10-bit mantissa (low 13 bits dropped), K = 8 per instruction;
+// K-major only (the library transposes the operands of the fp32-faithful weight gradient instead of using MN-major tf32)
+static inline float umma_operand_tf32(uint64_t desc, int r, int k) {
+  const uint32_t start = (uint32_t)(desc & 0x3FFF) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+  const uint32_t a = start + (uint32_t)(r / 8) * sbo + (uint32_t)(r % 8) * 128u + (uint32_t)k * 4u;
+  uint32_t bits;
+  std::memcpy(&bits, smem_ptr(swz128(a)), 4);
+  return emu::from_bits<float>((uint64_t)(bits & 0xFFFFE000u));
+}
+static inline void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
+  if (M != 128 || N < 16 || N > 256 || a_mn || b_mn || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2 || ((a_desc >> 61) & 7) != 2 ||
+      ((b_desc >> 61) & 7) != 2) {
+    std::fprintf(stderr, "emu: unsupported tcgen05.mma.kind::tf32 shape / majorness / format (M=%d N=%d)\n", M, N);
+    std::abort();
+  }
+  static float A[128][8], B[256][8];
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 8; ++k) A[m][k] = umma_operand_tf32(a_desc, m, k);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 8; ++k) B[n][k] = umma_operand_tf32(b_desc, n, k);
+  const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xFFFFu;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? emu::from_bits<float>(emu_tmem[lane0 + m][col0 + n]) : 0.f;
+      for (int k = 0; k < 8; ++k) acc += A[m][k] * B[n][k];
       emu_tmem[lane0 + m][col0 + n] = (uint32_t)emu::to_bits(acc);
     }
 }

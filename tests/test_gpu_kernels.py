@@ -279,6 +279,70 @@ def test_conv_fwd_dgrad_wgrad(F, gemm_kernel, B, T, Cin, Cout, k, d, pad):
     assert rel_l2(dw.cpu(), wr.grad.permute(2, 0, 1)) < 2e-5
 
 
+def _tf32(x):
+    """fp32 with the mantissa cut to 10 bits, as kind::tf32 reads its operands"""
+    return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,k,d,pad", [(2, 150, 64, 256, 1, 1, (0, 0)), (2, 140, 128, 224, 5, 1, (2, 2)), (2, 150, 64, 96, 7, 2, (6, 6)),
+                                                  (3, 203, 192, 384, 3, 1, (1, 1)), (1, 130, 72, 40, 3, 1, (1, 1)), (2, 260, 160, 29, 1, 1, (0, 0))])
+def test_conv_fp32_operands_tf32(F, B, T, Cin, Cout, k, d, pad):
+    """the fp32-faithful mode (w2l_conv_desc::x_dtype = F32): fp32 activations / weights in memory, tcgen05 kind::tf32, fp32
+    accumulation -- forward, backward-data (transposed fp32 weight shadow) and the weight gradient over transposed operands
+    (w2l_conv1d_wgrad_t), against torch fp32 on operands cut to tf32 (rel-L2 <= 2e-5: only the summation order differs) and against
+    plain fp32 (<= 1.5e-3: the tf32 rounding of the operands, the stated tolerance of this mode)"""
+    g = torch.Generator().manual_seed(B * T + Cin + k + 1)
+    pl, pr = pad
+    x = torch.randn(B, T, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    T_out = T + pl + pr - d * (k - 1)
+    cout_pad = max(64, (Cout + 15) // 16 * 16)
+    ldy = (Cout + 7) // 8 * 8
+    dy = torch.randn(B, Cout, T_out, generator=g)
+
+    def reference(xv, wv, dyv):
+        xr, wr = xv.transpose(1, 2).clone().requires_grad_(True), wv.clone().requires_grad_(True)
+        y = TF.conv1d(TF.pad(xr, (pl, pr)), wr, None, dilation=d)
+        y.backward(dyv)
+        return y.detach().transpose(1, 2), xr.grad.transpose(1, 2), wr.grad.permute(2, 0, 1)
+
+    y_t, dx_t, dw_t = reference(_tf32(x), _tf32(w), _tf32(dy))          # what the tensor core computes, up to summation order
+    y_f, dx_f, dw_f = reference(x, w, dy)
+    xc = x.cuda()
+    wc = torch.zeros(k, cout_pad, Cin, device="cuda")
+    wc[:, :Cout] = w.permute(2, 0, 1).cuda()
+    # ---- forward, fp32 output + bias + BatchNorm statistics of the (unrounded) fp32 output
+    desc = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, ldy, F.DT_F32, F.ACT_NONE, x_dtype=F.DT_F32)
+    y = torch.zeros(B, T_out, ldy, device="cuda")
+    st = torch.zeros(2 * Cout, device="cuda")
+    F.conv1d_fwd(xc, wc, desc, y, bn_stats=st)
+    got = y[:, :, :Cout].cpu()
+    assert rel_l2(got, y_t) < 2e-5, rel_l2(got, y_t)
+    assert rel_l2(got, y_f) < 1.5e-3, rel_l2(got, y_f)
+    yd = got.double().reshape(-1, Cout)
+    assert torch.allclose(st[:Cout].cpu().double(), yd.sum(0), rtol=1e-4, atol=1e-3) and torch.allclose(st[Cout:].cpu().double(), (yd * yd).sum(0), rtol=1e-4)
+    y2 = torch.zeros(B, T_out, ldy, device="cuda")
+    F.conv1d_fwd(xc, wc, desc, y2, bias=bias.cuda())
+    assert rel_l2(y2[:, :, :Cout].cpu(), y_t + bias) < 2e-5
+    # ---- backward-data over the transposed, tap-reversed fp32 weights: dx fp32
+    dyc = torch.zeros(B, T_out, cout_pad, device="cuda")
+    dyc[:, :, :Cout] = dy.transpose(1, 2).cuda()
+    desc3 = F.make_desc(B, T_out, Cin, Cout, cout_pad, k, d, T, -pl, T_out, 0, cout_pad, x_dtype=F.DT_F32)
+    cin_pad = (Cin + 15) // 16 * 16
+    wt = torch.zeros(k, cin_pad, cout_pad, device="cuda")
+    wt[:, :Cin, :Cout] = w.permute(2, 1, 0).flip(0).cuda()
+    dx = torch.full((B, T, Cin), 7.0, device="cuda")
+    F.conv1d_dgrad_wt(dyc, wt, desc3, dx)
+    assert rel_l2(dx.cpu(), dx_t) < 2e-5 and rel_l2(dx.cpu(), dx_f) < 1.5e-3
+    # ---- weight gradient: operands transposed to [B, C, rows] inside conv1d_wgrad_t (time contiguous: K-major like the forward GEMM)
+    xT = F.tm_to_ct_f32(xc, T, lead=3)
+    assert torch.equal(xT[:, :, 3:T + 3].cpu(), x.transpose(1, 2)) and (xT[:, :, :3] == 0).all()
+    dw = torch.full((k, Cout, Cin), 3.0, device="cuda")
+    F.conv1d_wgrad_t(dyc, xc, desc3, dw)
+    assert rel_l2(dw.cpu(), dw_t) < 2e-5 and rel_l2(dw.cpu(), dw_f) < 1.5e-3
+
+
 @pytest.mark.parametrize("B,T,C,Co,k,d", [(3, 200, 64, 128, 5, 1), (5, 131, 128, 64, 7, 2), (2, 750, 256, 256, 11, 1)])
 def test_conv_dgrad_flat_prepadded(F, gemm_kernel, B, T, C, Co, k, d):
     """Wav2Letter layout: the input carries its own halo (x_rows = T + (k-1)d), dz is stored with the input's row pitch and zero

@@ -104,6 +104,66 @@ def check_w2l_golden(pkg, g):
     assert model.scaling_factor == int(g["scaling_factor"])
 
 
+# fp32-faithful mode (precision="tf32"): activations / weights / gradients fp32 in memory, tf32 multiplies, fp32 accumulation.
+# Bounds against the UNMODIFIED reference's frozen fp32 outputs (host emulation of the same kernels: out 1.2e-4, loss 1.4e-5, worst
+# parameter gradient 5.5e-2 -- the first layer's weights of this freshly initialised BatchNorm stack, where the bf16 path is
+# allowed 0.35 -- running statistics 1.1e-3): logits 20x, loss 200x, gradients 3.5x inside the bf16 path's bounds
+TOL_TF32 = {"out": 1e-3, "loss": 1e-4, "grad": 1e-1, "running": 5e-3}
+
+
+def test_w2l_golden_fp32_faithful_mode(pkg, golden):
+    """SURVEY 8c asks for logits / gradients vs torch fp32: the same fixture as above with the model in precision='tf32' (fp32 storage,
+    kind::tf32 GEMMs incl. the weight gradient over transposed operands, fp32 BatchNorm / activation passes), train step + eval"""
+    from wav2letter_pytorch_b200.wav2letter import Wav2Letter
+    g = golden("w2l_small")
+    layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
+    cfg = _cfg(pkg, layers, len(layers))
+    cfg["precision"] = "tf32"
+    model = Wav2Letter(cfg)
+    assert model.precision == "tf32" and all(m.conv1.f32 for m in model.conv1ds.children())
+    head = "conv1d_%d" % len(layers)
+    _load_sd(model, g, "sd0:")
+    model.cuda().train()
+    x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
+    tg, tl = torch.from_numpy(g["tg"]).cuda(), torch.from_numpy(g["tl"]).cuda()
+    out, ol = model(x, il)
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    loss.backward()
+    report = {"out": rel_l2(out, g["train:out"]), "loss": abs(loss.item() - float(g["train:loss"])) / abs(float(g["train:loss"]))}
+    assert out.dtype == torch.float32 and np.array_equal(ol.cpu().numpy(), g["train:out_len"])
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        ref = g["train:grad:" + name]
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == torch.float32, name
+        if name.endswith("conv1.bias") and head not in name:
+            assert p.grad.abs().max().item() == 0.0
+            continue
+        e = rel_l2(p.grad, ref)
+        if e > worst[1]:
+            worst = (name, e)
+    report["grad"] = worst[1]
+    sd1 = {k[4:]: g[k] for k in g.files if k.startswith("sd1:")}
+    run = 0.0
+    for k, v in model.state_dict().items():
+        if "running" in k:
+            run = max(run, rel_l2(v, sd1[k]))
+    report["running"] = run
+    print("tf32 mode vs the reference fixture:", json.dumps(report), "worst gradient:", worst[0])
+    for key, bound in TOL_TF32.items():
+        assert report[key] < bound, (key, report, worst)
+    _load_sd(model, g, "sd1:")
+    model.eval()
+    with torch.no_grad():
+        o, _ = model(x, il)
+    assert rel_l2(o, g["eval:out"]) < TOL_TF32["out"]
+    # end-to-end transcripts of this random-init model (argmax near-ties everywhere): >= 95 % of the characters agree with the
+    # reference's (bit-exactness holds on identical scores, test_decode_golden)
+    import difflib
+    dec = model.ctc_decoder.decode(o, torch.from_numpy(g["eval:out_len"]).cuda())
+    for a, b in zip(dec, [str(s) for s in g["eval:decoded"]]):
+        assert difflib.SequenceMatcher(None, a, b).ratio() >= 0.95, (a, b)
+
+
 def test_conv1d_block_golden(pkg, golden):
     """Conv1dBlock(64, 256, (11,), 2): the reference's first layer, through the standalone NCW interface."""
     from wav2letter_pytorch_b200.wav2letter import Conv1dBlock

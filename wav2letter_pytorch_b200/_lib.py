@@ -95,7 +95,7 @@ c_ptr, c_size = ctypes.c_void_p, ctypes.c_size_t
 class ConvDesc(ctypes.Structure):
     """Mirror of w2l_conv_desc."""
     _fields_ = [(n, c_i32) for n in ("B", "T_out", "Cin", "Cout", "Cout_pad", "k", "dilation", "x_rows", "x_row_offset",
-                                     "y_rows", "y_row_offset", "ldy", "y_dtype", "act")]
+                                     "y_rows", "y_row_offset", "ldy", "y_dtype", "act", "x_dtype")]
 
 
 # name -> (restype, argtypes); every symbol declared in include/w2l_sm100.h appears here
@@ -125,6 +125,13 @@ SIGNATURES = {
     "w2l_pack_wt": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "w2l_conv1d_wgrad_splits": (c_i32, [ctypes.POINTER(ConvDesc)]),
     "w2l_conv1d_wgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_im2col_ncw_f32": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr, c_ptr]),
+    "w2l_reflect_halo_f32": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_log_softmax_bwd_f32": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
+    "w2l_colsum_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
+    "w2l_pack_wt_f32": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_conv1d_wgrad_t": (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
+    "w2l_tm_to_ct_f32": (c_i32, [c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr]),
     "w2l_depthwise_fwd": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_depthwise_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr, c_ptr]),
     "w2l_depthwise_dgrad_strided": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),

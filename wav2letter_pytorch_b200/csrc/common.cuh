@@ -123,6 +123,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 operands read as tf32 (10-bit mantissa), fp32 accumulate: K = 8 per instruction (32 bytes per row, as 16 bf16)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -217,11 +225,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
-__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+// (tf32 = true: kind::tf32, both operand formats TF32)
+__host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major, bool tf32 = false) {
   uint32_t d = 0;
   d |= 1u << 4;                       // C format: F32
-  d |= 1u << 7;                       // A format: BF16
-  d |= 1u << 10;                      // B format: BF16
+  d |= (tf32 ? 2u : 1u) << 7;         // A format: BF16 (1) / TF32 (2)
+  d |= (tf32 ? 2u : 1u) << 10;        // B format
   d |= (a_mn_major ? 1u : 0u) << 15;  // A major
   d |= (b_mn_major ? 1u : 0u) << 16;  // B major
   d |= (uint32_t)(N >> 3) << 17;

@@ -89,6 +89,16 @@ struct GemmParams {
   int32_t c2_ngroup;        // N tiles that run side by side on the same activation rows (their weight slices stay in L2 together)
   int32_t c2_k;             // wgrad pair kernel: the real tap count (p.k then counts tap PAIRS)
   int32_t c2_npad;          // fwd-kind pair kernel: padded column count (the last N tile covers [.., c2_npad))
+  // fp32-faithful mode (w2l_conv_desc::x_dtype == F32): operands are fp32 in memory, multiplied as tf32 (kind::tf32, K = 8 per
+  // MMA).  A 128-byte swizzle row then holds 32 elements, so a K-step covers kblk = 32 channels (fwd/dgrad) or 32 rows (wgrad);
+  // every byte offset of the pipeline (stage sizes, 32 bytes per MMA along K) is the same as with bf16.
+  int32_t tf32;
+  int32_t kblk;             // elements of the contraction per K-step: 64 (bf16) or 32 (tf32)
+  int32_t wg_kmajor;        // wgrad over TRANSPOSED operands dyT [B, Cout, T], xT [B, Cin, rows] (time contiguous): both K-major
+  // ... where TMA wants the innermost (time) coordinate 16-byte aligned: tap j reads x at time offset o = off + j*d, so the caller
+  // supplies xT DELAYED by s = (-o) mod 4 rows (xT_s[b, ci, u] = x[b, u - s, ci], s zeros in front) and the load uses map tmX[s] at
+  // coordinate t0 + o + s, a multiple of 4; coordinates below 0 read as zero, which is the conv's zero padding
+  CUtensorMap tmX[4];
 };
 
 // A unit of work: (part of) one output tile.  FWD/DGRAD: whole tiles, statically strided over the CTAs; the K loop
@@ -219,7 +229,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
     float s1[32], s2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float q = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+      const float q = !row_ok ? 0.f : p.y_dtype == W2L_DTYPE_BF16 ? __bfloat162float(__float2bfloat16_rn(v[i])) : v[i];
       s1[i] = q;
       s2[i] = q * q;
     }
@@ -286,7 +296,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   constexpr bool kAMN = (MODE == MODE_WGRAD);
   constexpr bool kBMN = (MODE != MODE_FWD);
   const int b_chunks = (p.BN + 63) >> 6;
-  const uint32_t stage_tx = kABytes + ((kBMN || (p.dbg & 1)) ? (uint32_t)b_chunks * 8192u : (uint32_t)p.BN * 128u);
+  const bool b_mn = kBMN && !p.wg_kmajor, a_mn = kAMN && !p.wg_kmajor;      // kernel-uniform
+  const uint32_t stage_tx = kABytes + ((b_mn || (p.dbg & 1)) ? (uint32_t)b_chunks * 8192u : (uint32_t)p.BN * 128u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -358,9 +369,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           if (MODE == MODE_WGRAD) {
-            const int b = it / p.kc_steps, t0 = (it - b * p.kc_steps) * kBlockK;
+            const int b = it / p.kc_steps, t0 = (it - b * p.kc_steps) * p.kblk;
             const int xr = t0 + p.b_row_off + u.j * p.dil;
-            if (p.mn4d) {       // one TMA op per operand: box (64 ch, 64 rows, chunks, 1) lands as [chunk][row][64]
+            if (p.wg_kmajor) {  // transposed operands: the contraction (time) is the innermost coordinate of both maps
+              const int o = p.b_row_off + u.j * p.dil, sft = (-o) & 3;       // two's complement: o + sft is a multiple of 4 for o < 0 too
+              tma_load_3d(sa, &p.tmA, &full_bar[stage], t0, u.m0, b);
+              tma_load_3d(sb, &p.tmX[sft], &full_bar[stage], t0 + o + sft, u.n0, b);
+            } else if (p.mn4d) {       // one TMA op per operand: box (64 ch, 64 rows, chunks, 1) lands as [chunk][row][64]
               tma_load_4d(sa, &p.tmA, &full_bar[stage], 0, t0, u.m0 >> 6, b);
               tma_load_4d(sb, &p.tmB, &full_bar[stage], 0, xr, u.n0 >> 6, b);
             } else {
@@ -370,12 +385,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
             }
           } else {
             const int j = it / p.kc_steps, kc = it - j * p.kc_steps;
-            tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * kBlockK, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
+            tma_load_3d(sa, &p.tmA, &full_bar[stage], kc * p.kblk, u.m0 + p.a_row_off + j * p.a_tap_step, u.b);
             if (MODE == MODE_FWD) {
               if (p.dbg & 1) {
-                for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0 + c * 64, j);
+                for (int c = 0; c < b_chunks; ++c) tma_load_3d(sb + c * 8192, &p.tmB, &full_bar[stage], kc * p.kblk, u.n0 + c * 64, j);
               } else {
-                tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * kBlockK, u.n0, j);
+                tma_load_3d(sb, &p.tmB, &full_bar[stage], kc * p.kblk, u.n0, j);
               }
             } else {
               for (int c = 0; c < b_chunks; ++c)
@@ -392,11 +407,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, kAMN, kBMN);
-      constexpr uint32_t a_kstep = kAMN ? 2048u : 32u;   // bytes per UMMA_K (16 elements of K)
-      constexpr uint32_t b_kstep = kBMN ? 2048u : 32u;
-      constexpr uint32_t a_lbo = kAMN ? 8192u : 16u;
-      constexpr uint32_t b_lbo = kBMN ? 8192u : 16u;
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.BN, a_mn, b_mn, p.tf32 != 0);
+      const uint32_t a_kstep = a_mn ? 2048u : 32u;       // bytes per UMMA_K (16 bf16 / 8 tf32 elements of K)
+      const uint32_t b_kstep = b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = b_mn ? 8192u : 16u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -464,7 +479,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
           for (int kk = 0; kk < kBlockK / 16; ++kk) {
             const uint64_t adesc = make_smem_desc(a_addr + kk * a_kstep, a_lbo, 1024u);
             const uint64_t bdesc = make_smem_desc(b_addr + kk * b_kstep, b_lbo, 1024u);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+            if (p.tf32)
+              umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
+            else
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
             accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);
@@ -1062,6 +1080,7 @@ template <int MODE>
 static int launch_gemm(const GemmParams& p_in, cudaStream_t st, int grid_override = 0) {
   GemmParams p = p_in;
   if (p.ring_bytes == 0) p.ring_bytes = kStages * kStageBytes;      // launchers that do not plan rings: the A+B stage ring
+  if (p.kblk == 0) p.kblk = kBlockK;                                // bf16 launchers that never set the operand type
   static bool configured = false;
   if (!configured) {
     W2L_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemMax));
@@ -1112,6 +1131,12 @@ static int launch_gemm_cg2(const GemmParams& p, cudaStream_t st) {
   if (pairs < 1) return W2L_OK;
   conv_gemm_cg2_kernel<<<2 * pairs, kGemmThreads, kC2Smem, st>>>(p);
   return after_launch("conv_gemm_cg2_kernel");
+}
+
+// operand type of a launch from the descriptor: bf16 (default) or fp32 storage multiplied as tf32
+static void set_operand_type(GemmParams& p, const w2l_conv_desc* d) {
+  p.tf32 = d->x_dtype == W2L_DTYPE_F32;
+  p.kblk = p.tf32 ? 32 : kBlockK;
 }
 
 static int check_desc(const w2l_conv_desc* d, const char* who) {
@@ -1201,22 +1226,24 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
     const char* e = getenv("W2L_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  const bool cg2 = cg2_wanted() && !(p.dbg & 1);
-  if (!cg2) plan_rings(p, d->k, d->dilation, true);
+  set_operand_type(p, d);
+  const uint64_t eb = p.tf32 ? 4 : 2;                   // bytes per operand element
+  const bool cg2 = cg2_wanted() && !(p.dbg & 1) && !p.tf32;
+  if (!cg2 && !p.tf32) plan_rings(p, d->k, d->dilation, true);
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->x_rows, (uint64_t)d->B};
-    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->x_rows * d->Cin * 2};
-    uint32_t box[3] = {kBlockK, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
-    rc = make_tensor_map(&p.tmA, x, 2, 3, dims, str, box, true);
+    uint64_t str[2] = {(uint64_t)d->Cin * eb, (uint64_t)d->x_rows * d->Cin * eb};
+    uint32_t box[3] = {(uint32_t)p.kblk, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, x, (int)eb, 3, dims, str, box, true);
     if (rc) return rc;
   }
   p.BN = cg2 ? cg2_bn(d->Cout_pad) : pick_bn(d->Cout_pad, 16);
   p.c2_npad = d->Cout_pad;
   {
     uint64_t dims[3] = {(uint64_t)d->Cin, (uint64_t)d->Cout_pad, (uint64_t)d->k};
-    uint64_t str[2] = {(uint64_t)d->Cin * 2, (uint64_t)d->Cout_pad * d->Cin * 2};
-    uint32_t box[3] = {kBlockK, cg2 ? (uint32_t)p.BN / 2 : (p.dbg & 1) ? 64u : (uint32_t)p.BN, 1};
-    rc = make_tensor_map(&p.tmB, w, 2, 3, dims, str, box, true);
+    uint64_t str[2] = {(uint64_t)d->Cin * eb, (uint64_t)d->Cout_pad * d->Cin * eb};
+    uint32_t box[3] = {(uint32_t)p.kblk, cg2 ? (uint32_t)p.BN / 2 : (p.dbg & 1) ? 64u : (uint32_t)p.BN, 1};
+    rc = make_tensor_map(&p.tmB, w, (int)eb, 3, dims, str, box, true);
     if (rc) return rc;
   }
   p.B = d->B;
@@ -1224,7 +1251,7 @@ int w2l_conv1d_fwd(const void* x, const void* w, const float* bias, const float*
   p.n_tiles = (d->Cout_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
-  p.kc_steps = (d->Cin + kBlockK - 1) / kBlockK;
+  p.kc_steps = (d->Cin + p.kblk - 1) / p.kblk;
   p.a_row_off = d->x_row_offset;
   p.a_tap_step = d->dilation;
   p.M_valid = d->T_out;
@@ -1277,6 +1304,7 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
   int rc = check_desc(d, "conv1d_dgrad");
   if (rc) return rc;
   W2L_REQUIRE(dy && w && dx, "conv1d_dgrad: null pointer");
+  W2L_REQUIRE(d->x_dtype == W2L_DTYPE_BF16, "conv1d_dgrad: bf16 operands only (fp32 operands: w2l_conv1d_dgrad_wt)");
   W2L_REQUIRE(d->Cout_pad >= 64, "conv1d_dgrad: Cout_pad=%d must be >= 64 (pad dy/weights)", d->Cout_pad);
   W2L_REQUIRE(d->ldy >= d->Cout_pad, "conv1d_dgrad: dy row pitch %d < Cout_pad %d", d->ldy, d->Cout_pad);
   GemmParams p;
@@ -1331,17 +1359,19 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   W2L_REQUIRE(d->ldy >= d->Cout, "conv1d_dgrad_wt: dy row pitch %d < Cout %d", d->ldy, d->Cout);
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const bool cg2 = cg2_wanted();
-  if (!cg2) plan_rings(p, d->k, d->dilation, true);
+  set_operand_type(p, d);
+  const uint64_t eb = p.tf32 ? 4 : 2;
+  const bool cg2 = cg2_wanted() && !p.tf32;
+  if (!cg2 && !p.tf32) plan_rings(p, d->k, d->dilation, true);
   {
     // dy rows normally carry Cout_pad columns (zero padded); a row of only Cout columns (a hidden width that is a multiple of 8 but
     // not of 16) is declared as such, and the tail of the last contraction chunk reads as zero (TMA out-of-bounds fill)
-    const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (int64_t)d->y_row_offset * d->ldy;
+    const char* base = reinterpret_cast<const char*>(dy) + (int64_t)d->y_row_offset * d->ldy * (int64_t)eb;
     const int a_cols = d->ldy >= d->Cout_pad ? d->Cout_pad : d->Cout;
     uint64_t dims[3] = {(uint64_t)a_cols, (uint64_t)d->T_out, (uint64_t)d->B};
-    uint64_t str[2] = {(uint64_t)d->ldy * 2, (uint64_t)d->y_rows * d->ldy * 2};
-    uint32_t box[3] = {kBlockK, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
-    rc = make_tensor_map(&p.tmA, base, 2, 3, dims, str, box, true);
+    uint64_t str[2] = {(uint64_t)d->ldy * eb, (uint64_t)d->y_rows * d->ldy * eb};
+    uint32_t box[3] = {(uint32_t)p.kblk, p.slab_rows ? (uint32_t)p.slab_rows : (uint32_t)kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, base, (int)eb, 3, dims, str, box, true);
     if (rc) return rc;
   }
   const int n_pad = (d->Cin + 15) / 16 * 16;
@@ -1349,9 +1379,9 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   p.c2_npad = n_pad;
   {
     uint64_t dims[3] = {(uint64_t)d->Cout_pad, (uint64_t)n_pad, (uint64_t)d->k};
-    uint64_t str[2] = {(uint64_t)d->Cout_pad * 2, (uint64_t)n_pad * d->Cout_pad * 2};
-    uint32_t box[3] = {kBlockK, cg2 ? (uint32_t)p.BN / 2 : (uint32_t)p.BN, 1};
-    rc = make_tensor_map(&p.tmB, wt, 2, 3, dims, str, box, true);
+    uint64_t str[2] = {(uint64_t)d->Cout_pad * eb, (uint64_t)n_pad * d->Cout_pad * eb};
+    uint32_t box[3] = {(uint32_t)p.kblk, cg2 ? (uint32_t)p.BN / 2 : (uint32_t)p.BN, 1};
+    rc = make_tensor_map(&p.tmB, wt, (int)eb, 3, dims, str, box, true);
     if (rc) return rc;
   }
   p.B = d->B;
@@ -1359,14 +1389,14 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   p.n_tiles = (n_pad + p.BN - 1) / p.BN;
   p.k = d->k;
   p.dil = d->dilation;
-  p.kc_steps = (d->Cout_pad + kBlockK - 1) / kBlockK;
+  p.kc_steps = (d->Cout_pad + p.kblk - 1) / p.kblk;
   p.a_row_off = -d->x_row_offset - (d->k - 1) * d->dilation;
   p.a_tap_step = d->dilation;
   p.M_valid = d->x_rows;
   p.N_valid = d->Cin;
   p.num_tiles = p.m_tiles * p.n_tiles * p.B;
   p.act = W2L_ACT_NONE;
-  p.y_dtype = W2L_DTYPE_BF16;
+  p.y_dtype = p.tf32 ? W2L_DTYPE_F32 : W2L_DTYPE_BF16;    // dx has the operand type
   p.y = dx;
   p.y_batch_stride = (int64_t)d->x_rows * d->Cin;
   p.y_row_off = 0;
@@ -1390,11 +1420,77 @@ int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {
   return zero ? 2 : 1;
 }
 
+int w2l_conv1d_wgrad_t(const float* dyT, int64_t dy_pitch, const float* const* xT_shifted, int64_t x_pitch, float* dw,
+                       const w2l_conv_desc* d, void* stream) {
+  // fp32-faithful weight gradient over TRANSPOSED fp32 operands (time contiguous), so that both are K-major like the forward
+  // GEMM (an MN-major tf32 operand would need the 32-byte-atom swizzle):
+  //   dw[j, co, ci] (+)= sum_b sum_t dyT[b, co, t] * xT[b, ci, t + x_row_offset + j*dilation]
+  // xT_shifted[s] (HOST array of 4 device pointers) = xT delayed by s rows, xT_s[b, ci, u] = x[b, u - s, ci] with s zeros in front,
+  // each with pitch x_pitch >= x_rows + s; only the residues s = (-(x_row_offset + j*dilation)) mod 4 that occur need to be non-null.
+  using namespace w2l;
+  int rc = check_desc(d, "conv1d_wgrad_t");
+  if (rc) return rc;
+  W2L_REQUIRE(dyT && xT_shifted && dw, "conv1d_wgrad_t: null pointer");
+  for (int j = 0; j < d->k; ++j)
+    W2L_REQUIRE(xT_shifted[(-(d->x_row_offset + j * d->dilation)) & 3] != nullptr, "conv1d_wgrad_t: tap %d needs the copy delayed by %d rows",
+                j, (-(d->x_row_offset + j * d->dilation)) & 3);
+  W2L_REQUIRE(d->x_dtype == W2L_DTYPE_F32, "conv1d_wgrad_t: fp32 operands only (x_dtype)");
+  W2L_REQUIRE(dy_pitch >= d->T_out && x_pitch >= d->x_rows + 3 && dy_pitch % 4 == 0 && x_pitch % 4 == 0,
+              "conv1d_wgrad_t: pitches must cover the rows and be multiples of 4 floats (dy_pitch %lld, x_pitch %lld)",
+              (long long)dy_pitch, (long long)x_pitch);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_operand_type(p, d);
+  p.wg_kmajor = 1;
+  const int n_pad = (d->Cin + 15) / 16 * 16;
+  p.BN = pick_bn(n_pad, 16);
+  {
+    uint64_t dims[3] = {(uint64_t)d->T_out, (uint64_t)d->Cout, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)dy_pitch * 4, (uint64_t)d->Cout * dy_pitch * 4};
+    uint32_t box[3] = {(uint32_t)p.kblk, kBlockM, 1};
+    rc = make_tensor_map(&p.tmA, dyT, 4, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.tmB = p.tmA;                                                   // (prefetched by the kernel; never loaded through in this mode)
+  for (int sft = 0; sft < 4; ++sft) {
+    if (!xT_shifted[sft]) {
+      p.tmX[sft] = p.tmA;
+      continue;
+    }
+    uint64_t dims[3] = {(uint64_t)(d->x_rows + sft), (uint64_t)d->Cin, (uint64_t)d->B};
+    uint64_t str[2] = {(uint64_t)x_pitch * 4, (uint64_t)d->Cin * x_pitch * 4};
+    uint32_t box[3] = {(uint32_t)p.kblk, (uint32_t)p.BN, 1};
+    rc = make_tensor_map(&p.tmX[sft], xT_shifted[sft], 4, 3, dims, str, box, true);
+    if (rc) return rc;
+  }
+  p.B = d->B;
+  p.m_tiles = (d->Cout + kBlockM - 1) / kBlockM;
+  p.n_tiles = (n_pad + p.BN - 1) / p.BN;
+  p.k = d->k;
+  p.dil = d->dilation;
+  p.kc_steps = (d->T_out + p.kblk - 1) / p.kblk;
+  p.b_row_off = d->x_row_offset;
+  p.M_valid = d->Cout;
+  p.N_valid = d->Cin;
+  p.num_tiles = p.k * p.m_tiles * p.n_tiles;
+  p.y = dw;
+  p.ldy = d->Cin;
+  p.dw_tap_stride = (int64_t)d->Cout * d->Cin;
+  // stream-K plan over the single-CTA grid; dw must be ZERO on entry (tiles shared between CTAs are accumulated with atomics)
+  const int64_t iters = (int64_t)p.B * p.kc_steps;
+  int64_t grid = gemm_sms();
+  if ((int64_t)p.num_tiles * iters / grid < 32) grid = (int64_t)p.num_tiles * iters / 32 > 0 ? (int64_t)p.num_tiles * iters / 32 : 1;
+  p.wg_rounds = (int32_t)(p.num_tiles / grid);
+  p.splits = 2;
+  return launch_gemm<MODE_WGRAD>(p, (cudaStream_t)stream, (int)grid);
+}
+
 int w2l_conv1d_wgrad(const void* dy, const void* x, float* dw, const w2l_conv_desc* d, void* stream) {
   using namespace w2l;
   int rc = check_desc(d, "conv1d_wgrad");
   if (rc) return rc;
   W2L_REQUIRE(dy && x && dw, "conv1d_wgrad: null pointer");
+  W2L_REQUIRE(d->x_dtype == W2L_DTYPE_BF16, "conv1d_wgrad: bf16 operands only (fp32 operands: w2l_conv1d_wgrad_t)");
   W2L_REQUIRE(d->ldy >= 64 && d->ldy % 8 == 0, "conv1d_wgrad: dy row pitch %d must be >= 64 and a multiple of 8", d->ldy);
   GemmParams p;
   memset(&p, 0, sizeof(p));

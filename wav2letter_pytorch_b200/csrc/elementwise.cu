@@ -55,6 +55,46 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   q.w = pack_bf16x2(v[6], v[7]);
   return q;
 }
+// scalar store of one value into bf16 / fp32 activation storage
+__device__ __forceinline__ void store_act(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store_act(float* p, float v) { *p = v; }
+__device__ __forceinline__ float load_act(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float load_act(const float* p) { return *p; }
+
+// 8 consecutive channels of one row as a thread stages them: one 16-byte vector of bf16, or two of fp32 (the fp32-faithful mode,
+// W2L_STORE_F32: activations stay fp32 between the tf32 GEMMs).  Every BatchNorm / activation pass is written once over this.
+template <typename TA>
+struct Vec8;
+template <>
+struct Vec8<__nv_bfloat16> {
+  uint4 q;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const { unpack8(q, v); }
+  __device__ __forceinline__ void pack(const float (&v)[8]) { q = pack8(v); }
+  __device__ __forceinline__ void zero() { q = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = q; }
+};
+template <>
+struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  __device__ __forceinline__ void pack(const float (&v)[8]) {
+    a = make_float4(v[0], v[1], v[2], v[3]);
+    b = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *(reinterpret_cast<float4*>(p) + 1) = b;
+  }
+};
 __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -64,7 +104,8 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
 
 // ---------------------------------------------------------------- NCW fp32 -> (unfolded, padded) time-major bf16
 // block: 32 output rows of one utterance; the needed input span is staged (transposed) in shared memory.
-__global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int F, int T, int rows, int k,
+template <typename TOut>
+__global__ void im2col_ncw_kernel(const float* __restrict__ x, TOut* __restrict__ out, int F, int T, int rows, int k,
                                   int stride, int dil, int pad_left, int pad_mode, const int32_t* __restrict__ lens, int span,
                                   int pitch) {
   extern __shared__ float tile[];   // [F][pitch]
@@ -89,8 +130,8 @@ __global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __
   }
   __syncthreads();
   const int KF = k * F;
-  __nv_bfloat16* ob = out + ((int64_t)b * rows + r0) * KF;
-  if ((F & 7) == 0) {                     // 16-byte stores: one thread packs 8 consecutive features of one (row, tap)
+  TOut* ob = out + ((int64_t)b * rows + r0) * KF;
+  if ((F & 7) == 0 && sizeof(TOut) == 2) {   // 16-byte stores: one thread packs 8 consecutive features of one (row, tap)
     const int F8 = F >> 3, KF8 = k * F8;
     for (int i = threadIdx.x; i < nrows * KF8; i += blockDim.x) {
       const int r = i / KF8, c = i - r * KF8;
@@ -101,14 +142,14 @@ __global__ void im2col_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __
       q.y = pack_bf16x2(src[2 * pitch], src[3 * pitch]);
       q.z = pack_bf16x2(src[4 * pitch], src[5 * pitch]);
       q.w = pack_bf16x2(src[6 * pitch], src[7 * pitch]);
-      *reinterpret_cast<uint4*>(ob + (int64_t)r * KF + j * F + f0) = q;
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ob) + (int64_t)r * KF + j * F + f0) = q;
     }
     return;
   }
   for (int i = threadIdx.x; i < nrows * KF; i += blockDim.x) {
     const int r = i / KF, c = i - r * KF;
     const int j = c / F, f = c - j * F;
-    ob[i] = __float2bfloat16_rn(tile[f * pitch + r * stride + j * dil]);
+    store_act(ob + i, tile[f * pitch + r * stride + j * dil]);
   }
 }
 
@@ -159,7 +200,7 @@ __global__ void col2im_tm_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bf
 // time-major (bf16 | f32) -> NCW fp32, 32x32 shared-memory transpose
 template <typename TIn>
 __global__ void tm_to_ncw_kernel(const TIn* __restrict__ x, float* __restrict__ out, int T, int C, int64_t x_batch_stride,
-                                 int x_row_offset, int ld) {
+                                 int x_row_offset, int ld, int out_pitch) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const TIn* xb = x + (int64_t)b * x_batch_stride + (int64_t)x_row_offset * ld;
@@ -170,7 +211,7 @@ __global__ void tm_to_ncw_kernel(const TIn* __restrict__ x, float* __restrict__ 
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, t = t0 + threadIdx.x;
-    if (c < C && t < T) out[((int64_t)b * C + c) * T + t] = tile[threadIdx.x][i];
+    if (c < C && t < T) out[((int64_t)b * C + c) * out_pitch + t] = tile[threadIdx.x][i];
   }
 }
 
@@ -261,8 +302,8 @@ constexpr int kBnBwdCtasPerSm = 2;   // backward passes: 3 streams + 5 per-chann
 constexpr int kRowGroup = 4;         // consecutive rows a thread stages together: all their 16-byte loads are issued before any is used
 
 struct BnFwdArgs {
-  const __nv_bfloat16* z;
-  const __nv_bfloat16* res;
+  const void* z;               // activations: bf16, or fp32 under W2L_STORE_F32 (the kernels' TA)
+  const void* res;
   const float* scale;          // given affine (eval / separately finalised statistics); unused when stats != null
   const float* shift;
   const float* res_scale;
@@ -279,7 +320,7 @@ struct BnFwdArgs {
   float* running_var;
   int64_t* num_batches_tracked;
   float* fin;                  // [4][C] scale, shift, mean, invstd
-  __nv_bfloat16* y;
+  void* y;
   int B, T, C, pl, pr;
   uint32_t keep_q;             // dropout: keep probability in units of 2^-kDropBits (0: no dropout)
   float inv_keep;              // 2^kDropBits / keep_q
@@ -292,9 +333,9 @@ struct BnFwdArgs {
 };
 
 struct BnBwdArgs {
-  const __nv_bfloat16* z;
-  const __nv_bfloat16* res;
-  const __nv_bfloat16* dyp;
+  const void* z;
+  const void* res;
+  const void* dyp;
   const float* scale;
   const float* shift;
   const float* res_scale;
@@ -304,8 +345,8 @@ struct BnBwdArgs {
   const float* gamma;
   float* red;                  // [2C] sum g, sum g*xhat: accumulated by the reduce pass (zero on entry), read by the apply pass
   float* red_out;              // apply pass: copy of red for the caller (dbeta, dgamma), so that `red` itself can be recycled
-  __nv_bfloat16* dz;
-  __nv_bfloat16* g_out;
+  void* dz;
+  void* g_out;
   int dz_rows;
   int B, T, C, pl, pr;
   uint32_t keep_q;
@@ -363,8 +404,11 @@ __device__ __forceinline__ void scale_for_dropout(float inv_keep, float (&sc)[8]
   }
 }
 
-template <int ACT, bool DROP, bool HAS_RES>
+template <typename TA, int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel(BnFwdArgs a) {
+  const TA* az = reinterpret_cast<const TA*>(a.z);
+  const TA* ares = reinterpret_cast<const TA*>(a.res);
+  TA* ay = reinterpret_cast<TA*>(a.y);
   zero_small(a.zero_ptr, a.zero_count);
   const int ny = blockDim.y;
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
@@ -415,20 +459,20 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
   scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
   const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
   const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);   // r_begin % kRowGroup == 0
-  constexpr int kBatch = HAS_RES ? 2 : kRowGroup;    // rows whose loads are in flight together (two streams with a residual)
+  constexpr int kBatch = (HAS_RES || sizeof(TA) == 4) ? 2 : kRowGroup;    // rows whose loads are in flight together (two streams with a residual)
   for (int r0 = r_begin + threadIdx.y * kRowGroup; r0 < r_end; r0 += ny * kRowGroup) {
     uint32_t keep = 0xFFFFFFFFu;
     if (DROP) keep = dropout_mask32(a.seed, (uint32_t)(r0 / kRowGroup), (uint32_t)cv, a.keep_q);
     int b = r0 / a.T, t = r0 - b * a.T;
 #pragma unroll
     for (int h = 0; h < kRowGroup; h += kBatch) {
-      uint4 zq[kBatch], rq[kBatch];
+      Vec8<TA> zq[kBatch], rq[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         if (r0 + h + u < r_end) {
           const int64_t e = (int64_t)(r0 + h + u) * a.C + c;
-          zq[u] = __ldg(reinterpret_cast<const uint4*>(a.z + e));
-          if (HAS_RES) rq[u] = __ldg(reinterpret_cast<const uint4*>(a.res + e));
+          zq[u].load(az + e);
+          if (HAS_RES) rq[u].load(ares + e);
         }
       }
 #pragma unroll
@@ -436,12 +480,12 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
         const int r = r0 + h + u;
         if (r < r_end) {
           float v[8];
-          unpack8(zq[u], v);
+          zq[u].unpack(v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], sc[i], sh[i]);
           if (HAS_RES) {
             float rv[8];
-            unpack8(rq[u], rv);
+            rq[u].unpack(rv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += fmaf(rv[i], rsc[i], rsh[i]);
           }
@@ -452,12 +496,13 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
             const bool on = !masked && (!DROP || ((keep >> (8 * (h + u) + i)) & 1u));
             v[i] = on ? act_fwd<ACT>(v[i]) : 0.f;
           }
-          const uint4 q = pack8(v);
-          __nv_bfloat16* yb = a.y + (int64_t)b * Tp * a.C + c;
-          *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + t) * a.C) = q;
-          if (t >= 1 && t <= a.pl) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl - t) * a.C) = q;                       // left mirror
+          Vec8<TA> q;
+          q.pack(v);
+          TA* yb = ay + (int64_t)b * Tp * a.C + c;
+          q.store(yb + (int64_t)(a.pl + t) * a.C);
+          if (t >= 1 && t <= a.pl) q.store(yb + (int64_t)(a.pl - t) * a.C);                       // left mirror
           const int d = a.T - 1 - t;
-          if (d >= 1 && d <= a.pr) *reinterpret_cast<uint4*>(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C) = q;              // right mirror
+          if (d >= 1 && d <= a.pr) q.store(yb + (int64_t)(a.pl + a.T - 1 + d) * a.C);              // right mirror
         }
         if (++t == a.T) {
           t = 0;
@@ -469,19 +514,20 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
 }
 
 // one staged row of the backward passes: conv output, residual, upstream gradient, dropout keep-bits -- all requested together
+template <typename TA>
 struct BwdRow {
-  uint4 z, r, d;
+  Vec8<TA> z, r, d;
   uint32_t bits;
   int len;
 };
 
-template <bool DROP, bool HAS_RES>
-__device__ __forceinline__ void load_bwd_row(const BnBwdArgs& a, int r, int b, int t, int cv, BwdRow& in) {
+template <typename TA, bool DROP, bool HAS_RES>
+__device__ __forceinline__ void load_bwd_row(const BnBwdArgs& a, int r, int b, int t, int cv, BwdRow<TA>& in) {
   const int c = cv * 8;
   const int64_t e = (int64_t)r * a.C + c;
-  in.z = __ldg(reinterpret_cast<const uint4*>(a.z + e));
-  if (HAS_RES) in.r = __ldg(reinterpret_cast<const uint4*>(a.res + e));
-  in.d = __ldg(reinterpret_cast<const uint4*>(a.dyp + ((int64_t)b * (a.pl + a.T + a.pr) + a.pl + t) * a.C + c));
+  in.z.load(reinterpret_cast<const TA*>(a.z) + e);
+  if (HAS_RES) in.r.load(reinterpret_cast<const TA*>(a.res) + e);
+  in.d.load(reinterpret_cast<const TA*>(a.dyp) + ((int64_t)b * (a.pl + a.T + a.pr) + a.pl + t) * a.C + c);
   // only LOADS here: a consumer of a load result between two rows' requests (the merge point of a "mask or hash" select was one)
   // makes the thread wait out the memory latency once per row instead of once per row group -- the regenerated-mask fallback
   // therefore lives in g_from_row
@@ -491,32 +537,35 @@ __device__ __forceinline__ void load_bwd_row(const BnBwdArgs& a, int r, int b, i
 }
 
 // masked upstream gradient g and the conv output for one staged row (reflect halo folded; activation gate, dropout, length mask)
-template <int ACT, bool DROP, bool HAS_RES>
-__device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int r, int b, int t, int c, const BwdRow& in, const float (&sc)[8],
+template <typename TA, int ACT, bool DROP, bool HAS_RES>
+__device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int r, int b, int t, int c, const BwdRow<TA>& in, const float (&sc)[8],
                                            const float (&sh)[8], const float (&rsc)[8], const float (&rsh)[8], float (&g)[8],
                                            float (&zv)[8]) {
-  unpack8(in.z, zv);
-  unpack8(in.d, g);
+  in.z.unpack(zv);
+  in.d.unpack(g);
   uint32_t bits = in.bits;
   if (DROP && !a.drop_mask)                                        // no stored keep-bits: regenerate them (kernel-uniform branch)
     bits = (dropout_mask32(a.seed, (uint32_t)(r / kRowGroup), (uint32_t)(c >> 3), a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
   const int dr = a.T - 1 - t;
   if ((t >= 1 && t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo (<8 % of the rows)
-    const __nv_bfloat16* base = a.dyp + (int64_t)b * (a.pl + a.T + a.pr) * a.C + c;
+    const TA* base = reinterpret_cast<const TA*>(a.dyp) + (int64_t)b * (a.pl + a.T + a.pr) * a.C + c;
     float h[8];
+    Vec8<TA> hq;
     if (t >= 1 && t <= a.pl) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl - t) * a.C)), h);
+      hq.load(base + (int64_t)(a.pl - t) * a.C);
+      hq.unpack(h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
     if (dr >= 1 && dr <= a.pr) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)(a.pl + a.T - 1 + dr) * a.C)), h);
+      hq.load(base + (int64_t)(a.pl + a.T - 1 + dr) * a.C);
+      hq.unpack(h);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] += h[i];
     }
   }
   float rv[8];
-  if (HAS_RES) unpack8(in.r, rv);
+  if (HAS_RES) in.r.unpack(rv);
   const bool masked = t >= in.len;
   const float gs = DROP ? a.inv_keep : 1.f;
 #pragma unroll
@@ -529,9 +578,9 @@ __device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int r, int b, int
 }
 
 // red[0:C] += sum g, red[C:2C] += sum g*xhat   (accumulated as sum g*(z-mean), scaled by invstd once per CTA; red is zero on entry)
-template <int ACT, bool DROP, bool HAS_RES>
+template <typename TA, int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
-  constexpr int kRows = HAS_RES ? 2 : kRowGroup;     // the residual variants carry a third stream: fewer rows in flight, no spills
+  constexpr int kRows = (HAS_RES || sizeof(TA) == 4) ? 2 : kRowGroup;     // a third stream / fp32 rows: fewer rows in flight, no spills
   __shared__ __align__(16) float s_a[kBnThreads * 8], s_b[kBnThreads * 8];
   const int bx = blockDim.x, ny = blockDim.y;
   const int cv = blockIdx.x * bx + threadIdx.x;
@@ -552,13 +601,13 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce
     const int rows = a.B * a.T;
     const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);
     for (int r0 = r_begin + threadIdx.y * kRows; r0 < r_end; r0 += ny * kRows) {
-      BwdRow in[kRows];
+      BwdRow<TA> in[kRows];
       const int b0 = r0 / a.T, t0 = r0 - b0 * a.T;
       {
         int b = b0, t = t0;
 #pragma unroll
         for (int u = 0; u < kRows; ++u) {
-          if (r0 + u < r_end) load_bwd_row<DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
+          if (r0 + u < r_end) load_bwd_row<TA, DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
           if (++t == a.T) {
             t = 0;
             ++b;
@@ -570,7 +619,7 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce
       for (int u = 0; u < kRows; ++u) {
         if (r0 + u < r_end) {
           float g[8], zv[8];
-          g_from_row<ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
+          g_from_row<TA, ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             sg[i] += g[i];
@@ -614,9 +663,9 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce
 // dz [B, dz_rows, C]: rows [0, T) carry the gradient, rows [T, dz_rows) are zero-filled (the flat dgrad reads them as the zero
 // padding between utterances).  Row ranges are taken in the REVERSE order of the reduce pass (last range first, each range from its
 // end) so that the second read of (dy, z) starts with what the first pass touched last and is still in the 126 MB L2.
-template <int ACT, bool DROP, bool HAS_RES>
+template <typename TA, int ACT, bool DROP, bool HAS_RES>
 __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_kernel(BnBwdArgs a) {
-  constexpr int kRows = HAS_RES ? 2 : kRowGroup;
+  constexpr int kRows = (HAS_RES || sizeof(TA) == 4) ? 2 : kRowGroup;
   zero_small(a.zero_ptr, a.zero_count);
   const int ny = blockDim.y;
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
@@ -660,13 +709,13 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
   const int groups = (r_end - r_begin + kRows - 1) / kRows;
   for (int gi = groups - 1 - (int)threadIdx.y; gi >= 0; gi -= ny) {
     const int r0 = r_begin + gi * kRows;
-    BwdRow in[kRows];
+    BwdRow<TA> in[kRows];
     const int b0 = r0 / a.T, t0 = r0 - b0 * a.T;
     {
       int b = b0, t = t0;
 #pragma unroll
       for (int u = 0; u < kRows; ++u) {
-        if (r0 + u < r_end) load_bwd_row<DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
+        if (r0 + u < r_end) load_bwd_row<TA, DROP, HAS_RES>(a, r0 + u, b, t, cv, in[u]);
         if (++t == a.T) {
           t = 0;
           ++b;
@@ -678,11 +727,16 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
     for (int u = 0; u < kRows; ++u) {
       if (r0 + u < r_end) {
         float g[8], zv[8], o[8];
-        g_from_row<ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
+        g_from_row<TA, ACT, DROP, HAS_RES>(a, r0 + u, b, t, c, in[u], sc, sh, rsc, rsh, g, zv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
-        *reinterpret_cast<uint4*>(a.dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = pack8(o);
-        if (a.g_out) *reinterpret_cast<uint4*>(a.g_out + (int64_t)(r0 + u) * a.C + c) = pack8(g);
+        Vec8<TA> q;
+        q.pack(o);
+        q.store(reinterpret_cast<TA*>(a.dz) + ((int64_t)b * a.dz_rows + t) * a.C + c);
+        if (a.g_out) {
+          q.pack(g);
+          q.store(reinterpret_cast<TA*>(a.g_out) + (int64_t)(r0 + u) * a.C + c);
+        }
       }
       if (++t == a.T) {
         t = 0;
@@ -697,7 +751,9 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
     const int q_begin = blockIdx.y * per, q_end = min(trows, q_begin + per);
     for (int q = q_begin + threadIdx.y; q < q_end; q += ny) {
       const int b = q / tail, t = a.T + (q - b * tail);
-      *reinterpret_cast<uint4*>(a.dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = make_uint4(0u, 0u, 0u, 0u);
+      Vec8<TA> zv;
+      zv.zero();
+      zv.store(reinterpret_cast<TA*>(a.dz) + ((int64_t)b * a.dz_rows + t) * a.C + c);
     }
   }
 }
@@ -728,8 +784,9 @@ __global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, flo
   if (nan_flag && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(nan_flag, 1);
 }
 
+template <typename TOut>
 __global__ void log_softmax_bwd_kernel(const float* __restrict__ g, const float* __restrict__ lp, const float* __restrict__ gscale,
-                                       __nv_bfloat16* __restrict__ dlogits, int ld_out, int64_t rows, int C, int fused_identity) {
+                                       TOut* __restrict__ dlogits, int ld_out, int64_t rows, int C, int fused_identity) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -747,12 +804,13 @@ __global__ void log_softmax_bwd_kernel(const float* __restrict__ g, const float*
       if (!fused_identity) v -= expf(lp[row * C + c]) * s;
       v *= sc;
     }
-    dlogits[row * ld_out + c] = __float2bfloat16_rn(v);
+    store_act(dlogits + row * ld_out + c, v);
   }
 }
 
 // column sums of a bf16 matrix (bias gradient); block (32, 8), 32 channels per block-column
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out,
+template <typename TIn>
+__global__ void colsum_kernel(const TIn* __restrict__ x, int64_t rows, int C, int ld, float* __restrict__ out,
                               int rows_per_block) {
   __shared__ float s[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -760,7 +818,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
   const int64_t r_end = min(rows, r_begin + rows_per_block);
   float acc = 0.f;
   if (c < C)
-    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) acc += __bfloat162float(x[r * ld + c]);
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) acc += load_act(x + r * ld + c);
   s[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
@@ -840,23 +898,31 @@ static BnGeo bn_geo(int64_t rows, int C, int ctas_per_sm) {
 }
 
 // compile-time (activation, dropout, residual) variants of the kernels above
-#define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                                \
+#define W2L_BN_DISPATCH_T(KERNEL, TA, act, drop, has_res, ...)                                                          \
   do {                                                                                                                 \
     const int key_ = (act) * 4 + ((drop) ? 2 : 0) + ((has_res) ? 1 : 0);                                               \
     switch (key_) {                                                                                                    \
-      case 0: KERNEL<W2L_ACT_NONE, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                  \
-      case 1: KERNEL<W2L_ACT_NONE, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 2: KERNEL<W2L_ACT_NONE, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 3: KERNEL<W2L_ACT_NONE, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 4: KERNEL<W2L_ACT_RELU, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                  \
-      case 5: KERNEL<W2L_ACT_RELU, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 6: KERNEL<W2L_ACT_RELU, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                   \
-      case 7: KERNEL<W2L_ACT_RELU, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                    \
-      case 8: KERNEL<W2L_ACT_CLAMP20, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
-      case 9: KERNEL<W2L_ACT_CLAMP20, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
-      case 10: KERNEL<W2L_ACT_CLAMP20, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
-      default: KERNEL<W2L_ACT_CLAMP20, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
+      case 0: KERNEL<TA, W2L_ACT_NONE, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;              \
+      case 1: KERNEL<TA, W2L_ACT_NONE, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      case 2: KERNEL<TA, W2L_ACT_NONE, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      case 3: KERNEL<TA, W2L_ACT_NONE, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
+      case 4: KERNEL<TA, W2L_ACT_RELU, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;              \
+      case 5: KERNEL<TA, W2L_ACT_RELU, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      case 6: KERNEL<TA, W2L_ACT_RELU, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;               \
+      case 7: KERNEL<TA, W2L_ACT_RELU, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;                \
+      case 8: KERNEL<TA, W2L_ACT_CLAMP20, false, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;           \
+      case 9: KERNEL<TA, W2L_ACT_CLAMP20, false, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;            \
+      case 10: KERNEL<TA, W2L_ACT_CLAMP20, true, false><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;           \
+      default: KERNEL<TA, W2L_ACT_CLAMP20, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;            \
     }                                                                                                                  \
+  } while (0)
+// `act` may carry W2L_STORE_F32: the activation buffers of the call are fp32 (kernels instantiated with TA = float)
+#define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                                \
+  do {                                                                                                                 \
+    if ((act) & W2L_STORE_F32)                                                                                         \
+      W2L_BN_DISPATCH_T(KERNEL, float, (act) & 0xFF, drop, has_res, __VA_ARGS__);                                      \
+    else                                                                                                               \
+      W2L_BN_DISPATCH_T(KERNEL, __nv_bfloat16, (act) & 0xFF, drop, has_res, __VA_ARGS__);                              \
   } while (0)
 
 // dropout probability -> (keep_q, inv_keep) of the kernels' 12-bit keep probability; every pass of a layer derives them the same way
@@ -882,7 +948,7 @@ static int check_bn_args(const char* who, const void* z, const void* res, const 
   W2L_REQUIRE(pl >= 0 && pr >= 0 && pl < T && pr < T, "%s: reflect halo (%d,%d) must be smaller than T=%d", who, pl, pr, T);
   W2L_REQUIRE((int64_t)B * (T + pl + pr) < (1ll << 31) / 8, "%s: B*T too large", who);
   W2L_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p=%f out of [0,1)", who, drop_p);
-  W2L_REQUIRE(act >= 0 && act <= 2, "%s: unknown activation %d", who, act);
+  W2L_REQUIRE((act & ~W2L_STORE_F32) >= 0 && (act & ~W2L_STORE_F32) <= 2, "%s: unknown activation %d", who, act);
   return W2L_OK;
 }
 
@@ -906,8 +972,8 @@ static int rows_per_block_for(int64_t rows, int col_blocks) {
 
 extern "C" {
 
-int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
-                   int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
+static int im2col_ncw_impl(int f32, const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                           int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(x && out, "im2col_ncw: null pointer");
   W2L_REQUIRE(B >= 1 && F >= 1 && T >= 1 && rows >= 1 && k >= 1 && stride >= 1 && dilation >= 1 && pad_left >= 0, "im2col_ncw: bad geometry");
@@ -919,13 +985,26 @@ int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, i
   W2L_REQUIRE(smem <= 200 * 1024, "im2col_ncw: F=%d k=%d needs %zu bytes of shared memory", F, k, smem);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    W2L_CUDA(cudaFuncSetAttribute(im2col_ncw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    W2L_CUDA(cudaFuncSetAttribute(im2col_ncw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    W2L_CUDA(cudaFuncSetAttribute(im2col_ncw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid((rows + 31) / 32, B);
-  im2col_ncw_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, F, T, rows, k, stride, dilation, pad_left,
-                                                               pad_mode, lens, span, pitch);
+  if (f32)
+    im2col_ncw_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (float*)out, F, T, rows, k, stride, dilation, pad_left, pad_mode,
+                                                                        lens, span, pitch);
+  else
+    im2col_ncw_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, F, T, rows, k, stride, dilation,
+                                                                                pad_left, pad_mode, lens, span, pitch);
   return after_launch("im2col_ncw_kernel");
+}
+int w2l_im2col_ncw(const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                   int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
+  return im2col_ncw_impl(0, x, out, B, F, T, rows, k, stride, dilation, pad_left, pad_mode, lens, stream);
+}
+int w2l_im2col_ncw_f32(const float* x, float* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
+                       int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
+  return im2col_ncw_impl(1, x, out, B, F, T, rows, k, stride, dilation, pad_left, pad_mode, lens, stream);
 }
 
 int w2l_im2col_tm(const void* x, void* out, int32_t B, int32_t x_rows, int32_t C, int32_t T_out, int32_t k, int32_t stride,
@@ -966,9 +1045,19 @@ int w2l_tm_to_ncw(const void* x, int32_t x_dtype, float* out, int32_t B, int32_t
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
   const int64_t bs = (int64_t)x_rows * ld;
   if (x_dtype == W2L_DTYPE_BF16)
-    tm_to_ncw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, T, C, bs, x_row_offset, ld);
+    tm_to_ncw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, T, C, bs, x_row_offset, ld, T);
   else
-    tm_to_ncw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, out, T, C, bs, x_row_offset, ld);
+    tm_to_ncw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, out, T, C, bs, x_row_offset, ld, T);
+  return after_launch("tm_to_ncw_kernel");
+}
+
+int w2l_tm_to_ct_f32(const float* x, float* out, int32_t B, int32_t T, int32_t C, int32_t x_rows, int32_t x_row_offset, int32_t ld,
+                     int32_t out_pitch, void* stream) {
+  using namespace w2l;
+  W2L_REQUIRE(x && out && B >= 1 && T >= 1 && C >= 1 && ld >= C && x_rows >= T + x_row_offset && out_pitch >= T, "tm_to_ct_f32: bad arguments");
+  W2L_REQUIRE(B <= 65535 && (C + 31) / 32 <= 65535, "tm_to_ct_f32: shape too large");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  tm_to_ncw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(x, out, T, C, (int64_t)x_rows * ld, x_row_offset, ld, out_pitch);
   return after_launch("tm_to_ncw_kernel");
 }
 
@@ -1003,13 +1092,13 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
   W2L_REQUIRE(y && scale && shift, "bn_act_pad: null pointer");
   BnFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.z = (const __nv_bfloat16*)z;
-  a.res = (const __nv_bfloat16*)res;
+  a.z = z;
+  a.res = res;
   a.scale = scale;
   a.shift = shift;
   a.res_scale = res_scale;
   a.res_shift = res_shift;
-  a.y = (__nv_bfloat16*)y;
+  a.y = y;
   a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
   drop_quant(drop_p, &a.keep_q, &a.inv_keep);
   a.seed = seed;
@@ -1031,8 +1120,8 @@ int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows
   W2L_REQUIRE(zero_count >= 0 && (zero_ptr != nullptr || zero_count == 0), "bn_finalize_act_pad: bad zero buffer");
   BnFwdArgs a;
   memset(&a, 0, sizeof(a));
-  a.z = (const __nv_bfloat16*)z;
-  a.res = (const __nv_bfloat16*)res;
+  a.z = z;
+  a.res = res;
   a.res_scale = res_scale;
   a.res_shift = res_shift;
   a.stats = stats;
@@ -1046,7 +1135,7 @@ int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows
   a.running_var = running_var;
   a.num_batches_tracked = num_batches_tracked;
   a.fin = fin;
-  a.y = (__nv_bfloat16*)y;
+  a.y = y;
   a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
   drop_quant(drop_p, &a.keep_q, &a.inv_keep);
   a.seed = seed;
@@ -1066,9 +1155,9 @@ static int fill_bwd_args(w2l::BnBwdArgs& a, const char* who, const void* dyp, co
   if (rc) return rc;
   W2L_REQUIRE(dyp && scale && shift && mean && invstd && red, "%s: null pointer", who);
   memset(&a, 0, sizeof(a));
-  a.z = (const __nv_bfloat16*)z;
-  a.res = (const __nv_bfloat16*)res;
-  a.dyp = (const __nv_bfloat16*)dyp;
+  a.z = z;
+  a.res = res;
+  a.dyp = dyp;
   a.scale = scale;
   a.shift = shift;
   a.res_scale = res_scale;
@@ -1114,9 +1203,9 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   W2L_REQUIRE(zero_count >= 0 && (zero_ptr != nullptr || zero_count == 0), "bn_act_bwd_apply: bad zero buffer");
   W2L_REQUIRE(zero_ptr == nullptr || zero_ptr != red, "bn_act_bwd_apply: the buffer to clear must not be the reduction this pass reads");
   a.gamma = gamma;
-  a.dz = (__nv_bfloat16*)dz;
+  a.dz = dz;
   a.dz_rows = dz_rows;
-  a.g_out = (__nv_bfloat16*)g_out;
+  a.g_out = g_out;
   a.red_out = red_out;
   a.zero_ptr = zero_ptr;
   a.zero_count = zero_count;
@@ -1134,24 +1223,43 @@ int w2l_log_softmax(const float* logits, int32_t ld, float* out, int64_t rows, i
   return after_launch("log_softmax_kernel");
 }
 
-int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out, int64_t rows,
-                        int32_t C, int32_t fused_identity, void* stream) {
+static int log_softmax_bwd_impl(int f32, const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out, int64_t rows,
+                                int32_t C, int32_t fused_identity, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(g && dlogits && rows >= 1 && C >= 1 && ld_out >= C, "log_softmax_bwd: bad arguments");
   W2L_REQUIRE(fused_identity || lp, "log_softmax_bwd: log-probs required");
-  log_softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, lp, gscale, (__nv_bfloat16*)dlogits, ld_out,
-                                                                                      rows, C, fused_identity);
+  if (f32)
+    log_softmax_bwd_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, lp, gscale, (float*)dlogits, ld_out, rows, C,
+                                                                                               fused_identity);
+  else
+    log_softmax_bwd_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(g, lp, gscale, (__nv_bfloat16*)dlogits,
+                                                                                                       ld_out, rows, C, fused_identity);
   return after_launch("log_softmax_bwd_kernel");
 }
+int w2l_log_softmax_bwd(const float* g, const float* lp, const float* gscale, void* dlogits, int32_t ld_out, int64_t rows,
+                        int32_t C, int32_t fused_identity, void* stream) {
+  return log_softmax_bwd_impl(0, g, lp, gscale, dlogits, ld_out, rows, C, fused_identity, stream);
+}
+int w2l_log_softmax_bwd_f32(const float* g, const float* lp, const float* gscale, float* dlogits, int32_t ld_out, int64_t rows,
+                            int32_t C, int32_t fused_identity, void* stream) {
+  return log_softmax_bwd_impl(1, g, lp, gscale, dlogits, ld_out, rows, C, fused_identity, stream);
+}
 
-int w2l_colsum(const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream) {
+static int colsum_impl(int f32, const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(x && out && rows >= 1 && C >= 1 && ld >= C, "colsum: bad arguments");
   const int col_blocks = (C + 31) / 32;
   const int rpb = rows_per_block_for(rows, col_blocks);
   dim3 grid(col_blocks, (unsigned)((rows + rpb - 1) / rpb)), block(32, 8);
-  colsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out, rpb);
+  if (f32)
+    colsum_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, rows, C, ld, out, rpb);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, ld, out, rpb);
   return after_launch("colsum_kernel");
+}
+int w2l_colsum(const void* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream) { return colsum_impl(0, x, rows, C, ld, out, stream); }
+int w2l_colsum_f32(const float* x, int64_t rows, int32_t C, int32_t ld, float* out, void* stream) {
+  return colsum_impl(1, x, rows, C, ld, out, stream);
 }
 
 int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
@@ -1168,7 +1276,8 @@ int w2l_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {
 // ---------------------------------------------------------------- reflect halo fill (inference path)
 // y [B, pl+T+pr, C] bf16 whose interior rows [pl, pl+T) are already written: fills the mirrored halo rows in place.
 namespace w2l {
-__global__ void reflect_halo_kernel(__nv_bfloat16* __restrict__ y, int B, int T, int C, int pl, int pr) {
+template <typename TA>
+__global__ void reflect_halo_kernel(TA* __restrict__ y, int B, int T, int C, int pl, int pr) {
   const int c8 = C >> 3, halo = pl + pr, Tp = pl + T + pr;
   const int64_t total = (int64_t)B * halo * c8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1178,26 +1287,40 @@ __global__ void reflect_halo_kernel(__nv_bfloat16* __restrict__ y, int B, int T,
     // halo row index and its mirror source (both in padded coordinates)
     const int dst = h < pl ? h : pl + T + (h - pl);
     const int src = h < pl ? 2 * pl - h : pl + T - 2 - (h - pl);
-    __nv_bfloat16* yb = y + (int64_t)b * Tp * C + c;
-    *reinterpret_cast<uint4*>(yb + (int64_t)dst * C) = *reinterpret_cast<const uint4*>(yb + (int64_t)src * C);
+    TA* yb = y + (int64_t)b * Tp * C + c;
+    Vec8<TA> q;
+    q.load(yb + (int64_t)src * C);
+    q.store(yb + (int64_t)dst * C);
   }
 }
 }  // namespace w2l
 
-extern "C" int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream) {
+namespace w2l {
+static int reflect_halo_impl(int f32, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(y && B >= 1 && T >= 1 && C >= 8 && C % 8 == 0, "reflect_halo: bad arguments");
   W2L_REQUIRE(pad_left >= 0 && pad_right >= 0 && pad_left < T && pad_right < T, "reflect_halo: halo must be smaller than T");
   if (pad_left + pad_right == 0) return W2L_OK;
   const int64_t total = (int64_t)B * (pad_left + pad_right) * (C / 8);
-  reflect_halo_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)y, B, T, C, pad_left, pad_right);
+  if (f32)
+    reflect_halo_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((float*)y, B, T, C, pad_left, pad_right);
+  else
+    reflect_halo_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)y, B, T, C, pad_left, pad_right);
   return after_launch("reflect_halo_kernel");
+}
+}  // namespace w2l
+extern "C" int w2l_reflect_halo(void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream) {
+  return w2l::reflect_halo_impl(0, y, B, T, C, pad_left, pad_right, stream);
+}
+extern "C" int w2l_reflect_halo_f32(float* y, int32_t B, int32_t T, int32_t C, int32_t pad_left, int32_t pad_right, void* stream) {
+  return w2l::reflect_halo_impl(1, y, B, T, C, pad_left, pad_right, stream);
 }
 
 // ---------------------------------------------------------------- transposed weight shadow for backward-data
 // w [k, Co, Ci] fp32 (kernel-layout master weights) -> wt [k, Ci_pad, Co_pad] bf16 with wt[k-1-j][ci][co] = w[j][co][ci]
 namespace w2l {
-__global__ void pack_wt_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int k, int Co, int Ci, int Co_pad, int Ci_pad) {
+template <typename TOut>
+__global__ void pack_wt_kernel(const float* __restrict__ w, TOut* __restrict__ wt, int k, int Co, int Ci, int Co_pad, int Ci_pad) {
   __shared__ float tile[32][33];
   const int j = blockIdx.z, co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
   const float* src = w + (int64_t)j * Co * Ci;
@@ -1206,21 +1329,32 @@ __global__ void pack_wt_kernel(const float* __restrict__ w, __nv_bfloat16* __res
     tile[i][threadIdx.x] = (co < Co && ci < Ci) ? src[(int64_t)co * Ci + ci] : 0.f;
   }
   __syncthreads();
-  __nv_bfloat16* dst = wt + (int64_t)(k - 1 - j) * Ci_pad * Co_pad;
+  TOut* dst = wt + (int64_t)(k - 1 - j) * Ci_pad * Co_pad;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int ci = ci0 + i, co = co0 + threadIdx.x;
-    if (ci < Ci_pad && co < Co_pad) dst[(int64_t)ci * Co_pad + co] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (ci < Ci_pad && co < Co_pad) store_act(dst + (int64_t)ci * Co_pad + co, tile[threadIdx.x][i]);
   }
 }
 }  // namespace w2l
 
-extern "C" int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream) {
+namespace w2l {
+static int pack_wt_impl(int f32, const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream) {
   using namespace w2l;
   W2L_REQUIRE(w && wt && k >= 1 && Cout >= 1 && Cin >= 1 && Cout_pad >= Cout && Cin_pad >= Cin, "pack_wt: bad arguments");
   W2L_REQUIRE(k <= 65535 && (Cout_pad + 31) / 32 <= 65535, "pack_wt: shape too large");
   dim3 grid((Cin_pad + 31) / 32, (Cout_pad + 31) / 32, k), block(32, 8);
-  pack_wt_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wt, k, Cout, Cin, Cout_pad, Cin_pad);
+  if (f32)
+    pack_wt_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(w, (float*)wt, k, Cout, Cin, Cout_pad, Cin_pad);
+  else
+    pack_wt_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wt, k, Cout, Cin, Cout_pad, Cin_pad);
   return after_launch("pack_wt_kernel");
+}
+}  // namespace w2l
+extern "C" int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream) {
+  return w2l::pack_wt_impl(0, w, wt, k, Cout, Cin, Cout_pad, Cin_pad, stream);
+}
+extern "C" int w2l_pack_wt_f32(const float* w, float* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream) {
+  return w2l::pack_wt_impl(1, w, wt, k, Cout, Cin, Cout_pad, Cin_pad, stream);
 }
 
 extern "C" int w2l_lens_chain(const void* lens_in, int32_t lens_is_int64, int32_t B, const int32_t* conv_params_host, int32_t n_convs,

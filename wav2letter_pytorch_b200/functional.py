@@ -13,6 +13,12 @@ from ._lib import ConvDesc
 ACT_NONE, ACT_RELU, ACT_CLAMP20 = 0, 1, 2
 PAD_ZERO, PAD_REFLECT = 0, 1
 DT_BF16, DT_F32 = 0, 1
+STORE_F32 = 0x100          # W2L_STORE_F32: OR-ed into `act` when the activation buffers of a BatchNorm / activation pass are fp32
+
+
+def _act_flag(act, t):
+    """`act` with W2L_STORE_F32 when tensor ``t`` (the pass's conv output) is fp32: the fp32-faithful mode"""
+    return act | STORE_F32 if t.dtype == torch.float32 else act
 
 
 def _ptr(t):
@@ -100,8 +106,8 @@ def ctc_loss_raw(x, targets, input_lengths, target_lengths, blank=0, zero_infini
 
 # --------------------------------------------------------------------------------------------- conv
 def make_desc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype=DT_BF16,
-              act=ACT_NONE):
-    return ConvDesc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype, act)
+              act=ACT_NONE, x_dtype=DT_BF16):
+    return ConvDesc(B, T_out, Cin, Cout, Cout_pad, k, dilation, x_rows, x_row_offset, y_rows, y_row_offset, ldy, y_dtype, act, x_dtype)
 
 
 _gemm_scratch = {}
@@ -148,8 +154,9 @@ def conv1d_dgrad_wt(dy, wt, desc, dx):
 def pack_wt(w_store, wt, cout, cin):
     """fp32 [k, Cout, Cin] -> bf16 wt [k, Cin_pad, Cout_pad], tap-reversed + transposed"""
     k = w_store.shape[0]
+    fn = _lib.load().w2l_pack_wt_f32 if wt.dtype == torch.float32 else _lib.load().w2l_pack_wt      # fp32 shadow: the fp32-faithful mode
     with torch.cuda.device(w_store.device):
-        _lib.check(_lib.load().w2l_pack_wt(_ptr(w_store), _ptr(wt), k, cout, cin, wt.shape[2], wt.shape[1], _stream()), "pack_wt")
+        _lib.check(fn(_ptr(w_store), _ptr(wt), k, cout, cin, wt.shape[2], wt.shape[1], _stream()), "pack_wt")
     return wt
 
 
@@ -161,6 +168,42 @@ def conv1d_wgrad(dy, x, desc, dw):
         if lib.w2l_conv1d_wgrad_splits(ctypes.byref(desc)) > 1:
             dw.zero_()
         _lib.check(lib.w2l_conv1d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(desc), _stream()), "conv1d_wgrad")
+    return dw
+
+
+def tm_to_ct_f32(x, T, x_row_offset=0, pitch=None, C=None, lead=0):
+    """time-major fp32 rows [x_row_offset, x_row_offset + T), first C columns, of x [B, rows, ld] -> channel-major [B, C, pitch] fp32
+    with ``lead`` zeros in front of every row (out[b, c, lead + t] = x[b, x_row_offset + t, c]; pitch defaults to lead + T rounded up
+    to 4 floats; the pad behind is never read): the transposed operands of the fp32-faithful weight gradient"""
+    _need_cuda(x)
+    B, rows, ld = x.shape
+    C = ld if C is None else C
+    pitch = (lead + T + 3) // 4 * 4 if pitch is None else pitch
+    out = torch.empty((B, C, pitch), dtype=torch.float32, device=x.device)
+    if lead:
+        out[:, :, :lead].zero_()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().w2l_tm_to_ct_f32(_ptr(x), ctypes.c_void_p(out.data_ptr() + 4 * lead), B, T, C, rows, x_row_offset, ld, pitch,
+                                                _stream()), "tm_to_ct_f32")
+    return out
+
+
+def conv1d_wgrad_t(dy, x, desc, dw):
+    """fp32-faithful weight gradient (tf32 multiply, fp32 accumulate) of time-major fp32 dy [B, y_rows, Cout] (rows [0, T_out) used)
+    and x [B, x_rows, Cin]: both are transposed to time-contiguous copies first (K-major operands, like the forward GEMM) -- x once
+    per residue mod 4 of the taps' row offsets, DELAYED by that many rows (s zeros in front), because TMA wants the time coordinate
+    of a load 16-byte aligned.  dw [k, Cout, Cin] fp32 is zero-filled here (tiles shared between CTAs are accumulated with atomics)."""
+    _need_cuda(dy, x, dw)
+    B, x_rows, _ = x.shape
+    dyT = tm_to_ct_f32(dy, desc.T_out, desc.y_row_offset, C=desc.Cout)
+    pitch = (x_rows + 3 + 3) // 4 * 4
+    need = sorted({(-(desc.x_row_offset + j * desc.dilation)) & 3 for j in range(desc.k)})
+    xs = {s: tm_to_ct_f32(x, x_rows, 0, pitch, lead=s) for s in need}
+    arr = (ctypes.c_void_p * 4)(*[xs[s].data_ptr() if s in xs else None for s in range(4)])
+    with torch.cuda.device(dy.device):
+        dw.zero_()
+        _lib.check(_lib.load().w2l_conv1d_wgrad_t(_ptr(dyT), dyT.shape[2], arr, pitch, _ptr(dw), ctypes.byref(desc), _stream()),
+                   "conv1d_wgrad_t")
     return dw
 
 
@@ -200,15 +243,15 @@ def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
 
 
 # --------------------------------------------------------------------------------------------- elementwise
-def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
-    """x [B,F,T] fp32 -> [B, rows, k*F] bf16 (unfold + pad + transpose + cast)."""
+def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None, out_dtype=torch.bfloat16):
+    """x [B,F,T] fp32 -> [B, rows, k*F] bf16 (fp32 with ``out_dtype=torch.float32``): unfold + pad + transpose + cast."""
     _need_cuda(x, lens)
     x = x.contiguous().float()
     B, F, T = x.shape
-    out = torch.empty((B, rows, k * F), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B, rows, k * F), dtype=out_dtype, device=x.device)
+    fn = _lib.load().w2l_im2col_ncw_f32 if out_dtype == torch.float32 else _lib.load().w2l_im2col_ncw
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().w2l_im2col_ncw(_ptr(x), _ptr(out), B, F, T, rows, k, stride, dilation, pad_left, pad_mode, _ptr(lens),
-                                              _stream()), "im2col_ncw")
+        _lib.check(fn(_ptr(x), _ptr(out), B, F, T, rows, k, stride, dilation, pad_left, pad_mode, _ptr(lens), _stream()), "im2col_ncw")
     return out
 
 
@@ -290,18 +333,19 @@ def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, s
                res_shift=None, out=None, drop_mask=None):
     """``drop_mask`` (uint8 [B*T*C/8], optional) receives the dropout keep-bits for the backward pass."""
     if out is None:
-        out = torch.empty((B, pad_left + T + pad_right, C), dtype=torch.bfloat16, device=z.device)
+        out = torch.empty((B, pad_left + T + pad_right, C), dtype=z.dtype, device=z.device)
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().w2l_bn_act_pad(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
-                                              B, T, C, pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask),
-                                              _stream()), "bn_act_pad")
+                                              B, T, C, pad_left, pad_right, _act_flag(act, z), float(drop_p), int(seed), _ptr(lens),
+                                              _ptr(drop_mask), _stream()), "bn_act_pad")
     return out
 
 
 def reflect_halo(y, T, pad_left, pad_right):
     B, rows, C = y.shape
+    fn = _lib.load().w2l_reflect_halo_f32 if y.dtype == torch.float32 else _lib.load().w2l_reflect_halo
     with torch.cuda.device(y.device):
-        _lib.check(_lib.load().w2l_reflect_halo(_ptr(y), B, T, C, pad_left, pad_right, _stream()), "reflect_halo")
+        _lib.check(fn(_ptr(y), B, T, C, pad_left, pad_right, _stream()), "reflect_halo")
     return y
 
 
@@ -312,13 +356,13 @@ def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running
     sums the conv epilogue left.  Returns (y bf16 [B, pl+T+pr, C], fin fp32 [4, C] = scale, shift, mean, invstd).  ``zero_after``
     (fp32 tensor, optional) is cleared by the same launch for a later kernel."""
     dev = z.device
-    out = torch.empty((B, pad_left + T + pad_right, C), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((B, pad_left + T + pad_right, C), dtype=z.dtype, device=dev)
     fin = torch.empty((4, C), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().w2l_bn_finalize_act_pad(
             _ptr(z), _ptr(stats), B * T, _ptr(gamma), _ptr(beta), _ptr(conv_bias), float(eps), float(momentum), _ptr(running_mean),
             _ptr(running_var), _ptr(num_batches_tracked), _ptr(fin), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out), B, T, C,
-            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask), _ptr(zero_after),
+            pad_left, pad_right, _act_flag(act, z), float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask), _ptr(zero_after),
             0 if zero_after is None else zero_after.numel(), _stream()), "bn_finalize_act_pad")
     return out, fin
 
@@ -336,8 +380,11 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
         red_out = None
     else:
         red, red_out = red_ws, torch.empty((2 * C,), dtype=torch.float32, device=dev)
-    dz = torch.empty((B, dz_rows, C), dtype=torch.bfloat16, device=dev)
-    g = torch.empty((B, T, C), dtype=torch.bfloat16, device=dev) if want_g else None
+    if dyp.dtype != z.dtype:
+        raise RuntimeError("bn_act_bwd: upstream gradient %s and conv output %s must have the same storage type" % (dyp.dtype, z.dtype))
+    dz = torch.empty((B, dz_rows, C), dtype=z.dtype, device=dev)
+    g = torch.empty((B, T, C), dtype=z.dtype, device=dev) if want_g else None
+    act = _act_flag(act, z)
     lib = _lib.load()
     with torch.cuda.device(dev):
         _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
@@ -362,15 +409,15 @@ def log_softmax(logits, C, mode=0, nan_flag=None):
     return out
 
 
-def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
-    """g, lp [..., C] fp32 -> d logits bf16 [..., ld_out] (zero padded)."""
+def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False, out_dtype=torch.bfloat16):
+    """g, lp [..., C] fp32 -> d logits bf16 (fp32 with ``out_dtype=torch.float32``) [..., ld_out] (zero padded)."""
     C = g.shape[-1]
     rows = g.numel() // C
     g = g.contiguous()
-    out = torch.empty(g.shape[:-1] + (ld_out,), dtype=torch.bfloat16, device=g.device)
+    out = torch.empty(g.shape[:-1] + (ld_out,), dtype=out_dtype, device=g.device)
+    fn = _lib.load().w2l_log_softmax_bwd_f32 if out_dtype == torch.float32 else _lib.load().w2l_log_softmax_bwd
     with torch.cuda.device(g.device):
-        _lib.check(_lib.load().w2l_log_softmax_bwd(_ptr(g), _ptr(lp), _ptr(gscale), _ptr(out), ld_out, rows, C, int(fused_identity),
-                                                   _stream()), "log_softmax_bwd")
+        _lib.check(fn(_ptr(g), _ptr(lp), _ptr(gscale), _ptr(out), ld_out, rows, C, int(fused_identity), _stream()), "log_softmax_bwd")
     return out
 
 
@@ -378,8 +425,9 @@ def colsum(x, C):
     ld = x.shape[-1]
     rows = x.numel() // ld
     out = torch.zeros((C,), dtype=torch.float32, device=x.device)
+    fn = _lib.load().w2l_colsum_f32 if x.dtype == torch.float32 else _lib.load().w2l_colsum
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().w2l_colsum(_ptr(x), rows, C, ld, _ptr(out), _stream()), "colsum")
+        _lib.check(fn(_ptr(x), rows, C, ld, _ptr(out), _stream()), "colsum")
     return out
 
 

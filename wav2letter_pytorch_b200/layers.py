@@ -64,10 +64,11 @@ class WgradStream:
 
 def wgrad_async(side, dy, x, desc, dw):
     """conv1d_wgrad on the side stream returned by ``WgradStream.fork`` (plain call when it is None)."""
+    wgrad = F.conv1d_wgrad_t if desc.x_dtype == F.DT_F32 else F.conv1d_wgrad      # fp32-faithful mode: tf32 over transposed operands
     if side is None:
-        return F.conv1d_wgrad(dy, x, desc, dw)
+        return wgrad(dy, x, desc, dw)
     with torch.cuda.stream(side):
-        F.conv1d_wgrad(dy, x, desc, dw)
+        wgrad(dy, x, desc, dw)
     for t in (dy, x) if getattr(dw, "_w2l_arena", False) else (dy, x, dw):
         t.record_stream(side)
     return dw
@@ -114,6 +115,17 @@ class ConvParams(nn.Module):
         self.bias = nn.Parameter(b0) if bias else None
         self._shadow = None
         self._shadow_version = None
+        # fp32-faithful mode (set by the owning model, ``precision="tf32"``): the GEMMs read fp32 activations and these fp32 weights
+        # as tf32 with fp32 accumulation -- no bf16 shadow exists, activations between the layers stay fp32
+        self.f32 = False
+
+    @property
+    def act_dtype(self):
+        return torch.float32 if self.f32 else torch.bfloat16
+
+    @property
+    def x_dtype(self):
+        return F.DT_F32 if self.f32 else F.DT_BF16
 
     @staticmethod
     def _default_bias(w):
@@ -162,12 +174,17 @@ class ConvParams(nn.Module):
         """bf16 shadow [k_eff, cout_pad, cin_eff] read by the GEMM kernels; refreshed when the Parameter changed."""
         w = self.weight
         ver = (w._version, w.data_ptr())
-        if self._shadow is None or self._shadow.device != w.device:
-            self._shadow = torch.zeros((self.k_eff, self.cout_pad, self.cin_eff), dtype=torch.bfloat16, device=w.device)
+        if self.f32 and self.cout_pad == self.out_channels:
+            return self.storage()              # fp32 mode: the master weights ARE the operand
+        dt = self.act_dtype
+        if self._shadow is None or self._shadow.device != w.device or self._shadow.dtype != dt:
+            self._shadow = torch.zeros((self.k_eff, self.cout_pad, self.cin_eff), dtype=dt, device=w.device)
             self._shadow_version = None
         if self._shadow_version != ver:
             st = self.storage()
-            if self.cout_pad == self.out_channels:
+            if self.f32:                       # padded fp32 copy (the head: Cout is not a multiple of 16)
+                self._shadow[:, :self.out_channels].copy_(st)
+            elif self.cout_pad == self.out_channels:
                 F.cast_bf16(st, self._shadow)
             else:                              # padded rows stay zero; k_eff == 1 for the only such layer (the head)
                 for j in range(self.k_eff):
@@ -179,9 +196,9 @@ class ConvParams(nn.Module):
         """bf16 shadow for backward-data: [k_eff, cin_pad16, cout_pad], taps reversed and transposed (K-major operand)."""
         w = self.weight
         ver = (w._version, w.data_ptr())
-        if getattr(self, "_shadow_t", None) is None or self._shadow_t.device != w.device:
+        if getattr(self, "_shadow_t", None) is None or self._shadow_t.device != w.device or self._shadow_t.dtype != self.act_dtype:
             cin_pad = (self.cin_eff + 15) // 16 * 16
-            self._shadow_t = torch.zeros((self.k_eff, cin_pad, self.cout_pad), dtype=torch.bfloat16, device=w.device)
+            self._shadow_t = torch.zeros((self.k_eff, cin_pad, self.cout_pad), dtype=self.act_dtype, device=w.device)
             self._shadow_t_version = None
         if self._shadow_t_version != ver:
             F.pack_wt(self.storage(), self._shadow_t, self.out_channels, self.cin_eff)
@@ -319,8 +336,11 @@ class BatchNormParams(nn.Module):
 
 
 def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0, ldy=None, y_dtype=F.DT_BF16, act=F.ACT_NONE):
+    if conv.f32 and y_dtype == F.DT_BF16:
+        y_dtype = F.DT_F32                     # fp32-faithful mode: every activation buffer is fp32
     return F.make_desc(B, T_out, conv.cin_eff, conv.out_channels, conv.cout_pad, conv.k_eff, conv.dilation[0], x_rows, x_row_offset,
-                       T_out if y_rows is None else y_rows, y_row_offset, conv.out_channels if ldy is None else ldy, y_dtype, act)
+                       T_out if y_rows is None else y_rows, y_row_offset, conv.out_channels if ldy is None else ldy, y_dtype, act,
+                       conv.x_dtype)
 
 
 _EPILOGUE_STATS = os.environ.get("W2L_EPILOGUE_STATS", "1") != "0"      # 0: separate bn_stats pass over z (A/B measurements)
@@ -399,7 +419,7 @@ class ConvBNActFn(torch.autograd.Function):
         T_out = geo["T_out"]
         Co = conv.out_channels
         pl, pr = geo.get("out_pad", (0, 0))
-        z = torch.empty((B, T_out, Co), dtype=torch.bfloat16, device=xin.device)
+        z = torch.empty((B, T_out, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
@@ -463,7 +483,7 @@ class ResidualBranchFn(torch.autograd.Function):
     def forward(ctx, xin, weight, gamma, beta, conv, bn):
         B, T, _ = xin.shape
         Co = conv.out_channels
-        z = torch.empty((B, T, Co), dtype=torch.bfloat16, device=xin.device)
+        z = torch.empty((B, T, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T, T, 0)
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
@@ -520,7 +540,7 @@ class ConvHeadFn(torch.autograd.Function):
             raise NotImplementedError("backward through the eval-mode softmax head is not supported")
         B, T, _ = xin.shape
         Co, cp = conv.out_channels, conv.cout_pad
-        dl = F.log_softmax_bwd(dout.contiguous(), out, cp, fused_identity=ctx.mode == 2)    # bf16 [B,T,cout_pad], zero padded
+        dl = F.log_softmax_bwd(dout.contiguous(), out, cp, fused_identity=ctx.mode == 2, out_dtype=conv.act_dtype)    # [B,T,cout_pad], zero padded
         desc = conv_desc(conv, B, T, T, 0, ldy=cp)
         dw = alloc_dw(conv, xin.device)
         side = WgradStream.fork(xin.device, conv.weight)
@@ -543,11 +563,11 @@ def conv_bn_act_eval(xin, conv, bn, geo, res=None):
     lens = geo.get("lens")
     scale, shift = bn.eval_scale_shift(conv.bias)
     if res is None and lens is None:
-        y = torch.empty((B, pl + T_out + pr, Co), dtype=torch.bfloat16, device=xin.device)
+        y = torch.empty((B, pl + T_out + pr, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=pl + T_out + pr, y_row_offset=pl, act=geo["act"])
         F.conv1d_fwd(xin, conv.packed(), desc, y, scale=scale, shift=shift)
         return F.reflect_halo(y, T_out, pl, pr)
-    z = torch.empty((B, T_out, Co), dtype=torch.bfloat16, device=xin.device)
+    z = torch.empty((B, T_out, Co), dtype=conv.act_dtype, device=xin.device)
     desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
     F.conv1d_fwd(xin, conv.packed(), desc, z)
     return F.bn_act_pad(z, scale, shift, B, T_out, Co, pl, pr, geo["act"], 0.0, 0, lens, res=None if res is None else res[0],

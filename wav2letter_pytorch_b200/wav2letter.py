@@ -63,10 +63,12 @@ class Conv1dBlock(nn.Module):
         pl, pr = self.pad_lr
         if from_ncw:
             if conv.unfold:
-                xin = F.im2col_ncw(xin, t_out, self.kernel_size[0], self.stride, self.dilation, pl, F.PAD_REFLECT)
+                xin = F.im2col_ncw(xin, t_out, self.kernel_size[0], self.stride, self.dilation, pl, F.PAD_REFLECT, out_dtype=conv.act_dtype)
             else:
-                xin = F.im2col_ncw(xin, t_in + pl + pr, 1, 1, 1, pl, F.PAD_REFLECT)
+                xin = F.im2col_ncw(xin, t_in + pl + pr, 1, 1, 1, pl, F.PAD_REFLECT, out_dtype=conv.act_dtype)
         elif conv.unfold:                                 # strided block inside the stack: unfold the halo-carrying input
+            if conv.f32:
+                raise NotImplementedError("precision='tf32': a strided block beyond the first layer is only implemented for bf16 activations")
             xin = UnfoldTmFn.apply(xin, t_out, self.kernel_size[0], self.stride, self.dilation, 0)
         if not self.has_bn:
             if self.activation_use or self.drop_p > 0:
@@ -96,12 +98,14 @@ class Conv1dBlock(nn.Module):
 class _TmToNcw(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, t, c):
-        ctx.shape = y.shape
+        ctx.shape, ctx.f32 = y.shape, y.dtype == torch.float32
         return F.tm_to_ncw(y, t, c)
 
     @staticmethod
     def backward(ctx, g):
         B, C, T = g.shape
+        if ctx.f32:
+            return g.transpose(1, 2).contiguous().float(), None, None
         out = torch.empty(ctx.shape, dtype=torch.bfloat16, device=g.device)
         F._lib.check(F._lib.load().w2l_ncw_to_tm(F._ptr(g.contiguous().float()), F._ptr(out), B, C, T, F._stream()), "ncw_to_tm")
         return out, None, None
@@ -127,6 +131,16 @@ class Wav2Letter(ConvCTCASR):
         mods = list(self.conv1ds.children())
         for cur, nxt in zip(mods[:-1], mods[1:]):
             cur.next_pad = nxt.pad_lr
+        # precision: "bf16" (default: bf16 operands and activations, fp32 accumulation and statistics) or "tf32" -- the fp32-faithful
+        # mode: activations, weights and gradients stay fp32 in memory (the reference's nn.Conv1d arithmetic, wav2letter.py:35-36),
+        # the GEMMs multiply them as tf32 with fp32 accumulation.  Logits within 1.5e-3 rel-L2 of torch fp32 per layer.
+        self.precision = str(getattr(cfg, "precision", "bf16") or "bf16").lower()
+        if self.precision in ("fp32", "float32"):
+            self.precision = "tf32"
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError("Wav2Letter: precision must be 'bf16' or 'tf32', got %r" % (self.precision,))
+        for m in mods:
+            m.conv1.f32 = self.precision == "tf32"
 
     @property
     def scaling_factor(self):
