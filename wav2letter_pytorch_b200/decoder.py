@@ -111,19 +111,27 @@ class GreedyDecoder(Decoder):
                     if ord(ch) < 0x10000:
                         lut[ord(ch)] = i
                 self._lut = lut.astype(np.int32)
+                ws = np.zeros(0x10000, dtype=bool)               # str.isspace() code points other than ' ' (all in the BMP)
+                for c in range(0x10000):
+                    if c != 32 and chr(c).isspace():
+                        ws[c] = True
+                self._other_ws = ws
                 self._pins = []
         if self._lut is False:
             return None
         n = len(texts)
-        smax = max(1, max(len(t) for t in texts))
+        lens_l = [len(t) for t in texts]
+        smax = max(1, max(lens_l))
         if smax > 1023:
             return None
-        words = 0
-        for t in texts:
-            w = len(t.split())
-            if w != sum(1 for x in t.split(" ") if x):          # whitespace other than ' ' present: host path
-                return None
-            words += w
+        # the whole batch in ONE pass over its code points (a Python loop per transcript -- split twice, encode, look up -- was 0.8 ms
+        # per step for 64 x 225 characters): the transcripts joined by single spaces, so that no word runs across two of them
+        cp = np.frombuffer(" ".join(texts).encode("utf-32-le"), dtype=np.int32)
+        low = np.minimum(cp, 0xFFFF)
+        if self._other_ws[low][cp < 0x10000].any():             # whitespace other than ' ' (str.split() would cut there): host path
+            return None
+        is_sp = cp == 32
+        words = int(np.count_nonzero(~is_sp[1:] & is_sp[:-1]) + (0 if cp.size == 0 or is_sp[0] else 1))
         slot = None
         for s in self._pins:                                    # rotate pinned staging buffers (CPU may run ahead of the GPU)
             if s[0].shape[0] >= n and s[0].shape[1] >= smax and (s[2] is None or s[2].query()):
@@ -133,12 +141,18 @@ class GreedyDecoder(Decoder):
             slot = [torch.zeros((n, max(smax, 256)), dtype=torch.int32).pin_memory(), torch.zeros((n,), dtype=torch.int32).pin_memory(), None]
             self._pins.append(slot)
         ids, lens = slot[0].numpy(), slot[1].numpy()
-        for i, t in enumerate(texts):
-            cp = np.frombuffer(t.encode("utf-32-le"), dtype=np.int32)
-            lens[i] = len(cp)
-            ids[i, :len(cp)] = np.where(cp < 0x10000, self._lut[np.minimum(cp, 0xFFFF)], cp + C)
-        cer_den = sum(len(t) - t.count(" ") for t in texts)
-        return slot, smax, cer_den, words, sum(len(t) for t in texts)
+        lens_a = np.asarray(lens_l, dtype=np.int64)
+        lens[:n] = lens_a
+        total = int(lens_a.sum())
+        if total:
+            starts = np.cumsum(lens_a) - lens_a                  # offset of transcript i among the characters proper ...
+            rows = np.repeat(np.arange(n), lens_a)
+            cols = np.arange(total) - np.repeat(starts, lens_a)
+            src = np.arange(total) + rows                        # ... and in the joined array (i separators precede it)
+            c = cp[src]
+            ids[rows, cols] = np.where(c < 0x10000, self._lut[np.minimum(c, 0xFFFF)], c + C)
+        n_spaces = int(np.count_nonzero(is_sp)) - (n - 1 if n > 0 else 0)
+        return slot, smax, total - n_spaces, words, total
 
     def error_ratios_device(self, probs, sizes, texts):
         """Greedy-decodes ``probs`` and scores the transcripts against ``texts`` entirely on the device.  Returns a CUDA
@@ -161,7 +175,7 @@ class GreedyDecoder(Decoder):
         lib = _lib.load()
         ws = torch.empty((lib.w2l_string_metrics_workspace_bytes(N, T, S) + 7) // 8, dtype=torch.int64, device=dev)
         ratios = torch.empty(3, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with F._on(dev):
             _lib.check(lib.w2l_string_metrics(F._ptr(tokens), F._ptr(counts), N, T, self.space_index, F._ptr(ref_ids), F._ptr(ref_lens), S,
                                               float(cer_den), float(wer_den), float(len_den), F._ptr(ratios), F._ptr(ws), ws.numel() * 8,
                                               F._stream()), "string_metrics")

@@ -25,8 +25,41 @@ def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+# The two per-call host costs of this module were torch.cuda.current_stream() and the torch.cuda.device() context (~15 us each, tens
+# of calls per training step: the literal default yaml -- one hidden layer -- was host-bound on them).  Both have a direct route: the
+# raw stream handle of the current device, and no device switch at all when the tensor already lives on the current device.
+_raw = {"ok": hasattr(torch._C, "_cuda_getCurrentRawStream") and hasattr(torch._C, "_cuda_getDevice")}
+
+
 def _stream():
+    if _raw["ok"]:
+        try:
+            return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+        except Exception:  # noqa: BLE001  (no CUDA runtime in this process, e.g. the host emulation: use the public API from now on)
+            _raw["ok"] = False
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(device):
+    """context that makes ``device`` the current CUDA device -- a no-op object when it already is"""
+    if _raw["ok"]:
+        try:
+            if device.index is None or device.index == torch._C._cuda_getDevice():
+                return _NO_SWITCH
+        except Exception:  # noqa: BLE001
+            _raw["ok"] = False
+    return torch.cuda.device(device)
 
 
 def _need_cuda(*ts):
@@ -63,7 +96,7 @@ def greedy_decode(scores, sizes=None, blank=0):
         sizes = sizes.to(device=dev, dtype=torch.int32).contiguous()
     wsb = lib.w2l_greedy_decode_workspace_bytes(N, T)
     ws = torch.empty((max(wsb, 4),), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.w2l_greedy_decode(_ptr(scores), N, T, C, scores.stride(0), scores.stride(1), _ptr(sizes), blank, _ptr(argmax),
                                          _ptr(tokens), _ptr(offsets), _ptr(counts), _ptr(ws), ws.numel(), _stream()),
                    "greedy_decode")
@@ -97,7 +130,7 @@ def ctc_loss_raw(x, targets, input_lengths, target_lengths, blank=0, zero_infini
     nll = torch.empty((N,), dtype=torch.float32, device=dev)
     loss = torch.empty((1,), dtype=torch.float32, device=dev)
     grad = torch.empty((N, T, C), dtype=torch.float32, device=dev) if need_grad else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.w2l_ctc_loss(_ptr(x), int(from_logits), N, T, C, x.stride(0), x.stride(1), _ptr(targets), S, _ptr(il), _ptr(tl),
                                     blank, int(zero_infinity), int(reduction_mean), _ptr(nll), _ptr(grad), _ptr(loss), _ptr(ws),
                                     ws.numel(), _stream()), "ctc_loss")
@@ -130,7 +163,7 @@ def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
     """``bn_stats`` (fp32 [2*Cout], zero-filled): receives the per-channel sum / sum of squares of the stored output."""
     _need_cuda(x, w, y)
     ensure_gemm_scratch(x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.load().w2l_conv1d_fwd(_ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(bn_stats), _ptr(y),
                                               ctypes.byref(desc), _stream()), "conv1d_fwd")
     return y
@@ -138,7 +171,7 @@ def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
 
 def conv1d_dgrad(dy, w, desc, dx):
     _need_cuda(dy, w, dx)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         _lib.check(_lib.load().w2l_conv1d_dgrad(_ptr(dy), _ptr(w), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad")
     return dx
 
@@ -146,7 +179,7 @@ def conv1d_dgrad(dy, w, desc, dx):
 def conv1d_dgrad_wt(dy, wt, desc, dx):
     """backward-data with the transposed (K-major) weight shadow; see w2l_conv1d_dgrad_wt"""
     _need_cuda(dy, wt, dx)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         _lib.check(_lib.load().w2l_conv1d_dgrad_wt(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad_wt")
     return dx
 
@@ -155,7 +188,7 @@ def pack_wt(w_store, wt, cout, cin):
     """fp32 [k, Cout, Cin] -> bf16 wt [k, Cin_pad, Cout_pad], tap-reversed + transposed"""
     k = w_store.shape[0]
     fn = _lib.load().w2l_pack_wt_f32 if wt.dtype == torch.float32 else _lib.load().w2l_pack_wt      # fp32 shadow: the fp32-faithful mode
-    with torch.cuda.device(w_store.device):
+    with _on(w_store.device):
         _lib.check(fn(_ptr(w_store), _ptr(wt), k, cout, cin, wt.shape[2], wt.shape[1], _stream()), "pack_wt")
     return wt
 
@@ -164,7 +197,7 @@ def conv1d_wgrad(dy, x, desc, dw):
     """dw [k, Cout, Cin] fp32; zero-filled here when the kernel will run split-K (atomic accumulation)."""
     _need_cuda(dy, x, dw)
     lib = _lib.load()
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         if lib.w2l_conv1d_wgrad_splits(ctypes.byref(desc)) > 1:
             dw.zero_()
         _lib.check(lib.w2l_conv1d_wgrad(_ptr(dy), _ptr(x), _ptr(dw), ctypes.byref(desc), _stream()), "conv1d_wgrad")
@@ -182,7 +215,7 @@ def tm_to_ct_f32(x, T, x_row_offset=0, pitch=None, C=None, lead=0):
     out = torch.empty((B, C, pitch), dtype=torch.float32, device=x.device)
     if lead:
         out[:, :, :lead].zero_()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.load().w2l_tm_to_ct_f32(_ptr(x), ctypes.c_void_p(out.data_ptr() + 4 * lead), B, T, C, rows, x_row_offset, ld, pitch,
                                                 _stream()), "tm_to_ct_f32")
     return out
@@ -200,7 +233,7 @@ def conv1d_wgrad_t(dy, x, desc, dw):
     need = sorted({(-(desc.x_row_offset + j * desc.dilation)) & 3 for j in range(desc.k)})
     xs = {s: tm_to_ct_f32(x, x_rows, 0, pitch, lead=s) for s in need}
     arr = (ctypes.c_void_p * 4)(*[xs[s].data_ptr() if s in xs else None for s in range(4)])
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         dw.zero_()
         _lib.check(_lib.load().w2l_conv1d_wgrad_t(_ptr(dyT), dyT.shape[2], arr, pitch, _ptr(dw), ctypes.byref(desc), _stream()),
                    "conv1d_wgrad_t")
@@ -213,7 +246,7 @@ def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
     _need_cuda(x, w)
     B, T, C = x.shape
     y = torch.empty((B, T_out, C), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.load().w2l_depthwise_fwd(_ptr(x), _ptr(w), _ptr(y), B, T, C, T_out, k, stride, dilation, pad, _ptr(out_lens), _stream()),
                    "depthwise_fwd")
     return y
@@ -222,7 +255,7 @@ def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
 def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None, stride=1):
     B, T_out, C = dy.shape
     dx = torch.empty((B, T, C), dtype=torch.bfloat16, device=dy.device)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         if stride == 1:
             _lib.check(_lib.load().w2l_depthwise_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens),
                                                        _stream()), "depthwise_dgrad")
@@ -236,7 +269,7 @@ def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
     B, T_out, C = dy.shape
     T = x.shape[1]
     dw = torch.zeros((k, C), dtype=torch.float32, device=dy.device)
-    with torch.cuda.device(dy.device):
+    with _on(dy.device):
         _lib.check(_lib.load().w2l_depthwise_wgrad(_ptr(dy), _ptr(x), _ptr(dw), B, T, C, T_out, k, stride, dilation, pad, _ptr(dy_lens),
                                                    _stream()), "depthwise_wgrad")
     return dw
@@ -250,7 +283,7 @@ def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None, out_
     B, F, T = x.shape
     out = torch.empty((B, rows, k * F), dtype=out_dtype, device=x.device)
     fn = _lib.load().w2l_im2col_ncw_f32 if out_dtype == torch.float32 else _lib.load().w2l_im2col_ncw
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(fn(_ptr(x), _ptr(out), B, F, T, rows, k, stride, dilation, pad_left, pad_mode, _ptr(lens), _stream()), "im2col_ncw")
     return out
 
@@ -263,7 +296,7 @@ def im2col_tm(x, T_out, k, stride, dilation, pad_left):
         raise RuntimeError("im2col_tm: contiguous bf16 [B, rows, C] required")
     B, rows, C = x.shape
     out = torch.empty((B, T_out, k * C), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.load().w2l_im2col_tm(_ptr(x), _ptr(out), B, rows, C, T_out, k, stride, dilation, pad_left, _stream()), "im2col_tm")
     return out
 
@@ -277,7 +310,7 @@ def col2im_tm(dcol, x_rows, C, k, stride, dilation, pad_left):
     if KC != k * C:
         raise RuntimeError("col2im_tm: dcol has %d columns, expected k*C = %d" % (KC, k * C))
     dx = torch.empty((B, x_rows, C), dtype=torch.bfloat16, device=dcol.device)
-    with torch.cuda.device(dcol.device):
+    with _on(dcol.device):
         _lib.check(_lib.load().w2l_col2im_tm(_ptr(dcol), _ptr(dx), B, x_rows, C, T_out, k, stride, dilation, pad_left, _stream()), "col2im_tm")
     return dx
 
@@ -288,7 +321,7 @@ def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
     B, rows, ld = x.shape
     out = torch.empty((B, C, T), dtype=torch.float32, device=x.device)
     dt = DT_BF16 if x.dtype == torch.bfloat16 else DT_F32
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(_lib.load().w2l_tm_to_ncw(_ptr(x), dt, _ptr(out), B, T, C, rows, x_row_offset, ld, _stream()), "tm_to_ncw")
     return out
 
@@ -296,7 +329,7 @@ def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
 def bn_stats(z, C):
     rows = z.numel() // C
     stats = torch.zeros((2 * C,), dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         _lib.check(_lib.load().w2l_bn_stats(_ptr(z), rows, C, _ptr(stats), _stream()), "bn_stats")
     return stats
 
@@ -305,7 +338,7 @@ def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_m
     """``num_batches_tracked`` (int64 0-dim CUDA buffer): incremented by the same kernel."""
     dev = stats.device
     out = torch.empty((4, C), dtype=torch.float32, device=dev)     # scale, shift, mean, invstd
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().w2l_bn_finalize(_ptr(stats), rows, C, _ptr(gamma), _ptr(beta), _ptr(conv_bias), eps, momentum,
                                                _ptr(running_mean), _ptr(running_var), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
                                                _ptr(out[3]), _ptr(num_batches_tracked), _stream()), "bn_finalize")
@@ -323,7 +356,7 @@ def lens_chain(lens, conv_params):
     rows = torch.empty((n + 1, B), dtype=torch.int32, device=lens.device)
     final = torch.empty((B,), dtype=torch.int64, device=lens.device)
     table = (ctypes.c_int32 * (4 * max(n, 1)))(*[int(v) for q in conv_params for v in q])
-    with torch.cuda.device(lens.device):
+    with _on(lens.device):
         _lib.check(_lib.load().w2l_lens_chain(_ptr(lens), int(lens.dtype == torch.int64), B, table, n, _ptr(rows), _ptr(final), _stream()),
                    "lens_chain")
     return rows, final
@@ -334,7 +367,7 @@ def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, s
     """``drop_mask`` (uint8 [B*T*C/8], optional) receives the dropout keep-bits for the backward pass."""
     if out is None:
         out = torch.empty((B, pad_left + T + pad_right, C), dtype=z.dtype, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         _lib.check(_lib.load().w2l_bn_act_pad(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out),
                                               B, T, C, pad_left, pad_right, _act_flag(act, z), float(drop_p), int(seed), _ptr(lens),
                                               _ptr(drop_mask), _stream()), "bn_act_pad")
@@ -344,7 +377,7 @@ def bn_act_pad(z, scale, shift, B, T, C, pad_left, pad_right, act, drop_p=0.0, s
 def reflect_halo(y, T, pad_left, pad_right):
     B, rows, C = y.shape
     fn = _lib.load().w2l_reflect_halo_f32 if y.dtype == torch.float32 else _lib.load().w2l_reflect_halo
-    with torch.cuda.device(y.device):
+    with _on(y.device):
         _lib.check(fn(_ptr(y), B, T, C, pad_left, pad_right, _stream()), "reflect_halo")
     return y
 
@@ -358,7 +391,7 @@ def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running
     dev = z.device
     out = torch.empty((B, pad_left + T + pad_right, C), dtype=z.dtype, device=dev)
     fin = torch.empty((4, C), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(_lib.load().w2l_bn_finalize_act_pad(
             _ptr(z), _ptr(stats), B * T, _ptr(gamma), _ptr(beta), _ptr(conv_bias), float(eps), float(momentum), _ptr(running_mean),
             _ptr(running_var), _ptr(num_batches_tracked), _ptr(fin), _ptr(res), _ptr(res_scale), _ptr(res_shift), _ptr(out), B, T, C,
@@ -386,7 +419,7 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
     g = torch.empty((B, T, C), dtype=z.dtype, device=dev) if want_g else None
     act = _act_flag(act, z)
     lib = _lib.load()
-    with torch.cuda.device(dev):
+    with _on(dev):
         _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
                                              _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
                                              int(seed), _ptr(lens), _ptr(drop_mask), _stream()), "bn_act_bwd_reduce")
@@ -404,7 +437,7 @@ def log_softmax(logits, C, mode=0, nan_flag=None):
     ld = logits.shape[-1]
     rows = logits.numel() // ld
     out = torch.empty(logits.shape[:-1] + (C,), dtype=torch.float32, device=logits.device)
-    with torch.cuda.device(logits.device):
+    with _on(logits.device):
         _lib.check(_lib.load().w2l_log_softmax(_ptr(logits), ld, _ptr(out), rows, C, mode, _ptr(nan_flag), _stream()), "log_softmax")
     return out
 
@@ -416,7 +449,7 @@ def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False, out_dtype=
     g = g.contiguous()
     out = torch.empty(g.shape[:-1] + (ld_out,), dtype=out_dtype, device=g.device)
     fn = _lib.load().w2l_log_softmax_bwd_f32 if out_dtype == torch.float32 else _lib.load().w2l_log_softmax_bwd
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         _lib.check(fn(_ptr(g), _ptr(lp), _ptr(gscale), _ptr(out), ld_out, rows, C, int(fused_identity), _stream()), "log_softmax_bwd")
     return out
 
@@ -426,7 +459,7 @@ def colsum(x, C):
     rows = x.numel() // ld
     out = torch.zeros((C,), dtype=torch.float32, device=x.device)
     fn = _lib.load().w2l_colsum_f32 if x.dtype == torch.float32 else _lib.load().w2l_colsum
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         _lib.check(fn(_ptr(x), rows, C, ld, _ptr(out), _stream()), "colsum")
     return out
 
@@ -435,6 +468,6 @@ def cast_bf16(src, dst=None):
     src = src.contiguous()
     if dst is None:
         dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         _lib.check(_lib.load().w2l_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast_bf16")
     return dst

@@ -163,7 +163,7 @@ class Novograd(Optimizer):
             slot[1].record()
             b1, b2 = group["betas"]
             P = F._ptr
-            with torch.cuda.device(dev.device):
+            with F._on(dev.device):
                 _lib.check(lib.w2l_novograd_step(P(dev[0]), P(dev[1]), P(dev[2]), P(plan["v"]),
                                                  P(plan["vmax"]) if group["amsgrad"] else None, P(dev[3]), P(dev[4]), P(plan["chunk_prefix"]),
                                                  len(params), plan["n_chunks"], float(group["lr"]), float(b1), float(b2), float(group["eps"]),
