@@ -196,9 +196,9 @@ class JasperBlock(nn.Module):
             mask = rows[ri] if (self.conv_mask and rows is not None) else None
             if not self.separable and m0.unfold:
                 t_first = (t + 2 * p - d * (k - 1) - 1) // s + 1
-                h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask)        # masked, zero padded, unfolded
+                h = F.im2col_ncw(h, t_first, k, s, d, p, F.PAD_ZERO, mask, out_dtype=m0.act_dtype)   # masked, zero padded, unfolded
             else:
-                h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask)              # masked time-major copy
+                h = F.im2col_ncw(h, t, 1, 1, 1, 0, F.PAD_ZERO, mask, out_dtype=getattr(m0, "act_dtype", torch.bfloat16))   # masked time-major copy
         block_in, res_pair = h, None
         training = self.training
         if self.res is not None:
@@ -209,7 +209,7 @@ class JasperBlock(nn.Module):
             if training:
                 res_pair = ResidualBranchFn.apply(block_in, rconv.weight, rbn.weight, rbn.bias, rconv, rbn)
             else:
-                zr = torch.empty((h.shape[0], t, rconv.out_channels), dtype=torch.bfloat16, device=h.device)
+                zr = torch.empty((h.shape[0], t, rconv.out_channels), dtype=rconv.act_dtype, device=h.device)
                 F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
                 res_pair = (zr, rbn.eval_scale_shift(None))
 
@@ -269,6 +269,20 @@ class Jasper(ConvCTCASR):
         last = self.jasper_encoder[-1].mconv[-1].num_features
         self.final_layer = nn.Sequential(ConvParams(last, len(self.labels), 1, bias=True))
         self.final_layer.apply(init_weights)
+        # precision: "bf16" (default) or "tf32" -- the fp32-faithful mode (fp32 activations / weights / gradients in memory, tf32
+        # multiplies, fp32 accumulation; see Wav2Letter).  Dense blocks only: the depthwise kernels of separable blocks and the
+        # time-major unfold of strided inner blocks exist for bf16 activations.
+        self.precision = str(getattr(cfg, "precision", "bf16") or "bf16").lower()
+        if self.precision in ("fp32", "float32"):
+            self.precision = "tf32"
+        if self.precision not in ("bf16", "tf32"):
+            raise ValueError("Jasper: precision must be 'bf16' or 'tf32', got %r" % (self.precision,))
+        if self.precision == "tf32":
+            convs = [m for m in self.modules() if isinstance(m, ConvParams)]
+            if any(isinstance(m, DepthwiseParams) for m in self.modules()) or any(c.unfold for c in convs[1:]):
+                raise NotImplementedError("Jasper: precision='tf32' is implemented for dense, unstrided blocks (separable: false)")
+            for c in convs:
+                c.f32 = True
 
     def _build_encoder(self, cfg):
         width, blocks = self.input_size, []
