@@ -42,6 +42,9 @@ extern "C" {
  * w2l_bn_act_bwd_reduce, w2l_bn_act_bwd_apply): the activation buffers of the call (z, res, y / dyp, dz, g_out) are fp32
  * instead of bf16 -- the fp32-faithful mode, whose GEMMs run with w2l_conv_desc::x_dtype = W2L_DTYPE_F32 */
 #define W2L_STORE_F32 0x100
+/* OR-ed into the `act` argument of w2l_bn_act_bwd_apply: red[C:2C] holds the RAW sums of g * (z - mean) that
+ * w2l_conv1d_dgrad_wt_bnred accumulated; the pass multiplies them by invstd itself */
+#define W2L_RED_RAW 0x200
 
 int w2l_version(void);
 const char* w2l_last_error(void);
@@ -173,6 +176,27 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
  * dy rows hold Cout_pad columns (ldy >= Cout_pad, zero padded) or just Cout columns (Cout <= ldy < Cout_pad: hidden widths
  * that are multiples of 8 but not of 16); in the latter case the tail of the last contraction chunk reads as zero. */
 int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream);
+/* The same backward-data GEMM with the BatchNorm-backward REDUCTION of the block below folded into its epilogue.  dx is the
+ * gradient with respect to that block's (halo-padded) output y [red->B, pad_left + T + pad_right, Cin]; the rows are in registers
+ * when they are stored, so the epilogue also accumulates what w2l_bn_act_bwd_reduce would compute in a separate pass over (dy, z):
+ *   red[0:C]  += sum_rows g,   red[C:2C] += sum_rows g * (z - mean)        g = gate(z*scale + shift) * keep-bit * dx/keep
+ * (a reflect-halo row counts with the z / gate of the interior row it mirrors; rows t >= lens[b] carry none).  red[C:2C] is RAW --
+ * not yet multiplied by invstd: the apply pass takes it with W2L_RED_RAW OR-ed into its `act`.  bf16 activations, blocks without
+ * a residual branch; with dropout the stored keep-bits are required.  Replaces one pass of nn.BatchNorm1d / clamp backward
+ * (wav2letter.py:43-46, jasper.py:363-376) per layer. */
+typedef struct {
+  const void* z;          /* the block's conv output, bf16 [B, T, C], C = the Cin of the GEMM's descriptor */
+  const void* drop_mask;  /* keep-bits [B*T*C/8] written by the forward pass, or NULL (no dropout) */
+  const float* scale;     /* the block's BatchNorm scale, shift, batch mean [C] (fin rows 0, 1, 2) */
+  const float* shift;
+  const float* mean;
+  const int32_t* lens;    /* nullable */
+  float* red;             /* fp32 [2C], accumulated into (zero before the launch) */
+  int32_t B, T, pad_left, pad_right;
+  int32_t act;            /* W2L_ACT_* of the block */
+  float drop_p;
+} w2l_bn_reduce;
+int w2l_conv1d_dgrad_wt_bnred(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, const w2l_bn_reduce* red, void* stream);
 int w2l_pack_wt(const float* w, void* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);
 /* the same shadow in fp32 (operand of w2l_conv1d_dgrad_wt with x_dtype = F32) */
 int w2l_pack_wt_f32(const float* w, float* wt, int32_t k, int32_t Cout, int32_t Cin, int32_t Cout_pad, int32_t Cin_pad, void* stream);

@@ -103,7 +103,8 @@ def ctc():
 
 
 # ------------------------------------------------------------------------------------------------ layout (elementwise.cu)
-def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
+def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None, out_dtype=torch.bfloat16):
+    assert out_dtype == torch.bfloat16, "the fp32-faithful mode is covered by the C-ABI emulation (tests/_emu_cabi.py) and the -m gpu tests"
     """w2l_im2col_ncw (elementwise.cu:713-733)"""
     x = x.contiguous().float()
     B, F, T = x.shape
@@ -263,7 +264,8 @@ def log_softmax(logits, C, mode=0, nan_flag=None):
     return out
 
 
-def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
+def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False, out_dtype=torch.bfloat16):
+    assert out_dtype == torch.bfloat16
     """w2l_log_softmax_bwd (elementwise.cu:875-883)"""
     C = g.shape[-1]
     rows = g.numel() // C

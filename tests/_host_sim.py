@@ -42,7 +42,8 @@ def _row_mask(lens, B, T):
 
 
 # ------------------------------------------------------------------------------------------------ layout
-def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None):
+def im2col_ncw(x, rows, k, stride, dilation, pad_left, pad_mode, lens=None, out_dtype=torch.bfloat16):
+    assert out_dtype == torch.bfloat16, "the fp32-faithful mode is covered by the C-ABI emulation (tests/_emu_cabi.py) and the -m gpu tests"
     x = x.contiguous().float()
     B, F, T = x.shape
     t = (torch.arange(rows).view(rows, 1) * stride + torch.arange(k).view(1, k) * dilation - pad_left)      # [rows, k]
@@ -223,7 +224,8 @@ def log_softmax(logits, C, mode=0, nan_flag=None):
     return out.contiguous()
 
 
-def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False):
+def log_softmax_bwd(g, lp, ld_out, gscale=None, fused_identity=False, out_dtype=torch.bfloat16):
+    assert out_dtype == torch.bfloat16
     C = g.shape[-1]
     v = g.float()
     if not fused_identity:

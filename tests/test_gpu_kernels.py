@@ -343,6 +343,53 @@ def test_conv_fp32_operands_tf32(F, B, T, Cin, Cout, k, d, pad):
     assert rel_l2(dw.cpu(), dw_t) < 2e-5 and rel_l2(dw.cpu(), dw_f) < 1.5e-3
 
 
+@pytest.mark.parametrize("B,T,C,Co,k,d,pl,pr,act,drop,flat,masked", [
+    (3, 150, 256, 128, 5, 1, 2, 2, 2, 0.0, True, False),       # Wav2Letter: reflect halo (k-1)d/2 each side, clamp, one flat row space
+    (2, 140, 896, 64, 29, 2, 28, 28, 2, 0.25, True, False),    # halo 28, dropout keep-bits, 4 N tiles of 224
+    (4, 97, 264, 96, 3, 1, 0, 0, 1, 0.0, False, True),         # Jasper: no halo, ReLU, length mask, C not a multiple of 32
+    (2, 260, 128, 256, 7, 1, 3, 3, 1, 0.1, False, False),      # per-utterance launch with a halo
+])
+def test_dgrad_fused_bn_reduce(F, gemm_kernel, B, T, C, Co, k, d, pl, pr, act, drop, flat, masked):
+    """w2l_conv1d_dgrad_wt_bnred: the BatchNorm-backward reduction of the block that produced a layer's input, formed in the epilogue
+    of that layer's backward-data GEMM -- against the separate reduce pass over the gradient the plain GEMM stored (sums to fp32
+    summation order), and the apply pass fed with the raw sums (W2L_RED_RAW) against the two-pass result"""
+    g = torch.Generator().manual_seed(B * T + C + k)
+    Tp = pl + T + pr                                 # rows of the block's padded output = this conv's input
+    halo = (k - 1) * d
+    T_out = Tp - halo                                # this conv's output rows (valid convolution over the padded input)
+    z = _bf(torch.randn(B, T, C, generator=g) * 1.5 + 0.3).to(torch.bfloat16).cuda()          # the block's conv output
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    stats = F.bn_stats(z, C)
+    fin = F.bn_finalize(stats, B * T, C, gamma, beta, None, 1e-3, 0.1, torch.zeros(C, device="cuda"), torch.ones(C, device="cuda"))
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g, dtype=torch.int32).cuda() if masked else None
+    seed, mask = 77, (torch.zeros(B * T * C // 8, dtype=torch.uint8, device="cuda") if drop > 0 else None)
+    F.bn_act_pad(z, fin[0], fin[1], B, T, C, pl, pr, act, drop, seed, lens, drop_mask=mask)   # (writes the keep-bits)
+    w = _bf(torch.randn(Co, C, k, generator=g) / (C * k) ** 0.5)
+    dy = _bf(torch.randn(B, T_out, Co, generator=g))
+    wt = torch.empty(k, (C + 15) // 16 * 16, max(64, (Co + 15) // 16 * 16), dtype=torch.bfloat16, device="cuda")
+    F.pack_wt(w.permute(2, 0, 1).contiguous().cuda(), wt, Co, C)
+    cout_pad = wt.shape[2]
+    dz_up = torch.zeros(B, Tp if flat else T_out, cout_pad, dtype=torch.bfloat16, device="cuda")      # the layer's own dz, zero tails when flat
+    dz_up[:, :T_out, :Co] = dy.to(torch.bfloat16).cuda()
+    desc = (F.make_desc(1, B * Tp, C, Co, cout_pad, k, d, B * Tp, 0, B * Tp, 0, cout_pad) if flat
+            else F.make_desc(B, T_out, C, Co, cout_pad, k, d, Tp, 0, T_out, 0, cout_pad))
+    # ---- two-pass reference: plain GEMM, then reduce + apply over what it stored
+    dx_a = torch.empty(B, Tp, C, dtype=torch.bfloat16, device="cuda")
+    F.conv1d_dgrad_wt(dz_up, wt, desc, dx_a)
+    dz_a, red_a, _ = F.bn_act_bwd(dx_a, z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, C, pl, pr, act, drop, seed, lens, drop_mask=mask)
+    # ---- fused: the GEMM's epilogue accumulates the raw sums, the apply pass takes them
+    dx_b = torch.empty_like(dx_a)
+    red_raw = torch.zeros(2 * C, device="cuda")
+    F.conv1d_dgrad_wt(dz_up, wt, desc, dx_b, bnred=dict(z=z, mask=mask, scale=fin[0], shift=fin[1], mean=fin[2], lens=lens, red=red_raw, B=B, T=T,
+                                                       pad_left=pl, pad_right=pr, act=act, drop_p=drop))
+    assert torch.equal(dx_a, dx_b)
+    dz_b, red_b, _ = F.bn_act_bwd(dx_b, z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, C, pl, pr, act, drop, seed, lens, drop_mask=mask,
+                                  red_raw=red_raw)
+    scale_ref = float(red_a.abs().max())
+    assert float((red_b - red_a).abs().max()) < 2e-4 * max(scale_ref, 1.0), float((red_b - red_a).abs().max())
+    assert rel_l2(red_b, red_a) < 1e-4 and rel_l2(dz_b.float(), dz_a.float()) < 2e-3
+
+
 @pytest.mark.parametrize("B,T,C,Co,k,d", [(3, 200, 64, 128, 5, 1), (5, 131, 128, 64, 7, 2), (2, 750, 256, 256, 11, 1)])
 def test_conv_dgrad_flat_prepadded(F, gemm_kernel, B, T, C, Co, k, d):
     """Wav2Letter layout: the input carries its own halo (x_rows = T + (k-1)d), dz is stored with the input's row pitch and zero

@@ -98,6 +98,13 @@ class ConvDesc(ctypes.Structure):
                                      "y_rows", "y_row_offset", "ldy", "y_dtype", "act", "x_dtype")]
 
 
+class BnReduce(ctypes.Structure):
+    """Mirror of w2l_bn_reduce: the BatchNorm-backward reduction folded into the epilogue of w2l_conv1d_dgrad_wt_bnred."""
+    _fields_ = [("z", ctypes.c_void_p), ("drop_mask", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+                ("mean", ctypes.c_void_p), ("lens", ctypes.c_void_p), ("red", ctypes.c_void_p), ("B", c_i32), ("T", c_i32),
+                ("pad_left", c_i32), ("pad_right", c_i32), ("act", c_i32), ("drop_p", ctypes.c_float)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/w2l_sm100.h appears here
 SIGNATURES = {
     "w2l_version": (c_i32, []),
@@ -130,6 +137,7 @@ SIGNATURES = {
     "w2l_log_softmax_bwd_f32": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_pack_wt_f32": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_conv1d_dgrad_wt_bnred": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), ctypes.POINTER(BnReduce), c_ptr]),
     "w2l_conv1d_wgrad_t": (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_tm_to_ct_f32": (c_i32, [c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr]),
     "w2l_depthwise_fwd": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),

@@ -32,7 +32,7 @@ constexpr int kBBytesMax = 256 * kBlockK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytesMax;
 constexpr int kAccCols = 256;
 constexpr int kGemmThreads = 192;
-constexpr int kAffBytes = 2 * 256 * 8;          // per-accumulator (scale, shift) of the tile's columns for the epilogue
+constexpr int kAffBytes = 2 * 256 * 8 + 2 * 256 * 4;   // per-accumulator (scale, shift) [+ mean: the fused BatchNorm-backward reduction] of the tile's columns
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kAffBytes;
 constexpr int kSlabBufs = 3;                    // slab mode: the next chunk's slab is requested a whole chunk ahead
 constexpr size_t kGemmSmemMax = 227 * 1024;     // opt-in limit per CTA on sm_100
@@ -89,6 +89,20 @@ struct GemmParams {
   int32_t c2_ngroup;        // N tiles that run side by side on the same activation rows (their weight slices stay in L2 together)
   int32_t c2_k;             // wgrad pair kernel: the real tap count (p.k then counts tap PAIRS)
   int32_t c2_npad;          // fwd-kind pair kernel: padded column count (the last N tile covers [.., c2_npad))
+  // Backward-data GEMM of the layer ABOVE a BatchNorm block (w2l_conv1d_dgrad_wt_bnred): the rows this launch produces are the
+  // gradient with respect to that block's padded OUTPUT, so its epilogue also forms the block's backward reduction --
+  // r_red[0:C] += sum g, r_red[C:2C] += sum g * (z - mean), g = gate(z) * keep-bit * (this row's gradient, as stored) -- and the
+  // separate pass over (dy, z) that w2l_bn_act_bwd_reduce would make is not needed.  A reflect-halo row contributes with the z /
+  // gate of the interior row it mirrors, which is exactly the halo fold of that pass.
+  const __nv_bfloat16* r_z;     // the block's conv output [r_B, r_T, C], C = N_valid
+  const uint8_t* r_mask;        // dropout keep-bits (nullable)
+  const float* r_scale;         // the block's BatchNorm scale / shift / mean [C]
+  const float* r_shift;
+  const float* r_mean;
+  const int32_t* r_lens;        // nullable: rows t >= r_lens[b] carry no gradient
+  float* r_red;                 // null: no fused reduction
+  int32_t r_B, r_T, r_pl, r_Tp, r_act;
+  float r_inv_keep;             // 1 without dropout
   // fp32-faithful mode (w2l_conv_desc::x_dtype == F32): operands are fp32 in memory, multiplied as tf32 (kind::tf32, K = 8 per
   // MMA).  A 128-byte swizzle row then holds 32 elements, so a K-step covers kblk = 32 channels (fwd/dgrad) or 32 rows (wgrad);
   // every byte offset of the pipeline (stage sizes, 32 bytes per MMA along K) is the same as with bf16.
@@ -213,7 +227,65 @@ __device__ __forceinline__ float warp_column_sum32(float (&x)[32], int lane) {
 // batch statistics of what is stored -> bf16 / fp32 store.  `aff` = this chunk's (scale, shift) pairs in shared memory.
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int c0, int nbase, const float2* aff, bool has_aff,
-                                               bool has_act, float act_hi, bool row_ok, int b, int m, int lane) {
+                                               bool has_act, float act_hi, bool row_ok, int b, int m, int lane,
+                                               const float* mean = nullptr) {
+  if (MODE == MODE_FWD && p.r_red != nullptr) {      // kernel-uniform: fused BatchNorm-backward reduction of the block below (see GemmParams)
+    // (utterance, interior row) of the block's output that this row of the gradient belongs to: M_valid rows per launch batch entry
+    // (r_Tp per utterance; the flat launch covers all utterances in one batch entry)
+    const int64_t flat = (int64_t)b * p.M_valid + m;
+    const int bb = (int)(flat / p.r_Tp);
+    int t = (int)(flat - (int64_t)bb * p.r_Tp) - p.r_pl;
+    if (t < 0) t = -t;                                 // left halo row: mirrors interior row pl - p
+    else if (t >= p.r_T) t = 2 * (p.r_T - 1) - t;      // right halo row
+    const bool live = row_ok && bb < p.r_B && !(p.r_lens != nullptr && t >= __ldg(p.r_lens + bb));
+    float s1[32], s2[32];
+    if (live) {
+      const int64_t e = ((int64_t)bb * p.r_T + t) * p.N_valid + nbase;
+      const bool full = (c0 + 32 <= p.BN) && (nbase + 32 <= p.N_valid);
+      float zf[32];
+      if (full) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 zq = __ldg(reinterpret_cast<const uint4*>(p.r_z + e) + q4);
+          const uint32_t w4[4] = {zq.x, zq.y, zq.z, zq.w};                   // two bf16 per word: value = the 16 bits as the top of an fp32
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            zf[q4 * 8 + 2 * i] = __uint_as_float(w4[i] << 16);
+            zf[q4 * 8 + 2 * i + 1] = __uint_as_float(w4[i] & 0xFFFF0000u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zf[i] = (c0 + i < p.BN && nbase + i < p.N_valid) ? __bfloat162float(p.r_z[e + i]) : 0.f;
+      }
+      uint32_t bits = 0xFFFFFFFFu;
+      if (p.r_mask != nullptr) {
+        bits = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (nbase + 8 * q < p.N_valid) bits |= (uint32_t)__ldg(p.r_mask + ((e + 8 * q) >> 3)) << (8 * q);
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool col_ok = (c0 + i < p.BN) && (nbase + i < p.N_valid);
+        const float2 a = aff[i];                                              // (scale, shift) of the block, 1/keep folded in
+        const float pre = fmaf(zf[i], a.x, a.y);
+        const bool pass = p.r_act == W2L_ACT_RELU ? pre > 0.f : p.r_act == W2L_ACT_CLAMP20 ? (pre >= 0.f && pre <= 20.f) : true;
+        const float gq = __bfloat162float(__float2bfloat16_rn(v[i])) * p.r_inv_keep;   // the gradient as the apply pass will read it
+        const float g = (col_ok && pass && ((bits >> i) & 1u)) ? gq : 0.f;
+        s1[i] = g;
+        s2[i] = g * (zf[i] - mean[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.f;
+    }
+    const float c1 = warp_column_sum32(s1, lane), c2 = warp_column_sum32(s2, lane);
+    if (c0 + lane < p.BN && nbase + lane < p.N_valid) {
+      atomicAdd(p.r_red + nbase + lane, c1);
+      atomicAdd(p.r_red + p.N_valid + nbase + lane, c2);
+    }
+  }
   if (has_aff) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -273,6 +345,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
   }
 }
 
+// per-tile epilogue constants into shared memory (the epilogue warps, ep_tid = 0..127; a bar.sync of the 128 follows): the fused
+// affine terms of a forward launch, or -- backward-data with the fused BatchNorm-backward reduction -- the block's scale / shift with
+// the dropout factor folded in, and its mean
+__device__ __forceinline__ void stage_epilogue_constants(const GemmParams& p, float2* aff, float* mean, int n0, int ep_tid, bool has_aff) {
+  for (int c = ep_tid; c < p.BN; c += 128) {
+    const int n = min(n0 + c, p.N_valid - 1);
+    if (has_aff) {
+      const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
+      const float sh = (p.bias ? __ldg(p.bias + n) * sc : 0.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
+      aff[c] = make_float2(sc, sh);
+    } else {
+      aff[c] = make_float2(__ldg(p.r_scale + n) * p.r_inv_keep, __ldg(p.r_shift + n) * p.r_inv_keep);
+      mean[c] = __ldg(p.r_mean + n);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -291,6 +380,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
   const bool slab_mode = (MODE == MODE_FWD) && p.slab_rows > 0;
   const uint32_t slab_bytes = (uint32_t)p.slab_bytes, b_ring_off = kSlabBufs * slab_bytes;
   float2* s_aff = reinterpret_cast<float2*>(smem + p.ring_bytes + 256);   // [2][256]
+  float* s_mean = reinterpret_cast<float*>(s_aff + 2 * 256);               // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool kAMN = (MODE == MODE_WGRAD);
@@ -504,19 +594,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
     uint32_t acc_phase = 0;
     // fused epilogue: v = clamp(acc * scale + shift', lo, hi) with shift' = bias * scale + shift (kernel-uniform switches)
     const bool has_aff = (MODE == MODE_FWD) && (p.bias != nullptr || p.scale != nullptr);
+    const bool has_red = (MODE == MODE_FWD) && p.r_red != nullptr;      // (never together with has_aff: forward vs backward-data launches)
     const bool has_act = (MODE == MODE_FWD) && p.act != W2L_ACT_NONE;
     const float act_hi = p.act == W2L_ACT_CLAMP20 ? 20.f : INFINITY;
     const int ep_tid = threadIdx.x - 64;                       // 0..127 within the epilogue warps
     UnitIter<MODE> units(p);
     Unit tc;
     while (units.next(tc)) {
-      if (has_aff) {                                           // stage this tile's per-channel constants (broadcast reads below)
-        for (int c = ep_tid; c < p.BN; c += 128) {
-          const int n = min(tc.n0 + c, p.N_valid - 1);
-          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
-          const float sh = (p.bias ? __ldg(p.bias + n) * sc : 0.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
-          s_aff[acc * 256 + c] = make_float2(sc, sh);
-        }
+      if (has_aff || has_red) {                                // stage this tile's per-channel constants (broadcast reads below)
+        stage_epilogue_constants(p, s_aff + acc * 256, s_mean + acc * 256, tc.n0, ep_tid, has_aff);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -525,7 +611,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_gemm_kernel(const __grid
       const int m = tc.m0 + row;
       const bool row_ok = m < p.M_valid;
       auto finish_chunk = [&](float (&v)[32], int c0, int nbase) {
-        epilogue_chunk<MODE>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, tc.b, m, lane);
+        epilogue_chunk<MODE>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, tc.b, m, lane,
+                             s_mean + acc * 256 + c0);
       };
       if (MODE != MODE_WGRAD && tc.partial) {
         // ---- fwd tail split: this CTA computed one K piece of the tile.  Park the fp32 partial in the scratch slot, free the
@@ -685,6 +772,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* s_aff = reinterpret_cast<float2*>(smem + kC2Stages * kC2StageBytes + 256);   // [2][256]
+  float* s_mean = reinterpret_cast<float*>(s_aff + 2 * 256);                            // [2][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -784,19 +872,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool has_aff = p.bias != nullptr || p.scale != nullptr;
+    const bool has_red = p.r_red != nullptr;
     const bool has_act = p.act != W2L_ACT_NONE;
     const float act_hi = p.act == W2L_ACT_CLAMP20 ? 20.f : INFINITY;
     const int ep_tid = threadIdx.x - 64;
     PairTile u;
     for (int t = pair; t < p.num_tiles; t += npairs) {
       decode_pair(p, t, (int)rank, u);
-      if (has_aff) {
-        for (int c = ep_tid; c < p.BN; c += 128) {
-          const int n = min(u.n0 + c, p.N_valid - 1);
-          const float sc = p.scale ? __ldg(p.scale + n) : 1.f;
-          const float sh = (p.bias ? __ldg(p.bias + n) * sc : 0.f) + (p.shift ? __ldg(p.shift + n) : 0.f);
-          s_aff[acc * 256 + c] = make_float2(sc, sh);
-        }
+      if (has_aff || has_red) {
+        stage_epilogue_constants(p, s_aff + acc * 256, s_mean + acc * 256, u.n0, ep_tid, has_aff);
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -814,7 +898,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) con
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_chunk<MODE_FWD>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, u.b, m, lane);
+        epilogue_chunk<MODE_FWD>(p, v, c0, nbase, s_aff + acc * 256 + c0, has_aff, has_act, act_hi, row_ok, u.b, m, lane,
+                                 s_mean + acc * 256 + c0);
       }
       tc_fence_before();
       __syncwarp();
@@ -1348,7 +1433,7 @@ int w2l_conv1d_dgrad(const void* dy, const void* w, void* dx, const w2l_conv_des
   return launch_gemm<MODE_DGRAD>(p, (cudaStream_t)stream);
 }
 
-int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream) {
+static int dgrad_wt_impl(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, const w2l_bn_reduce* red, void* stream) {
   // Backward-data as a FORWARD implicit GEMM over dy with tap-reversed, transposed weights wt[k-1-j][ci][co] = w[j][co][ci]:
   //   dx[u, ci] = sum_{j'} sum_co dy[u - off - (k-1)d + j'd, co] * wt[j'][ci][co]      (both operands K-major)
   using namespace w2l;
@@ -1402,12 +1487,53 @@ int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv
   p.y_row_off = 0;
   p.ldy = d->Cin;
   p.splits = 1;
+  if (red != nullptr) {                // fold the BatchNorm-backward reduction of the block below into the epilogue
+    const int Tp = red->pad_left + red->T + red->pad_right;
+    W2L_REQUIRE(!p.tf32, "conv1d_dgrad_wt_bnred: bf16 activations only");
+    W2L_REQUIRE(red->z && red->scale && red->shift && red->mean && red->red, "conv1d_dgrad_wt_bnred: null pointer");
+    W2L_REQUIRE(red->B >= 1 && red->T >= 1 && red->pad_left >= 0 && red->pad_right >= 0 && red->pad_left < red->T && red->pad_right < red->T,
+                "conv1d_dgrad_wt_bnred: bad block geometry");
+    W2L_REQUIRE((int64_t)red->B * Tp == (int64_t)d->B * d->x_rows, "conv1d_dgrad_wt_bnred: %d x %d padded rows of the block do not match the %d x %d rows of dx",
+                red->B, Tp, d->B, d->x_rows);
+    W2L_REQUIRE(d->B == 1 || d->x_rows == Tp, "conv1d_dgrad_wt_bnred: dx rows per batch entry must be the block's padded rows (or one flat entry)");
+    W2L_REQUIRE(red->act >= 0 && red->act <= 2 && red->drop_p >= 0.f && red->drop_p < 1.f, "conv1d_dgrad_wt_bnred: bad activation / dropout");
+    W2L_REQUIRE(!(red->drop_p > 0.f) || red->drop_mask, "conv1d_dgrad_wt_bnred: dropout needs the stored keep-bits");
+    p.r_z = reinterpret_cast<const __nv_bfloat16*>(red->z);
+    p.r_mask = reinterpret_cast<const uint8_t*>(red->drop_mask);
+    p.r_scale = red->scale;
+    p.r_shift = red->shift;
+    p.r_mean = red->mean;
+    p.r_lens = red->lens;
+    p.r_red = red->red;
+    p.r_B = red->B;
+    p.r_T = red->T;
+    p.r_pl = red->pad_left;
+    p.r_Tp = Tp;
+    p.r_act = red->act;
+    p.r_inv_keep = 1.f;
+    if (red->drop_p > 0.f) {           // the passes' 12-bit keep probability (elementwise.cu drop_quant): the SAME quantisation
+      const uint32_t one = 1u << 12;
+      uint32_t q = (uint32_t)((1.0 - (double)red->drop_p) * (double)one + 0.5);
+      if (q < 1) q = 1;
+      if (q > one - 1) q = one - 1;
+      p.r_inv_keep = (float)((double)one / (double)q);
+    }
+  }
   if (cg2) {
     plan_cg2(p, (int64_t)d->k * p.BN * d->Cout_pad * 2);
     return launch_gemm_cg2(p, (cudaStream_t)stream);
   }
   p.tail_first = p.num_tiles;          // backward-data overlaps with wgrad, whose CTAs fill its last wave: no tail split here
   return launch_gemm<MODE_FWD>(p, (cudaStream_t)stream);
+}
+
+int w2l_conv1d_dgrad_wt(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, void* stream) {
+  return dgrad_wt_impl(dy, wt, dx, d, nullptr, stream);
+}
+
+int w2l_conv1d_dgrad_wt_bnred(const void* dy, const void* wt, void* dx, const w2l_conv_desc* d, const w2l_bn_reduce* red, void* stream) {
+  W2L_REQUIRE(red != nullptr, "conv1d_dgrad_wt_bnred: null reduction descriptor");
+  return dgrad_wt_impl(dy, wt, dx, d, red, stream);
 }
 
 int32_t w2l_conv1d_wgrad_splits(const w2l_conv_desc* d) {

@@ -357,6 +357,7 @@ struct BnBwdArgs {
   float* zero_ptr;             // apply pass: a small buffer cleared for a LATER kernel (the layer's forward statistics)
   int zero_count;
   int rows_per_block;
+  int red_raw;                 // apply pass: red[C:2C] holds raw sums of g*(z-mean) (from the GEMM epilogue, W2L_RED_RAW): scale by invstd here
 };
 
 // NaN passes through the activations, as torch.relu / torch.clamp do (fmaxf / fminf would swallow it): one instruction each
@@ -688,6 +689,10 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
     load8f(a.red + c, sg);
     load8f(a.red + a.C + c, sx);
     if (a.gamma) load8f(a.gamma + c, ga);
+    if (a.red_raw) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sx[i] *= is[i];
+    }
     if (a.red_out && rb == 0 && threadIdx.y == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -948,7 +953,7 @@ static int check_bn_args(const char* who, const void* z, const void* res, const 
   W2L_REQUIRE(pl >= 0 && pr >= 0 && pl < T && pr < T, "%s: reflect halo (%d,%d) must be smaller than T=%d", who, pl, pr, T);
   W2L_REQUIRE((int64_t)B * (T + pl + pr) < (1ll << 31) / 8, "%s: B*T too large", who);
   W2L_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p=%f out of [0,1)", who, drop_p);
-  W2L_REQUIRE((act & ~W2L_STORE_F32) >= 0 && (act & ~W2L_STORE_F32) <= 2, "%s: unknown activation %d", who, act);
+  W2L_REQUIRE((act & ~(W2L_STORE_F32 | W2L_RED_RAW)) >= 0 && (act & ~(W2L_STORE_F32 | W2L_RED_RAW)) <= 2, "%s: unknown activation %d", who, act);
   return W2L_OK;
 }
 
@@ -1203,6 +1208,7 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   W2L_REQUIRE(zero_count >= 0 && (zero_ptr != nullptr || zero_count == 0), "bn_act_bwd_apply: bad zero buffer");
   W2L_REQUIRE(zero_ptr == nullptr || zero_ptr != red, "bn_act_bwd_apply: the buffer to clear must not be the reduction this pass reads");
   a.gamma = gamma;
+  a.red_raw = (act & W2L_RED_RAW) != 0;
   a.dz = dz;
   a.dz_rows = dz_rows;
   a.g_out = g_out;

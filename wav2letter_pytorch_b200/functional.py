@@ -8,11 +8,12 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvDesc
+from ._lib import BnReduce, ConvDesc
 
 ACT_NONE, ACT_RELU, ACT_CLAMP20 = 0, 1, 2
 PAD_ZERO, PAD_REFLECT = 0, 1
 DT_BF16, DT_F32 = 0, 1
+RED_RAW = 0x200            # W2L_RED_RAW: the apply pass takes raw sums of g*(z-mean) from the GEMM epilogue
 STORE_F32 = 0x100          # W2L_STORE_F32: OR-ed into `act` when the activation buffers of a BatchNorm / activation pass are fp32
 
 
@@ -176,11 +177,21 @@ def conv1d_dgrad(dy, w, desc, dx):
     return dx
 
 
-def conv1d_dgrad_wt(dy, wt, desc, dx):
-    """backward-data with the transposed (K-major) weight shadow; see w2l_conv1d_dgrad_wt"""
+def conv1d_dgrad_wt(dy, wt, desc, dx, bnred=None):
+    """backward-data with the transposed (K-major) weight shadow; see w2l_conv1d_dgrad_wt.  ``bnred`` (dict: z, mask, scale, shift,
+    mean, lens, red, B, T, pad_left, pad_right, act, drop_p) folds the BatchNorm-backward reduction of the block that PRODUCED this
+    layer's input into the epilogue (w2l_conv1d_dgrad_wt_bnred): ``red`` [2C] fp32, zero on entry, receives sum g and the raw
+    sum g*(z-mean)."""
     _need_cuda(dy, wt, dx)
     with _on(dy.device):
-        _lib.check(_lib.load().w2l_conv1d_dgrad_wt(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad_wt")
+        if bnred is None:
+            _lib.check(_lib.load().w2l_conv1d_dgrad_wt(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(desc), _stream()), "conv1d_dgrad_wt")
+        else:
+            p = lambda t: None if t is None else t.data_ptr()       # noqa: E731
+            r = BnReduce(p(bnred["z"]), p(bnred.get("mask")), p(bnred["scale"]), p(bnred["shift"]), p(bnred["mean"]), p(bnred.get("lens")),
+                         p(bnred["red"]), bnred["B"], bnred["T"], bnred["pad_left"], bnred["pad_right"], bnred["act"], float(bnred.get("drop_p", 0.0)))
+            _lib.check(_lib.load().w2l_conv1d_dgrad_wt_bnred(_ptr(dy), _ptr(wt), _ptr(dx), ctypes.byref(desc), ctypes.byref(r), _stream()),
+                       "conv1d_dgrad_wt_bnred")
     return dx
 
 
@@ -401,14 +412,17 @@ def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running
 
 
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None):
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None,
+               red_raw=None):
     """Returns (dz bf16 [B, dz_rows, C] (rows >= T zero), red fp32 [2C] = (dbeta, dgamma), g bf16 [B,T,C] | None).
     ``red_ws`` (fp32 [2C], ZERO on entry, dirty afterwards): a persistent accumulation buffer -- the sums are then returned in a
     fresh tensor and no memset launch is needed; without it a zero-filled buffer is allocated per call.  ``zero_after`` (fp32
     tensor, optional) is cleared by the second pass for a later kernel."""
     dev = z.device
     dz_rows = T if dz_rows is None else dz_rows
-    if red_ws is None:
+    if red_raw is not None:        # the reduction came out of the backward-data GEMM's epilogue (conv1d_dgrad_wt(bnred=...)): apply only
+        red, red_out = red_raw, torch.empty((2 * C,), dtype=torch.float32, device=dev)
+    elif red_ws is None:
         red = torch.zeros((2 * C,), dtype=torch.float32, device=dev)
         red_out = None
     else:
@@ -420,12 +434,14 @@ def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad
     act = _act_flag(act, z)
     lib = _lib.load()
     with _on(dev):
-        _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
-                                             _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
-                                             int(seed), _ptr(lens), _ptr(drop_mask), _stream()), "bn_act_bwd_reduce")
+        if red_raw is None:
+            _lib.check(lib.w2l_bn_act_bwd_reduce(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
+                                                 _ptr(mean), _ptr(invstd), _ptr(red), B, T, C, pad_left, pad_right, act, float(drop_p),
+                                                 int(seed), _ptr(lens), _ptr(drop_mask), _stream()), "bn_act_bwd_reduce")
         _lib.check(lib.w2l_bn_act_bwd_apply(_ptr(dyp), _ptr(z), _ptr(res), _ptr(scale), _ptr(shift), _ptr(res_scale), _ptr(res_shift),
                                             _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(red), _ptr(dz), dz_rows, _ptr(g), B, T, C,
-                                            pad_left, pad_right, act, float(drop_p), int(seed), _ptr(lens), _ptr(drop_mask),
+                                            pad_left, pad_right, act | (RED_RAW if red_raw is not None else 0), float(drop_p), int(seed),
+                                            _ptr(lens), _ptr(drop_mask),
                                             _ptr(red_out), _ptr(zero_after), 0 if zero_after is None else zero_after.numel(),
                                             _stream()), "bn_act_bwd_apply")
     return dz, (red if red_out is None else red_out), g
