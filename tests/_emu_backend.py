@@ -518,7 +518,7 @@ def gemm():
     from wav2letter_pytorch_b200 import _lib
     K = KE.build(["conv_gemm.cu"], [], helpers_from_common=("pack_bf16x2", "make_smem_desc", "make_idesc_bf16"), subs=GEMM_SUBS,
                  drop=GEMM_DROP, c_abi=True, post=GEMM_POST, opt="-O2")
-    for name in ("w2l_conv1d_fwd", "w2l_conv1d_dgrad", "w2l_conv1d_dgrad_wt", "w2l_conv1d_wgrad", "w2l_conv1d_wgrad_splits",
+    for name in ("w2l_conv1d_fwd", "w2l_conv1d_dgrad", "w2l_conv1d_dgrad_wt", "w2l_conv1d_dgrad_wt_bnred", "w2l_conv1d_wgrad", "w2l_conv1d_wgrad_splits",
                  "w2l_set_gemm_scratch", "w2l_conv1d_fwd_tail_parts"):
         res, args = _lib.SIGNATURES[name]
         fn = getattr(K.lib, name)
@@ -559,8 +559,15 @@ def conv1d_dgrad(dy, w, desc, dx):
     return dx
 
 
-def conv1d_dgrad_wt(dy, wt, desc, dx):
-    _gemm_check(gemm().lib.w2l_conv1d_dgrad_wt(_p(dy), _p(wt), _p(dx), ctypes.byref(desc), None), "conv1d_dgrad_wt")
+def conv1d_dgrad_wt(dy, wt, desc, dx, bnred=None):
+    if bnred is None:
+        _gemm_check(gemm().lib.w2l_conv1d_dgrad_wt(_p(dy), _p(wt), _p(dx), ctypes.byref(desc), None), "conv1d_dgrad_wt")
+        return dx
+    from wav2letter_pytorch_b200._lib import BnReduce
+    q = lambda t: None if t is None else t.data_ptr()       # noqa: E731
+    r = BnReduce(q(bnred["z"]), q(bnred.get("mask")), q(bnred["scale"]), q(bnred["shift"]), q(bnred["mean"]), q(bnred.get("lens")), q(bnred["red"]),
+                 bnred["B"], bnred["T"], bnred["pad_left"], bnred["pad_right"], bnred["act"], float(bnred.get("drop_p", 0.0)))
+    _gemm_check(gemm().lib.w2l_conv1d_dgrad_wt_bnred(_p(dy), _p(wt), _p(dx), ctypes.byref(desc), ctypes.byref(r), None), "conv1d_dgrad_wt_bnred")
     return dx
 
 
@@ -584,6 +591,9 @@ def install(monkeypatch, gemm_too=True):
     ``gemm_too=False`` the tcgen05 GEMMs stay with the torch restatement of tests/_host_sim.py"""
     import _host_sim
     F = _host_sim.install(monkeypatch)
+    if gemm_too:
+        from wav2letter_pytorch_b200 import layers
+        monkeypatch.setattr(layers.FusedBnReduce, "enabled", True)        # this backend's backward-data GEMM has the fused reduction
     for n in _NAMES + (_GEMM_NAMES if gemm_too else []):
         assert hasattr(F, n), n
         monkeypatch.setattr(F, n, globals()[n])

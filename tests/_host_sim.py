@@ -186,8 +186,9 @@ def bn_finalize_act_pad(z, stats, gamma, beta, conv_bias, eps, momentum, running
 
 
 def bn_act_bwd(dyp, z, scale, shift, mean, invstd, gamma, B, T, C, pad_left, pad_right, act, drop_p=0.0, seed=0, lens=None,
-               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None):
-    assert drop_p == 0.0
+               res=None, res_scale=None, res_shift=None, want_g=False, dz_rows=None, drop_mask=None, red_ws=None, zero_after=None,
+               red_raw=None):
+    assert drop_p == 0.0 and red_raw is None
     dz_rows = T if dz_rows is None else dz_rows
     zf = z.view(B, T, C).float()
     pre = _pre(z.view(B, T, C), scale, shift, None if res is None else res.view(B, T, C), res_scale, res_shift)
@@ -272,7 +273,8 @@ def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
     return y
 
 
-def conv1d_dgrad_wt(dy, wt, desc, dx):
+def conv1d_dgrad_wt(dy, wt, desc, dx, bnred=None):
+    assert bnred is None, "the fused BatchNorm-backward reduction is switched off under the torch restatement (install())"
     """dx[b, u, ci] = sum_j sum_co dy[b, u - off - j*dil, co] * w[j][co][ci]; wt [k, Cin_pad16, Cout_pad] = tap-reversed transpose"""
     d = desc
     assert dy.dtype == BF16 and wt.dtype == BF16 and dy.shape[-1] == d.ldy and d.ldy >= d.Cout and d.Cout_pad >= 64
@@ -368,4 +370,5 @@ def install(monkeypatch):
         monkeypatch.setattr(F, n, globals()[n])
     monkeypatch.setattr(F, "_need_cuda", lambda *ts: None)
     monkeypatch.setattr(layers.WgradStream, "enabled", False)
+    monkeypatch.setattr(layers.FusedBnReduce, "enabled", False)      # (the emu / cabi backends switch it back on: their GEMM epilogue has it)
     return F

@@ -61,6 +61,8 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
     _install(monkeypatch, backend)
     launches0 = _gemm_launches(backend)
+    from wav2letter_pytorch_b200.layers import FusedBnReduce
+    fused0 = FusedBnReduce.fused_launches
     g = golden(fixture)
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
     cfg = config.compose(overrides=["model.mid_layers=3"]).model
@@ -100,6 +102,10 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
     assert model.scaling_factor == int(g["scaling_factor"])
     if backend != "sim":                          # the GEMMs really went through the emulated conv_gemm_kernel: fwd + dgrad + wgrad per layer
         assert _gemm_launches(backend) - launches0 >= 3 * len(layers)
+    # every BatchNorm block whose output feeds the next layer unchanged had its backward reduction folded into that layer's
+    # backward-data GEMM (FusedBnReduce; a strided inner layer unfolds its input first: that producer keeps the separate pass)
+    want = 0 if backend == "sim" else sum(1 for i in range(len(layers)) if i + 1 >= len(layers) or layers[i + 1]["stride"] == 1)
+    assert FusedBnReduce.fused_launches - fused0 == want, (FusedBnReduce.fused_launches - fused0, want)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
@@ -108,6 +114,8 @@ def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, s
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
     _install(monkeypatch, backend)
+    from wav2letter_pytorch_b200.layers import FusedBnReduce
+    fused0 = FusedBnReduce.fused_launches
     g = golden(fixture)
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
@@ -133,6 +141,10 @@ def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, s
         ref = torch.from_numpy(g["train:grad:" + name])
         assert p.grad is not None and p.grad.shape == p.shape, name
         assert rel_l2(p.grad, ref) < E2E_TOY_BOUND, (name, rel_l2(p.grad, ref))
+    if backend == "sim":
+        assert FusedBnReduce.fused_launches == fused0
+    elif fixture == "jasper_dense":               # repeats inside a block chain linearly: folded; a block output feeds two consumers: not
+        assert FusedBnReduce.fused_launches - fused0 > 0
     for k in g.files:
         if k.startswith("sd1:") and "running" in k:
             np.testing.assert_allclose(model.state_dict()[k[4:]].numpy(), g[k], rtol=2e-2, atol=2e-3, err_msg=k)

@@ -346,6 +346,46 @@ def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0,
 _EPILOGUE_STATS = os.environ.get("W2L_EPILOGUE_STATS", "1") != "0"      # 0: separate bn_stats pass over z (A/B measurements)
 
 
+class FusedBnReduce:
+    """The first of the two BatchNorm-backward passes of a block (sum g, sum g*xhat over all rows) folded into the epilogue of the
+    backward-data GEMM of the layer ABOVE it, which holds exactly those rows of the gradient in registers when it stores them
+    (``F.conv1d_dgrad_wt(bnred=...)``).  The producer block tags its output tensor with what the epilogue needs; the consumer (the next
+    ``ConvBNActFn`` / ``ConvHeadFn``) claims the tag in its forward pass and, in its backward pass, hands it to its GEMM and marks the
+    reduction done, so that the producer runs the apply pass only.  Not fused -- the separate reduce pass runs as before -- when the
+    output has a second consumer (a Jasper block output also feeds the next block's residual conv: two gradients are summed), for
+    blocks with a residual branch, in the fp32-faithful mode, or with W2L_FUSE_BN_REDUCE=0 (the A/B switch)."""
+    enabled = os.environ.get("W2L_FUSE_BN_REDUCE", "1") != "0"
+    fused_launches = 0           # diagnostic counter (tests)
+
+    @staticmethod
+    def tag(yp, **info):
+        info.update(consumers=0, red=None)
+        yp._w2l_producer = info
+        return info
+
+    @staticmethod
+    def claim(xin):
+        info = getattr(xin, "_w2l_producer", None)
+        if info is not None:
+            info["consumers"] += 1
+        return info
+
+    @classmethod
+    def for_dgrad(cls, info, xin):
+        """the ``bnred`` argument for the consumer's backward-data GEMM, or None"""
+        if not cls.enabled or info is None or info["consumers"] != 1 or info["red"] is not None:
+            return None
+        B, T, (pl, pr) = info["B"], info["T"], info["pad"]
+        if xin.dtype != torch.bfloat16 or tuple(xin.shape) != (B, pl + T + pr, info["C"]) or (info["drop_p"] > 0 and info["mask"] is None):
+            return None
+        fin = info["fin"]
+        red = info["scratch"].take_red()
+        info["red"] = red
+        cls.fused_launches += 1
+        return dict(z=info["z"], mask=info["mask"], scale=fin[0], shift=fin[1], mean=fin[2], lens=info["lens"], red=red, B=B, T=T,
+                    pad_left=pl, pad_right=pr, act=info["act"], drop_p=info["drop_p"])
+
+
 class BnScratch:
     """Two small persistent fp32 buffers of a BatchNorm layer that kernels accumulate into with atomics -- ``stats`` [2C] (the conv
     epilogue's batch sums, forward) and ``red`` [2C] (sum g, sum g*xhat, backward) -- each cleared by a kernel of the OTHER pass that
@@ -439,6 +479,11 @@ class ConvBNActFn(torch.autograd.Function):
         ctx.bn = bn
         ctx.conv, ctx.geo, ctx.seed, ctx.desc, ctx.has_res = conv, geo, seed, desc, has_res
         ctx.has_bias = bias is not None
+        ctx.prod_in = FusedBnReduce.claim(xin) if ctx.needs_input_grad[0] else None
+        ctx.prod_out = None
+        if not has_res and not conv.f32:
+            ctx.prod_out = FusedBnReduce.tag(yp, z=z, fin=fin, mask=mask, B=B, T=T_out, C=Co, pad=(pl, pr), act=geo["act"], drop_p=drop_p,
+                                             lens=geo.get("lens"), scratch=sc)
         ctx.save_for_backward(xin, z, fin, gamma, z_res, fin_res, mask)
         return yp
 
@@ -455,20 +500,23 @@ class ConvBNActFn(torch.autograd.Function):
         flat = ctx.needs_input_grad[0] and geo["x_row_offset"] == 0 and x_rows == T_out + halo
         dz_rows = x_rows if flat else T_out
         sc = bn_scratch(ctx.bn, z.device)
+        pre_red = ctx.prod_out["red"] if ctx.prod_out is not None else None      # the consumer's GEMM epilogue already reduced (FusedBnReduce)
         dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
                                   res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
-                                  want_g=has_res, dz_rows=dz_rows, drop_mask=mask, red_ws=sc.take_red(), zero_after=sc.stats)
+                                  want_g=has_res, dz_rows=dz_rows, drop_mask=mask, red_ws=None if pre_red is not None else sc.take_red(),
+                                  zero_after=sc.stats, red_raw=pre_red)
         sc.stats_clean = True                            # the apply pass cleared the forward statistics for the next step
         dw = alloc_dw(conv, z.device)
         side = WgradStream.fork(z.device, conv.weight)   # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
+            bnred = FusedBnReduce.for_dgrad(ctx.prod_in, xin)         # fold the reduction of the block that produced xin into this GEMM
             if flat:
-                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx)
+                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx, bnred=bnred)
             else:
-                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx)
+                F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx, bnred=bnred)
         wgrad_async(side, dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
         dbias = zero_bias_grad(conv, z.device) if ctx.has_bias else None                          # exactly 0 under train BN
         return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
@@ -490,6 +538,7 @@ class ResidualBranchFn(torch.autograd.Function):
         stats = conv_fwd_with_stats(xin, conv, desc, z)
         fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
                             bn.num_batches_tracked)
+        FusedBnReduce.claim(xin)            # a second consumer of the block input: its producer's reduction cannot be folded into one GEMM
         ctx.conv, ctx.desc = conv, desc
         ctx.save_for_backward(xin, z, fin, gamma)
         ctx.mark_non_differentiable(fin)
@@ -527,6 +576,7 @@ class ConvHeadFn(torch.autograd.Function):
             conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
         out = logits[..., :Co].contiguous() if mode == 2 else F.log_softmax(logits, Co, mode, nan_flag)     # 2: raw logits
+        ctx.prod_in = FusedBnReduce.claim(xin) if ctx.needs_input_grad[0] else None
         ctx.conv, ctx.mode = conv, mode
         ctx.has_bias = bias is not None
         ctx.save_for_backward(xin, out)
@@ -547,7 +597,7 @@ class ConvHeadFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
-            F.conv1d_dgrad_wt(dl, conv.packed_t_synced(), desc, dx)
+            F.conv1d_dgrad_wt(dl, conv.packed_t_synced(), desc, dx, bnred=FusedBnReduce.for_dgrad(ctx.prod_in, xin))
         wgrad_async(side, dl, xin, desc, dw)
         dbias = F.colsum(dl, Co) if ctx.has_bias else None
         return dx, conv.grad_view(dw), dbias, None, None, None
