@@ -353,8 +353,12 @@ class FusedBnReduce:
     ``ConvBNActFn`` / ``ConvHeadFn``) claims the tag in its forward pass and, in its backward pass, hands it to its GEMM and marks the
     reduction done, so that the producer runs the apply pass only.  Not fused -- the separate reduce pass runs as before -- when the
     output has a second consumer (a Jasper block output also feeds the next block's residual conv: two gradients are summed), for
-    blocks with a residual branch, in the fp32-faithful mode, or with W2L_FUSE_BN_REDUCE=0 (the A/B switch)."""
-    enabled = os.environ.get("W2L_FUSE_BN_REDUCE", "1") != "0"
+    blocks with a residual branch, in the fp32-faithful mode.
+    OPT-IN (W2L_FUSE_BN_REDUCE=1): measured on B200 (profiles/r2_bn_reduce_fusion.md) it removes 1.2 ms of serialized kernel time per
+    W2L-20 step but the step gets 0.3 ms SLOWER (37.4 -> 37.7; Jasper 10x5 81.4 -> 82.5): the separate pass was already hidden beside
+    the weight-gradient GEMM on the side stream, while the heavier epilogue (row-strided z loads, 124 more shuffles per 32 columns)
+    lengthens the backward-data GEMMs that sit on the critical chain."""
+    enabled = os.environ.get("W2L_FUSE_BN_REDUCE", "0") == "1"
     fused_launches = 0           # diagnostic counter (tests)
 
     @staticmethod
