@@ -371,6 +371,10 @@ class KernelTimer:
         self.spans = []
         self.bytes = {}
 
+    def reset(self):
+        self.spans = []
+        self.bytes = {}
+
     def wrap(self, F, names):
         self._orig = {n: getattr(F, n) for n in names}
         for n in names:
@@ -698,8 +702,14 @@ def run_gpu_arm(args):
     loss_trace = []                                       # loss of the last step of every timed region (asserted finite)
 
     def timed(model, opt, reducer, steps, warmup, from_host):
+        # e2e leg: every step's inputs come from pinned host memory through the package's DevicePrefetcher (the copy of step i+1's
+        # batch is enqueued on a side stream when step i's batch is handed out: it runs beside step i's kernels), and every step's loss
+        # is read back; all of it inside the timed region
+        from wav2letter_pytorch_b200.data_loader import DevicePrefetcher
+        feed = DevicePrefetcher((host for _ in range(warmup + steps)), dev) if from_host else None
+
         def batch():
-            return tuple(t.to(dev, non_blocking=True) for t in host) if from_host else resident
+            return next(feed) if from_host else resident
         for it in range(warmup):
             l = one_step(model, opt, reducer, batch(), it)
             if from_host:
@@ -749,12 +759,26 @@ def run_gpu_arm(args):
     timer = KernelTimer()
     if rank == 0:
         sampler.start()                                   # polls from here on; only samples inside the timed windows are kept
+    # allocator settling (set-up, not warm-up): the caching allocator keeps one pool per stream, and with the host running several
+    # steps ahead of the device the side streams (metrics, weight-shadow prefetch) need a second generation of blocks before the first is
+    # released -- run call 21 saw those two cudaMalloc calls land inside the timed region once (47 instead of 37 ms/step).  Eight
+    # back-to-back steps put them in front of the warm-up instead.
+    timed(model, opt, reducer, 0, 8, False)
     timed(model, opt, reducer, 0, args.warmup, False)
     timer.wrap(F, ["conv1d_fwd", "conv1d_dgrad", "conv1d_dgrad_wt", "conv1d_wgrad", "ctc_loss_raw", "greedy_decode"])
-    launches0 = _lib.launch_count()
-    seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
-    ms = timed(model, opt, reducer, args.steps, 0, False)
-    new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0    # cudaMalloc calls inside the timed region
+    remeasured = None
+    for attempt in range(2):
+        timer.reset()
+        launches0 = _lib.launch_count()
+        seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+        ms = timed(model, opt, reducer, args.steps, 0, False)
+        new_segments = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0    # cudaMalloc calls inside the timed region
+        if new_segments == 0 or attempt == 1:
+            break
+        # a cudaMalloc inside the timed region stalls the device pipeline: that is the allocator growing, not the step -- time the K steps again
+        remeasured = "first timed region discarded: %d cudaMalloc call(s) inside it (%.2f ms/step)" % (new_segments, ms)
+        step_spread.pop()
+        loss_trace.pop()
     launches_total = _lib.launch_count() - launches0
     launches = launches_total // max(args.steps, 1)
     timer.unwrap()
@@ -887,10 +911,12 @@ def run_gpu_arm(args):
                                 "mode is measured in the precision_tf32 leg)",
                    "gemm": "CTA pairs (tcgen05 cta_group::2): conv_gemm_cg2_kernel fwd/dgrad, conv_wgrad_cg2_kernel; W2L_CG2=0 = single CTA"},
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4,
+                "h2d": "pinned host batch -> device through data_loader.DevicePrefetcher, every step, inside the timed region: the copy of "
+                       "step i+1's inputs runs on a side stream beside step i's kernels"},
         "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "step_ms_min_median_max": {"value": step_spread[0], "e2e": step_spread[2] if len(step_spread) > 2 else None},
-        "cuda_mallocs_in_timed_region": int(new_segments),
+        "cuda_mallocs_in_timed_region": int(new_segments), "remeasured": remeasured,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_gemm_cg2_kernel (fwd, dgrad) + conv_wgrad_cg2_kernel: tcgen05 cta_group::2 implicit GEMMs", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained", "unit": "TFLOP/s",

@@ -53,6 +53,18 @@ def test_w2l_golden_train_eval(pkg, golden):
     check_w2l_golden(pkg, golden("w2l_small"))
 
 
+def test_w2l_golden_with_fused_bn_reduce(pkg, golden, monkeypatch):
+    """the same fixture with the opt-in W2L_FUSE_BN_REDUCE path: every block's backward reduction comes out of the next layer's
+    backward-data GEMM epilogue (layers.FusedBnReduce) -- same closed tolerances, and the number of folded reductions is the number of
+    BatchNorm blocks"""
+    from wav2letter_pytorch_b200.layers import FusedBnReduce
+    monkeypatch.setattr(FusedBnReduce, "enabled", True)
+    before = FusedBnReduce.fused_launches
+    g = golden("w2l_small")
+    check_w2l_golden(pkg, g)
+    assert FusedBnReduce.fused_launches - before == len(g["layers"])
+
+
 def check_w2l_golden(pkg, g):
     """train step + eval forward of a small Wav2Letter against a fixture frozen from the unmodified reference"""
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter

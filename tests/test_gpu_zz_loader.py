@@ -47,3 +47,21 @@ def test_loader_batches_match_oracle_features(tmp_path):
         assert list(got_texts) == texts[seen:seen + 2]
         seen += 2
     assert seen == 4
+
+
+def test_device_prefetcher_hands_out_the_batches_in_order():
+    """DevicePrefetcher: pinned host batches -> device batches, next copy in flight on a side stream; values, order, pass-through of
+    non-tensor entries, StopIteration at the end"""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from wav2letter_pytorch_b200.data_loader import DevicePrefetcher
+    g = torch.Generator().manual_seed(0)
+    host = [(torch.randn(4, 64, 300, generator=g).pin_memory(), torch.randint(1, 300, (4,), generator=g, dtype=torch.int32).pin_memory(), ["a", "b"], i)
+            for i in range(5)]
+    got = []
+    for x, il, texts, idx in DevicePrefetcher(iter(host), "cuda:0"):
+        assert x.is_cuda and il.is_cuda and texts == ["a", "b"]
+        got.append(((x * 2).sum().item(), il.clone(), idx))          # some work on the compute stream between batches
+    assert [i for _, _, i in got] == list(range(5))
+    for (s, il, i), (hx, hil, _, _) in zip(got, host):
+        assert abs(s - float((hx * 2).sum())) < 1e-2 * max(1.0, abs(s)) and torch.equal(il.cpu(), hil)

@@ -159,3 +159,44 @@ class BatchAudioDataLoader(DataLoader):
         else:
             collate = _collator
         super().__init__(dataset, *args, collate_fn=collate, **kwargs)
+
+
+class DevicePrefetcher:
+    """Hands out the batches of ``loader`` (tuples whose tensors live in PINNED host memory, as ``DataLoader(pin_memory=True)`` or the
+    reference's collated batches after ``.pin_memory()`` give them) as device batches -- with the host->device copy of batch i+1
+    enqueued on a side stream the moment batch i is handed out, so that it runs beside step i's kernels instead of in front of step
+    i+1's (24.6 MB per 64 x 15 s batch: ~1 ms of PCIe time per step when it is not hidden).  The compute stream waits for the copy
+    stream before a batch is returned, and the batch's memory is tied to the compute stream (``record_stream``), so the consumer
+    needs no extra care.  Non-tensor entries (paths, transcripts) pass through.  Lightning does the same for the reference
+    (train.py hands the DataLoader to ``pl.Trainer``, which moves batches asynchronously)."""
+
+    def __init__(self, loader, device):
+        self.it = iter(loader)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self._next = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in host)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)
+        batch = self._next
+        for t in batch:
+            if torch.is_tensor(t):
+                t.record_stream(cur)
+        self._preload()
+        return batch
