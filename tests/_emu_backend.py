@@ -61,11 +61,8 @@ def decode():
 ELEMENTWISE_PTX = r"""
 static inline float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 static inline float min_nan(float a, float b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
-static inline void cp_async16(void* smem, const void* gmem) { std::memcpy(smem, gmem, 16); }     // cp.async.cg 16 B (eager on the host)
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
 """
-ELEMENTWISE_DROP = ["max_nan", "min_nan", "cp_async16", "cp_async_commit", "cp_async_wait"]
+ELEMENTWISE_DROP = ["max_nan", "min_nan"]
 
 # host stand-ins for the inline PTX of csrc/ctc.cu (file:line of what each replaces)
 CTC_PTX = r"""

@@ -1,7 +1,6 @@
 // Memory-bound companions of the conv kernels: layout changes, BatchNorm statistics / apply / backward with
 // fused activation, dropout, reflection halo and length mask, log_softmax fwd/bwd, bias gradient, casts.
 // All activations are time-major [B, T, C] bf16; every kernel moves 16 bytes (8 channels) per thread access.
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -764,237 +763,6 @@ __global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_
   }
 }
 
-// ---------------------------------------------------------------- the two backward passes with a shared-memory load pipeline (bf16)
-// The register-staged kernels above keep 4 rows x (z, dy[, res]) in flight per thread and then compute: at 126-128 registers only
-// two CTAs fit an SM (20 % occupancy) and a warp's loads never overlap its own arithmetic -- 2.1 TB/s in the reduce pass (ncu,
-// profiles/r2_bn_passes.md).  Here every thread streams ITS rows through a private ring of kPipe shared-memory slots filled by
-// cp.async (16 bytes per stream and row; no register is held while a row is in flight, no barrier is needed because a slot is written
-// and read by the same thread): kPipe rows are always in flight while the oldest is being consumed.  Same row -> thread assignment,
-// same arithmetic (g_from_row) and the same reduction order within a thread as the kernels above.
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-template <bool HAS_RES>
-struct BwdPipe {
-  static constexpr int kStreams = HAS_RES ? 3 : 2;
-  static constexpr int kPipe = HAS_RES ? 6 : 8;
-  static constexpr size_t kSmem = (size_t)kPipe * kStreams * kBnThreads * sizeof(uint4);
-};
-
-// the q-th row of the rows a thread walks: groups of kRowGroup consecutive rows, one group per row lane and round
-__device__ __forceinline__ int pipe_row(int q, int r_begin, int ny) {
-  return r_begin + (((q >> 2) * ny + (int)threadIdx.y) << 2) + (q & 3);
-}
-static_assert(kRowGroup == 4, "pipe_row assumes groups of 4 rows");
-
-template <bool DROP, bool HAS_RES>
-__device__ __forceinline__ uint32_t pipe_issue(const BnBwdArgs& a, uint4* ring, int slot, int tid, int r, bool live, int c) {
-  uint32_t bits = 0;
-  if (live) {
-    const int b = r / a.T, t = r - b * a.T;
-    const int64_t e = (int64_t)r * a.C + c;
-    constexpr int S = BwdPipe<HAS_RES>::kStreams;
-    cp_async16(ring + (slot * S + 0) * kBnThreads + tid, reinterpret_cast<const __nv_bfloat16*>(a.z) + e);
-    cp_async16(ring + (slot * S + 1) * kBnThreads + tid,
-               reinterpret_cast<const __nv_bfloat16*>(a.dyp) + ((int64_t)b * (a.pl + a.T + a.pr) + a.pl + t) * a.C + c);
-    if (HAS_RES) cp_async16(ring + (slot * S + 2) * kBnThreads + tid, reinterpret_cast<const __nv_bfloat16*>(a.res) + e);
-    if (DROP && a.drop_mask) bits = (uint32_t)__ldg(a.drop_mask + (e >> 3));
-  }
-  cp_async_commit();                                   // one group per call, issued or not: the wait below counts groups
-  return bits;
-}
-
-template <bool HAS_RES>
-__device__ __forceinline__ void pipe_take(const BnBwdArgs& a, const uint4* ring, int slot, int tid, int b, uint32_t bits,
-                                          BwdRow<__nv_bfloat16>& in) {
-  constexpr int S = BwdPipe<HAS_RES>::kStreams;
-  in.z.q = ring[(slot * S + 0) * kBnThreads + tid];
-  in.d.q = ring[(slot * S + 1) * kBnThreads + tid];
-  if (HAS_RES) in.r.q = ring[(slot * S + 2) * kBnThreads + tid];
-  in.bits = bits;
-  in.len = a.lens ? __ldg(a.lens + b) : 0x7fffffff;
-}
-
-template <int ACT, bool DROP, bool HAS_RES>
-__global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_reduce_pipe_kernel(BnBwdArgs a) {
-  constexpr int D = BwdPipe<HAS_RES>::kPipe;
-  extern __shared__ uint4 ring[];
-  __shared__ __align__(16) float s_a[kBnThreads * 8], s_b[kBnThreads * 8];
-  const int bx = blockDim.x, ny = blockDim.y;
-  const int tid = threadIdx.y * bx + threadIdx.x;
-  const int cv = blockIdx.x * bx + threadIdx.x;
-  const int c = cv * 8;
-  float sg[8], sx[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) sg[i] = sx[i] = 0.f;
-  if (c < a.C) {
-    float sc[8], sh[8], rsc[8], rsh[8], mu[8];
-    load8f(a.scale + c, sc);
-    load8f(a.shift + c, sh);
-    if (HAS_RES) {
-      load8f(a.res_scale + c, rsc);
-      load8f(a.res_shift + c, rsh);
-    }
-    scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
-    load8f(a.mean + c, mu);
-    const int rows = a.B * a.T;
-    const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);
-    const int groups = (r_end - r_begin + kRowGroup - 1) / kRowGroup;
-    const int nq = (int)threadIdx.y < groups ? ((groups - (int)threadIdx.y + ny - 1) / ny) * kRowGroup : 0;
-    uint32_t bits[D];
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      const int r = pipe_row(u, r_begin, ny);
-      bits[u] = pipe_issue<DROP, HAS_RES>(a, ring, u, tid, r, u < nq && r < r_end, c);
-    }
-    for (int q0 = 0; q0 < nq; q0 += D) {
-#pragma unroll
-      for (int u = 0; u < D; ++u) {
-        cp_async_wait<D - 1>();                        // the oldest group -- slot u -- has landed
-        const int q = q0 + u, r = pipe_row(q, r_begin, ny);
-        if (q < nq && r < r_end) {
-          const int b = r / a.T, t = r - b * a.T;
-          BwdRow<__nv_bfloat16> in;
-          pipe_take<HAS_RES>(a, ring, u, tid, b, bits[u], in);
-          float g[8], zv[8];
-          g_from_row<__nv_bfloat16, ACT, DROP, HAS_RES>(a, r, b, t, c, in, sc, sh, rsc, rsh, g, zv);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            sg[i] += g[i];
-            sx[i] = fmaf(g[i], zv[i] - mu[i], sx[i]);
-          }
-        }
-        const int rn = pipe_row(q + D, r_begin, ny);
-        bits[u] = pipe_issue<DROP, HAS_RES>(a, ring, u, tid, rn, q + D < nq && rn < r_end, c);
-      }
-    }
-    cp_async_wait<0>();
-    float is[8];
-    load8f(a.invstd + c, is);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sx[i] *= is[i];
-  }
-  float* pa = s_a + (threadIdx.y * bx + threadIdx.x) * 8;
-  float* pb = s_b + (threadIdx.y * bx + threadIdx.x) * 8;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    pa[i] = sg[i];
-    pb[i] = sx[i];
-  }
-  __syncthreads();
-  if (threadIdx.y == 0 && c < a.C) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float u = 0.f, v = 0.f;
-      for (int y = 0; y < ny; ++y) {
-        u += s_a[(y * bx + threadIdx.x) * 8 + i];
-        v += s_b[(y * bx + threadIdx.x) * 8 + i];
-      }
-      atomicAdd(a.red + c + i, u);
-      atomicAdd(a.red + a.C + c + i, v);
-    }
-  }
-}
-
-// apply pass, same pipeline; the rows are walked from the END of each range and the ranges in reverse order (see the kernel above it)
-template <int ACT, bool DROP, bool HAS_RES>
-__global__ void __launch_bounds__(kBnThreads, kBnBwdCtasPerSm) bn_act_bwd_apply_pipe_kernel(BnBwdArgs a) {
-  constexpr int D = BwdPipe<HAS_RES>::kPipe;
-  extern __shared__ uint4 ring[];
-  zero_small(a.zero_ptr, a.zero_count);
-  const int bx = blockDim.x, ny = blockDim.y;
-  const int tid = threadIdx.y * bx + threadIdx.x;
-  const int cv = blockIdx.x * bx + threadIdx.x;
-  const int c = cv * 8;
-  if (c >= a.C) return;
-  const int rb = gridDim.y - 1 - blockIdx.y;
-  float sc[8], sh[8], rsc[8], rsh[8];
-  load8f(a.scale + c, sc);
-  load8f(a.shift + c, sh);
-  if (HAS_RES) {
-    load8f(a.res_scale + c, rsc);
-    load8f(a.res_shift + c, rsh);
-  }
-  scale_for_dropout<DROP, HAS_RES>(a.inv_keep, sc, sh, rsc, rsh);
-  float kA[8], kB[8], kC[8];
-  {
-    float mu[8], is[8], sg[8], sx[8], ga[8];
-    load8f(a.mean + c, mu);
-    load8f(a.invstd + c, is);
-    load8f(a.red + c, sg);
-    load8f(a.red + a.C + c, sx);
-    if (a.gamma) load8f(a.gamma + c, ga);
-    if (a.red_raw) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sx[i] *= is[i];
-    }
-    if (a.red_out && rb == 0 && threadIdx.y == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a.red_out[c + i] = sg[i];
-        a.red_out[a.C + c + i] = sx[i];
-      }
-    }
-    const float inv_m = 1.f / (float)((int64_t)a.B * a.T);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float coef = (a.gamma ? ga[i] : 1.f) * is[i];
-      kA[i] = coef;
-      kB[i] = -coef * sx[i] * inv_m * is[i];
-      kC[i] = -coef * sg[i] * inv_m - kB[i] * mu[i];
-    }
-  }
-  const int rows = a.B * a.T;
-  const int r_begin = rb * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);
-  const int groups = (r_end - r_begin + kRowGroup - 1) / kRowGroup;
-  const int nq = (int)threadIdx.y < groups ? ((groups - (int)threadIdx.y + ny - 1) / ny) * kRowGroup : 0;
-  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(a.dz);
-  __nv_bfloat16* g_out = reinterpret_cast<__nv_bfloat16*>(a.g_out);
-  uint32_t bits[D];
-#pragma unroll
-  for (int u = 0; u < D; ++u) {
-    const int r = pipe_row(nq - 1 - u, r_begin, ny);
-    bits[u] = pipe_issue<DROP, HAS_RES>(a, ring, u, tid, r, u < nq && r < r_end, c);
-  }
-  for (int q0 = 0; q0 < nq; q0 += D) {
-#pragma unroll
-    for (int u = 0; u < D; ++u) {
-      cp_async_wait<D - 1>();
-      const int q = q0 + u, r = pipe_row(nq - 1 - q, r_begin, ny);
-      if (q < nq && r < r_end) {
-        const int b = r / a.T, t = r - b * a.T;
-        BwdRow<__nv_bfloat16> in;
-        pipe_take<HAS_RES>(a, ring, u, tid, b, bits[u], in);
-        float g[8], zv[8], o[8];
-        g_from_row<__nv_bfloat16, ACT, DROP, HAS_RES>(a, r, b, t, c, in, sc, sh, rsc, rsh, g, zv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(kA[i], g[i], fmaf(kB[i], zv[i], kC[i]));
-        *reinterpret_cast<uint4*>(dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = pack8(o);
-        if (g_out) *reinterpret_cast<uint4*>(g_out + (int64_t)r * a.C + c) = pack8(g);
-      }
-      const int rn = pipe_row(nq - 1 - (q + D), r_begin, ny);
-      bits[u] = pipe_issue<DROP, HAS_RES>(a, ring, u, tid, rn, q + D < nq && rn < r_end, c);
-    }
-  }
-  cp_async_wait<0>();
-  const int tail = a.dz_rows - a.T;
-  if (tail > 0) {
-    const int trows = a.B * tail;
-    const int per = (trows + gridDim.y - 1) / gridDim.y;
-    const int q_begin = blockIdx.y * per, q_end = min(trows, q_begin + per);
-    for (int q = q_begin + threadIdx.y; q < q_end; q += ny) {
-      const int b = q / tail, t = a.T + (q - b * tail);
-      *reinterpret_cast<uint4*>(dz + ((int64_t)b * a.dz_rows + t) * a.C + c) = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-}
-
 // ---------------------------------------------------------------- log_softmax fwd / bwd (one warp per row)
 __global__ void log_softmax_kernel(const float* __restrict__ logits, int ld, float* __restrict__ out, int64_t rows, int C, int mode,
                                    int32_t* __restrict__ nan_flag) {
@@ -1153,48 +921,6 @@ static BnGeo bn_geo(int64_t rows, int C, int ctas_per_sm) {
       default: KERNEL<TA, W2L_ACT_CLAMP20, true, true><<<geo.grid, geo.block, 0, st>>>(__VA_ARGS__); break;            \
     }                                                                                                                  \
   } while (0)
-// the shared-memory-pipelined backward kernels (bf16): dynamic shared memory above 48 KB needs the attribute once per instantiation
-static int set_bn_pipe_smem(const void* fn, size_t smem) {
-  static const void* done[64];
-  static int n_done = 0;
-  for (int i = 0; i < n_done; ++i)
-    if (done[i] == fn) return W2L_OK;
-  W2L_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (n_done < 64) done[n_done++] = fn;
-  return W2L_OK;
-}
-#define W2L_BN_PIPE_CASE(KERNEL, A, D_, R_, ...)                                                                       \
-  {                                                                                                                    \
-    const size_t sm_ = BwdPipe<R_>::kSmem;                                                                             \
-    int rc_ = set_bn_pipe_smem((const void*)KERNEL<A, D_, R_>, sm_);                                                   \
-    if (rc_) return rc_;                                                                                               \
-    KERNEL<A, D_, R_><<<geo.grid, geo.block, sm_, st>>>(__VA_ARGS__);                                                  \
-  }                                                                                                                    \
-  break
-#define W2L_BN_PIPE_DISPATCH(KERNEL, act, drop, has_res, ...)                                                           \
-  do {                                                                                                                 \
-    const int key_ = ((act) & 0xFF) * 4 + ((drop) ? 2 : 0) + ((has_res) ? 1 : 0);                                      \
-    switch (key_) {                                                                                                    \
-      case 0: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_NONE, false, false, __VA_ARGS__);                                       \
-      case 1: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_NONE, false, true, __VA_ARGS__);                                        \
-      case 2: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_NONE, true, false, __VA_ARGS__);                                        \
-      case 3: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_NONE, true, true, __VA_ARGS__);                                         \
-      case 4: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_RELU, false, false, __VA_ARGS__);                                       \
-      case 5: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_RELU, false, true, __VA_ARGS__);                                        \
-      case 6: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_RELU, true, false, __VA_ARGS__);                                        \
-      case 7: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_RELU, true, true, __VA_ARGS__);                                         \
-      case 8: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_CLAMP20, false, false, __VA_ARGS__);                                    \
-      case 9: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_CLAMP20, false, true, __VA_ARGS__);                                     \
-      case 10: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_CLAMP20, true, false, __VA_ARGS__);                                    \
-      default: W2L_BN_PIPE_CASE(KERNEL, W2L_ACT_CLAMP20, true, true, __VA_ARGS__);                                     \
-    }                                                                                                                  \
-  } while (0)
-// W2L_BN_PIPE=0: the register-staged backward kernels for bf16 too (the A/B switch of profiles/r2_bn_passes.md); read per call
-static bool bn_pipe_wanted(int act) {
-  if (act & W2L_STORE_F32) return false;
-  const char* e = getenv("W2L_BN_PIPE");
-  return !(e && atoi(e) == 0);
-}
 // `act` may carry W2L_STORE_F32: the activation buffers of the call are fp32 (kernels instantiated with TA = float)
 #define W2L_BN_DISPATCH(KERNEL, act, drop, has_res, ...)                                                                \
   do {                                                                                                                 \
@@ -1464,10 +1190,6 @@ int w2l_bn_act_bwd_reduce(const void* dyp, const void* z, const void* res, const
   const BnGeo geo = bn_geo((int64_t)B * T, C, kBnBwdCtasPerSm);
   a.rows_per_block = geo.rows_per_block;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn_pipe_wanted(act)) {
-    W2L_BN_PIPE_DISPATCH(bn_act_bwd_reduce_pipe_kernel, act, a.keep_q != 0, res != nullptr, a);
-    return after_launch("bn_act_bwd_reduce_pipe_kernel");
-  }
   W2L_BN_DISPATCH(bn_act_bwd_reduce_kernel, act, a.keep_q != 0, res != nullptr, a);
   return after_launch("bn_act_bwd_reduce_kernel");
 }
@@ -1496,10 +1218,6 @@ int w2l_bn_act_bwd_apply(const void* dyp, const void* z, const void* res, const 
   const BnGeo geo = bn_geo((int64_t)B * T, C, kBnBwdCtasPerSm);
   a.rows_per_block = geo.rows_per_block;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn_pipe_wanted(act)) {
-    W2L_BN_PIPE_DISPATCH(bn_act_bwd_apply_pipe_kernel, act, a.keep_q != 0, res != nullptr, a);
-    return after_launch("bn_act_bwd_apply_pipe_kernel");
-  }
   W2L_BN_DISPATCH(bn_act_bwd_apply_kernel, act, a.keep_q != 0, res != nullptr, a);
   return after_launch("bn_act_bwd_apply_kernel");
 }
