@@ -707,6 +707,8 @@ def run_gpu_arm(args):
         # is read back; all of it inside the timed region
         from wav2letter_pytorch_b200.data_loader import DevicePrefetcher
         feed = DevicePrefetcher((host for _ in range(warmup + steps)), dev) if from_host else None
+        loss_slots = [torch.zeros(1).pin_memory() for _ in range(2)] if from_host else None
+        host_losses = []
 
         def batch():
             return next(feed) if from_host else resident
@@ -721,13 +723,27 @@ def run_gpu_arm(args):
         marks = []
         host_t0 = time.perf_counter()                     # GPU idle here (barrier above) and again after the barrier below
         e0.record()
+        pending = None
         for it in range(steps):
             l = one_step(model, opt, reducer, batch(), it)
             if from_host:
-                l.item()                                  # device->host read of the step's loss
+                # device->host read of EVERY step's loss, one step late: step i's loss is copied to pinned memory on the compute stream
+                # behind step i and read by the host while step i+1 is already enqueued (asynchronous logging, as a training loop
+                # does it); the last one is read before the region closes
+                if pending is not None:
+                    pending[1].synchronize()
+                    host_losses.append(float(pending[0]))
+                slot = loss_slots[it % 2]
+                slot.copy_(l.detach().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending = (slot, ev)
             m = torch.cuda.Event(enable_timing=True)
             m.record()
             marks.append(m)
+        if pending is not None:
+            pending[1].synchronize()
+            host_losses.append(float(pending[0]))
         e1.record()
         barrier()
         if sampling[0]:
@@ -913,7 +929,9 @@ def run_gpu_arm(args):
         "e2e": {"value": world * BATCH * UTT_SEC / (ms_e2e / 1e3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 + BATCH * 4,
                 "h2d": "pinned host batch -> device through data_loader.DevicePrefetcher, every step, inside the timed region: the copy of "
-                       "step i+1's inputs runs on a side stream beside step i's kernels"},
+                       "step i+1's inputs runs on a side stream beside step i's kernels",
+                "d2h": "every step's loss is copied to pinned host memory behind the step and read by the host one step later (the last one "
+                       "before the region closes): the host never drains the GPU between steps"},
         "gpu_launches": int(launches_total), "gpu_launches_per_step": int(launches),
         "step_ms_min_median_max": {"value": step_spread[0], "e2e": step_spread[2] if len(step_spread) > 2 else None},
         "cuda_mallocs_in_timed_region": int(new_segments), "remeasured": remeasured,
