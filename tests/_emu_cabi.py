@@ -154,4 +154,5 @@ def install(monkeypatch):
     monkeypatch.setattr(F, "_gemm_scratch", _keep[-1])
     monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
     monkeypatch.setattr(layers.WgradStream, "enabled", False)
+    monkeypatch.setattr(layers.FusedBnReduce, "enabled", True)       # the opt-in fused BatchNorm-backward reduction: covered here on the host
     return F
