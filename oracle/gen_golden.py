@@ -317,6 +317,46 @@ def gen_narrow(ref):
     np.savez_compressed(os.path.join(OUT, "w2l_narrow.npz"), **_np(out))
 
 
+def gen_odd(ref):
+    """widths the tensor-core path has to PAD internally: the reference accepts any ``output_size`` (wav2letter.py:59-64; 250 is the
+    hidden width of the original paper) and, with ``input_size`` unset, feeds the 161 STFT bins of the default audio config
+    (wav2letter.py:52-56) -- none a multiple of 8, one below 64"""
+    torch.manual_seed(17)
+    cfg = rl.reference_model_cfg("wav2letter", mid_layers=3, dropout=-1)
+    cfg["input_size"] = 0                                  # -> int(1 + sample_rate * window_size / 2) = 161
+    odd = [dict(output_size=250, kernel_size=5, stride=2, dilation=1, dropout=-1),
+           dict(output_size=36, kernel_size=7, stride=1, dilation=1, dropout=-1),
+           dict(output_size=250, kernel_size=5, stride=1, dilation=2, dropout=-1)]
+    cfg["layers"] = rl.to_attr(odd)
+    model = ref.wav2letter.Wav2Letter(cfg)
+    assert model.input_size == 161
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 161, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tl = torch.tensor([18, 11, 6], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 18), dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "layers": np.array([[l["output_size"], l["kernel_size"], l["stride"],
+                                                                     l["dilation"]] for l in odd])}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update(_sd(model, "sd1:"))
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["eval:decoded"] = np.array(model.ctc_decoder.decode(o, ol))
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "w2l_odd.npz"), **_np(out))
+
+
 def gen_ctc(ref):
     g = torch.Generator().manual_seed(5)
     crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)    # base_asr_models.py:23
@@ -420,10 +460,10 @@ def gen_beam(ref):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd", "strided", "narrow"):      # regenerate one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd", "strided", "narrow", "odd"):      # regenerate one fixture without touching the others
         ref = rl.load_reference()
         torch.set_num_threads(1)
-        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd, "strided": gen_strided, "narrow": gen_narrow}[sys.argv[1]](ref)
+        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd, "strided": gen_strided, "narrow": gen_narrow, "odd": gen_odd}[sys.argv[1]](ref)
         return
     ref = rl.load_reference()
     torch.set_num_threads(1)
@@ -434,6 +474,7 @@ def main():
     gen_jasper_dense(ref)
     gen_strided(ref)
     gen_narrow(ref)
+    gen_odd(ref)
     gen_ctc(ref)
     gen_novograd(ref)
     gen_features(ref)

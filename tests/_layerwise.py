@@ -22,9 +22,14 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _ncw(h):
-    """time-major device tensor [B, rows, C] -> NCW fp32 on the host"""
-    return h.detach().float().cpu().transpose(1, 2).contiguous()
+def _ncw(h, C=None):
+    """time-major device tensor [B, rows, Cp] -> NCW fp32 on the host; ``C``: the logical channel count when the buffer's width is
+    padded (ConvParams.phys) -- the surplus channels must then be exact zeros"""
+    h = h.detach().float().cpu()
+    if C is not None and h.shape[2] != C:
+        assert float(h[:, :, C:].abs().max()) == 0.0, "surplus channels of a padded activation / gradient buffer must be exactly zero"
+        h = h[:, :, :C]
+    return h.transpose(1, 2).contiguous()
 
 
 def _bf(t):
@@ -85,20 +90,21 @@ def w2l_layerwise_table(model, hs, out):
         first, last = i == 0, i == len(blocks) - 1
         dev_out = out if last else hs[i + 1]
         cot = dev_out.grad.detach().float().cpu()
+        c_in, c_out = blk.input_channels, blk.output_channels         # logical widths (the device buffers may be padded)
         row = {}
         for emu in (True, False):
-            hin = (hs[i].detach().float().cpu() if first else _ncw(hs[i])).clone().requires_grad_(not first)
+            hin = (hs[i].detach().float().cpu() if first else _ncw(hs[i], c_in)).clone().requires_grad_(not first)
             y, leaves = w2l_block_oracle(blk, hin, first, last, emu)
             if last:
                 want, got = y, dev_out.detach().float().cpu()
                 y.backward(cot)
             else:
-                want, got = y, _ncw(dev_out)
-                y.backward(cot.transpose(1, 2))
+                want, got = y, _ncw(dev_out, c_out)
+                y.backward(cot[:, :, :c_out].transpose(1, 2))
             col = 0 if emu else 1
             row.setdefault("out", [None, None])[col] = rel_l2(got, want.detach())
             if not first:
-                row.setdefault("d_input", [None, None])[col] = rel_l2(_ncw(hs[i].grad), hin.grad)
+                row.setdefault("d_input", [None, None])[col] = rel_l2(_ncw(hs[i].grad, c_in), hin.grad)
             for pname, leaf in leaves.items():
                 p = dict(blk.named_parameters())[pname]
                 if pname == "conv1.bias" and not last:       # analytically zero under train-mode BN: the device returns exact zeros

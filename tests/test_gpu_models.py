@@ -65,11 +65,21 @@ def test_w2l_golden_with_fused_bn_reduce(pkg, golden, monkeypatch):
     assert FusedBnReduce.fused_launches - before == len(g["layers"])
 
 
-def check_w2l_golden(pkg, g):
+def test_w2l_odd_widths_golden(pkg, golden):
+    """channel counts the reference accepts and the tensor-core path pads internally: 161 STFT bins in (input_size unset,
+    wav2letter.py:52-56), hidden widths 250 / 36 / 250 (wav2letter.py:59-64; 250 is the original paper's) -- same checks and bounds as
+    the other fixtures; the per-block table also asserts that the surplus channels of every buffer and gradient are exact zeros"""
+    check_w2l_golden(pkg, golden("w2l_odd"), input_size=0)
+
+
+def check_w2l_golden(pkg, g, input_size=None):
     """train step + eval forward of a small Wav2Letter against a fixture frozen from the unmodified reference"""
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
-    model = Wav2Letter(_cfg(pkg, layers, len(layers)))
+    cfg = _cfg(pkg, layers, len(layers))
+    if input_size is not None:
+        cfg["input_size"] = input_size
+    model = Wav2Letter(cfg)
     head = "conv1d_%d" % len(layers)                        # the bias-only label head follows the BatchNorm blocks
     assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0:"))     # checkpoint contract
     _load_sd(model, g, "sd0:")

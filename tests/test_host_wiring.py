@@ -55,7 +55,7 @@ def _load_sd(model, g, prefix):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided", "w2l_narrow"])
+@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_strided", "w2l_narrow", "w2l_odd"])
 def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, backend):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
@@ -67,6 +67,8 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
     cfg = config.compose(overrides=["model.mid_layers=3"]).model
     cfg["layers"] = config.to_attr(layers)
+    if fixture == "w2l_odd":                      # 161 STFT bins (input_size unset), hidden widths 250 / 36 / 250: padded internally
+        cfg["input_size"] = 0
     model = Wav2Letter(cfg)
     assert sorted(model.state_dict().keys()) == sorted(k[4:] for k in g.files if k.startswith("sd0:"))
     _load_sd(model, g, "sd0:")

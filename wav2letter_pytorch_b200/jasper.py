@@ -269,6 +269,11 @@ class Jasper(ConvCTCASR):
         last = self.jasper_encoder[-1].mconv[-1].num_features
         self.final_layer = nn.Sequential(ConvParams(last, len(self.labels), 1, bias=True))
         self.final_layer.apply(init_weights)
+        self.final_layer[0].is_head = True
+        for m in self.modules():                   # (Wav2Letter pads odd widths internally, ConvParams.phys; the Jasper blocks do not yet)
+            if isinstance(m, ConvParams) and m is not self.final_layer[0] and m.padded:
+                raise ValueError("Jasper: channel counts must be multiples of 8 and >= 64 for the tensor-core path (got %d -> %d)"
+                                 % (m.in_channels, m.out_channels))
         # precision: "bf16" (default) or "tf32" -- the fp32-faithful mode (fp32 activations / weights / gradients in memory, tf32
         # multiplies, fp32 accumulation; see Wav2Letter).  Dense blocks only: the depthwise kernels of separable blocks and the
         # time-major unfold of strided inner blocks exist for bf16 activations.

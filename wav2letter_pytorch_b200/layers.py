@@ -62,25 +62,30 @@ class WgradStream:
         cls._pending.clear()
 
 
-def wgrad_async(side, dy, x, desc, dw):
-    """conv1d_wgrad on the side stream returned by ``WgradStream.fork`` (plain call when it is None)."""
+def wgrad_async(side, dy, x, desc, dw, conv=None):
+    """conv1d_wgrad on the side stream returned by ``WgradStream.fork`` (plain call when it is None).  Returns the gradient in the
+    Parameter's own [k_eff, Cout, cin_eff] layout: for a conv whose channel counts are padded internally (``conv.padded``) the logical
+    part is cut out of the padded result on the same stream."""
     wgrad = F.conv1d_wgrad_t if desc.x_dtype == F.DT_F32 else F.conv1d_wgrad      # fp32-faithful mode: tf32 over transposed operands
     if side is None:
-        return wgrad(dy, x, desc, dw)
+        wgrad(dy, x, desc, dw)
+        return conv.unpad_dw(dw) if conv is not None and conv.padded else dw
     with torch.cuda.stream(side):
         wgrad(dy, x, desc, dw)
-    for t in (dy, x) if getattr(dw, "_w2l_arena", False) else (dy, x, dw):
+        out = conv.unpad_dw(dw) if conv is not None and conv.padded else dw
+    for t in (dy, x) if getattr(dw, "_w2l_arena", False) else (dy, x, dw, out):
         t.record_stream(side)
-    return dw
+    return out
 
 
-def alloc_dw(conv, device):
+def alloc_dw(conv, device, cout=None):
     """fp32 [k_eff, Cout, cin_eff] buffer for the weight gradient: the layer's slice of the data-parallel gradient arena when a
     ``PeerGradientReducer`` owns one (wgrad then writes where the NVLink all-reduce reads: no copy), else a fresh tensor."""
     buf = getattr(conv, "_grad_buffer", None)
-    if buf is not None and conv.weight.grad is None and buf.device == device:
+    if buf is not None and conv.weight.grad is None and buf.device == device and not conv.padded:
         return buf
-    return torch.empty((conv.k_eff, conv.out_channels, conv.cin_eff), dtype=torch.float32, device=device)
+    rows = conv.out_channels if cout is None else cout            # (padded channel counts: the kernel writes the padded shape)
+    return torch.empty((conv.k_eff, rows, conv.cin_phys), dtype=torch.float32, device=device)
 
 
 def next_dropout_seed():
@@ -118,6 +123,7 @@ class ConvParams(nn.Module):
         # fp32-faithful mode (set by the owning model, ``precision="tf32"``): the GEMMs read fp32 activations and these fp32 weights
         # as tf32 with fp32 accumulation -- no bf16 shadow exists, activations between the layers stay fp32
         self.f32 = False
+        self.is_head = False                  # the bias-only label head (set by the owning model): its output is not an activation buffer
 
     @property
     def act_dtype(self):
@@ -154,6 +160,34 @@ class ConvParams(nn.Module):
         """rows per tap of the packed weights: multiple of 16 (UMMA N granularity), at least 64 (dgrad K chunk)"""
         return max(64, (self.out_channels + 15) // 16 * 16)
 
+    # ---- physical channel counts.  Every memory-bound pass moves 16-byte vectors of 8 channels and the GEMMs contract over at least
+    # 64, while the reference accepts ANY width (wav2letter.py:59-64; 250 in the original paper; 161 STFT bins when input_size is unset):
+    # activation buffers therefore carry max(64, ceil8(C)) columns, the surplus ones exact zeros -- zero weight rows produce them, zero
+    # weight columns ignore them, BatchNorm maps 0 to 0 there (mean 0, shift 0) and every activation keeps 0 -- and parameters /
+    # gradients keep the reference's logical shapes.  ``padded`` is False for every shipped yaml: nothing changes for those.
+    @staticmethod
+    def phys(c):
+        return max(64, (c + 7) // 8 * 8)
+
+    @property
+    def cin_phys(self):
+        return self.phys(self.in_channels) * (self.kernel_size[0] if self.unfold else 1)
+
+    @property
+    def cout_phys(self):
+        return self.out_channels if self.is_head else self.phys(self.out_channels)     # (the label head writes its logical columns)
+
+    @property
+    def padded(self):
+        return self.cin_phys != self.cin_eff or self.cout_phys != self.out_channels
+
+    def unpad_dw(self, dw):
+        """[k_eff, rows, cin_phys] as the weight-gradient kernel wrote it -> contiguous [k_eff, Cout, cin_eff] (the Parameter's layout)"""
+        Co, Ci, k = self.out_channels, self.in_channels, self.kernel_size[0]
+        if self.unfold:
+            return dw.view(dw.shape[1], k, self.phys(Ci))[:Co, :, :Ci].reshape(1, Co, k * Ci)
+        return dw[:, :Co, :Ci].contiguous()
+
     def storage(self):
         """fp32 weights in kernel layout [k_eff, Cout, cin_eff] (a view of the Parameter's memory)."""
         perm = (0, 2, 1) if self.unfold else (2, 0, 1)
@@ -174,15 +208,21 @@ class ConvParams(nn.Module):
         """bf16 shadow [k_eff, cout_pad, cin_eff] read by the GEMM kernels; refreshed when the Parameter changed."""
         w = self.weight
         ver = (w._version, w.data_ptr())
-        if self.f32 and self.cout_pad == self.out_channels:
+        if self.f32 and self.cout_pad == self.out_channels and not self.padded:
             return self.storage()              # fp32 mode: the master weights ARE the operand
         dt = self.act_dtype
         if self._shadow is None or self._shadow.device != w.device or self._shadow.dtype != dt:
-            self._shadow = torch.zeros((self.k_eff, self.cout_pad, self.cin_eff), dtype=dt, device=w.device)
+            self._shadow = torch.zeros((self.k_eff, self.cout_pad, self.cin_phys), dtype=dt, device=w.device)
             self._shadow_version = None
         if self._shadow_version != ver:
             st = self.storage()
-            if self.f32:                       # padded fp32 copy (the head: Cout is not a multiple of 16)
+            Co, Ci, k = self.out_channels, self.in_channels, self.kernel_size[0]
+            if self.cin_phys != self.cin_eff:  # padded input channels: zero columns (per tap for the unfolded first layer)
+                if self.unfold:
+                    self._shadow[0].view(self.cout_pad, k, self.phys(Ci))[:Co, :, :Ci].copy_(st[0].view(Co, k, Ci))
+                else:
+                    self._shadow[:, :Co, :Ci].copy_(st)
+            elif self.f32:                     # padded fp32 copy (the head: Cout is not a multiple of 16)
                 self._shadow[:, :self.out_channels].copy_(st)
             elif self.cout_pad == self.out_channels:
                 F.cast_bf16(st, self._shadow)
@@ -196,8 +236,10 @@ class ConvParams(nn.Module):
         """bf16 shadow for backward-data: [k_eff, cin_pad16, cout_pad], taps reversed and transposed (K-major operand)."""
         w = self.weight
         ver = (w._version, w.data_ptr())
+        if self.unfold and self.cin_phys != self.cin_eff:
+            raise NotImplementedError("backward-data through an unfolded layer with padded input channels")     # (never needed: the model input has no gradient)
         if getattr(self, "_shadow_t", None) is None or self._shadow_t.device != w.device or self._shadow_t.dtype != self.act_dtype:
-            cin_pad = (self.cin_eff + 15) // 16 * 16
+            cin_pad = (self.cin_phys + 15) // 16 * 16
             self._shadow_t = torch.zeros((self.k_eff, cin_pad, self.cout_pad), dtype=self.act_dtype, device=w.device)
             self._shadow_t_version = None
         if self._shadow_t_version != ver:
@@ -335,11 +377,14 @@ class BatchNormParams(nn.Module):
         return "%d, eps=%g, momentum=%g" % (self.num_features, self.eps, self.momentum)
 
 
-def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0, ldy=None, y_dtype=F.DT_BF16, act=F.ACT_NONE):
+def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0, ldy=None, y_dtype=F.DT_BF16, act=F.ACT_NONE, cout=None):
+    """``cout``: output columns of the GEMM -- default the layer's PHYSICAL width (the activation buffer's columns; the surplus ones come
+    out as exact zeros from the zero rows of the packed weights); the label head passes its logical width."""
     if conv.f32 and y_dtype == F.DT_BF16:
         y_dtype = F.DT_F32                     # fp32-faithful mode: every activation buffer is fp32
-    return F.make_desc(B, T_out, conv.cin_eff, conv.out_channels, conv.cout_pad, conv.k_eff, conv.dilation[0], x_rows, x_row_offset,
-                       T_out if y_rows is None else y_rows, y_row_offset, conv.out_channels if ldy is None else ldy, y_dtype, act,
+    cout = conv.cout_phys if cout is None else cout
+    return F.make_desc(B, T_out, conv.cin_phys, cout, conv.cout_pad, conv.k_eff, conv.dilation[0], x_rows, x_row_offset,
+                       T_out if y_rows is None else y_rows, y_row_offset, cout if ldy is None else ldy, y_dtype, act,
                        conv.x_dtype)
 
 
@@ -416,11 +461,21 @@ class BnScratch:
         return self.red
 
 
-def bn_scratch(bn, device):
+def bn_scratch(bn, device, C=None):
+    C = bn.num_features if C is None else C               # (the physical width when the channel count is padded)
     sc = bn.__dict__.get("_w2l_scratch")
-    if sc is None or sc.stats.device != device:
-        sc = bn.__dict__["_w2l_scratch"] = BnScratch(bn.num_features, device)
+    if sc is None or sc.stats.device != device or sc.stats.numel() != 2 * C:
+        sc = bn.__dict__["_w2l_scratch"] = BnScratch(C, device)
     return sc
+
+
+def pad_channels(t, Cp, value=0.0):
+    """per-channel vector [C] -> [Cp] (a copy with ``value`` in the surplus channels); None and already-wide vectors pass through"""
+    if t is None or t.numel() == Cp:
+        return t
+    out = torch.full((Cp,), value, dtype=t.dtype, device=t.device)
+    out[:t.numel()].copy_(t.detach())
+    return out
 
 
 def conv_fwd_with_stats(xin, conv, desc, z, stats=None):
@@ -428,10 +483,10 @@ def conv_fwd_with_stats(xin, conv, desc, z, stats=None):
     ``stats`` (zero on entry) when given."""
     if not _EPILOGUE_STATS:
         F.conv1d_fwd(xin, conv.packed(), desc, z)
-        st = F.bn_stats(z, conv.out_channels)
+        st = F.bn_stats(z, conv.cout_phys)
         return st if stats is None else stats.copy_(st)
     if stats is None:
-        stats = torch.zeros((2 * conv.out_channels,), dtype=torch.float32, device=xin.device)
+        stats = torch.zeros((2 * conv.cout_phys,), dtype=torch.float32, device=xin.device)
     F.conv1d_fwd(xin, conv.packed(), desc, z, bn_stats=stats)
     return stats
 
@@ -461,13 +516,17 @@ class ConvBNActFn(torch.autograd.Function):
     def forward(ctx, xin, weight, bias, gamma, beta, z_res, fin_res, conv, bn, geo):
         B, x_rows, _ = xin.shape
         T_out = geo["T_out"]
-        Co = conv.out_channels
+        Co, C_log = conv.cout_phys, conv.out_channels      # physical (buffer) / logical (parameter) width: equal unless padded
         pl, pr = geo.get("out_pad", (0, 0))
         z = torch.empty((B, T_out, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"])
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()                       # side stream: runs beside the GEMM launched next
-        sc = bn_scratch(bn, xin.device)
+        sc = bn_scratch(bn, xin.device, Co)
+        rm, rv = bn.running_mean, bn.running_var
+        if Co != C_log:                                    # padded width: per-channel vectors with neutral surplus entries (see ConvParams.phys)
+            gamma, beta, bias = pad_channels(gamma, Co, 1.0), pad_channels(beta, Co), pad_channels(bias, Co)
+            rm, rv = pad_channels(rm, Co), pad_channels(rv, Co, 1.0)
         stats = conv_fwd_with_stats(xin, conv, desc, z, sc.take_stats())      # batch statistics from the GEMM epilogue
         drop_p = geo.get("drop_p", 0.0)
         seed = next_dropout_seed() if drop_p > 0 else 0
@@ -475,11 +534,14 @@ class ConvBNActFn(torch.autograd.Function):
         has_res = z_res is not None
         # ONE launch: statistics -> scale/shift (+ running statistics, conv bias folded into the running mean), BatchNorm apply,
         # residual, dropout, activation, the consumer's halo / mask; it also clears this layer's backward reduction buffer
-        yp, fin = F.bn_finalize_act_pad(z, stats, gamma, beta, bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+        yp, fin = F.bn_finalize_act_pad(z, stats, gamma, beta, bias, bn.eps, bn.momentum, rm, rv,
                                         bn.num_batches_tracked, B, T_out, Co, pl, pr, geo["act"], drop_p, seed, geo.get("lens"),
                                         res=z_res, res_scale=fin_res[0] if has_res else None, res_shift=fin_res[1] if has_res else None,
                                         drop_mask=mask, zero_after=sc.red)
         sc.red_clean = True
+        if Co != C_log:
+            bn.running_mean.copy_(rm[:C_log])
+            bn.running_var.copy_(rv[:C_log])
         ctx.bn = bn
         ctx.conv, ctx.geo, ctx.seed, ctx.desc, ctx.has_res = conv, geo, seed, desc, has_res
         ctx.has_bias = bias is not None
@@ -503,7 +565,7 @@ class ConvBNActFn(torch.autograd.Function):
         # zero tails, so that backward-data runs over one flat [B*x_rows] row space (no per-utterance tile padding).
         flat = ctx.needs_input_grad[0] and geo["x_row_offset"] == 0 and x_rows == T_out + halo
         dz_rows = x_rows if flat else T_out
-        sc = bn_scratch(ctx.bn, z.device)
+        sc = bn_scratch(ctx.bn, z.device, Co)
         pre_red = ctx.prod_out["red"] if ctx.prod_out is not None else None      # the consumer's GEMM epilogue already reduced (FusedBnReduce)
         dz, red, g = F.bn_act_bwd(dyp.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T_out, Co, pl, pr, geo["act"],
                                   geo.get("drop_p", 0.0), ctx.seed, geo.get("lens"), res=z_res,
@@ -511,7 +573,7 @@ class ConvBNActFn(torch.autograd.Function):
                                   want_g=has_res, dz_rows=dz_rows, drop_mask=mask, red_ws=None if pre_red is not None else sc.take_red(),
                                   zero_after=sc.stats, red_raw=pre_red)
         sc.stats_clean = True                            # the apply pass cleared the forward statistics for the next step
-        dw = alloc_dw(conv, z.device)
+        dw = alloc_dw(conv, z.device, cout=Co)
         side = WgradStream.fork(z.device, conv.weight)   # dz is enqueued: wgrad may start; dgrad goes first on the compute stream
         dx = None
         if ctx.needs_input_grad[0]:
@@ -521,9 +583,10 @@ class ConvBNActFn(torch.autograd.Function):
                 F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), conv_desc(conv, 1, B * x_rows, B * x_rows, 0), dx, bnred=bnred)
             else:
                 F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx, bnred=bnred)
-        wgrad_async(side, dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw)
+        dw = wgrad_async(side, dz, xin, conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=dz_rows), dw, conv)
         dbias = zero_bias_grad(conv, z.device) if ctx.has_bias else None                          # exactly 0 under train BN
-        return dx, conv.grad_view(dw), dbias, red[Co:], red[:Co], g, None, None, None, None
+        C_log = conv.out_channels                                                                 # (Co is the physical width: padded layers)
+        return dx, conv.grad_view(dw), dbias, red[Co:Co + C_log], red[:C_log], g, None, None, None, None
 
 
 class ResidualBranchFn(torch.autograd.Function):
@@ -575,7 +638,7 @@ class ConvHeadFn(torch.autograd.Function):
         Co = conv.out_channels
         ld = (Co + 7) // 8 * 8
         logits = torch.empty((B, T, ld), dtype=torch.float32, device=xin.device)
-        desc = conv_desc(conv, B, T, T, 0, ldy=ld, y_dtype=F.DT_F32)
+        desc = conv_desc(conv, B, T, T, 0, ldy=ld, y_dtype=F.DT_F32, cout=Co)
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
         F.conv1d_fwd(xin, conv.packed(), desc, logits, bias=bias)
@@ -595,14 +658,14 @@ class ConvHeadFn(torch.autograd.Function):
         B, T, _ = xin.shape
         Co, cp = conv.out_channels, conv.cout_pad
         dl = F.log_softmax_bwd(dout.contiguous(), out, cp, fused_identity=ctx.mode == 2, out_dtype=conv.act_dtype)    # [B,T,cout_pad], zero padded
-        desc = conv_desc(conv, B, T, T, 0, ldy=cp)
-        dw = alloc_dw(conv, xin.device)
+        desc = conv_desc(conv, B, T, T, 0, ldy=cp, cout=Co)
+        dw = alloc_dw(conv, xin.device, cout=Co)
         side = WgradStream.fork(xin.device, conv.weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
             F.conv1d_dgrad_wt(dl, conv.packed_t_synced(), desc, dx, bnred=FusedBnReduce.for_dgrad(ctx.prod_in, xin))
-        wgrad_async(side, dl, xin, desc, dw)
+        dw = wgrad_async(side, dl, xin, desc, dw, conv)
         dbias = F.colsum(dl, Co) if ctx.has_bias else None
         return dx, conv.grad_view(dw), dbias, None, None, None
 
@@ -612,10 +675,12 @@ def conv_bn_act_eval(xin, conv, bn, geo, res=None):
     fill; with a residual branch or a length mask the BN/act/mask pass runs as in training (running statistics).
     ``res`` = (z_res, (scale_res, shift_res))."""
     B, x_rows, _ = xin.shape
-    T_out, Co = geo["T_out"], conv.out_channels
+    T_out, Co = geo["T_out"], conv.cout_phys
     pl, pr = geo.get("out_pad", (0, 0))
     lens = geo.get("lens")
     scale, shift = bn.eval_scale_shift(conv.bias)
+    if Co != conv.out_channels:                    # padded width: the surplus channels come out as 0 * 0 + 0
+        scale, shift = pad_channels(scale, Co), pad_channels(shift, Co)
     if res is None and lens is None:
         y = torch.empty((B, pl + T_out + pr, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T_out, x_rows, geo["x_row_offset"], y_rows=pl + T_out + pr, y_row_offset=pl, act=geo["act"])

@@ -101,7 +101,7 @@ class Novograd(Optimizer):
                     vmax[i] = torch.as_tensor(st["max_exp_avg_sq"], dtype=torch.float32).to(dev)
                 st["max_exp_avg_sq"] = vmax[i]
             conv = self._conv_of.get(id(p))
-            if conv is not None and conv.cout_pad == conv.out_channels and not getattr(conv, "f32", False):   # (fp32 mode: no bf16 shadow)
+            if conv is not None and conv.cout_pad == conv.out_channels and not getattr(conv, "f32", False) and not conv.padded:   # (fp32 mode: no bf16 shadow; padded widths: re-packed by ConvParams.packed)
                 shadows.append(conv.packed().data_ptr())
                 convs.append(conv)
                 shadow_of.append(conv)

@@ -40,9 +40,8 @@ class Conv1dBlock(nn.Module):
         self.conv1 = ConvParams(input_channels, output_channels, k, stride=stride, dilation=dilation, bias=True, unfold=stride > 1)
         self.batch_norm = BatchNormParams(output_channels, eps=0.001, momentum=0.9) if bn else nn.Identity()
         self.has_bn = bn
+        self.conv1.is_head = not bn  # the bias-only label head
         self.next_pad = (0, 0)       # reflect halo the consumer block wants; set by the owning model
-        if bn and (output_channels % 8 or output_channels < 64):         # 16-byte (8 x bf16) vectors in every memory-bound pass
-            raise ValueError("Conv1dBlock: hidden width %d must be a multiple of 8 and >= 64 for the tensor-core path" % output_channels)
 
     # ---- geometry
     def out_rows(self, t_in):
@@ -62,6 +61,9 @@ class Conv1dBlock(nn.Module):
         t_out = self.out_rows(t_in)
         pl, pr = self.pad_lr
         if from_ncw:
+            Fp = conv.phys(conv.in_channels)
+            if Fp != xin.shape[1]:                        # feature counts that are not a multiple of 8 (161 STFT bins) or below 64: zero rows
+                xin = torch.nn.functional.pad(xin, (0, 0, 0, Fp - xin.shape[1]))
             if conv.unfold:
                 xin = F.im2col_ncw(xin, t_out, self.kernel_size[0], self.stride, self.dilation, pl, F.PAD_REFLECT, out_dtype=conv.act_dtype)
             else:
@@ -104,6 +106,10 @@ class _TmToNcw(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         B, C, T = g.shape
+        if ctx.shape[2] != C:                             # padded width: the surplus channels of the buffer have no gradient
+            out = torch.zeros(ctx.shape, dtype=torch.float32 if ctx.f32 else torch.bfloat16, device=g.device)
+            out[:, :, :C] = g.transpose(1, 2)
+            return out, None, None
         if ctx.f32:
             return g.transpose(1, 2).contiguous().float(), None, None
         out = torch.empty(ctx.shape, dtype=torch.bfloat16, device=g.device)
