@@ -229,6 +229,16 @@ int w2l_depthwise_dgrad_strided(const void* dy, const float* w, void* dx, int32_
                                 int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
 int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
                         int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+/* the four with fp32 activations (a separable Jasper block in the fp32-faithful mode; plain fp32 FMAs, as the reference's depthwise
+ * nn.Conv1d runs them) */
+int w2l_depthwise_fwd_f32(const float* x, const float* w, float* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                          int32_t stride, int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream);
+int w2l_depthwise_dgrad_f32(const float* dy, const float* w, float* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                            int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+int w2l_depthwise_dgrad_strided_f32(const float* dy, const float* w, float* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                    int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
+int w2l_depthwise_wgrad_f32(const float* dy, const float* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                            int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Memory-bound companions of the conv kernels (all time-major).

@@ -49,7 +49,7 @@ def elementwise():
 
 @functools.lru_cache(maxsize=None)
 def depthwise():
-    return KE.build(["depthwise.cu"], ["depthwise_corr_kernel", "depthwise_dgrad_strided_kernel", "depthwise_wgrad_kernel"])
+    return KE.build(["depthwise.cu"], ["depthwise_corr_kernel<__nv_bfloat16>", "depthwise_dgrad_strided_kernel<__nv_bfloat16>", "depthwise_wgrad_kernel<__nv_bfloat16>"])
 
 
 @functools.lru_cache(maxsize=None)
@@ -296,7 +296,7 @@ def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
     B, T, C = x.shape
     y = torch.full((B, T_out, C), float("nan"), dtype=BF16)
     ol = None if out_lens is None else out_lens.to(torch.int32).contiguous()
-    depthwise().launch("depthwise_corr_kernel", ((C // 8 + 31) // 32, (B * T_out + 7) // 8), (32, 8), _p(x), _p(w), _p(y), B, T, T_out, C, k,
+    depthwise().launch("depthwise_corr_kernel<__nv_bfloat16>", ((C // 8 + 31) // 32, (B * T_out + 7) // 8), (32, 8), _p(x), _p(w), _p(y), B, T, T_out, C, k,
                        stride, dilation, -pad, 0, None, _p(ol))
     return y
 
@@ -309,10 +309,10 @@ def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None, stride=1):
     dl = None if dy_lens is None else dy_lens.to(torch.int32).contiguous()
     grid = ((C // 8 + 31) // 32, (B * T + 7) // 8)
     if stride == 1:
-        depthwise().launch("depthwise_corr_kernel", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T_out, T, C, k, 1, dilation,
+        depthwise().launch("depthwise_corr_kernel<__nv_bfloat16>", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T_out, T, C, k, 1, dilation,
                            pad - (k - 1) * dilation, 1, _p(dl), None)
     else:
-        depthwise().launch("depthwise_dgrad_strided_kernel", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T, T_out, C, k, stride, dilation, pad,
+        depthwise().launch("depthwise_dgrad_strided_kernel<__nv_bfloat16>", grid, (32, 8), _p(dy), _p(w), _p(dx), B, T, T_out, C, k, stride, dilation, pad,
                            _p(dl))
     return dx
 
@@ -326,7 +326,7 @@ def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
     dl = None if dy_lens is None else dy_lens.to(torch.int32).contiguous()
     rows = B * T_out
     rpb = max(64, (rows + SMS - 1) // SMS)
-    depthwise().launch("depthwise_wgrad_kernel", ((C // 8 + 31) // 32, (rows + rpb - 1) // rpb, (k + 3) // 4), (32, 8), _p(dy), _p(x), _p(dw),
+    depthwise().launch("depthwise_wgrad_kernel<__nv_bfloat16>", ((C // 8 + 31) // 32, (rows + rpb - 1) // rpb, (k + 3) // 4), (32, 8), _p(dy), _p(x), _p(dw),
                        B, T, T_out, C, k, stride, dilation, pad, _p(dl), rpb)
     return dw
 

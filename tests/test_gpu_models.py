@@ -524,9 +524,40 @@ def test_jasper_dense_golden_fp32_faithful_mode(pkg, golden):
     # eval probabilities: 1.9e-3 on the host emulation (running statistics do not re-centre the tf32 roundings of 11 convs the way
     # batch statistics do in training: 4.2e-4 there); bf16 path: 2e-2
     assert rel_l2(o, g["eval:out"]) < 5e-3 and abs(float(o.sum(-1).mean()) - 1.0) < 1e-5
-    cfg["jasper_blocks"] = config.to_attr([dict(b, separable=True) for b in blocks])
-    with pytest.raises(NotImplementedError):
-        Jasper(cfg)
+
+
+def test_jasper_separable_golden_fp32_faithful_mode(pkg, golden):
+    """``jasper_small`` -- with a separable (depthwise + pointwise) block as in the shipped model/jasper.yaml -- in precision='tf32': the
+    depthwise convs run as plain fp32 FMAs over fp32 activations (w2l_depthwise_*_f32)"""
+    from wav2letter_pytorch_b200 import config
+    from wav2letter_pytorch_b200.jasper import Jasper
+    g = golden("jasper_small")
+    blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
+    assert any(b.get("separable", True) for b in blocks)
+    cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
+    cfg["jasper_blocks"] = config.to_attr(blocks)
+    cfg["precision"] = "tf32"
+    torch.manual_seed(2)
+    model = Jasper(cfg)
+    _load_sd(model, g, "sd0:")
+    model.cuda().train()
+    x, il = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["il"]).cuda()
+    tg, tl = torch.from_numpy(g["tg"]).cuda(), torch.from_numpy(g["tl"]).cuda()
+    out, ol = model(x, il)
+    loss = model.criterion(out.transpose(0, 1), tg, ol, tl)
+    loss.backward()
+    assert np.array_equal(ol.cpu().numpy(), g["train:out_len"])
+    report = {"out": rel_l2(out.detach(), g["train:out"]), "loss": abs(loss.item() - float(g["train:loss"])) / abs(float(g["train:loss"]))}
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.dtype == torch.float32, name
+        e = rel_l2(p.grad, torch.from_numpy(g["train:grad:" + name]))
+        if e > worst[1]:
+            worst = (name, e)
+    report["grad"] = worst[1]
+    print("separable Jasper tf32 mode vs the reference fixture:", json.dumps(report), "worst gradient:", worst[0])
+    for key, bound in dict(out=TOL_TF32["out"], loss=TOL_TF32["loss"], grad=2e-1).items():
+        assert report[key] < bound, (key, report, worst)
 
 
 @pytest.mark.parametrize("mid_layers", [1, 20])

@@ -94,6 +94,10 @@ def test_config_compose_and_labels():
     assert type(dec).__name__ == "GreedyDecoder" and dec.space_index == 28 and dec.blank_index == 0
 
 
+from wav2letter_pytorch_b200.layers import ConvParams as _CP
+ConvParamsPhys = _CP.phys
+
+
 def test_padding_rule_and_model_contract():
     from oracle import w2l_oracle as O
     from wav2letter_pytorch_b200 import config
@@ -119,8 +123,11 @@ def test_padding_rule_and_model_contract():
     assert blk.conv1.weight.shape == (896, 768, 29) and blk.pad_lr == (28, 28) and blk.batch_norm.momentum == 0.9
     assert model.conv1ds.conv1d_15.next_pad == (28, 28) and model.conv1ds.conv1d_19.next_pad == (0, 0)
     assert Wav2Letter(config.compose().model).conv1ds.conv1d_1.conv1.out_channels == 29         # literal default: 1 block + head
-    with pytest.raises(ValueError):
-        Conv1dBlock(64, 100, (3,), 1)
+    odd = Conv1dBlock(161, 250, (11,), 2)                     # any width, as in the reference: padded internally (ConvParams.phys)
+    assert odd.conv1.weight.shape == (250, 161, 11) and odd.conv1.padded
+    assert (odd.conv1.cin_phys, odd.conv1.cout_phys, odd.conv1.cout_pad) == (11 * 168, 256, 256)
+    assert not Conv1dBlock(64, 256, (11,), 2).conv1.padded and not model.conv1ds.conv1d_16.conv1.padded
+    assert ConvParamsPhys(36) == 64 and ConvParamsPhys(250) == 256 and ConvParamsPhys(896) == 896
 
 
 def test_conv_params_layout_roundtrip():

@@ -21,7 +21,7 @@ class _Both:
 
     def __init__(self):
         self.parts = [KE.build(["elementwise.cu"], ["im2col_tm_kernel", "col2im_tm_kernel"], drop=E.ELEMENTWISE_DROP, extra=E.ELEMENTWISE_PTX),
-                      KE.build(["depthwise.cu"], ["depthwise_corr_kernel", "depthwise_dgrad_strided_kernel", "depthwise_wgrad_kernel"])]
+                      KE.build(["depthwise.cu"], ["depthwise_corr_kernel<__nv_bfloat16>", "depthwise_dgrad_strided_kernel<__nv_bfloat16>", "depthwise_wgrad_kernel<__nv_bfloat16>"])]
 
     def launch(self, kernel, *a, **k):
         next(p for p in self.parts if kernel in p._sigs).launch(kernel, *a, **k)
@@ -96,7 +96,7 @@ def test_depthwise_dgrad_strided_source(emu, B, T, C, k, s, d, pad):
     grid, block = dw_grid(C, B * T)
     for dl in (None, lens):
         dx = torch.full((B, T, C), float("nan"), dtype=torch.bfloat16)
-        emu.launch("depthwise_dgrad_strided_kernel", grid, block, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, T, T_out, C, k, s, d, pad,
+        emu.launch("depthwise_dgrad_strided_kernel<__nv_bfloat16>", grid, block, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, T, T_out, C, k, s, d, pad,
                    None if dl is None else dl.data_ptr())
         want = O.depthwise_dgrad_strided(dy.float().numpy(), w.numpy(), T, s, d, pad, None if dl is None else dl.numpy())
         assert not torch.isnan(dx.float()).any()
@@ -105,7 +105,7 @@ def test_depthwise_dgrad_strided_source(emu, B, T, C, k, s, d, pad):
     if s == 1:
         # control: the stride-1 backward-data path of the hardware-verified correlation kernel computes the same thing
         a = torch.full((B, T, C), float("nan"), dtype=torch.bfloat16)
-        emu.launch("depthwise_corr_kernel", grid, block, dy.data_ptr(), w.data_ptr(), a.data_ptr(), B, T_out, T, C, k, 1, d, pad - (k - 1) * d, 1,
+        emu.launch("depthwise_corr_kernel<__nv_bfloat16>", grid, block, dy.data_ptr(), w.data_ptr(), a.data_ptr(), B, T_out, T, C, k, 1, d, pad - (k - 1) * d, 1,
                    lens.data_ptr(), None)
         torch.testing.assert_close(a.float(), dx.float(), rtol=2.0 ** -7, atol=2.0 ** -9 * float(a.float().abs().max()))
 
@@ -119,12 +119,12 @@ def test_depthwise_fwd_source_is_adjoint_of_strided_dgrad(emu, B, T, C, k, s, d,
     w = torch.randn(k, C, generator=gen).contiguous()
     y = torch.full((B, T_out, C), float("nan"), dtype=torch.bfloat16)
     grid, block = dw_grid(C, B * T_out)
-    emu.launch("depthwise_corr_kernel", grid, block, x.data_ptr(), w.data_ptr(), y.data_ptr(), B, T, T_out, C, k, s, d, -pad, 0, None, None)
+    emu.launch("depthwise_corr_kernel<__nv_bfloat16>", grid, block, x.data_ptr(), w.data_ptr(), y.data_ptr(), B, T, T_out, C, k, s, d, -pad, 0, None, None)
     want = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.t().reshape(C, 1, k), stride=s, padding=pad, dilation=d, groups=C).transpose(1, 2)
     torch.testing.assert_close(y.float(), want, rtol=2.0 ** -7, atol=2.0 ** -9 * float(want.abs().max()))
     dx = torch.full((B, T, C), float("nan"), dtype=torch.bfloat16)
     grid, block = dw_grid(C, B * T)
-    emu.launch("depthwise_dgrad_strided_kernel", grid, block, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, T, T_out, C, k, s, d, pad, None)
+    emu.launch("depthwise_dgrad_strided_kernel<__nv_bfloat16>", grid, block, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, T, T_out, C, k, s, d, pad, None)
     lhs = float((y.double() * dy.double()).sum())
     rhs = float((x.double() * dx.double()).sum())
     norm = float(y.double().norm() * dy.double().norm())
@@ -143,7 +143,7 @@ def test_depthwise_wgrad_source(emu, B, T, C, k, s, d, pad):
     grid = ((C // 8 + 31) // 32, (rows + rpb - 1) // rpb, (k + 3) // 4)
     for dl in (None, lens):
         dw = torch.zeros(k, C)
-        emu.launch("depthwise_wgrad_kernel", grid, (32, 8), dy.data_ptr(), x.data_ptr(), dw.data_ptr(), B, T, T_out, C, k, s, d, pad,
+        emu.launch("depthwise_wgrad_kernel<__nv_bfloat16>", grid, (32, 8), dy.data_ptr(), x.data_ptr(), dw.data_ptr(), B, T, T_out, C, k, s, d, pad,
                    None if dl is None else dl.data_ptr(), rpb)
         g = dy.float().clone()
         if dl is not None:

@@ -137,6 +137,10 @@ SIGNATURES = {
     "w2l_log_softmax_bwd_f32": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i32, c_i32, c_ptr]),
     "w2l_colsum_f32": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "w2l_pack_wt_f32": (c_i32, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "w2l_depthwise_fwd_f32": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
+    "w2l_depthwise_dgrad_f32": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr, c_ptr]),
+    "w2l_depthwise_dgrad_strided_f32": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
+    "w2l_depthwise_wgrad_f32": (c_i32, [c_ptr, c_ptr, c_ptr] + [c_i32] * 8 + [c_ptr, c_ptr]),
     "w2l_conv1d_dgrad_wt_bnred": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), ctypes.POINTER(BnReduce), c_ptr]),
     "w2l_conv1d_wgrad_t": (c_i32, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_tm_to_ct_f32": (c_i32, [c_ptr, c_ptr] + [c_i32] * 7 + [c_ptr]),

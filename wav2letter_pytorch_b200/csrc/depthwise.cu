@@ -23,28 +23,49 @@ __device__ __forceinline__ void dw_unpack8(const uint4& q, float (&v)[8]) {
   }
 }
 
+// 8 consecutive channels of one row, bf16 or fp32 storage (the fp32-faithful mode of a separable Jasper block): the plain kernels
+// below are written once over these; the register-tiled ones stay bf16-only
+__device__ __forceinline__ void dw_load8(const __nv_bfloat16* p, float (&v)[8]) { dw_unpack8(__ldg(reinterpret_cast<const uint4*>(p)), v); }
+__device__ __forceinline__ void dw_load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void dw_store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void dw_store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // Generic correlation: out[b,t,c] = sum_j in[b, t*stride + j*dil*dir + off, c] * w[jw(j), c], jw(j) = flip ? k-1-j : j.
 // Rows of `in` outside [0, in_rows) or >= in_lens[b] read as zero; rows of `out` >= out_lens[b] are written as zero.
+template <typename TA>
 __global__ void __launch_bounds__(256)
-depthwise_corr_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int B,
+depthwise_corr_kernel(const TA* __restrict__ in, const float* __restrict__ w, TA* __restrict__ out, int B,
                       int in_rows, int out_rows, int C, int k, int stride, int dil, int off, int flip,
                       const int32_t* __restrict__ in_lens, const int32_t* __restrict__ out_lens) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r = blockIdx.y * 8 + threadIdx.y;            // flattened (b, t)
   if (c >= C || r >= B * out_rows) return;
   const int b = r / out_rows, t = r - b * out_rows;
-  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (!out_lens || t < out_lens[b]) {
     const int lim = in_lens ? min(in_rows, max(0, in_lens[b])) : in_rows;
-    const __nv_bfloat16* ib = in + (int64_t)b * in_rows * C + c;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const TA* ib = in + (int64_t)b * in_rows * C + c;
     for (int j = 0; j < k; ++j) {
       const int u = t * stride + j * dil + off;
       if (u < 0 || u >= lim) continue;
       float xv[8];
-      dw_unpack8(__ldg(reinterpret_cast<const uint4*>(ib + (int64_t)u * C)), xv);
+      dw_load8(ib + (int64_t)u * C, xv);
       const float* wj = w + (int64_t)(flip ? k - 1 - j : j) * C + c;
       const float4 w0 = __ldg(reinterpret_cast<const float4*>(wj)), w1 = __ldg(reinterpret_cast<const float4*>(wj) + 1);
       acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
@@ -52,25 +73,22 @@ depthwise_corr_kernel(const __nv_bfloat16* __restrict__ in, const float* __restr
       acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
       acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
     }
-    q.x = pack_bf16x2(acc[0], acc[1]);
-    q.y = pack_bf16x2(acc[2], acc[3]);
-    q.z = pack_bf16x2(acc[4], acc[5]);
-    q.w = pack_bf16x2(acc[6], acc[7]);
   }
-  *reinterpret_cast<uint4*>(out + (int64_t)r * C + c) = q;
+  dw_store8(out + (int64_t)r * C + c, acc);
 }
 
 // Backward-data of a STRIDED depthwise conv (a strided separable block that is not the encoder's first one):
 // dx[b,u,c] = sum over taps j with u + pad - j*dil = t*stride, 0 <= t < min(y_rows, dy_lens[b]), of dy[b,t,c] * w[j,c].
+template <typename TA>
 __global__ void __launch_bounds__(256)
-depthwise_dgrad_strided_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, int B,
+depthwise_dgrad_strided_kernel(const TA* __restrict__ dy, const float* __restrict__ w, TA* __restrict__ dx, int B,
                                int x_rows, int y_rows, int C, int k, int stride, int dil, int pad, const int32_t* __restrict__ dy_lens) {
   const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r = blockIdx.y * 8 + threadIdx.y;            // flattened (b, u)
   if (c >= C || r >= B * x_rows) return;
   const int b = r / x_rows, u = r - b * x_rows;
   const int lim = dy_lens ? min(y_rows, max(0, dy_lens[b])) : y_rows;
-  const __nv_bfloat16* gb = dy + (int64_t)b * y_rows * C + c;
+  const TA* gb = dy + (int64_t)b * y_rows * C + c;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -80,7 +98,7 @@ depthwise_dgrad_strided_kernel(const __nv_bfloat16* __restrict__ dy, const float
     const int t = v / stride;
     if (t * stride != v || t >= lim) continue;
     float g[8];
-    dw_unpack8(__ldg(reinterpret_cast<const uint4*>(gb + (int64_t)t * C)), g);
+    dw_load8(gb + (int64_t)t * C, g);
     const float* wj = w + (int64_t)j * C + c;
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(wj)), w1 = __ldg(reinterpret_cast<const float4*>(wj) + 1);
     acc[0] = fmaf(g[0], w0.x, acc[0]); acc[1] = fmaf(g[1], w0.y, acc[1]);
@@ -88,17 +106,13 @@ depthwise_dgrad_strided_kernel(const __nv_bfloat16* __restrict__ dy, const float
     acc[4] = fmaf(g[4], w1.x, acc[4]); acc[5] = fmaf(g[5], w1.y, acc[5]);
     acc[6] = fmaf(g[6], w1.z, acc[6]); acc[7] = fmaf(g[7], w1.w, acc[7]);
   }
-  uint4 q;
-  q.x = pack_bf16x2(acc[0], acc[1]);
-  q.y = pack_bf16x2(acc[2], acc[3]);
-  q.z = pack_bf16x2(acc[4], acc[5]);
-  q.w = pack_bf16x2(acc[6], acc[7]);
-  *reinterpret_cast<uint4*>(dx + (int64_t)r * C + c) = q;
+  dw_store8(dx + (int64_t)r * C + c, acc);
 }
 
 // block (32, 8); grid (channel blocks, row chunks, tap groups of 4)
+template <typename TA>
 __global__ void __launch_bounds__(256)
-depthwise_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, float* __restrict__ dw, int B,
+depthwise_wgrad_kernel(const TA* __restrict__ dy, const TA* __restrict__ x, float* __restrict__ dw, int B,
                        int x_rows, int y_rows, int C, int k, int stride, int dil, int pad, const int32_t* __restrict__ dy_lens,
                        int rows_per_block) {
   __shared__ float s_acc[8][4][256 + 8];
@@ -116,14 +130,14 @@ depthwise_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
       const int b = r / y_rows, t = r - b * y_rows;
       if (dy_lens && t >= dy_lens[b]) continue;
       float g[8];
-      dw_unpack8(__ldg(reinterpret_cast<const uint4*>(dy + (int64_t)r * C + c)), g);
-      const __nv_bfloat16* xb = x + (int64_t)b * x_rows * C + c;
+      dw_load8(dy + (int64_t)r * C + c, g);
+      const TA* xb = x + (int64_t)b * x_rows * C + c;
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const int j = j0 + a, u = t * stride + j * dil - pad;
         if (j < k && u >= 0 && u < x_rows) {
           float xv[8];
-          dw_unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (int64_t)u * C)), xv);
+          dw_load8(xb + (int64_t)u * C, xv);
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[a][i] = fmaf(g[i], xv[i], acc[a][i]);
         }
@@ -319,13 +333,18 @@ static int dw_check(const char* who, int B, int T, int C, int T_out, int k, int 
 
 extern "C" {
 
-int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k, int32_t stride,
-                      int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream) {
+static int dw_fwd_impl(int f32, const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                       int32_t stride, int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream) {
   using namespace w2l;
   int rc = dw_check("depthwise_fwd", B, T, C, T_out, k, stride, dilation, pad);
   if (rc) return rc;
   W2L_REQUIRE(x && w && y, "depthwise_fwd: null pointer");
   dim3 grid((C / 8 + 31) / 32, (B * T_out + 7) / 8), block(32, 8);
+  if (f32) {
+    depthwise_corr_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)x, w, (float*)y, B, T, T_out, C, k, stride, dilation,
+                                                                           -pad, 0, nullptr, out_lens);
+    return after_launch("depthwise_corr_kernel<fwd>");
+  }
   if (stride == 1 && dilation == 1 && dw_tiled_requested()) {
     const int tiles = (T_out + kDwTile - 1) / kDwTile;
     dim3 tgrid((C / 8 + 31) / 32, (B * tiles + 7) / 8);
@@ -333,19 +352,32 @@ int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t
                                                                            -pad, 0, nullptr, out_lens, tiles);
     return after_launch("depthwise_corr_tiled_kernel<fwd>");
   }
-  depthwise_corr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, B, T, T_out, C, k, stride,
-                                                                  dilation, -pad, 0, nullptr, out_lens);
+  depthwise_corr_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, B, T, T_out, C,
+                                                                                 k, stride, dilation, -pad, 0, nullptr, out_lens);
   return after_launch("depthwise_corr_kernel<fwd>");
 }
+int w2l_depthwise_fwd(const void* x, const float* w, void* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                      int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream) {
+  return dw_fwd_impl(0, x, w, y, B, T, C, T_out, k, stride, dilation, pad, out_lens, stream);
+}
+int w2l_depthwise_fwd_f32(const float* x, const float* w, float* y, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k, int32_t stride,
+                          int32_t dilation, int32_t pad, const int32_t* out_lens, void* stream) {
+  return dw_fwd_impl(1, x, w, y, B, T, C, T_out, k, stride, dilation, pad, out_lens, stream);
+}
 
-int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
-                        int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+static int dw_dgrad_impl(int f32, const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                         int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
   using namespace w2l;
   int rc = dw_check("depthwise_dgrad", B, T, C, T_out, k, 1, dilation, pad);
   if (rc) return rc;
   W2L_REQUIRE(dy && w && dx, "depthwise_dgrad: null pointer");
   // dx[u] = sum_j dy[u + p - j*d] w[j] = sum_j' dy[u + p - (k-1)d + j'*d] w[k-1-j']
   dim3 grid((C / 8 + 31) / 32, (B * T + 7) / 8), block(32, 8);
+  if (f32) {
+    depthwise_corr_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)dy, w, (float*)dx, B, T_out, T, C, k, 1, dilation,
+                                                                           pad - (k - 1) * dilation, 1, dy_lens, nullptr);
+    return after_launch("depthwise_corr_kernel<dgrad>");
+  }
   if (dilation == 1 && dw_tiled_requested()) {
     const int tiles = (T + kDwTile - 1) / kDwTile;
     dim3 tgrid((C / 8 + 31) / 32, (B * tiles + 7) / 8);
@@ -353,25 +385,45 @@ int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int
                                                                            pad - (k - 1), 1, dy_lens, nullptr, tiles);
     return after_launch("depthwise_corr_tiled_kernel<dgrad>");
   }
-  depthwise_corr_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T_out, T, C, k, 1,
-                                                                  dilation, pad - (k - 1) * dilation, 1, dy_lens, nullptr);
+  depthwise_corr_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T_out, T, C,
+                                                                                 k, 1, dilation, pad - (k - 1) * dilation, 1, dy_lens, nullptr);
   return after_launch("depthwise_corr_kernel<dgrad>");
 }
+int w2l_depthwise_dgrad(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_dgrad_impl(0, dy, w, dx, B, T, C, T_out, k, dilation, pad, dy_lens, stream);
+}
+int w2l_depthwise_dgrad_f32(const float* dy, const float* w, float* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                            int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_dgrad_impl(1, dy, w, dx, B, T, C, T_out, k, dilation, pad, dy_lens, stream);
+}
 
-int w2l_depthwise_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
-                                int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+static int dw_dgrad_strided_impl(int f32, const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                 int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
   using namespace w2l;
   int rc = dw_check("depthwise_dgrad_strided", B, T, C, T_out, k, stride, dilation, pad);
   if (rc) return rc;
   W2L_REQUIRE(dy && w && dx, "depthwise_dgrad_strided: null pointer");
   dim3 grid((C / 8 + 31) / 32, (B * T + 7) / 8), block(32, 8);
-  depthwise_dgrad_strided_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T, T_out, C, k,
-                                                                           stride, dilation, pad, dy_lens);
+  if (f32)
+    depthwise_dgrad_strided_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)dy, w, (float*)dx, B, T, T_out, C, k, stride,
+                                                                                    dilation, pad, dy_lens);
+  else
+    depthwise_dgrad_strided_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, w, (__nv_bfloat16*)dx, B, T,
+                                                                                            T_out, C, k, stride, dilation, pad, dy_lens);
   return after_launch("depthwise_dgrad_strided_kernel");
 }
+int w2l_depthwise_dgrad_strided(const void* dy, const float* w, void* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_dgrad_strided_impl(0, dy, w, dx, B, T, C, T_out, k, stride, dilation, pad, dy_lens, stream);
+}
+int w2l_depthwise_dgrad_strided_f32(const float* dy, const float* w, float* dx, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                                    int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_dgrad_strided_impl(1, dy, w, dx, B, T, C, T_out, k, stride, dilation, pad, dy_lens, stream);
+}
 
-int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
-                        int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+static int dw_wgrad_impl(int f32, const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                         int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
   using namespace w2l;
   int rc = dw_check("depthwise_wgrad", B, T, C, T_out, k, stride, dilation, pad);
   if (rc) return rc;
@@ -379,16 +431,28 @@ int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int
   const int rows = B * T_out;
   int rpb = (rows + num_sms() - 1) / num_sms();
   if (rpb < 64) rpb = 64;
-  if (stride == 1 && dilation == 1 && dw_tiled_requested()) {
+  if (!f32 && stride == 1 && dilation == 1 && dw_tiled_requested()) {
     dim3 tgrid((C / 8 + 31) / 32, (rows + rpb - 1) / rpb, (k + kDwTile - 1) / kDwTile), tblock(32, 8);
     depthwise_wgrad_tiled_kernel<<<tgrid, tblock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, B, T, T_out,
                                                                              C, k, pad, dy_lens, rpb);
     return after_launch("depthwise_wgrad_tiled_kernel");
   }
   dim3 grid((C / 8 + 31) / 32, (rows + rpb - 1) / rpb, (k + 3) / 4), block(32, 8);
-  depthwise_wgrad_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, B, T, T_out, C, k,
-                                                                   stride, dilation, pad, dy_lens, rpb);
+  if (f32)
+    depthwise_wgrad_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)dy, (const float*)x, dw, B, T, T_out, C, k, stride,
+                                                                            dilation, pad, dy_lens, rpb);
+  else
+    depthwise_wgrad_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, dw, B, T,
+                                                                                    T_out, C, k, stride, dilation, pad, dy_lens, rpb);
   return after_launch("depthwise_wgrad_kernel");
+}
+int w2l_depthwise_wgrad(const void* dy, const void* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                        int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_wgrad_impl(0, dy, x, dw, B, T, C, T_out, k, stride, dilation, pad, dy_lens, stream);
+}
+int w2l_depthwise_wgrad_f32(const float* dy, const float* x, float* dw, int32_t B, int32_t T, int32_t C, int32_t T_out, int32_t k,
+                            int32_t stride, int32_t dilation, int32_t pad, const int32_t* dy_lens, void* stream) {
+  return dw_wgrad_impl(1, dy, x, dw, B, T, C, T_out, k, stride, dilation, pad, dy_lens, stream);
 }
 
 }  // extern "C"

@@ -252,37 +252,44 @@ def conv1d_wgrad_t(dy, x, desc, dw):
 
 
 # --------------------------------------------------------------------------------------------- depthwise
+def _dw(name, t):
+    """the depthwise entry point for the storage type of tensor ``t`` (bf16, or fp32 in the fp32-faithful mode)"""
+    return getattr(_lib.load(), name + ("_f32" if t.dtype == torch.float32 else ""))
+
+
 def depthwise_fwd(x, w, T_out, k, stride, dilation, pad, out_lens=None):
-    """x [B,T,C] bf16, w fp32 [k,C] -> y [B,T_out,C] bf16"""
+    """x [B,T,C] bf16 (fp32), w fp32 [k,C] -> y [B,T_out,C] of x's type"""
     _need_cuda(x, w)
     B, T, C = x.shape
-    y = torch.empty((B, T_out, C), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, T_out, C), dtype=x.dtype, device=x.device)
     with _on(x.device):
-        _lib.check(_lib.load().w2l_depthwise_fwd(_ptr(x), _ptr(w), _ptr(y), B, T, C, T_out, k, stride, dilation, pad, _ptr(out_lens), _stream()),
+        _lib.check(_dw("w2l_depthwise_fwd", x)(_ptr(x), _ptr(w), _ptr(y), B, T, C, T_out, k, stride, dilation, pad, _ptr(out_lens), _stream()),
                    "depthwise_fwd")
     return y
 
 
 def depthwise_dgrad(dy, w, T, k, dilation, pad, dy_lens=None, stride=1):
     B, T_out, C = dy.shape
-    dx = torch.empty((B, T, C), dtype=torch.bfloat16, device=dy.device)
+    dx = torch.empty((B, T, C), dtype=dy.dtype, device=dy.device)
     with _on(dy.device):
         if stride == 1:
-            _lib.check(_lib.load().w2l_depthwise_dgrad(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens),
-                                                       _stream()), "depthwise_dgrad")
+            _lib.check(_dw("w2l_depthwise_dgrad", dy)(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, dilation, pad, _ptr(dy_lens),
+                                                      _stream()), "depthwise_dgrad")
         else:
-            _lib.check(_lib.load().w2l_depthwise_dgrad_strided(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, stride, dilation, pad,
-                                                               _ptr(dy_lens), _stream()), "depthwise_dgrad_strided")
+            _lib.check(_dw("w2l_depthwise_dgrad_strided", dy)(_ptr(dy), _ptr(w), _ptr(dx), B, T, C, T_out, k, stride, dilation, pad,
+                                                              _ptr(dy_lens), _stream()), "depthwise_dgrad_strided")
     return dx
 
 
 def depthwise_wgrad(dy, x, k, stride, dilation, pad, dy_lens=None):
     B, T_out, C = dy.shape
     T = x.shape[1]
+    if dy.dtype != x.dtype:
+        raise RuntimeError("depthwise_wgrad: dy %s and x %s must have the same storage type" % (dy.dtype, x.dtype))
     dw = torch.zeros((k, C), dtype=torch.float32, device=dy.device)
     with _on(dy.device):
-        _lib.check(_lib.load().w2l_depthwise_wgrad(_ptr(dy), _ptr(x), _ptr(dw), B, T, C, T_out, k, stride, dilation, pad, _ptr(dy_lens),
-                                                   _stream()), "depthwise_wgrad")
+        _lib.check(_dw("w2l_depthwise_wgrad", dy)(_ptr(dy), _ptr(x), _ptr(dw), B, T, C, T_out, k, stride, dilation, pad, _ptr(dy_lens),
+                                                  _stream()), "depthwise_wgrad")
     return dw
 
 

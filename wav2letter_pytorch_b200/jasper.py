@@ -275,8 +275,8 @@ class Jasper(ConvCTCASR):
                 raise ValueError("Jasper: channel counts must be multiples of 8 and >= 64 for the tensor-core path (got %d -> %d)"
                                  % (m.in_channels, m.out_channels))
         # precision: "bf16" (default) or "tf32" -- the fp32-faithful mode (fp32 activations / weights / gradients in memory, tf32
-        # multiplies, fp32 accumulation; see Wav2Letter).  Dense blocks only: the depthwise kernels of separable blocks and the
-        # time-major unfold of strided inner blocks exist for bf16 activations.
+        # multiplies in the GEMMs, plain fp32 FMAs in the depthwise convs, fp32 accumulation; see Wav2Letter).  Not for strided inner
+        # blocks: their time-major unfold exists for bf16 activations.
         self.precision = str(getattr(cfg, "precision", "bf16") or "bf16").lower()
         if self.precision in ("fp32", "float32"):
             self.precision = "tf32"
@@ -284,9 +284,10 @@ class Jasper(ConvCTCASR):
             raise ValueError("Jasper: precision must be 'bf16' or 'tf32', got %r" % (self.precision,))
         if self.precision == "tf32":
             convs = [m for m in self.modules() if isinstance(m, ConvParams)]
-            if any(isinstance(m, DepthwiseParams) for m in self.modules()) or any(c.unfold for c in convs[1:]):
-                raise NotImplementedError("Jasper: precision='tf32' is implemented for dense, unstrided blocks (separable: false)")
-            for c in convs:
+            if any(c.unfold for c in convs[1:]) or any(m.stride[0] != 1 for m in self.modules() if isinstance(m, DepthwiseParams)
+                                                       and m is not getattr(self.jasper_encoder[0].mconv[0], "conv", None)):
+                raise NotImplementedError("Jasper: precision='tf32' is not implemented for strided blocks beyond the first")
+            for c in convs + [m for m in self.modules() if isinstance(m, DepthwiseParams)]:
                 c.f32 = True
 
     def _build_encoder(self, cfg):

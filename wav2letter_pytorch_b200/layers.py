@@ -291,6 +291,11 @@ class DepthwiseParams(nn.Module):
         nn.init.kaiming_uniform_(w, a=math.sqrt(5))                     # nn.Conv1d's default, same RNG consumption
         self.weight = nn.Parameter(w.permute(2, 1, 0).contiguous().permute(2, 1, 0))
         self.bias = None
+        self.f32 = False                      # fp32-faithful mode (set by the owning model): fp32 activations in and out
+
+    @property
+    def act_dtype(self):
+        return torch.float32 if self.f32 else torch.bfloat16
 
     def storage(self):
         v = self.weight.detach().permute(2, 1, 0)
