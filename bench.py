@@ -17,6 +17,7 @@ import argparse
 import ctypes
 import inspect
 import json
+import math
 import os
 import subprocess
 import sys
@@ -839,7 +840,35 @@ def run_gpu_arm(args):
         t_host = (time.perf_counter() - t_host) * 1e3 / (max(args.steps, 10) + max(args.warmup, 3))
         extra = {"workload": "Wav2Letter mid_layers=1 (literal yaml default) train step, B=%d/GPU x %d s" % (BATCH, UTT_SEC),
                  "ms_per_step": ms1, "value": world * BATCH * UTT_SEC / (ms1 / 1e3), "unit": "audio-s/s",
-                 "host_wall_ms_per_step_incl_warmup": t_host}
+                 "host_wall_ms_per_step_incl_warmup": t_host, "path": "eager (one Python launch per kernel)"}
+        if world == 1 and not args.profile:
+            # the same step replayed from a CUDA graph (graph_step.GraphedTrainStep): this configuration is launch-bound when eager
+            try:
+                from wav2letter_pytorch_b200.graph_step import GraphedTrainStep
+                full = resident + (None, texts)
+                gstep = GraphedTrainStep(m1, o1, full, warmup=2)
+                n_g = 5 * max(args.steps, 10)
+                for it in range(5):
+                    gstep(full, it)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for it in range(n_g):
+                    last = gstep(full, it)
+                e1.record()
+                barrier()
+                ms_g = e0.elapsed_time(e1) / n_g
+                lv = float(last)
+                assert math.isfinite(lv), "graphed default-config step produced a non-finite loss"
+                gstep.close()
+                extra.update({"eager_ms_per_step": ms1, "ms_per_step": ms_g, "value": world * BATCH * UTT_SEC / (ms_g / 1e3), "steps": n_g,
+                              "loss_last_step": lv,
+                              "path": "GraphedTrainStep: the whole step (fwd + CTC + decode + CER/WER + bwd + NovoGrad) replayed from one CUDA "
+                                      "graph; per step the host copies the batch into the static operands, encodes the transcripts and "
+                                      "launches the graph (all inside the timed region)"})
+                del gstep
+            except Exception as e:  # noqa: BLE001  (a secondary table must never take the headline line down)
+                extra["graphed_error"] = repr(e)[:300]
         del m1, o1, r1
 
     # ---- secondary legs the driver's single line must carry (N=1 only: the scaling runs stay lean): BASELINE config 3 (Jasper 10x5),

@@ -293,6 +293,11 @@ int w2l_lens_chain(const void* lens_in, int32_t lens_is_int64, int32_t B, const 
  * dropout (nn.Dropout, wav2letter.py:44 / jasper.py:372-376): keep-bits from a counter-based splitmix64 stream
  * (seed, element index / 8), 16 bits per element, p = drop_p (0 disables); drop_mask (nullable, B*T*C/8 bytes) receives
  * the keep-bits so that the backward passes read them back instead of re-deriving them. */
+/* Optional device-resident dropout epoch (one uint64, caller-owned; NULL unregisters; per process like the GEMM scratch).  While
+ * registered, every launch that draws keep-bits uses seed + *epoch * 0xA0761D6478BD642F instead of its by-value seed: a captured
+ * CUDA graph replays its by-value arguments unchanged, so a step captured once (graph_step.py) bumps the epoch inside the graph
+ * to draw a fresh mask per replay, the way the reference's nn.Dropout draws one per call (wav2letter.py:44). */
+int w2l_set_dropout_epoch(const uint64_t* epoch);
 int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                    const float* res_shift, void* y, int32_t B, int32_t T, int32_t C, int32_t pad_left,
                    int32_t pad_right, int32_t act, float drop_p, uint64_t seed, const int32_t* lens, void* drop_mask,

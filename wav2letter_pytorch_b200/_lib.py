@@ -126,6 +126,7 @@ SIGNATURES = {
                              c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "w2l_conv1d_fwd": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_set_gemm_scratch": (c_i32, [c_ptr, c_size]),
+    "w2l_set_dropout_epoch": (c_i32, [c_ptr]),
     "w2l_conv1d_fwd_tail_parts": (c_i32, [ctypes.POINTER(ConvDesc)]),
     "w2l_conv1d_dgrad": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),
     "w2l_conv1d_dgrad_wt": (c_i32, [c_ptr, c_ptr, c_ptr, ctypes.POINTER(ConvDesc), c_ptr]),

@@ -17,7 +17,9 @@ try:  # pragma: no cover - not installed in the build image
 except Exception:  # noqa: BLE001
     class _Base(nn.Module):
         def log_dict(self, logs, *args, **kwargs):
-            self.logged = dict(logs)
+            # detached, as Lightning's logger stores them: a kept loss would keep the step's autograd graph (and its AccumulateGrad
+            # nodes, bound to the stream of the step that made them) alive into the next step
+            self.logged = {k: v.detach() if torch.is_tensor(v) else v for k, v in logs.items()}
 
         def optimizers(self):
             return self._optimizer

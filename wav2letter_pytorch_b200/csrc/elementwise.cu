@@ -7,6 +7,9 @@
 
 namespace w2l {
 
+// device-resident dropout epoch registered by the host (w2l_set_dropout_epoch); per process, like the GEMM scratch
+static const uint64_t* g_dropout_epoch = nullptr;
+
 // ---------------------------------------------------------------- dropout keep-bits
 // 32 keep-bits at a time -- the 4 consecutive rows x 8 channels a thread of the BatchNorm passes stages together: bit 8u + i belongs to
 // row 4*rg + u, channel 8*cv + i -- each 1 with probability keep_q / 2^kDropBits.  Bitwise Bernoulli synthesis: walking the binary digits
@@ -36,6 +39,13 @@ __device__ __forceinline__ uint32_t dropout_mask32(uint64_t seed, uint32_t rg, u
     m = (m & w) | (digit & (m ^ w));                               // digit ? (m | w) : (m & w): one LOP3
   }
   return m;
+}
+// The seed a launch draws its keep-bits from: the by-value seed of the call, advanced by the device-resident epoch when one is
+// registered -- a captured CUDA graph replays the same by-value arguments, the epoch (bumped inside the graph) makes every replay
+// draw a fresh mask while forward and backward of one step still agree.
+template <typename Args>
+__device__ __forceinline__ uint64_t drop_seed(const Args& a) {
+  return a.epoch ? a.seed + *a.epoch * 0xA0761D6478BD642Full : a.seed;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
@@ -325,6 +335,7 @@ struct BnFwdArgs {
   uint32_t keep_q;             // dropout: keep probability in units of 2^-kDropBits (0: no dropout)
   float inv_keep;              // 2^kDropBits / keep_q
   uint64_t seed;
+  const uint64_t* epoch;       // device-resident step counter folded into the seed (w2l_set_dropout_epoch), or nullptr
   const int32_t* lens;
   uint8_t* drop_mask;          // [B*T*C/8] keep-bits: written by the forward pass, read back by the backward passes
   float* zero_ptr;             // a small buffer this launch clears for a LATER kernel (the layer's backward reduction sums)
@@ -352,6 +363,7 @@ struct BnBwdArgs {
   uint32_t keep_q;
   float inv_keep;
   uint64_t seed;
+  const uint64_t* epoch;
   const int32_t* lens;
   const uint8_t* drop_mask;
   float* zero_ptr;             // apply pass: a small buffer cleared for a LATER kernel (the layer's forward statistics)
@@ -461,9 +473,10 @@ __global__ void __launch_bounds__(kBnThreads, kBnFwdCtasPerSm) bn_act_pad_kernel
   const int rows = a.B * a.T, Tp = a.pl + a.T + a.pr;
   const int r_begin = blockIdx.y * a.rows_per_block, r_end = min(rows, r_begin + a.rows_per_block);   // r_begin % kRowGroup == 0
   constexpr int kBatch = (HAS_RES || sizeof(TA) == 4) ? 2 : kRowGroup;    // rows whose loads are in flight together (two streams with a residual)
+  const uint64_t seed = DROP ? drop_seed(a) : 0;
   for (int r0 = r_begin + threadIdx.y * kRowGroup; r0 < r_end; r0 += ny * kRowGroup) {
     uint32_t keep = 0xFFFFFFFFu;
-    if (DROP) keep = dropout_mask32(a.seed, (uint32_t)(r0 / kRowGroup), (uint32_t)cv, a.keep_q);
+    if (DROP) keep = dropout_mask32(seed, (uint32_t)(r0 / kRowGroup), (uint32_t)cv, a.keep_q);
     int b = r0 / a.T, t = r0 - b * a.T;
 #pragma unroll
     for (int h = 0; h < kRowGroup; h += kBatch) {
@@ -546,7 +559,7 @@ __device__ __forceinline__ void g_from_row(const BnBwdArgs& a, int r, int b, int
   in.d.unpack(g);
   uint32_t bits = in.bits;
   if (DROP && !a.drop_mask)                                        // no stored keep-bits: regenerate them (kernel-uniform branch)
-    bits = (dropout_mask32(a.seed, (uint32_t)(r / kRowGroup), (uint32_t)(c >> 3), a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
+    bits = (dropout_mask32(drop_seed(a), (uint32_t)(r / kRowGroup), (uint32_t)(c >> 3), a.keep_q) >> (8 * (r % kRowGroup))) & 0xFFu;
   const int dr = a.T - 1 - t;
   if ((t >= 1 && t <= a.pl) || (dr >= 1 && dr <= a.pr)) {          // rows with a mirror image in the reflect halo (<8 % of the rows)
     const TA* base = reinterpret_cast<const TA*>(a.dyp) + (int64_t)b * (a.pl + a.T + a.pr) * a.C + c;
@@ -977,6 +990,11 @@ static int rows_per_block_for(int64_t rows, int col_blocks) {
 
 extern "C" {
 
+int w2l_set_dropout_epoch(const uint64_t* epoch) {
+  w2l::g_dropout_epoch = epoch;
+  return W2L_OK;
+}
+
 static int im2col_ncw_impl(int f32, const float* x, void* out, int32_t B, int32_t F, int32_t T, int32_t rows, int32_t k, int32_t stride,
                            int32_t dilation, int32_t pad_left, int32_t pad_mode, const int32_t* lens, void* stream) {
   using namespace w2l;
@@ -1107,6 +1125,7 @@ int w2l_bn_act_pad(const void* z, const float* scale, const float* shift, const 
   a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
   drop_quant(drop_p, &a.keep_q, &a.inv_keep);
   a.seed = seed;
+  a.epoch = g_dropout_epoch;
   a.lens = lens;
   a.drop_mask = (uint8_t*)drop_mask;
   return launch_bn_fwd(a, act, res, stream);
@@ -1144,6 +1163,7 @@ int w2l_bn_finalize_act_pad(const void* z, const float* stats, int64_t stat_rows
   a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
   drop_quant(drop_p, &a.keep_q, &a.inv_keep);
   a.seed = seed;
+  a.epoch = g_dropout_epoch;
   a.lens = lens;
   a.drop_mask = (uint8_t*)drop_mask;
   a.zero_ptr = zero_ptr;
@@ -1173,6 +1193,7 @@ static int fill_bwd_args(w2l::BnBwdArgs& a, const char* who, const void* dyp, co
   a.B = B, a.T = T, a.C = C, a.pl = pad_left, a.pr = pad_right;
   drop_quant(drop_p, &a.keep_q, &a.inv_keep);
   a.seed = seed;
+  a.epoch = g_dropout_epoch;
   a.lens = lens;
   a.drop_mask = (const uint8_t*)drop_mask;
   return W2L_OK;

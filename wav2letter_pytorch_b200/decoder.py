@@ -98,9 +98,10 @@ class GreedyDecoder(Decoder):
         return tokens, offsets, counts
 
     # ---- device-side scoring (no host sync): CER / WER / length ratio as a CUDA tensor
-    def _encode_refs(self, texts):
+    def _encode_refs(self, texts, into=None):
         """texts -> (ids [N,S] int32 pinned, lens [N] int32 pinned, cer_den, wer_den, len_den) or None when the device path
-        does not apply (multi-character labels, exotic whitespace, references longer than 1023)."""
+        does not apply (multi-character labels, exotic whitespace, references longer than 1023).  ``into`` = (ids, lens): caller-owned
+        pinned tensors to encode into instead of the rotating internal ones (graph_step.py keeps one fixed pair per captured step)."""
         C = len(self.labels)
         if getattr(self, "_lut", None) is None:
             if any(len(l) != 1 for l in self.labels) or " " not in self.labels:
@@ -133,7 +134,11 @@ class GreedyDecoder(Decoder):
         is_sp = cp == 32
         words = int(np.count_nonzero(~is_sp[1:] & is_sp[:-1]) + (0 if cp.size == 0 or is_sp[0] else 1))
         slot = None
-        for s in self._pins:                                    # rotate pinned staging buffers (CPU may run ahead of the GPU)
+        if into is not None:
+            if into[0].shape[0] < n or into[0].shape[1] < smax:
+                return None
+            slot = [into[0], into[1], None]
+        for s in self._pins if slot is None else ():            # rotate pinned staging buffers (CPU may run ahead of the GPU)
             if s[0].shape[0] >= n and s[0].shape[1] >= smax and (s[2] is None or s[2].query()):
                 slot = s
                 break
@@ -164,20 +169,28 @@ class GreedyDecoder(Decoder):
         slot, smax, cer_den, wer_den, len_den = enc
         if cer_den == 0 or wer_den == 0 or len_den == 0:
             raise ZeroDivisionError("division by zero")            # what the reference's host arithmetic raises
-        tokens, _offsets, counts = self.decode_tokens(probs, sizes)
-        dev = tokens.device
-        N, T = tokens.shape
-        S = slot[0].shape[1]
+        dev = probs.device if torch.is_tensor(probs) and probs.is_cuda else torch.device("cuda", torch.cuda.current_device())
         ref_ids = slot[0].to(dev, non_blocking=True)
         ref_lens = slot[1].to(dev, non_blocking=True)
         slot[2] = torch.cuda.Event()
         slot[2].record()
+        return self.score_device(probs, sizes, ref_ids, ref_lens, (cer_den, wer_den, len_den))
+
+    def score_device(self, probs, sizes, ref_ids, ref_lens, dens=(1.0, 1.0, 1.0)):
+        """Device part of ``error_ratios_device`` over references that are already encoded and resident (ids [N,S] / lens [N] int32
+        CUDA): greedy decode + edit distances, returns fp32 [3] = (character errors, word errors, hypothesis characters) each divided
+        by its entry of ``dens``.  With the default denominators these are the raw sums, which is what a captured step needs -- the
+        denominators change with every batch's texts and would be frozen into the graph as by-value arguments."""
+        tokens, _offsets, counts = self.decode_tokens(probs, sizes)
+        dev = tokens.device
+        N, T = tokens.shape
+        S = ref_ids.shape[1]
         lib = _lib.load()
         ws = torch.empty((lib.w2l_string_metrics_workspace_bytes(N, T, S) + 7) // 8, dtype=torch.int64, device=dev)
         ratios = torch.empty(3, dtype=torch.float32, device=dev)
         with F._on(dev):
             _lib.check(lib.w2l_string_metrics(F._ptr(tokens), F._ptr(counts), N, T, self.space_index, F._ptr(ref_ids), F._ptr(ref_lens), S,
-                                              float(cer_den), float(wer_den), float(len_den), F._ptr(ratios), F._ptr(ws), ws.numel() * 8,
+                                              float(dens[0]), float(dens[1]), float(dens[2]), F._ptr(ratios), F._ptr(ws), ws.numel() * 8,
                                               F._stream()), "string_metrics")
         return ratios
 

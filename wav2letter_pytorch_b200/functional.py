@@ -160,6 +160,16 @@ def ensure_gemm_scratch(device):
     _gemm_scratch[device] = buf
 
 
+def set_dropout_epoch(epoch):
+    """Registers (None: unregisters) a device-resident int64 step counter that every dropout launch folds into its seed
+    (w2l_set_dropout_epoch): what lets a captured step draw a fresh mask on every replay.  The caller keeps the tensor alive."""
+    if epoch is not None:
+        _need_cuda(epoch)
+        if epoch.dtype != torch.int64 or epoch.numel() != 1:
+            raise ValueError("set_dropout_epoch: one int64 CUDA element expected")
+    _lib.check(_lib.load().w2l_set_dropout_epoch(_ptr(epoch)), "set_dropout_epoch")
+
+
 def conv1d_fwd(x, w, desc, y, bias=None, scale=None, shift=None, bn_stats=None):
     """``bn_stats`` (fp32 [2*Cout], zero-filled): receives the per-channel sum / sum of squares of the stored output."""
     _need_cuda(x, w, y)

@@ -130,6 +130,13 @@ class Novograd(Optimizer):
         self._plans[key] = plan
         return plan
 
+    def prepare_capture(self):
+        """Call between the eager warm-up steps and the capture of ``step()`` into a CUDA graph: gives every fused-step plan a pinned
+        pointer table of its own for the capture (see ``step``).  One call per capture."""
+        for plan in self._plans.values():
+            n = plan["dev"].shape[1]
+            plan["capture_host"] = torch.empty((5, n), dtype=torch.int64).pin_memory()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -153,14 +160,27 @@ class Novograd(Optimizer):
                 grads.append(g)
             plan = self._plan(gi, params)
             dev = plan["dev"]
-            slot = plan["hosts"][plan["turn"] % len(plan["hosts"])]
-            plan["turn"] += 1
-            if slot[1] is not None:
-                slot[1].synchronize()
-            slot[0][1] = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64)
-            dev.copy_(slot[0], non_blocking=True)
-            slot[1] = torch.cuda.Event()
-            slot[1].record()
+            if torch.cuda.is_current_stream_capturing():
+                # the step is being captured into a CUDA graph (graph_step.py): the upload becomes a memcpy node that re-reads ITS pinned
+                # table on every replay, so the table is one that no later eager step rewrites (allocated by prepare_capture -- pinned
+                # allocations are not allowed while capturing); the gradients it points at live in the graph's private pool
+                cap = plan.get("capture_host")
+                if cap is None:
+                    raise RuntimeError("Novograd: call prepare_capture() after the warm-up steps and before capturing step() in a CUDA graph")
+                plan["capture_host"] = None               # owned by this capture from here on
+                plan.setdefault("captured_hosts", []).append(cap)
+                cap.copy_(plan["hosts"][0][0])
+                cap[1] = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64)
+                dev.copy_(cap, non_blocking=True)
+            else:
+                slot = plan["hosts"][plan["turn"] % len(plan["hosts"])]
+                plan["turn"] += 1
+                if slot[1] is not None:
+                    slot[1].synchronize()
+                slot[0][1] = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64)
+                dev.copy_(slot[0], non_blocking=True)
+                slot[1] = torch.cuda.Event()
+                slot[1].record()
             b1, b2 = group["betas"]
             P = F._ptr
             with F._on(dev.device):
