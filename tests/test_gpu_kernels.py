@@ -588,21 +588,23 @@ def test_log_softmax_and_colsum(F):
     assert torch.equal(F.cast_bf16(w.cuda()).cpu(), w.to(torch.bfloat16))
 
 
-def test_string_metrics_device(F):
-    """device-side CER/WER/len-ratio vs the reference's host arithmetic (base_asr_models.py:58-69)."""
+@pytest.mark.parametrize("T", [120, 700])
+def test_string_metrics_device(F, T):
+    """device-side CER/WER/len-ratio vs the reference's host arithmetic (base_asr_models.py:58-69); T=700: transcripts longer than
+    the 128-symbol chunks of the split kernel (words that straddle a chunk boundary, several chunks of running offsets)."""
     import random
     from wav2letter_pytorch_b200.decoder import GreedyDecoder
     labels = O.ENGLISH_LOWERCASE
     dec = GreedyDecoder(labels)
     rnd = random.Random(5)
-    N, T, C = 9, 120, 29
+    N, C = 9, 29
     g = torch.Generator().manual_seed(2)
     probs = torch.softmax(torch.randn(N, T, C, generator=g) * 3, -1)
     probs[:, :, 28] *= 6                                        # plenty of spaces -> many words
     probs[3] = 0
     probs[3, :, 0] = 1                                          # an all-blank (empty) hypothesis
     sizes = torch.tensor([T, T, 60, T, 1, T, 100, T, 7], dtype=torch.int32)
-    texts = ["".join(rnd.choice(labels[1:]) for _ in range(rnd.randint(1, 90))) for _ in range(N)]
+    texts = ["".join(rnd.choice(labels[1:]) for _ in range(rnd.randint(1, 90 if T == 120 else 600))) for _ in range(N)]
     texts[1] = "  " + texts[1] + "  a "                        # leading / trailing / double spaces
     texts[5] = "word"
     hyps = dec.decode(probs.cuda(), sizes.cuda())

@@ -13,34 +13,62 @@ __device__ __forceinline__ unsigned long long hash_step(unsigned long long h, in
 }
 constexpr unsigned long long kHashSeed = 1469598103934665603ull;
 
-// one thread per utterance: tokens[n, :counts[n]] -> chars (ids != space) and word hashes (runs of ids != space)
-__global__ void metrics_split_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ counts, int N, int T, int space,
-                                     int32_t* __restrict__ chars, int32_t* __restrict__ n_chars, long long* __restrict__ words,
-                                     int32_t* __restrict__ n_words) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// One CTA per utterance: tokens[n, :counts[n]] -> chars (ids != space, order kept) and word hashes (one per run of ids != space,
+// order kept).  Stream compaction over 128-token chunks: warp ballots give every symbol its rank among the chunk's characters
+// and every word start its rank among the word starts; the thread that owns a word start walks its word (words are short) and
+// writes the hash.  (Round 1 ran one THREAD per utterance: a 750-step dependent loop, 129 us at N=64 x T=750.)
+constexpr int kSplitThreads = 128;
+__global__ void __launch_bounds__(kSplitThreads)
+metrics_split_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ counts, int N, int T, int space,
+                     int32_t* __restrict__ chars, int32_t* __restrict__ n_chars, long long* __restrict__ words,
+                     int32_t* __restrict__ n_words) {
+  __shared__ int s_c[kSplitThreads / 32], s_w[kSplitThreads / 32];
+  const int n = blockIdx.x;
   if (n >= N) return;
   const int32_t* tk = tokens + (int64_t)n * T;
   int32_t* ch = chars + (int64_t)n * T;
   long long* wd = words + (int64_t)n * T;
   const int cnt = max(0, min(T, counts[n]));
-  int nc = 0, nw = 0;
-  bool in_word = false;
-  unsigned long long h = kHashSeed;
-  for (int i = 0; i < cnt; ++i) {
-    const int s = tk[i];
-    if (s == space) {
-      if (in_word) wd[nw++] = (long long)h;
-      in_word = false;
-      h = kHashSeed;
-    } else {
-      ch[nc++] = s;
-      h = hash_step(h, s);
-      in_word = true;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned below = (1u << lane) - 1u;
+  int nc = 0, nw = 0;                                    // running totals, the same in every thread
+  for (int base = 0; base < cnt; base += kSplitThreads) {
+    const int i = base + (int)threadIdx.x;
+    const int s = i < cnt ? tk[i] : space;
+    const bool is_char = i < cnt && s != space;
+    const bool is_start = is_char && (i == 0 || tk[i - 1] == space);
+    const unsigned mc = __ballot_sync(0xffffffffu, is_char), mw = __ballot_sync(0xffffffffu, is_start);
+    if (lane == 0) {
+      s_c[warp] = __popc(mc);
+      s_w[warp] = __popc(mw);
     }
+    __syncthreads();
+    int oc = nc + __popc(mc & below), ow = nw + __popc(mw & below);
+#pragma unroll
+    for (int w = 0; w < kSplitThreads / 32; ++w) {
+      if (w < warp) {
+        oc += s_c[w];
+        ow += s_w[w];
+      }
+      nc += s_c[w];
+      nw += s_w[w];
+    }
+    if (is_char) ch[oc] = s;
+    if (is_start) {
+      unsigned long long h = kHashSeed;
+      for (int k = i; k < cnt; ++k) {
+        const int v = tk[k];
+        if (v == space) break;
+        h = hash_step(h, v);
+      }
+      wd[ow] = (long long)h;
+    }
+    __syncthreads();                                     // s_c / s_w are rewritten by the next chunk
   }
-  if (in_word) wd[nw++] = (long long)h;
-  n_chars[n] = nc;
-  n_words[n] = nw;
+  if (threadIdx.x == 0) {
+    n_chars[n] = nc;
+    n_words[n] = nw;
+  }
 }
 
 // Wavefront Levenshtein: one CTA per pair; thread j owns column j+1 of the DP table (reference symbol j); anti-diagonals are
@@ -159,11 +187,10 @@ int w2l_string_metrics(const int32_t* tokens, const int32_t* counts, int64_t N, 
   int32_t* r_nw = r_nc + N;
   int32_t* cer_d = r_nw + N;
   int32_t* wer_d = cer_d + N;
-  const unsigned blocks = (unsigned)((N + 63) / 64);
-  metrics_split_kernel<<<blocks, 64, 0, st>>>(tokens, counts, (int)N, (int)T, space_index, h_chars, h_nc, h_words, h_nw);
+  metrics_split_kernel<<<(unsigned)N, kSplitThreads, 0, st>>>(tokens, counts, (int)N, (int)T, space_index, h_chars, h_nc, h_words, h_nw);
   int rc = after_launch("metrics_split_kernel<hyp>");
   if (rc) return rc;
-  metrics_split_kernel<<<blocks, 64, 0, st>>>(ref_ids, ref_lens, (int)N, (int)ref_stride, space_index, r_chars, r_nc, r_words, r_nw);
+  metrics_split_kernel<<<(unsigned)N, kSplitThreads, 0, st>>>(ref_ids, ref_lens, (int)N, (int)ref_stride, space_index, r_chars, r_nc, r_words, r_nw);
   rc = after_launch("metrics_split_kernel<ref>");
   if (rc) return rc;
   const int threads = (int)((ref_stride + 31) / 32 * 32);

@@ -41,6 +41,14 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def capturing():
+    """True while the current stream is being captured into a CUDA graph (graph_step.py).  False in a process without a CUDA runtime."""
+    try:
+        return torch.cuda.is_current_stream_capturing()
+    except Exception:  # noqa: BLE001
+        return False
+
+
 class _NoSwitch:
     def __enter__(self):
         return None

@@ -51,6 +51,7 @@ class GraphedTrainStep:
             return buf[:4].view(torch.float32)[:3], buf[4:4 + n], buf[4 + n4:].view(n, s_ref)
         self._den_h, self._lens_h, self._ids_h = views(self._ref_host)
         self._den_d, self._lens_d, self._ids_d = views(self._ref_dev)
+        self._metric_stream = torch.cuda.Stream(device=dev)
         self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         F.set_dropout_epoch(self._epoch)
         self._metrics_on = self._load(batch)             # False: this decoder / these texts have no device scoring path
@@ -63,6 +64,7 @@ class GraphedTrainStep:
                 loss, _ = self._body()
                 loss.backward()
                 optimizer.step()
+                self._join()
                 del loss                                 # no autograd graph of an eager step may outlive it (see _capture)
         cur.wait_stream(side)
         self.graph, self._key = None, None
@@ -92,11 +94,24 @@ class GraphedTrainStep:
         x, il, tg, tl = self._static
         m = self.model
         scores, out_lens = m.forward(x, il)
+        if not self._metrics_on:
+            return m.criterion(scores.transpose(0, 1), tg, out_lens, tl), None
+        # decode + CER/WER feed only the logger: their own branch, forked behind the forward pass (as ConvCTCASR._step does).  In the
+        # graph nothing waits for it before the very end of the step, so it runs beside the CTC kernels AND the backward pass -- at
+        # the default yaml's size the branch is a quarter of the step's kernel time.  `scores` / `out_lens` are kept referenced until
+        # the join: memory freed on the compute stream could otherwise be handed to a backward kernel while the branch still reads it.
+        main = torch.cuda.current_stream(self.device)
+        self._metric_stream.wait_stream(main)
         loss = m.criterion(scores.transpose(0, 1), tg, out_lens, tl)
-        ratios = None
-        if self._metrics_on:
+        with torch.cuda.stream(self._metric_stream):
             ratios = m.ctc_decoder.score_device(scores, out_lens, self._ids_d, self._lens_d) / self._den_d
+        self._branch_keep = (scores, out_lens)
         return loss, ratios
+
+    def _join(self):
+        if self._metrics_on:
+            torch.cuda.current_stream(self.device).wait_stream(self._metric_stream)
+        self._branch_keep = None
 
     def _hyper(self):
         return tuple(tuple(sorted((k, repr(v)) for k, v in g.items() if k != "params")) for g in self.optimizer.param_groups)
@@ -117,6 +132,7 @@ class GraphedTrainStep:
             loss, ratios = self._body()
             loss.backward()
             self.optimizer.step()
+            self._join()
         self.graph, self._loss, self._ratios, self._key = g, loss.detach(), ratios, self._hyper()
         # Jasper's NaN assertion (jasper.py:474): the captured forward left its device flag here instead of reading it
         self._nan_flag = self.model.__dict__.pop("_nan_flag_graph", None)

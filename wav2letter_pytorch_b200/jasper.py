@@ -350,7 +350,7 @@ class Jasper(ConvCTCASR):
     def _assert_no_nan(self, flag, mode):
         if mode == "off":
             return
-        if torch.cuda.is_current_stream_capturing():
+        if F.capturing():
             # inside a CUDA graph capture (graph_step.py) nothing can be read back: the flag is a static operand of the graph, and
             # GraphedTrainStep copies it out after every replay and raises like "deferred" does
             self._nan_flag_graph = flag

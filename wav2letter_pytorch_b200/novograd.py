@@ -160,7 +160,7 @@ class Novograd(Optimizer):
                 grads.append(g)
             plan = self._plan(gi, params)
             dev = plan["dev"]
-            if torch.cuda.is_current_stream_capturing():
+            if F.capturing():
                 # the step is being captured into a CUDA graph (graph_step.py): the upload becomes a memcpy node that re-reads ITS pinned
                 # table on every replay, so the table is one that no later eager step rewrites (allocated by prepare_capture -- pinned
                 # allocations are not allowed while capturing); the gradients it points at live in the graph's private pool
