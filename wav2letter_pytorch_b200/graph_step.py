@@ -23,6 +23,21 @@ import torch
 from . import functional as F
 
 
+_epochs = {}
+
+
+def _dropout_epoch(dev):
+    """The device-resident step counter the library folds into every dropout seed, registered once per process and never freed
+    (the library keeps a raw pointer to it; one device per process, like the GEMM scratch): captured steps bump it inside their graph."""
+    t = _epochs.get(dev)
+    if t is None:
+        if _epochs:
+            raise RuntimeError("wav2letter_pytorch_b200 runs one process per GPU: the dropout epoch already lives on %s" % next(iter(_epochs)))
+        t = _epochs[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
+        F.set_dropout_epoch(t)
+    return t
+
+
 class GraphedTrainStep:
     def __init__(self, model, optimizer, batch, warmup=2, max_text_len=None):
         """``batch`` = (inputs [B,F,T] fp32, input_lengths [B], targets [B,S], target_lengths [B], paths, texts) -- the collator's
@@ -52,8 +67,7 @@ class GraphedTrainStep:
         self._den_h, self._lens_h, self._ids_h = views(self._ref_host)
         self._den_d, self._lens_d, self._ids_d = views(self._ref_dev)
         self._metric_stream = torch.cuda.Stream(device=dev)
-        self._epoch = torch.zeros(1, dtype=torch.int64, device=dev)
-        F.set_dropout_epoch(self._epoch)
+        self._epoch = _dropout_epoch(dev)
         self._metrics_on = self._load(batch)             # False: this decoder / these texts have no device scoring path
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)             # warm up off the default stream, as CUDA graph capture requires
@@ -178,8 +192,8 @@ class GraphedTrainStep:
             assert not bad  # is there any NAN in result?
 
     def close(self):
-        """Unregisters the dropout epoch (eager steps go back to their by-value seeds) and drops the graph."""
-        F.set_dropout_epoch(None)
+        """Raises a pending NaN assertion and drops the graph with its memory pool.  (The dropout epoch stays registered: eager steps
+        fold the -- then constant -- counter into their per-call seeds, which changes nothing about their statistics.)"""
         if self._nan_flag is not None:
             self.check_nan(block=True)
         self.graph = None
