@@ -619,6 +619,53 @@ def test_string_metrics_device(F, T):
         dec.error_ratios_device(probs.cuda(), sizes.cuda(), [" "] * N)
 
 
+@pytest.mark.parametrize("ref_lens", [(1, 7, 8, 9, 33, 255, 256), (257, 600, 1023, 1, 512, 40, 300)])
+def test_string_metrics_strip_boundaries(F, ref_lens):
+    """the warp-per-pair edit distance at the edges of its column strips (8 columns per lane up to 256 reference symbols, 32 above):
+    reference lengths 1 / 8 / 9 / 255 / 256 / 257 / 1023, hypotheses shorter, equal and longer, identical pairs, an empty hypothesis --
+    bit-exact sums against the reference's host arithmetic (decoder.py:49-68)"""
+    import random
+    from wav2letter_pytorch_b200.decoder import GreedyDecoder
+    labels = O.ENGLISH_LOWERCASE
+    dec = GreedyDecoder(labels)
+    rnd = random.Random(sum(ref_lens))
+    alpha = [l for l in labels[1:] if len(l) == 1]                # every single-character label but the blank (space included)
+
+    def text(n):
+        t = "".join(rnd.choice(alpha) for _ in range(n))
+        return t if t.strip() else "a" * n                       # at least one word: the reference divides by the word count
+    refs = [text(n) for n in ref_lens]
+    hyps = []
+    for i, r in enumerate(refs):
+        kind = i % 4
+        if kind == 0:
+            hyps.append(r)                                       # identical
+        elif kind == 1:
+            hyps.append("".join(ch for ch in r if rnd.random() > 0.3) + text(rnd.randint(0, 5)))
+        elif kind == 2:
+            hyps.append(text(max(1, len(r) // 2)))
+        else:
+            hyps.append(text(min(1000, len(r) + rnd.randint(1, 40))))
+    hyps[-1] = ""                                               # nothing decoded
+    # hypotheses as one-hot scores: every character followed by a blank frame (so repeats survive the collapse)
+    T = 2 * max(1, max(len(h) for h in hyps))
+    probs = torch.zeros(len(hyps), T, len(labels))
+    probs[:, :, 0] = 1.0
+    for i, h in enumerate(hyps):
+        for j, ch in enumerate(h):
+            probs[i, 2 * j, 0] = 0.0
+            probs[i, 2 * j, labels.index(ch)] = 1.0
+    sizes = torch.full((len(hyps),), T, dtype=torch.int32)
+    got_h = dec.decode(probs.cuda(), sizes.cuda())
+    assert got_h == hyps
+    ratios = dec.error_ratios_device(probs.cuda(), sizes.cuda(), refs)
+    assert ratios is not None
+    cer = sum(dec.cer(t, h) for t, h in zip(refs, hyps)) / sum(len(t.replace(" ", "")) for t in refs)
+    wer = sum(dec.wer(t, h) for t, h in zip(refs, hyps)) / sum(len(t.split()) for t in refs)
+    lr = sum(map(len, hyps)) / sum(map(len, refs))
+    np.testing.assert_allclose(ratios.cpu().numpy(), [cer, wer, lr], rtol=1e-6)
+
+
 @pytest.mark.parametrize("B,T,C,k,s,d", [(3, 97, 64, 33, 1, 1), (2, 201, 256, 13, 2, 1), (2, 60, 128, 7, 1, 2), (1, 40, 72, 1, 1, 1)])
 def test_depthwise_conv(F, B, T, C, k, s, d):
     """depthwise (groups=C) conv fwd / dgrad / wgrad vs torch fp32 on the same bf16-rounded operands, with the length masks"""

@@ -90,26 +90,12 @@ class ConvCTCASR(_Base):
     def _step(self, batch, prefix):
         inputs, input_lengths, targets, target_lengths, _paths, texts = batch
         scores, out_lens = self.forward(inputs, input_lengths)
-        from .layers import WgradStream
-        if not (scores.is_cuda and WgradStream.enabled):
-            # the criterion takes [T, N, C]; this is a strided view, the CTC kernel reads it in place
-            loss = self.criterion(scores.transpose(0, 1), targets, out_lens, target_lengths)
-            return loss, self.add_string_metrics(scores, out_lens, texts, prefix)
-        # decode + WER/CER feed only the logger: the side stream forks HERE, right behind the forward pass and before the CTC
-        # kernels are enqueued, so both run side by side (one CTA per utterance leaves most SMs idle); joined before the step returns
-        main, side = torch.cuda.current_stream(scores.device), WgradStream.side(scores.device)
-        side.wait_stream(main)
+        # the criterion takes [T, N, C]; this is a strided view, the CTC kernel reads it in place
         loss = self.criterion(scores.transpose(0, 1), targets, out_lens, target_lengths)
-        with torch.cuda.stream(side):
-            metrics = self.add_string_metrics(scores, out_lens, texts, prefix)
-        for t in (scores, out_lens):
-            if torch.is_tensor(t) and t.is_cuda:
-                t.record_stream(side)
-        for v in metrics.values():                    # allocated from the side stream's pool, read by the caller on main
-            if torch.is_tensor(v) and v.is_cuda:
-                v.record_stream(main)
-        main.wait_stream(side)
-        return loss, metrics
+        # decode + WER/CER feed only the logger.  They run inline, behind the CTC kernels: on a side stream BESIDE them (rounds 1-2) the
+        # barrier-heavy edit-distance CTAs shared SMs with the latency-bound lattice recursion and cost it 0.2 ms for the 0.13 ms they
+        # take (profiles/r2_graph_step.md, call 32).  graph_step.GraphedTrainStep forks them as a branch that overlaps the backward pass.
+        return loss, self.add_string_metrics(scores, out_lens, texts, prefix)
 
     def training_step(self, batch, batch_idx):
         loss, metrics = self._step(batch, "train")

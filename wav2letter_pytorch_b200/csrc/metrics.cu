@@ -71,54 +71,72 @@ metrics_split_kernel(const int32_t* __restrict__ tokens, const int32_t* __restri
   }
 }
 
-// Wavefront Levenshtein: one CTA per pair; thread j owns column j+1 of the DP table (reference symbol j); anti-diagonals are
-// swept with three rolling buffers in shared memory.  dist(a[0:m], b[0:n]); n <= blockDim.x.
-template <typename Sym>
-__global__ void edit_distance_kernel(const Sym* __restrict__ hyp, const int32_t* __restrict__ hyp_len, int64_t hyp_stride,
-                                     const Sym* __restrict__ ref, const int32_t* __restrict__ ref_len, int64_t ref_stride,
-                                     int32_t* __restrict__ out) {
-  extern __shared__ int32_t diag[];                 // [3][blockDim.x + 1]
-  const int pair = blockIdx.x;
+// Levenshtein distance, one WARP per (hypothesis, reference) pair: lane l owns the K reference columns l*K+1 .. l*K+K of the DP table
+// in registers and sweeps the hypothesis rows one step behind lane l-1 (at step s lane l is on row s-l+1), so the only traffic between
+// lanes is one shuffle per step -- the last column of the left neighbour's strip.  m + (n-1)/K steps, each a log2(K)-deep prefix
+// minimum over the strip; no shared memory, no block barriers.  (Rounds 1-2 ran one CTA per pair, a __syncthreads per anti-diagonal: 90 us for 225-symbol
+// pairs, and barrier-heavy CTAs beside the CTC recursion.)  dist(a[0:m], b[0:n]); n <= 32*K.
+constexpr int kEditWarps = 4;
+template <typename Sym, int K>
+__global__ void __launch_bounds__(32 * kEditWarps)
+edit_distance_kernel(const Sym* __restrict__ hyp, const int32_t* __restrict__ hyp_len, int64_t hyp_stride, const Sym* __restrict__ ref,
+                     const int32_t* __restrict__ ref_len, int64_t ref_stride, int32_t* __restrict__ out, int pairs) {
+  const int pair = blockIdx.x * kEditWarps + (int)(threadIdx.x >> 5);
+  if (pair >= pairs) return;                         // (the whole warp leaves together)
+  const int lane = threadIdx.x & 31;
   const int m = hyp_len[pair], n = ref_len[pair];
   const Sym* a = hyp + (int64_t)pair * hyp_stride;
   const Sym* b = ref + (int64_t)pair * ref_stride;
   if (m == 0 || n == 0) {
-    if (threadIdx.x == 0) out[pair] = m + n;
+    if (lane == 0) out[pair] = m + n;
     return;
   }
-  const int W = blockDim.x + 1;
-  const int j = threadIdx.x;                         // column j+1 (1-based), valid when j < n
-  const Sym bj = j < n ? b[j] : Sym(0);
-  // D[i][c] with i = row (0..m), c = column (0..n); diagonal d = i + c.  buffers hold D[d - c][c] indexed by c.
-  int32_t* d2 = diag;            // diagonal d-2
-  int32_t* d1 = diag + W;        // diagonal d-1
-  int32_t* d0 = diag + 2 * W;    // diagonal d
-  if (threadIdx.x == 0) {
-    d2[0] = 0;                   // D[0][0]   (diag 0)
-    d1[0] = 1;                   // D[1][0]   (diag 1)
-    d1[1] = 1;                   // D[0][1]
+  Sym bq[K];
+  int row[K];                                        // D[i-1][c] of the strip while the lane works on row i; D[0][c] = c to start with
+#pragma unroll
+  for (int q = 0; q < K; ++q) {
+    const int c = lane * K + q + 1;
+    bq[q] = c <= n ? b[c - 1] : Sym(0);
+    row[q] = c;
   }
-  __syncthreads();
-  for (int d = 2; d <= m + n; ++d) {
-    const int c = j + 1, i = d - c;
-    if (c <= n) {
-      if (i == 0) {
-        d0[c] = c;                                                   // first row
-      } else if (i > 0 && i <= m) {
-        const int sub = d2[c - 1] + (a[i - 1] != bj);                // D[i-1][c-1]
-        const int del = d1[c] + 1;                                   // D[i-1][c]
-        const int ins = d1[c - 1] + 1;                               // D[i][c-1]
-        d0[c] = min(sub, min(del, ins));
+  const int owner = (n - 1) / K;                     // the lane that holds column n
+  int left_prev = lane * K;                          // D[i-1][lane*K], the column left of the strip: D[0][lane*K] for row 1
+  int my_last = 0;                                   // D[i][lane*K + K] of the row finished in the previous step
+  Sym a_next = lane == 0 ? a[0] : Sym(0);            // hypothesis symbol of the row this lane starts next, fetched a step ahead
+  for (int s = 0; s < m + owner; ++s) {
+    const int recv = __shfl_up_sync(0xffffffffu, my_last, 1);
+    const int i = s - lane + 1;                      // 1-based row of this lane at this step
+    const Sym ai = a_next;
+    a_next = a[min(max(i, 0), m - 1)];               // row i+1's symbol (clamped: an unconditional load keeps the address math out of the loop)
+    if (i >= 1 && i <= m) {
+      // v_q = min(t_q, v_{q-1} + 1) with t_q = min(D[i-1][c] + 1, D[i-1][c-1] + cost) and v_{-1} = D[i][lane*K] (from the left lane).
+      // Unrolled: v_q = q + min(left + 1, min_{j<=q}(t_j - j)) -- the t_j and their prefix minimum depend on the lane's own previous
+      // row only, so what waits for the neighbour's shuffle is one add, one min, one add instead of a K-cell chain.
+      const int left = lane == 0 ? i : recv;         // D[i][lane*K]
+      int pm[K];
+#pragma unroll
+      for (int q = 0; q < K; ++q) {
+        const int diag = q == 0 ? left_prev : row[q - 1];            // D[i-1][c-1]
+        pm[q] = min(row[q] + 1, diag + (ai != bq[q] ? 1 : 0)) - q;
       }
+      left_prev = left;
+#pragma unroll
+      for (int d = 1; d < K; d <<= 1) {              // inclusive prefix minimum (Kogge-Stone, in place from the top)
+#pragma unroll
+        for (int q = K - 1; q >= d; --q) pm[q] = min(pm[q], pm[q - d]);
+      }
+      const int l1 = left + 1;
+#pragma unroll
+      for (int q = 0; q < K; ++q) row[q] = min(l1, pm[q]) + q;
+      my_last = row[K - 1];
     }
-    if (threadIdx.x == 0 && d <= m) d0[0] = d;                       // first column
-    __syncthreads();
-    int32_t* t = d2;
-    d2 = d1;
-    d1 = d0;
-    d0 = t;
   }
-  if (threadIdx.x == 0) out[pair] = d1[n];                           // D[m][n] lives on the last diagonal
+  int res = 0;
+#pragma unroll
+  for (int q = 0; q < K; ++q)
+    if (q == (n - 1) % K) res = row[q];
+  res = __shfl_sync(0xffffffffu, res, owner);
+  if (lane == 0) out[pair] = res;
 }
 
 // ratios[0] = cer, [1] = wer, [2] = len_ratio
@@ -193,12 +211,18 @@ int w2l_string_metrics(const int32_t* tokens, const int32_t* counts, int64_t N, 
   metrics_split_kernel<<<(unsigned)N, kSplitThreads, 0, st>>>(ref_ids, ref_lens, (int)N, (int)ref_stride, space_index, r_chars, r_nc, r_words, r_nw);
   rc = after_launch("metrics_split_kernel<ref>");
   if (rc) return rc;
-  const int threads = (int)((ref_stride + 31) / 32 * 32);
-  const size_t smem = 3 * (size_t)(threads + 1) * sizeof(int32_t);
-  edit_distance_kernel<int32_t><<<(unsigned)N, threads, smem, st>>>(h_chars, h_nc, T, r_chars, r_nc, ref_stride, cer_d);
-  rc = after_launch("edit_distance_kernel<chars>");
-  if (rc) return rc;
-  edit_distance_kernel<long long><<<(unsigned)N, threads, smem, st>>>(h_words, h_nw, T, r_words, r_nw, ref_stride, wer_d);
+  const unsigned eblocks = (unsigned)((N + kEditWarps - 1) / kEditWarps);
+  if (ref_stride <= 256) {                          // 8 columns per lane
+    edit_distance_kernel<int32_t, 8><<<eblocks, 32 * kEditWarps, 0, st>>>(h_chars, h_nc, T, r_chars, r_nc, ref_stride, cer_d, (int)N);
+    rc = after_launch("edit_distance_kernel<chars>");
+    if (rc) return rc;
+    edit_distance_kernel<long long, 8><<<eblocks, 32 * kEditWarps, 0, st>>>(h_words, h_nw, T, r_words, r_nw, ref_stride, wer_d, (int)N);
+  } else {                                          // up to 1023 reference symbols: 32 columns per lane
+    edit_distance_kernel<int32_t, 32><<<eblocks, 32 * kEditWarps, 0, st>>>(h_chars, h_nc, T, r_chars, r_nc, ref_stride, cer_d, (int)N);
+    rc = after_launch("edit_distance_kernel<chars>");
+    if (rc) return rc;
+    edit_distance_kernel<long long, 32><<<eblocks, 32 * kEditWarps, 0, st>>>(h_words, h_nw, T, r_words, r_nw, ref_stride, wer_d, (int)N);
+  }
   rc = after_launch("edit_distance_kernel<words>");
   if (rc) return rc;
   metrics_finalize_kernel<<<1, 256, 0, st>>>(cer_d, wer_d, counts, (int)N, cer_den, wer_den, len_den, ratios);

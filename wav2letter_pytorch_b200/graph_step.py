@@ -110,13 +110,14 @@ class GraphedTrainStep:
         scores, out_lens = m.forward(x, il)
         if not self._metrics_on:
             return m.criterion(scores.transpose(0, 1), tg, out_lens, tl), None
-        # decode + CER/WER feed only the logger: their own branch, forked behind the forward pass (as ConvCTCASR._step does).  In the
-        # graph nothing waits for it before the very end of the step, so it runs beside the CTC kernels AND the backward pass -- at
-        # the default yaml's size the branch is a quarter of the step's kernel time.  `scores` / `out_lens` are kept referenced until
-        # the join: memory freed on the compute stream could otherwise be handed to a backward kernel while the branch still reads it.
+        # decode + CER/WER feed only the logger: their own branch, forked behind the CTC kernels (beside them the edit-distance CTAs
+        # slow the latency-bound lattice recursion down, call 32).  In the graph nothing waits for the branch before the very end of
+        # the step, so it runs beside the backward pass -- at the default yaml's size it is a fifth of the step's kernel time.
+        # `scores` / `out_lens` are kept referenced until the join: memory freed on the compute stream could otherwise be handed to a
+        # backward kernel while the branch still reads it.
         main = torch.cuda.current_stream(self.device)
-        self._metric_stream.wait_stream(main)
         loss = m.criterion(scores.transpose(0, 1), tg, out_lens, tl)
+        self._metric_stream.wait_stream(main)
         with torch.cuda.stream(self._metric_stream):
             ratios = m.ctc_decoder.score_device(scores, out_lens, self._ids_d, self._lens_d) / self._den_d
         self._branch_keep = (scores, out_lens)
