@@ -149,6 +149,8 @@ class GraphedTrainStep:
             self.optimizer.step()
             self._join()
         self.graph, self._loss, self._ratios, self._key = g, loss.detach(), ratios, self._hyper()
+        self._mutated = list(self.model.parameters()) + list(self.model.buffers())
+        self._fresh_convs = [c for plan in getattr(self.optimizer, "_plans", {}).values() for c in plan.get("convs", ())]
         # Jasper's NaN assertion (jasper.py:474): the captured forward left its device flag here instead of reading it
         self._nan_flag = self.model.__dict__.pop("_nan_flag_graph", None)
         self._nan_pending = []
@@ -161,6 +163,12 @@ class GraphedTrainStep:
         if self._hyper() != self._key:                   # a scheduler moved the learning rate: by-value operand, capture again
             self._capture()
         self.graph.replay()
+        # the replay rewrote parameters, optimizer moments and BatchNorm statistics behind autograd's back: bump their version counters
+        # as the eager step does, so that every cache keyed on them (the eval-mode BatchNorm fold, the operand copies of the weights)
+        # is rebuilt by its next eager user; the bf16 operand copies the fused optimizer maintains inside the graph stay marked fresh
+        torch.autograd.graph.increment_version(self._mutated)
+        for conv in self._fresh_convs:
+            conv.mark_shadow_fresh()
         if self._nan_flag is not None:
             self.check_nan(block=False)
             host = self._nan_free.pop() if getattr(self, "_nan_free", None) else torch.zeros(1, dtype=torch.int32).pin_memory()
