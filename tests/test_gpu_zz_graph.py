@@ -110,6 +110,9 @@ def test_graphed_step_trains_like_the_eager_step():
     finally:
         step.close()
     assert ref_losses[-1] < ref_losses[0]
+    steps_e = sorted(int(st["step"]) for st in oe.state.values())
+    steps_g = sorted(int(st["step"]) for st in og.state.values())
+    assert steps_e == steps_g and steps_g[0] == warm + len(bs) + 1, (steps_e[:3], steps_g[:3])     # host-side step counters follow the replays
     m2, o2 = _model(0.0, 0.02)                           # calibration: a second eager run of the same schedule
     for _ in range(warm):
         _eager(m2, o2, bs[0])

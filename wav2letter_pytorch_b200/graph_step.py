@@ -132,6 +132,8 @@ class GraphedTrainStep:
         return tuple(tuple(sorted((k, repr(v)) for k, v in g.items() if k != "params")) for g in self.optimizer.param_groups)
 
     def _capture(self):
+        if self.graph is not None:
+            self.sync_optimizer_state()
         if hasattr(self.optimizer, "prepare_capture"):
             self.optimizer.prepare_capture()
         # The captured backward allocates the gradients in the graph's own pool.  Autograd binds a parameter's AccumulateGrad node to the
@@ -150,6 +152,8 @@ class GraphedTrainStep:
             self._join()
         self.graph, self._loss, self._ratios, self._key = g, loss.detach(), ratios, self._hyper()
         self._mutated = list(self.model.parameters()) + list(self.model.buffers())
+        self._replays = -1                               # the optimizer's host-side step counters: the capture itself counted one step
+        self.sync_optimizer_state()                      # that never ran
         self._fresh_convs = [c for plan in getattr(self.optimizer, "_plans", {}).values() for c in plan.get("convs", ())]
         # Jasper's NaN assertion (jasper.py:474): the captured forward left its device flag here instead of reading it
         self._nan_flag = self.model.__dict__.pop("_nan_flag_graph", None)
@@ -163,6 +167,7 @@ class GraphedTrainStep:
         if self._hyper() != self._key:                   # a scheduler moved the learning rate: by-value operand, capture again
             self._capture()
         self.graph.replay()
+        self._replays += 1
         # the replay rewrote parameters, optimizer moments and BatchNorm statistics behind autograd's back: bump their version counters
         # as the eager step does, so that every cache keyed on them (the eval-mode BatchNorm fold, the operand copies of the weights)
         # is rebuilt by its next eager user; the bf16 operand copies the fused optimizer maintains inside the graph stay marked fresh
@@ -183,6 +188,16 @@ class GraphedTrainStep:
             logs.update({"train_cer": r[0], "train_wer": r[1], "train_len_ratio": r[2]})
         self.model.log_dict(logs)
         return loss
+
+    def sync_optimizer_state(self):
+        """Adds the replayed steps to the optimizer's host-side per-parameter ``step`` counters (the reference's state layout,
+        novograd.py:85-88; nothing on the device reads them).  Called by ``close()`` and before every re-capture; call it before
+        ``optimizer.state_dict()`` if the counters matter."""
+        n, self._replays = self._replays, 0
+        if n:
+            for st in self.optimizer.state.values():
+                if "step" in st:
+                    st["step"] += n
 
     def check_nan(self, block=True):
         """Raises AssertionError if a replayed forward produced a NaN (the reference asserts inside forward, jasper.py:474; a replay
@@ -205,4 +220,6 @@ class GraphedTrainStep:
         fold the -- then constant -- counter into their per-call seeds, which changes nothing about their statistics.)"""
         if self._nan_flag is not None:
             self.check_nan(block=True)
+        if self.graph is not None:
+            self.sync_optimizer_state()
         self.graph = None
