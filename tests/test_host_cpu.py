@@ -348,3 +348,27 @@ def test_jasper_unmasked_block_speaks_reference_state_dict_keys():
     assert {"mconv.0.conv.weight", "mconv.1.conv.weight"} <= set(masked.state_dict().keys())
     with pytest.raises(NotImplementedError):                 # activation-then-dropout differs from the fused order for a clamp
         JasperBlock(64, 64, repeat=1, kernel_size=5, dropout=0.2)
+
+
+def test_encode_refs_into_caller_buffers():
+    """decoder._encode_refs(into=...): what graph_step.GraphedTrainStep uses to refresh the static reference operands of a captured
+    step -- label ids, lengths and the three denominators of base_asr_models.py:58-69 (characters without spaces, words, characters)"""
+    from wav2letter_pytorch_b200.decoder import GreedyDecoder
+    from wav2letter_pytorch_b200.label_sets import english_lowercase_labels as labels
+    dec = GreedyDecoder(labels)
+    texts = ["hello world", " a  b ", "it's", "x"]
+    ids = torch.full((4, 16), -7, dtype=torch.int32)
+    lens = torch.zeros(4, dtype=torch.int32)
+    enc = dec._encode_refs(texts, into=(ids, lens))
+    assert enc is not None
+    slot, smax, cer_den, wer_den, len_den = enc
+    assert slot[0] is ids and slot[1] is lens and smax == 11
+    assert lens.tolist() == [len(t) for t in texts]
+    for i, t in enumerate(texts):
+        assert ids[i, :len(t)].tolist() == [labels.index(c) for c in t]
+        assert (ids[i, len(t):] == -7).all()                                  # nothing beyond the transcript is touched
+    assert cer_den == sum(len(t.replace(" ", "")) for t in texts)
+    assert wer_den == sum(len(t.split()) for t in texts)
+    assert len_den == sum(len(t) for t in texts)
+    assert dec._encode_refs(texts, into=(ids[:, :8], lens)) is None          # a transcript longer than the buffer: no device path
+    assert dec._encode_refs(texts + ["y"], into=(ids, lens)) is None         # more transcripts than rows
