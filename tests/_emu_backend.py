@@ -432,8 +432,8 @@ def novograd_step(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq, shadows, l
 # ------------------------------------------------------------------------------------------------ WER / CER (metrics.cu)
 @functools.lru_cache(maxsize=None)
 def metrics():
-    return KE.build(["metrics.cu"], ["metrics_split_kernel", "edit_distance_kernel<int32_t>", "edit_distance_kernel<long long>",
-                                     "metrics_finalize_kernel"])
+    return KE.build(["metrics.cu"], ["metrics_split_kernel", "edit_distance_kernel<int32_t, 8>", "edit_distance_kernel<long long, 8>",
+                                     "edit_distance_kernel<int32_t, 32>", "edit_distance_kernel<long long, 32>", "metrics_finalize_kernel"])
 
 
 def string_metrics(tokens, counts, space_index, ref_ids, ref_lens, cer_den, wer_den, len_den):
@@ -449,13 +449,12 @@ def string_metrics(tokens, counts, space_index, ref_ids, ref_lens, cer_den, wer_
     h_nc, h_nw, r_nc, r_nw, cer_d, wer_d = (i32(N) for _ in range(6))
     ratios = torch.full((3,), float("nan"))
     K = metrics()
-    blocks = (N + 63) // 64
-    K.launch("metrics_split_kernel", blocks, 64, _p(tokens), _p(counts), N, T, space_index, _p(h_chars), _p(h_nc), _p(h_words), _p(h_nw))
-    K.launch("metrics_split_kernel", blocks, 64, _p(ref_ids), _p(ref_lens), N, S, space_index, _p(r_chars), _p(r_nc), _p(r_words), _p(r_nw))
-    threads = (S + 31) // 32 * 32
-    smem = 3 * (threads + 1) * 4
-    K.launch("edit_distance_kernel<int32_t>", N, threads, _p(h_chars), _p(h_nc), T, _p(r_chars), _p(r_nc), S, _p(cer_d), smem=smem)
-    K.launch("edit_distance_kernel<long long>", N, threads, _p(h_words), _p(h_nw), T, _p(r_words), _p(r_nw), S, _p(wer_d), smem=smem)
+    # one CTA of 128 threads per utterance (kSplitThreads); one warp per pair, 4 warps per CTA (kEditWarps), 8 / 32 columns per lane
+    K.launch("metrics_split_kernel", N, 128, _p(tokens), _p(counts), N, T, space_index, _p(h_chars), _p(h_nc), _p(h_words), _p(h_nw))
+    K.launch("metrics_split_kernel", N, 128, _p(ref_ids), _p(ref_lens), N, S, space_index, _p(r_chars), _p(r_nc), _p(r_words), _p(r_nw))
+    kk = 8 if S <= 256 else 32
+    K.launch("edit_distance_kernel<int32_t, %d>" % kk, (N + 3) // 4, 128, _p(h_chars), _p(h_nc), T, _p(r_chars), _p(r_nc), S, _p(cer_d), N)
+    K.launch("edit_distance_kernel<long long, %d>" % kk, (N + 3) // 4, 128, _p(h_words), _p(h_nw), T, _p(r_words), _p(r_nw), S, _p(wer_d), N)
     K.launch("metrics_finalize_kernel", 1, 256, _p(cer_d), _p(wer_d), _p(counts), N, float(cer_den), float(wer_den), float(len_den),
              _p(ratios))
     return ratios, cer_d, wer_d
