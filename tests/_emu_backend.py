@@ -201,11 +201,11 @@ def lens_chain(lens, conv_params):
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm + activation
-def bn_stats(z, C):
-    """w2l_bn_stats (elementwise.cu:779-787)"""
+def bn_stats(z, C, out=None):
+    """w2l_bn_stats (elementwise.cu:779-787); accumulates into ``out`` when given, as the kernel does"""
     z = z.contiguous()
     rows = z.numel() // C
-    stats = torch.zeros((2 * C,))
+    stats = torch.zeros((2 * C,)) if out is None else out
     col_blocks = (C + 255) // 256
     rpb = _rows_per_block_for(rows, col_blocks)
     elementwise().launch("bn_stats_kernel", (col_blocks, (rows + rpb - 1) // rpb), (32, 8), _p(z), rows, C, _p(stats), rpb)

@@ -104,9 +104,10 @@ def pack_wt(w_store, wt, cout, cin):
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm / activation passes
-def bn_stats(z, C):
+def bn_stats(z, C, out=None):
     v = z.float().reshape(-1, C)
-    return torch.cat([v.sum(0), (v * v).sum(0)])
+    st = torch.cat([v.sum(0), (v * v).sum(0)])
+    return st if out is None else out.add_(st)
 
 
 def bn_finalize(stats, rows, C, gamma, beta, conv_bias, eps, momentum, running_mean, running_var, num_batches_tracked=None):

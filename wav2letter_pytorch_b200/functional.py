@@ -362,9 +362,10 @@ def tm_to_ncw(x, T, C, x_rows=None, x_row_offset=0):
     return out
 
 
-def bn_stats(z, C):
+def bn_stats(z, C, out=None):
+    """per-channel (sum, sum of squares) of bf16 ``z`` [rows, C], ADDED into ``out`` (fp32 [2C], zero-filled by the caller) when given"""
     rows = z.numel() // C
-    stats = torch.zeros((2 * C,), dtype=torch.float32, device=z.device)
+    stats = torch.zeros((2 * C,), dtype=torch.float32, device=z.device) if out is None else out
     with _on(z.device):
         _lib.check(_lib.load().w2l_bn_stats(_ptr(z), rows, C, _ptr(stats), _stream()), "bn_stats")
     return stats

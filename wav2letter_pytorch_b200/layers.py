@@ -394,6 +394,7 @@ def conv_desc(conv, B, T_out, x_rows, x_row_offset, y_rows=None, y_row_offset=0,
 
 
 _EPILOGUE_STATS = os.environ.get("W2L_EPILOGUE_STATS", "1") != "0"      # 0: separate bn_stats pass over z (A/B measurements)
+_STATS_PASS_K1 = os.environ.get("W2L_STATS_PASS_K1", "1") != "0"        # 0: k = 1 convs keep their statistics in the GEMM epilogue too
 
 
 class FusedBnReduce:
@@ -486,12 +487,14 @@ def pad_channels(t, Cp, value=0.0):
 def conv_fwd_with_stats(xin, conv, desc, z, stats=None):
     """conv forward into ``z`` + BatchNorm batch statistics [2*Cout] (sum, sum of squares of the stored bf16 values), accumulated into
     ``stats`` (zero on entry) when given."""
-    if not _EPILOGUE_STATS:
-        F.conv1d_fwd(xin, conv.packed(), desc, z)
-        st = F.bn_stats(z, conv.cout_phys)
-        return st if stats is None else stats.copy_(st)
     if stats is None:
         stats = torch.zeros((2 * conv.cout_phys,), dtype=torch.float32, device=xin.device)
+    # k = 1 (Jasper's residual 1x1 convs, the 1024-wide tail layer, the unfolded first layer): the mainloop of a tile is too short to
+    # hide the statistics block of the epilogue -- the forward GEMM ran at half the speed of the backward-data GEMM of the same shape
+    # (profiles/r2_gemm_cg2.md, addendum) -- while the stored output is still L2-resident for a separate pass
+    if not _EPILOGUE_STATS or (_STATS_PASS_K1 and conv.k_eff == 1 and not conv.f32):
+        F.conv1d_fwd(xin, conv.packed(), desc, z)
+        return F.bn_stats(z, conv.cout_phys, out=stats)
     F.conv1d_fwd(xin, conv.packed(), desc, z, bn_stats=stats)
     return stats
 
