@@ -357,6 +357,45 @@ def gen_odd(ref):
     np.savez_compressed(os.path.join(OUT, "w2l_odd.npz"), **_np(out))
 
 
+def gen_jasper_odd(ref):
+    """Jasper with channel counts the tensor-core path has to pad internally (the reference takes any ``layer_size``, jasper.py:289-298):
+    161 STFT bins in, a stride-2 prologue, a residual dense block, a separable block and a dilated one at widths 100 / 36 / 250 / 52"""
+    import json
+    torch.manual_seed(23)
+    blocks = [dict(layer_size=100, kernel_size=10, stride=2, residual=False, separable=False, repeat=1),
+              dict(layer_size=36, kernel_size=5, stride=1, residual=True, separable=False, repeat=2),
+              dict(layer_size=250, kernel_size=7, stride=1, residual=True, separable=True, repeat=2),
+              dict(layer_size=52, kernel_size=3, stride=1, dilation=2, residual=False, separable=False, repeat=1)]
+    cfg = rl.reference_model_cfg("jasper", mid_layers=4, dropout=0, jasper_blocks=blocks)
+    cfg["input_size"] = 0                                  # -> 161 STFT bins
+    model = ref.jasper.Jasper(cfg)
+    assert model.input_size == 161
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    x = torch.randn(3, 161, 201)
+    il = torch.tensor([201, 160, 121], dtype=torch.int32)
+    tg = torch.randint(1, 29, (3, 20), dtype=torch.int32)
+    tl = torch.tensor([20, 12, 7], dtype=torch.int32)
+    for n in range(3):
+        tg[n, tl[n]:] = 0
+        x[n, :, il[n]:] = 0
+    out = {"x": x, "il": il, "tg": tg, "tl": tl, "blocks_json": np.array(json.dumps(blocks))}
+    out.update(_sd(model, "sd0:"))
+    model.train()
+    rec = _train_step_record(ref, model, x, il, tg, tl, None)
+    out.update({"train:" + k: v for k, v in rec.items()})
+    out.update(_sd(model, "sd1:"))
+    model.eval()
+    with torch.no_grad():
+        o, ol = model(x, il)
+    out["eval:out"], out["eval:out_len"] = o, ol
+    out["scaling_factor"] = model.scaling_factor
+    np.savez_compressed(os.path.join(OUT, "jasper_odd.npz"), **_np(out))
+
+
 def gen_ctc(ref):
     g = torch.Generator().manual_seed(5)
     crit = torch.nn.CTCLoss(blank=0, reduction="mean", zero_infinity=True)    # base_asr_models.py:23
@@ -460,10 +499,10 @@ def gen_beam(ref):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd", "strided", "narrow", "odd"):      # regenerate one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("features", "beam", "novograd", "strided", "narrow", "odd", "jasper_odd"):      # regenerate one fixture without touching the others
         ref = rl.load_reference()
         torch.set_num_threads(1)
-        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd, "strided": gen_strided, "narrow": gen_narrow, "odd": gen_odd}[sys.argv[1]](ref)
+        {"features": gen_features, "beam": gen_beam, "novograd": gen_novograd, "strided": gen_strided, "narrow": gen_narrow, "odd": gen_odd, "jasper_odd": gen_jasper_odd}[sys.argv[1]](ref)
         return
     ref = rl.load_reference()
     torch.set_num_threads(1)
@@ -475,6 +514,7 @@ def main():
     gen_strided(ref)
     gen_narrow(ref)
     gen_odd(ref)
+    gen_jasper_odd(ref)
     gen_ctc(ref)
     gen_novograd(ref)
     gen_features(ref)

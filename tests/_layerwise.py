@@ -167,6 +167,8 @@ def jasper_layerwise_table(model, specs, hs, taps, rows, out):
         spec, R = specs[i], specs[i]["repeat"]
         assert len(taps[i]) == R
         prefix = "jasper_encoder.%d." % i
+        # logical widths (the device buffers may be padded, see _ncw): the block's input and its BatchNorms' feature count
+        cin, planes = blk.mconv[0].conv.in_channels, [m for m in blk.mconv if hasattr(m, "num_features")][-1].num_features
         rows_of = [dict() for _ in range(R)]
         for emu in (True, False):
             col = 0 if emu else 1
@@ -178,20 +180,21 @@ def jasper_layerwise_table(model, specs, hs, taps, rows, out):
             for r in reversed(range(R)):
                 first = i == 0 and r == 0
                 h_dev, ri = taps[i][r]
-                hin = (hs[0].detach().float().cpu() if first else _ncw(h_dev)).clone().requires_grad_(not first)
+                c_in = cin if r == 0 else planes
+                hin = (hs[0].detach().float().cpu() if first else _ncw(h_dev, c_in)).clone().requires_grad_(not first)
                 xin = _bf(hin) if (first and emu) else hin
                 lens = rows[ri].clone()
                 last_sub = r == R - 1
                 block_in = None
                 if last_sub and spec["residual"]:
-                    block_in = hin if R == 1 else _ncw(hs[i]).clone().requires_grad_(True)
+                    block_in = hin if R == 1 else _ncw(hs[i], cin).clone().requires_grad_(True)
                 y = jasper_sub_oracle(spec, sd_i, i, r, xin, lens, block_in, rows[taps[i][0][1]].clone(), emu)
                 dev_out = hs[i + 1] if last_sub else taps[i][r + 1][0]
                 nxt_ri = (taps[i + 1][0][1] if i + 1 < len(blocks) else None) if last_sub else taps[i][r + 1][1]
                 if spec["conv_mask"] and nxt_ri is not None:
                     y = _mask_rows(y, rows[nxt_ri])         # the consumer's masked_fill (jasper.py:116-119), written by this build's producer
-                y.backward(_ncw(dev_out.grad))
-                rows_of[r].setdefault("out", [None, None])[col] = rel_l2(_ncw(dev_out), y.detach())
+                y.backward(_ncw(dev_out.grad, planes))
+                rows_of[r].setdefault("out", [None, None])[col] = rel_l2(_ncw(dev_out, planes), y.detach())
                 if last_sub and spec["residual"] and R > 1:
                     d_block_in = block_in.grad
                 if not first:
@@ -199,7 +202,7 @@ def jasper_layerwise_table(model, specs, hs, taps, rows, out):
                     if r == 0 and d_block_in is not None:
                         want = want + d_block_in
                     # rows past an utterance's length carry no gradient in the reference (masked_fill); the device leaves them unspecified
-                    got = _mask_rows(_ncw(h_dev.grad), lens) if spec["conv_mask"] else _ncw(h_dev.grad)
+                    got = _mask_rows(_ncw(h_dev.grad, c_in), lens) if spec["conv_mask"] else _ncw(h_dev.grad, c_in)
                     rows_of[r].setdefault("d_input", [None, None])[col] = rel_l2(got, want)
             step = 5 if spec["separable"] else 4
             for k, leaf in leaves.items():
@@ -214,12 +217,12 @@ def jasper_layerwise_table(model, specs, hs, taps, rows, out):
     for emu in (True, False):
         w = head.weight.detach().float().cpu().contiguous().clone().requires_grad_(True)
         b = head.bias.detach().float().cpu().clone().requires_grad_(True)
-        hin = _ncw(hs[-1]).clone().requires_grad_(True)
+        hin = _ncw(hs[-1], head.in_channels).clone().requires_grad_(True)
         lp = torch.log_softmax(TF.conv1d(hin, O._bf16_weight(w) if emu else w, b).transpose(1, 2), -1)
         lp.backward(out.grad.detach().float().cpu())
         col = 0 if emu else 1
         row.setdefault("out", [None, None])[col] = rel_l2(out.detach().float().cpu(), lp.detach())
-        row.setdefault("d_input", [None, None])[col] = rel_l2(_ncw(hs[-1].grad), hin.grad)
+        row.setdefault("d_input", [None, None])[col] = rel_l2(_ncw(hs[-1].grad, head.in_channels), hin.grad)
         row.setdefault("d_weight", [None, None])[col] = rel_l2(head.weight.grad, w.grad)
         row.setdefault("d_bias", [None, None])[col] = rel_l2(head.bias.grad, b.grad)
     table.append(("head", row))

@@ -440,12 +440,20 @@ def test_jasper_dense_golden(pkg, golden, fixture):
     check_jasper_golden(pkg, golden(fixture), seed=4 if fixture == "jasper_dense" else 2)
 
 
-def check_jasper_golden(pkg, g, seed):
+def test_jasper_odd_widths_golden(pkg, golden):
+    """Jasper at channel counts that are padded internally (161 STFT bins in; widths 100 / 36 / 250 / 52 over a stride-2 prologue, a
+    residual dense block, a separable block and a dilated one): same checks and bounds as the other Jasper fixtures"""
+    check_jasper_golden(pkg, golden("jasper_odd"), seed=23, input_size=0)
+
+
+def check_jasper_golden(pkg, g, seed, input_size=None):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
     cfg["jasper_blocks"] = config.to_attr(blocks)
+    if input_size is not None:
+        cfg["input_size"] = input_size
     torch.manual_seed(seed)
     model = Jasper(cfg)
     for k in g.files:                                                   # seeded construction == the reference's

@@ -111,7 +111,7 @@ def test_w2l_wiring_against_reference_fixture(golden, monkeypatch, fixture, back
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("fixture,seed", [("jasper_dense", 4), ("jasper_small", 2), ("jasper_strided", 10)])
+@pytest.mark.parametrize("fixture,seed", [("jasper_dense", 4), ("jasper_small", 2), ("jasper_strided", 10), ("jasper_odd", 23)])
 def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, seed, backend):
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
@@ -122,6 +122,8 @@ def test_jasper_wiring_against_reference_fixture(golden, monkeypatch, fixture, s
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
     cfg["jasper_blocks"] = config.to_attr(blocks)
+    if fixture == "jasper_odd":                   # 161 STFT bins (input_size unset), widths 100 / 36 / 250 / 52: padded internally
+        cfg["input_size"] = 0
     torch.manual_seed(seed)
     model = Jasper(cfg)
     for k in g.files:                                                   # seeded construction == the reference's

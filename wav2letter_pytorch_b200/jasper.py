@@ -21,7 +21,7 @@ import torch.nn as nn
 from . import functional as F
 from .base_asr_models import ConvCTCASR
 from .layers import (BatchNormParams, ConvBNActFn, ConvHeadFn, ConvParams, DepthwiseFn, DepthwiseParams, ResidualBranchFn,
-                     UnfoldTmFn, conv_bn_act_eval, conv_desc)
+                     UnfoldTmFn, conv_bn_act_eval, conv_desc, pad_channels)
 
 jasper_activations = {"hardtanh": nn.Hardtanh, "relu": nn.ReLU, "selu": nn.SELU}
 
@@ -123,8 +123,6 @@ class JasperBlock(nn.Module):
             raise NotImplementedError("grouped (shuffled) Jasper sub-blocks are not reachable from Jasper._build_encoder and not implemented")
         if residual_mode != "add" or len(residual_panes) != 0:
             raise NotImplementedError("only the plain 'add' residual is implemented")
-        if planes % 8 or planes < 64 or (inplanes % 8) or inplanes < 64:
-            raise ValueError("JasperBlock: widths (%d -> %d) must be >= 64 and multiples of 8 for the tensor-core path" % (inplanes, planes))
         kernel_size = compute_new_kernel_size(kernel_size, float(kernel_size_factor))
         pad = get_same_padding(kernel_size, stride, dilation)
         self.conv_mask, self.separable, self.residual_mode = conv_mask, separable, residual_mode
@@ -193,6 +191,9 @@ class JasperBlock(nn.Module):
         if from_ncw:
             m0 = first.conv
             k, s, d, p = m0.kernel_size[0], m0.stride[0], m0.dilation[0], m0.padding[0]
+            Fp = ConvParams.phys(m0.in_channels)
+            if Fp != h.shape[1]:                         # feature counts that are not a multiple of 8 (161 STFT bins) or below 64: zero rows
+                h = torch.nn.functional.pad(h, (0, 0, 0, Fp - h.shape[1]))
             mask = rows[ri] if (self.conv_mask and rows is not None) else None
             if not self.separable and m0.unfold:
                 t_first = (t + 2 * p - d * (k - 1) - 1) // s + 1
@@ -209,9 +210,12 @@ class JasperBlock(nn.Module):
             if training:
                 res_pair = ResidualBranchFn.apply(block_in, rconv.weight, rbn.weight, rbn.bias, rconv, rbn)
             else:
-                zr = torch.empty((h.shape[0], t, rconv.out_channels), dtype=rconv.act_dtype, device=h.device)
+                zr = torch.empty((h.shape[0], t, rconv.cout_phys), dtype=rconv.act_dtype, device=h.device)
                 F.conv1d_fwd(block_in, rconv.packed(), conv_desc(rconv, h.shape[0], t, t, 0), zr)
-                res_pair = (zr, rbn.eval_scale_shift(None))
+                rfold = rbn.eval_scale_shift(None)
+                if rconv.cout_phys != rconv.out_channels:                        # padded width: the surplus channels come out as 0 * 0 + 0
+                    rfold = (pad_channels(rfold[0], rconv.cout_phys), pad_channels(rfold[1], rconv.cout_phys))
+                res_pair = (zr, rfold)
 
         tap = getattr(self, "_tap", None)           # parity instrumentation (tests/_layerwise.py): every sub-block's input
         for r, (dwm, mc, bn) in enumerate(subs):
@@ -230,7 +234,7 @@ class JasperBlock(nn.Module):
                 if training:
                     h = DepthwiseFn.apply(h, dc.weight, dc, t_dw, dmask)
                 else:
-                    h = F.depthwise_fwd(h, dc.storage(), t_dw, k, s, d, p, dmask)
+                    h = F.depthwise_fwd(h, dc.storage_phys(), t_dw, k, s, d, p, dmask)
                 t = t_dw
             if conv.unfold:
                 if not (from_ncw and r == 0):                                    # (the encoder's first conv was unfolded from NCW above)
@@ -270,10 +274,14 @@ class Jasper(ConvCTCASR):
         self.final_layer = nn.Sequential(ConvParams(last, len(self.labels), 1, bias=True))
         self.final_layer.apply(init_weights)
         self.final_layer[0].is_head = True
-        for m in self.modules():                   # (Wav2Letter pads odd widths internally, ConvParams.phys; the Jasper blocks do not yet)
-            if isinstance(m, ConvParams) and m is not self.final_layer[0] and m.padded:
-                raise ValueError("Jasper: channel counts must be multiples of 8 and >= 64 for the tensor-core path (got %d -> %d)"
-                                 % (m.in_channels, m.out_channels))
+        # channel counts that are not multiples of 8 (or below 64) are padded internally like Wav2Letter's (ConvParams.phys: exact-zero
+        # surplus channels in every buffer, logical shapes for parameters and gradients).  One combination is not wired: a strided dense
+        # block beyond the first whose INPUT width is padded (its unfolded weights would need a per-tap padded backward-data copy).
+        convs = [m for m in self.modules() if isinstance(m, ConvParams)]
+        for m in convs[1:]:
+            if m.unfold and m.cin_phys != m.cin_eff:
+                raise NotImplementedError("Jasper: a strided dense block beyond the first with an input width that is not a multiple "
+                                          "of 8 (got %d)" % m.in_channels)
         # precision: "bf16" (default) or "tf32" -- the fp32-faithful mode (fp32 activations / weights / gradients in memory, tf32
         # multiplies in the GEMMs, plain fp32 FMAs in the depthwise convs, fp32 accumulation; see Wav2Letter).  Not for strided inner
         # blocks: their time-major unfold exists for bf16 activations.

@@ -307,6 +307,23 @@ class DepthwiseParams(nn.Module):
     def grad_view(self, dw_store):
         return dw_store.view(self.kernel_size[0], 1, self.in_channels).permute(2, 1, 0)
 
+    # channel counts that are not a multiple of 8 (or below 64): the activation buffers carry ConvParams.phys(C) channels whose surplus
+    # ones are exact zeros; the depthwise kernels see zero taps there, the gradient keeps the Parameter's logical shape
+    @property
+    def c_phys(self):
+        return ConvParams.phys(self.in_channels)
+
+    def storage_phys(self):
+        st = self.storage()
+        if self.c_phys == self.in_channels:
+            return st
+        out = torch.zeros((st.shape[0], self.c_phys), dtype=st.dtype, device=st.device)
+        out[:, :self.in_channels].copy_(st)
+        return out
+
+    def unpad_dw(self, dw):
+        return dw if self.c_phys == self.in_channels else dw[:, :self.in_channels].contiguous()
+
 
 class DepthwiseFn(torch.autograd.Function):
     """depthwise conv over time-major bf16 (zero 'same' padding); rows >= out_lens are written as zeros because the
@@ -315,7 +332,7 @@ class DepthwiseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xin, weight, conv, T_out, out_lens):
         k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
-        y = F.depthwise_fwd(xin, conv.storage(), T_out, k, s, d, p, out_lens)
+        y = F.depthwise_fwd(xin, conv.storage_phys(), T_out, k, s, d, p, out_lens)
         ctx.conv, ctx.out_lens = conv, out_lens
         ctx.save_for_backward(xin)
         return y
@@ -326,10 +343,10 @@ class DepthwiseFn(torch.autograd.Function):
         conv = ctx.conv
         k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
         dy = dy.contiguous()
-        dw = F.depthwise_wgrad(dy, xin, k, s, d, p, ctx.out_lens)
+        dw = conv.unpad_dw(F.depthwise_wgrad(dy, xin, k, s, d, p, ctx.out_lens))
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = F.depthwise_dgrad(dy, conv.storage(), xin.shape[1], k, d, p, ctx.out_lens, stride=s)
+            dx = F.depthwise_dgrad(dy, conv.storage_phys(), xin.shape[1], k, d, p, ctx.out_lens, stride=s)
         return dx, conv.grad_view(dw), None, None, None
 
 
@@ -605,14 +622,20 @@ class ResidualBranchFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xin, weight, gamma, beta, conv, bn):
         B, T, _ = xin.shape
-        Co = conv.out_channels
+        Co, C_log = conv.cout_phys, conv.out_channels      # physical (buffer) / logical (parameter) width: equal unless padded
         z = torch.empty((B, T, Co), dtype=conv.act_dtype, device=xin.device)
         desc = conv_desc(conv, B, T, T, 0)
         if ctx.needs_input_grad[0]:
             conv.prefetch_packed_t()
+        rm, rv = bn.running_mean, bn.running_var
+        if Co != C_log:                                    # neutral surplus entries, as in ConvBNActFn
+            gamma, beta = pad_channels(gamma, Co, 1.0), pad_channels(beta, Co)
+            rm, rv = pad_channels(rm, Co), pad_channels(rv, Co, 1.0)
         stats = conv_fwd_with_stats(xin, conv, desc, z)
-        fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
-                            bn.num_batches_tracked)
+        fin = F.bn_finalize(stats, B * T, Co, gamma, beta, None, bn.eps, bn.momentum, rm, rv, bn.num_batches_tracked)
+        if Co != C_log:
+            bn.running_mean.copy_(rm[:C_log])
+            bn.running_var.copy_(rv[:C_log])
         FusedBnReduce.claim(xin)            # a second consumer of the block input: its producer's reduction cannot be folded into one GEMM
         ctx.conv, ctx.desc = conv, desc
         ctx.save_for_backward(xin, z, fin, gamma)
@@ -625,14 +648,15 @@ class ResidualBranchFn(torch.autograd.Function):
         conv = ctx.conv
         B, T, Co = z.shape
         dz, red, _ = F.bn_act_bwd(g.contiguous(), z, fin[0], fin[1], fin[2], fin[3], gamma, B, T, Co, 0, 0, F.ACT_NONE)
-        dw = alloc_dw(conv, z.device)
+        dw = alloc_dw(conv, z.device, cout=Co)
         side = WgradStream.fork(z.device, conv.weight)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(xin)
             F.conv1d_dgrad_wt(dz, conv.packed_t_synced(), ctx.desc, dx)
-        wgrad_async(side, dz, xin, ctx.desc, dw)
-        return dx, conv.grad_view(dw), red[Co:], red[:Co], None, None
+        dw = wgrad_async(side, dz, xin, ctx.desc, dw, conv)
+        C_log = conv.out_channels
+        return dx, conv.grad_view(dw), red[Co:Co + C_log], red[:C_log], None, None
 
 
 class ConvHeadFn(torch.autograd.Function):
