@@ -133,14 +133,18 @@ def check_w2l_golden(pkg, g, input_size=None):
 TOL_TF32 = {"out": 1e-3, "loss": 1e-4, "grad": 1e-1, "running": 5e-3}
 
 
-def test_w2l_golden_fp32_faithful_mode(pkg, golden):
+@pytest.mark.parametrize("fixture", ["w2l_small", "w2l_odd"])
+def test_w2l_golden_fp32_faithful_mode(pkg, golden, fixture):
     """SURVEY 8c asks for logits / gradients vs torch fp32: the same fixture as above with the model in precision='tf32' (fp32 storage,
-    kind::tf32 GEMMs incl. the weight gradient over transposed operands, fp32 BatchNorm / activation passes), train step + eval"""
+    kind::tf32 GEMMs incl. the weight gradient over transposed operands, fp32 BatchNorm / activation passes), train step + eval;
+    ``w2l_odd``: the same mode over internally padded channel counts (161 -> 250 -> 36 -> 250)"""
     from wav2letter_pytorch_b200.wav2letter import Wav2Letter
-    g = golden("w2l_small")
+    g = golden(fixture)
     layers = [dict(output_size=int(o), kernel_size=int(k), stride=int(s), dilation=int(d), dropout=-1) for o, k, s, d in g["layers"]]
     cfg = _cfg(pkg, layers, len(layers))
     cfg["precision"] = "tf32"
+    if fixture == "w2l_odd":
+        cfg["input_size"] = 0
     model = Wav2Letter(cfg)
     assert model.precision == "tf32" and all(m.conv1.f32 for m in model.conv1ds.children())
     head = "conv1d_%d" % len(layers)
@@ -534,17 +538,21 @@ def test_jasper_dense_golden_fp32_faithful_mode(pkg, golden):
     assert rel_l2(o, g["eval:out"]) < 5e-3 and abs(float(o.sum(-1).mean()) - 1.0) < 1e-5
 
 
-def test_jasper_separable_golden_fp32_faithful_mode(pkg, golden):
+@pytest.mark.parametrize("fixture", ["jasper_small", "jasper_odd"])
+def test_jasper_separable_golden_fp32_faithful_mode(pkg, golden, fixture):
     """``jasper_small`` -- with a separable (depthwise + pointwise) block as in the shipped model/jasper.yaml -- in precision='tf32': the
-    depthwise convs run as plain fp32 FMAs over fp32 activations (w2l_depthwise_*_f32)"""
+    depthwise convs run as plain fp32 FMAs over fp32 activations (w2l_depthwise_*_f32); ``jasper_odd``: the same mode over internally
+    padded channel counts"""
     from wav2letter_pytorch_b200 import config
     from wav2letter_pytorch_b200.jasper import Jasper
-    g = golden("jasper_small")
+    g = golden(fixture)
     blocks = [dict(b, dropout=0) for b in json.loads(str(g["blocks_json"]))]
     assert any(b.get("separable", True) for b in blocks)
     cfg = config.compose(overrides=["model=jasper", "model.mid_layers=%d" % len(blocks)]).model
     cfg["jasper_blocks"] = config.to_attr(blocks)
     cfg["precision"] = "tf32"
+    if fixture == "jasper_odd":
+        cfg["input_size"] = 0
     torch.manual_seed(2)
     model = Jasper(cfg)
     _load_sd(model, g, "sd0:")
