@@ -167,7 +167,7 @@ def test_graphed_step_draws_fresh_dropout_masks_and_follows_the_scheduler():
             step.close()
 
 
-def test_graphed_step_rejects_other_shapes():
+def test_graphed_step_rejects_other_shapes_and_a_replaced_optimizer_state():
     _need_cuda()
     from wav2letter_pytorch_b200.graph_step import GraphedTrainStep
     b = _batches(1)[0]
@@ -178,6 +178,9 @@ def test_graphed_step_rejects_other_shapes():
         with pytest.raises(ValueError):
             step(short)
         float(step(b))                                    # still usable afterwards
+        o.load_state_dict(o.state_dict())                 # the optimizer's moments now live in new tensors: the graph must not go on
+        with pytest.raises(RuntimeError):
+            step(b)
     finally:
         step.close()
 

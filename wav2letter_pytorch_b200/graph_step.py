@@ -155,6 +155,9 @@ class GraphedTrainStep:
         self._replays = -1                               # the optimizer's host-side step counters: the capture itself counted one step
         self.sync_optimizer_state()                      # that never ran
         self._fresh_convs = [c for plan in getattr(self.optimizer, "_plans", {}).values() for c in plan.get("convs", ())]
+        # the graph holds raw pointers into the fused optimizer's plans (moments, pointer tables): keep them alive, and notice when the
+        # optimizer drops them (load_state_dict / add_param_group) -- its state then lives in new tensors the graph knows nothing about
+        self._plans_held = list(getattr(self.optimizer, "_plans", {}).values())
         # Jasper's NaN assertion (jasper.py:474): the captured forward left its device flag here instead of reading it
         self._nan_flag = self.model.__dict__.pop("_nan_flag_graph", None)
         self._nan_pending = []
@@ -164,6 +167,10 @@ class GraphedTrainStep:
         if self._load(batch) != self._metrics_on:
             raise RuntimeError("GraphedTrainStep: this batch's transcripts %s device scoring but the captured step %s it"
                                % (("allow", "lacks") if not self._metrics_on else ("rule out", "contains")))
+        plans = getattr(self.optimizer, "_plans", None)
+        if plans is not None and (len(plans) != len(self._plans_held) or any(a is not b for a, b in zip(plans.values(), self._plans_held))):
+            raise RuntimeError("GraphedTrainStep: the optimizer's state was replaced after the capture (load_state_dict / add_param_group); "
+                               "close() this step and build a new one")
         if self._hyper() != self._key:                   # a scheduler moved the learning rate: by-value operand, capture again
             self._capture()
         self.graph.replay()
